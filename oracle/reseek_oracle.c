@@ -1,0 +1,399 @@
+/* reseek_oracle.c - CPU restatement of the Reseek per-pair search hot path (see reseek_oracle.h).
+ *
+ * TEST INFRASTRUCTURE ONLY: parity checker for the CUDA library; never part of the product path.
+ * Parity status: PINNED against oracle/_ref (the unmodified reference) - tests/test_oracle_vs_reference.py.
+ *
+ * Written from the behaviour described in SURVEY.md Appendix A and the cited reference lines; it is a
+ * restatement (flat arrays, explicit DP matrices), not a copy.  Build: -O2 -ffp-contract=off, no fast-math.
+ */
+#include "reseek_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../reseek_b200/csrc/score_tables_data.inc"
+
+/* xdpmem.h:6 - a finite "minus infinity" */
+#define ORC_NEG_INF (-9e9f)
+
+int orc_feat_alpha(int f) { return rsk_tbl_feat_alpha[f]; }
+
+int orc_feat_offset(int f)
+{
+	int off = 0;
+	for (int k = 0; k < f; ++k)
+		off += rsk_tbl_feat_alpha[k] * rsk_tbl_feat_alpha[k];
+	return off;
+}
+
+const float *orc_bgfreq(int f)
+{
+	int off = 0;
+	for (int k = 0; k < f; ++k)
+		off += rsk_tbl_feat_alpha[k];
+	return rsk_tbl_bgfreq + off;
+}
+
+const signed char *orc_mu_i8(void) { return rsk_tbl_mu_i8; }
+const signed char *orc_mu_kmer_i8(void) { return rsk_tbl_mu_kmer_i8; }
+const float *orc_mu_f32(void) { return rsk_tbl_mu_f32; }
+
+/* namedparams.cpp:32-53 SetDefaults, dssparams.cpp:44-111 SetDSSParams, dssparams.cpp:344-364 ApplyWeights */
+int orc_params_preset(orc_params *p, int mode)
+{
+	memset(p, 0, sizeof(*p));
+	p->gap_open = rsk_tbl_gap_open;
+	p->gap_ext = rsk_tbl_gap_ext;
+	p->min_fwd_score = 7.0f;
+	p->mu_gap_open = 2;
+	p->mu_gap_ext = 1;
+	switch (mode) {
+	case ORC_MODE_FAST:
+		p->omega = 22; p->omega_fwd = 50; p->mkfl = 500;
+		p->mkf_x1 = 8; p->mkf_x2 = 8; p->mkf_min_hsp_score = 50; p->mkf_min_mega_hsp_score = -4;
+		break;
+	case ORC_MODE_SENSITIVE:
+		p->omega = 12; p->omega_fwd = 20; p->mkfl = 600;
+		p->mkf_x1 = 8; p->mkf_x2 = 8; p->mkf_min_hsp_score = 50; p->mkf_min_mega_hsp_score = -4;
+		break;
+	case ORC_MODE_VERYSENSITIVE:
+		p->omega = 0; p->omega_fwd = 0; p->mkfl = 99999;
+		p->mkf_x1 = 99999; p->mkf_x2 = 99999; p->mkf_min_hsp_score = 0; p->mkf_min_mega_hsp_score = -99999;
+		p->min_fwd_score = 0;
+		break;
+	default:
+		return -1;
+	}
+	int off = 0;
+	for (int f = 0; f < ORC_NFEAT; ++f) {
+		const float w = rsk_tbl_feat_weight[f];
+		const int n = rsk_tbl_feat_alpha[f] * rsk_tbl_feat_alpha[f];
+		p->weights[f] = w;
+		for (int k = 0; k < n; ++k)
+			p->tables[off + k] = w * rsk_tbl_logodds[off + k]; /* fp32 multiply */
+		off += n;
+	}
+	return 0;
+}
+
+float orc_cell_score(const orc_params *p, const uint8_t *profA, uint32_t LA, uint32_t i,
+		const uint8_t *profB, uint32_t LB, uint32_t j)
+{
+	float s = 0;
+	int off = 0;
+	for (int f = 0; f < ORC_NFEAT; ++f) {
+		const int n = rsk_tbl_feat_alpha[f];
+		const float t = p->tables[off + profA[(size_t)f * LA + i] * n + profB[(size_t)f * LB + j]];
+		s = (f == 0) ? t : s + t; /* feature 0 assigns, the rest accumulate: dssaligner.cpp:557-595 */
+		off += n * n;
+	}
+	return s;
+}
+
+/* trace codes per cell: 2 bits = where the match state came from, +4 = D opened from M, +8 = I opened from M */
+enum { SRC_M = 0, SRC_D = 1, SRC_I = 2, SRC_START = 3, BIT_MD = 4, BIT_MI = 8 };
+
+/* The recurrence of sw.cpp:119-197 on full matrices instead of rolling rows; scorefn supplies S[i][j]. */
+typedef float (*cellfn)(const void *ctx, uint32_t i, uint32_t j);
+
+static float sw_core(cellfn fn, const void *ctx, uint32_t LA, uint32_t LB, float open, float ext,
+		uint32_t *lo_a, uint32_t *lo_b, char *path, uint32_t *path_len)
+{
+	*path_len = 0;
+	if (path)
+		path[0] = 0;
+	*lo_a = UINT32_MAX;
+	*lo_b = UINT32_MAX;
+	if (LA == 0 || LB == 0)
+		return 0.0f;
+	float *Mprev = (float *)malloc(sizeof(float) * (LB + 1)); /* M[i][0..LB]: M[i][j] = match score ending at (i-1,j-1) */
+	float *Mcur = (float *)malloc(sizeof(float) * (LB + 1));
+	float *D = (float *)malloc(sizeof(float) * LB);           /* D[i][j] for the current i */
+	uint8_t *tb = (uint8_t *)malloc((size_t)LA * LB);
+	for (uint32_t j = 0; j <= LB; ++j)
+		Mprev[j] = ORC_NEG_INF;
+	Mprev[0] = 0.0f; /* sw.cpp:116: M0 = 0 for cell (0,0) only */
+	for (uint32_t j = 0; j < LB; ++j)
+		D[j] = ORC_NEG_INF;
+	float best = 0.0f;
+	uint32_t bi = UINT32_MAX, bj = UINT32_MAX;
+	for (uint32_t i = 0; i < LA; ++i) {
+		float I = ORC_NEG_INF; /* I[i][0] */
+		Mcur[0] = ORC_NEG_INF; /* sw.cpp:196: M0 = -inf at the start of rows >= 1 */
+		for (uint32_t j = 0; j < LB; ++j) {
+			const float m = Mprev[j];
+			uint8_t t = SRC_M;
+			float x = m;
+			if (D[j] > x) { x = D[j]; t = SRC_D; }
+			if (I > x) { x = I; t = SRC_I; }
+			if (0.0f >= x) { x = 0.0f; t = SRC_START; }
+			x += fn(ctx, i, j);
+			if (x > best) { best = x; bi = i; bj = j; } /* strict >, row-major first max */
+			Mcur[j + 1] = x;
+			const float mo = m + open;
+			float d = D[j] + ext;
+			if (mo >= d) { d = mo; t |= BIT_MD; }
+			D[j] = d; /* D[i+1][j] */
+			float ins = I + ext;
+			if (mo >= ins) { ins = mo; t |= BIT_MI; }
+			I = ins; /* I[i][j+1] */
+			tb[(size_t)i * LB + j] = t;
+		}
+		float *tmp = Mprev; Mprev = Mcur; Mcur = tmp;
+	}
+	if (best == 0.0f) {
+		free(Mprev); free(Mcur); free(D); free(tb);
+		return 0.0f;
+	}
+	/* traceback, sw.cpp:8-77 (1-based i,j; state M first) */
+	uint32_t i = bi + 1, j = bj + 1, n = 0;
+	char state = 'M';
+	char *rev = (char *)malloc((size_t)LA + LB + 2);
+	for (;;) {
+		rev[n++] = state;
+		if (state == 'M') {
+			const uint8_t t = tb[(size_t)(i - 1) * LB + (j - 1)];
+			const int src = t & 3;
+			--i; --j;
+			if (src == SRC_D) state = 'D';
+			else if (src == SRC_I) state = 'I';
+			else if (src == SRC_START) break;
+		} else if (state == 'D') {
+			const uint8_t t = tb[(size_t)(i - 1) * LB + j];
+			--i;
+			state = (t & BIT_MD) ? 'M' : 'D';
+		} else {
+			const uint8_t t = tb[(size_t)i * LB + (j - 1)];
+			--j;
+			state = (t & BIT_MI) ? 'M' : 'I';
+		}
+	}
+	*lo_a = i; /* = Besti+1-Leni */
+	*lo_b = j;
+	*path_len = n;
+	if (path) {
+		for (uint32_t k = 0; k < n; ++k)
+			path[k] = rev[n - 1 - k];
+		path[n] = 0;
+	}
+	free(rev); free(Mprev); free(Mcur); free(D); free(tb);
+	return best;
+}
+
+typedef struct { const orc_params *p; const uint8_t *a, *b; uint32_t LA, LB; } prof_ctx;
+static float prof_cell(const void *c, uint32_t i, uint32_t j)
+{
+	const prof_ctx *x = (const prof_ctx *)c;
+	return orc_cell_score(x->p, x->a, x->LA, i, x->b, x->LB, j);
+}
+
+typedef struct { const float *S; uint32_t LB; } mx_ctx;
+static float mx_cell(const void *c, uint32_t i, uint32_t j)
+{
+	const mx_ctx *x = (const mx_ctx *)c;
+	return x->S[(size_t)i * x->LB + j];
+}
+
+float orc_sw_align(const orc_params *p, const uint8_t *profA, uint32_t LA, const uint8_t *profB, uint32_t LB,
+		uint32_t *lo_a, uint32_t *lo_b, char *path, uint32_t *path_len)
+{
+	prof_ctx c = {p, profA, profB, LA, LB};
+	return sw_core(prof_cell, &c, LA, LB, p->gap_open, p->gap_ext, lo_a, lo_b, path, path_len);
+}
+
+float orc_swfast_matrix(const float *S, uint32_t LA, uint32_t LB, float open, float ext,
+		uint32_t *lo_a, uint32_t *lo_b, char *path, uint32_t *path_len)
+{
+	mx_ctx c = {S, LB};
+	return sw_core(mx_cell, &c, LA, LB, open, ext, lo_a, lo_b, path, path_len);
+}
+
+/* Scalar Gotoh, every value floored at 0 (the int8 lanes are biased by -128 and saturate downwards:
+ * parasail.cpp:580-583, 671-690).  E/F are derived from H (not from the other gap state). */
+int orc_mu_sw_score(const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB, int open, int ext, int *saturated)
+{
+	int best = 0;
+	if (saturated)
+		*saturated = 0;
+	if (LA == 0 || LB == 0)
+		return 0;
+	int *H = (int *)calloc(LA + 1, sizeof(int)); /* H[i] for the previous column, index i+1 */
+	int *E = (int *)calloc(LA + 1, sizeof(int)); /* gap state running along b for each query row */
+	for (uint32_t j = 0; j < LB; ++j) {
+		const signed char *row = rsk_tbl_mu_i8 + 36 * b[j];
+		int diag = 0, F = 0;
+		for (uint32_t i = 0; i < LA; ++i) {
+			int h = diag + row[a[i]];
+			if (h < 0) h = 0;
+			if (E[i] > h) h = E[i];
+			if (F > h) h = F;
+			diag = H[i + 1];
+			H[i + 1] = h;
+			if (h > best) best = h;
+			int ho = h - open; if (ho < 0) ho = 0;
+			int e = E[i] - ext; if (e < 0) e = 0;
+			E[i] = e > ho ? e : ho;
+			int f = F - ext; if (f < 0) f = 0;
+			F = f > ho ? f : ho;
+		}
+	}
+	free(H); free(E);
+	if (saturated)
+		*saturated = best > 250; /* maxp = 127-(4+1) biased: parasail.cpp:585, 728-733 */
+	return best;
+}
+
+float orc_mu_filter_score(const orc_params *p, const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB,
+		int *fwd_out, int *rev_out)
+{
+	int sat = 0;
+	int fwd = orc_mu_sw_score(a, LA, b, LB, p->mu_gap_open, p->mu_gap_ext, &sat);
+	if (sat)
+		fwd = 777; /* parasail_mu.cpp:133-137 */
+	if (fwd_out) *fwd_out = fwd;
+	if (rev_out) *rev_out = 0;
+	if ((float)fwd < p->omega_fwd)
+		return 0; /* :139-144 */
+	uint8_t *ar = (uint8_t *)malloc(LA ? LA : 1);
+	for (uint32_t i = 0; i < LA; ++i)
+		ar[i] = a[LA - 1 - i]; /* parasail_mu.cpp:174-177 */
+	int rev = orc_mu_sw_score(ar, LA, b, LB, p->mu_gap_open, p->mu_gap_ext, &sat);
+	free(ar);
+	if (sat)
+		rev = 255; /* score read before the 777 assignment (:149-155); saturated result->score = 127+128 */
+	if (rev_out) *rev_out = rev;
+	return (float)fwd - (float)rev;
+}
+
+static float dist2(const orc_chain *c, uint32_t p1, uint32_t p2)
+{
+	/* pdbchain.cpp:320-336 */
+	const float dx = c->x[p1] - c->x[p2];
+	const float dy = c->y[p1] - c->y[p2];
+	const float dz = c->z[p1] - c->z[p2];
+	return dx * dx + dy * dy + dz * dz;
+}
+
+float orc_lddt(const orc_chain *A, const orc_chain *B, const uint32_t *posA, const uint32_t *posB, uint32_t n)
+{
+	static const float R0sq = 15.0f * 15.0f;
+	static const float thr[4] = {0.5f, 1.0f, 2.0f, 4.0f};
+	if (n == 0)
+		return 0;
+	uint32_t *cons = (uint32_t *)calloc(n, sizeof(uint32_t));
+	uint32_t *pres = (uint32_t *)calloc(n, sizeof(uint32_t));
+	for (uint32_t ci = 0; ci < n; ++ci) {
+		for (uint32_t cj = ci + 1; cj < n; ++cj) {
+			const float d1s = dist2(A, posA[ci], posA[cj]);
+			const float d2s = dist2(B, posB[ci], posB[cj]);
+			if (d1s > R0sq && d2s > R0sq)
+				continue;
+			const float d1 = sqrtf(d1s), d2 = sqrtf(d2s);
+			const float diff = fabsf(d1 - d2);
+			for (int k = 0; k < 4; ++k)
+				if (diff <= thr[k]) { pres[ci]++; pres[cj]++; }
+			cons[ci] += 4;
+			cons[cj] += 4;
+		}
+	}
+	float total = 0;
+	for (uint32_t c = 0; c < n; ++c) {
+		float score = 0;
+		if (cons[c] > 0)
+			score = (float)pres[c] / (float)cons[c];
+		total += score;
+	}
+	free(cons); free(pres);
+	return total / (float)n;
+}
+
+double orc_pvalue(double ts)
+{
+	const double log10p = (ts < 0.11) ? (-80.0 * ts + -0.58) : (-52.0 * ts + -3.7);
+	double P = pow(10, log10p);
+	if (P > 1) P = 1;
+	return P;
+}
+
+double orc_evalue(double ts) { return orc_pvalue(ts) * 8340; /* statsig.h:3 */ }
+
+double orc_qual(double ts)
+{
+	const double logE = 5.0 + -40.0 * ts;
+	if (logE < -20)
+		return 1;
+	const double x = pow(10, logE / 10);
+	return 1 / (1 + x / 2);
+}
+
+void orc_calc_evalue(const orc_params *p, const orc_chain *A, const orc_chain *B, const char *path, orc_result *r)
+{
+	if (r->score < p->min_fwd_score)
+		return; /* dssaligner.cpp:861-862: everything stays at its ClearAlign value */
+	const uint32_t n = r->path_len;
+	uint32_t M = 0, D = 0, I = 0;
+	uint32_t *pa = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+	uint32_t *pb = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+	uint32_t ia = r->lo_a, ib = r->lo_b;
+	for (uint32_t k = 0; k < n; ++k) {
+		if (path[k] == 'M') { pa[M] = ia++; pb[M] = ib++; ++M; }
+		else if (path[k] == 'D') { ++ia; ++D; }
+		else { ++ib; ++I; }
+	}
+	r->hi_a = r->lo_a + M + D - 1;
+	r->hi_b = r->lo_b + M + I - 1;
+	r->ids = M;
+	r->gaps = D + I;
+	const float lddt = orc_lddt(A, B, pa, pb, M);
+	free(pa); free(pb);
+	float rev = 0;
+	if (A->selfrev != FLT_MAX && B->selfrev != FLT_MAX)
+		rev = (A->selfrev + B->selfrev) / 2;
+	const float L = (float)(A->L + B->L) / 2;
+	float ts = 0.13f * lddt;
+	ts += (1.7f * r->score - 2.0f * rev) / (L + 250.0f);
+	r->lddt = lddt;
+	r->ts = ts;
+	r->pvalue = (float)orc_pvalue(ts);
+	r->qual = (float)orc_qual(ts);
+	r->evalue = (float)orc_evalue(ts);
+}
+
+static void clear_result(orc_result *r)
+{
+	/* dssaligner.cpp:906-927 ClearAlign */
+	memset(r, 0, sizeof(*r));
+	r->lo_a = r->lo_b = r->hi_a = r->hi_b = r->ids = r->gaps = UINT32_MAX;
+	r->pvalue = r->evalue = FLT_MAX;
+	r->qual = FLT_MAX;
+	r->ts = -FLT_MAX;
+	r->lddt = 0;
+}
+
+void orc_align_pair(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path)
+{
+	clear_result(r);
+	if (path)
+		path[0] = 0;
+	if (p->omega > 0 && A->mu && B->mu) {
+		r->mu_score = orc_mu_filter_score(p, A->mu, A->L, B->mu, B->L, &r->mu_fwd, &r->mu_rev);
+		if (r->mu_score < p->omega) {
+			r->filtered = 1;
+			return;
+		}
+	}
+	char *tmp = path ? path : (char *)malloc((size_t)A->L + B->L + 2);
+	r->score = orc_sw_align(p, A->prof, A->L, B->prof, B->L, &r->lo_a, &r->lo_b, tmp, &r->path_len);
+	orc_calc_evalue(p, A, B, tmp, r);
+	if (!path)
+		free(tmp);
+}
+
+void orc_align_pairs(const orc_params *p, const orc_chain *chainsA, const orc_chain *chainsB,
+		const uint32_t *ia, const uint32_t *ib, size_t npairs, orc_result *out)
+{
+	for (size_t k = 0; k < npairs; ++k)
+		orc_align_pair(p, &chainsA[ia[k]], &chainsB[ib[k]], &out[k], NULL);
+}

@@ -1,0 +1,126 @@
+/* reseek_oracle.h - CPU restatement of the Reseek per-pair search hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is the parity checker for the CUDA library in reseek_b200/csrc.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product (libreseek_b200.so) never links, loads or calls anything in oracle/.
+ *
+ * Parity status: PINNED.  Every function below is checked in tests/test_oracle_vs_reference.py against
+ * the unmodified reference compiled from /root/reference/src (oracle/_ref/libreseek_ref.so, strict IEEE
+ * flags, recipe in oracle/Makefile) and against the committed fixtures in tests/golden/ that the same
+ * reference build produced (tools/make_golden.py).
+ *
+ * Each function cites the reference file:line (under /root/reference/src) whose behaviour it restates.
+ * Plain C11, compile with -O2 -ffp-contract=off (no -ffast-math): float results are bit-exact targets.
+ */
+#ifndef RESEEK_ORACLE_H
+#define RESEEK_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_NFEAT 8
+#define ORC_TABLE_FLOATS 2192 /* 20*20 + 7*16*16 */
+#define ORC_MU_ALPHA 36
+
+/* Mirror of the DSSParams scalars the hot path reads (dssparams.h:29-68). */
+typedef struct orc_params {
+	float gap_open;   /* <= 0, namedparams.cpp:45 */
+	float gap_ext;    /* <= 0, namedparams.cpp:46 */
+	float min_fwd_score; /* dssparams.cpp:80, namedparams.cpp:48 */
+	float omega;      /* Mu filter threshold, dssparams.cpp:52-81 */
+	float omega_fwd;
+	int mu_gap_open;  /* dssparams.h:45 */
+	int mu_gap_ext;   /* dssparams.h:46 */
+	uint32_t mkfl;    /* MKF length threshold */
+	int mkf_x1, mkf_x2, mkf_min_hsp_score;
+	float mkf_min_mega_hsp_score;
+	float weights[ORC_NFEAT];
+	/* weighted tables: feature f at offset orc_feat_offset(f), alpha x alpha row-major (dssparams.cpp:344-364) */
+	float tables[ORC_TABLE_FLOATS];
+} orc_params;
+
+enum { ORC_MODE_FAST = 1, ORC_MODE_SENSITIVE = 2, ORC_MODE_VERYSENSITIVE = 3 };
+
+/* dssparams.cpp:44-111 (SetDSSParams presets) + namedparams.cpp:32-53 (SetDefaults) + ApplyWeights */
+int orc_params_preset(orc_params *p, int mode);
+int orc_feat_offset(int f);
+int orc_feat_alpha(int f);
+/* raw data accessors (trained parameters; used by the synthetic-data generator) */
+const float *orc_bgfreq(int f); /* background letter frequencies, trained_features.cpp X_f_i */
+const signed char *orc_mu_i8(void);      /* IntScoreMx_Mu mumx_data.cpp:42 */
+const signed char *orc_mu_kmer_i8(void); /* Mu_S_ij_i8 mumx_data.cpp:81 */
+const float *orc_mu_f32(void);           /* ScoreMx_Mu mumx_data.cpp:3 */
+
+/* One chain as the aligner sees it (dssaligner.h:109-119 SetQuery/SetTarget arguments). */
+typedef struct orc_chain {
+	uint32_t L;
+	const uint8_t *prof; /* [ORC_NFEAT][L] feature letters (dss.cpp:716 GetProfile) */
+	const uint8_t *mu;   /* [L] Mu letters 0..35, may be NULL (dss.cpp:700) */
+	const float *x, *y, *z; /* [L] C-alpha coordinates (pdbchain.h:13-17) */
+	float selfrev;       /* self-reverse score; FLT_MAX = unset (alignpair.cpp:7-25) */
+} orc_chain;
+
+/* Result of one pair; mirrors the DSSAligner public members (dssaligner.h:46-72). */
+typedef struct orc_result {
+	float score;          /* m_AlnFwdScore */
+	uint32_t lo_a, lo_b;  /* m_LoA, m_LoB (UINT32_MAX if no alignment) */
+	uint32_t hi_a, hi_b;  /* m_HiA, m_HiB */
+	uint32_t ids, gaps;   /* M count, D+I count */
+	float lddt;
+	float ts;             /* m_NewTestStatisticA */
+	float pvalue, evalue, qual; /* (float) casts as in dssaligner.cpp:891-900; FLT_MAX if unset */
+	float mu_score;       /* Mu filter score fwd-rev (0 if not run) */
+	int32_t mu_fwd, mu_rev;
+	int32_t filtered;     /* 1 = rejected by the Mu filter (no SW run) */
+	uint32_t path_len;    /* 0 = no alignment */
+} orc_result;
+
+/* sw.cpp:79-212 SWFast + sw.cpp:8-77 TraceBackBitSW over the on-the-fly 8-feature score
+ * (dssaligner.cpp:529-596 SetSMx_NoRev summation order).  path must hold LA+LB+1 bytes; returns score. */
+float orc_sw_align(const orc_params *p, const uint8_t *profA, uint32_t LA, const uint8_t *profB, uint32_t LB,
+		uint32_t *lo_a, uint32_t *lo_b, char *path, uint32_t *path_len);
+
+/* same DP over an explicit LA x LB float score matrix (row-major) - sw.cpp:79-212 verbatim semantics */
+float orc_swfast_matrix(const float *S, uint32_t LA, uint32_t LB, float open, float ext,
+		uint32_t *lo_a, uint32_t *lo_b, char *path, uint32_t *path_len);
+
+/* dssaligner.cpp:557-595: S[i][j] in fp32, feature 0 first then += features 1..7 */
+float orc_cell_score(const orc_params *p, const uint8_t *profA, uint32_t LA, uint32_t i,
+		const uint8_t *profB, uint32_t LB, uint32_t j);
+
+/* Score-only local affine SW on Mu letters; parasail.cpp:515-797 restated as scalar Gotoh with all values
+ * floored at 0.  Returns best H; *saturated = (best > 250) (parasail.cpp:585,728-733). */
+int orc_mu_sw_score(const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB, int open, int ext, int *saturated);
+
+/* parasail_mu.cpp:120-161 AlignMuQP_Para: fwd (777 when saturated), early 0 if fwd < omega_fwd,
+ * rev on reversed A (255 when saturated), score = fwd - rev. */
+float orc_mu_filter_score(const orc_params *p, const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB,
+		int *fwd, int *rev);
+
+/* lddt.cpp:63-124 GetLDDT_mu_fast over aligned column pairs */
+float orc_lddt(const orc_chain *A, const orc_chain *B, const uint32_t *posA, const uint32_t *posB, uint32_t n);
+
+/* statsig.cpp:27-50, statsig.h:8-23 */
+double orc_pvalue(double ts);
+double orc_evalue(double ts);
+double orc_qual(double ts);
+
+/* dssaligner.cpp:852-904 CalcEvalue (+GetPathCounts, GetPosABs :1282, GetLDDT :1313) given score/lo/path in r */
+void orc_calc_evalue(const orc_params *p, const orc_chain *A, const orc_chain *B, const char *path, orc_result *r);
+
+/* dssaligner.cpp:793-831 AlignQueryTarget for pairs below the MKF length threshold:
+ * ClearAlign -> (omega>0 && mu present: MuFilter :619) -> Align_NoAccel :929.  path: LA+LB+1 bytes. */
+void orc_align_pair(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path);
+
+/* Batch helpers for the CPU baseline timing (scalar port, one thread). */
+void orc_align_pairs(const orc_params *p, const orc_chain *chainsA, const orc_chain *chainsB,
+		const uint32_t *ia, const uint32_t *ib, size_t npairs, orc_result *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
