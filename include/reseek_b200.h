@@ -1,0 +1,193 @@
+/* reseek_b200.h - C ABI of the B200-native Reseek search hot path (libreseek_b200.so).
+ *
+ * The reference (rcedgar/reseek, C++) has no FFI; its boundary is the class surface its search drivers use:
+ *   DSSAligner::SetParams/SetQuery/SetTarget/AlignQueryTarget/AlignBags + result members  dssaligner.h:106-223, :46-72
+ *   DBSearcher::LoadDB/Setup/RunQuery/RunSelf/OnAln/Reject                                 dbsearcher.h:83-104
+ *   MuPreFilter / PostMuFilter free functions                                              search.cpp:9-18
+ * Each entry point below names the reference interface it replaces.  The C++ look-alikes that sit on top of
+ * this ABI (same class and method names) live in reseek_b200/csrc/host/; INTEGRATION.md shows the binding a
+ * reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success or a
+ * negative rsk_status, with a message available from rsk_last_error() (the reference's Die() -> exit(1),
+ * myutils.cpp:785, becomes an error code; the C++ shim turns it back into Die).  There is NO CPU fallback:
+ * if no CUDA device / sm_100 kernel image is available the call fails with RSK_ERR_CUDA.
+ * All "host" pointers are ordinary (preferably pinned) host memory; "dev" pointers are device memory on the
+ * context's GPU.  A context is bound to one GPU and one stream and must not be shared between threads
+ * (same rule as one DSSAligner per thread, dbsearcher.cpp:98-106).
+ */
+#ifndef RESEEK_B200_H
+#define RESEEK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSK_NFEAT 8            /* AA, NENDist, Conf, NENConf, RENDist, DstNxtHlx, StrandDens, NormDens (namedparams.cpp:36-43) */
+#define RSK_TABLE_FLOATS 2192  /* 20*20 + 7*16*16 weighted log-odds entries */
+#define RSK_NLETTERS 132       /* 20 + 7*16: one "row table" entry per (feature, letter) */
+#define RSK_MU_ALPHA 36
+
+typedef enum rsk_status {
+	RSK_OK = 0,
+	RSK_ERR_ARG = -1,     /* bad argument (the reference would asserta/Die) */
+	RSK_ERR_CUDA = -2,    /* CUDA runtime error, no device, or no sm_100a kernel image */
+	RSK_ERR_NOMEM = -3,
+	RSK_ERR_LIMIT = -4    /* input exceeds a documented limit (e.g. chain length) */
+} rsk_status;
+
+enum { RSK_MODE_FAST = 1, RSK_MODE_SENSITIVE = 2, RSK_MODE_VERYSENSITIVE = 3 };
+
+/* POD copy of the DSSParams scalars + weighted score tables the hot path reads (dssparams.h:29-68).
+ * Replaces: DSSParams::SetDSSParams (dssparams.cpp:44-111), SetDefaults (namedparams.cpp:32-53),
+ * ApplyWeights (dssparams.cpp:344-364). */
+typedef struct rsk_params {
+	float gap_open;              /* <= 0 */
+	float gap_ext;               /* <= 0 */
+	float min_fwd_score;         /* CalcEvalue skipped below this (dssaligner.cpp:861) */
+	float omega;                 /* Mu filter threshold; <= 0 disables the filter */
+	float omega_fwd;
+	int32_t mu_gap_open;         /* int8 Mu SW penalties (dssparams.h:45-46) */
+	int32_t mu_gap_ext;
+	uint32_t mkfl;               /* chains >= mkfl take the k-mer/x-drop path (dssaligner.cpp:715-732) */
+	int32_t mkf_x1, mkf_x2, mkf_min_hsp_score;
+	float mkf_min_mega_hsp_score;
+	double max_evalue;           /* DBSearcher::m_MaxEvalue (dbsearcher.cpp:75-83) */
+	float weights[RSK_NFEAT];
+	float tables[RSK_TABLE_FLOATS]; /* weighted: float(w) * float(logodds), feature after feature, row-major */
+} rsk_params;
+
+typedef struct rsk_ctx rsk_ctx;           /* one GPU + one stream + scratch; the "DSSAligner pool" of a DBSearcher */
+typedef struct rsk_chainset rsk_chainset; /* device-resident chains: DBSearcher::m_DBChains/m_DBProfiles/... (dbsearcher.h:26-33) */
+typedef struct rsk_results rsk_results;   /* hits of one search call */
+
+/* Host-side structure-of-arrays view of a set of chains.  Layout mirrors what the reference holds per chain:
+ * profile = vector<vector<byte>>[feature][pos] (dss.cpp:716), Mu letters vector<byte> (dss.cpp:700),
+ * coordinates PDBChain::m_Xs/m_Ys/m_Zs (pdbchain.h:13-17), self-reverse score (alignpair.cpp:7-25). */
+typedef struct rsk_chains_host {
+	uint32_t n;            /* number of chains */
+	uint64_t total;        /* sum of len[] */
+	const uint32_t *len;   /* [n] chain lengths (>= 1) */
+	const uint8_t *prof;   /* [RSK_NFEAT][total]: plane-major, chains concatenated in order */
+	const uint8_t *mu;     /* [total] Mu letters 0..35, or NULL (then no Mu filter for these chains) */
+	const float *xyz;      /* [3][total] x plane, y plane, z plane */
+	const float *selfrev;  /* [n] self-reverse scores, or NULL (= FLT_MAX "unset", dssaligner.cpp:876-877) */
+} rsk_chains_host;
+
+/* One alignment, fixed width; mirrors the DSSAligner result members (dssaligner.h:46-72).
+ * a/b index the A ("query" slot, rows) and B ("target" slot, columns) chain sets of the call. */
+typedef struct rsk_hit {
+	uint32_t a, b;
+	float score;            /* m_AlnFwdScore (fp32 bits identical to the reference) */
+	uint32_t lo_a, lo_b;    /* m_LoA, m_LoB (0-based) */
+	uint32_t hi_a, hi_b;    /* m_HiA, m_HiB; UINT32_MAX when CalcEvalue was skipped */
+	uint32_t ids, gaps;     /* m_Ids (M columns), m_Gaps (D+I columns) */
+	float lddt;
+	float ts;               /* m_NewTestStatisticA; -FLT_MAX when unset */
+	float pvalue, evalue, qual; /* (float) of the double formulas, statsig.cpp:27-50; FLT_MAX when unset */
+	float mu_score;         /* Mu filter score fwd - rev when the filter ran, else 0 */
+	int32_t mu_fwd, mu_rev;
+	uint32_t flags;         /* RSK_HIT_* */
+	uint32_t path_len;      /* number of path columns (0 = no alignment) */
+	uint64_t path_off;      /* offset of the path in the results' path pool */
+} rsk_hit;
+
+enum {
+	RSK_HIT_MU_REJECTED = 1u, /* dropped by the Mu filter: no SW was run */
+	RSK_HIT_HAS_EVALUE = 2u,  /* CalcEvalue ran (score >= min_fwd_score) */
+	RSK_HIT_REPORTED = 4u     /* passes DBSearcher::Reject (E <= max_evalue) */
+};
+
+/* which pairs come back from a search call */
+enum {
+	RSK_KEEP_HITS = 0,   /* only pairs the reference would emit: non-empty path and !Reject (runquery.cpp:72-73) */
+	RSK_KEEP_ALL = 1     /* one record per scheduled pair, in schedule order (parity tests, OnAln subclasses) */
+};
+
+typedef struct rsk_search_opts {
+	int32_t keep;           /* RSK_KEEP_* */
+	int32_t want_paths;     /* 0: records only; 1: also the M/D/I path strings */
+	int32_t skip_evalue;    /* 1: stop after SW+traceback (no LDDT/TS) - kernel benchmarking only */
+	int32_t reserved;
+} rsk_search_opts;
+
+/* Work counters of the last search call (DSSAligner::Stats dssaligner.cpp:1088, DBSearcher::RunStats dbsearcher.cpp:29-56) */
+typedef struct rsk_stats {
+	uint64_t pairs;          /* scheduled pairs */
+	uint64_t mu_filter_in;   /* pairs that went through the Mu filter */
+	uint64_t mu_filter_rejected;
+	uint64_t mu_saturated;   /* forward int8 saturations (m_ParasailSaturateCount) */
+	uint64_t sw_pairs;       /* pairs that reached the float SW */
+	uint64_t sw_cells;       /* sum LA*LB over those pairs */
+	uint64_t evalue_pairs;   /* pairs for which LDDT/TS were computed */
+	uint64_t hits;           /* pairs passing Reject */
+	uint64_t kernel_launches;/* CUDA kernels of this library launched by the call */
+	uint64_t h2d_bytes, d2h_bytes;
+	float sw_kernel_ms;      /* device time of the SW kernel(s) (CUDA events on the context stream) */
+	float mu_kernel_ms;
+	float lddt_kernel_ms;
+	float total_ms;          /* device time of the whole call on the context stream */
+} rsk_stats;
+
+/* ---- library ---- */
+const char *rsk_version(void);
+const char *rsk_last_error(void); /* thread-local message of the last failing call */
+int rsk_device_count(void);       /* CUDA devices visible; 0 when there is none (no fallback exists) */
+
+/* ---- parameters (DSSParams) ---- */
+int rsk_params_preset(rsk_params *p, int mode);
+/* raw trained data, for tools and tests */
+int rsk_feature_alpha(int f);
+int rsk_feature_offset(int f);            /* offset of feature f in tables[] */
+const float *rsk_feature_bgfreq(int f);   /* background letter frequencies (trained_features.cpp X_f_i) */
+const int8_t *rsk_mu_matrix_i8(void);     /* IntScoreMx_Mu [36][36] (mumx_data.cpp:42) */
+const int8_t *rsk_mu_kmer_matrix_i8(void);/* Mu_S_ij_i8 [36][36] (mumx_data.cpp:81) */
+const float *rsk_mu_matrix_f32(void);     /* ScoreMx_Mu [36][36] (mumx_data.cpp:3) */
+
+/* ---- context: DBSearcher::Setup (dbsearcher.cpp:73) + DSSAligner::SetParams (dssaligner.h:106) ---- */
+int rsk_ctx_create(int device, const rsk_params *params, void *cuda_stream /* cudaStream_t or NULL */, rsk_ctx **out);
+int rsk_ctx_set_params(rsk_ctx *ctx, const rsk_params *params);
+void rsk_ctx_destroy(rsk_ctx *ctx);
+int rsk_ctx_stats(const rsk_ctx *ctx, rsk_stats *out);
+int rsk_ctx_sync(rsk_ctx *ctx);
+
+/* ---- chains: DBSearcher::LoadDB / the per-chain vectors (dbsearcher.cpp:242, dbsearcher.h:26-33) ---- */
+int rsk_chainset_upload(rsk_ctx *ctx, const rsk_chains_host *chains, rsk_chainset **out);
+uint32_t rsk_chainset_count(const rsk_chainset *cs);
+uint64_t rsk_chainset_residues(const rsk_chainset *cs);
+void rsk_chainset_free(rsk_chainset *cs);
+
+/* ---- the per-pair hot loop ----
+ * rsk_search_cross: every chain of A (the streamed "-db" side, DSSAligner query slot) against every chain of
+ *   B (the in-memory side, target slot): DBSearcher::RunQuery / ThreadBodyQuery (runquery.cpp:18-80).
+ * rsk_search_self:  pairs i <= j of one set, A = chain i, B = chain j: DBSearcher::RunSelf (runself.cpp:72-145).
+ * rsk_search_pairs: explicit (ia[k], ib[k]) list: PostMuFilter's per-line AlignBags loop (postmufilter.cpp:185-195),
+ *   -alignpair (alignpair.cpp:107-118) and DSSAligner::AlignQueryTarget itself (batch of one).
+ * Per pair the control flow is DSSAligner::AlignQueryTarget (dssaligner.cpp:793-831). */
+int rsk_search_cross(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, const rsk_search_opts *opts, rsk_results **out);
+int rsk_search_self(rsk_ctx *ctx, const rsk_chainset *S, const rsk_search_opts *opts, rsk_results **out);
+int rsk_search_pairs(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib, const rsk_search_opts *opts, rsk_results **out);
+
+/* Same hot loop with results left on the device (no D2H): used to time the resident-data kernel path. */
+int rsk_search_cross_device(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, const rsk_search_opts *opts);
+
+/* ---- results ---- */
+uint64_t rsk_results_count(const rsk_results *r);
+const rsk_hit *rsk_results_hits(const rsk_results *r);  /* [count], host memory owned by r */
+const char *rsk_results_paths(const rsk_results *r);    /* path pool: 'M','D','I' bytes, hit k at path_off..+path_len */
+uint64_t rsk_results_paths_bytes(const rsk_results *r);
+void rsk_results_free(rsk_results *r);
+
+/* ---- host-side statistics: StatSig (statsig.cpp:27-50, statsig.h:8-23); libm double pow, as the reference ---- */
+double rsk_pvalue(double ts);
+double rsk_evalue(double ts);
+double rsk_qual(double ts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESEEK_B200_H */

@@ -1,0 +1,891 @@
+// rsk_api.cu - C ABI of libreseek_b200: context, device chain store, batched search drivers, results.
+// See include/reseek_b200.h for the reference interfaces each entry point replaces.
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "rsk_internal.cuh"
+#include "score_tables_data.inc"
+
+using namespace rsk;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_err = buf;
+	return code;
+}
+
+#define CK(call)                                                                                     \
+	do {                                                                                             \
+		cudaError_t e_ = (call);                                                                     \
+		if (e_ != cudaSuccess)                                                                       \
+			return fail(RSK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+// ------------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------------
+struct rsk_chainset {
+	rsk_ctx *ctx = nullptr;  // identity only (never dereferenced by rsk_chainset_free: the context may be gone)
+	int device = 0;
+	DevChains d;
+	std::vector<uint32_t> hlen;
+	std::vector<uint64_t> hoff;
+	uint32_t maxlen = 0;
+	bool has_mu = false;
+};
+
+template <typename T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0;  // elements
+	int ensure(size_t n)
+	{
+		if (n <= cap)
+			return 0;
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 16;
+		if (cudaMalloc((void **)&p, want * sizeof(T)) != cudaSuccess) {
+			cudaGetLastError();
+			if (cudaMalloc((void **)&p, n * sizeof(T)) != cudaSuccess)
+				return -1;
+			want = n;
+		}
+		cap = want;
+		return 0;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+template <typename T>
+struct PinBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t n)
+	{
+		if (n <= cap)
+			return 0;
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 16;
+		if (cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess)
+			return -1;
+		cap = want;
+		return 0;
+	}
+	void release()
+	{
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct rsk_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	int num_sms = 0;
+	rsk_params params;
+	float *d_tables = nullptr;
+	uint32_t *d_task_counter = nullptr;
+	unsigned long long *d_pool_cursor = nullptr;
+	cudaEvent_t ev[8] = {};
+	// grow-only scratch
+	DevBuf<uint4> trace;
+	DevBuf<float2> bnd;
+	DevBuf<uint8_t> stage;
+	DevBuf<PairRec> rec;
+	DevBuf<uint8_t> pool;
+	DevBuf<uint32_t> blist, bslot, task_a, task_begin, task_cnt, pair_a, pair_b;
+	PinBuf<PairRec> h_rec;
+	PinBuf<uint8_t> h_pool;
+	PinBuf<uint32_t> h_idx;
+	rsk_stats stats;
+	size_t max_batch_pairs = 2u << 20;
+	size_t scratch_budget = (size_t)24 << 30;
+};
+
+struct rsk_results {
+	std::vector<rsk_hit> hits;
+	std::vector<char> paths;
+};
+
+// ------------------------------------------------------------------------------------------------
+// library / params
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *rsk_version(void) { return "reseek_b200 0.1 (sm_100a)"; }
+extern "C" const char *rsk_last_error(void) { return g_err.c_str(); }
+
+extern "C" int rsk_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" int rsk_feature_alpha(int f) { return (f >= 0 && f < RSK_NFEAT) ? rsk_tbl_feat_alpha[f] : -1; }
+extern "C" int rsk_feature_offset(int f) { return (f >= 0 && f < RSK_NFEAT) ? feat_table_off(f) : -1; }
+extern "C" const float *rsk_feature_bgfreq(int f)
+{
+	if (f < 0 || f >= RSK_NFEAT)
+		return nullptr;
+	int off = 0;
+	for (int k = 0; k < f; ++k)
+		off += rsk_tbl_feat_alpha[k];
+	return rsk_tbl_bgfreq + off;
+}
+extern "C" const int8_t *rsk_mu_matrix_i8(void) { return (const int8_t *)rsk_tbl_mu_i8; }
+extern "C" const int8_t *rsk_mu_kmer_matrix_i8(void) { return (const int8_t *)rsk_tbl_mu_kmer_i8; }
+extern "C" const float *rsk_mu_matrix_f32(void) { return rsk_tbl_mu_f32; }
+
+// DSSParams::SetDefaults (namedparams.cpp:32-53) + SetDSSParams presets (dssparams.cpp:52-81) + ApplyWeights
+extern "C" int rsk_params_preset(rsk_params *p, int mode)
+{
+	if (!p)
+		return fail(RSK_ERR_ARG, "rsk_params_preset: null params");
+	memset(p, 0, sizeof(*p));
+	p->gap_open = rsk_tbl_gap_open;
+	p->gap_ext = rsk_tbl_gap_ext;
+	p->min_fwd_score = 7.0f;
+	p->mu_gap_open = 2;
+	p->mu_gap_ext = 1;
+	p->max_evalue = 10;
+	switch (mode) {
+	case RSK_MODE_FAST:
+		p->omega = 22; p->omega_fwd = 50; p->mkfl = 500;
+		p->mkf_x1 = 8; p->mkf_x2 = 8; p->mkf_min_hsp_score = 50; p->mkf_min_mega_hsp_score = -4;
+		break;
+	case RSK_MODE_SENSITIVE:
+		p->omega = 12; p->omega_fwd = 20; p->mkfl = 600;
+		p->mkf_x1 = 8; p->mkf_x2 = 8; p->mkf_min_hsp_score = 50; p->mkf_min_mega_hsp_score = -4;
+		break;
+	case RSK_MODE_VERYSENSITIVE:
+		p->omega = 0; p->omega_fwd = 0; p->mkfl = 99999;
+		p->mkf_x1 = 99999; p->mkf_x2 = 99999; p->mkf_min_hsp_score = 0; p->mkf_min_mega_hsp_score = -99999;
+		p->min_fwd_score = 0;
+		p->max_evalue = DBL_MAX;  // dbsearcher.cpp:79-80
+		break;
+	default:
+		return fail(RSK_ERR_ARG, "rsk_params_preset: unknown mode %d (the reference dies: 'Must set -fast, -sensitive or -verysensitive')", mode);
+	}
+	for (int f = 0; f < RSK_NFEAT; ++f) {
+		const float w = rsk_tbl_feat_weight[f];
+		p->weights[f] = w;
+		const int off = feat_table_off(f), n = feat_alpha(f) * feat_alpha(f);
+		for (int k = 0; k < n; ++k)
+			p->tables[off + k] = w * rsk_tbl_logodds[off + k];
+	}
+	return RSK_OK;
+}
+
+// statsig.cpp:27-50, statsig.h:8-23
+extern "C" double rsk_pvalue(double ts)
+{
+	const double l = (ts < 0.11) ? (-80.0 * ts + -0.58) : (-52.0 * ts + -3.7);
+	double P = pow(10, l);
+	return P > 1 ? 1 : P;
+}
+extern "C" double rsk_evalue(double ts) { return rsk_pvalue(ts) * 8340; }
+extern "C" double rsk_qual(double ts)
+{
+	const double logE = 5.0 + -40.0 * ts;
+	if (logE < -20)
+		return 1;
+	return 1 / (1 + pow(10, logE / 10) / 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+static int check_params(const rsk_params *p)
+{
+	if (!p)
+		return fail(RSK_ERR_ARG, "null params");
+	if (p->gap_open > 0 || p->gap_ext > 0)
+		return fail(RSK_ERR_ARG, "open=%.3g ext=%.3g, gap penalties must be >= 0", -p->gap_open, -p->gap_ext);  // dssparams.cpp:106-108
+	return RSK_OK;
+}
+
+extern "C" int rsk_ctx_set_params(rsk_ctx *ctx, const rsk_params *params)
+{
+	if (!ctx)
+		return fail(RSK_ERR_ARG, "null context");
+	int rc = check_params(params);
+	if (rc)
+		return rc;
+	ctx->params = *params;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMemcpyAsync(ctx->d_tables, ctx->params.tables, sizeof(float) * RSK_TABLE_FLOATS, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RSK_OK;
+}
+
+extern "C" int rsk_ctx_create(int device, const rsk_params *params, void *cuda_stream, rsk_ctx **out)
+{
+	if (!out)
+		return fail(RSK_ERR_ARG, "rsk_ctx_create: null out");
+	*out = nullptr;
+	int rc = check_params(params);
+	if (rc)
+		return rc;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(RSK_ERR_CUDA, "no CUDA device available: libreseek_b200 has no CPU fallback");
+	}
+	if (device < 0 || device >= ndev)
+		return fail(RSK_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+	CK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		return fail(RSK_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a kernels only", device, prop.major, prop.minor);
+	rsk_ctx *ctx = new rsk_ctx();
+	ctx->device = device;
+	ctx->num_sms = prop.multiProcessorCount;
+	if (cuda_stream) {
+		ctx->stream = (cudaStream_t)cuda_stream;
+	} else {
+		if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+			delete ctx;
+			return fail(RSK_ERR_CUDA, "cudaStreamCreate failed");
+		}
+		ctx->own_stream = true;
+	}
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	if (cudaMalloc((void **)&ctx->d_tables, sizeof(float) * RSK_TABLE_FLOATS) != cudaSuccess ||
+		cudaMalloc((void **)&ctx->d_task_counter, sizeof(uint32_t)) != cudaSuccess ||
+		cudaMalloc((void **)&ctx->d_pool_cursor, sizeof(unsigned long long)) != cudaSuccess) {
+		rsk_ctx_destroy(ctx);
+		return fail(RSK_ERR_NOMEM, "cudaMalloc failed in rsk_ctx_create");
+	}
+	for (auto &e : ctx->ev)
+		cudaEventCreate(&e);
+	if (const char *s = getenv("RSK_BATCH_PAIRS")) {
+		const long long v = atoll(s);
+		if (v > 0)
+			ctx->max_batch_pairs = (size_t)v;
+	}
+	rc = rsk_ctx_set_params(ctx, params);
+	if (rc) {
+		rsk_ctx_destroy(ctx);
+		return rc;
+	}
+	*out = ctx;
+	return RSK_OK;
+}
+
+extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
+{
+	if (!ctx)
+		return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->trace.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
+	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();
+	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
+	ctx->h_rec.release(); ctx->h_pool.release(); ctx->h_idx.release();
+	if (ctx->d_tables) cudaFree(ctx->d_tables);
+	if (ctx->d_task_counter) cudaFree(ctx->d_task_counter);
+	if (ctx->d_pool_cursor) cudaFree(ctx->d_pool_cursor);
+	for (auto &e : ctx->ev)
+		if (e) cudaEventDestroy(e);
+	if (ctx->own_stream && ctx->stream)
+		cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" int rsk_ctx_stats(const rsk_ctx *ctx, rsk_stats *out)
+{
+	if (!ctx || !out)
+		return fail(RSK_ERR_ARG, "rsk_ctx_stats: null argument");
+	*out = ctx->stats;
+	return RSK_OK;
+}
+
+extern "C" int rsk_ctx_sync(rsk_ctx *ctx)
+{
+	if (!ctx)
+		return fail(RSK_ERR_ARG, "null context");
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain sets
+// ------------------------------------------------------------------------------------------------
+extern "C" void rsk_chainset_free(rsk_chainset *cs)
+{
+	if (!cs)
+		return;
+	cudaSetDevice(cs->device);
+	DevChains &d = cs->d;
+	cudaFree(d.len); cudaFree(d.off); cudaFree(d.prof8); cudaFree(d.mu);
+	cudaFree(d.x); cudaFree(d.y); cudaFree(d.z); cudaFree(d.selfrev);
+	delete cs;
+}
+
+extern "C" uint32_t rsk_chainset_count(const rsk_chainset *cs) { return cs ? cs->d.n : 0; }
+extern "C" uint64_t rsk_chainset_residues(const rsk_chainset *cs) { return cs ? cs->d.total : 0; }
+
+extern "C" int rsk_chainset_upload(rsk_ctx *ctx, const rsk_chains_host *h, rsk_chainset **out)
+{
+	if (!ctx || !h || !out)
+		return fail(RSK_ERR_ARG, "rsk_chainset_upload: null argument");
+	*out = nullptr;
+	if (h->n == 0 || !h->len || !h->prof || !h->xyz)
+		return fail(RSK_ERR_ARG, "rsk_chainset_upload: empty chain set or missing len/prof/xyz");
+	CK(cudaSetDevice(ctx->device));
+	rsk_chainset *cs = new rsk_chainset();
+	cs->ctx = ctx;
+	cs->device = ctx->device;
+	cs->hlen.assign(h->len, h->len + h->n);
+	cs->hoff.resize(h->n);
+	uint64_t tot = 0;
+	for (uint32_t i = 0; i < h->n; ++i) {
+		if (h->len[i] == 0) {
+			delete cs;
+			return fail(RSK_ERR_ARG, "chain %u has length 0 (the reference's reader skips such chains, chainreader2.cpp:103-107)", i);
+		}
+		cs->hoff[i] = tot;
+		tot += h->len[i];
+		cs->maxlen = std::max(cs->maxlen, h->len[i]);
+	}
+	if (tot != h->total) {
+		delete cs;
+		return fail(RSK_ERR_ARG, "rsk_chainset_upload: total=%llu but sum(len)=%llu", (unsigned long long)h->total, (unsigned long long)tot);
+	}
+	DevChains &d = cs->d;
+	d.n = h->n;
+	d.total = tot;
+	cs->has_mu = h->mu != nullptr;
+	uint8_t *d_planes = nullptr;
+	bool ok = cudaMalloc((void **)&d.len, sizeof(uint32_t) * d.n) == cudaSuccess &&
+			  cudaMalloc((void **)&d.off, sizeof(uint64_t) * d.n) == cudaSuccess &&
+			  cudaMalloc((void **)&d.prof8, sizeof(uint64_t) * tot) == cudaSuccess &&
+			  cudaMalloc((void **)&d.x, sizeof(float) * tot) == cudaSuccess &&
+			  cudaMalloc((void **)&d.y, sizeof(float) * tot) == cudaSuccess &&
+			  cudaMalloc((void **)&d.z, sizeof(float) * tot) == cudaSuccess &&
+			  cudaMalloc((void **)&d.selfrev, sizeof(float) * d.n) == cudaSuccess &&
+			  cudaMalloc((void **)&d_planes, (size_t)RSK_NFEAT * tot) == cudaSuccess &&
+			  (!h->mu || cudaMalloc((void **)&d.mu, tot) == cudaSuccess);
+	if (!ok) {
+		cudaGetLastError();
+		cudaFree(d_planes);
+		rsk_chainset_free(cs);
+		return fail(RSK_ERR_NOMEM, "rsk_chainset_upload: cudaMalloc failed for %llu residues", (unsigned long long)tot);
+	}
+	cudaStream_t st = ctx->stream;
+	std::vector<float> sr(d.n, FLT_MAX);
+	if (h->selfrev)
+		sr.assign(h->selfrev, h->selfrev + d.n);
+	cudaError_t e = cudaSuccess;
+	auto cp = [&](void *dst, const void *src, size_t bytes) {
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+	};
+	cp(d.len, h->len, sizeof(uint32_t) * d.n);
+	cp(d.off, cs->hoff.data(), sizeof(uint64_t) * d.n);
+	cp(d_planes, h->prof, (size_t)RSK_NFEAT * tot);
+	cp(d.x, h->xyz, sizeof(float) * tot);
+	cp(d.y, h->xyz + tot, sizeof(float) * tot);
+	cp(d.z, h->xyz + 2 * tot, sizeof(float) * tot);
+	cp(d.selfrev, sr.data(), sizeof(float) * d.n);
+	if (h->mu)
+		cp(d.mu, h->mu, tot);
+	int nl = 0;
+	if (e == cudaSuccess) {
+		nl = launch_pack_profiles(d_planes, tot, d.prof8, st);
+		if (nl < 0)
+			e = cudaErrorLaunchFailure;
+	}
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(st);
+	cudaFree(d_planes);
+	if (e != cudaSuccess) {
+		rsk_chainset_free(cs);
+		return fail(RSK_ERR_CUDA, "rsk_chainset_upload: %s", cudaGetErrorString(e));
+	}
+	ctx->stats.h2d_bytes += (uint64_t)tot * (RSK_NFEAT + 12 + (h->mu ? 1 : 0)) + (uint64_t)d.n * 16;
+	ctx->stats.kernel_launches += nl;
+	*out = cs;
+	return RSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search drivers
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Batch {
+	// cross mode: A range [a0,a1) x all B
+	bool cross = true;
+	uint32_t a0 = 0, a1 = 0;
+	// explicit mode: sorted pair range [k0,k1)
+	size_t k0 = 0, k1 = 0;
+	size_t npairs = 0;
+	uint32_t ntasks = 0;
+	uint32_t maxLA = 0, maxLB = 0;
+	uint64_t cells = 0;
+	uint64_t pool_bound = 0;
+};
+
+struct SearchPlan {
+	const rsk_chainset *A = nullptr, *B = nullptr;
+	bool cross = true;
+	// cross: B indices sorted by length
+	std::vector<uint32_t> border;
+	// explicit: pairs sorted by (a, lenB); perm[k] = original pair index
+	std::vector<uint32_t> sa, sb;
+	std::vector<uint64_t> perm;
+	uint64_t npairs = 0;
+};
+
+int ensure_scratch(rsk_ctx *ctx, uint32_t maxLA, uint32_t maxLB, int &grid, uint64_t &trace_stride, uint32_t &bnd_stride,
+		uint32_t &stage_stride)
+{
+	int npass, R;
+	sw_geometry(maxLA, npass, R);
+	// every pair of the batch has npass(LA) <= npass(maxLA) and LBpad <= maxLBpad
+	const uint64_t lbpad = ((uint64_t)maxLB + 3) & ~3ull;
+	trace_stride = (uint64_t)npass * (lbpad / 4) * 32;  // uint4 units
+	bnd_stride = (uint32_t)lbpad + 4;
+	stage_stride = ((maxLA + maxLB + 16) + 15) & ~15u;
+	const uint64_t per_cta = (trace_stride * 16 + (uint64_t)bnd_stride * 8 + stage_stride) * kSwWarps;
+	grid = ctx->num_sms;
+	if (per_cta * (uint64_t)grid > ctx->scratch_budget)
+		grid = (int)std::max<uint64_t>(1, ctx->scratch_budget / per_cta);
+	const size_t warps = (size_t)grid * kSwWarps;
+	if (ctx->trace.ensure(trace_stride * warps) || ctx->bnd.ensure((size_t)bnd_stride * warps) ||
+		ctx->stage.ensure((size_t)stage_stride * warps)) {
+		cudaGetLastError();
+		return fail(RSK_ERR_NOMEM, "SW scratch allocation failed (maxLA=%u maxLB=%u)", maxLA, maxLB);
+	}
+	return RSK_OK;
+}
+
+// Run one batch on the device: SW+traceback, then LDDT/TS.  Records land in ctx->rec[0..npairs).
+int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_search_opts &opts)
+{
+	const rsk_chainset *A = plan.A, *B = plan.B;
+	cudaStream_t st = ctx->stream;
+	int grid;
+	uint64_t trace_stride;
+	uint32_t bnd_stride, stage_stride;
+	int rc = ensure_scratch(ctx, b.maxLA, b.maxLB, grid, trace_stride, bnd_stride, stage_stride);
+	if (rc)
+		return rc;
+	if (ctx->rec.ensure(b.npairs) || ctx->pool.ensure((size_t)b.pool_bound + 64)) {
+		cudaGetLastError();
+		return fail(RSK_ERR_NOMEM, "result buffers: %zu pairs, %llu path bytes", b.npairs, (unsigned long long)b.pool_bound);
+	}
+	CK(cudaMemsetAsync(ctx->rec.p, 0, b.npairs * sizeof(PairRec), st));
+	CK(cudaMemsetAsync(ctx->d_task_counter, 0, sizeof(uint32_t), st));
+	CK(cudaMemsetAsync(ctx->d_pool_cursor, 0, sizeof(unsigned long long), st));
+
+	SwArgs sa;
+	memset(&sa, 0, sizeof(sa));
+	sa.profA = A->d.prof8; sa.offA = A->d.off; sa.lenA = A->d.len;
+	sa.profB = B->d.prof8; sa.offB = B->d.off; sa.lenB = B->d.len;
+	sa.ntasks = b.ntasks;
+	sa.cross = b.cross ? 1 : 0;
+	sa.blist = ctx->blist.p;
+	if (b.cross) {
+		sa.a_begin = b.a0;
+		sa.nB = B->d.n;
+		sa.nseg = (B->d.n + kSwWarps - 1) / kSwWarps;
+	} else {
+		sa.task_a = ctx->task_a.p; sa.task_begin = ctx->task_begin.p; sa.task_cnt = ctx->task_cnt.p;
+		sa.bslot = ctx->bslot.p;
+	}
+	sa.trace = ctx->trace.p; sa.trace_stride = trace_stride;
+	sa.bnd = ctx->bnd.p; sa.bnd_stride = bnd_stride;
+	sa.stage = ctx->stage.p; sa.stage_stride = stage_stride;
+	sa.rec = ctx->rec.p;
+	sa.pool = ctx->pool.p; sa.pool_cursor = ctx->d_pool_cursor;
+	sa.task_counter = ctx->d_task_counter;
+	sa.tables = ctx->d_tables;
+	sa.open = ctx->params.gap_open; sa.ext = ctx->params.gap_ext;
+
+	CK(cudaEventRecord(ctx->ev[0], st));
+	int nl = launch_sw(sa, std::min<int>(grid, (int)b.ntasks), sw_smem_bytes(), st);
+	if (nl < 0)
+		return fail(RSK_ERR_CUDA, "SW kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+	ctx->stats.kernel_launches += nl;
+	CK(cudaEventRecord(ctx->ev[1], st));
+
+	if (!opts.skip_evalue) {
+		LddtArgs la;
+		memset(&la, 0, sizeof(la));
+		la.lenA = A->d.len; la.offA = A->d.off; la.xA = A->d.x; la.yA = A->d.y; la.zA = A->d.z; la.selfrevA = A->d.selfrev;
+		la.lenB = B->d.len; la.offB = B->d.off; la.xB = B->d.x; la.yB = B->d.y; la.zB = B->d.z; la.selfrevB = B->d.selfrev;
+		la.npairs = (uint32_t)b.npairs;
+		la.cross = b.cross ? 1 : 0;
+		la.a_begin = b.a0;
+		la.nB = B->d.n;
+		la.pair_a = ctx->pair_a.p; la.pair_b = ctx->pair_b.p;
+		la.rec = ctx->rec.p;
+		la.pool = ctx->pool.p;
+		la.min_fwd_score = ctx->params.min_fwd_score;
+		la.maxcols = std::max(1u, std::min(b.maxLA, b.maxLB));
+		if ((size_t)la.maxcols * 7 * sizeof(float) > 220 * 1024)
+			return fail(RSK_ERR_LIMIT, "alignment of %u columns exceeds the LDDT kernel's shared-memory limit", la.maxcols);
+		nl = launch_lddt(la, st);
+		if (nl < 0)
+			return fail(RSK_ERR_CUDA, "LDDT kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->stats.kernel_launches += nl;
+	}
+	CK(cudaEventRecord(ctx->ev[2], st));
+	ctx->stats.sw_pairs += b.npairs;
+	ctx->stats.sw_cells += b.cells;
+	return RSK_OK;
+}
+
+int finish_batch_timing(rsk_ctx *ctx)
+{
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+	ctx->stats.sw_kernel_ms += ms;
+	CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+	ctx->stats.lddt_kernel_ms += ms;
+	return RSK_OK;
+}
+
+void fill_hit(const rsk_params &P, const PairRec &r, uint32_t a, uint32_t b, uint64_t pool_base, rsk_hit &h)
+{
+	h.a = a; h.b = b;
+	h.score = r.score;
+	h.lo_a = r.lo_a; h.lo_b = r.lo_b;
+	h.mu_score = 0; h.mu_fwd = r.mu_fwd; h.mu_rev = r.mu_rev;
+	h.flags = r.flags;
+	h.path_len = r.path_len;
+	h.path_off = pool_base + r.path_off;
+	if (r.flags & RSK_HIT_HAS_EVALUE) {
+		h.hi_a = r.hi_a; h.hi_b = r.hi_b; h.ids = r.ids; h.gaps = r.gaps;
+		h.lddt = r.lddt; h.ts = r.ts;
+		h.pvalue = (float)rsk_pvalue(r.ts);   // dssaligner.cpp:891-893: (float) of the double result
+		h.qual = (float)rsk_qual(r.ts);
+		h.evalue = (float)rsk_evalue(r.ts);
+	} else {
+		// ClearAlign values (dssaligner.cpp:906-927)
+		h.hi_a = h.hi_b = h.ids = h.gaps = 0xffffffffu;
+		h.lddt = 0; h.ts = -FLT_MAX;
+		h.pvalue = h.evalue = h.qual = FLT_MAX;
+		if (r.path_len == 0) { h.lo_a = h.lo_b = 0xffffffffu; }
+	}
+	// runquery.cpp:72-73 + DBSearcher::Reject (dbsearcher.cpp:258-265)
+	if (r.path_len > 0 && !((double)h.evalue > P.max_evalue))
+		h.flags |= RSK_HIT_REPORTED;
+}
+
+int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, rsk_results **out, bool device_only)
+{
+	rsk_search_opts opts;
+	memset(&opts, 0, sizeof(opts));
+	if (opts_in)
+		opts = *opts_in;
+	const rsk_chainset *A = plan.A, *B = plan.B;
+	if (A->ctx != ctx || B->ctx != ctx)
+		return fail(RSK_ERR_ARG, "chain sets belong to a different context");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	rsk_stats &S = ctx->stats;
+	const uint64_t launches0 = S.kernel_launches;
+	memset(&S, 0, sizeof(S));
+	S.kernel_launches = 0;
+	(void)launches0;
+	CK(cudaEventRecord(ctx->ev[6], st));
+
+	// ---- batches ----
+	std::vector<Batch> batches;
+	if (plan.cross) {
+		const uint32_t nA = A->d.n, nB = B->d.n;
+		plan.npairs = (uint64_t)nA * nB;
+		uint64_t sumLB = B->d.total;
+		uint32_t maxLB = B->maxlen;
+		const uint32_t per = (uint32_t)std::max<uint64_t>(1, ctx->max_batch_pairs / nB);
+		for (uint32_t a0 = 0; a0 < nA; a0 += per) {
+			Batch b;
+			b.cross = true;
+			b.a0 = a0;
+			b.a1 = std::min(nA, a0 + per);
+			b.npairs = (size_t)(b.a1 - b.a0) * nB;
+			b.ntasks = (b.a1 - b.a0) * ((nB + kSwWarps - 1) / kSwWarps);
+			uint64_t sumLA = 0;
+			for (uint32_t a = b.a0; a < b.a1; ++a) {
+				sumLA += A->hlen[a];
+				b.maxLA = std::max(b.maxLA, A->hlen[a]);
+			}
+			b.maxLB = maxLB;
+			b.cells = sumLA * sumLB;
+			b.pool_bound = sumLA * nB + (uint64_t)(b.a1 - b.a0) * sumLB;
+			batches.push_back(b);
+		}
+		// B order: by length so that the 16 chains of a task have similar lengths
+		plan.border.resize(nB);
+		std::iota(plan.border.begin(), plan.border.end(), 0u);
+		std::stable_sort(plan.border.begin(), plan.border.end(),
+				[&](uint32_t x, uint32_t y) { return B->hlen[x] > B->hlen[y]; });
+		if (ctx->blist.ensure(nB))
+			return fail(RSK_ERR_NOMEM, "blist");
+		CK(cudaMemcpyAsync(ctx->blist.p, plan.border.data(), sizeof(uint32_t) * nB, cudaMemcpyHostToDevice, st));
+		S.h2d_bytes += sizeof(uint32_t) * nB;
+	} else {
+		const uint64_t np = plan.npairs;
+		for (size_t k0 = 0; k0 < np; ) {
+			// a batch ends on a task boundary: cut at max_batch_pairs, then extend to the end of that A run
+			size_t k1 = std::min<size_t>(np, k0 + ctx->max_batch_pairs);
+			Batch b;
+			b.cross = false;
+			b.k0 = k0; b.k1 = k1;
+			b.npairs = k1 - k0;
+			for (size_t k = k0; k < k1; ++k) {
+				const uint32_t la = A->hlen[plan.sa[k]], lb = B->hlen[plan.sb[k]];
+				b.maxLA = std::max(b.maxLA, la);
+				b.maxLB = std::max(b.maxLB, lb);
+				b.cells += (uint64_t)la * lb;
+				b.pool_bound += (uint64_t)la + lb;
+			}
+			batches.push_back(b);
+			k0 = k1;
+		}
+	}
+	S.pairs = plan.npairs;
+
+	rsk_results *res = nullptr;
+	if (!device_only) {
+		res = new rsk_results();
+		if (opts.keep == RSK_KEEP_ALL)
+			res->hits.resize(plan.npairs);
+	}
+
+	std::vector<uint32_t> t_a, t_begin, t_cnt, slots;
+	for (const Batch &b0 : batches) {
+		Batch b = b0;
+		if (!b.cross) {
+			// build tasks for sorted pairs [k0,k1): runs of equal A, chunks of kSwWarps
+			t_a.clear(); t_begin.clear(); t_cnt.clear();
+			const size_t n = b.k1 - b.k0;
+			slots.resize(n);
+			for (size_t k = 0; k < n; ++k)
+				slots[k] = (uint32_t)k;
+			size_t k = 0;
+			while (k < n) {
+				size_t e = k + 1;
+				while (e < n && e - k < (size_t)kSwWarps && plan.sa[b.k0 + e] == plan.sa[b.k0 + k])
+					++e;
+				t_a.push_back(plan.sa[b.k0 + k]);
+				t_begin.push_back((uint32_t)k);
+				t_cnt.push_back((uint32_t)(e - k));
+				k = e;
+			}
+			b.ntasks = (uint32_t)t_a.size();
+			if (ctx->blist.ensure(n) || ctx->bslot.ensure(n) || ctx->pair_a.ensure(n) || ctx->pair_b.ensure(n) ||
+				ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks))
+				return fail(RSK_ERR_NOMEM, "task buffers");
+			CK(cudaMemcpyAsync(ctx->blist.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->bslot.p, slots.data(), 4 * n, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->pair_a.p, plan.sa.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->pair_b.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->task_a.p, t_a.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->task_begin.p, t_begin.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->task_cnt.p, t_cnt.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+			S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks;
+		}
+		int rc = run_batch(ctx, plan, b, opts);
+		if (rc) {
+			delete res;
+			return rc;
+		}
+		if (device_only) {
+			CK(cudaStreamSynchronize(st));
+			rc = finish_batch_timing(ctx);
+			if (rc)
+				return rc;
+			continue;
+		}
+		// ---- D2H: records (+ paths) of this batch ----
+		if (ctx->h_rec.ensure(b.npairs)) {
+			delete res;
+			return fail(RSK_ERR_NOMEM, "pinned record buffer");
+		}
+		unsigned long long pool_used = 0;
+		CK(cudaMemcpyAsync(ctx->h_rec.p, ctx->rec.p, b.npairs * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&pool_used, ctx->d_pool_cursor, sizeof(pool_used), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		S.d2h_bytes += b.npairs * sizeof(PairRec) + 8;
+		const uint64_t pool_base = res->paths.size();
+		if (opts.want_paths && pool_used > 0) {
+			if (ctx->h_pool.ensure(pool_used)) {
+				delete res;
+				return fail(RSK_ERR_NOMEM, "pinned path buffer");
+			}
+			CK(cudaMemcpyAsync(ctx->h_pool.p, ctx->pool.p, pool_used, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			res->paths.insert(res->paths.end(), (const char *)ctx->h_pool.p, (const char *)ctx->h_pool.p + pool_used);
+			S.d2h_bytes += pool_used;
+		}
+		rc = finish_batch_timing(ctx);
+		if (rc) {
+			delete res;
+			return rc;
+		}
+		// ---- records -> rsk_hit ----
+		const uint32_t nB = B->d.n;
+		for (size_t k = 0; k < b.npairs; ++k) {
+			uint32_t a, bb;
+			uint64_t orig;
+			if (b.cross) {
+				a = b.a0 + (uint32_t)(k / nB);
+				bb = (uint32_t)(k % nB);
+				orig = (uint64_t)a * nB + bb;
+			} else {
+				a = plan.sa[b.k0 + k];
+				bb = plan.sb[b.k0 + k];
+				orig = plan.perm[b.k0 + k];
+			}
+			rsk_hit h;
+			fill_hit(ctx->params, ctx->h_rec.p[k], a, bb, pool_base, h);
+			if (h.flags & RSK_HIT_HAS_EVALUE)
+				++S.evalue_pairs;
+			if (h.flags & RSK_HIT_REPORTED)
+				++S.hits;
+			if (opts.keep == RSK_KEEP_ALL)
+				res->hits[orig] = h;
+			else if (h.flags & RSK_HIT_REPORTED)
+				res->hits.push_back(h);
+		}
+	}
+	CK(cudaEventRecord(ctx->ev[7], st));
+	CK(cudaEventSynchronize(ctx->ev[7]));
+	CK(cudaEventElapsedTime(&S.total_ms, ctx->ev[6], ctx->ev[7]));
+	if (out)
+		*out = res;
+	return RSK_OK;
+}
+
+}  // namespace
+
+extern "C" int rsk_search_cross(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, const rsk_search_opts *opts, rsk_results **out)
+{
+	if (!ctx || !A || !B || !out)
+		return fail(RSK_ERR_ARG, "rsk_search_cross: null argument");
+	*out = nullptr;
+	SearchPlan plan;
+	plan.A = A; plan.B = B; plan.cross = true;
+	return search_impl(ctx, plan, opts, out, false);
+}
+
+extern "C" int rsk_search_cross_device(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, const rsk_search_opts *opts)
+{
+	if (!ctx || !A || !B)
+		return fail(RSK_ERR_ARG, "rsk_search_cross_device: null argument");
+	SearchPlan plan;
+	plan.A = A; plan.B = B; plan.cross = true;
+	return search_impl(ctx, plan, opts, nullptr, true);
+}
+
+static int build_explicit_plan(SearchPlan &plan, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib)
+{
+	plan.A = A; plan.B = B; plan.cross = false; plan.npairs = npairs;
+	plan.perm.resize(npairs);
+	std::iota(plan.perm.begin(), plan.perm.end(), (uint64_t)0);
+	for (uint64_t k = 0; k < npairs; ++k)
+		if (ia[k] >= A->d.n || ib[k] >= B->d.n)
+			return fail(RSK_ERR_ARG, "pair %llu: chain index out of range (%u,%u)", (unsigned long long)k, ia[k], ib[k]);
+	std::stable_sort(plan.perm.begin(), plan.perm.end(), [&](uint64_t x, uint64_t y) {
+		if (ia[x] != ia[y])
+			return ia[x] < ia[y];
+		return B->hlen[ib[x]] > B->hlen[ib[y]];
+	});
+	plan.sa.resize(npairs);
+	plan.sb.resize(npairs);
+	for (uint64_t k = 0; k < npairs; ++k) {
+		plan.sa[k] = ia[plan.perm[k]];
+		plan.sb[k] = ib[plan.perm[k]];
+	}
+	return RSK_OK;
+}
+
+extern "C" int rsk_search_pairs(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib, const rsk_search_opts *opts, rsk_results **out)
+{
+	if (!ctx || !A || !B || !out || (npairs && (!ia || !ib)))
+		return fail(RSK_ERR_ARG, "rsk_search_pairs: null argument");
+	*out = nullptr;
+	if (npairs == 0) {
+		*out = new rsk_results();
+		return RSK_OK;
+	}
+	SearchPlan plan;
+	int rc = build_explicit_plan(plan, A, B, npairs, ia, ib);
+	if (rc)
+		return rc;
+	return search_impl(ctx, plan, opts, out, false);
+}
+
+extern "C" int rsk_search_self(rsk_ctx *ctx, const rsk_chainset *Sx, const rsk_search_opts *opts, rsk_results **out)
+{
+	if (!ctx || !Sx || !out)
+		return fail(RSK_ERR_ARG, "rsk_search_self: null argument");
+	*out = nullptr;
+	const uint64_t n = Sx->d.n;
+	const uint64_t np = n * (n + 1) / 2;
+	std::vector<uint32_t> ia, ib;
+	ia.reserve(np);
+	ib.reserve(np);
+	for (uint32_t i = 0; i < n; ++i)  // runself.cpp:72-99: (i, j >= i), A = chain i, B = chain j
+		for (uint32_t j = i; j < n; ++j) {
+			ia.push_back(i);
+			ib.push_back(j);
+		}
+	SearchPlan plan;
+	int rc = build_explicit_plan(plan, Sx, Sx, np, ia.data(), ib.data());
+	if (rc)
+		return rc;
+	return search_impl(ctx, plan, opts, out, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+extern "C" uint64_t rsk_results_count(const rsk_results *r) { return r ? r->hits.size() : 0; }
+extern "C" const rsk_hit *rsk_results_hits(const rsk_results *r) { return (r && !r->hits.empty()) ? r->hits.data() : nullptr; }
+extern "C" const char *rsk_results_paths(const rsk_results *r) { return (r && !r->paths.empty()) ? r->paths.data() : nullptr; }
+extern "C" uint64_t rsk_results_paths_bytes(const rsk_results *r) { return r ? r->paths.size() : 0; }
+extern "C" void rsk_results_free(rsk_results *r) { delete r; }

@@ -1,0 +1,270 @@
+"""ctypes binding of libreseek_b200.so (include/reseek_b200.h).  No compute happens in Python."""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libreseek_b200.so"
+
+NFEAT = 8
+TABLE_FLOATS = 2192
+MODE_FAST, MODE_SENSITIVE, MODE_VERYSENSITIVE = 1, 2, 3
+KEEP_HITS, KEEP_ALL = 0, 1
+HIT_MU_REJECTED, HIT_HAS_EVALUE, HIT_REPORTED = 1, 2, 4
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+class ReseekB200Error(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("gap_open", C.c_float), ("gap_ext", C.c_float), ("min_fwd_score", C.c_float),
+                ("omega", C.c_float), ("omega_fwd", C.c_float), ("mu_gap_open", C.c_int32),
+                ("mu_gap_ext", C.c_int32), ("mkfl", C.c_uint32), ("mkf_x1", C.c_int32), ("mkf_x2", C.c_int32),
+                ("mkf_min_hsp_score", C.c_int32), ("mkf_min_mega_hsp_score", C.c_float),
+                ("max_evalue", C.c_double), ("weights", C.c_float * NFEAT), ("tables", C.c_float * TABLE_FLOATS)]
+
+
+class ChainsHost(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("total", C.c_uint64), ("len", C.c_void_p), ("prof", C.c_void_p),
+                ("mu", C.c_void_p), ("xyz", C.c_void_p), ("selfrev", C.c_void_p)]
+
+
+class SearchOpts(C.Structure):
+    _fields_ = [("keep", C.c_int32), ("want_paths", C.c_int32), ("skip_evalue", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("pairs", C.c_uint64), ("mu_filter_in", C.c_uint64), ("mu_filter_rejected", C.c_uint64),
+                ("mu_saturated", C.c_uint64), ("sw_pairs", C.c_uint64), ("sw_cells", C.c_uint64),
+                ("evalue_pairs", C.c_uint64), ("hits", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sw_kernel_ms", C.c_float),
+                ("mu_kernel_ms", C.c_float), ("lddt_kernel_ms", C.c_float), ("total_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# numpy view of rsk_hit (include/reseek_b200.h)
+HIT_DTYPE = np.dtype([
+    ("a", np.uint32), ("b", np.uint32), ("score", np.float32), ("lo_a", np.uint32), ("lo_b", np.uint32),
+    ("hi_a", np.uint32), ("hi_b", np.uint32), ("ids", np.uint32), ("gaps", np.uint32), ("lddt", np.float32),
+    ("ts", np.float32), ("pvalue", np.float32), ("evalue", np.float32), ("qual", np.float32),
+    ("mu_score", np.float32), ("mu_fwd", np.int32), ("mu_rev", np.int32), ("flags", np.uint32),
+    ("path_len", np.uint32), ("path_off", np.uint64)], align=True)
+
+_lib = None
+
+
+def load_library():
+    """Load libreseek_b200.so; raise (loudly) when it has not been built - there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ReseekB200Error(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "or `make -C reseek_b200/csrc` (no CPU fallback exists)")
+    L = C.CDLL(str(LIB_PATH))
+    L.rsk_version.restype = C.c_char_p
+    L.rsk_last_error.restype = C.c_char_p
+    L.rsk_feature_bgfreq.restype = C.POINTER(C.c_float)
+    L.rsk_mu_matrix_i8.restype = C.POINTER(C.c_int8)
+    L.rsk_mu_kmer_matrix_i8.restype = C.POINTER(C.c_int8)
+    L.rsk_mu_matrix_f32.restype = C.POINTER(C.c_float)
+    L.rsk_chainset_count.restype = C.c_uint32
+    L.rsk_chainset_residues.restype = C.c_uint64
+    L.rsk_results_count.restype = C.c_uint64
+    L.rsk_results_hits.restype = C.c_void_p
+    L.rsk_results_paths.restype = C.c_void_p
+    L.rsk_results_paths_bytes.restype = C.c_uint64
+    for fn in (L.rsk_pvalue, L.rsk_evalue, L.rsk_qual):
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_double]
+    L.rsk_ctx_create.argtypes = [C.c_int, C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rsk_ctx_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    L.rsk_ctx_destroy.argtypes = [C.c_void_p]
+    L.rsk_ctx_destroy.restype = None
+    L.rsk_ctx_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.rsk_ctx_sync.argtypes = [C.c_void_p]
+    L.rsk_chainset_upload.argtypes = [C.c_void_p, C.POINTER(ChainsHost), C.POINTER(C.c_void_p)]
+    L.rsk_chainset_free.argtypes = [C.c_void_p]
+    L.rsk_chainset_free.restype = None
+    L.rsk_chainset_count.argtypes = [C.c_void_p]
+    L.rsk_chainset_residues.argtypes = [C.c_void_p]
+    L.rsk_search_cross.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
+    L.rsk_search_self.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
+    L.rsk_search_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                   C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
+    L.rsk_search_cross_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts)]
+    for fn in (L.rsk_results_count, L.rsk_results_hits, L.rsk_results_paths, L.rsk_results_paths_bytes):
+        fn.argtypes = [C.c_void_p]
+    L.rsk_results_free.argtypes = [C.c_void_p]
+    L.rsk_results_free.restype = None
+    _lib = L
+    return L
+
+
+def version():
+    return load_library().rsk_version().decode()
+
+
+def device_count():
+    return load_library().rsk_device_count()
+
+
+def _check(rc):
+    if rc != 0:
+        raise ReseekB200Error(f"libreseek_b200 error {rc}: {load_library().rsk_last_error().decode()}")
+
+
+def params_preset(mode):
+    p = Params()
+    _check(load_library().rsk_params_preset(C.byref(p), int(mode)))
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Results:
+    """Hits of one search call, copied into numpy arrays (the C object is freed immediately)."""
+
+    def __init__(self, handle):
+        L = load_library()
+        n = L.rsk_results_count(handle)
+        if n:
+            buf = (C.c_char * (n * HIT_DTYPE.itemsize)).from_address(L.rsk_results_hits(handle))
+            self.hits = np.frombuffer(buf, dtype=HIT_DTYPE, count=n).copy()
+        else:
+            self.hits = np.zeros(0, HIT_DTYPE)
+        nb = L.rsk_results_paths_bytes(handle)
+        if nb:
+            buf = (C.c_char * nb).from_address(L.rsk_results_paths(handle))
+            self.paths = bytes(buf)
+        else:
+            self.paths = b""
+        L.rsk_results_free(handle)
+
+    def path(self, k):
+        h = self.hits[k]
+        off, n = int(h["path_off"]), int(h["path_len"])
+        return self.paths[off:off + n].decode()
+
+    def __len__(self):
+        return len(self.hits)
+
+
+class ChainSet:
+    """Device-resident chains (DBSearcher's per-chain vectors, dbsearcher.h:26-33)."""
+
+    def __init__(self, ctx, lens, prof, mu, xyz, selfrev):
+        self.ctx = ctx
+        self.lens = np.ascontiguousarray(lens, np.uint32)
+        self.n = len(self.lens)
+        self.total = int(self.lens.sum(dtype=np.uint64))
+        self.prof = np.ascontiguousarray(prof, np.uint8)
+        assert self.prof.shape == (NFEAT, self.total), (self.prof.shape, self.total)
+        self.mu = None if mu is None else np.ascontiguousarray(mu, np.uint8)
+        self.xyz = np.ascontiguousarray(xyz, np.float32)
+        assert self.xyz.shape == (3, self.total)
+        self.selfrev = None if selfrev is None else np.ascontiguousarray(selfrev, np.float32)
+        h = ChainsHost(self.n, self.total, _ptr(self.lens), _ptr(self.prof), _ptr(self.mu), _ptr(self.xyz),
+                       _ptr(self.selfrev))
+        self.handle = C.c_void_p()
+        _check(load_library().rsk_chainset_upload(ctx.handle, C.byref(h), C.byref(self.handle)))
+
+    @property
+    def h2d_bytes(self):
+        return self.lens.nbytes + self.prof.nbytes + (0 if self.mu is None else self.mu.nbytes) + self.xyz.nbytes + \
+            (0 if self.selfrev is None else self.selfrev.nbytes)
+
+    def free(self):
+        if self.handle:
+            load_library().rsk_chainset_free(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU + stream + scratch: the aligner pool of a DBSearcher (dbsearcher.cpp:73)."""
+
+    def __init__(self, device=0, mode=MODE_VERYSENSITIVE, params=None, stream=None):
+        L = load_library()
+        self.params = params if params is not None else params_preset(mode)
+        self.handle = C.c_void_p()
+        _check(L.rsk_ctx_create(int(device), C.byref(self.params), C.c_void_p(stream) if stream else None,
+                                C.byref(self.handle)))
+
+    def set_params(self, params):
+        self.params = params
+        _check(load_library().rsk_ctx_set_params(self.handle, C.byref(params)))
+
+    def upload(self, lens, prof, mu, xyz, selfrev=None):
+        return ChainSet(self, lens, prof, mu, xyz, selfrev)
+
+    def upload_chains(self, chains):
+        """chains: objects with .prof [8][L], .mu, .xyz [3][L], .selfrev (e.g. oracle.pyoracle.Chain)."""
+        lens = np.array([c.L for c in chains], np.uint32)
+        prof = np.concatenate([c.prof for c in chains], axis=1)
+        mu = None if any(c.mu is None for c in chains) else np.concatenate([c.mu for c in chains])
+        xyz = np.concatenate([c.xyz for c in chains], axis=1)
+        selfrev = np.array([c.selfrev for c in chains], np.float32)
+        return self.upload(lens, prof, mu, xyz, selfrev)
+
+    @staticmethod
+    def _opts(keep, want_paths, skip_evalue):
+        return SearchOpts(int(keep), int(bool(want_paths)), int(bool(skip_evalue)), 0)
+
+    def search_cross(self, A, B, keep=KEEP_ALL, want_paths=True, skip_evalue=False):
+        o = self._opts(keep, want_paths, skip_evalue)
+        r = C.c_void_p()
+        _check(load_library().rsk_search_cross(self.handle, A.handle, B.handle, C.byref(o), C.byref(r)))
+        return Results(r)
+
+    def search_cross_device(self, A, B, skip_evalue=False):
+        o = self._opts(KEEP_ALL, False, skip_evalue)
+        _check(load_library().rsk_search_cross_device(self.handle, A.handle, B.handle, C.byref(o)))
+
+    def search_self(self, S, keep=KEEP_ALL, want_paths=True, skip_evalue=False):
+        o = self._opts(keep, want_paths, skip_evalue)
+        r = C.c_void_p()
+        _check(load_library().rsk_search_self(self.handle, S.handle, C.byref(o), C.byref(r)))
+        return Results(r)
+
+    def search_pairs(self, A, B, ia, ib, keep=KEEP_ALL, want_paths=True, skip_evalue=False):
+        ia = np.ascontiguousarray(ia, np.uint32)
+        ib = np.ascontiguousarray(ib, np.uint32)
+        assert len(ia) == len(ib)
+        o = self._opts(keep, want_paths, skip_evalue)
+        r = C.c_void_p()
+        _check(load_library().rsk_search_pairs(self.handle, A.handle, B.handle, len(ia), _ptr(ia), _ptr(ib),
+                                               C.byref(o), C.byref(r)))
+        return Results(r)
+
+    def stats(self):
+        s = Stats()
+        _check(load_library().rsk_ctx_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def sync(self):
+        _check(load_library().rsk_ctx_sync(self.handle))
+
+    def close(self):
+        if self.handle:
+            load_library().rsk_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
