@@ -308,6 +308,22 @@ class Ref:
             C.c_float(B.selfrev), int(noaccel), C.byref(r), path, A.L + B.L + 2)
         return r, path.value.decode()
 
+    def align_batch(self, A, B, ia, ib, nthreads):
+        """A, B: SoA chain sets (objects with lens/prof/mu/xyz/selfrev numpy arrays).  Multi-threaded reference loop."""
+        ia = np.ascontiguousarray(ia, np.uint32)
+        ib = np.ascontiguousarray(ib, np.uint32)
+        score = np.zeros(len(ia), np.float32)
+        evalue = np.zeros(len(ia), np.float32)
+        plen = np.zeros(len(ia), np.uint32)
+
+        def p(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+        self.lib.ref_align_batch(int(nthreads), A.n, p(A.lens), p(A.prof), p(A.mu), p(A.xyz), p(A.selfrev),
+                                 B.n, p(B.lens), p(B.prof), p(B.mu), p(B.xyz), p(B.selfrev),
+                                 C.c_uint64(len(ia)), p(ia), p(ib), p(score), p(evalue), p(plen))
+        return score, evalue, plen
+
     def mu_score(self, a, b):
         a = np.ascontiguousarray(a, np.uint8)
         b = np.ascontiguousarray(b, np.uint8)

@@ -15,6 +15,8 @@
 #include "statsig.h"
 #include "mumx.h"
 #include "parasail.h"
+#include <thread>
+#include <atomic>
 
 // normally defined in reseek_main.cpp (which holds main() and is left out of the library)
 int g_Frame = 0;
@@ -310,6 +312,78 @@ double ref_lddt(uint LA, const float *xA, const float *yA, const float *zA,
 	MakeChain(CB, "B", LB, 0, xB, yB, zB);
 	vector<uint> PA(posA, posA + n), PB(posB, posB + n);
 	return GetLDDT_mu_fast(CA, CB, PA, PB);
+	}
+
+// Multi-threaded batch for CPU-baseline timing: the reference's own per-pair loop (one DSSAligner per thread,
+// SetQuery when the A chain changes, SetTarget + AlignQueryTarget per pair - runquery.cpp:45,70-71), std::thread
+// over contiguous pair ranges like dbsearcher's thread pool.  Chains are SoA: len[], prof [8][total] plane-major,
+// mu [total] (may be NULL), xyz [3][total], selfrev[].  out_score / out_evalue: per pair.
+int ref_align_batch(int nthreads,
+  uint nA, const uint32_t *lenA, const uint8_t *profA, const uint8_t *muA, const float *xyzA, const float *selfrevA,
+  uint nB, const uint32_t *lenB, const uint8_t *profB, const uint8_t *muB, const float *xyzB, const float *selfrevB,
+  uint64_t npairs, const uint32_t *ia, const uint32_t *ib, float *out_score, float *out_evalue, uint32_t *out_pathlen)
+	{
+	struct Set
+		{
+		vector<PDBChain *> Chains;
+		vector<vector<vector<byte> > > Profs;
+		vector<vector<byte> > Mus;
+		};
+	auto Build = [](Set &S, uint n, const uint32_t *len, const uint8_t *prof, const uint8_t *mu, const float *xyz)
+		{
+		uint64_t total = 0;
+		for (uint i = 0; i < n; ++i) total += len[i];
+		uint64_t off = 0;
+		S.Profs.resize(n);
+		S.Mus.resize(n);
+		for (uint i = 0; i < n; ++i)
+			{
+			uint L = len[i];
+			PDBChain *C = new PDBChain;
+			MakeChain(*C, "c", L, 0, xyz + off, xyz + total + off, xyz + 2*total + off);
+			S.Chains.push_back(C);
+			S.Profs[i].resize(8);
+			for (uint f = 0; f < 8; ++f)
+				S.Profs[i][f].assign(prof + f*total + off, prof + f*total + off + L);
+			if (mu)
+				S.Mus[i].assign(mu + off, mu + off + L);
+			off += L;
+			}
+		};
+	Set SA, SB;
+	Build(SA, nA, lenA, profA, muA, xyzA);
+	Build(SB, nB, lenB, profB, muB, xyzB);
+	if (nthreads < 1) nthreads = 1;
+	vector<thread> ts;
+	for (int t = 0; t < nthreads; ++t)
+		{
+		ts.emplace_back([&, t]()
+			{
+			DSSAligner DA;
+			DA.SetParams(*g_Params);
+			uint64_t k0 = npairs*t/nthreads, k1 = npairs*(t + 1)/nthreads;
+			uint32_t cur = UINT_MAX;
+			for (uint64_t k = k0; k < k1; ++k)
+				{
+				uint a = ia[k], b = ib[k];
+				if (a != cur)
+					{
+					DA.SetQuery(*SA.Chains[a], &SA.Profs[a], muA ? &SA.Mus[a] : 0, 0, selfrevA ? selfrevA[a] : FLT_MAX);
+					cur = a;
+					}
+				DA.SetTarget(*SB.Chains[b], &SB.Profs[b], muB ? &SB.Mus[b] : 0, 0, selfrevB ? selfrevB[b] : FLT_MAX);
+				DA.AlignQueryTarget();
+				if (out_score) out_score[k] = DA.m_AlnFwdScore;
+				if (out_evalue) out_evalue[k] = DA.m_EvalueA;
+				if (out_pathlen) out_pathlen[k] = SIZE(DA.m_Path);
+				}
+			DA.UnsetQuery();
+			});
+		}
+	for (auto &t : ts) t.join();
+	for (auto *C : SA.Chains) delete C;
+	for (auto *C : SB.Chains) delete C;
+	return 0;
 	}
 
 void ref_statsig(double ts, double *p, double *e, double *q)

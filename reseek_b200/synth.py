@@ -86,6 +86,24 @@ def _walk_fast(rng, L):
     return (ic.astype(np.float32) / np.float32(10.0) - np.float32(1000.0)).astype(np.float32).T
 
 
+def _walk_all(rng, lens):
+    """All chains at once: smoothed random unit steps of 3.8 A, positions restarted at every chain start,
+    quantised to the .bca grid (0.1 A) and decoded as ICToCoord does."""
+    lens = np.asarray(lens, np.int64)
+    total = int(lens.sum())
+    d = rng.standard_normal(size=(total + 8, 3), dtype=np.float32)
+    k = np.array([0.05, 0.1, 0.2, 0.3, 0.2, 0.1, 0.05], np.float32)
+    d = np.stack([np.convolve(d[:, c], k, mode="same") for c in range(3)], axis=1)[4:4 + total]
+    d /= np.linalg.norm(d, axis=1, keepdims=True) + 1e-12
+    pos = np.cumsum(3.8 * d, axis=0, dtype=np.float64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    base = np.repeat(pos[starts] , lens, axis=0)
+    pos = pos - base
+    ic = np.floor((pos + 1000.0) * 10.0 + 0.5)
+    ic = np.clip(ic, 0, 65535).astype(np.uint16)
+    return np.ascontiguousarray((ic.astype(np.float32) / np.float32(10.0) - np.float32(1000.0)).astype(np.float32).T)
+
+
 def make_chains(n, length, seed, length_jitter=0.0, bg=None, selfrev_scale=0.08):
     """n chains of (about) `length` residues.  length may be an int or an array of n lengths."""
     rng = np.random.default_rng(seed)
@@ -100,7 +118,10 @@ def make_chains(n, length, seed, length_jitter=0.0, bg=None, selfrev_scale=0.08)
     total = int(lens.sum())
     prof = np.empty((NFEAT, total), np.uint8)
     for f in range(NFEAT):
-        prof[f] = rng.choice(ALPHA[f], size=total, p=bg[f]).astype(np.uint8)
+        # inverse CDF through a 16-bit lookup table (quantisation 2^-16, far below the frequencies' precision)
+        cdf = np.cumsum(bg[f])
+        lut = np.minimum(np.searchsorted(cdf, (np.arange(65536) + 0.5) / 65536.0, side="right"), ALPHA[f] - 1).astype(np.uint8)
+        prof[f] = lut[rng.integers(0, 65536, size=total, dtype=np.uint16)]
     # Mu letters: sticky first-order chain (secondary structure persists), 36 letters
     mu = rng.integers(0, 36, size=total).astype(np.uint8)
     stick = rng.random(total) < 0.55
@@ -108,11 +129,7 @@ def make_chains(n, length, seed, length_jitter=0.0, bg=None, selfrev_scale=0.08)
     idx = np.arange(total)
     last = np.maximum.accumulate(np.where(~stick, idx, 0))
     mu = mu[last]
-    xyz = np.empty((3, total), np.float32)
-    off = 0
-    for L in lens:
-        xyz[:, off:off + L] = _walk_fast(rng, int(L))
-        off += int(L)
+    xyz = _walk_all(rng, lens)
     # self-reverse scores are per-chain inputs of the hot path (alignpair.cpp:7-25); plausible magnitude ~ 0.08*L
     selfrev = (selfrev_scale * lens * (0.5 + rng.random(n))).astype(np.float32)
     return SynthChains(lens.astype(np.uint32), prof, mu, xyz, selfrev)
