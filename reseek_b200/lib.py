@@ -212,7 +212,7 @@ class Context:
         return ChainSet(self, lens, prof, mu, xyz, selfrev)
 
     def upload_chains(self, chains):
-        """chains: objects with .prof [8][L], .mu, .xyz [3][L], .selfrev (e.g. oracle.pyoracle.Chain)."""
+        """chains: objects with .prof [8][L], .mu, .xyz [3][L], .selfrev (duck-typed)."""
         lens = np.array([c.L for c in chains], np.uint32)
         prof = np.concatenate([c.prof for c in chains], axis=1)
         mu = None if any(c.mu is None for c in chains) else np.concatenate([c.mu for c in chains])

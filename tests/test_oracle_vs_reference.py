@@ -1,0 +1,62 @@
+"""CPU, build container only: the C oracle against the live reference library on fresh random inputs."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import Ref
+from tests.util import bits
+
+pytestmark = pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def test_tables_and_presets(port):
+    for mode in (1, 2, 3):
+        ref = Ref(mode)
+        p = port(mode)
+        sc, tb = ref.get_params()
+        assert np.array_equal(bits(tb), bits(p.tables()))
+        P = p.params
+        mine = [P.gap_open, P.gap_ext, P.min_fwd_score, P.omega, P.omega_fwd, P.mkfl, P.mkf_x1, P.mkf_x2,
+                P.mkf_min_hsp_score, P.mkf_min_mega_hsp_score, P.mu_gap_open, P.mu_gap_ext]
+        assert np.array_equal(bits(np.array(mine, np.float32)), bits(sc))
+    f, a, b = ref.mu_matrices()
+    assert np.array_equal(bits(f), bits(p.mu_f32())) and np.array_equal(a, p.mu_i8()) and np.array_equal(b, p.mu_kmer_i8())
+
+
+@pytest.mark.parametrize("mode", [3, 2])
+def test_random_synthetic_pairs(port, built_lib, mode):
+    from reseek_b200 import synth
+    from tests.util import to_oracle_chains
+    ref = Ref(mode)
+    p = port(mode)
+    a = synth.make_chains(6, 90, seed=31 + mode, length_jitter=0.4)
+    b = synth.make_chains(12, 110, seed=41 + mode, length_jitter=0.4)
+    synth.plant_homologs(b, a, 0.5, seed=51)
+    ca, cb = to_oracle_chains(a), to_oracle_chains(b)
+    nalign = 0
+    for A in ca:
+        for B in cb:
+            rr, rpath = ref.align_pair(A, B, use_mu=(mode != 3), use_kmers=False)
+            if mode == 3:
+                A2, B2 = type(A)(A.prof, None, A.xyz, A.selfrev), type(B)(B.prof, None, B.xyz, B.selfrev)
+            else:
+                A2, B2 = A, B
+            r, path = p.align_pair(A2, B2)
+            assert path == rpath and bits(r.score) == bits(rr.score)
+            assert bits(r.ts) == bits(rr.ts) and bits(r.evalue) == bits(rr.evalue)
+            nalign += bool(path)
+    assert nalign > 5
+
+
+def test_mu_filter_random(port):
+    ref = Ref(2)
+    p = port(2)
+    rng = np.random.default_rng(3)
+    for t in range(300):
+        la, lb = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        a = rng.integers(0, 36, la).astype(np.uint8)
+        b = rng.integers(0, 36, lb).astype(np.uint8)
+        if t % 3 == 0:
+            n = min(la, lb)
+            b[:n] = a[:n]
+        s, fwd, rev = p.mu_filter_score(a, b)
+        assert s == ref.mu_score(a, b), f"case {t}"
