@@ -98,7 +98,9 @@ typedef struct rsk_hit {
 enum {
 	RSK_HIT_MU_REJECTED = 1u, /* dropped by the Mu filter: no SW was run */
 	RSK_HIT_HAS_EVALUE = 2u,  /* CalcEvalue ran (score >= min_fwd_score) */
-	RSK_HIT_REPORTED = 4u     /* passes DBSearcher::Reject (E <= max_evalue) */
+	RSK_HIT_REPORTED = 4u,    /* passes DBSearcher::Reject (E <= max_evalue) */
+	RSK_HIT_MKF_PENDING = 8u  /* DoMKF() pair (a chain >= mkfl, dssaligner.cpp:715-732): the k-mer/x-drop path is not built yet;
+	                             the pair is NOT aligned and is reported with this flag instead of a wrong answer */
 };
 
 /* which pairs come back from a search call */

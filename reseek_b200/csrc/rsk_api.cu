@@ -128,10 +128,19 @@ struct rsk_ctx {
 	DevBuf<PairRec> rec;
 	DevBuf<uint8_t> pool;
 	DevBuf<uint32_t> blist, bslot, task_a, task_begin, task_cnt, pair_a, pair_b;
+	// Mu filter (K3) state
+	int *d_mu_mx = nullptr;                 // IntScoreMx_Mu widened to int32
+	DevBuf<uint8_t> keep;
+	DevBuf<int2> mu_bnd;
+	DevBuf<uint32_t> c_blist, c_bslot, c_task_a, c_task_begin, c_task_cnt;  // compacted survivors
+	size_t filt_explicit_pairs = 0; uint64_t filt_explicit_cells = 0; uint32_t filt_explicit_tasks = 0; bool batch_cross = true;
+	struct Counters { uint32_t task_count, sat_count, mu_task_counter, pad; unsigned long long pair_count, cell_count; };
+	Counters *d_counters = nullptr;
 	PinBuf<PairRec> h_rec;
 	PinBuf<uint8_t> h_pool;
 	PinBuf<uint32_t> h_idx;
 	rsk_stats stats;
+	bool batch_filtered = false;
 	size_t max_batch_pairs = 2u << 20;
 	size_t scratch_budget = (size_t)24 << 30;
 };
@@ -250,6 +259,10 @@ extern "C" int rsk_ctx_set_params(rsk_ctx *ctx, const rsk_params *params)
 	ctx->params = *params;
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaMemcpyAsync(ctx->d_tables, ctx->params.tables, sizeof(float) * RSK_TABLE_FLOATS, cudaMemcpyHostToDevice, ctx->stream));
+	int mx[36 * 36];
+	for (int k = 0; k < 36 * 36; ++k)
+		mx[k] = rsk_tbl_mu_i8[k];
+	CK(cudaMemcpyAsync(ctx->d_mu_mx, mx, sizeof(mx), cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	return RSK_OK;
 }
@@ -289,7 +302,9 @@ extern "C" int rsk_ctx_create(int device, const rsk_params *params, void *cuda_s
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if (cudaMalloc((void **)&ctx->d_tables, sizeof(float) * RSK_TABLE_FLOATS) != cudaSuccess ||
 		cudaMalloc((void **)&ctx->d_task_counter, sizeof(uint32_t)) != cudaSuccess ||
-		cudaMalloc((void **)&ctx->d_pool_cursor, sizeof(unsigned long long)) != cudaSuccess) {
+		cudaMalloc((void **)&ctx->d_pool_cursor, sizeof(unsigned long long)) != cudaSuccess ||
+		cudaMalloc((void **)&ctx->d_mu_mx, sizeof(int) * 36 * 36) != cudaSuccess ||
+		cudaMalloc((void **)&ctx->d_counters, sizeof(rsk_ctx::Counters)) != cudaSuccess) {
 		rsk_ctx_destroy(ctx);
 		return fail(RSK_ERR_NOMEM, "cudaMalloc failed in rsk_ctx_create");
 	}
@@ -319,6 +334,10 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();
 	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
 	ctx->h_rec.release(); ctx->h_pool.release(); ctx->h_idx.release();
+	ctx->keep.release(); ctx->mu_bnd.release(); ctx->c_blist.release(); ctx->c_bslot.release();
+	ctx->c_task_a.release(); ctx->c_task_begin.release(); ctx->c_task_cnt.release();
+	if (ctx->d_mu_mx) cudaFree(ctx->d_mu_mx);
+	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->d_tables) cudaFree(ctx->d_tables);
 	if (ctx->d_task_counter) cudaFree(ctx->d_task_counter);
 	if (ctx->d_pool_cursor) cudaFree(ctx->d_pool_cursor);
@@ -517,14 +536,124 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	CK(cudaMemsetAsync(ctx->d_task_counter, 0, sizeof(uint32_t), st));
 	CK(cudaMemsetAsync(ctx->d_pool_cursor, 0, sizeof(unsigned long long), st));
 
+	// ---- Mu filter (K3) + survivor compaction: only when the reference would run MuFilter (dssaligner.cpp:819-829) ----
+	const bool filter = ctx->params.omega > 0 && A->has_mu && B->has_mu;
+	uint32_t nA_b = b.a1 - b.a0;
+	CK(cudaEventRecord(ctx->ev[3], st));
+	if (filter) {
+		const uint32_t nseg = (B->d.n + kSwWarps - 1) / kSwWarps;
+		const size_t warps = (size_t)ctx->num_sms * 2 * kSwWarps;
+		const uint32_t mu_bnd_stride = ((B->maxlen + 3) & ~3u) + 4;
+		if (ctx->keep.ensure(b.npairs) || ctx->mu_bnd.ensure((size_t)mu_bnd_stride * warps)) {
+			cudaGetLastError();
+			return fail(RSK_ERR_NOMEM, "Mu filter buffers for %zu pairs", b.npairs);
+		}
+		if (b.cross && (ctx->c_blist.ensure(b.npairs) || ctx->c_bslot.ensure(b.npairs) ||
+			ctx->task_a.ensure((size_t)nA_b * nseg) || ctx->task_begin.ensure((size_t)nA_b * nseg) || ctx->task_cnt.ensure((size_t)nA_b * nseg))) {
+			cudaGetLastError();
+			return fail(RSK_ERR_NOMEM, "Mu filter task buffers for %zu pairs", b.npairs);
+		}
+		CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(rsk_ctx::Counters), st));
+		MuArgs ma;
+		memset(&ma, 0, sizeof(ma));
+		ma.muA = A->d.mu; ma.offA = A->d.off; ma.lenA = A->d.len;
+		ma.muB = B->d.mu; ma.offB = B->d.off; ma.lenB = B->d.len;
+		ma.cross = b.cross ? 1 : 0;
+		if (b.cross) {
+			ma.ntasks = nA_b * nseg; ma.a_begin = b.a0; ma.nseg = nseg; ma.nB = B->d.n;
+		} else {
+			ma.ntasks = b.ntasks;
+			ma.task_a = ctx->task_a.p; ma.task_begin = ctx->task_begin.p; ma.task_cnt = ctx->task_cnt.p;
+			ma.bslot = ctx->bslot.p;
+		}
+		ma.blist = ctx->blist.p;
+		ma.bnd = ctx->mu_bnd.p; ma.bnd_stride = mu_bnd_stride;
+		ma.rec = ctx->rec.p; ma.keep = ctx->keep.p;
+		ma.task_counter = &ctx->d_counters->mu_task_counter;
+		ma.sat_counter = &ctx->d_counters->sat_count;
+		ma.mu_mx = ctx->d_mu_mx;
+		ma.open = ctx->params.mu_gap_open; ma.ext = ctx->params.mu_gap_ext;
+		ma.omega = ctx->params.omega; ma.omega_fwd = ctx->params.omega_fwd;
+		ma.mkfl = ctx->params.mkfl;
+		int nlm = launch_mu_filter(ma, (int)std::min<uint64_t>((uint64_t)ctx->num_sms * 2, ma.ntasks), st);
+		if (nlm < 0)
+			return fail(RSK_ERR_CUDA, "Mu filter kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->stats.kernel_launches += nlm;
+		if (!b.cross) {
+			// explicit pair lists are small (PostMuFilter, -alignpair): compact the survivors on the host
+			std::vector<uint8_t> keep(b.npairs);
+			CK(cudaMemcpyAsync(keep.data(), ctx->keep.p, b.npairs, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			ctx->stats.d2h_bytes += b.npairs;
+			std::vector<uint32_t> t_a, t_begin, t_cnt, bl, bs;
+			size_t k = 0;
+			uint64_t cells = 0;
+			while (k < b.npairs) {
+				const uint32_t a0 = plan.sa[b.k0 + k];
+				const uint32_t begin = (uint32_t)bl.size();
+				uint32_t cnt = 0;
+				while (k < b.npairs && plan.sa[b.k0 + k] == a0 && cnt < (uint32_t)kSwWarps) {
+					if (keep[k]) {
+						bl.push_back(plan.sb[b.k0 + k]);
+						bs.push_back((uint32_t)k);
+						cells += (uint64_t)A->hlen[a0] * B->hlen[plan.sb[b.k0 + k]];
+						++cnt;
+					}
+					++k;
+				}
+				if (cnt) {
+					t_a.push_back(a0); t_begin.push_back(begin); t_cnt.push_back(cnt);
+				}
+			}
+			ctx->filt_explicit_pairs = bl.size();
+			ctx->filt_explicit_cells = cells;
+			ctx->filt_explicit_tasks = (uint32_t)t_a.size();
+			const size_t n = std::max<size_t>(1, bl.size()), nt = std::max<size_t>(1, t_a.size());
+			if (ctx->c_blist.ensure(n) || ctx->c_bslot.ensure(n) || ctx->c_task_a.ensure(nt) || ctx->c_task_begin.ensure(nt) || ctx->c_task_cnt.ensure(nt))
+				return fail(RSK_ERR_NOMEM, "survivor task buffers");
+			if (!bl.empty()) {
+				CK(cudaMemcpyAsync(ctx->c_blist.p, bl.data(), 4 * bl.size(), cudaMemcpyHostToDevice, st));
+				CK(cudaMemcpyAsync(ctx->c_bslot.p, bs.data(), 4 * bs.size(), cudaMemcpyHostToDevice, st));
+				CK(cudaMemcpyAsync(ctx->c_task_a.p, t_a.data(), 4 * t_a.size(), cudaMemcpyHostToDevice, st));
+				CK(cudaMemcpyAsync(ctx->c_task_begin.p, t_begin.data(), 4 * t_a.size(), cudaMemcpyHostToDevice, st));
+				CK(cudaMemcpyAsync(ctx->c_task_cnt.p, t_cnt.data(), 4 * t_a.size(), cudaMemcpyHostToDevice, st));
+				CK(cudaStreamSynchronize(st));  // the vectors die at the end of this scope
+			}
+			ctx->stats.mu_filter_in += b.npairs;
+		} else {
+		CompactArgs ca;
+		memset(&ca, 0, sizeof(ca));
+		ca.a_begin = b.a0; ca.nB = B->d.n; ca.blist = ctx->blist.p; ca.keep = ctx->keep.p;
+		ca.lenA = A->d.len; ca.lenB = B->d.len;
+		ca.out_blist = ctx->c_blist.p; ca.out_bslot = ctx->c_bslot.p;
+		ca.task_a = ctx->task_a.p; ca.task_begin = ctx->task_begin.p; ca.task_cnt = ctx->task_cnt.p;
+		ca.task_count = &ctx->d_counters->task_count;
+		ca.pair_count = &ctx->d_counters->pair_count;
+		ca.cell_count = &ctx->d_counters->cell_count;
+		nlm = launch_compact_survivors(ca, nA_b, st);
+		if (nlm < 0)
+			return fail(RSK_ERR_CUDA, "compaction kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->stats.kernel_launches += nlm;
+		ctx->stats.mu_filter_in += b.npairs;
+		}
+	}
+
 	SwArgs sa;
 	memset(&sa, 0, sizeof(sa));
 	sa.profA = A->d.prof8; sa.offA = A->d.off; sa.lenA = A->d.len;
 	sa.profB = B->d.prof8; sa.offB = B->d.off; sa.lenB = B->d.len;
 	sa.ntasks = b.ntasks;
-	sa.cross = b.cross ? 1 : 0;
+	sa.cross = (b.cross && !filter) ? 1 : 0;
 	sa.blist = ctx->blist.p;
-	if (b.cross) {
+	if (filter && b.cross) {
+		sa.task_a = ctx->task_a.p; sa.task_begin = ctx->task_begin.p; sa.task_cnt = ctx->task_cnt.p;
+		sa.blist = ctx->c_blist.p; sa.bslot = ctx->c_bslot.p;
+		sa.ntasks_dev = &ctx->d_counters->task_count;
+	} else if (filter) {
+		sa.task_a = ctx->c_task_a.p; sa.task_begin = ctx->c_task_begin.p; sa.task_cnt = ctx->c_task_cnt.p;
+		sa.blist = ctx->c_blist.p; sa.bslot = ctx->c_bslot.p;
+		sa.ntasks = ctx->filt_explicit_tasks;
+	} else if (b.cross) {
 		sa.a_begin = b.a0;
 		sa.nB = B->d.n;
 		sa.nseg = (B->d.n + kSwWarps - 1) / kSwWarps;
@@ -542,7 +671,9 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	sa.open = ctx->params.gap_open; sa.ext = ctx->params.gap_ext;
 
 	CK(cudaEventRecord(ctx->ev[0], st));
-	int nl = launch_sw(sa, std::min<int>(grid, (int)b.ntasks), sw_smem_bytes(), st);
+	int nl = 0;
+	if (!(filter && !b.cross && ctx->filt_explicit_tasks == 0))
+		nl = launch_sw(sa, (filter && b.cross) ? grid : std::min<int>(grid, (int)sa.ntasks), sw_smem_bytes(), st);
 	if (nl < 0)
 		return fail(RSK_ERR_CUDA, "SW kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 	ctx->stats.kernel_launches += nl;
@@ -570,14 +701,32 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		ctx->stats.kernel_launches += nl;
 	}
 	CK(cudaEventRecord(ctx->ev[2], st));
-	ctx->stats.sw_pairs += b.npairs;
-	ctx->stats.sw_cells += b.cells;
+	if (!filter) {
+		ctx->stats.sw_pairs += b.npairs;
+		ctx->stats.sw_cells += b.cells;
+	}
+	ctx->batch_filtered = filter;
+	ctx->batch_cross = b.cross;
 	return RSK_OK;
 }
 
 int finish_batch_timing(rsk_ctx *ctx)
 {
 	float ms = 0;
+	if (ctx->batch_filtered) {
+		rsk_ctx::Counters c;
+		CK(cudaMemcpy(&c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+		if (ctx->batch_cross) {
+			ctx->stats.sw_pairs += c.pair_count;
+			ctx->stats.sw_cells += c.cell_count;
+		} else {
+			ctx->stats.sw_pairs += ctx->filt_explicit_pairs;
+			ctx->stats.sw_cells += ctx->filt_explicit_cells;
+		}
+		ctx->stats.mu_saturated += c.sat_count;
+		CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[0]));
+		ctx->stats.mu_kernel_ms += ms;
+	}
 	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
 	ctx->stats.sw_kernel_ms += ms;
 	CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
@@ -590,7 +739,8 @@ void fill_hit(const rsk_params &P, const PairRec &r, uint32_t a, uint32_t b, uin
 	h.a = a; h.b = b;
 	h.score = r.score;
 	h.lo_a = r.lo_a; h.lo_b = r.lo_b;
-	h.mu_score = 0; h.mu_fwd = r.mu_fwd; h.mu_rev = r.mu_rev;
+	h.mu_fwd = r.mu_fwd; h.mu_rev = r.mu_rev;
+	h.mu_score = (r.mu_fwd != 0 && !((float)r.mu_fwd < P.omega_fwd)) ? (float)r.mu_fwd - (float)r.mu_rev : 0.0f;
 	h.flags = r.flags;
 	h.path_len = r.path_len;
 	h.path_off = pool_base + r.path_off;
@@ -784,6 +934,8 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 				++S.evalue_pairs;
 			if (h.flags & RSK_HIT_REPORTED)
 				++S.hits;
+			if (h.flags & RSK_HIT_MU_REJECTED)
+				++S.mu_filter_rejected;
 			if (opts.keep == RSK_KEEP_ALL)
 				res->hits[orig] = h;
 			else if (h.flags & RSK_HIT_REPORTED)

@@ -74,6 +74,7 @@ struct SwArgs {
 	const uint32_t *task_cnt;    // explicit mode [ntasks] 1..kSwWarps
 	const uint32_t *blist;       // B chain indices
 	const uint32_t *bslot;       // explicit mode: record slot of each blist entry; cross: slot = (a-a_begin)*nB + b
+	const uint32_t *ntasks_dev;  // when non-null the task count is read from device memory (filter -> SW hand-off)
 	// scratch (per warp of the grid)
 	uint4 *trace; uint64_t trace_stride;   // uint4 units per warp
 	float2 *bnd; uint32_t bnd_stride;      // pass-boundary row (M, D) per column
@@ -98,10 +99,45 @@ struct LddtArgs {
 	uint32_t maxcols;
 };
 
+// K3: Mu int8 SW filter over the full A x B rectangle of a batch
+struct MuArgs {
+	const uint8_t *muA; const uint64_t *offA; const uint32_t *lenA;
+	const uint8_t *muB; const uint64_t *offB; const uint32_t *lenB;
+	uint32_t ntasks, a_begin, nseg, nB;
+	uint32_t cross;             // 1: rectangle tasks (see SwArgs); 0: explicit task arrays below
+	const uint32_t *task_a, *task_begin, *task_cnt, *bslot;
+	const uint32_t *blist;      // B indices sorted by length
+	int2 *bnd; uint32_t bnd_stride;
+	PairRec *rec;
+	uint8_t *keep;              // [batch pairs] 1 = passes the filter
+	uint32_t *task_counter;
+	uint32_t *sat_counter;
+	const int *mu_mx;           // IntScoreMx_Mu as int32 [36*36]
+	int open, ext;
+	float omega, omega_fwd;
+	uint32_t mkfl;              // pairs with LA >= mkfl or LB >= mkfl belong to the k-mer/x-drop path (dssaligner.cpp:715-732)
+};
+
+// survivor compaction: keep flags -> SW tasks (explicit-mode arrays of SwArgs)
+struct CompactArgs {
+	uint32_t a_begin, nB;
+	const uint32_t *blist;
+	const uint8_t *keep;
+	const uint32_t *lenA; const uint32_t *lenB;
+	uint32_t *out_blist, *out_bslot;   // [nA_batch * nB]
+	uint32_t *task_a, *task_begin, *task_cnt;
+	uint32_t *task_count;              // device counters
+	unsigned long long *pair_count;
+	unsigned long long *cell_count;
+};
+
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_sw(const SwArgs &args, int grid, size_t smem, cudaStream_t stream);
 size_t sw_smem_bytes();
 int launch_lddt(const LddtArgs &args, cudaStream_t stream);
+int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);
+size_t mu_smem_bytes();
+int launch_compact_survivors(const CompactArgs &args, uint32_t nA, cudaStream_t stream);
 int launch_pack_profiles(const uint8_t *planes, uint64_t total, uint64_t *prof8, cudaStream_t stream);
 
 }  // namespace rsk

@@ -311,13 +311,14 @@ __global__ void __launch_bounds__(kSwThreads, 1) sw_affine_f32_tb_kernel(const S
 	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += kSwThreads)
 		tab[k] = a.tables[k];
 	__syncthreads();
+	const uint32_t ntasks = a.ntasks_dev ? *a.ntasks_dev : a.ntasks;
 	for (;;) {
 		if (threadIdx.x == 0)
 			bcast[0] = (int)atomicAdd(a.task_counter, 1u);
 		__syncthreads();
 		const uint32_t task = (uint32_t)bcast[0];
 		__syncthreads();
-		if (task >= a.ntasks)
+		if (task >= ntasks)
 			break;
 		uint32_t ai, begin, cnt, slot_base = 0;
 		if (a.cross) {

@@ -12,7 +12,7 @@ NFEAT = 8
 TABLE_FLOATS = 2192
 MODE_FAST, MODE_SENSITIVE, MODE_VERYSENSITIVE = 1, 2, 3
 KEEP_HITS, KEEP_ALL = 0, 1
-HIT_MU_REJECTED, HIT_HAS_EVALUE, HIT_REPORTED = 1, 2, 4
+HIT_MU_REJECTED, HIT_HAS_EVALUE, HIT_REPORTED, HIT_MKF_PENDING = 1, 2, 4, 8
 FLT_MAX = float(np.finfo(np.float32).max)
 
 

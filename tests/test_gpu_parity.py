@@ -56,6 +56,73 @@ def test_explicit_pairs_and_self(rb, port):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", [2, 1])
+def test_cross_with_mu_filter_matches_oracle(rb, port, mode):
+    """-sensitive / -fast: Mu int8 SW filter (fwd, reversed, 777/255 saturation rules) -> survivors -> SW."""
+    from reseek_b200 import synth
+    from tests.util import to_oracle_chains
+    a = synth.make_chains(40, 150, seed=900 + mode, length_jitter=0.5)
+    b = synth.make_chains(23, 170, seed=950 + mode, length_jitter=0.5)
+    synth.plant_homologs(a, b, 0.5, seed=77, sub=0.15)   # close homologs: int8 saturation on the forward pass
+    synth.plant_homologs(a, b, 0.3, seed=78, sub=0.45)   # remote ones: around the omega thresholds
+    ctx = rb.Context(0, mode)
+    A = ctx.upload(a.lens, a.prof, a.mu, a.xyz, a.selfrev)
+    B = ctx.upload(b.lens, b.prof, b.mu, b.xyz, b.selfrev)
+    res = ctx.search_cross(A, B, keep=rb.KEEP_ALL, want_paths=True)
+    st = ctx.stats()
+    assert len(res.hits) == a.n * b.n
+    _check_all(rb, port(mode), res, to_oracle_chains(a), to_oracle_chains(b))
+    nrej = int(np.sum((res.hits["flags"] & rb.HIT_MU_REJECTED) != 0))
+    assert 0 < nrej < len(res.hits), "the test must exercise both outcomes of the filter"
+    assert st["mu_filter_in"] == len(res.hits) and st["mu_filter_rejected"] == nrej
+    assert st["mu_saturated"] == int(np.sum(res.hits["mu_fwd"] == 777)) > 0
+    assert st["sw_pairs"] == len(res.hits) - nrej
+    # the same pairs as an explicit list (PostMuFilter-style) must give identical records
+    ia = np.repeat(np.arange(a.n, dtype=np.uint32), b.n)
+    ib = np.tile(np.arange(b.n, dtype=np.uint32), a.n)
+    res2 = ctx.search_pairs(A, B, ia, ib, keep=rb.KEEP_ALL, want_paths=True)
+    for k in ("score", "lo_a", "lo_b", "hi_a", "hi_b", "ids", "gaps", "ts", "evalue", "mu_fwd", "mu_rev", "flags", "path_len"):
+        assert np.array_equal(res.hits[k], res2.hits[k]), k
+    # KEEP_HITS returns exactly the reported subset
+    res3 = ctx.search_cross(A, B, keep=rb.KEEP_HITS, want_paths=True)
+    rep = res.hits[(res.hits["flags"] & rb.HIT_REPORTED) != 0]
+    assert len(res3.hits) == len(rep) and np.array_equal(np.sort(res3.hits["score"]), np.sort(rep["score"]))
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", [3, 2, 1])
+def test_golden_reference_fixtures_on_gpu(rb, mode):
+    """Real chains (test_data/q100.bca, scop40.bca) with the reference's own answers (tests/golden)."""
+    from tests.golden_util import load_chains, load_pairs
+    from tests.util import bits
+    g = load_pairs(mode)
+    chains = load_chains(g["selfrev"])
+    ctx = rb.Context(0, mode)
+    if mode == 3:  # -verysensitive never loads Mu letters (dbsearcher.cpp:251-252)
+        for c in chains:
+            c.mu = None
+    S = ctx.upload_chains(chains)
+    res = ctx.search_cross(S, S, keep=rb.KEEP_ALL, want_paths=True)
+    n = 0
+    for k, h in enumerate(res.hits):
+        assert (int(h["a"]), int(h["b"])) == (int(g["a"][k]), int(g["b"][k]))
+        if g["mkf"][k]:
+            assert int(h["flags"]) & rb.HIT_MKF_PENDING, "DoMKF pairs must be flagged, not silently mis-aligned"
+            continue
+        n += 1
+        assert res.path(k) == g["path_list"][k], f"pair {k} path"
+        assert bits(h["score"]) == bits(g["score"][k]), f"pair {k} score"
+        assert (int(h["hi_a"]), int(h["hi_b"]), int(h["ids"]), int(h["gaps"])) == (int(g["hi_a"][k]), int(g["hi_b"][k]), int(g["ids"][k]), int(g["gaps"][k]))
+        assert bits(h["ts"]) == bits(g["ts"][k]), f"pair {k} ts"
+        assert bits(h["evalue"]) == bits(g["evalue"][k]) and bits(h["pvalue"]) == bits(g["pvalue"][k]), f"pair {k} E/P"
+        if res.path(k):
+            assert (int(h["lo_a"]), int(h["lo_b"])) == (int(g["lo_a"][k]), int(g["lo_b"][k]))
+        if g["evalue"][k] < 1e38:
+            assert bits(h["lddt"]) == bits(g["lddt"][k]) and bits(h["qual"]) == bits(g["qual"][k])
+    assert n > 150
+    ctx.close()
+
+
 def test_smoke_entry(rb):
     import __graft_entry__ as g
     g.smoke()
