@@ -8,7 +8,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <numeric>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -136,9 +138,9 @@ struct rsk_ctx {
 	size_t filt_explicit_pairs = 0; uint64_t filt_explicit_cells = 0; uint32_t filt_explicit_tasks = 0; bool batch_cross = true;
 	struct Counters { uint32_t task_count, sat_count, mu_task_counter, pad; unsigned long long pair_count, cell_count; };
 	Counters *d_counters = nullptr;
-	PinBuf<PairRec> h_rec;
-	PinBuf<uint8_t> h_pool;
-	PinBuf<uint32_t> h_idx;
+	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU
+	PinBuf<uint8_t> h_pool[2];
+	int host_threads = 1;
 	rsk_stats stats;
 	bool batch_filtered = false;
 	size_t max_batch_pairs = 2u << 20;
@@ -146,8 +148,15 @@ struct rsk_ctx {
 };
 
 struct rsk_results {
-	std::vector<rsk_hit> hits;
-	std::vector<char> paths;
+	rsk_hit *hits = nullptr;   // malloc'ed, never value-initialised (filled by the conversion workers)
+	uint64_t nhits = 0;
+	char *paths = nullptr;
+	uint64_t npath = 0;
+	~rsk_results()
+	{
+		free(hits);
+		free(paths);
+	}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -310,6 +319,12 @@ extern "C" int rsk_ctx_create(int device, const rsk_params *params, void *cuda_s
 	}
 	for (auto &e : ctx->ev)
 		cudaEventCreate(&e);
+	ctx->host_threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+	if (const char *s = getenv("RSK_HOST_THREADS")) {
+		const int v = atoi(s);
+		if (v > 0)
+			ctx->host_threads = v;
+	}
 	if (const char *s = getenv("RSK_BATCH_PAIRS")) {
 		const long long v = atoll(s);
 		if (v > 0)
@@ -333,7 +348,7 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->trace.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
 	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();
 	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
-	ctx->h_rec.release(); ctx->h_pool.release(); ctx->h_idx.release();
+	ctx->h_rec[0].release(); ctx->h_rec[1].release(); ctx->h_pool[0].release(); ctx->h_pool[1].release();
 	ctx->keep.release(); ctx->mu_bnd.release(); ctx->c_blist.release(); ctx->c_bslot.release();
 	ctx->c_task_a.release(); ctx->c_task_begin.release(); ctx->c_task_cnt.release();
 	if (ctx->d_mu_mx) cudaFree(ctx->d_mu_mx);
@@ -373,7 +388,7 @@ extern "C" void rsk_chainset_free(rsk_chainset *cs)
 		return;
 	cudaSetDevice(cs->device);
 	DevChains &d = cs->d;
-	cudaFree(d.len); cudaFree(d.off); cudaFree(d.prof8); cudaFree(d.mu);
+	cudaFree(d.len); cudaFree(d.off); cudaFree(d.prof8); cudaFree(d.mu); cudaFree(d.coloff);
 	cudaFree(d.x); cudaFree(d.y); cudaFree(d.z); cudaFree(d.selfrev);
 	delete cs;
 }
@@ -501,7 +516,7 @@ int ensure_scratch(rsk_ctx *ctx, uint32_t maxLA, uint32_t maxLB, int &grid, uint
 	sw_geometry(maxLA, npass, R);
 	// every pair of the batch has npass(LA) <= npass(maxLA) and LBpad <= maxLBpad
 	const uint64_t lbpad = ((uint64_t)maxLB + 3) & ~3ull;
-	trace_stride = (uint64_t)npass * (lbpad / 4) * 32;  // uint4 units
+	trace_stride = sw_trace_units(npass, maxLB);  // uint4 units
 	bnd_stride = (uint32_t)lbpad + 4;
 	stage_stride = ((maxLA + maxLB + 16) + 15) & ~15u;
 	const uint64_t per_cta = (trace_stride * 16 + (uint64_t)bnd_stride * 8 + stage_stride) * kSwWarps;
@@ -641,7 +656,19 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	SwArgs sa;
 	memset(&sa, 0, sizeof(sa));
 	sa.profA = A->d.prof8; sa.offA = A->d.off; sa.lenA = A->d.len;
-	sa.profB = B->d.prof8; sa.offB = B->d.off; sa.lenB = B->d.len;
+	if (!B->d.coloff) {
+		// first use of this set as the column side: derive the per-residue table offsets (32 B/residue)
+		rsk_chainset *Bm = const_cast<rsk_chainset *>(B);
+		if (cudaMalloc((void **)&Bm->d.coloff, (size_t)B->d.total * 32) != cudaSuccess) {
+			cudaGetLastError();
+			return fail(RSK_ERR_NOMEM, "column-offset table for %llu residues", (unsigned long long)B->d.total);
+		}
+		int nlc = launch_make_coloff(B->d.prof8, B->d.total, Bm->d.coloff, st);
+		if (nlc < 0)
+			return fail(RSK_ERR_CUDA, "make_coloff launch failed");
+		ctx->stats.kernel_launches += nlc;
+	}
+	sa.coloffB = B->d.coloff; sa.offB = B->d.off; sa.lenB = B->d.len;
 	sa.ntasks = b.ntasks;
 	sa.cross = (b.cross && !filter) ? 1 : 0;
 	sa.blist = ctx->blist.p;
@@ -837,15 +864,66 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 	S.pairs = plan.npairs;
 
 	rsk_results *res = nullptr;
+	const bool keep_all = opts.keep == RSK_KEEP_ALL;
 	if (!device_only) {
 		res = new rsk_results();
-		if (opts.keep == RSK_KEEP_ALL)
-			res->hits.resize(plan.npairs);
+		if (keep_all) {
+			res->hits = (rsk_hit *)malloc(std::max<uint64_t>(1, plan.npairs) * sizeof(rsk_hit));
+			if (!res->hits) {
+				delete res;
+				return fail(RSK_ERR_NOMEM, "host memory for %llu hit records", (unsigned long long)plan.npairs);
+			}
+			res->nhits = plan.npairs;
+		}
 	}
 
+	// Host conversion jobs (PairRec -> rsk_hit incl. the libm P/E/Qual of statsig.cpp) run on worker threads while the
+	// next batch occupies the GPU.  Hits of RSK_KEEP_HITS and the path bytes are collected as chunks and concatenated once.
+	struct Job {
+		std::vector<std::thread> threads;
+		std::vector<std::vector<rsk_hit>> kept;  // per thread (KEEP_HITS)
+		std::vector<uint64_t> n_eval, n_hit, n_rej;
+		char *paths = nullptr;
+		uint64_t npath = 0;
+		bool active = false;
+	};
+	Job jobs[2];
+	std::vector<std::vector<rsk_hit>> hit_chunks;
+	std::vector<std::pair<char *, uint64_t>> path_chunks;
+	auto wait_job = [&](Job &J) {
+		if (!J.active)
+			return;
+		for (auto &t : J.threads)
+			t.join();
+		J.threads.clear();
+		for (size_t t = 0; t < J.n_eval.size(); ++t) {
+			S.evalue_pairs += J.n_eval[t];
+			S.hits += J.n_hit[t];
+			S.mu_filter_rejected += J.n_rej[t];
+		}
+		if (!keep_all)
+			for (auto &v : J.kept)
+				hit_chunks.push_back(std::move(v));
+		J.kept.clear();
+		if (J.paths)
+			path_chunks.push_back({J.paths, J.npath});
+		J.paths = nullptr;
+		J.active = false;
+	};
+	auto abort_all = [&]() {
+		wait_job(jobs[0]);
+		wait_job(jobs[1]);
+		for (auto &pc : path_chunks)
+			free(pc.first);
+		delete res;
+	};
+
 	std::vector<uint32_t> t_a, t_begin, t_cnt, slots;
+	uint64_t pool_total = 0;
+	size_t bi = 0;
 	for (const Batch &b0 : batches) {
 		Batch b = b0;
+		const int buf = (int)(bi++ & 1);
 		if (!b.cross) {
 			// build tasks for sorted pairs [k0,k1): runs of equal A, chunks of kSwWarps
 			t_a.clear(); t_begin.clear(); t_cnt.clear();
@@ -865,8 +943,10 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			}
 			b.ntasks = (uint32_t)t_a.size();
 			if (ctx->blist.ensure(n) || ctx->bslot.ensure(n) || ctx->pair_a.ensure(n) || ctx->pair_b.ensure(n) ||
-				ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks))
+				ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks)) {
+				abort_all();
 				return fail(RSK_ERR_NOMEM, "task buffers");
+			}
 			CK(cudaMemcpyAsync(ctx->blist.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
 			CK(cudaMemcpyAsync(ctx->bslot.p, slots.data(), 4 * n, cudaMemcpyHostToDevice, st));
 			CK(cudaMemcpyAsync(ctx->pair_a.p, plan.sa.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
@@ -878,7 +958,8 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		}
 		int rc = run_batch(ctx, plan, b, opts);
 		if (rc) {
-			delete res;
+			if (!device_only)
+				abort_all();
 			return rc;
 		}
 		if (device_only) {
@@ -888,58 +969,130 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 				return rc;
 			continue;
 		}
+		// the GPU is busy with this batch: now make sure the host buffer we are about to overwrite is free
+		Job &J = jobs[buf];
+		wait_job(J);
 		// ---- D2H: records (+ paths) of this batch ----
-		if (ctx->h_rec.ensure(b.npairs)) {
-			delete res;
+		if (ctx->h_rec[buf].ensure(b.npairs)) {
+			abort_all();
 			return fail(RSK_ERR_NOMEM, "pinned record buffer");
 		}
 		unsigned long long pool_used = 0;
-		CK(cudaMemcpyAsync(ctx->h_rec.p, ctx->rec.p, b.npairs * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(ctx->h_rec[buf].p, ctx->rec.p, b.npairs * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(&pool_used, ctx->d_pool_cursor, sizeof(pool_used), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 		S.d2h_bytes += b.npairs * sizeof(PairRec) + 8;
-		const uint64_t pool_base = res->paths.size();
-		if (opts.want_paths && pool_used > 0) {
-			if (ctx->h_pool.ensure(pool_used)) {
-				delete res;
+		const uint64_t pool_base = pool_total;
+		const bool copy_paths = opts.want_paths && pool_used > 0;
+		if (copy_paths) {
+			if (ctx->h_pool[buf].ensure(pool_used)) {
+				abort_all();
 				return fail(RSK_ERR_NOMEM, "pinned path buffer");
 			}
-			CK(cudaMemcpyAsync(ctx->h_pool.p, ctx->pool.p, pool_used, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(ctx->h_pool[buf].p, ctx->pool.p, pool_used, cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
-			res->paths.insert(res->paths.end(), (const char *)ctx->h_pool.p, (const char *)ctx->h_pool.p + pool_used);
 			S.d2h_bytes += pool_used;
+			pool_total += pool_used;
 		}
 		rc = finish_batch_timing(ctx);
 		if (rc) {
-			delete res;
+			abort_all();
 			return rc;
 		}
-		// ---- records -> rsk_hit ----
+		// ---- records -> rsk_hit on worker threads (overlaps the next batch's kernels) ----
+		const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->host_threads, b.npairs / 4096 + 1));
+		J.active = true;
+		J.kept.assign(T, {});
+		J.n_eval.assign(T, 0); J.n_hit.assign(T, 0); J.n_rej.assign(T, 0);
+		J.npath = copy_paths ? pool_used : 0;
+		J.paths = copy_paths ? (char *)malloc(pool_used) : nullptr;
+		const PairRec *hrec = ctx->h_rec[buf].p;
+		const uint8_t *hpool = ctx->h_pool[buf].p;
+		const rsk_params *P = &ctx->params;
 		const uint32_t nB = B->d.n;
-		for (size_t k = 0; k < b.npairs; ++k) {
-			uint32_t a, bb;
-			uint64_t orig;
-			if (b.cross) {
-				a = b.a0 + (uint32_t)(k / nB);
-				bb = (uint32_t)(k % nB);
-				orig = (uint64_t)a * nB + bb;
-			} else {
-				a = plan.sa[b.k0 + k];
-				bb = plan.sb[b.k0 + k];
-				orig = plan.perm[b.k0 + k];
+		rsk_hit *all = keep_all ? res->hits : nullptr;
+		const SearchPlan *pl = &plan;
+		for (int t = 0; t < T; ++t) {
+			J.threads.emplace_back([=, &J]() {
+				const size_t k0 = b.npairs * (size_t)t / T, k1 = b.npairs * (size_t)(t + 1) / T;
+				if (J.paths) {  // path bytes: each worker copies its share of the pinned pool
+					const uint64_t p0 = J.npath * (uint64_t)t / T, p1 = J.npath * (uint64_t)(t + 1) / T;
+					memcpy(J.paths + p0, hpool + p0, p1 - p0);
+				}
+				uint64_t ne = 0, nh = 0, nr = 0;
+				std::vector<rsk_hit> &kept = J.kept[t];
+				for (size_t k = k0; k < k1; ++k) {
+					uint32_t a, bb;
+					uint64_t orig;
+					if (b.cross) {
+						a = b.a0 + (uint32_t)(k / nB);
+						bb = (uint32_t)(k % nB);
+						orig = (uint64_t)a * nB + bb;
+					} else {
+						a = pl->sa[b.k0 + k];
+						bb = pl->sb[b.k0 + k];
+						orig = pl->perm[b.k0 + k];
+					}
+					rsk_hit h;
+					fill_hit(*P, hrec[k], a, bb, pool_base, h);
+					ne += (h.flags & RSK_HIT_HAS_EVALUE) != 0;
+					nh += (h.flags & RSK_HIT_REPORTED) != 0;
+					nr += (h.flags & RSK_HIT_MU_REJECTED) != 0;
+					if (all)
+						all[orig] = h;
+					else if (h.flags & RSK_HIT_REPORTED)
+						kept.push_back(h);
+				}
+				J.n_eval[t] = ne; J.n_hit[t] = nh; J.n_rej[t] = nr;
+			});
+		}
+	}
+	if (!device_only) {
+		// explicit-mode KEEP_HITS chunks arrive in sorted-pair order; cross-mode chunks in (a, b) order
+		wait_job(jobs[bi & 1]);
+		wait_job(jobs[(bi + 1) & 1]);
+		if (!keep_all) {
+			uint64_t n = 0;
+			for (auto &c : hit_chunks)
+				n += c.size();
+			res->hits = (rsk_hit *)malloc(std::max<uint64_t>(1, n) * sizeof(rsk_hit));
+			res->nhits = n;
+			if (!res->hits) {
+				abort_all();
+				return fail(RSK_ERR_NOMEM, "host memory for %llu hits", (unsigned long long)n);
 			}
-			rsk_hit h;
-			fill_hit(ctx->params, ctx->h_rec.p[k], a, bb, pool_base, h);
-			if (h.flags & RSK_HIT_HAS_EVALUE)
-				++S.evalue_pairs;
-			if (h.flags & RSK_HIT_REPORTED)
-				++S.hits;
-			if (h.flags & RSK_HIT_MU_REJECTED)
-				++S.mu_filter_rejected;
-			if (opts.keep == RSK_KEEP_ALL)
-				res->hits[orig] = h;
-			else if (h.flags & RSK_HIT_REPORTED)
-				res->hits.push_back(h);
+			std::vector<std::thread> cp;
+			uint64_t off = 0;
+			for (auto &c : hit_chunks) {
+				if (!c.empty()) {
+					rsk_hit *dst = res->hits + off;
+					const std::vector<rsk_hit> *src = &c;
+					cp.emplace_back([dst, src]() { memcpy(dst, src->data(), src->size() * sizeof(rsk_hit)); });
+					if ((int)cp.size() >= ctx->host_threads) {
+						for (auto &t : cp) t.join();
+						cp.clear();
+					}
+				}
+				off += c.size();
+			}
+			for (auto &t : cp) t.join();
+		}
+		uint64_t np = 0;
+		for (auto &pc : path_chunks)
+			np += pc.second;
+		if (np) {
+			if (path_chunks.size() == 1) {
+				res->paths = path_chunks[0].first;
+			} else {
+				res->paths = (char *)malloc(np);
+				uint64_t off = 0;
+				for (auto &pc : path_chunks) {
+					memcpy(res->paths + off, pc.first, pc.second);
+					off += pc.second;
+					free(pc.first);
+				}
+			}
+			res->npath = np;
 		}
 	}
 	CK(cudaEventRecord(ctx->ev[7], st));
@@ -1036,8 +1189,8 @@ extern "C" int rsk_search_self(rsk_ctx *ctx, const rsk_chainset *Sx, const rsk_s
 // ------------------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------------------
-extern "C" uint64_t rsk_results_count(const rsk_results *r) { return r ? r->hits.size() : 0; }
-extern "C" const rsk_hit *rsk_results_hits(const rsk_results *r) { return (r && !r->hits.empty()) ? r->hits.data() : nullptr; }
-extern "C" const char *rsk_results_paths(const rsk_results *r) { return (r && !r->paths.empty()) ? r->paths.data() : nullptr; }
-extern "C" uint64_t rsk_results_paths_bytes(const rsk_results *r) { return r ? r->paths.size() : 0; }
+extern "C" uint64_t rsk_results_count(const rsk_results *r) { return r ? r->nhits : 0; }
+extern "C" const rsk_hit *rsk_results_hits(const rsk_results *r) { return (r && r->nhits) ? r->hits : nullptr; }
+extern "C" const char *rsk_results_paths(const rsk_results *r) { return (r && r->npath) ? r->paths : nullptr; }
+extern "C" uint64_t rsk_results_paths_bytes(const rsk_results *r) { return r ? r->npath : 0; }
 extern "C" void rsk_results_free(rsk_results *r) { delete r; }

@@ -26,6 +26,7 @@ struct DevChains {
 	uint32_t *len = nullptr;    // [n]
 	uint64_t *off = nullptr;    // [n] residue offset of each chain
 	uint64_t *prof8 = nullptr;  // [total] 8 e-letter bytes per residue (byte f = feature f)
+	uint4 *coloff = nullptr;    // [2*total] per-residue row-table offsets (made on first use as the column side)
 	uint8_t *mu = nullptr;      // [total] or null
 	float *x = nullptr, *y = nullptr, *z = nullptr;  // [total] each
 	float *selfrev = nullptr;   // [n]
@@ -62,7 +63,7 @@ __host__ __device__ inline void sw_geometry(uint32_t LA, int &npass, int &R)
 struct SwArgs {
 	// chains
 	const uint64_t *profA; const uint64_t *offA; const uint32_t *lenA;
-	const uint64_t *profB; const uint64_t *offB; const uint32_t *lenB;
+	const uint4 *coloffB; const uint64_t *offB; const uint32_t *lenB;
 	// tasks: one task = one A chain x up to kSwWarps B chains
 	uint32_t ntasks;
 	uint32_t cross;          // 1: task t -> a = a_begin + t / nseg, B's = blist[(t % nseg)*kSwWarps ...]
@@ -134,6 +135,8 @@ struct CompactArgs {
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_sw(const SwArgs &args, int grid, size_t smem, cudaStream_t stream);
 size_t sw_smem_bytes();
+uint64_t sw_trace_units(int npass, uint32_t LB);
+int launch_make_coloff(const uint64_t *prof8, uint64_t total, uint4 *coloff, cudaStream_t stream);
 int launch_lddt(const LddtArgs &args, cudaStream_t stream);
 int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);
 size_t mu_smem_bytes();

@@ -7,18 +7,24 @@
 //
 // Design (B200, sm_100a):
 //  * The score matrix S is never materialised.  For the CTA's A chain a "row table" is staged in shared
-//    memory: T[e][h][lane][q] = tab_f[a_f(row)][b] for every (feature,letter) code e = 0..131 and every row
-//    of the current pass, laid out so that lane L's 16-byte vector lives in bank group L%8: one conflict-free
-//    LDS.128 returns a feature's score for 4 consecutive rows.  The B chain supplies one 8-byte column code
-//    per DP column (pre-offset "e-letters"), so a cell's score is 8 table reads + 7 fp32 adds in the
-//    reference's summation order.
+//    memory for the current pass of 32*R rows: plane 0 holds rows 0..3 of every lane as float4
+//    P0[e][lane], plane 1 rows 4..R-1 as float/float2/float4 P1[e][lane], e = (feature,letter) code 0..131,
+//    both with a 512-byte stride per code.  A lane's vector sits in its own bank group, so every LDS is
+//    conflict-free.  The B chain supplies, per DP column, 8 ready-made table offsets (32 bytes, prepared
+//    once per chain set), so a cell's score costs 8 table reads + 7 fp32 adds in the reference's order.
 //  * DP wavefront: lane L owns R consecutive rows (R = 1..8), lanes are skewed by one column per step, the
 //    last row's (M,D) travels to the next lane by warp shuffle.  A chain longer than 32*R rows is cut into
 //    passes; the bottom row of a pass is parked in a small global (L2-resident) boundary buffer.
-//  * Traceback bits: 4 bits per cell (2 bits match-source, MD, MI), 8 rows -> one 32-bit word per lane and
-//    column, 4 columns -> one 16-byte store.  The buffer is per-warp scratch that is re-used pair after pair,
-//    so it stays in the 126 MB L2; the in-kernel traceback reads it back through a 2 KB shared-memory tile.
+//    Steps whose 32 lanes are all inside the matrix run a predicate-free body (the steady state).
+//  * Traceback bits: 4 bits per cell (2 bits match-source, MD, MI) -> one 32-bit word per lane and step,
+//    four steps -> one fully coalesced 16-byte store per lane ("step-major", i.e. anti-diagonal, layout).
+//    The in-kernel traceback reads it back through a 2 KB shared-memory tile.
+//  * The running maximum is tracked per lane with one FMNMX3 chain per step; the exact first-maximum rule of
+//    the reference (row-major order, strict >) is restored in a rarely taken slow path and in the final
+//    (score desc, row asc) warp reduction.
 //  * Persistent CTAs (one per SM) pull tasks from an atomic counter.
+#include <type_traits>
+
 #include "rsk_internal.cuh"
 
 namespace rsk {
@@ -29,17 +35,25 @@ constexpr int kNLet = RSK_NLETTERS;
 constexpr unsigned kFull = 0xffffffffu;
 
 // shared memory carve-up
-constexpr size_t kSmemTab = 0;                                        // float[2192]
-constexpr size_t kSmemRowTab = 8768;                                  // float4[132*2*32]
-constexpr size_t kSmemTiles = kSmemRowTab + (size_t)kNLet * 2 * 32 * 16;  // uint4[kSwWarps][4][32]
+constexpr size_t kSmemTab = 0;                          // float[2192] weighted tables
+constexpr size_t kSmemP0 = 8768;                        // plane 0: float4[132][32], rows 0..3 of each lane
+constexpr size_t kPlaneBytes = (size_t)kNLet * 512;     // 67584
+constexpr size_t kSmemP1 = kSmemP0 + kPlaneBytes;       // plane 1: rows 4..R-1, same 512-byte stride per code
+constexpr size_t kSmemTiles = kSmemP1 + kPlaneBytes;    // uint4[kSwWarps][4][32] traceback tiles
 constexpr size_t kSmemBcast = kSmemTiles + (size_t)kSwWarps * 4 * 32 * 16;
 constexpr size_t kSmemTotal = kSmemBcast + 16;
 
+// floats per lane in plane 1 for R rows per lane (R-4 rounded up to a vector width)
+__host__ __device__ constexpr int plane1_width(int R) { return R <= 4 ? 0 : R == 5 ? 1 : R == 6 ? 2 : 4; }
+
+// table value of rows beyond the end of the chain: such cells are hugely negative and can never be a maximum
+constexpr float kPadScore = -1e30f;
+
 template <int R>
-__device__ __forceinline__ void build_rowtab(float *rt, const float *tab, const uint64_t *__restrict__ profA,
+__device__ __forceinline__ void build_rowtab(float *p0, float *p1, const float *tab, const uint64_t *__restrict__ profA,
 		uint32_t LA, int pass)
 {
-	constexpr int NH = (R + 3) / 4;
+	constexpr int W1 = plane1_width(R);
 	constexpr int ROWS = 32 * R;
 	const uint32_t rowbase = (uint32_t)pass * ROWS;
 	for (int idx = threadIdx.x; idx < kNLet * ROWS; idx += kSwThreads) {
@@ -48,7 +62,7 @@ __device__ __forceinline__ void build_rowtab(float *rt, const float *tab, const 
 		const int l = rr / R;
 		const int r = rr - l * R;
 		const uint32_t row = rowbase + rr;
-		float v = 0.0f;
+		float v = kPadScore;
 		if (row < LA) {
 			const int f = e < 20 ? 0 : 1 + ((e - 20) >> 4);
 			const int b = e - feat_base(f);
@@ -56,75 +70,109 @@ __device__ __forceinline__ void build_rowtab(float *rt, const float *tab, const 
 			const int a = (int)((pa >> (8 * f)) & 0xff) - feat_base(f);
 			v = tab[feat_table_off(f) + a * feat_alpha(f) + b];
 		}
-		rt[((e * NH + (r >> 2)) * 32 + l) * 4 + (r & 3)] = v;
+		if (r < 4)
+			p0[e * 128 + l * 4 + r] = v;
+		else
+			p1[e * 128 + l * W1 + (r - 4)] = v;
 	}
 }
 
-__device__ __forceinline__ float pick4(const float4 &v, int q)
+__device__ __forceinline__ float lds_f32(uint32_t addr)
 {
-	return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w;
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
+{
+	float2 v;
+	asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
 }
 
 // One pass: rows [pass*32R, (pass+1)*32R) of A against all LB columns of B.
+// colB: two uint4 per column = the column's 8 table offsets in units of 16 bytes (code * 32).
 template <int R>
-__device__ __forceinline__ void sw_pass(const float4 *__restrict__ rowtab, const int lane, const int pass,
-		const int npass, const uint32_t LA, const uint64_t *__restrict__ colB, const int LB, const int LBpad,
-		float2 *__restrict__ bnd, uint4 *__restrict__ trace_pass, const float open, const float ext,
-		float &lbest, int &lbi, int &lbj)
+__device__ __forceinline__ void sw_pass(const uint32_t smem_p0, const int lane, const int pass, const int npass,
+		const uint32_t LA, const uint4 *__restrict__ colB, const int LB, float2 *__restrict__ bnd,
+		uint4 *__restrict__ trace_pass, const float open, const float ext, float &lbest, int &lbi, int &lbj)
 {
-	constexpr int NH = (R + 3) / 4;
-	float Mrow[R], Irow[R], best[R];
-	int bestj[R];
+	constexpr int W1 = plane1_width(R);
+	const uint32_t base0 = smem_p0 + (uint32_t)lane * 16u;
+	const uint32_t base1 = smem_p0 + (uint32_t)kPlaneBytes + (uint32_t)lane * (uint32_t)(W1 * 4);
+	float Mrow[R], Irow[R];
 #pragma unroll
 	for (int r = 0; r < R; ++r) {
 		Mrow[r] = kNegInf;  // M[i_r+1][0]
 		Irow[r] = kNegInf;  // I[i_r][0]
-		best[r] = 0.0f;
-		bestj[r] = 0;
 	}
 	const bool first = (pass == 0), last = (pass == npass - 1);
-	float mdiag_next = (lane == 0 && first) ? 0.0f : kNegInf;  // M[i0][0]; M[0][0] = 0 (sw.cpp:116)
+	const bool lane0 = (lane == 0);
+	const bool use_bnd = lane0 && !first;
+	const bool put_bnd = (lane == 31) && !last;
+	float mdiag_next = (lane0 && first) ? 0.0f : kNegInf;  // M[i0][0]; M[0][0] = 0 (sw.cpp:116)
 	float outM = kNegInf, outD = kNegInf;
-	uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-	const int nsteps = LBpad + 31;
+	const uint32_t row0 = (uint32_t)pass * 32 * R + (uint32_t)lane * R;
+	const int nsteps = LB + 31;
+	const int ngroups = (nsteps + 3) >> 2;
 	int j = -lane;
-	uint64_t cb = (j >= 0 && j < LB) ? __ldg(colB + j) : 0ull;
+	uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+	if (j >= 0 && j < LB) {
+		c0 = __ldg(colB + 2 * j);
+		c1 = __ldg(colB + 2 * j + 1);
+	}
 	float2 bn = make_float2(kNegInf, kNegInf);
-	if (lane == 0 && !first)
+	if (use_bnd)
 		bn = bnd[0];
-	for (int s = 0; s < nsteps; ++s, ++j) {
+
+	// CHECK = false: every lane is inside the matrix at this step and at the next one (no range predicates)
+	auto step = [&](auto check_tag) -> uint32_t {
+		constexpr bool CHECK = decltype(check_tag)::value;
 		const float inM = __shfl_up_sync(kFull, outM, 1);
 		const float inD = __shfl_up_sync(kFull, outD, 1);
 		const int jn = j + 1;
-		const uint64_t cb_next = (jn >= 0 && jn < LB) ? __ldg(colB + jn) : 0ull;
+		uint4 n0 = c0, n1 = c1;
+		if (!CHECK || (jn >= 0 && jn < LB)) {
+			n0 = __ldg(colB + 2 * jn);
+			n1 = __ldg(colB + 2 * jn + 1);
+		}
 		float2 bn_next = bn;
-		if (lane == 0 && !first && jn < LB)
+		if (use_bnd && (!CHECK || jn < LB))
 			bn_next = bnd[jn];
 		uint32_t tw = 0;
-		if (j >= 0 && j < LB) {
-			float d, mdiag = mdiag_next;
-			if (lane == 0) {
-				d = first ? kNegInf : bn.y;           // D[i0][j]
-				mdiag_next = first ? kNegInf : bn.x;  // M[i0][j+1]
-			} else {
-				d = inD;
-				mdiag_next = inM;
-			}
+		if (!CHECK || (j >= 0 && j < LB)) {
+			float d = lane0 ? bn.y : inD;  // D[i0][j]   (bn = -inf pair in the first pass)
+			float mdiag = mdiag_next;      // M[i0][j]
+			mdiag_next = lane0 ? bn.x : inM;  // M[i0][j+1]
+			const uint32_t co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 			float S[R];
 #pragma unroll
 			for (int f = 0; f < RSK_NFEAT; ++f) {
-				const uint32_t e = (uint32_t)(cb >> (8 * f)) & 0xffu;
-				const float4 *p = rowtab + (e * NH) * 32 + lane;
-				const float4 v0 = p[0];
-				float4 v1 = v0;
-				if (NH == 2)
-					v1 = p[32];
-#pragma unroll
-				for (int r = 0; r < R; ++r) {
-					const float v = (r < 4) ? pick4(v0, r & 3) : pick4(v1, r & 3);
-					S[r] = (f == 0) ? v : S[r] + v;  // feature 0 assigns, 1..7 accumulate (dssaligner.cpp:557-595)
+				const uint32_t a0 = co[f] * 16u + base0;
+				const float4 v0 = lds_f32x4(a0);
+				float v[8];
+				v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+				v[4] = v[5] = v[6] = v[7] = 0.0f;
+				if (W1 == 1) {
+					v[4] = lds_f32(co[f] * 16u + base1);
+				} else if (W1 == 2) {
+					const float2 t = lds_f32x2(co[f] * 16u + base1);
+					v[4] = t.x; v[5] = t.y;
+				} else if (W1 == 4) {
+					const float4 t = lds_f32x4(a0 + (uint32_t)kPlaneBytes);
+					v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w;
 				}
+#pragma unroll
+				for (int r = 0; r < R; ++r)
+					S[r] = (f == 0) ? v[r] : S[r] + v[r];  // feature 0 assigns, 1..7 accumulate (dssaligner.cpp:557-595)
 			}
+			float xmax = kNegInf;
 #pragma unroll
 			for (int r = 0; r < R; ++r) {
 				const float m = mdiag;  // M[i][j]
@@ -136,7 +184,7 @@ __device__ __forceinline__ void sw_pass(const float4 *__restrict__ rowtab, const
 				if (ii > x) { x = ii; code = 2; }
 				if (0.0f >= x) { x = 0.0f; code = 3; }
 				x += S[r];
-				if (x > best[r]) { best[r] = x; bestj[r] = j; }
+				xmax = fmaxf(xmax, x);
 				Mrow[r] = x;  // M[i+1][j+1]
 				const float mo = m + open;
 				float dn = d + ext;
@@ -149,38 +197,62 @@ __device__ __forceinline__ void sw_pass(const float4 *__restrict__ rowtab, const
 			}
 			outM = Mrow[R - 1];
 			outD = d;
-			if (lane == 31 && !last)
+			if (put_bnd)
 				bnd[j] = make_float2(outM, outD);
-		}
-		t0 = t1; t1 = t2; t2 = t3; t3 = tw;
-		if (j >= 0 && j < LBpad && (j & 3) == 3)
-			trace_pass[(j >> 2) * 32 + lane] = make_uint4(t0, t1, t2, t3);
-		cb = cb_next;
-		bn = bn_next;
-	}
-	const uint32_t row0 = (uint32_t)pass * 32 * R + (uint32_t)lane * R;
+			if (xmax >= lbest) {
+				// rare: a cell reached the lane's running maximum.  Keep the reference's first-maximum rule:
+				// higher score wins; equal score -> smaller row; same row -> the earlier column (already stored).
 #pragma unroll
-	for (int r = 0; r < R; ++r) {
-		if (row0 + r < LA && best[r] > lbest) {
-			lbest = best[r];
-			lbi = (int)(row0 + r);
-			lbj = bestj[r];
+				for (int r = 0; r < R; ++r) {
+					const float x = Mrow[r];
+					const int row = (int)(row0 + r);
+					if ((x > lbest || (x == lbest && row < lbi)) && (uint32_t)row < LA) {
+						lbest = x;
+						lbi = row;
+						lbj = j;
+					}
+				}
+			}
 		}
+		j = jn;
+		c0 = n0;
+		c1 = n1;
+		bn = bn_next;
+		return tw;
+	};
+
+	for (int g = 0; g < ngroups; ++g) {
+		const int s0 = 4 * g;
+		uint32_t t0, t1, t2, t3;
+		if (s0 >= 31 && s0 + 4 < LB) {
+			t0 = step(std::false_type{});
+			t1 = step(std::false_type{});
+			t2 = step(std::false_type{});
+			t3 = step(std::false_type{});
+		} else {
+			t0 = step(std::true_type{});
+			t1 = step(std::true_type{});
+			t2 = step(std::true_type{});
+			t3 = step(std::true_type{});
+		}
+		trace_pass[g * 32 + lane] = make_uint4(t0, t1, t2, t3);
 	}
 }
 
 // Warp-cooperative traceback (sw.cpp:8-77) through a 2 KB shared tile of the packed trace.
-__device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int lane, const int R, const int LBpad,
+// Trace word of cell (row, col): pass p = row / (32R), lane l = (row % 32R) / R, nibble r = row % R,
+// step s = col + l, group g = s / 4, word s % 4 of uint4 trace[(p*ngroups + g)*32 + l].
+__device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int lane, const int R, const int LB,
 		const uint4 *__restrict__ trace, uint4 *tile, uint8_t *stage, const float score, const int bi, const int bj,
 		PairRec *rec)
 {
 	const int rows_per_pass = 32 * R;
-	const int nblk = LBpad >> 2;
+	const int ngroups = (LB + 31 + 3) >> 2;
 	const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
 	int i = bi + 1, j = bj + 1;
 	int state = 0;  // 0 = M, 1 = D, 2 = I
 	uint32_t n = 0;
-	int cur_p = -1, cur_g = -1;
+	int cur_p = -1, cur_G = -1;
 	for (;;) {
 		if (lane == 0)
 			stage[n] = (uint8_t)(state == 0 ? 'M' : state == 1 ? 'D' : 'I');
@@ -189,22 +261,24 @@ __device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int la
 		const int cj = (state == 1) ? j : j - 1;
 		const int p = ci / rows_per_pass;
 		const int rr = ci - p * rows_per_pass;
-		const int g = cj >> 4;
-		if (p != cur_p || g != cur_g) {
+		const int srcl = rr / R;
+		const int r = rr - srcl * R;
+		const int s = cj + srcl;
+		const int g = s >> 2;
+		const int G = g >> 2;
+		if (p != cur_p || G != cur_G) {
 			__syncwarp();
 #pragma unroll
 			for (int k = 0; k < 4; ++k) {
-				const int jb = 4 * g + k;
-				if (jb < nblk)
-					tile[k * 32 + lane] = trace[((size_t)p * nblk + jb) * 32 + lane];
+				const int gg = 4 * G + k;
+				if (gg < ngroups)
+					tile[k * 32 + lane] = trace[((size_t)p * ngroups + gg) * 32 + lane];
 			}
 			__syncwarp();
 			cur_p = p;
-			cur_g = g;
+			cur_G = G;
 		}
-		const int srcl = rr / R;
-		const int r = rr - srcl * R;
-		const uint32_t w = tile32[((((cj >> 2) & 3) * 32 + srcl) << 2) + (cj & 3)];
+		const uint32_t w = tile32[(((g & 3) * 32 + srcl) << 2) + (s & 3)];
 		const uint32_t nib = (w >> (4 * r)) & 15u;
 		if (state == 0) {
 			--i; --j;
@@ -243,7 +317,9 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const float *tab = reinterpret_cast<const float *>(smem + kSmemTab);
-	float4 *rowtab = reinterpret_cast<float4 *>(smem + kSmemRowTab);
+	float *p0 = reinterpret_cast<float *>(smem + kSmemP0);
+	float *p1 = reinterpret_cast<float *>(smem + kSmemP1);
+	const uint32_t smem_p0 = (uint32_t)__cvta_generic_to_shared(p0);
 	uint4 *tile = reinterpret_cast<uint4 *>(smem + kSmemTiles) + warp * 128;
 
 	const uint32_t LA = a.lenA[ai];
@@ -252,15 +328,15 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 
 	const bool have = (uint32_t)warp < cnt;
 	uint32_t bidx = 0, slot = 0;
-	int LB = 0, LBpad = 0;
-	const uint64_t *colB = nullptr;
+	int LB = 0;
+	const uint4 *colB = nullptr;
 	if (have) {
 		bidx = a.blist[begin + warp];
 		slot = a.cross ? slot_base + bidx : a.bslot[begin + warp];
 		LB = (int)a.lenB[bidx];
-		LBpad = (LB + 3) & ~3;
-		colB = a.profB + a.offB[bidx];
+		colB = a.coloffB + 2 * a.offB[bidx];
 	}
+	const int ngroups = (LB + 31 + 3) >> 2;
 	const size_t gw = (size_t)blockIdx.x * kSwWarps + warp;
 	uint4 *trace = a.trace + gw * a.trace_stride;
 	float2 *bnd = a.bnd + gw * a.bnd_stride;
@@ -270,11 +346,11 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 	int lbi = 0x7fffffff, lbj = 0;
 	for (int pass = 0; pass < npass; ++pass) {
 		__syncthreads();  // every warp is done with the previous pass's row table
-		build_rowtab<R>(reinterpret_cast<float *>(rowtab), tab, profA, LA, pass);
+		build_rowtab<R>(p0, p1, tab, profA, LA, pass);
 		__syncthreads();
 		if (have)
-			sw_pass<R>(rowtab, lane, pass, npass, LA, colB, LB, LBpad, bnd,
-					trace + (size_t)pass * (LBpad >> 2) * 32, a.open, a.ext, lbest, lbi, lbj);
+			sw_pass<R>(smem_p0, lane, pass, npass, LA, colB, LB, bnd, trace + (size_t)pass * ngroups * 32,
+					a.open, a.ext, lbest, lbi, lbj);
 	}
 	if (!have)
 		return;
@@ -300,7 +376,7 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 		return;
 	}
 	__syncwarp();  // trace words written by other lanes of this warp are visible
-	traceback_and_emit(a, lane, R, LBpad, trace, tile, stage, lbest, lbi, lbj, rec);
+	traceback_and_emit(a, lane, R, LB, trace, tile, stage, lbest, lbi, lbj, rec);
 }
 
 __global__ void __launch_bounds__(kSwThreads, 1) sw_affine_f32_tb_kernel(const SwArgs a)
@@ -366,18 +442,32 @@ __global__ void pack_profiles_kernel(const uint8_t *__restrict__ planes, uint64_
 	prof8[i] = v;
 }
 
+// e-letters -> per-column row-table offsets in units of 16 bytes (code * 512 bytes / 16)
+__global__ void make_coloff_kernel(const uint64_t *__restrict__ prof8, uint64_t total, uint4 *__restrict__ coloff)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= total)
+		return;
+	const uint64_t v = prof8[i];
+	uint32_t o[8];
+#pragma unroll
+	for (int f = 0; f < 8; ++f)
+		o[f] = (uint32_t)((v >> (8 * f)) & 0xff) * 32u;
+	coloff[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+	coloff[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
 }  // namespace
 
 size_t sw_smem_bytes() { return kSmemTotal; }
 
+// uint4 units of packed trace one warp needs for a pair with npass passes and LB columns
+uint64_t sw_trace_units(int npass, uint32_t LB) { return (uint64_t)npass * ((LB + 31 + 3) >> 2) * 32; }
+
 int launch_sw(const SwArgs &args, int grid, size_t smem, cudaStream_t stream)
 {
-	static bool attr_set = false;
-	if (!attr_set) {
-		if (cudaFuncSetAttribute(sw_affine_f32_tb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal) != cudaSuccess)
-			return -1;
-		attr_set = true;
-	}
+	if (cudaFuncSetAttribute(sw_affine_f32_tb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal) != cudaSuccess)
+		return -1;
 	sw_affine_f32_tb_kernel<<<grid, kSwThreads, smem, stream>>>(args);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -389,6 +479,16 @@ int launch_pack_profiles(const uint8_t *planes, uint64_t total, uint64_t *prof8,
 	const int threads = 256;
 	const unsigned blocks = (unsigned)((total + threads - 1) / threads);
 	pack_profiles_kernel<<<blocks, threads, 0, stream>>>(planes, total, prof8);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_make_coloff(const uint64_t *prof8, uint64_t total, uint4 *coloff, cudaStream_t stream)
+{
+	if (total == 0)
+		return 0;
+	const int threads = 256;
+	const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+	make_coloff_kernel<<<blocks, threads, 0, stream>>>(prof8, total, coloff);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

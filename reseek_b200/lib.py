@@ -131,28 +131,42 @@ def _ptr(a):
 
 
 class Results:
-    """Hits of one search call, copied into numpy arrays (the C object is freed immediately)."""
+    """Hits of one search call.  `hits` is a zero-copy numpy view (HIT_DTYPE) of the library's rsk_hit array and
+    `paths` a view of its path pool; both stay valid while this object is alive."""
 
     def __init__(self, handle):
         L = load_library()
+        self._handle = handle
         n = L.rsk_results_count(handle)
         if n:
             buf = (C.c_char * (n * HIT_DTYPE.itemsize)).from_address(L.rsk_results_hits(handle))
-            self.hits = np.frombuffer(buf, dtype=HIT_DTYPE, count=n).copy()
+            self.hits = np.frombuffer(buf, dtype=HIT_DTYPE, count=n)
         else:
             self.hits = np.zeros(0, HIT_DTYPE)
         nb = L.rsk_results_paths_bytes(handle)
         if nb:
             buf = (C.c_char * nb).from_address(L.rsk_results_paths(handle))
-            self.paths = bytes(buf)
+            self.paths = np.frombuffer(buf, dtype=np.uint8, count=nb)
         else:
-            self.paths = b""
-        L.rsk_results_free(handle)
+            self.paths = np.zeros(0, np.uint8)
 
     def path(self, k):
         h = self.hits[k]
         off, n = int(h["path_off"]), int(h["path_len"])
-        return self.paths[off:off + n].decode()
+        return self.paths[off:off + n].tobytes().decode()
+
+    def close(self):
+        if self._handle:
+            self.hits = np.zeros(0, HIT_DTYPE)
+            self.paths = np.zeros(0, np.uint8)
+            load_library().rsk_results_free(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __len__(self):
         return len(self.hits)
