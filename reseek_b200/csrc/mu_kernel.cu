@@ -96,7 +96,7 @@ __device__ __forceinline__ int mu_pass(const int4 *__restrict__ T, const int lan
 }
 
 __device__ __forceinline__ void build_mu_table(int *T32, const int *mx, const uint8_t *__restrict__ muA, const int LA,
-		const int pass, const bool reversed)
+		const int pass, const bool reversed, const bool tr)
 {
 	// T[b][h][lane][q]: row rr = lane*8 + h*4 + q of this pass
 	for (int idx = threadIdx.x; idx < kMuLetters * kMuRows; idx += kSwThreads) {
@@ -106,7 +106,7 @@ __device__ __forceinline__ void build_mu_table(int *T32, const int *mx, const ui
 		int v = -1000;  // rows beyond the chain: never contribute (every value is floored at 0)
 		if (row < LA) {
 			const int a = muA[reversed ? (LA - 1 - row) : row];
-			v = mx[a * kMuLetters + b];
+			v = tr ? mx[b * kMuLetters + a] : mx[a * kMuLetters + b];  // matrix[reference A letter][reference B letter]
 		}
 		const int l = rr >> 3, r = rr & 7;
 		T32[(((b * 2 + (r >> 2)) * 32 + l) << 2) + (r & 3)] = v;
@@ -134,30 +134,29 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter_kernel(const MuArg
 		__syncthreads();
 		if (task >= a.ntasks)
 			break;
-		uint32_t ai, begin, cnt, slot_base = 0;
+		uint32_t rowchain, begin, cnt;
 		if (a.cross) {
-			const uint32_t arel = task / a.nseg;
-			const uint32_t seg = task - arel * a.nseg;
-			ai = a.a_begin + arel;
+			const uint32_t ridx = task / a.nseg;
+			const uint32_t seg = task - ridx * a.nseg;
+			rowchain = a.rowlist[ridx];
 			begin = seg * kSwWarps;
-			cnt = min((uint32_t)kSwWarps, a.nB - begin);
-			slot_base = arel * a.nB;
+			cnt = min((uint32_t)kSwWarps, a.ncols - begin);
 		} else {
-			ai = a.task_a[task];
+			rowchain = a.task_row[task];
 			begin = a.task_begin[task];
 			cnt = a.task_cnt[task];
 		}
-		const int LA = (int)a.lenA[ai];
-		const uint8_t *muA = a.muA + a.offA[ai];
+		const int LA = (int)a.len_row[rowchain];
+		const uint8_t *muA = a.mu_row + a.off_row[rowchain];
 		const int npass = (LA + kMuRows - 1) / kMuRows;
 		const bool have = (uint32_t)warp < cnt;
-		uint32_t bidx = 0;
+		uint32_t cidx = 0;
 		int LB = 0;
 		const uint8_t *colB = nullptr;
 		if (have) {
-			bidx = a.blist[begin + warp];
-			LB = (int)a.lenB[bidx];
-			colB = a.muB + a.offB[bidx];
+			cidx = a.clist[begin + warp];
+			LB = (int)a.len_col[cidx];
+			colB = a.mu_col + a.off_col[cidx];
 		}
 		int fwd = 0, rev = 0;
 		bool need_rev = false;
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter_kernel(const MuArg
 			int best = 0;
 			for (int pass = 0; pass < npass; ++pass) {
 				__syncthreads();
-				build_mu_table(T32, mx, muA, LA, pass, dir == 1);
+				build_mu_table(T32, mx, muA, LA, pass, dir == 1, a.tr != 0);
 				__syncthreads();
 				if (run && (dir == 0 || need_rev))
 					best = max(best, mu_pass(T, lane, pass == 0, pass == npass - 1, colB, LB, bnd, a.open, a.ext));
@@ -189,7 +188,13 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter_kernel(const MuArg
 				rev = best > 250 ? 255 : best;  // value read before the 777 assignment (:149-155)
 		}
 		if (have && lane == 0) {
-			const uint32_t slot = a.cross ? slot_base + bidx : a.bslot[begin + warp];
+			uint32_t slot;
+			if (a.cross) {
+				const uint32_t ra = a.tr ? cidx : rowchain, rb = a.tr ? rowchain : cidx;
+				slot = (ra - a.a_begin) * a.nB + rb;
+			} else {
+				slot = a.cslot[begin + warp];
+			}
 			PairRec *rec = a.rec + slot;
 			float score = 0.0f;
 			int rrev = 0;
@@ -208,24 +213,27 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter_kernel(const MuArg
 	}
 }
 
-// One CTA per A chain of the batch: compact the surviving B's (in blist order, so lengths stay sorted)
-// and emit SW tasks of up to kSwWarps pairs.  task slots are reserved with one atomicAdd per A chain.
+// One CTA per row chain of the batch: compact the surviving column chains (in clist order, so lengths stay
+// sorted) and emit SW tasks of up to W pairs into the task list of the row chain's kernel class.
 __global__ void __launch_bounds__(256) compact_survivors_kernel(const CompactArgs a)
 {
 	__shared__ uint32_t s_warp[8];
 	__shared__ uint32_t s_taskbase;
-	const uint32_t arel = blockIdx.x;
+	const uint32_t ridx = blockIdx.x;
+	const uint32_t rowchain = a.rowlist[ridx];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint32_t running = 0;
-	unsigned long long lbsum = 0;
-	for (uint32_t k0 = 0; k0 < a.nB; k0 += 256) {
+	unsigned long long lsum = 0;
+	for (uint32_t k0 = 0; k0 < a.ncols; k0 += 256) {
 		const uint32_t k = k0 + tid;
-		uint32_t b = 0, keep = 0;
-		if (k < a.nB) {
-			b = a.blist[k];
-			keep = a.keep[(size_t)arel * a.nB + b];
+		uint32_t c = 0, keep = 0, slot = 0;
+		if (k < a.ncols) {
+			c = a.clist[k];
+			const uint32_t ra = a.tr ? c : rowchain, rb = a.tr ? rowchain : c;
+			slot = (ra - a.a_begin) * a.nB + rb;
+			keep = a.keep[slot];
 			if (keep)
-				lbsum += a.lenB[b];
+				lsum += a.len_col[c];
 		}
 		const unsigned m = __ballot_sync(kFull, keep != 0);
 		if (lane == 0)
@@ -239,28 +247,30 @@ __global__ void __launch_bounds__(256) compact_survivors_kernel(const CompactArg
 		}
 		if (keep) {
 			const uint32_t pos = running + before + __popc(m & ((1u << lane) - 1u));
-			a.out_blist[(size_t)arel * a.nB + pos] = b;
-			a.out_bslot[(size_t)arel * a.nB + pos] = arel * a.nB + b;
+			a.out_clist[(size_t)ridx * a.ncols + pos] = c;
+			a.out_cslot[(size_t)ridx * a.ncols + pos] = slot;
 		}
 		running += tot;
 		__syncthreads();
 	}
-	const uint32_t ntask = (running + kSwWarps - 1) / kSwWarps;
+	const int cls = sw_class_of_len(a.len_row[rowchain]);
+	const uint32_t W = (uint32_t)sw_class_warps(cls);
+	const uint32_t ntask = (running + W - 1) / W;
 #pragma unroll
 	for (int o = 16; o >= 1; o >>= 1)
-		lbsum += __shfl_xor_sync(kFull, lbsum, o);
-	if (lane == 0 && lbsum)
-		atomicAdd(a.cell_count, lbsum * (unsigned long long)a.lenA[a.a_begin + arel]);
+		lsum += __shfl_xor_sync(kFull, lsum, o);
+	if (lane == 0 && lsum)
+		atomicAdd(a.cell_count, lsum * (unsigned long long)a.len_row[rowchain]);
 	if (tid == 0) {
-		s_taskbase = ntask ? atomicAdd(a.task_count, ntask) : 0;
+		s_taskbase = ntask ? atomicAdd(a.task_count + cls, ntask) : 0;
 		atomicAdd(a.pair_count, (unsigned long long)running);
 	}
 	__syncthreads();
-	const uint32_t tb = s_taskbase;
+	const size_t tb = (size_t)cls * a.task_cap + s_taskbase;
 	for (uint32_t t = tid; t < ntask; t += 256) {
-		a.task_a[tb + t] = a.a_begin + arel;
-		a.task_begin[tb + t] = arel * a.nB + t * kSwWarps;
-		a.task_cnt[tb + t] = min((uint32_t)kSwWarps, running - t * kSwWarps);
+		a.task_row[tb + t] = rowchain;
+		a.task_begin[tb + t] = ridx * a.ncols + t * W;
+		a.task_cnt[tb + t] = min(W, running - t * W);
 	}
 }
 
@@ -276,11 +286,11 @@ int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream)
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_compact_survivors(const CompactArgs &args, uint32_t nA, cudaStream_t stream)
+int launch_compact_survivors(const CompactArgs &args, uint32_t nrows, cudaStream_t stream)
 {
-	if (nA == 0)
+	if (nrows == 0)
 		return 0;
-	compact_survivors_kernel<<<nA, 256, 0, stream>>>(args);
+	compact_survivors_kernel<<<nrows, 256, 0, stream>>>(args);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

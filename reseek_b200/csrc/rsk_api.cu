@@ -120,7 +120,6 @@ struct rsk_ctx {
 	int num_sms = 0;
 	rsk_params params;
 	float *d_tables = nullptr;
-	uint32_t *d_task_counter = nullptr;
 	unsigned long long *d_pool_cursor = nullptr;
 	cudaEvent_t ev[8] = {};
 	// grow-only scratch
@@ -136,7 +135,8 @@ struct rsk_ctx {
 	DevBuf<int2> mu_bnd;
 	DevBuf<uint32_t> c_blist, c_bslot, c_task_a, c_task_begin, c_task_cnt;  // compacted survivors
 	size_t filt_explicit_pairs = 0; uint64_t filt_explicit_cells = 0; uint32_t filt_explicit_tasks = 0; bool batch_cross = true;
-	struct Counters { uint32_t task_count, sat_count, mu_task_counter, pad; unsigned long long pair_count, cell_count; };
+	struct Counters { uint32_t task_count[4]; uint32_t sw_task_counter[4]; uint32_t sat_count, mu_task_counter; unsigned long long pair_count, cell_count; };
+	DevBuf<uint32_t> rowlist, colsort;
 	Counters *d_counters = nullptr;
 	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU
 	PinBuf<uint8_t> h_pool[2];
@@ -310,7 +310,6 @@ extern "C" int rsk_ctx_create(int device, const rsk_params *params, void *cuda_s
 	}
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if (cudaMalloc((void **)&ctx->d_tables, sizeof(float) * RSK_TABLE_FLOATS) != cudaSuccess ||
-		cudaMalloc((void **)&ctx->d_task_counter, sizeof(uint32_t)) != cudaSuccess ||
 		cudaMalloc((void **)&ctx->d_pool_cursor, sizeof(unsigned long long)) != cudaSuccess ||
 		cudaMalloc((void **)&ctx->d_mu_mx, sizeof(int) * 36 * 36) != cudaSuccess ||
 		cudaMalloc((void **)&ctx->d_counters, sizeof(rsk_ctx::Counters)) != cudaSuccess) {
@@ -350,11 +349,10 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
 	ctx->h_rec[0].release(); ctx->h_rec[1].release(); ctx->h_pool[0].release(); ctx->h_pool[1].release();
 	ctx->keep.release(); ctx->mu_bnd.release(); ctx->c_blist.release(); ctx->c_bslot.release();
-	ctx->c_task_a.release(); ctx->c_task_begin.release(); ctx->c_task_cnt.release();
+	ctx->c_task_a.release(); ctx->c_task_begin.release(); ctx->c_task_cnt.release(); ctx->rowlist.release(); ctx->colsort.release();
 	if (ctx->d_mu_mx) cudaFree(ctx->d_mu_mx);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->d_tables) cudaFree(ctx->d_tables);
-	if (ctx->d_task_counter) cudaFree(ctx->d_task_counter);
 	if (ctx->d_pool_cursor) cudaFree(ctx->d_pool_cursor);
 	for (auto &e : ctx->ev)
 		if (e) cudaEventDestroy(e);
@@ -509,79 +507,142 @@ struct SearchPlan {
 	uint64_t npairs = 0;
 };
 
-int ensure_scratch(rsk_ctx *ctx, uint32_t maxLA, uint32_t maxLB, int &grid, uint64_t &trace_stride, uint32_t &bnd_stride,
+int ensure_scratch(rsk_ctx *ctx, uint32_t maxRow, uint32_t maxCol, int &grid, uint64_t &trace_stride, uint32_t &bnd_stride,
 		uint32_t &stage_stride)
 {
 	int npass, R;
-	sw_geometry(maxLA, npass, R);
-	// every pair of the batch has npass(LA) <= npass(maxLA) and LBpad <= maxLBpad
-	const uint64_t lbpad = ((uint64_t)maxLB + 3) & ~3ull;
-	trace_stride = sw_trace_units(npass, maxLB);  // uint4 units
-	bnd_stride = (uint32_t)lbpad + 4;
-	stage_stride = ((maxLA + maxLB + 16) + 15) & ~15u;
-	const uint64_t per_cta = (trace_stride * 16 + (uint64_t)bnd_stride * 8 + stage_stride) * kSwWarps;
+	sw_geometry(maxRow, npass, R);
+	// every pair of the batch has npass(rows) <= npass(maxRow) and columns <= maxCol
+	trace_stride = sw_trace_units(npass, maxCol);  // uint4 units
+	bnd_stride = ((maxCol + 3) & ~3u) + 4;
+	stage_stride = ((maxRow + maxCol + 16) + 15) & ~15u;
+	const uint64_t per_cta = (trace_stride * 16 + (uint64_t)bnd_stride * 8 + stage_stride) * kSwMaxWarps;
 	grid = ctx->num_sms;
 	if (per_cta * (uint64_t)grid > ctx->scratch_budget)
 		grid = (int)std::max<uint64_t>(1, ctx->scratch_budget / per_cta);
-	const size_t warps = (size_t)grid * kSwWarps;
+	const size_t warps = (size_t)grid * kSwMaxWarps;
 	if (ctx->trace.ensure(trace_stride * warps) || ctx->bnd.ensure((size_t)bnd_stride * warps) ||
 		ctx->stage.ensure((size_t)stage_stride * warps)) {
 		cudaGetLastError();
-		return fail(RSK_ERR_NOMEM, "SW scratch allocation failed (maxLA=%u maxLB=%u)", maxLA, maxLB);
+		return fail(RSK_ERR_NOMEM, "SW scratch allocation failed (rows=%u cols=%u)", maxRow, maxCol);
 	}
 	return RSK_OK;
 }
 
-// Run one batch on the device: SW+traceback, then LDDT/TS.  Records land in ctx->rec[0..npairs).
+int ensure_coloff(rsk_ctx *ctx, const rsk_chainset *Cs)
+{
+	if (Cs->d.coloff)
+		return RSK_OK;
+	// first use of this set as the column side: derive the per-residue table offsets (32 B/residue)
+	rsk_chainset *Cm = const_cast<rsk_chainset *>(Cs);
+	if (cudaMalloc((void **)&Cm->d.coloff, (size_t)Cs->d.total * 32) != cudaSuccess) {
+		cudaGetLastError();
+		return fail(RSK_ERR_NOMEM, "column-offset table for %llu residues", (unsigned long long)Cs->d.total);
+	}
+	int nl = launch_make_coloff(Cs->d.prof8, Cs->d.total, Cm->d.coloff, ctx->stream);
+	if (nl < 0)
+		return fail(RSK_ERR_CUDA, "make_coloff launch failed");
+	ctx->stats.kernel_launches += nl;
+	return RSK_OK;
+}
+
+template <typename T>
+int upload_vec(rsk_ctx *ctx, DevBuf<T> &dst, const std::vector<T> &src)
+{
+	if (dst.ensure(std::max<size_t>(1, src.size())))
+		return fail(RSK_ERR_NOMEM, "device task buffer (%zu elements)", src.size());
+	if (!src.empty())
+		CK(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->stats.h2d_bytes += src.size() * sizeof(T);
+	return RSK_OK;
+}
+
+// Run one batch on the device: (Mu filter + compaction), SW+traceback, then LDDT/TS.  Records land in ctx->rec[0..npairs).
+// Task model: a task is one "row" chain (its score table is staged in shared memory by the CTA) against up to W
+// "column" chains.  In cross mode the side with fewer chains supplies the rows (tr = rows are the reference's B).
 int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_search_opts &opts)
 {
 	const rsk_chainset *A = plan.A, *B = plan.B;
 	cudaStream_t st = ctx->stream;
+	const uint32_t nA_b = b.cross ? (b.a1 - b.a0) : 0;
+	const bool tr = b.cross && B->d.n <= nA_b;
+	const rsk_chainset *Rw = tr ? B : A, *Cl = tr ? A : B;
+	const uint32_t maxRow = tr ? b.maxLB : b.maxLA, maxCol = tr ? b.maxLA : b.maxLB;
 	int grid;
 	uint64_t trace_stride;
 	uint32_t bnd_stride, stage_stride;
-	int rc = ensure_scratch(ctx, b.maxLA, b.maxLB, grid, trace_stride, bnd_stride, stage_stride);
+	int rc = ensure_scratch(ctx, maxRow, maxCol, grid, trace_stride, bnd_stride, stage_stride);
 	if (rc)
+		return rc;
+	if ((rc = ensure_coloff(ctx, Cl)))
 		return rc;
 	if (ctx->rec.ensure(b.npairs) || ctx->pool.ensure((size_t)b.pool_bound + 64)) {
 		cudaGetLastError();
 		return fail(RSK_ERR_NOMEM, "result buffers: %zu pairs, %llu path bytes", b.npairs, (unsigned long long)b.pool_bound);
 	}
 	CK(cudaMemsetAsync(ctx->rec.p, 0, b.npairs * sizeof(PairRec), st));
-	CK(cudaMemsetAsync(ctx->d_task_counter, 0, sizeof(uint32_t), st));
 	CK(cudaMemsetAsync(ctx->d_pool_cursor, 0, sizeof(unsigned long long), st));
+	CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(rsk_ctx::Counters), st));
+
+	const bool filter = ctx->params.omega > 0 && A->has_mu && B->has_mu;
+
+	// ---- row lists per kernel class and the column list (cross mode) ----
+	std::vector<uint32_t> rowlist;            // rows grouped by class
+	uint32_t row_off[kSwClasses + 1] = {0, 0, 0, 0};
+	uint32_t ncols = 0;
+	if (b.cross) {
+		std::vector<uint32_t> byclass[kSwClasses];
+		const uint32_t r0 = tr ? 0 : b.a0, r1 = tr ? B->d.n : b.a1;
+		for (uint32_t r = r0; r < r1; ++r)
+			byclass[sw_class_of_len(Rw->hlen[r])].push_back(r);
+		for (int c = 0; c < kSwClasses; ++c) {
+			row_off[c] = (uint32_t)rowlist.size();
+			rowlist.insert(rowlist.end(), byclass[c].begin(), byclass[c].end());
+		}
+		row_off[kSwClasses] = (uint32_t)rowlist.size();
+		if ((rc = upload_vec(ctx, ctx->rowlist, rowlist)))
+			return rc;
+		if (tr) {
+			// columns = this batch's A range, longest first so that the chains of a task have similar lengths
+			std::vector<uint32_t> cl(nA_b);
+			std::iota(cl.begin(), cl.end(), b.a0);
+			std::stable_sort(cl.begin(), cl.end(), [&](uint32_t x, uint32_t y) { return A->hlen[x] > A->hlen[y]; });
+			if ((rc = upload_vec(ctx, ctx->colsort, cl)))
+				return rc;
+			ncols = nA_b;
+		} else {
+			ncols = B->d.n;  // ctx->blist already holds B sorted by length (uploaded once per search call)
+		}
+	}
 
 	// ---- Mu filter (K3) + survivor compaction: only when the reference would run MuFilter (dssaligner.cpp:819-829) ----
-	const bool filter = ctx->params.omega > 0 && A->has_mu && B->has_mu;
-	uint32_t nA_b = b.a1 - b.a0;
 	CK(cudaEventRecord(ctx->ev[3], st));
+	uint32_t task_cap = 0;
 	if (filter) {
-		const uint32_t nseg = (B->d.n + kSwWarps - 1) / kSwWarps;
 		const size_t warps = (size_t)ctx->num_sms * 2 * kSwWarps;
-		const uint32_t mu_bnd_stride = ((B->maxlen + 3) & ~3u) + 4;
+		const uint32_t mu_bnd_stride = ((maxCol + 3) & ~3u) + 4;
 		if (ctx->keep.ensure(b.npairs) || ctx->mu_bnd.ensure((size_t)mu_bnd_stride * warps)) {
 			cudaGetLastError();
 			return fail(RSK_ERR_NOMEM, "Mu filter buffers for %zu pairs", b.npairs);
 		}
-		if (b.cross && (ctx->c_blist.ensure(b.npairs) || ctx->c_bslot.ensure(b.npairs) ||
-			ctx->task_a.ensure((size_t)nA_b * nseg) || ctx->task_begin.ensure((size_t)nA_b * nseg) || ctx->task_cnt.ensure((size_t)nA_b * nseg))) {
-			cudaGetLastError();
-			return fail(RSK_ERR_NOMEM, "Mu filter task buffers for %zu pairs", b.npairs);
-		}
-		CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(rsk_ctx::Counters), st));
 		MuArgs ma;
 		memset(&ma, 0, sizeof(ma));
-		ma.muA = A->d.mu; ma.offA = A->d.off; ma.lenA = A->d.len;
-		ma.muB = B->d.mu; ma.offB = B->d.off; ma.lenB = B->d.len;
+		ma.mu_row = Rw->d.mu; ma.off_row = Rw->d.off; ma.len_row = Rw->d.len;
+		ma.mu_col = Cl->d.mu; ma.off_col = Cl->d.off; ma.len_col = Cl->d.len;
+		ma.tr = tr ? 1 : 0;
 		ma.cross = b.cross ? 1 : 0;
+		ma.a_begin = b.a0; ma.nB = B->d.n;
 		if (b.cross) {
-			ma.ntasks = nA_b * nseg; ma.a_begin = b.a0; ma.nseg = nseg; ma.nB = B->d.n;
+			ma.nseg = (ncols + kSwWarps - 1) / kSwWarps;
+			ma.ncols = ncols;
+			ma.rowlist = ctx->rowlist.p;
+			ma.ntasks = (uint32_t)rowlist.size() * ma.nseg;
+			ma.clist = tr ? ctx->colsort.p : ctx->blist.p;
 		} else {
 			ma.ntasks = b.ntasks;
-			ma.task_a = ctx->task_a.p; ma.task_begin = ctx->task_begin.p; ma.task_cnt = ctx->task_cnt.p;
-			ma.bslot = ctx->bslot.p;
+			ma.task_row = ctx->task_a.p; ma.task_begin = ctx->task_begin.p; ma.task_cnt = ctx->task_cnt.p;
+			ma.clist = ctx->blist.p; ma.cslot = ctx->bslot.p;
 		}
-		ma.blist = ctx->blist.p;
 		ma.bnd = ctx->mu_bnd.p; ma.bnd_stride = mu_bnd_stride;
 		ma.rec = ctx->rec.p; ma.keep = ctx->keep.p;
 		ma.task_counter = &ctx->d_counters->mu_task_counter;
@@ -590,120 +651,144 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		ma.open = ctx->params.mu_gap_open; ma.ext = ctx->params.mu_gap_ext;
 		ma.omega = ctx->params.omega; ma.omega_fwd = ctx->params.omega_fwd;
 		ma.mkfl = ctx->params.mkfl;
-		int nlm = launch_mu_filter(ma, (int)std::min<uint64_t>((uint64_t)ctx->num_sms * 2, ma.ntasks), st);
+		int nlm = launch_mu_filter(ma, (int)std::min<uint64_t>((uint64_t)ctx->num_sms * 2, std::max<uint32_t>(1, ma.ntasks)), st);
 		if (nlm < 0)
 			return fail(RSK_ERR_CUDA, "Mu filter kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->stats.kernel_launches += nlm;
-		if (!b.cross) {
-			// explicit pair lists are small (PostMuFilter, -alignpair): compact the survivors on the host
-			std::vector<uint8_t> keep(b.npairs);
-			CK(cudaMemcpyAsync(keep.data(), ctx->keep.p, b.npairs, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
-			ctx->stats.d2h_bytes += b.npairs;
-			std::vector<uint32_t> t_a, t_begin, t_cnt, bl, bs;
-			size_t k = 0;
-			uint64_t cells = 0;
-			while (k < b.npairs) {
-				const uint32_t a0 = plan.sa[b.k0 + k];
-				const uint32_t begin = (uint32_t)bl.size();
-				uint32_t cnt = 0;
-				while (k < b.npairs && plan.sa[b.k0 + k] == a0 && cnt < (uint32_t)kSwWarps) {
-					if (keep[k]) {
-						bl.push_back(plan.sb[b.k0 + k]);
-						bs.push_back((uint32_t)k);
-						cells += (uint64_t)A->hlen[a0] * B->hlen[plan.sb[b.k0 + k]];
-						++cnt;
-					}
-					++k;
-				}
-				if (cnt) {
-					t_a.push_back(a0); t_begin.push_back(begin); t_cnt.push_back(cnt);
-				}
-			}
-			ctx->filt_explicit_pairs = bl.size();
-			ctx->filt_explicit_cells = cells;
-			ctx->filt_explicit_tasks = (uint32_t)t_a.size();
-			const size_t n = std::max<size_t>(1, bl.size()), nt = std::max<size_t>(1, t_a.size());
-			if (ctx->c_blist.ensure(n) || ctx->c_bslot.ensure(n) || ctx->c_task_a.ensure(nt) || ctx->c_task_begin.ensure(nt) || ctx->c_task_cnt.ensure(nt))
-				return fail(RSK_ERR_NOMEM, "survivor task buffers");
-			if (!bl.empty()) {
-				CK(cudaMemcpyAsync(ctx->c_blist.p, bl.data(), 4 * bl.size(), cudaMemcpyHostToDevice, st));
-				CK(cudaMemcpyAsync(ctx->c_bslot.p, bs.data(), 4 * bs.size(), cudaMemcpyHostToDevice, st));
-				CK(cudaMemcpyAsync(ctx->c_task_a.p, t_a.data(), 4 * t_a.size(), cudaMemcpyHostToDevice, st));
-				CK(cudaMemcpyAsync(ctx->c_task_begin.p, t_begin.data(), 4 * t_a.size(), cudaMemcpyHostToDevice, st));
-				CK(cudaMemcpyAsync(ctx->c_task_cnt.p, t_cnt.data(), 4 * t_a.size(), cudaMemcpyHostToDevice, st));
-				CK(cudaStreamSynchronize(st));  // the vectors die at the end of this scope
-			}
-			ctx->stats.mu_filter_in += b.npairs;
-		} else {
-		CompactArgs ca;
-		memset(&ca, 0, sizeof(ca));
-		ca.a_begin = b.a0; ca.nB = B->d.n; ca.blist = ctx->blist.p; ca.keep = ctx->keep.p;
-		ca.lenA = A->d.len; ca.lenB = B->d.len;
-		ca.out_blist = ctx->c_blist.p; ca.out_bslot = ctx->c_bslot.p;
-		ca.task_a = ctx->task_a.p; ca.task_begin = ctx->task_begin.p; ca.task_cnt = ctx->task_cnt.p;
-		ca.task_count = &ctx->d_counters->task_count;
-		ca.pair_count = &ctx->d_counters->pair_count;
-		ca.cell_count = &ctx->d_counters->cell_count;
-		nlm = launch_compact_survivors(ca, nA_b, st);
-		if (nlm < 0)
-			return fail(RSK_ERR_CUDA, "compaction kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-		ctx->stats.kernel_launches += nlm;
 		ctx->stats.mu_filter_in += b.npairs;
+		if (b.cross) {
+			const uint32_t nrows = (uint32_t)rowlist.size();
+			task_cap = nrows * (ncols / kClassWarps[kSwClasses - 1] + 1);
+			if (ctx->c_blist.ensure(b.npairs) || ctx->c_bslot.ensure(b.npairs) || ctx->c_task_a.ensure((size_t)task_cap * kSwClasses) ||
+				ctx->c_task_begin.ensure((size_t)task_cap * kSwClasses) || ctx->c_task_cnt.ensure((size_t)task_cap * kSwClasses)) {
+				cudaGetLastError();
+				return fail(RSK_ERR_NOMEM, "survivor task buffers for %zu pairs", b.npairs);
+			}
+			CompactArgs ca;
+			memset(&ca, 0, sizeof(ca));
+			ca.tr = tr ? 1 : 0; ca.a_begin = b.a0; ca.nB = B->d.n;
+			ca.rowlist = ctx->rowlist.p; ca.ncols = ncols; ca.clist = tr ? ctx->colsort.p : ctx->blist.p; ca.keep = ctx->keep.p;
+			ca.len_row = Rw->d.len; ca.len_col = Cl->d.len;
+			ca.out_clist = ctx->c_blist.p; ca.out_cslot = ctx->c_bslot.p;
+			ca.task_row = ctx->c_task_a.p; ca.task_begin = ctx->c_task_begin.p; ca.task_cnt = ctx->c_task_cnt.p;
+			ca.task_cap = task_cap;
+			ca.task_count = ctx->d_counters->task_count;
+			ca.pair_count = &ctx->d_counters->pair_count;
+			ca.cell_count = &ctx->d_counters->cell_count;
+			nlm = launch_compact_survivors(ca, nrows, st);
+			if (nlm < 0)
+				return fail(RSK_ERR_CUDA, "compaction kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+			ctx->stats.kernel_launches += nlm;
 		}
 	}
 
+	// ---- explicit pair lists: tasks per class are built on the host (lists are small: PostMuFilter, -alignpair, self) ----
+	std::vector<uint32_t> e_row[kSwClasses], e_begin[kSwClasses], e_cnt[kSwClasses];
+	std::vector<uint32_t> e_clist, e_cslot;
+	uint32_t e_off[kSwClasses + 1] = {0, 0, 0, 0};
+	if (!b.cross) {
+		std::vector<uint8_t> keep;
+		if (filter) {
+			keep.resize(b.npairs);
+			CK(cudaMemcpyAsync(keep.data(), ctx->keep.p, b.npairs, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			ctx->stats.d2h_bytes += b.npairs;
+		}
+		size_t k = 0;
+		uint64_t cells = 0;
+		while (k < b.npairs) {
+			const uint32_t a0 = plan.sa[b.k0 + k];
+			const int cls = sw_class_of_len(A->hlen[a0]);
+			const uint32_t W = (uint32_t)kClassWarps[cls];
+			const uint32_t begin = (uint32_t)e_clist.size();
+			uint32_t cnt = 0;
+			while (k < b.npairs && plan.sa[b.k0 + k] == a0 && cnt < W) {
+				if (!filter || keep[k]) {
+					e_clist.push_back(plan.sb[b.k0 + k]);
+					e_cslot.push_back((uint32_t)k);
+					cells += (uint64_t)A->hlen[a0] * B->hlen[plan.sb[b.k0 + k]];
+					++cnt;
+				}
+				++k;
+			}
+			if (cnt) {
+				e_row[cls].push_back(a0); e_begin[cls].push_back(begin); e_cnt[cls].push_back(cnt);
+			}
+		}
+		std::vector<uint32_t> trow, tbegin, tcnt;
+		for (int c = 0; c < kSwClasses; ++c) {
+			e_off[c] = (uint32_t)trow.size();
+			trow.insert(trow.end(), e_row[c].begin(), e_row[c].end());
+			tbegin.insert(tbegin.end(), e_begin[c].begin(), e_begin[c].end());
+			tcnt.insert(tcnt.end(), e_cnt[c].begin(), e_cnt[c].end());
+		}
+		e_off[kSwClasses] = (uint32_t)trow.size();
+		if ((rc = upload_vec(ctx, ctx->c_blist, e_clist)) || (rc = upload_vec(ctx, ctx->c_bslot, e_cslot)) ||
+			(rc = upload_vec(ctx, ctx->c_task_a, trow)) || (rc = upload_vec(ctx, ctx->c_task_begin, tbegin)) ||
+			(rc = upload_vec(ctx, ctx->c_task_cnt, tcnt)))
+			return rc;
+		CK(cudaStreamSynchronize(st));  // the host vectors die at the end of this scope
+		ctx->filt_explicit_pairs = e_clist.size();
+		ctx->filt_explicit_cells = cells;
+	}
+
+	// ---- K1: one launch per kernel class ----
 	SwArgs sa;
 	memset(&sa, 0, sizeof(sa));
-	sa.profA = A->d.prof8; sa.offA = A->d.off; sa.lenA = A->d.len;
-	if (!B->d.coloff) {
-		// first use of this set as the column side: derive the per-residue table offsets (32 B/residue)
-		rsk_chainset *Bm = const_cast<rsk_chainset *>(B);
-		if (cudaMalloc((void **)&Bm->d.coloff, (size_t)B->d.total * 32) != cudaSuccess) {
-			cudaGetLastError();
-			return fail(RSK_ERR_NOMEM, "column-offset table for %llu residues", (unsigned long long)B->d.total);
-		}
-		int nlc = launch_make_coloff(B->d.prof8, B->d.total, Bm->d.coloff, st);
-		if (nlc < 0)
-			return fail(RSK_ERR_CUDA, "make_coloff launch failed");
-		ctx->stats.kernel_launches += nlc;
-	}
-	sa.coloffB = B->d.coloff; sa.offB = B->d.off; sa.lenB = B->d.len;
-	sa.ntasks = b.ntasks;
-	sa.cross = (b.cross && !filter) ? 1 : 0;
-	sa.blist = ctx->blist.p;
-	if (filter && b.cross) {
-		sa.task_a = ctx->task_a.p; sa.task_begin = ctx->task_begin.p; sa.task_cnt = ctx->task_cnt.p;
-		sa.blist = ctx->c_blist.p; sa.bslot = ctx->c_bslot.p;
-		sa.ntasks_dev = &ctx->d_counters->task_count;
-	} else if (filter) {
-		sa.task_a = ctx->c_task_a.p; sa.task_begin = ctx->c_task_begin.p; sa.task_cnt = ctx->c_task_cnt.p;
-		sa.blist = ctx->c_blist.p; sa.bslot = ctx->c_bslot.p;
-		sa.ntasks = ctx->filt_explicit_tasks;
-	} else if (b.cross) {
-		sa.a_begin = b.a0;
-		sa.nB = B->d.n;
-		sa.nseg = (B->d.n + kSwWarps - 1) / kSwWarps;
-	} else {
-		sa.task_a = ctx->task_a.p; sa.task_begin = ctx->task_begin.p; sa.task_cnt = ctx->task_cnt.p;
-		sa.bslot = ctx->bslot.p;
-	}
+	sa.prof_row = Rw->d.prof8; sa.off_row = Rw->d.off; sa.len_row = Rw->d.len;
+	sa.coloff_col = Cl->d.coloff; sa.off_col = Cl->d.off; sa.len_col = Cl->d.len;
+	sa.tr = tr ? 1 : 0;
+	sa.a_begin = b.a0; sa.nB = B->d.n;
 	sa.trace = ctx->trace.p; sa.trace_stride = trace_stride;
 	sa.bnd = ctx->bnd.p; sa.bnd_stride = bnd_stride;
 	sa.stage = ctx->stage.p; sa.stage_stride = stage_stride;
 	sa.rec = ctx->rec.p;
 	sa.pool = ctx->pool.p; sa.pool_cursor = ctx->d_pool_cursor;
-	sa.task_counter = ctx->d_task_counter;
 	sa.tables = ctx->d_tables;
 	sa.open = ctx->params.gap_open; sa.ext = ctx->params.gap_ext;
 
 	CK(cudaEventRecord(ctx->ev[0], st));
-	int nl = 0;
-	if (!(filter && !b.cross && ctx->filt_explicit_tasks == 0))
-		nl = launch_sw(sa, (filter && b.cross) ? grid : std::min<int>(grid, (int)sa.ntasks), sw_smem_bytes(), st);
-	if (nl < 0)
-		return fail(RSK_ERR_CUDA, "SW kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-	ctx->stats.kernel_launches += nl;
+	for (int c = 0; c < kSwClasses; ++c) {
+		SwArgs sc = sa;
+		sc.task_counter = &ctx->d_counters->sw_task_counter[c];
+		int g = grid;
+		if (b.cross && !filter) {
+			const uint32_t nrows = row_off[c + 1] - row_off[c];
+			if (nrows == 0)
+				continue;
+			sc.cross = 1;
+			sc.rowlist = ctx->rowlist.p + row_off[c];
+			sc.ncols = ncols;
+			sc.nseg = (ncols + kClassWarps[c] - 1) / kClassWarps[c];
+			sc.clist = tr ? ctx->colsort.p : ctx->blist.p;
+			sc.ntasks = nrows * sc.nseg;
+			g = (int)std::min<uint64_t>((uint64_t)grid, sc.ntasks);
+		} else if (b.cross) {
+			if (row_off[c + 1] == row_off[c])
+				continue;  // no row chain of this class: its task list stays empty
+			sc.cross = 0;
+			sc.task_row = ctx->c_task_a.p + (size_t)c * task_cap;
+			sc.task_begin = ctx->c_task_begin.p + (size_t)c * task_cap;
+			sc.task_cnt = ctx->c_task_cnt.p + (size_t)c * task_cap;
+			sc.clist = ctx->c_blist.p; sc.cslot = ctx->c_bslot.p;
+			sc.ntasks_dev = &ctx->d_counters->task_count[c];
+		} else {
+			const uint32_t nt = e_off[c + 1] - e_off[c];
+			if (nt == 0)
+				continue;
+			sc.cross = 0;
+			sc.task_row = ctx->c_task_a.p + e_off[c];
+			sc.task_begin = ctx->c_task_begin.p + e_off[c];
+			sc.task_cnt = ctx->c_task_cnt.p + e_off[c];
+			sc.clist = ctx->c_blist.p; sc.cslot = ctx->c_bslot.p;
+			sc.ntasks = nt;
+			g = (int)std::min<uint32_t>((uint32_t)grid, nt);
+		}
+		int nl = launch_sw(sc, c, g, st);
+		if (nl < 0)
+			return fail(RSK_ERR_CUDA, "SW kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->stats.kernel_launches += nl;
+	}
 	CK(cudaEventRecord(ctx->ev[1], st));
 
 	if (!opts.skip_evalue) {
@@ -722,7 +807,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		la.maxcols = std::max(1u, std::min(b.maxLA, b.maxLB));
 		if ((size_t)la.maxcols * 7 * sizeof(float) > 220 * 1024)
 			return fail(RSK_ERR_LIMIT, "alignment of %u columns exceeds the LDDT kernel's shared-memory limit", la.maxcols);
-		nl = launch_lddt(la, st);
+		int nl = launch_lddt(la, st);
 		if (nl < 0)
 			return fail(RSK_ERR_CUDA, "LDDT kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->stats.kernel_launches += nl;

@@ -46,10 +46,25 @@ struct PairRec {
 static_assert(sizeof(PairRec) == 64, "PairRec layout");
 
 // ---- SW kernel geometry ----
-constexpr int kSwWarps = 16;                 // warps per CTA: each aligns one B chain against the CTA's A chain
+constexpr int kSwWarps = 16;                 // warps per CTA of the Mu filter kernel
 constexpr int kSwThreads = kSwWarps * 32;
 constexpr int kMaxRowsPerLane = 8;           // R: DP rows owned by one lane within a pass
 constexpr int kRowsPerPassMax = 32 * kMaxRowsPerLane;
+// SW kernel classes by rows per lane: R <= 5 | R == 6 | R >= 7, with the warps per CTA (= pairs per task) of each
+constexpr int kSwClasses = 3;
+#ifndef RSK_CLASS_W0
+#define RSK_CLASS_W0 20
+#endif
+#ifndef RSK_CLASS_W1
+#define RSK_CLASS_W1 16
+#endif
+#ifndef RSK_CLASS_W2
+#define RSK_CLASS_W2 16
+#endif
+constexpr int kClassWarps[kSwClasses] = {RSK_CLASS_W0, RSK_CLASS_W1, RSK_CLASS_W2};
+constexpr int kSwMaxWarps = 20;
+__host__ __device__ inline int sw_class_of_R(int R) { return R <= 5 ? 0 : R == 6 ? 1 : 2; }
+__host__ __device__ inline int sw_class_warps(int c) { return c == 0 ? RSK_CLASS_W0 : c == 1 ? RSK_CLASS_W1 : RSK_CLASS_W2; }
 
 // How a chain of LA rows is cut into passes of 32*R rows (R rows per lane).
 __host__ __device__ inline void sw_geometry(uint32_t LA, int &npass, int &R)
@@ -59,26 +74,32 @@ __host__ __device__ inline void sw_geometry(uint32_t LA, int &npass, int &R)
 	R = (int)((LA + 32u * npass - 1) / (32u * npass));
 	if (R < 1) R = 1;
 }
+__host__ __device__ inline int sw_class_of_len(uint32_t L)
+{
+	int npass, R;
+	sw_geometry(L, npass, R);
+	return sw_class_of_R(R);
+}
 
+// K1 arguments.  "row"/"col" are the kernel's view; tr says which reference slot supplies the rows.
 struct SwArgs {
-	// chains
-	const uint64_t *profA; const uint64_t *offA; const uint32_t *lenA;
-	const uint4 *coloffB; const uint64_t *offB; const uint32_t *lenB;
-	// tasks: one task = one A chain x up to kSwWarps B chains
+	const uint64_t *prof_row; const uint64_t *off_row; const uint32_t *len_row;
+	const uint4 *coloff_col; const uint64_t *off_col; const uint32_t *len_col;
+	uint32_t tr;             // 0: rows = reference A (DSSAligner query slot), 1: rows = reference B
+	// tasks: one task = one row chain x up to W column chains (W = warps of the kernel class)
 	uint32_t ntasks;
-	uint32_t cross;          // 1: task t -> a = a_begin + t / nseg, B's = blist[(t % nseg)*kSwWarps ...]
-	uint32_t a_begin;        // first A index of this batch (cross mode)
-	uint32_t nseg;           // segments per A chain (cross mode)
-	uint32_t nB;             // entries in blist (cross mode)
-	const uint32_t *task_a;      // explicit mode [ntasks]
-	const uint32_t *task_begin;  // explicit mode [ntasks] offset into blist/bslot
-	const uint32_t *task_cnt;    // explicit mode [ntasks] 1..kSwWarps
-	const uint32_t *blist;       // B chain indices
-	const uint32_t *bslot;       // explicit mode: record slot of each blist entry; cross: slot = (a-a_begin)*nB + b
 	const uint32_t *ntasks_dev;  // when non-null the task count is read from device memory (filter -> SW hand-off)
+	uint32_t cross;          // 1: task t -> row chain rowlist[t / nseg], columns clist[(t % nseg)*W ...]
+	const uint32_t *rowlist;
+	uint32_t nseg;           // segments per row chain = ceil(ncols / W)
+	uint32_t ncols;          // entries in clist (cross mode)
+	const uint32_t *clist;   // column chain indices (cross: sorted by length; explicit: per task)
+	const uint32_t *task_row, *task_begin, *task_cnt;  // explicit mode
+	const uint32_t *cslot;   // explicit mode: record slot of each clist entry
+	uint32_t a_begin, nB;    // cross mode: slot = (a - a_begin)*nB + b with (a,b) the reference indices
 	// scratch (per warp of the grid)
 	uint4 *trace; uint64_t trace_stride;   // uint4 units per warp
-	float2 *bnd; uint32_t bnd_stride;      // pass-boundary row (M, D) per column
+	float2 *bnd; uint32_t bnd_stride;      // pass-boundary row (M, vertical gap) per column
 	uint8_t *stage; uint32_t stage_stride; // reversed path staging
 	// outputs
 	PairRec *rec;
@@ -100,14 +121,17 @@ struct LddtArgs {
 	uint32_t maxcols;
 };
 
-// K3: Mu int8 SW filter over the full A x B rectangle of a batch
+// K3: Mu int8 SW filter; same row/column task model as K1 (16 warps per CTA)
 struct MuArgs {
-	const uint8_t *muA; const uint64_t *offA; const uint32_t *lenA;
-	const uint8_t *muB; const uint64_t *offB; const uint32_t *lenB;
-	uint32_t ntasks, a_begin, nseg, nB;
-	uint32_t cross;             // 1: rectangle tasks (see SwArgs); 0: explicit task arrays below
-	const uint32_t *task_a, *task_begin, *task_cnt, *bslot;
-	const uint32_t *blist;      // B indices sorted by length
+	const uint8_t *mu_row; const uint64_t *off_row; const uint32_t *len_row;
+	const uint8_t *mu_col; const uint64_t *off_col; const uint32_t *len_col;
+	uint32_t tr;
+	uint32_t ntasks;
+	uint32_t cross;
+	const uint32_t *rowlist; uint32_t nseg; uint32_t ncols;
+	const uint32_t *clist;
+	const uint32_t *task_row, *task_begin, *task_cnt, *cslot;  // explicit mode
+	uint32_t a_begin, nB;
 	int2 *bnd; uint32_t bnd_stride;
 	PairRec *rec;
 	uint8_t *keep;              // [batch pairs] 1 = passes the filter
@@ -116,31 +140,33 @@ struct MuArgs {
 	const int *mu_mx;           // IntScoreMx_Mu as int32 [36*36]
 	int open, ext;
 	float omega, omega_fwd;
-	uint32_t mkfl;              // pairs with LA >= mkfl or LB >= mkfl belong to the k-mer/x-drop path (dssaligner.cpp:715-732)
+	uint32_t mkfl;              // pairs with a chain >= mkfl belong to the k-mer/x-drop path (dssaligner.cpp:715-732)
 };
 
-// survivor compaction: keep flags -> SW tasks (explicit-mode arrays of SwArgs)
+// survivor compaction: keep flags -> per-class SW task lists (explicit-mode arrays of SwArgs)
 struct CompactArgs {
-	uint32_t a_begin, nB;
-	const uint32_t *blist;
+	uint32_t tr, a_begin, nB;
+	const uint32_t *rowlist; uint32_t ncols;
+	const uint32_t *clist;
 	const uint8_t *keep;
-	const uint32_t *lenA; const uint32_t *lenB;
-	uint32_t *out_blist, *out_bslot;   // [nA_batch * nB]
-	uint32_t *task_a, *task_begin, *task_cnt;
-	uint32_t *task_count;              // device counters
+	const uint32_t *len_row; const uint32_t *len_col;
+	uint32_t *out_clist, *out_cslot;   // [nrows * ncols]
+	uint32_t *task_row, *task_begin, *task_cnt;  // [kSwClasses * task_cap]
+	uint32_t task_cap;
+	uint32_t *task_count;              // [kSwClasses] device counters
 	unsigned long long *pair_count;
 	unsigned long long *cell_count;
 };
 
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
-int launch_sw(const SwArgs &args, int grid, size_t smem, cudaStream_t stream);
+int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();
 uint64_t sw_trace_units(int npass, uint32_t LB);
 int launch_make_coloff(const uint64_t *prof8, uint64_t total, uint4 *coloff, cudaStream_t stream);
 int launch_lddt(const LddtArgs &args, cudaStream_t stream);
 int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);
 size_t mu_smem_bytes();
-int launch_compact_survivors(const CompactArgs &args, uint32_t nA, cudaStream_t stream);
+int launch_compact_survivors(const CompactArgs &args, uint32_t nrows, cudaStream_t stream);
 int launch_pack_profiles(const uint8_t *planes, uint64_t total, uint64_t *prof8, cudaStream_t stream);
 
 }  // namespace rsk

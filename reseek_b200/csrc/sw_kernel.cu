@@ -22,7 +22,10 @@
 //  * The running maximum is tracked per lane with one FMNMX3 chain per step; the exact first-maximum rule of
 //    the reference (row-major order, strict >) is restored in a rarely taken slow path and in the final
 //    (score desc, row asc) warp reduction.
-//  * Persistent CTAs (one per SM) pull tasks from an atomic counter.
+//  * Either chain of a pair can supply the rows (template TR): the scheduler puts the side with fewer chains on
+//    the rows so that a CTA's row table is shared by a full set of warps.
+//  * Persistent CTAs (one per SM) pull tasks from an atomic counter; one kernel per row-length class so that
+//    short row blocks (few registers) run with 24 warps per SM and long ones with 16.
 #include <type_traits>
 
 #include "rsk_internal.cuh"
@@ -39,8 +42,8 @@ constexpr size_t kSmemTab = 0;                          // float[2192] weighted 
 constexpr size_t kSmemP0 = 8768;                        // plane 0: float4[132][32], rows 0..3 of each lane
 constexpr size_t kPlaneBytes = (size_t)kNLet * 512;     // 67584
 constexpr size_t kSmemP1 = kSmemP0 + kPlaneBytes;       // plane 1: rows 4..R-1, same 512-byte stride per code
-constexpr size_t kSmemTiles = kSmemP1 + kPlaneBytes;    // uint4[kSwWarps][4][32] traceback tiles
-constexpr size_t kSmemBcast = kSmemTiles + (size_t)kSwWarps * 4 * 32 * 16;
+constexpr size_t kSmemTiles = kSmemP1 + kPlaneBytes;    // uint4[warps][4][32] traceback tiles
+constexpr size_t kSmemBcast = kSmemTiles + (size_t)kSwMaxWarps * 4 * 32 * 16;
 constexpr size_t kSmemTotal = kSmemBcast + 16;
 
 // floats per lane in plane 1 for R rows per lane (R-4 rounded up to a vector width)
@@ -49,14 +52,14 @@ __host__ __device__ constexpr int plane1_width(int R) { return R <= 4 ? 0 : R ==
 // table value of rows beyond the end of the chain: such cells are hugely negative and can never be a maximum
 constexpr float kPadScore = -1e30f;
 
-template <int R>
+template <int R, int NTHREADS>
 __device__ __forceinline__ void build_rowtab(float *p0, float *p1, const float *tab, const uint64_t *__restrict__ profA,
 		uint32_t LA, int pass)
 {
 	constexpr int W1 = plane1_width(R);
 	constexpr int ROWS = 32 * R;
 	const uint32_t rowbase = (uint32_t)pass * ROWS;
-	for (int idx = threadIdx.x; idx < kNLet * ROWS; idx += kSwThreads) {
+	for (int idx = threadIdx.x; idx < kNLet * ROWS; idx += NTHREADS) {
 		const int e = idx / ROWS;
 		const int rr = idx - e * ROWS;
 		const int l = rr / R;
@@ -96,16 +99,68 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr)
 	return v;
 }
 
+// Packed fp32 add (FADD2 on sm_100a): two independent IEEE round-to-nearest adds in one issue slot.
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b)
+{
+	unsigned long long ra, rb, rd;
+	asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+	asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+	float2 d;
+	asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+	return d;
+}
+
+// out[r] = in[r] + c for r < N, two rows per instruction
+template <int N>
+__device__ __forceinline__ void add_const(float (&out)[N], const float (&in)[N], const float c)
+{
+#pragma unroll
+	for (int r = 0; r + 1 < N; r += 2) {
+		const float2 t = add2(make_float2(in[r], in[r + 1]), make_float2(c, c));
+		out[r] = t.x;
+		out[r + 1] = t.y;
+	}
+	if (N & 1)
+		out[N - 1] = in[N - 1] + c;
+}
+
+// acc[r] += v[r] for r < N, two rows per instruction
+template <int N>
+__device__ __forceinline__ void add_vec(float (&acc)[N], const float (&v)[8])
+{
+#pragma unroll
+	for (int r = 0; r + 1 < N; r += 2) {
+		const float2 t = add2(make_float2(acc[r], acc[r + 1]), make_float2(v[r], v[r + 1]));
+		acc[r] = t.x;
+		acc[r + 1] = t.y;
+	}
+	if (N & 1)
+		acc[N - 1] = acc[N - 1] + v[N - 1];
+}
+
 // One pass: rows [pass*32R, (pass+1)*32R) of A against all LB columns of B.
 // colB: two uint4 per column = the column's 8 table offsets in units of 16 bytes (code * 32).
-template <int R>
-__device__ __forceinline__ void sw_pass(const uint32_t smem_p0, const int lane, const int pass, const int npass,
+// TR = false: kernel rows are the reference's A chain (index i), columns its B chain (j).
+// TR = true : rows are the reference's B chain, columns its A chain.  The recurrence is the same with the
+//             roles of the two gap states exchanged: the reference tests D (gap that consumes A) before I
+//             (sw.cpp:136-147), and its first-maximum rule prefers the smaller i, then the smaller j.
+// lbi/lbj are in kernel coordinates (row, column).
+template <int R, bool TR>
+__device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int lane, const int pass, const int npass,
 		const uint32_t LA, const uint4 *__restrict__ colB, const int LB, float2 *__restrict__ bnd,
 		uint4 *__restrict__ trace_pass, const float open, const float ext, float &lbest, int &lbi, int &lbj)
 {
 	constexpr int W1 = plane1_width(R);
-	const uint32_t base0 = smem_p0 + (uint32_t)lane * 16u;
-	const uint32_t base1 = smem_p0 + (uint32_t)kPlaneBytes + (uint32_t)lane * (uint32_t)(W1 * 4);
+	// Per-lane byte offsets into the two planes.  They are made opaque to the optimiser so that "offset*16 + lane
+	// term" stays one IMAD; the loads themselves are ordinary shared-memory loads (LDS with the plane base folded into
+	// the immediate) which the scheduler may hoist above the warp shuffles of the next step.
+	uint32_t base0 = (uint32_t)lane * 16u;
+	uint32_t base1 = (uint32_t)lane * (uint32_t)(W1 * 4);
+	asm volatile("" : "+r"(base0));
+	asm volatile("" : "+r"(base1));
+	const unsigned char *const plane0 = smem_p0;
+	const unsigned char *const plane1 = smem_p0 + kPlaneBytes;
 	float Mrow[R], Irow[R];
 #pragma unroll
 	for (int r = 0; r < R; ++r) {
@@ -148,65 +203,96 @@ __device__ __forceinline__ void sw_pass(const uint32_t smem_p0, const int lane, 
 		uint32_t tw = 0;
 		if (!CHECK || (j >= 0 && j < LB)) {
 			float d = lane0 ? bn.y : inD;  // D[i0][j]   (bn = -inf pair in the first pass)
-			float mdiag = mdiag_next;      // M[i0][j]
+			const float mdiag = mdiag_next;  // M[i0][j]
 			mdiag_next = lane0 ? bn.x : inM;  // M[i0][j+1]
 			const uint32_t co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 			float S[R];
 #pragma unroll
 			for (int f = 0; f < RSK_NFEAT; ++f) {
 				const uint32_t a0 = co[f] * 16u + base0;
-				const float4 v0 = lds_f32x4(a0);
+				const float4 v0 = *reinterpret_cast<const float4 *>(plane0 + a0);
 				float v[8];
 				v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
 				v[4] = v[5] = v[6] = v[7] = 0.0f;
 				if (W1 == 1) {
-					v[4] = lds_f32(co[f] * 16u + base1);
+					v[4] = *reinterpret_cast<const float *>(plane1 + (co[f] * 16u + base1));
 				} else if (W1 == 2) {
-					const float2 t = lds_f32x2(co[f] * 16u + base1);
+					const float2 t = *reinterpret_cast<const float2 *>(plane1 + (co[f] * 16u + base1));
 					v[4] = t.x; v[5] = t.y;
 				} else if (W1 == 4) {
-					const float4 t = lds_f32x4(a0 + (uint32_t)kPlaneBytes);
+					const float4 t = *reinterpret_cast<const float4 *>(plane1 + a0);
 					v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w;
 				}
+				// feature 0 assigns, 1..7 accumulate in this order (dssaligner.cpp:557-595)
+				if (f == 0) {
 #pragma unroll
-				for (int r = 0; r < R; ++r)
-					S[r] = (f == 0) ? v[r] : S[r] + v[r];  // feature 0 assigns, 1..7 accumulate (dssaligner.cpp:557-595)
+					for (int r = 0; r < R; ++r)
+						S[r] = v[r];
+				} else {
+					add_vec<R>(S, v);
+				}
 			}
+			// the adds that do not depend on this column's gap chain, two rows at a time
+			float Mdg[R], Mo[R], Ie[R];  // M[i][j] of each row, M[i][j] + open, horizontal gap state + ext
+			Mdg[0] = mdiag;
+#pragma unroll
+			for (int r = 1; r < R; ++r)
+				Mdg[r] = Mrow[r - 1];
+			Mo[0] = mdiag + open;
+			if (R > 1) {
+				float prev[R > 1 ? R - 1 : 1], po[R > 1 ? R - 1 : 1];
+#pragma unroll
+				for (int r = 0; r + 1 < R; ++r)
+					prev[r] = Mrow[r];
+				add_const<(R > 1 ? R - 1 : 1)>(po, prev, open);
+#pragma unroll
+				for (int r = 1; r < R; ++r)
+					Mo[r] = po[r - 1];
+			}
+			add_const<R>(Ie, Irow, ext);
 			float xmax = kNegInf;
 #pragma unroll
 			for (int r = 0; r < R; ++r) {
-				const float m = mdiag;  // M[i][j]
-				mdiag = Mrow[r];        // becomes M[i+1][j] for the next row
+				const float m = Mdg[r];  // M[i][j]
 				const float ii = Irow[r];
 				float x = m;
 				uint32_t code = 0;
-				if (d > x) { x = d; code = 1; }
-				if (ii > x) { x = ii; code = 2; }
+				// code: 1 = reference D state (consumes A), 2 = reference I state; D is tested first
+				if (!TR) {
+					if (d > x) { x = d; code = 1; }
+					if (ii > x) { x = ii; code = 2; }
+				} else {
+					if (ii > x) { x = ii; code = 1; }
+					if (d > x) { x = d; code = 2; }
+				}
 				if (0.0f >= x) { x = 0.0f; code = 3; }
 				x += S[r];
 				xmax = fmaxf(xmax, x);
-				Mrow[r] = x;  // M[i+1][j+1]
-				const float mo = m + open;
+				Mrow[r] = x;  // M[row+1][col+1]
+				const float mo = Mo[r];
 				float dn = d + ext;
-				if (mo >= dn) { dn = mo; code |= 4u; }
-				d = dn;  // D[i+1][j]
-				float in2 = ii + ext;
-				if (mo >= in2) { in2 = mo; code |= 8u; }
-				Irow[r] = in2;  // I[i][j+1]
+				if (mo >= dn) { dn = mo; code |= TR ? 8u : 4u; }
+				d = dn;  // vertical gap state entering the next row
+				float in2 = Ie[r];
+				if (mo >= in2) { in2 = mo; code |= TR ? 4u : 8u; }
+				Irow[r] = in2;  // horizontal gap state entering the next column
 				tw |= code << (4 * r);
 			}
 			outM = Mrow[R - 1];
 			outD = d;
 			if (put_bnd)
 				bnd[j] = make_float2(outM, outD);
-			if (xmax >= lbest) {
-				// rare: a cell reached the lane's running maximum.  Keep the reference's first-maximum rule:
-				// higher score wins; equal score -> smaller row; same row -> the earlier column (already stored).
+			if (TR ? (xmax > lbest) : (xmax >= lbest)) {
+				// rare: a cell reached the lane's running maximum.  Keep the reference's first-maximum rule
+				// (row-major over (i,j), strict >).  !TR: higher score wins; equal score -> smaller row i; same row ->
+				// the earlier column (already stored).  TR: columns are i and are visited in ascending order, rows (j)
+				// ascending within a step, so the first cell seen with a score is already the right one: strict > only.
 #pragma unroll
 				for (int r = 0; r < R; ++r) {
 					const float x = Mrow[r];
 					const int row = (int)(row0 + r);
-					if ((x > lbest || (x == lbest && row < lbi)) && (uint32_t)row < LA) {
+					const bool better = TR ? (x > lbest) : (x > lbest || (x == lbest && row < lbi));
+					if (better && (uint32_t)row < LA) {
 						lbest = x;
 						lbi = row;
 						lbj = j;
@@ -242,7 +328,8 @@ __device__ __forceinline__ void sw_pass(const uint32_t smem_p0, const int lane, 
 // Warp-cooperative traceback (sw.cpp:8-77) through a 2 KB shared tile of the packed trace.
 // Trace word of cell (row, col): pass p = row / (32R), lane l = (row % 32R) / R, nibble r = row % R,
 // step s = col + l, group g = s / 4, word s % 4 of uint4 trace[(p*ngroups + g)*32 + l].
-__device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int lane, const int R, const int LB,
+// bi/bj and the walk are in reference coordinates (i over A, j over B); tr maps them onto the kernel's (row, column).
+__device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int lane, const int R, const int LB, const bool tr,
 		const uint4 *__restrict__ trace, uint4 *tile, uint8_t *stage, const float score, const int bi, const int bj,
 		PairRec *rec)
 {
@@ -259,11 +346,12 @@ __device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int la
 		++n;
 		const int ci = (state == 2) ? i : i - 1;
 		const int cj = (state == 1) ? j : j - 1;
-		const int p = ci / rows_per_pass;
-		const int rr = ci - p * rows_per_pass;
+		const int krow = tr ? cj : ci, kcol = tr ? ci : cj;
+		const int p = krow / rows_per_pass;
+		const int rr = krow - p * rows_per_pass;
 		const int srcl = rr / R;
 		const int r = rr - srcl * R;
-		const int s = cj + srcl;
+		const int s = kcol + srcl;
 		const int g = s >> 2;
 		const int G = g >> 2;
 		if (p != cur_p || G != cur_G) {
@@ -311,56 +399,66 @@ __device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int la
 	}
 }
 
-template <int R>
-__device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *smem, const uint32_t ai,
-		const uint32_t begin, const uint32_t cnt, const uint32_t slot_base)
+template <int R, bool TR, int W>
+__device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *smem, const uint32_t rowchain,
+		const uint32_t begin, const uint32_t cnt)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const float *tab = reinterpret_cast<const float *>(smem + kSmemTab);
 	float *p0 = reinterpret_cast<float *>(smem + kSmemP0);
 	float *p1 = reinterpret_cast<float *>(smem + kSmemP1);
-	const uint32_t smem_p0 = (uint32_t)__cvta_generic_to_shared(p0);
+	const unsigned char *smem_p0 = smem + kSmemP0;
 	uint4 *tile = reinterpret_cast<uint4 *>(smem + kSmemTiles) + warp * 128;
 
-	const uint32_t LA = a.lenA[ai];
-	const uint64_t *profA = a.profA + a.offA[ai];
+	const uint32_t LA = a.len_row[rowchain];  // kernel rows
+	const uint64_t *profA = a.prof_row + a.off_row[rowchain];
 	const int npass = (int)((LA + 32 * R - 1) / (32 * R));
 
 	const bool have = (uint32_t)warp < cnt;
-	uint32_t bidx = 0, slot = 0;
-	int LB = 0;
+	uint32_t cidx = 0, slot = 0;
+	int LB = 0;  // kernel columns
 	const uint4 *colB = nullptr;
 	if (have) {
-		bidx = a.blist[begin + warp];
-		slot = a.cross ? slot_base + bidx : a.bslot[begin + warp];
-		LB = (int)a.lenB[bidx];
-		colB = a.coloffB + 2 * a.offB[bidx];
+		cidx = a.clist[begin + warp];
+		if (a.cross) {
+			const uint32_t ra = TR ? cidx : rowchain, rb = TR ? rowchain : cidx;  // reference (a, b)
+			slot = (ra - a.a_begin) * a.nB + rb;
+		} else {
+			slot = a.cslot[begin + warp];
+		}
+		LB = (int)a.len_col[cidx];
+		colB = a.coloff_col + 2 * a.off_col[cidx];
 	}
 	const int ngroups = (LB + 31 + 3) >> 2;
-	const size_t gw = (size_t)blockIdx.x * kSwWarps + warp;
+	const size_t gw = (size_t)blockIdx.x * W + warp;
 	uint4 *trace = a.trace + gw * a.trace_stride;
 	float2 *bnd = a.bnd + gw * a.bnd_stride;
 	uint8_t *stage = a.stage + gw * a.stage_stride;
 
 	float lbest = 0.0f;
-	int lbi = 0x7fffffff, lbj = 0;
+	int lbi = 0x7fffffff, lbj = 0x7fffffff;  // kernel (row, column) of the best cell
 	for (int pass = 0; pass < npass; ++pass) {
 		__syncthreads();  // every warp is done with the previous pass's row table
-		build_rowtab<R>(p0, p1, tab, profA, LA, pass);
+		build_rowtab<R, W * 32>(p0, p1, tab, profA, LA, pass);
 		__syncthreads();
 		if (have)
-			sw_pass<R>(smem_p0, lane, pass, npass, LA, colB, LB, bnd, trace + (size_t)pass * ngroups * 32,
+			sw_pass<R, TR>(smem_p0, lane, pass, npass, LA, colB, LB, bnd, trace + (size_t)pass * ngroups * 32,
 					a.open, a.ext, lbest, lbi, lbj);
 	}
 	if (!have)
 		return;
-	// first maximum in row-major order: max score, ties -> smallest row (a row lives in exactly one lane)
+	// first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j
 #pragma unroll
 	for (int o = 16; o >= 1; o >>= 1) {
 		const float os = __shfl_xor_sync(kFull, lbest, o);
 		const int oi = __shfl_xor_sync(kFull, lbi, o);
 		const int oj = __shfl_xor_sync(kFull, lbj, o);
-		if (os > lbest || (os == lbest && oi < lbi)) {
+		bool take;
+		if (!TR)  // i = row (unique per lane), j = column
+			take = os > lbest || (os == lbest && oi < lbi);
+		else      // i = column, j = row
+			take = os > lbest || (os == lbest && (oj < lbj || (oj == lbj && oi < lbi)));
+		if (take) {
 			lbest = os; lbi = oi; lbj = oj;
 		}
 	}
@@ -376,15 +474,19 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 		return;
 	}
 	__syncwarp();  // trace words written by other lanes of this warp are visible
-	traceback_and_emit(a, lane, R, LB, trace, tile, stage, lbest, lbi, lbj, rec);
+	traceback_and_emit(a, lane, R, LB, TR, trace, tile, stage, lbest, TR ? lbj : lbi, TR ? lbi : lbj, rec);
 }
 
-__global__ void __launch_bounds__(kSwThreads, 1) sw_affine_f32_tb_kernel(const SwArgs a)
+// One kernel per (row-length class, orientation).  Class C handles R in [kClassRLo[C], kClassRHi[C]] with
+// kClassWarps[C] warps: fewer rows per lane need fewer registers, so more warps fit and hide latency better.
+template <int C, bool TR>
+__global__ void __launch_bounds__(kClassWarps[C] * 32, 1) sw_affine_f32_tb_kernel(const SwArgs a)
 {
+	constexpr int W = kClassWarps[C];
 	extern __shared__ __align__(16) unsigned char smem[];
 	float *tab = reinterpret_cast<float *>(smem + kSmemTab);
 	volatile int *bcast = reinterpret_cast<volatile int *>(smem + kSmemBcast);
-	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += kSwThreads)
+	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += W * 32)
 		tab[k] = a.tables[k];
 	__syncthreads();
 	const uint32_t ntasks = a.ntasks_dev ? *a.ntasks_dev : a.ntasks;
@@ -396,30 +498,35 @@ __global__ void __launch_bounds__(kSwThreads, 1) sw_affine_f32_tb_kernel(const S
 		__syncthreads();
 		if (task >= ntasks)
 			break;
-		uint32_t ai, begin, cnt, slot_base = 0;
+		uint32_t rowchain, begin, cnt;
 		if (a.cross) {
-			const uint32_t arel = task / a.nseg;
-			const uint32_t seg = task - arel * a.nseg;
-			ai = a.a_begin + arel;
-			begin = seg * kSwWarps;
-			cnt = min((uint32_t)kSwWarps, a.nB - begin);
-			slot_base = arel * a.nB;
+			const uint32_t ridx = task / a.nseg;
+			const uint32_t seg = task - ridx * a.nseg;
+			rowchain = a.rowlist[ridx];
+			begin = seg * W;
+			cnt = min((uint32_t)W, a.ncols - begin);
 		} else {
-			ai = a.task_a[task];
+			rowchain = a.task_row[task];
 			begin = a.task_begin[task];
 			cnt = a.task_cnt[task];
 		}
 		int npass, R;
-		sw_geometry(a.lenA[ai], npass, R);
-		switch (R) {
-		case 1: process_task<1>(a, smem, ai, begin, cnt, slot_base); break;
-		case 2: process_task<2>(a, smem, ai, begin, cnt, slot_base); break;
-		case 3: process_task<3>(a, smem, ai, begin, cnt, slot_base); break;
-		case 4: process_task<4>(a, smem, ai, begin, cnt, slot_base); break;
-		case 5: process_task<5>(a, smem, ai, begin, cnt, slot_base); break;
-		case 6: process_task<6>(a, smem, ai, begin, cnt, slot_base); break;
-		case 7: process_task<7>(a, smem, ai, begin, cnt, slot_base); break;
-		default: process_task<8>(a, smem, ai, begin, cnt, slot_base); break;
+		sw_geometry(a.len_row[rowchain], npass, R);
+		if (C == 0) {
+			switch (R) {
+			case 1: process_task<1, TR, W>(a, smem, rowchain, begin, cnt); break;
+			case 2: process_task<2, TR, W>(a, smem, rowchain, begin, cnt); break;
+			case 3: process_task<3, TR, W>(a, smem, rowchain, begin, cnt); break;
+			case 4: process_task<4, TR, W>(a, smem, rowchain, begin, cnt); break;
+			default: process_task<5, TR, W>(a, smem, rowchain, begin, cnt); break;
+			}
+		} else if (C == 1) {
+			process_task<6, TR, W>(a, smem, rowchain, begin, cnt);
+		} else {
+			if (R == 7)
+				process_task<7, TR, W>(a, smem, rowchain, begin, cnt);
+			else
+				process_task<8, TR, W>(a, smem, rowchain, begin, cnt);
 		}
 	}
 }
@@ -464,12 +571,23 @@ size_t sw_smem_bytes() { return kSmemTotal; }
 // uint4 units of packed trace one warp needs for a pair with npass passes and LB columns
 uint64_t sw_trace_units(int npass, uint32_t LB) { return (uint64_t)npass * ((LB + 31 + 3) >> 2) * 32; }
 
-int launch_sw(const SwArgs &args, int grid, size_t smem, cudaStream_t stream)
+template <int C, bool TR>
+static int launch_sw_ct(const SwArgs &args, int grid, cudaStream_t stream)
 {
-	if (cudaFuncSetAttribute(sw_affine_f32_tb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal) != cudaSuccess)
+	if (cudaFuncSetAttribute(sw_affine_f32_tb_kernel<C, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal) != cudaSuccess)
 		return -1;
-	sw_affine_f32_tb_kernel<<<grid, kSwThreads, smem, stream>>>(args);
+	sw_affine_f32_tb_kernel<C, TR><<<grid, kClassWarps[C] * 32, kSmemTotal, stream>>>(args);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream)
+{
+	const bool tr = args.tr != 0;
+	switch (cls) {
+	case 0: return tr ? launch_sw_ct<0, true>(args, grid, stream) : launch_sw_ct<0, false>(args, grid, stream);
+	case 1: return tr ? launch_sw_ct<1, true>(args, grid, stream) : launch_sw_ct<1, false>(args, grid, stream);
+	default: return tr ? launch_sw_ct<2, true>(args, grid, stream) : launch_sw_ct<2, false>(args, grid, stream);
+	}
 }
 
 int launch_pack_profiles(const uint8_t *planes, uint64_t total, uint64_t *prof8, cudaStream_t stream)

@@ -6,7 +6,7 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libreseek_b200.so"
+LIB_PATH = Path(os.environ.get("RSK_LIB", HERE / "libreseek_b200.so"))  # RSK_LIB: developer override for A/B builds
 
 NFEAT = 8
 TABLE_FLOATS = 2192

@@ -126,3 +126,32 @@ def test_golden_reference_fixtures_on_gpu(rb, mode):
 def test_smoke_entry(rb):
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_both_orientations_and_all_row_classes(rb, port):
+    """The scheduler puts the smaller set on the kernel's rows (transposed DP) and picks a kernel class by row
+    length: cover rows = A and rows = B for lengths that hit every R = 1..8 and multi-pass tables, with exact
+    score ties (duplicated chains) so that the first-maximum rule is exercised in both orientations."""
+    from reseek_b200 import synth
+    from tests.util import to_oracle_chains
+    lens = [20, 33, 70, 100, 129, 161, 193, 225, 250, 300, 420, 530]
+    small = synth.make_chains(len(lens), lens, seed=4242)
+    big = synth.make_chains(40, 140, seed=4343, length_jitter=0.6)
+    synth.plant_homologs(big, small, 0.7, seed=4444, sub=0.2)
+    # internal repeats -> equal best scores at different cells
+    for i in range(0, big.n, 5):
+        s, e = int(big.off[i]), int(big.off[i + 1])
+        h = (e - s) // 2
+        big.prof[:, s + h:s + 2 * h] = big.prof[:, s:s + h]
+        big.xyz[:, s + h:s + 2 * h] = big.xyz[:, s:s + h]
+    ctx = rb.Context(0, rb.MODE_VERYSENSITIVE)
+    S = ctx.upload(small.lens, small.prof, small.mu, small.xyz, small.selfrev)
+    Bg = ctx.upload(big.lens, big.prof, big.mu, big.xyz, big.selfrev)
+    os_, ob = to_oracle_chains(small), to_oracle_chains(big)
+    res = ctx.search_cross(S, Bg, keep=rb.KEEP_ALL)     # A = small (12 chains), B = big (40): rows = A
+    _check_all(rb, port(3), res, os_, ob)
+    res = ctx.search_cross(Bg, S, keep=rb.KEEP_ALL)     # A = big, B = small: rows = B (transposed kernel)
+    _check_all(rb, port(3), res, ob, os_)
+    res = ctx.search_self(Bg, keep=rb.KEEP_ALL)
+    _check_all(rb, port(3), res, ob, ob)
+    ctx.close()
