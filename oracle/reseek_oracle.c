@@ -372,8 +372,394 @@ static void clear_result(orc_result *r)
 	r->lddt = 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Long-chain path
+ * ------------------------------------------------------------------------------------------------ */
+int orc_mu_xdrop(const uint8_t *Q, int LQ, const uint8_t *T, int LT, int PosQ, int PosT, int X, int *Loi, int *Loj, int *Len)
+{
+	*Loi = PosQ;
+	*Loj = PosT;
+	int fwd = 0, bestfwd = 0, fwdlen = 0;
+	for (int i = PosQ, j = PosT; i < LQ && j < LT; ) {
+		fwd += rsk_tbl_mu_i8[36 * Q[i] + T[j]];
+		++i; ++j;
+		if (fwd > bestfwd) { bestfwd = fwd; fwdlen = i - PosQ; }
+		else if (fwd + X < bestfwd) break;
+	}
+	int rev = 0, bestrev = 0, revlen = 0;
+	for (int i = PosQ - 1, j = PosT - 1; i >= 0 && j >= 0; --i, --j) {
+		rev += rsk_tbl_mu_i8[36 * Q[i] + T[j]];
+		if (rev > bestrev) { bestrev = rev; *Loi = i; *Loj = j; revlen = PosQ - i; }
+		else if (rev + X < bestrev) break;
+	}
+	*Len = fwdlen + revlen;
+	return bestfwd + bestrev;
+}
+
+/* 1-D chaining of intervals on the query axis (chainer.cpp:31-194).  Breakpoints sorted by position, interval
+ * starts before interval ends at equal positions; remaining ties keep input order (stable). */
+static float chain_hsps(const orc_hsp *h, int n, int *idx_out, int *nidx)
+{
+	*nidx = 0;
+	if (n == 0)
+		return 0;
+	typedef struct { uint32_t pos; int is_lo; int index; } bp_t;
+	bp_t *bp = (bp_t *)malloc(sizeof(bp_t) * 2 * n);
+	for (int i = 0; i < n; ++i) {
+		bp[2 * i].pos = (uint32_t)h[i].loi; bp[2 * i].is_lo = 1; bp[2 * i].index = i;
+		bp[2 * i + 1].pos = (uint32_t)(h[i].loi + h[i].len - 1); bp[2 * i + 1].is_lo = 0; bp[2 * i + 1].index = i;
+	}
+	for (int i = 1; i < 2 * n; ++i) { /* stable insertion sort */
+		bp_t t = bp[i];
+		int k = i - 1;
+		while (k >= 0 && (bp[k].pos > t.pos || (bp[k].pos == t.pos && !bp[k].is_lo && t.is_lo))) {
+			bp[k + 1] = bp[k];
+			--k;
+		}
+		bp[k + 1] = t;
+	}
+	float *cs = (float *)malloc(sizeof(float) * n);
+	int *tb = (int *)malloc(sizeof(int) * n);
+	int best_end = -1;
+	for (int i = 0; i < 2 * n; ++i) {
+		const int ix = bp[i].index;
+		const float sc = (float)h[ix].score;
+		if (bp[i].is_lo) {
+			tb[ix] = best_end;
+			cs[ix] = best_end < 0 ? sc : cs[best_end] + sc;
+		} else if (best_end < 0 || cs[ix] > cs[best_end]) {
+			best_end = ix;
+		}
+	}
+	float total = 0;
+	for (int ix = best_end; ix >= 0; ix = tb[ix]) {
+		total += (float)h[ix].score;
+		idx_out[(*nidx)++] = ix;
+	}
+	free(bp); free(cs); free(tb);
+	return total;
+}
+
+int orc_mkf_align(const orc_params *p, const uint8_t *muQ, int LQ, const uint8_t *muT, int LT,
+		orc_hsp *hsps, int cap, int *nhsp, int *best_hsp_score, int *best_chain_score, int *chain_idx, int *nchain)
+{
+	*nhsp = 0; *best_hsp_score = 0; *best_chain_score = 0; *nchain = 0;
+	if (LQ < 3 || LT < 3)
+		return 0;
+	/* query hash: the first 4 positions of every 3-mer (mukmerfilter.cpp:208-230) */
+	const int D = 36 * 36 * 36;
+	uint16_t *ht = (uint16_t *)malloc(sizeof(uint16_t) * 4 * D);
+	memset(ht, 0xff, sizeof(uint16_t) * 4 * D);
+	for (int pos = 0; pos + 3 <= LQ; ++pos) {
+		const int k = (muQ[pos] * 36 + muQ[pos + 1]) * 36 + muQ[pos + 2];
+		for (int w = 0; w < 4; ++w)
+			if (ht[4 * k + w] == 0xffff) { ht[4 * k + w] = (uint16_t)pos; break; }
+	}
+	int found = 0, best = 0, n = 0;
+	for (int pt = 0; pt + 3 <= LT; ++pt) {
+		const int k = (muT[pt] * 36 + muT[pt + 1]) * 36 + muT[pt + 2];
+		for (int w = 0; w < 4; ++w) {
+			const int pq = ht[4 * k + w];
+			if (pq == 0xffff)
+				continue;
+			int loi, loj, len;
+			const int sc = orc_mu_xdrop(muQ, LQ, muT, LT, pq, pt, p->mkf_x1, &loi, &loj, &len);
+			if (sc >= p->mkf_min_hsp_score) {
+				found = 1;
+				if (sc > best) { /* order-dependent gating, mukmerfilter.cpp:354-377 */
+					best = sc;
+					int old = 0;
+					for (int i = 0; i < n; ++i)
+						if (hsps[i].loi == loi) { old = 1; break; }
+					if (!old && n < cap) {
+						hsps[n].loi = loi; hsps[n].loj = loj; hsps[n].len = len; hsps[n].score = sc;
+						++n;
+					}
+				}
+			}
+		}
+	}
+	free(ht);
+	*nhsp = n;
+	*best_hsp_score = best;
+	if (found)
+		*best_chain_score = (int)chain_hsps(hsps, n, chain_idx, nchain);
+	return found;
+}
+
+float orc_mega_hsp_score(const orc_params *p, const uint8_t *profA, uint32_t LA, const uint8_t *profB, uint32_t LB,
+		uint32_t lo_i, uint32_t lo_j, uint32_t len)
+{
+	float total = 0;
+	int off = 0;
+	for (int f = 0; f < ORC_NFEAT; ++f) {
+		const int n = rsk_tbl_feat_alpha[f];
+		for (uint32_t k = 0; k < len; ++k)
+			total += p->tables[off + profA[(size_t)f * LA + lo_i + k] * n + profB[(size_t)f * LB + lo_j + k]];
+		off += n * n;
+	}
+	return total;
+}
+
+/* xdrophsp.cpp:8-33 SubstScore: starts from 0 and adds the 8 features in order */
+static float subst(const orc_params *p, const uint8_t *profA, uint32_t LA, const uint8_t *profB, uint32_t LB,
+		uint32_t pa, uint32_t pb)
+{
+	float t = 0;
+	int off = 0;
+	for (int f = 0; f < ORC_NFEAT; ++f) {
+		const int n = rsk_tbl_feat_alpha[f];
+		t += p->tables[off + profA[(size_t)f * LA + pa] * n + profB[(size_t)f * LB + pb]];
+		off += n * n;
+	}
+	return t;
+}
+
+enum { XB_DM = 1, XB_IM = 2, XB_MD = 4, XB_MI = 8 };
+#define XNONE 0xffffffffu
+static uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+float orc_xdrop_fwd(const orc_params *p, const uint8_t *profA, uint32_t LAfull, const uint8_t *profB, uint32_t LBfull,
+		int reverse, uint32_t revLA, uint32_t revLB, float X, uint32_t LoA, uint32_t aLA, uint32_t LoB, uint32_t aLB,
+		char *path, uint32_t *path_len)
+{
+#define SUB(pa, pb) (reverse ? subst(p, profA, LAfull, profB, LBfull, revLA - (pa) - 1, revLB - (pb) - 1) \
+                             : subst(p, profA, LAfull, profB, LBfull, (pa), (pb)))
+	*path_len = 0;
+	path[0] = 0;
+	const uint32_t LA = aLA - LoA, LB = aLB - LoB;
+	const float open = p->gap_open, ext = p->gap_ext;
+	if (LA == 1 || LB == 1) { /* xdropfwd.cpp:87-93 */
+		const float sc = SUB(LoA, LoB);
+		if (sc > 0) { path[0] = 'M'; path[1] = 0; *path_len = 1; }
+		return sc;
+	}
+	const float absopen = -open, absext = -ext;
+	float *Mbuf = (float *)malloc(sizeof(float) * (LB + 4));
+	float *M = Mbuf + 1; /* M[-1] is addressable */
+	float *Dr = (float *)malloc(sizeof(float) * (LB + 4));
+	const size_t W = (size_t)LB + 3;
+	uint8_t *tb = (uint8_t *)calloc((size_t)(LA + 3) * W, 1);
+	M[-1] = ORC_NEG_INF;
+	Dr[0] = ORC_NEG_INF;
+	Dr[1] = ORC_NEG_INF;
+	float best = 0;
+	uint32_t besti = 0, bestj = 0;
+	uint32_t prev_jlo = 0, prev_jhi = 0, jlo = 1, jhi = 1;
+	float M0 = best;
+	for (uint32_t i = 1; i <= LA; ++i) {
+		if (jlo == prev_jlo) {
+			M[jlo - 1] = ORC_NEG_INF;
+			Dr[jlo] = ORC_NEG_INF;
+		}
+		uint32_t endj = umin(prev_jhi + 1, LB);
+		for (uint32_t j = endj + 1; j <= umin(jhi + 1, LB); ++j) {
+			M[j - 1] = ORC_NEG_INF;
+			Dr[j] = ORC_NEG_INF;
+		}
+		uint32_t next_jlo = XNONE, next_jhi = XNONE;
+		float I0 = ORC_NEG_INF;
+		uint8_t *row = tb + (size_t)i * W;
+		for (uint32_t j = jlo; j <= jhi; ++j) {
+			uint8_t bits = 0;
+			const float saved = M0;
+			float x = M0;
+			if (Dr[j] > x) { x = Dr[j]; bits = XB_DM; }
+			if (I0 > x) { x = I0; bits = XB_IM; }
+			M0 = M[j];
+			float s = SUB(LoA + i - 1, LoB + j - 1);
+			s += x;
+			M[j] = s;
+			float h = s - best + X;
+			if (h > 0) { next_jlo = umin(next_jlo, j + 1); next_jhi = j + 1; }
+			if (h > absopen) next_jlo = umin(next_jlo, j);
+			if (h > absext && j == jhi && jhi + 1 < LB) { /* the match can be followed by an insert: widen this row */
+				++jhi;
+				const uint32_t ne = umax(umin(jhi + 1, LB), endj);
+				for (uint32_t j2 = endj + 1; j2 <= ne; ++j2) {
+					if (j2 - 1 > j) M[j2 - 1] = ORC_NEG_INF;
+					Dr[j2] = ORC_NEG_INF;
+				}
+				endj = ne;
+			}
+			if (s >= best) { best = s; besti = i; bestj = j; }
+			if (j != jlo) {
+				const float md = saved + open;
+				Dr[j] += ext;
+				if (md >= Dr[j]) { Dr[j] = md; bits |= XB_MD; }
+				h = Dr[j] - best + X;
+				if (h > 0) { next_jlo = umin(next_jlo, j - 1); next_jhi = umax(next_jhi, j - 1); }
+			}
+			const float mi = saved + open;
+			I0 += ext;
+			if (mi >= I0) { I0 = mi; bits |= XB_MI; }
+			h = I0 - best + X;
+			if (h > 0) { next_jlo = umin(next_jlo, j + 1); next_jhi = umax(next_jhi, j + 1); }
+			if (h > absext && j == jhi && jhi + 1 < LB) {
+				++jhi;
+				const uint32_t ne = umax(umin(jhi + 1, LB), endj);
+				for (uint32_t j2 = endj + 1; j2 <= ne; ++j2) {
+					M[j2 - 1] = ORC_NEG_INF;
+					Dr[j2] = ORC_NEG_INF;
+				}
+				endj = ne;
+			}
+			row[j] = bits;
+		}
+		if (jhi < LB) { /* the D cell just right of the band */
+			const uint32_t j1 = jhi + 1;
+			row[j1] = 0;
+			const float md = M0 + open;
+			Dr[j1] += ext;
+			if (md >= Dr[j1]) { Dr[j1] = md; row[j1] = XB_MD; }
+		}
+		if (next_jlo == XNONE)
+			break;
+		prev_jlo = jlo; prev_jhi = jhi;
+		jlo = next_jlo; jhi = next_jhi;
+		if (jlo > LB) jlo = LB;
+		if (jhi > LB) jhi = LB;
+		if (jlo == prev_jlo) { M0 = ORC_NEG_INF; Dr[jlo] = ORC_NEG_INF; }
+		else M0 = M[jlo - 1];
+	}
+	float result = 0.0f;
+	if (best > 0.0f) {
+		result = best;
+		uint32_t i = besti, j = bestj, n = 0;
+		char st = 'M';
+		char *rev = (char *)malloc((size_t)LA + LB + 4);
+		for (;;) {
+			rev[n++] = st;
+			if (i == 1 || j == 1)
+				break;
+			char nx;
+			if (st == 'M') {
+				const uint8_t c = tb[(size_t)i * W + j];
+				nx = (c & XB_DM) ? 'D' : (c & XB_IM) ? 'I' : 'M';
+				--i; --j;
+			} else if (st == 'D') {
+				nx = (tb[(size_t)i * W + j + 1] & XB_MD) ? 'M' : 'D';
+				--i;
+			} else {
+				nx = (tb[(size_t)(i + 1) * W + j] & XB_MI) ? 'M' : 'I';
+				--j;
+			}
+			st = nx;
+		}
+		for (uint32_t k = 0; k < n; ++k)
+			path[k] = rev[n - 1 - k];
+		path[n] = 0;
+		*path_len = n;
+		free(rev);
+	}
+	free(Mbuf); free(Dr); free(tb);
+	return result;
+#undef SUB
+}
+
+int orc_do_mkf(const orc_params *p, const orc_chain *A, const orc_chain *B)
+{
+	if (!A->mu || !B->mu || A->L < 3 || B->L < 3)
+		return 0;
+	return A->L >= p->mkfl || B->L >= p->mkfl;
+}
+
+static void path_counts(const char *path, uint32_t n, uint32_t *M, uint32_t *D, uint32_t *I)
+{
+	*M = *D = *I = 0;
+	for (uint32_t k = 0; k < n; ++k) {
+		if (path[k] == 'M') ++*M;
+		else if (path[k] == 'D') ++*D;
+		else ++*I;
+	}
+}
+
+void orc_align_mkf(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path,
+		int *best_hsp_score, int *best_chain_score, float *xdrop_score)
+{
+	clear_result(r);
+	path[0] = 0;
+	*xdrop_score = 0;
+	enum { CAP = 256 };
+	orc_hsp hsps[CAP];
+	int chain_idx[CAP], nhsp, nchain;
+	orc_mkf_align(p, A->mu, (int)A->L, B->mu, (int)B->L, hsps, CAP, &nhsp, best_hsp_score, best_chain_score, chain_idx, &nchain);
+	if (*best_chain_score <= 0)
+		return;
+	/* PostAlignMKF: dssaligner.cpp:1395-1437 */
+	float mega_total = 0, best_mega = 0;
+	int best_idx = 0;
+	for (int k = 0; k < nchain; ++k) {
+		const orc_hsp *h = &hsps[chain_idx[k]];
+		const float ms = orc_mega_hsp_score(p, A->prof, A->L, B->prof, B->L, (uint32_t)h->loi, (uint32_t)h->loj, (uint32_t)h->len);
+		if (ms > best_mega) { best_mega = ms; best_idx = k; }
+		mega_total += ms;
+	}
+	if (mega_total < p->mkf_min_mega_hsp_score)
+		return;
+	/* XDropHSP: xdrophsp.cpp:42-150 */
+	const orc_hsp *h = &hsps[chain_idx[best_idx]];
+	const uint32_t loi_in = (uint32_t)h->loi, loj_in = (uint32_t)h->loj, len = (uint32_t)h->len;
+	uint32_t LoA = loi_in + len / 2, LoB = loj_in + len / 2;
+	const uint32_t K = 8;
+	float *v = (float *)malloc(sizeof(float) * len);
+	for (uint32_t c = 0; c < len; ++c)
+		v[c] = subst(p, A->prof, A->L, B->prof, B->L, loi_in + c, loj_in + c);
+	float best_mer = 0;
+	for (uint32_t ms = 0; ms + K <= len; ++ms) {
+		float sc = 0;
+		for (uint32_t k = 0; k < K; ++k)
+			sc += v[ms + k];
+		if (sc > best_mer) { best_mer = sc; LoA = loi_in + ms; LoB = loj_in + ms; }
+	}
+	free(v);
+	if ((LoA < LoB ? LoA : LoB) < K / 2) { LoA += K / 2; LoB += K / 2; }
+	const float X = (float)p->mkf_x2;
+	char *fwd = (char *)malloc((size_t)A->L + B->L + 4), *bwd = (char *)malloc((size_t)A->L + B->L + 4);
+	uint32_t nf = 0, nb = 0;
+	const float sf = orc_xdrop_fwd(p, A->prof, A->L, B->prof, B->L, 0, 0, 0, X, LoA, A->L, LoB, B->L, fwd, &nf);
+	/* XDropBwd(HiA = LoA-1, HiB = LoB-1): forward DP on mirrored coordinates, then the path is reversed */
+	const float sb = orc_xdrop_fwd(p, A->prof, A->L, B->prof, B->L, 1, LoA, LoB, X, 0, LoA, 0, LoB, bwd, &nb);
+	for (uint32_t k = 0; k < nb / 2; ++k) { const char t = bwd[k]; bwd[k] = bwd[nb - 1 - k]; bwd[nb - 1 - k] = t; }
+	const float total = sf + sb;
+	if (total < 10) { /* xdrophsp.cpp:109-113: path cleared, score 0; Lo stays UINT_MAX and Hi = Lo + 0 - 1 wraps */
+		free(fwd); free(bwd);
+		r->score = 0;
+		r->hi_a = r->lo_a - 1u;
+		r->hi_b = r->lo_b - 1u;
+		return;
+	}
+	/* MergeFwdBwd: mergefwdback.cpp:6-50 */
+	uint32_t bM, bD, bI;
+	path_counts(bwd, nb, &bM, &bD, &bI);
+	r->lo_a = nb ? LoA - (bM + bD) : LoA;
+	r->lo_b = nb ? LoB - (bM + bI) : LoB;
+	memcpy(path, bwd, nb);
+	memcpy(path + nb, fwd, nf);
+	path[nb + nf] = 0;
+	r->path_len = nb + nf;
+	free(fwd); free(bwd);
+	*xdrop_score = total;
+	r->score = total;
+	uint32_t nM, nD, nI;
+	path_counts(path, r->path_len, &nM, &nD, &nI);
+	r->hi_a = r->lo_a + nM + nD - 1; /* dssaligner.cpp:1432-1435 */
+	r->hi_b = r->lo_b + nM + nI - 1;
+	orc_calc_evalue(p, A, B, path, r);
+}
+
 void orc_align_pair(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path)
 {
+	if (orc_do_mkf(p, A, B)) { /* dssaligner.cpp:811-815 */
+		int bh, bc;
+		float xs;
+		char *tmp = path ? path : (char *)malloc((size_t)A->L + B->L + 4);
+		orc_align_mkf(p, A, B, r, tmp, &bh, &bc, &xs);
+		if (!path)
+			free(tmp);
+		return;
+	}
 	clear_result(r);
 	if (path)
 		path[0] = 0;

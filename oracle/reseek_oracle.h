@@ -116,6 +116,35 @@ void orc_calc_evalue(const orc_params *p, const orc_chain *A, const orc_chain *B
  * ClearAlign -> (omega>0 && mu present: MuFilter :619) -> Align_NoAccel :929.  path: LA+LB+1 bytes. */
 void orc_align_pair(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path);
 
+/* ---- long-chain path: Mu k-mer filter (MKF) + chaining + banded x-drop ---- */
+typedef struct orc_hsp { int loi, loj, len, score; } orc_hsp;
+
+/* mukmerfilter.cpp:105-175 MuXDrop: ungapped x-drop extension of a 3-mer seed on IntScoreMx_Mu */
+int orc_mu_xdrop(const uint8_t *Q, int LQ, const uint8_t *T, int LT, int PosQ, int PosT, int X, int *Loi, int *Loj, int *Len);
+
+/* mukmerfilter.cpp:208-230 SetHashTable + :316-389 Align + :391-464 ChainHSPs + chainer.cpp:31-194.
+ * hsps: the kept HSP list in discovery order (cap entries); chain_idx: indices into hsps, chain end first. */
+int orc_mkf_align(const orc_params *p, const uint8_t *muQ, int LQ, const uint8_t *muT, int LT,
+		orc_hsp *hsps, int cap, int *nhsp, int *best_hsp_score, int *best_chain_score, int *chain_idx, int *nchain);
+
+/* xdropfwd.cpp:71-386 (forward) / xdropbwd.cpp:28-50 (reverse != 0: coordinates mirrored as RevSubFn does).
+ * Aligns A[LoA..aLA) x B[LoB..aLB) starting exactly at (LoA,LoB); path gets the forward-order M/D/I string of the
+ * DP's own orientation (the caller reverses it for the backward pass, xdropbwd.cpp:48). */
+float orc_xdrop_fwd(const orc_params *p, const uint8_t *profA, uint32_t LAfull, const uint8_t *profB, uint32_t LBfull,
+		int reverse, uint32_t revLA, uint32_t revLB, float X, uint32_t LoA, uint32_t aLA, uint32_t LoB, uint32_t aLB,
+		char *path, uint32_t *path_len);
+
+/* dssaligner.cpp:488-527 GetMegaHSPScore: feature-major accumulation */
+float orc_mega_hsp_score(const orc_params *p, const uint8_t *profA, uint32_t LA, const uint8_t *profB, uint32_t LB,
+		uint32_t lo_i, uint32_t lo_j, uint32_t len);
+
+/* dssaligner.cpp:1387-1437 AlignMKF + PostAlignMKF, xdrophsp.cpp:42-150 XDropHSP, mergefwdback.cpp:6-50 */
+void orc_align_mkf(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path,
+		int *best_hsp_score, int *best_chain_score, float *xdrop_score);
+
+/* dssaligner.cpp:715-732 DoMKF (k-mers exist iff the chain has >= 3 residues) */
+int orc_do_mkf(const orc_params *p, const orc_chain *A, const orc_chain *B);
+
 /* Batch helpers for the CPU baseline timing (scalar port, one thread). */
 void orc_align_pairs(const orc_params *p, const orc_chain *chainsA, const orc_chain *chainsB,
 		const uint32_t *ia, const uint32_t *ib, size_t npairs, orc_result *out);

@@ -13,8 +13,6 @@ def test_align_pair_matches_reference_fixtures(port, mode):
     p = port(mode)
     n = checked = with_path = 0
     for k in range(len(g["a"])):
-        if g["mkf"][k]:
-            continue  # long-chain k-mer/x-drop path: covered by test_mkf_* once that row of SURVEY §8 is built
         A, B = chains[int(g["a"][k])], chains[int(g["b"][k])]
         if mode == 3:  # verysensitive never loads Mu letters (dbsearcher.cpp:251-252)
             A = type(A)(A.prof, None, A.xyz, A.selfrev)
@@ -34,7 +32,9 @@ def test_align_pair_matches_reference_fixtures(port, mode):
             checked += 1
         if mode != 3 and not r.filtered:
             assert r.mu_score == g["mu_score"][k], f"pair {k} mu score"
-    assert n > 100 and with_path > 10 and checked > 10
+    assert n == len(g['a']) and with_path > 10 and checked > 10
+    if mode != 3:
+        assert int(np.sum(g['mkf'])) > 100  # the long-chain (MKF / x-drop) path is part of the fixtures
 
 
 def test_mu_sw_matches_parasail_fixtures(port):

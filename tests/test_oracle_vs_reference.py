@@ -60,3 +60,34 @@ def test_mu_filter_random(port):
             b[:n] = a[:n]
         s, fwd, rev = p.mu_filter_score(a, b)
         assert s == ref.mu_score(a, b), f"case {t}"
+
+
+@pytest.mark.parametrize("mode", [2, 1])
+def test_mkf_xdrop_path_random_long_chains(port, built_lib, mode):
+    """Chains >= MKFL: 3-mer seeds, ordered HSP gating, chaining, mega-HSP scores, 8-mer seed, banded x-drop
+    forward/backward with traceback and merge against the live reference."""
+    from reseek_b200 import synth
+    from tests.util import to_oracle_chains
+    from oracle.pyoracle import Chain
+    ref = Ref(mode)
+    p = port(mode)
+    a = synth.make_chains(6, [650, 700, 820, 610, 900, 640], seed=61)
+    b = synth.make_chains(8, [300, 640, 720, 150, 660, 1000, 90, 605], seed=62)
+    synth.plant_homologs(b, a, 0.9, seed=63, sub=0.25, indel=0.03)
+    ca, cb = to_oracle_chains(a), to_oracle_chains(b)
+    for c in ca + cb:  # 3-mers as DSS::GetMuKmers makes them (pattern "111")
+        m = c.mu.astype(np.uint32)
+        c.kmers = (m[:-2] * 36 + m[1:-1]) * 36 + m[2:]
+    npath = nmkf = 0
+    for A in ca:
+        for B in cb:
+            rr, rpath = ref.align_pair(A, B)
+            r, path = p.align_pair(A, B)
+            nmkf += rr.mkf
+            assert path == rpath, (A.L, B.L)
+            assert bits(r.score) == bits(rr.score)
+            assert bits(r.ts) == bits(rr.ts) and bits(r.evalue) == bits(rr.evalue)
+            if path:
+                npath += 1
+                assert (r.lo_a, r.lo_b, r.hi_a, r.hi_b) == (rr.lo_a, rr.lo_b, rr.hi_a, rr.hi_b)
+    assert nmkf == len(ca) * len(cb) and npath >= 5
