@@ -99,8 +99,8 @@ enum {
 	RSK_HIT_MU_REJECTED = 1u, /* dropped by the Mu filter: no SW was run */
 	RSK_HIT_HAS_EVALUE = 2u,  /* CalcEvalue ran (score >= min_fwd_score) */
 	RSK_HIT_REPORTED = 4u,    /* passes DBSearcher::Reject (E <= max_evalue) */
-	RSK_HIT_MKF_PENDING = 8u  /* DoMKF() pair (a chain >= mkfl, dssaligner.cpp:715-732): the k-mer/x-drop path is not built yet;
-	                             the pair is NOT aligned and is reported with this flag instead of a wrong answer */
+	RSK_HIT_MKF = 8u          /* DoMKF() pair (a chain >= mkfl, dssaligner.cpp:715-732): aligned by the k-mer / x-drop path
+	                             (AlignMKF); mu_fwd = m_MKF.m_BestHSPScore, mu_rev = m_MKF.m_BestChainScore */
 };
 
 /* which pairs come back from a search call */
@@ -132,6 +132,9 @@ typedef struct rsk_stats {
 	float mu_kernel_ms;
 	float lddt_kernel_ms;
 	float total_ms;          /* device time of the whole call on the context stream */
+	float mkf_kernel_ms;     /* long-chain path kernels */
+	uint32_t reserved;
+	uint64_t mkf_pairs;      /* pairs that took the k-mer / x-drop path (DoMKF) */
 } rsk_stats;
 
 /* ---- library ---- */

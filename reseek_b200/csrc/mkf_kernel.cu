@@ -1,0 +1,512 @@
+// mkf_kernel.cu - K4: the long-chain path (a chain >= MKFL): Mu 3-mer seeds -> ungapped x-drop HSPs with the
+// reference's order-dependent gating -> 1-D chaining -> mega-HSP re-scoring -> best 8-mer seed -> banded affine
+// x-drop forward and backward with traceback -> merged path.
+//
+// Replaces DSSAligner::AlignMKF / PostAlignMKF (dssaligner.cpp:1387-1437), MuKmerFilter::SetHashTable / Align /
+// MuXDrop / ChainHSPs (mukmerfilter.cpp:208, 316, 105, 391), Chainer::Chain (chainer.cpp:31-194),
+// GetMegaHSPScore (dssaligner.cpp:488-527), XDropHSP (xdrophsp.cpp:42-150), XDropFwd (xdropfwd.cpp:71-386),
+// XDropBwd (xdropbwd.cpp:28-50), MergeFwdBwd (mergefwdback.cpp:6-50).
+//
+// These pairs are rare (3 % of SCOP40 pairs) and their DP is inherently sequential: the band of row i+1 and every
+// x-drop test depend on the running best score in row-major order (xdropfwd.cpp:226-262).  They are therefore
+// mapped as: one CTA per query chain for the hash table, one warp per pair for seeding/chaining/re-scoring, and
+// ONE THREAD per (pair, direction) for the banded DP, thousands of pairs in flight.  Every float operation is
+// performed in the reference's order, so scores and paths are bit-identical.
+#include "rsk_internal.cuh"
+
+namespace rsk {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kDict = 36 * 36 * 36;       // 3-mer dictionary (pattern "111", dssparams.cpp:88)
+constexpr int kHashW = 4;                 // first 4 positions of every 3-mer (mukmerfilter.h:7)
+constexpr int kMaxHsp = 80;               // kept HSPs per pair (each must beat the previous best score: never many)
+constexpr int kSeedWarps = 4;
+
+// ---- query hash tables: uint16 ht[kDict][4], 0xffff = empty ----
+__global__ void __launch_bounds__(256) mkf_hash_kernel(const MkfArgs a)
+{
+	const uint32_t q = a.hash_chain[blockIdx.x];
+	uint16_t *ht = a.hash + (size_t)blockIdx.x * kDict * kHashW;
+	uint4 *ht4 = reinterpret_cast<uint4 *>(ht);
+	const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+	for (int k = threadIdx.x; k < kDict * kHashW * 2 / 16; k += 256)
+		ht4[k] = ff;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const uint8_t *mu = a.muA + a.offA[q];
+		const int L = (int)a.lenA[q];
+		for (int pos = 0; pos + 3 <= L; ++pos) {  // insertion order = position order (mukmerfilter.cpp:212-227)
+			const int k = (mu[pos] * 36 + mu[pos + 1]) * 36 + mu[pos + 2];
+			for (int w = 0; w < kHashW; ++w)
+				if (ht[kHashW * k + w] == 0xffff) {
+					ht[kHashW * k + w] = (uint16_t)pos;
+					break;
+				}
+		}
+	}
+}
+
+// mukmerfilter.cpp:105-175
+__device__ __forceinline__ int mu_xdrop(const int *mx, const uint8_t *__restrict__ Q, int LQ, const uint8_t *__restrict__ T, int LT,
+		int PosQ, int PosT, int X, int &Loi, int &Loj, int &Len)
+{
+	Loi = PosQ;
+	Loj = PosT;
+	int fwd = 0, bestfwd = 0, fwdlen = 0;
+	for (int i = PosQ, j = PosT; i < LQ && j < LT;) {
+		fwd += mx[36 * Q[i] + T[j]];
+		++i; ++j;
+		if (fwd > bestfwd) { bestfwd = fwd; fwdlen = i - PosQ; }
+		else if (fwd + X < bestfwd) break;
+	}
+	int rev = 0, bestrev = 0, revlen = 0;
+	for (int i = PosQ - 1, j = PosT - 1; i >= 0 && j >= 0; --i, --j) {
+		rev += mx[36 * Q[i] + T[j]];
+		if (rev > bestrev) { bestrev = rev; Loi = i; Loj = j; revlen = PosQ - i; }
+		else if (rev + X < bestrev) break;
+	}
+	Len = fwdlen + revlen;
+	return bestfwd + bestrev;
+}
+
+struct Hsp { int loi, loj, len, score; };
+
+// cell score in the order of xdrophsp.cpp:8-33 (starts from 0, features 0..7)
+__device__ __forceinline__ float subst(const float *tab, const uint64_t ea, const uint64_t eb)
+{
+	float t = 0.0f;
+#pragma unroll
+	for (int f = 0; f < RSK_NFEAT; ++f) {
+		const int a = (int)((ea >> (8 * f)) & 0xff) - feat_base(f);
+		const int b = (int)((eb >> (8 * f)) & 0xff) - feat_base(f);
+		t += tab[feat_table_off(f) + a * feat_alpha(f) + b];
+	}
+	return t;
+}
+
+// One warp per pair: seeds, gating, chaining, mega-HSP scores, 8-mer seed.
+__global__ void __launch_bounds__(kSeedWarps * 32) mkf_seed_kernel(const MkfArgs a)
+{
+	__shared__ int s_mx[36 * 36];
+	__shared__ float s_tab[RSK_TABLE_FLOATS];
+	__shared__ Hsp s_cand[kSeedWarps][32 * kHashW];
+	__shared__ Hsp s_hsp[kSeedWarps][kMaxHsp];
+	__shared__ int s_chain[kSeedWarps][kMaxHsp];
+	__shared__ float s_mega[kSeedWarps][kMaxHsp];
+	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
+		s_mx[k] = a.mu_mx[k];
+	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += blockDim.x)
+		s_tab[k] = a.tables[k];
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t pair = blockIdx.x * kSeedWarps + warp;
+	if (pair >= a.npairs)
+		return;
+	const uint32_t qa = a.pair_a[pair], tb = a.pair_b[pair];
+	const uint8_t *Q = a.muA + a.offA[qa];
+	const uint8_t *T = a.muB + a.offB[tb];
+	const int LQ = (int)a.lenA[qa], LT = (int)a.lenB[tb];
+	const uint16_t *ht = a.hash + (size_t)a.pair_hash[pair] * kDict * kHashW;
+	Hsp *cand = s_cand[warp];
+	Hsp *hsp = s_hsp[warp];
+	int *chain = s_chain[warp];
+	MkfSeed out;
+	out.valid = 0; out.lo_a = 0; out.lo_b = 0; out.best_hsp = 0; out.best_chain = 0;
+
+	// ---- seeds + gating (mukmerfilter.cpp:316-389): the order is PosT ascending, slot ascending ----
+	int nh = 0, best = 0;
+	bool found = false;
+	const int nkT = LT - 2;
+	for (int base = 0; base < nkT; base += 32) {
+		const int pt = base + lane;
+#pragma unroll
+		for (int w = 0; w < kHashW; ++w)
+			cand[lane * kHashW + w].score = -1;
+		if (pt < nkT) {
+			const int k = (T[pt] * 36 + T[pt + 1]) * 36 + T[pt + 2];
+			const ushort4 slots = *reinterpret_cast<const ushort4 *>(ht + kHashW * k);
+			const uint16_t pq[4] = {slots.x, slots.y, slots.z, slots.w};
+#pragma unroll
+			for (int w = 0; w < kHashW; ++w) {
+				if (pq[w] != 0xffff) {
+					Hsp h;
+					h.score = mu_xdrop(s_mx, Q, LQ, T, LT, (int)pq[w], pt, a.x1, h.loi, h.loj, h.len);
+					cand[lane * kHashW + w] = h;
+				}
+			}
+		}
+		__syncwarp();
+		if (lane == 0) {
+			for (int c = 0; c < 32 * kHashW; ++c) {
+				const Hsp h = cand[c];
+				if (h.score < 0 || h.score < a.min_hsp_score)
+					continue;
+				found = true;
+				if (h.score > best) {
+					best = h.score;
+					bool old = false;
+					for (int i = 0; i < nh; ++i)
+						if (hsp[i].loi == h.loi) { old = true; break; }
+					if (!old && nh < kMaxHsp)
+						hsp[nh++] = h;
+				}
+			}
+		}
+		__syncwarp();
+	}
+	nh = __shfl_sync(kFull, nh, 0);
+	best = __shfl_sync(kFull, best, 0);
+	found = __shfl_sync(kFull, (int)found, 0) != 0;
+	out.best_hsp = best;
+
+	// ---- chaining on the query axis (chainer.cpp:31-194); lane 0, N is tiny ----
+	int nchain = 0, chain_score = 0;
+	if (found && lane == 0 && nh > 0) {
+		// breakpoints: (pos, is_lo, index), sorted by pos, starts before ends, stable
+		int *bp = reinterpret_cast<int *>(cand);  // reuse the candidate buffer: 2*nh*3 <= 480 ints of its 512
+		const int nb = 2 * nh;
+		for (int i = 0; i < nh; ++i) {
+			bp[3 * (2 * i)] = hsp[i].loi; bp[3 * (2 * i) + 1] = 1; bp[3 * (2 * i) + 2] = i;
+			bp[3 * (2 * i + 1)] = hsp[i].loi + hsp[i].len - 1; bp[3 * (2 * i + 1) + 1] = 0; bp[3 * (2 * i + 1) + 2] = i;
+		}
+		for (int i = 1; i < nb; ++i) {
+			const int tp = bp[3 * i], tl = bp[3 * i + 1], ti = bp[3 * i + 2];
+			int k = i - 1;
+			while (k >= 0 && (bp[3 * k] > tp || (bp[3 * k] == tp && !bp[3 * k + 1] && tl))) {
+				bp[3 * (k + 1)] = bp[3 * k]; bp[3 * (k + 1) + 1] = bp[3 * k + 1]; bp[3 * (k + 1) + 2] = bp[3 * k + 2];
+				--k;
+			}
+			bp[3 * (k + 1)] = tp; bp[3 * (k + 1) + 1] = tl; bp[3 * (k + 1) + 2] = ti;
+		}
+		float *cs = s_mega[warp];      // chain scores
+		int *tbk = chain;              // traceback links (overwritten by the chain itself afterwards)
+		int best_end = -1;
+		for (int i = 0; i < nb; ++i) {
+			const int ix = bp[3 * i + 2];
+			const float sc = (float)hsp[ix].score;
+			if (bp[3 * i + 1]) {
+				tbk[ix] = best_end;
+				cs[ix] = best_end < 0 ? sc : cs[best_end] + sc;
+			} else if (best_end < 0 || cs[ix] > cs[best_end]) {
+				best_end = ix;
+			}
+		}
+		float total = 0.0f;
+		int tmp[kMaxHsp];
+		for (int ix = best_end; ix >= 0; ix = tbk[ix]) {
+			total += (float)hsp[ix].score;
+			tmp[nchain++] = ix;
+		}
+		for (int k = 0; k < nchain; ++k)
+			chain[k] = tmp[k];
+		chain_score = (int)total;
+	}
+	nchain = __shfl_sync(kFull, nchain, 0);
+	chain_score = __shfl_sync(kFull, chain_score, 0);
+	out.best_chain = chain_score;
+	__syncwarp();
+
+	if (chain_score > 0) {  // PostAlignMKF: dssaligner.cpp:1395-1437
+		const uint64_t *PA = a.profA + a.offA[qa];
+		const uint64_t *PB = a.profB + a.offB[tb];
+		// mega-HSP scores: feature-major running sum (dssaligner.cpp:504-524); one lane per chained HSP
+		for (int k = lane; k < nchain; k += 32) {
+			const Hsp h = hsp[chain[k]];
+			float total = 0.0f;
+			for (int f = 0; f < RSK_NFEAT; ++f) {
+				const float *tf = s_tab + feat_table_off(f);
+				const int al = feat_alpha(f), fb = feat_base(f);
+				for (int c = 0; c < h.len; ++c) {
+					const int ea = (int)((PA[h.loi + c] >> (8 * f)) & 0xff) - fb;
+					const int eb = (int)((PB[h.loj + c] >> (8 * f)) & 0xff) - fb;
+					total += tf[ea * al + eb];
+				}
+			}
+			s_mega[warp][k] = total;
+		}
+		__syncwarp();
+		float mega_total = 0.0f, best_mega = 0.0f;
+		int best_idx = 0;
+		for (int k = 0; k < nchain; ++k) {  // every lane redundantly: sequential order matters for the float sum
+			const float ms = s_mega[warp][k];
+			if (ms > best_mega) { best_mega = ms; best_idx = k; }
+			mega_total += ms;
+		}
+		if (!(mega_total < a.min_mega_hsp_score)) {
+			// XDropHSP: best 8-mer of the best HSP (xdrophsp.cpp:62-98)
+			const Hsp h = hsp[chain[best_idx]];
+			const int K = 8;
+			float bestmer = 0.0f;
+			int bestms = -1;
+			for (int ms = lane; ms + K <= h.len; ms += 32) {
+				float sc = 0.0f;
+				for (int k = 0; k < K; ++k)
+					sc += subst(s_tab, PA[h.loi + ms + k], PB[h.loj + ms + k]);
+				if (sc > bestmer) { bestmer = sc; bestms = ms; }  // first maximum within this lane's stride
+			}
+			// first maximum overall: highest score, then smallest start
+#pragma unroll
+			for (int o = 16; o >= 1; o >>= 1) {
+				const float os = __shfl_xor_sync(kFull, bestmer, o);
+				const int om = __shfl_xor_sync(kFull, bestms, o);
+				if (om >= 0 && (os > bestmer || (os == bestmer && (bestms < 0 || om < bestms)))) { bestmer = os; bestms = om; }
+			}
+			uint32_t LoA = (uint32_t)(h.loi + h.len / 2), LoB = (uint32_t)(h.loj + h.len / 2);
+			if (bestms >= 0 && bestmer > 0.0f) { LoA = (uint32_t)(h.loi + bestms); LoB = (uint32_t)(h.loj + bestms); }
+			if (min(LoA, LoB) < (uint32_t)(K / 2)) { LoA += K / 2; LoB += K / 2; }
+			out.valid = 1;
+			out.lo_a = LoA;
+			out.lo_b = LoB;
+		}
+	}
+	if (lane == 0)
+		a.seeds[pair] = out;
+}
+
+enum { XB_DM = 1, XB_IM = 2, XB_MD = 4, XB_MI = 8 };
+constexpr uint32_t kNone = 0xffffffffu;
+
+// One thread per (pair, direction): xdropfwd.cpp:71-386.  dir 0 = forward from the seed, dir 1 = backward
+// (XDropBwd: the same DP on mirrored coordinates, xdropbwd.cpp:16-26).
+__global__ void __launch_bounds__(64) mkf_xdrop_kernel(const MkfArgs a)
+{
+	__shared__ float s_tab[RSK_TABLE_FLOATS];
+	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += blockDim.x)
+		s_tab[k] = a.tables[k];
+	__syncthreads();
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= 2 * a.npairs)
+		return;
+	const uint32_t pair = t >> 1, dir = t & 1;
+	MkfXdrop &res = a.xres[t];
+	res.score = 0.0f;
+	res.path_len = 0;
+	const MkfSeed sd = a.seeds[pair];
+	if (!sd.valid)
+		return;
+	const uint32_t qa = a.pair_a[pair], tb_ = a.pair_b[pair];
+	const uint64_t *PA = a.profA + a.offA[qa];
+	const uint64_t *PB = a.profB + a.offB[tb_];
+	const uint32_t LAf = a.lenA[qa], LBf = a.lenB[tb_];
+	const uint32_t LA = dir ? sd.lo_a : LAf - sd.lo_a;  // rows of this DP
+	const uint32_t LB = dir ? sd.lo_b : LBf - sd.lo_b;
+	// scratch of this pair: [bwd region | fwd region]; each region = M row, D row, path staging, TB matrix
+	unsigned char *base = a.scratch + a.scratch_off[pair];
+	if (!dir)
+		base += xdrop_region_bytes(sd.lo_a, sd.lo_b);
+	float *Mbuf = reinterpret_cast<float *>(base);
+	float *M = Mbuf + 1;
+	float *Dr = Mbuf + (LB + 4);
+	uint8_t *stage = reinterpret_cast<uint8_t *>(Mbuf + 2 * (LB + 4));
+	const size_t W = (size_t)LB + 3;
+	uint8_t *tbm = stage + (((size_t)LA + LB + 4 + 15) & ~(size_t)15);
+	res.stage_off = (unsigned long long)(stage - a.scratch);
+	const float open = a.open, ext = a.ext, X = a.x2;
+	// mirrored coordinates for the backward pass: position p of the DP is original position lo - 1 - p
+#define SUBST(pa, pb) (dir ? subst(s_tab, PA[sd.lo_a - 1 - (pa)], PB[sd.lo_b - 1 - (pb)]) : subst(s_tab, PA[sd.lo_a + (pa)], PB[sd.lo_b + (pb)]))
+	if (LA == 1 || LB == 1) {  // xdropfwd.cpp:87-93
+		const float sc = SUBST(0, 0);
+		if (sc > 0) {
+			stage[0] = 'M';
+			res.path_len = 1;
+		}
+		res.score = sc;
+		return;
+	}
+	const float absopen = -open, absext = -ext;
+	M[-1] = kNegInf;
+	Dr[0] = kNegInf;
+	Dr[1] = kNegInf;
+	float best = 0.0f;
+	uint32_t besti = 0, bestj = 0;
+	uint32_t prev_jlo = 0, prev_jhi = 0, jlo = 1, jhi = 1;
+	float M0 = best;
+	for (uint32_t i = 1; i <= LA; ++i) {
+		if (jlo == prev_jlo) {
+			M[jlo - 1] = kNegInf;
+			Dr[jlo] = kNegInf;
+		}
+		uint32_t endj = min(prev_jhi + 1, LB);
+		for (uint32_t j = endj + 1; j <= min(jhi + 1, LB); ++j) {
+			M[j - 1] = kNegInf;
+			Dr[j] = kNegInf;
+		}
+		uint32_t next_jlo = kNone, next_jhi = kNone;
+		float I0 = kNegInf;
+		uint8_t *row = tbm + (size_t)i * W;
+		const uint64_t ea = dir ? PA[sd.lo_a - i] : PA[sd.lo_a + i - 1];
+		for (uint32_t j = jlo; j <= jhi; ++j) {
+			uint8_t bits = 0;
+			const float saved = M0;
+			float x = M0;
+			const float dj = Dr[j];
+			if (dj > x) { x = dj; bits = XB_DM; }
+			if (I0 > x) { x = I0; bits = XB_IM; }
+			M0 = M[j];
+			const uint64_t eb = dir ? PB[sd.lo_b - j] : PB[sd.lo_b + j - 1];
+			float s = subst(s_tab, ea, eb);
+			s += x;
+			M[j] = s;
+			float h = s - best + X;
+			if (h > 0) { next_jlo = min(next_jlo, j + 1); next_jhi = j + 1; }
+			if (h > absopen) next_jlo = min(next_jlo, j);
+			if (h > absext && j == jhi && jhi + 1 < LB) {
+				++jhi;
+				const uint32_t ne = max(min(jhi + 1, LB), endj);
+				for (uint32_t j2 = endj + 1; j2 <= ne; ++j2) {
+					if (j2 - 1 > j) M[j2 - 1] = kNegInf;
+					Dr[j2] = kNegInf;
+				}
+				endj = ne;
+			}
+			if (s >= best) { best = s; besti = i; bestj = j; }
+			if (j != jlo) {
+				const float md = saved + open;
+				float dn = Dr[j] + ext;
+				if (md >= dn) { dn = md; bits |= XB_MD; }
+				Dr[j] = dn;
+				h = dn - best + X;
+				if (h > 0) { next_jlo = min(next_jlo, j - 1); next_jhi = max(next_jhi, j - 1); }
+			}
+			const float mi = saved + open;
+			I0 += ext;
+			if (mi >= I0) { I0 = mi; bits |= XB_MI; }
+			h = I0 - best + X;
+			if (h > 0) { next_jlo = min(next_jlo, j + 1); next_jhi = max(next_jhi, j + 1); }
+			if (h > absext && j == jhi && jhi + 1 < LB) {
+				++jhi;
+				const uint32_t ne = max(min(jhi + 1, LB), endj);
+				for (uint32_t j2 = endj + 1; j2 <= ne; ++j2) {
+					M[j2 - 1] = kNegInf;
+					Dr[j2] = kNegInf;
+				}
+				endj = ne;
+			}
+			row[j] = bits;
+		}
+		if (jhi < LB) {
+			const uint32_t j1 = jhi + 1;
+			uint8_t b1 = 0;
+			const float md = M0 + open;
+			float dn = Dr[j1] + ext;
+			if (md >= dn) { dn = md; b1 = XB_MD; }
+			Dr[j1] = dn;
+			row[j1] = b1;
+		}
+		if (next_jlo == kNone)
+			break;
+		prev_jlo = jlo; prev_jhi = jhi;
+		jlo = next_jlo; jhi = next_jhi;
+		if (jlo > LB) jlo = LB;
+		if (jhi > LB) jhi = LB;
+		if (jlo == prev_jlo) { M0 = kNegInf; Dr[jlo] = kNegInf; }
+		else M0 = M[jlo - 1];
+	}
+#undef SUBST
+	if (!(best > 0.0f))
+		return;
+	res.score = best;
+	uint32_t i = besti, j = bestj, n = 0;
+	int st = 0;  // 0 M, 1 D, 2 I
+	for (;;) {
+		stage[n++] = (uint8_t)(st == 0 ? 'M' : st == 1 ? 'D' : 'I');
+		if (i == 1 || j == 1)
+			break;
+		int nx;
+		if (st == 0) {
+			const uint8_t c = tbm[(size_t)i * W + j];
+			nx = (c & XB_DM) ? 1 : (c & XB_IM) ? 2 : 0;
+			--i; --j;
+		} else if (st == 1) {
+			nx = (tbm[(size_t)i * W + j + 1] & XB_MD) ? 0 : 1;
+			--i;
+		} else {
+			nx = (tbm[(size_t)(i + 1) * W + j] & XB_MI) ? 0 : 2;
+			--j;
+		}
+		st = nx;
+	}
+	res.path_len = n;  // stage[] holds the path from its end to its start
+}
+
+// One warp per pair: total score test, MergeFwdBwd, publish record + path.
+__global__ void __launch_bounds__(128) mkf_finish_kernel(const MkfArgs a)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t pair = blockIdx.x * 4 + warp;
+	if (pair >= a.npairs)
+		return;
+	PairRec *rec = a.rec + a.pair_slot[pair];
+	const MkfSeed sd = a.seeds[pair];
+	if (lane == 0) {
+		rec->flags = RSK_HIT_MKF;
+		rec->mu_fwd = sd.best_hsp;
+		rec->mu_rev = sd.best_chain;
+	}
+	if (!sd.valid) {  // ClearAlign state: score 0, no path (also undoes a record a non-filtered SW pass may have written)
+		if (lane == 0) {
+			rec->score = 0.0f;
+			rec->path_len = 0;
+			rec->lo_a = rec->lo_b = 0xffffffffu;
+		}
+		return;
+	}
+	const MkfXdrop f = a.xres[2 * pair], b = a.xres[2 * pair + 1];
+	const float total = f.score + b.score;
+	if (total < 10) {  // xdrophsp.cpp:109-113
+		if (lane == 0) {
+			rec->score = 0.0f;
+			rec->path_len = 0;
+			rec->lo_a = rec->lo_b = 0xffffffffu;
+		}
+		return;
+	}
+	const uint8_t *fs = a.scratch + f.stage_off, *bs = a.scratch + b.stage_off;
+	const uint32_t nf = f.path_len, nb = b.path_len, n = nf + nb;
+	unsigned long long off = 0;
+	if (lane == 0)
+		off = atomicAdd(a.pool_cursor, (unsigned long long)n);
+	off = __shfl_sync(kFull, off, 0);
+	// backward DP: its own forward order is reverse(stage); XDropBwd reverses once more -> stage order as is.
+	uint32_t bM = 0, bD = 0;
+	for (uint32_t k = lane; k < nb; k += 32) {
+		const uint8_t c = bs[k];
+		a.pool[off + k] = c;
+		bM += (c == 'M');
+		bD += (c == 'D');
+	}
+	for (uint32_t k = lane; k < nf; k += 32)
+		a.pool[off + nb + k] = fs[nf - 1 - k];
+#pragma unroll
+	for (int o = 16; o >= 1; o >>= 1) {
+		bM += __shfl_xor_sync(kFull, bM, o);
+		bD += __shfl_xor_sync(kFull, bD, o);
+	}
+	if (lane == 0) {
+		const uint32_t bI = nb - bM - bD;
+		rec->score = total;
+		rec->lo_a = nb ? sd.lo_a - (bM + bD) : sd.lo_a;  // mergefwdback.cpp:36-49
+		rec->lo_b = nb ? sd.lo_b - (bM + bI) : sd.lo_b;
+		rec->path_len = n;
+		rec->path_off = off;
+	}
+}
+
+}  // namespace
+
+int launch_mkf(const MkfArgs &args, uint32_t nhash, cudaStream_t stream)
+{
+	if (args.npairs == 0)
+		return 0;
+	mkf_hash_kernel<<<nhash, 256, 0, stream>>>(args);
+	mkf_seed_kernel<<<(args.npairs + kSeedWarps - 1) / kSeedWarps, kSeedWarps * 32, 0, stream>>>(args);
+	mkf_xdrop_kernel<<<(2 * args.npairs + 63) / 64, 64, 0, stream>>>(args);
+	mkf_finish_kernel<<<(args.npairs + 3) / 4, 128, 0, stream>>>(args);
+	return cudaGetLastError() == cudaSuccess ? 4 : -1;
+}
+
+size_t mkf_hash_bytes() { return (size_t)kDict * kHashW * sizeof(uint16_t); }
+
+}  // namespace rsk

@@ -161,8 +161,9 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter_kernel(const MuArg
 		int fwd = 0, rev = 0;
 		bool need_rev = false;
 		// DoMKF() pairs are not the filter's business (dssaligner.cpp:811-815 returns before the filter)
-		const bool mkf_a = (uint32_t)LA >= a.mkfl;
-		const bool mkf = have && (mkf_a || (uint32_t)LB >= a.mkfl);
+		// (k-mers exist only for chains of >= 3 residues: dss.cpp:659-682)
+		const bool mkf_a = false;
+		const bool mkf = have && LA >= 3 && LB >= 3 && ((uint32_t)LA >= a.mkfl || (uint32_t)LB >= a.mkfl);
 		const bool run = have && !mkf;
 		for (int dir = 0; dir < 2 && !mkf_a; ++dir) {
 			if (dir == 1) {
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter_kernel(const MuArg
 			rec->mu_fwd = fwd;
 			rec->mu_rev = rrev;
 			const bool pass_ = !mkf && !(score < a.omega);  // dssaligner.cpp:627
-			rec->flags = mkf ? (uint32_t)RSK_HIT_MKF_PENDING : pass_ ? 0u : (uint32_t)RSK_HIT_MU_REJECTED;
+			rec->flags = mkf ? (uint32_t)RSK_HIT_MKF : pass_ ? 0u : (uint32_t)RSK_HIT_MU_REJECTED;
 			a.keep[slot] = pass_ ? 1 : 0;
 			if (fwd == 777)
 				atomicAdd(a.sat_counter, 1u);

@@ -137,6 +137,13 @@ struct rsk_ctx {
 	size_t filt_explicit_pairs = 0; uint64_t filt_explicit_cells = 0; uint32_t filt_explicit_tasks = 0; bool batch_cross = true;
 	struct Counters { uint32_t task_count[4]; uint32_t sw_task_counter[4]; uint32_t sat_count, mu_task_counter; unsigned long long pair_count, cell_count; };
 	DevBuf<uint32_t> rowlist, colsort;
+	// long-chain path (K4)
+	DevBuf<uint32_t> mk_a, mk_b, mk_slot, mk_hash, mk_hchain;
+	DevBuf<unsigned long long> mk_off;
+	DevBuf<uint16_t> mk_ht;
+	DevBuf<MkfSeed> mk_seed;
+	DevBuf<MkfXdrop> mk_x;
+	DevBuf<unsigned char> mk_scratch;
 	Counters *d_counters = nullptr;
 	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU
 	PinBuf<uint8_t> h_pool[2];
@@ -350,6 +357,8 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->h_rec[0].release(); ctx->h_rec[1].release(); ctx->h_pool[0].release(); ctx->h_pool[1].release();
 	ctx->keep.release(); ctx->mu_bnd.release(); ctx->c_blist.release(); ctx->c_bslot.release();
 	ctx->c_task_a.release(); ctx->c_task_begin.release(); ctx->c_task_cnt.release(); ctx->rowlist.release(); ctx->colsort.release();
+	ctx->mk_a.release(); ctx->mk_b.release(); ctx->mk_slot.release(); ctx->mk_hash.release(); ctx->mk_hchain.release();
+	ctx->mk_off.release(); ctx->mk_ht.release(); ctx->mk_seed.release(); ctx->mk_x.release(); ctx->mk_scratch.release();
 	if (ctx->d_mu_mx) cudaFree(ctx->d_mu_mx);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->d_tables) cudaFree(ctx->d_tables);
@@ -554,6 +563,100 @@ int upload_vec(rsk_ctx *ctx, DevBuf<T> &dst, const std::vector<T> &src)
 	if (!src.empty())
 		CK(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
 	ctx->stats.h2d_bytes += src.size() * sizeof(T);
+	return RSK_OK;
+}
+
+// Long-chain pairs of a batch through K4 (hash tables, seeds/chain/re-score, banded x-drop, merge), in chunks that
+// respect the scratch budget.  Pair order is A-major so that one hash table serves consecutive pairs.
+int run_mkf(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b)
+{
+	const rsk_chainset *A = plan.A, *B = plan.B;
+	cudaStream_t st = ctx->stream;
+	const uint32_t mkfl = ctx->params.mkfl;
+	std::vector<uint32_t> pa, pb, ps;
+	auto is_mkf = [&](uint32_t la, uint32_t lb) { return la >= 3 && lb >= 3 && (la >= mkfl || lb >= mkfl); };
+	if (b.cross) {
+		const uint32_t nB = B->d.n;
+		std::vector<uint32_t> longB;
+		for (uint32_t j = 0; j < nB; ++j)
+			if (B->hlen[j] >= mkfl)
+				longB.push_back(j);
+		for (uint32_t a = b.a0; a < b.a1; ++a) {
+			const uint32_t la = A->hlen[a];
+			if (la < 3)
+				continue;
+			if (la >= mkfl) {
+				for (uint32_t j = 0; j < nB; ++j)
+					if (B->hlen[j] >= 3) { pa.push_back(a); pb.push_back(j); ps.push_back((a - b.a0) * nB + j); }
+			} else {
+				for (uint32_t j : longB) { pa.push_back(a); pb.push_back(j); ps.push_back((a - b.a0) * nB + j); }
+			}
+		}
+	} else {
+		for (size_t k = 0; k < b.npairs; ++k) {
+			const uint32_t a = plan.sa[b.k0 + k], j = plan.sb[b.k0 + k];
+			if (is_mkf(A->hlen[a], B->hlen[j])) { pa.push_back(a); pb.push_back(j); ps.push_back((uint32_t)k); }
+		}
+	}
+	const size_t n = pa.size();
+	if (n == 0)
+		return RSK_OK;
+	ctx->stats.mkf_pairs += n;
+	const size_t scratch_cap = std::min<size_t>(ctx->scratch_budget / 2, (size_t)12 << 30);
+	const size_t max_hash = 1024;
+	size_t k0 = 0;
+	while (k0 < n) {
+		std::vector<uint32_t> hidx, hchain;
+		std::vector<unsigned long long> off;
+		size_t bytes = 0, k1 = k0;
+		while (k1 < n) {
+			const size_t need = (xdrop_pair_bytes(A->hlen[pa[k1]], B->hlen[pb[k1]]) + 255) & ~(size_t)255;
+			const bool newchain = hchain.empty() || hchain.back() != pa[k1];
+			if (k1 > k0 && (bytes + need > scratch_cap || (newchain && hchain.size() >= max_hash)))
+				break;
+			if (newchain)
+				hchain.push_back(pa[k1]);
+			hidx.push_back((uint32_t)hchain.size() - 1);
+			off.push_back(bytes);
+			bytes += need;
+			++k1;
+		}
+		const size_t m = k1 - k0;
+		if (ctx->mk_a.ensure(m) || ctx->mk_b.ensure(m) || ctx->mk_slot.ensure(m) || ctx->mk_hash.ensure(m) ||
+			ctx->mk_hchain.ensure(hchain.size()) || ctx->mk_off.ensure(m) || ctx->mk_seed.ensure(m) || ctx->mk_x.ensure(2 * m) ||
+			ctx->mk_ht.ensure(hchain.size() * (mkf_hash_bytes() / 2)) || ctx->mk_scratch.ensure(bytes + 256)) {
+			cudaGetLastError();
+			return fail(RSK_ERR_NOMEM, "long-chain path buffers (%zu pairs, %zu MB scratch)", m, bytes >> 20);
+		}
+		CK(cudaMemcpyAsync(ctx->mk_a.p, pa.data() + k0, 4 * m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(ctx->mk_b.p, pb.data() + k0, 4 * m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(ctx->mk_slot.p, ps.data() + k0, 4 * m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(ctx->mk_hash.p, hidx.data(), 4 * m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(ctx->mk_hchain.p, hchain.data(), 4 * hchain.size(), cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(ctx->mk_off.p, off.data(), 8 * m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemsetAsync(ctx->mk_scratch.p, 0, bytes, st));  // trace matrices start zeroed
+		ctx->stats.h2d_bytes += 24 * m + 4 * hchain.size();
+		MkfArgs ma;
+		memset(&ma, 0, sizeof(ma));
+		ma.muA = A->d.mu; ma.profA = A->d.prof8; ma.offA = A->d.off; ma.lenA = A->d.len;
+		ma.muB = B->d.mu; ma.profB = B->d.prof8; ma.offB = B->d.off; ma.lenB = B->d.len;
+		ma.npairs = (uint32_t)m;
+		ma.pair_a = ctx->mk_a.p; ma.pair_b = ctx->mk_b.p; ma.pair_slot = ctx->mk_slot.p; ma.pair_hash = ctx->mk_hash.p;
+		ma.hash_chain = ctx->mk_hchain.p; ma.hash = ctx->mk_ht.p;
+		ma.seeds = ctx->mk_seed.p; ma.xres = ctx->mk_x.p;
+		ma.scratch = ctx->mk_scratch.p; ma.scratch_off = ctx->mk_off.p;
+		ma.rec = ctx->rec.p; ma.pool = ctx->pool.p; ma.pool_cursor = ctx->d_pool_cursor;
+		ma.mu_mx = ctx->d_mu_mx; ma.tables = ctx->d_tables;
+		ma.x1 = ctx->params.mkf_x1; ma.min_hsp_score = ctx->params.mkf_min_hsp_score;
+		ma.x2 = (float)ctx->params.mkf_x2; ma.min_mega_hsp_score = ctx->params.mkf_min_mega_hsp_score;
+		ma.open = ctx->params.gap_open; ma.ext = ctx->params.gap_ext;
+		int nl = launch_mkf(ma, (uint32_t)hchain.size(), st);
+		if (nl < 0)
+			return fail(RSK_ERR_CUDA, "long-chain kernels failed to launch: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->stats.kernel_launches += nl;
+		CK(cudaStreamSynchronize(st));  // the host vectors of this chunk are reused
+		k0 = k1;
+	}
 	return RSK_OK;
 }
 
@@ -791,6 +894,14 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	}
 	CK(cudaEventRecord(ctx->ev[1], st));
 
+	// ---- K4: pairs with a chain >= MKFL take the k-mer / x-drop path instead (dssaligner.cpp:811-815, 715-732) ----
+	if (A->has_mu && B->has_mu && (b.maxLA >= ctx->params.mkfl || b.maxLB >= ctx->params.mkfl)) {
+		rc = run_mkf(ctx, plan, b);
+		if (rc)
+			return rc;
+	}
+	CK(cudaEventRecord(ctx->ev[4], st));
+
 	if (!opts.skip_evalue) {
 		LddtArgs la;
 		memset(&la, 0, sizeof(la));
@@ -841,8 +952,10 @@ int finish_batch_timing(rsk_ctx *ctx)
 	}
 	CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
 	ctx->stats.sw_kernel_ms += ms;
-	CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+	CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[2]));
 	ctx->stats.lddt_kernel_ms += ms;
+	CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[4]));
+	ctx->stats.mkf_kernel_ms += ms;
 	return RSK_OK;
 }
 

@@ -158,6 +158,42 @@ struct CompactArgs {
 	unsigned long long *cell_count;
 };
 
+// K4: long-chain path (MKF seeds -> chain -> x-drop), see mkf_kernel.cu
+struct MkfSeed { uint32_t valid, lo_a, lo_b; int32_t best_hsp, best_chain; };
+struct MkfXdrop { float score; uint32_t path_len; unsigned long long stage_off; };
+// bytes of scratch one banded DP of la rows x lb columns needs (2 float rows, path staging, trace matrix)
+__host__ __device__ inline size_t xdrop_region_bytes(uint32_t la, uint32_t lb)
+{
+	const size_t rows = (size_t)2 * (lb + 4) * sizeof(float);
+	const size_t stage = ((size_t)la + lb + 4 + 15) & ~(size_t)15;
+	const size_t tb = (size_t)(la + 3) * (lb + 3);
+	return (rows + stage + tb + 15) & ~(size_t)15;
+}
+// upper bound for the backward + forward regions of one pair, whatever the seed position
+__host__ __device__ inline size_t xdrop_pair_bytes(uint32_t LA, uint32_t LB)
+{
+	return (size_t)(LA + 6) * (LB + 6) + (size_t)8 * (LB + 8) + (size_t)LA + LB + 38 + 64;
+}
+struct MkfArgs {
+	// reference orientation: A = query slot (hash table side), B = target slot
+	const uint8_t *muA; const uint64_t *profA; const uint64_t *offA; const uint32_t *lenA;
+	const uint8_t *muB; const uint64_t *profB; const uint64_t *offB; const uint32_t *lenB;
+	uint32_t npairs;
+	const uint32_t *pair_a, *pair_b, *pair_slot, *pair_hash;  // [npairs]; pair_hash = index of the A chain's hash table
+	const uint32_t *hash_chain;  // [nhash] A chain of each hash table
+	uint16_t *hash;
+	MkfSeed *seeds;              // [npairs]
+	MkfXdrop *xres;              // [2*npairs]
+	unsigned char *scratch; const unsigned long long *scratch_off;  // per pair
+	PairRec *rec;
+	uint8_t *pool; unsigned long long *pool_cursor;
+	const int *mu_mx; const float *tables;
+	int x1, min_hsp_score; float x2, min_mega_hsp_score;
+	float open, ext;
+};
+int launch_mkf(const MkfArgs &args, uint32_t nhash, cudaStream_t stream);
+size_t mkf_hash_bytes();
+
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();

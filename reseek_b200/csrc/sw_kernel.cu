@@ -80,25 +80,6 @@ __device__ __forceinline__ void build_rowtab(float *p0, float *p1, const float *
 	}
 }
 
-__device__ __forceinline__ float lds_f32(uint32_t addr)
-{
-	float v;
-	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-	return v;
-}
-__device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
-{
-	float2 v;
-	asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-	return v;
-}
-__device__ __forceinline__ float4 lds_f32x4(uint32_t addr)
-{
-	float4 v;
-	asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-	return v;
-}
-
 // Packed fp32 add (FADD2 on sm_100a): two independent IEEE round-to-nearest adds in one issue slot.
 __device__ __forceinline__ float2 add2(const float2 a, const float2 b)
 {

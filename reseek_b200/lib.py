@@ -12,7 +12,7 @@ NFEAT = 8
 TABLE_FLOATS = 2192
 MODE_FAST, MODE_SENSITIVE, MODE_VERYSENSITIVE = 1, 2, 3
 KEEP_HITS, KEEP_ALL = 0, 1
-HIT_MU_REJECTED, HIT_HAS_EVALUE, HIT_REPORTED, HIT_MKF_PENDING = 1, 2, 4, 8
+HIT_MU_REJECTED, HIT_HAS_EVALUE, HIT_REPORTED, HIT_MKF = 1, 2, 4, 8
 FLT_MAX = float(np.finfo(np.float32).max)
 
 
@@ -42,7 +42,8 @@ class Stats(C.Structure):
                 ("mu_saturated", C.c_uint64), ("sw_pairs", C.c_uint64), ("sw_cells", C.c_uint64),
                 ("evalue_pairs", C.c_uint64), ("hits", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sw_kernel_ms", C.c_float),
-                ("mu_kernel_ms", C.c_float), ("lddt_kernel_ms", C.c_float), ("total_ms", C.c_float)]
+                ("mu_kernel_ms", C.c_float), ("lddt_kernel_ms", C.c_float), ("total_ms", C.c_float),
+                ("mkf_kernel_ms", C.c_float), ("reserved", C.c_uint32), ("mkf_pairs", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

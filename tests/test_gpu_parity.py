@@ -103,12 +103,19 @@ def test_golden_reference_fixtures_on_gpu(rb, mode):
             c.mu = None
     S = ctx.upload_chains(chains)
     res = ctx.search_cross(S, S, keep=rb.KEEP_ALL, want_paths=True)
-    n = 0
+    n = nmkf = nmkf_path = 0
     for k, h in enumerate(res.hits):
         assert (int(h["a"]), int(h["b"])) == (int(g["a"][k]), int(g["b"][k]))
-        if g["mkf"][k]:
-            assert int(h["flags"]) & rb.HIT_MKF_PENDING, "DoMKF pairs must be flagged, not silently mis-aligned"
-            continue
+        mkf = bool(g["mkf"][k])
+        assert bool(int(h["flags"]) & rb.HIT_MKF) == mkf, f"pair {k}: DoMKF routing"
+        if mkf:
+            nmkf += 1
+            nmkf_path += bool(g["path_list"][k])
+            assert (int(h["mu_fwd"]), int(h["mu_rev"])) == (int(g["best_hsp"][k]), int(g["best_chain"][k])), f"pair {k} MKF HSP/chain scores"
+            if not g["path_list"][k]:
+                # no alignment: the reference leaves Hi at Lo + 0 - 1 (wrapped) in one branch; unobservable
+                assert res.path(k) == "" and float(h["score"]) == 0.0 and float(h["evalue"]) > 1e38
+                continue
         n += 1
         assert res.path(k) == g["path_list"][k], f"pair {k} path"
         assert bits(h["score"]) == bits(g["score"][k]), f"pair {k} score"
@@ -120,6 +127,8 @@ def test_golden_reference_fixtures_on_gpu(rb, mode):
         if g["evalue"][k] < 1e38:
             assert bits(h["lddt"]) == bits(g["lddt"][k]) and bits(h["qual"]) == bits(g["qual"][k])
     assert n > 150
+    if mode != 3:
+        assert nmkf > 150 and nmkf_path >= 20 and ctx.stats()["mkf_pairs"] == nmkf
     ctx.close()
 
 
@@ -154,4 +163,43 @@ def test_both_orientations_and_all_row_classes(rb, port):
     _check_all(rb, port(3), res, ob, os_)
     res = ctx.search_self(Bg, keep=rb.KEEP_ALL)
     _check_all(rb, port(3), res, ob, ob)
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", [2, 1])
+def test_long_chain_path_matches_oracle(rb, port, mode):
+    """Chains >= MKFL (k-mer seeds -> chain -> banded x-drop) mixed with short ones, cross and explicit."""
+    from reseek_b200 import synth
+    from tests.util import to_oracle_chains
+    a = synth.make_chains(7, [650, 120, 700, 820, 610, 300, 640], seed=61)
+    b = synth.make_chains(9, [300, 640, 720, 150, 660, 1000, 90, 605, 2], seed=62)
+    synth.plant_homologs(b, a, 0.9, seed=63, sub=0.25, indel=0.03)
+    ctx = rb.Context(0, mode)
+    A = ctx.upload(a.lens, a.prof, a.mu, a.xyz, a.selfrev)
+    B = ctx.upload(b.lens, b.prof, b.mu, b.xyz, b.selfrev)
+    oa, ob = to_oracle_chains(a), to_oracle_chains(b)
+    res = ctx.search_cross(A, B, keep=rb.KEEP_ALL, want_paths=True)
+    p = port(mode)
+    nmkf = npath = 0
+    from tests.util import bits
+    for k, h in enumerate(res.hits):
+        r, rpath = p.align_pair(oa[int(h["a"])], ob[int(h["b"])])
+        mkf = bool(int(h["flags"]) & rb.HIT_MKF)
+        if not mkf:
+            from tests.util import assert_hit_matches_oracle
+            assert_hit_matches_oracle(h, res.path(k), r, rpath, ctx=f"pair {k}")
+            continue
+        nmkf += 1
+        assert res.path(k) == rpath, f"pair {k} ({oa[int(h['a'])].L} x {ob[int(h['b'])].L}) path"
+        assert bits(h["score"]) == bits(r.score), f"pair {k} score {h['score']} vs {r.score}"
+        if rpath:
+            npath += 1
+            assert (int(h["lo_a"]), int(h["lo_b"]), int(h["hi_a"]), int(h["hi_b"])) == (r.lo_a, r.lo_b, r.hi_a, r.hi_b)
+            assert bits(h["ts"]) == bits(r.ts) and bits(h["lddt"]) == bits(r.lddt), f"pair {k} ts/lddt"
+    assert nmkf >= 40 and npath >= 5
+    ia = np.repeat(np.arange(a.n, dtype=np.uint32), b.n)
+    ib = np.tile(np.arange(b.n, dtype=np.uint32), a.n)
+    res2 = ctx.search_pairs(A, B, ia, ib, keep=rb.KEEP_ALL, want_paths=True)
+    for f in ("score", "lo_a", "lo_b", "hi_a", "hi_b", "ts", "flags", "path_len", "mu_fwd", "mu_rev"):
+        assert np.array_equal(res.hits[f], res2.hits[f]), f
     ctx.close()
