@@ -187,6 +187,20 @@ const char *rsk_results_paths(const rsk_results *r);    /* path pool: 'M','D','I
 uint64_t rsk_results_paths_bytes(const rsk_results *r);
 void rsk_results_free(rsk_results *r);
 
+/* ---- hit writers: DSSAligner::ToTsv / WriteUserField (dssaligner.cpp:1016, userfields.cpp:45-152), PathToCIGAR (cigar.cpp:95) ----
+ * Host-only formatting, byte-compatible with the reference's -output TSV.  up != 0: query = A, target = B. */
+typedef struct rsk_hit_view {
+	const rsk_hit *hit;
+	const char *path;               /* the hit's M/D/I path (path pool + hit->path_off), may be NULL without cigar/pctid */
+	const char *label_a, *label_b;  /* chain labels */
+	const char *seq_a, *seq_b;      /* amino-acid sequences (only for pctid), may be NULL */
+	uint32_t len_a, len_b;
+} rsk_hit_view;
+int rsk_path_to_cigar(const char *path, uint32_t path_len, int up, char *out, size_t cap);
+/* columns: '+'-separated names as for -columns (userfieldnames.h); NULL = the reference's default ("std", usage.h:49).
+ * Returns the line length (no newline) or a negative rsk_status. */
+int rsk_format_tsv(const rsk_hit_view *v, int up, const char *columns, char *out, size_t cap);
+
 /* ---- host-side statistics: StatSig (statsig.cpp:27-50, statsig.h:8-23); libm double pow, as the reference ---- */
 double rsk_pvalue(double ts);
 double rsk_evalue(double ts);

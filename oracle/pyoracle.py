@@ -324,6 +324,24 @@ class Ref:
                                  C.c_uint64(len(ia)), p(ia), p(ib), p(score), p(evalue), p(plen))
         return score, evalue, plen
 
+    def align_pair_tsv(self, A, B, columns, up, use_mu=True):
+        """The reference's own TSV line (DSSAligner::ToTsv) for the pair, '' when there is no alignment."""
+        def p(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+        out = C.create_string_buffer(1 << 16)
+        muA = A.mu if use_mu else None
+        muB = B.mu if use_mu else None
+        kA = A.kmers if use_mu else None
+        kB = B.kmers if use_mu else None
+        self.lib.ref_align_pair_tsv(
+            A.L, (A.label or "A").encode(), A.seq, p(A.prof), p(muA), p(kA), 0 if kA is None else len(kA),
+            p(A.xyz[0]), p(A.xyz[1]), p(A.xyz[2]), C.c_float(A.selfrev),
+            B.L, (B.label or "B").encode(), B.seq, p(B.prof), p(muB), p(kB), 0 if kB is None else len(kB),
+            p(B.xyz[0]), p(B.xyz[1]), p(B.xyz[2]), C.c_float(B.selfrev),
+            columns.encode(), int(up), out, 1 << 16)
+        return out.value.decode().rstrip("\n")
+
     def mu_score(self, a, b):
         a = np.ascontiguousarray(a, np.uint8)
         b = np.ascontiguousarray(b, np.uint8)

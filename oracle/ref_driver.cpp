@@ -258,6 +258,54 @@ int ref_align_pair(
 	return 0;
 	}
 
+// AlignQueryTarget followed by the reference's own TSV writer (DSSAligner::ToTsv, userfields.cpp:45-152).
+// Returns the number of bytes written to out (0 when the pair has no alignment).
+int ref_align_pair_tsv(
+  uint LA, const char *labelA, const char *seqA, const uint8_t *profA, const uint8_t *muA, const uint32_t *kmA, uint nkA,
+  const float *xA, const float *yA, const float *zA, float selfrevA,
+  uint LB, const char *labelB, const char *seqB, const uint8_t *profB, const uint8_t *muB, const uint32_t *kmB, uint nkB,
+  const float *xB, const float *yB, const float *zB, float selfrevB,
+  const char *columns, int up, char *out, uint cap)
+	{
+	PDBChain CA, CB;
+	MakeChain(CA, labelA, LA, seqA, xA, yA, zA);
+	MakeChain(CB, labelB, LB, seqB, xB, yB, zB);
+	vector<vector<byte> > PA, PB;
+	MakeProfile(PA, LA, profA);
+	MakeProfile(PB, LB, profB);
+	vector<byte> MuA, MuB;
+	vector<uint> KA, KB;
+	if (muA) MuA.assign(muA, muA + LA);
+	if (muB) MuB.assign(muB, muB + LB);
+	if (kmA) KA.assign(kmA, kmA + nkA);
+	if (kmB) KB.assign(kmB, kmB + nkB);
+	DSSAligner &DA = *g_DA;
+	DA.m_UFs.clear();
+	vector<string> Fields;
+	Split(string(columns), Fields, '+');
+	for (uint i = 0; i < SIZE(Fields); ++i)
+		DA.m_UFs.push_back(StrToUF(Fields[i]));
+	DA.SetQuery(CA, &PA, muA ? &MuA : 0, kmA ? &KA : 0, selfrevA);
+	DA.SetTarget(CB, &PB, muB ? &MuB : 0, kmB ? &KB : 0, selfrevB);
+	DA.AlignQueryTarget();
+	out[0] = 0;
+	uint n = 0;
+	if (!DA.m_Path.empty() && DA.m_EvalueA != FLT_MAX)
+		{
+		char *buf = 0;
+		size_t sz = 0;
+		FILE *f = open_memstream(&buf, &sz);
+		DA.ToTsv(f, up != 0);
+		fclose(f);
+		n = (uint) min(sz, (size_t) cap - 1);
+		memcpy(out, buf, n);
+		out[n] = 0;
+		free(buf);
+		}
+	DA.UnsetQuery();
+	return (int) n;
+	}
+
 // Mu filter score exactly as DSSAligner::GetMuScore() under the search params (parasail_mu.cpp:120-161)
 float ref_mu_score(uint LA, const uint8_t *muA, uint LB, const uint8_t *muB)
 	{

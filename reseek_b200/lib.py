@@ -33,6 +33,11 @@ class ChainsHost(C.Structure):
                 ("mu", C.c_void_p), ("xyz", C.c_void_p), ("selfrev", C.c_void_p)]
 
 
+class HitView(C.Structure):
+    _fields_ = [("hit", C.c_void_p), ("path", C.c_char_p), ("label_a", C.c_char_p), ("label_b", C.c_char_p),
+                ("seq_a", C.c_char_p), ("seq_b", C.c_char_p), ("len_a", C.c_uint32), ("len_b", C.c_uint32)]
+
+
 class SearchOpts(C.Structure):
     _fields_ = [("keep", C.c_int32), ("want_paths", C.c_int32), ("skip_evalue", C.c_int32), ("reserved", C.c_int32)]
 
@@ -102,6 +107,8 @@ def load_library():
     L.rsk_search_cross_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts)]
     for fn in (L.rsk_results_count, L.rsk_results_hits, L.rsk_results_paths, L.rsk_results_paths_bytes):
         fn.argtypes = [C.c_void_p]
+    L.rsk_format_tsv.argtypes = [C.POINTER(HitView), C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
+    L.rsk_path_to_cigar.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]
     L.rsk_results_free.argtypes = [C.c_void_p]
     L.rsk_results_free.restype = None
     _lib = L
@@ -125,6 +132,28 @@ def params_preset(mode):
     p = Params()
     _check(load_library().rsk_params_preset(C.byref(p), int(mode)))
     return p
+
+
+def format_tsv(hit, path, label_a, label_b, len_a, len_b, up=True, columns=None, seq_a=None, seq_b=None):
+    """One TSV line for a hit record (numpy void of HIT_DTYPE), as DSSAligner::ToTsv would print it."""
+    L = load_library()
+    rec = np.array([hit], dtype=HIT_DTYPE)
+    v = HitView(rec.ctypes.data, path.encode() if isinstance(path, str) else path, label_a.encode(), label_b.encode(),
+                seq_a, seq_b, int(len_a), int(len_b))
+    out = C.create_string_buffer(1 << 16)
+    n = L.rsk_format_tsv(C.byref(v), int(bool(up)), columns.encode() if columns else None, out, 1 << 16)
+    if n < 0:
+        raise ReseekB200Error(f"rsk_format_tsv failed ({n})")
+    return out.value.decode()
+
+
+def path_to_cigar(path, up=True):
+    L = load_library()
+    out = C.create_string_buffer(4 * len(path) + 16)
+    n = L.rsk_path_to_cigar(path.encode(), len(path), int(bool(up)), out, len(out))
+    if n < 0:
+        raise ReseekB200Error(f"rsk_path_to_cigar failed ({n})")
+    return out.value.decode()
 
 
 def _ptr(a):

@@ -52,3 +52,35 @@ def test_product_never_imports_oracle():
         if f.suffix in (".py", ".cu", ".cuh", ".cpp", ".h", ".hpp") and f.is_file():
             txt = f.read_text(errors="ignore")
             assert "pyoracle" not in txt and "reseek_oracle" not in txt and "oracle/" not in txt.replace("oracle/_ref", ""), f
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_tsv_writer_matches_reference_lines(built_lib, mode):
+    """rsk_format_tsv against lines printed by the reference's own DSSAligner::ToTsv (golden fixtures), both
+    directions (Up / !Up: query/target swap and the D<->I swap of the CIGAR)."""
+    import reseek_b200 as rb
+    from tests.golden_util import load_chains, load_pairs
+    g = load_pairs(mode)
+    chains = load_chains()
+    cols = str(g["tsv_cols"])
+    names = cols.split("+")
+    assert len(g["tsv_lines"]) >= 20
+    for k, up, line in zip(g["tsv_k"], g["tsv_up"], g["tsv_lines"]):
+        k = int(k)
+        h = np.zeros(1, rb.HIT_DTYPE)[0]
+        for f in ("score", "lo_a", "lo_b", "hi_a", "hi_b", "ids", "gaps", "lddt", "ts", "pvalue", "evalue", "qual"):
+            h[f] = g[f][k]
+        h["path_len"] = len(g["path_list"][k])
+        mkf = bool(g["mkf"][k])
+        if mkf:
+            h["flags"] = rb.HIT_MKF
+            h["mu_fwd"], h["mu_rev"] = g["best_hsp"][k], g["best_chain"][k]
+        A, B = chains[int(g["a"][k])], chains[int(g["b"][k])]
+        mine = rb.format_tsv(h, g["path_list"][k], A.label, B.label, A.L, B.L, up=bool(up), columns=cols, seq_a=A.seq, seq_b=B.seq)
+        want, got = str(line).split("\t"), mine.split("\t")
+        assert len(want) == len(got) == len(names)
+        for nm, w, m in zip(names, want, got):
+            if nm in ("muhsp", "muchain") and not mkf:
+                continue  # the reference prints whatever the previous long-chain alignment left in m_MKF
+            assert w == m, f"pair {k} up={up} column {nm}: reference '{w}' vs '{m}'"
+    assert rb.path_to_cigar("MMDDIM", up=True) == "2M2D1I1M" and rb.path_to_cigar("MMDDIM", up=False) == "2M2I1D1M"

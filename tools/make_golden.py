@@ -92,6 +92,20 @@ def main():
                 out[k] = np.array(v, np.int32)
             else:
                 out[k] = np.array(v, np.uint32)
+        # the reference's own TSV writer on a sample of pairs, both directions (DSSAligner::ToTsv)
+        cols = "query+target+evalue+pvalue+ql+tl+qlo+qhi+tlo+thi+qcovpct+tcovpct+pctid+newts+raw+dpscore+lddt+ids+gaps+aq+muhsp+muchain+cigar"
+        tsv_k, tsv_up, tsv_line = [], [], []
+        for k in range(0, nc * nc, 3):
+            if not paths[k] or rec["evalue"][k] > 1e38:
+                continue
+            a, b2 = rec["a"][k], rec["b"][k]
+            for up in (1, 0):
+                line = r.align_pair_tsv(chains[a], chains[b2], cols, up, use_mu=(mode != 3))
+                tsv_k.append(k); tsv_up.append(up); tsv_line.append(line)
+        out["tsv_cols"] = np.array(cols)
+        out["tsv_k"] = np.array(tsv_k, np.uint32)
+        out["tsv_up"] = np.array(tsv_up, np.uint8)
+        out["tsv_lines"] = np.array(tsv_line)
         out["selfrev"] = np.array(srs, np.float32)
         out["path_off"] = np.concatenate([[0], np.cumsum([len(p) for p in paths])]).astype(np.uint64)
         out["paths"] = np.frombuffer("".join(paths).encode(), np.uint8)
