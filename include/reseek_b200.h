@@ -165,6 +165,13 @@ uint32_t rsk_chainset_count(const rsk_chainset *cs);
 uint64_t rsk_chainset_residues(const rsk_chainset *cs);
 void rsk_chainset_free(rsk_chainset *cs);
 
+/* Self-reverse scores: GetSelfRevScore (alignpair.cpp:7-25) for every chain of S.  Srev holds, chain by chain, the
+ * profile of the coordinate-reversed chain (PDBChain::GetReverse + DSS, upstream of this library) together with the
+ * FORWARD Mu letters (the reference passes the forward letters for the reversed chain, alignpair.cpp:22).  Chain i of S is
+ * aligned to chain i of Srev with the context's current parameters (ProfileLoader uses omega = 0, profileloader.cpp:22-26;
+ * RunQuery the full search parameters, runquery.cpp:43); the scores are stored in S (host + device) and optionally copied out. */
+int rsk_chainset_selfrev(rsk_ctx *ctx, rsk_chainset *S, const rsk_chainset *Srev, float *scores_out);
+
 /* ---- the per-pair hot loop ----
  * rsk_search_cross: every chain of A (the streamed "-db" side, DSSAligner query slot) against every chain of
  *   B (the in-memory side, target slot): DBSearcher::RunQuery / ThreadBodyQuery (runquery.cpp:18-80).
@@ -179,6 +186,12 @@ int rsk_search_pairs(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B,
 
 /* Same hot loop with results left on the device (no D2H): used to time the resident-data kernel path. */
 int rsk_search_cross_device(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, const rsk_search_opts *opts);
+
+/* Alternative gapless Mu pre-scores: for every listed pair, out_profb[k] = SWFastGaplessProfb
+ * (swgaplessprofb.cpp:6-61, float ScoreMx_Mu, forward minus reversed-A) and out_int[k] = SWFastPinopGapless
+ * (swfastpinopgapless.cpp:6-47, IntScoreMx_Mu).  Either output pointer may be NULL.  Both sets need Mu letters. */
+int rsk_mu_gapless_scores(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib, float *out_profb, int32_t *out_int);
 
 /* ---- results ---- */
 uint64_t rsk_results_count(const rsk_results *r);

@@ -103,6 +103,7 @@ class Port:
         L.orc_cell_score.restype = C.c_float
         L.orc_mu_filter_score.restype = C.c_float
         L.orc_lddt.restype = C.c_float
+        L.orc_mu_gapless_profb.restype = C.c_float
         L.orc_pvalue.restype = C.c_double
         L.orc_evalue.restype = C.c_double
         L.orc_qual.restype = C.c_double
@@ -184,6 +185,13 @@ class Port:
                                          b.ctypes.data_as(C.c_void_p), len(b), C.byref(fwd), C.byref(rev))
         return float(s), fwd.value, rev.value
 
+    def mu_gapless(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        pa, pb = a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)
+        return (float(np.float32(self.lib.orc_mu_gapless_profb(pa, len(a), pb, len(b)))),
+                int(self.lib.orc_mu_gapless_int(pa, len(a), pb, len(b))))
+
     def lddt(self, A, B, posA, posB):
         posA = np.ascontiguousarray(posA, np.uint32)
         posB = np.ascontiguousarray(posB, np.uint32)
@@ -225,6 +233,7 @@ class Ref:
         L.ref_selfrev.restype = C.c_float
         L.ref_mu_score.restype = C.c_float
         L.ref_swfast.restype = C.c_float
+        L.ref_gapless_profb.restype = C.c_float
         L.ref_lddt.restype = C.c_double
         L.ref_init(int(mode))
         self.mode = mode
@@ -346,6 +355,13 @@ class Ref:
         a = np.ascontiguousarray(a, np.uint8)
         b = np.ascontiguousarray(b, np.uint8)
         return float(self.lib.ref_mu_score(len(a), a.ctypes.data_as(C.c_void_p), len(b), b.ctypes.data_as(C.c_void_p)))
+
+    def mu_gapless(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        pa, pb = a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)
+        return (float(np.float32(self.lib.ref_gapless_profb(len(a), pa, len(b), pb))),
+                int(self.lib.ref_gapless_int(len(a), pa, len(b), pb)))
 
     def parasail_sw(self, a, b, open_=2, ext=1):
         a = np.ascontiguousarray(a, np.uint8)

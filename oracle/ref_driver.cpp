@@ -28,6 +28,9 @@ float GetSelfRevScore(DSSAligner &DA, DSS &D, const PDBChain &Chain,
 double GetLDDT_mu_fast(const PDBChain &Q, const PDBChain &T,
   const vector<uint> &PosQs, const vector<uint> &PosTs);
 
+float SWFastGaplessProfb(float *DProw_, const float * const *ProfA, uint LA, const byte *B, uint LB);
+uint SWFastPinopGapless(const int8_t * const *AP, uint LA, const int8_t *B, uint LB);
+
 namespace {
 DSSParams *g_Params = 0;      // search params (RunQuery / RunSelf / PostMuFilter view)
 DSSParams *g_LoadParams = 0;  // ProfileLoader view: Omega=0, UsePara=false (profileloader.cpp:22-26)
@@ -320,6 +323,23 @@ float ref_mu_score(uint LA, const uint8_t *muA, uint LB, const uint8_t *muB)
 	float s = DA.GetMuScore();
 	DA.UnsetQuery();
 	return s;
+	}
+
+// gapless alternatives (declared in dssaligner.cpp:18-32; unreachable from the CLI)
+float ref_gapless_profb(uint LA, const uint8_t *muA, uint LB, const uint8_t *muB)
+	{
+	vector<const float *> Prof(LA);
+	for (uint i = 0; i < LA; ++i)
+		Prof[i] = ScoreMx_Mu[muA[i]];
+	vector<float> DProw(2*LB + 8);
+	return SWFastGaplessProfb(DProw.data(), Prof.data(), LA, muB, LB);
+	}
+int ref_gapless_int(uint LA, const uint8_t *muA, uint LB, const uint8_t *muB)
+	{
+	vector<const int8_t *> AP(LA);
+	for (uint i = 0; i < LA; ++i)
+		AP[i] = IntScoreMx_Mu[muA[i]];
+	return (int) SWFastPinopGapless(AP.data(), LA, (const int8_t *) muB, LB);
 	}
 
 // raw parasail int8 striped SW (parasail.cpp:515): returns score, *sat = saturated flag

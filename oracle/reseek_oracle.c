@@ -372,6 +372,54 @@ static void clear_result(orc_result *r)
 	r->lddt = 0;
 }
 
+/* Gapless variants: on every diagonal a running sum that restarts from 0 whenever it went negative. */
+float orc_mu_gapless_profb(const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB)
+{
+	float bestf = 0, bestr = 0;
+	float *prevf = (float *)malloc(sizeof(float) * (LB + 1)), *prevr = (float *)malloc(sizeof(float) * (LB + 1));
+	float *curf = (float *)malloc(sizeof(float) * (LB + 1)), *curr = (float *)malloc(sizeof(float) * (LB + 1));
+	for (uint32_t j = 0; j <= LB; ++j) prevf[j] = prevr[j] = ORC_NEG_INF; /* row "-1": every diagonal starts fresh */
+	for (uint32_t i = 0; i < LA; ++i) {
+		const float *rowf = rsk_tbl_mu_f32 + 36 * a[i], *rowr = rsk_tbl_mu_f32 + 36 * a[LA - 1 - i];
+		curf[0] = curr[0] = 0; /* M0 = 0 at the start of a row (swgaplessprofb.cpp:55-56; the first row starts at 0 too) */
+		for (uint32_t j = 0; j < LB; ++j) {
+			float xf = (j == 0) ? 0.0f : prevf[j], xr = (j == 0) ? 0.0f : prevr[j]; /* diagonal predecessor (i-1,j-1) */
+			if (xf < 0.0f) xf = 0.0f;
+			if (xr < 0.0f) xr = 0.0f;
+			xf += rowf[b[j]];
+			xr += rowr[b[j]];
+			if (xf > bestf) bestf = xf;
+			if (xr > bestr) bestr = xr;
+			curf[j + 1] = xf;
+			curr[j + 1] = xr;
+		}
+		float *t = prevf; prevf = curf; curf = t;
+		t = prevr; prevr = curr; curr = t;
+	}
+	free(prevf); free(prevr); free(curf); free(curr);
+	return bestf - bestr;
+}
+
+int orc_mu_gapless_int(const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB)
+{
+	int best = 0;
+	int *prev = (int *)calloc(LB + 1, sizeof(int)), *cur = (int *)calloc(LB + 1, sizeof(int));
+	for (uint32_t i = 0; i < LA; ++i) {
+		const signed char *row = rsk_tbl_mu_i8 + 36 * a[i];
+		cur[0] = 0;
+		for (uint32_t j = 0; j < LB; ++j) {
+			int x = (j == 0) ? 0 : prev[j];
+			if (x < 0) x = 0;
+			x += row[b[j]];
+			if (x > best) best = x;
+			cur[j + 1] = x;
+		}
+		int *t = prev; prev = cur; cur = t;
+	}
+	free(prev); free(cur);
+	return best;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Long-chain path
  * ------------------------------------------------------------------------------------------------ */

@@ -116,6 +116,12 @@ void orc_calc_evalue(const orc_params *p, const orc_chain *A, const orc_chain *B
  * ClearAlign -> (omega>0 && mu present: MuFilter :619) -> Align_NoAccel :929.  path: LA+LB+1 bytes. */
 void orc_align_pair(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path);
 
+/* ---- alternative gapless Mu pre-scores (not reachable from the reference CLI) ---- */
+/* swgaplessprofb.cpp:6-61 SWFastGaplessProfb: best gapless local run on ScoreMx_Mu, forward minus reversed-A */
+float orc_mu_gapless_profb(const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB);
+/* swfastpinopgapless.cpp:6-47 SWFastPinopGapless on IntScoreMx_Mu rows: best gapless local run, integer */
+int orc_mu_gapless_int(const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB);
+
 /* ---- long-chain path: Mu k-mer filter (MKF) + chaining + banded x-drop ---- */
 typedef struct orc_hsp { int loi, loj, len, score; } orc_hsp;
 

@@ -131,6 +131,7 @@ struct rsk_ctx {
 	DevBuf<uint32_t> blist, bslot, task_a, task_begin, task_cnt, pair_a, pair_b;
 	// Mu filter (K3) state
 	int *d_mu_mx = nullptr;                 // IntScoreMx_Mu widened to int32
+	float *d_mu_f32 = nullptr;              // ScoreMx_Mu
 	DevBuf<uint8_t> keep;
 	DevBuf<int2> mu_bnd;
 	DevBuf<uint32_t> c_blist, c_bslot, c_task_a, c_task_begin, c_task_cnt;  // compacted survivors
@@ -279,6 +280,7 @@ extern "C" int rsk_ctx_set_params(rsk_ctx *ctx, const rsk_params *params)
 	for (int k = 0; k < 36 * 36; ++k)
 		mx[k] = rsk_tbl_mu_i8[k];
 	CK(cudaMemcpyAsync(ctx->d_mu_mx, mx, sizeof(mx), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->d_mu_f32, rsk_tbl_mu_f32, sizeof(float) * 36 * 36, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	return RSK_OK;
 }
@@ -319,6 +321,7 @@ extern "C" int rsk_ctx_create(int device, const rsk_params *params, void *cuda_s
 	if (cudaMalloc((void **)&ctx->d_tables, sizeof(float) * RSK_TABLE_FLOATS) != cudaSuccess ||
 		cudaMalloc((void **)&ctx->d_pool_cursor, sizeof(unsigned long long)) != cudaSuccess ||
 		cudaMalloc((void **)&ctx->d_mu_mx, sizeof(int) * 36 * 36) != cudaSuccess ||
+		cudaMalloc((void **)&ctx->d_mu_f32, sizeof(float) * 36 * 36) != cudaSuccess ||
 		cudaMalloc((void **)&ctx->d_counters, sizeof(rsk_ctx::Counters)) != cudaSuccess) {
 		rsk_ctx_destroy(ctx);
 		return fail(RSK_ERR_NOMEM, "cudaMalloc failed in rsk_ctx_create");
@@ -360,6 +363,7 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->mk_a.release(); ctx->mk_b.release(); ctx->mk_slot.release(); ctx->mk_hash.release(); ctx->mk_hchain.release();
 	ctx->mk_off.release(); ctx->mk_ht.release(); ctx->mk_seed.release(); ctx->mk_x.release(); ctx->mk_scratch.release();
 	if (ctx->d_mu_mx) cudaFree(ctx->d_mu_mx);
+	if (ctx->d_mu_f32) cudaFree(ctx->d_mu_f32);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->d_tables) cudaFree(ctx->d_tables);
 	if (ctx->d_pool_cursor) cudaFree(ctx->d_pool_cursor);
@@ -1382,6 +1386,88 @@ extern "C" int rsk_search_self(rsk_ctx *ctx, const rsk_chainset *Sx, const rsk_s
 	if (rc)
 		return rc;
 	return search_impl(ctx, plan, opts, out, false);
+}
+
+extern "C" int rsk_mu_gapless_scores(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib, float *out_profb, int32_t *out_int)
+{
+	if (!ctx || !A || !B || (npairs && (!ia || !ib)))
+		return fail(RSK_ERR_ARG, "rsk_mu_gapless_scores: null argument");
+	if (!A->has_mu || !B->has_mu)
+		return fail(RSK_ERR_ARG, "rsk_mu_gapless_scores: both chain sets need Mu letters");
+	if (npairs == 0)
+		return RSK_OK;
+	if (npairs > 0xffffffffull)
+		return fail(RSK_ERR_LIMIT, "rsk_mu_gapless_scores: too many pairs");
+	for (uint64_t k = 0; k < npairs; ++k)
+		if (ia[k] >= A->d.n || ib[k] >= B->d.n)
+			return fail(RSK_ERR_ARG, "pair %llu: chain index out of range", (unsigned long long)k);
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	uint32_t *d_a = nullptr, *d_b = nullptr;
+	float *d_f = nullptr;
+	int *d_i = nullptr;
+	auto cleanup = [&]() { cudaFree(d_a); cudaFree(d_b); cudaFree(d_f); cudaFree(d_i); };
+	if (cudaMalloc((void **)&d_a, 4 * npairs) != cudaSuccess || cudaMalloc((void **)&d_b, 4 * npairs) != cudaSuccess ||
+		cudaMalloc((void **)&d_f, 4 * npairs) != cudaSuccess || cudaMalloc((void **)&d_i, 4 * npairs) != cudaSuccess) {
+		cudaGetLastError();
+		cleanup();
+		return fail(RSK_ERR_NOMEM, "rsk_mu_gapless_scores: device buffers");
+	}
+	cudaMemcpyAsync(d_a, ia, 4 * npairs, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(d_b, ib, 4 * npairs, cudaMemcpyHostToDevice, st);
+	GaplessArgs ga;
+	memset(&ga, 0, sizeof(ga));
+	ga.muA = A->d.mu; ga.offA = A->d.off; ga.lenA = A->d.len;
+	ga.muB = B->d.mu; ga.offB = B->d.off; ga.lenB = B->d.len;
+	ga.npairs = (uint32_t)npairs; ga.pair_a = d_a; ga.pair_b = d_b;
+	ga.mu_f32 = ctx->d_mu_f32; ga.mu_i32 = ctx->d_mu_mx;
+	ga.out_f = d_f; ga.out_i = d_i;
+	const int nl = launch_mu_gapless(ga, st);
+	cudaError_t e = nl < 0 ? cudaErrorLaunchFailure : cudaSuccess;
+	if (e == cudaSuccess && out_profb)
+		e = cudaMemcpyAsync(out_profb, d_f, 4 * npairs, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess && out_int)
+		e = cudaMemcpyAsync(out_int, d_i, 4 * npairs, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(st);
+	cleanup();
+	if (e != cudaSuccess)
+		return fail(RSK_ERR_CUDA, "rsk_mu_gapless_scores: %s", cudaGetErrorString(e));
+	ctx->stats.kernel_launches += nl;
+	return RSK_OK;
+}
+
+extern "C" int rsk_chainset_selfrev(rsk_ctx *ctx, rsk_chainset *S, const rsk_chainset *Srev, float *scores_out)
+{
+	if (!ctx || !S || !Srev)
+		return fail(RSK_ERR_ARG, "rsk_chainset_selfrev: null argument");
+	if (S->d.n != Srev->d.n)
+		return fail(RSK_ERR_ARG, "rsk_chainset_selfrev: %u chains but %u reversed chains", S->d.n, Srev->d.n);
+	for (uint32_t i = 0; i < S->d.n; ++i)
+		if (S->hlen[i] != Srev->hlen[i])
+			return fail(RSK_ERR_ARG, "rsk_chainset_selfrev: chain %u has length %u, its reverse %u", i, S->hlen[i], Srev->hlen[i]);
+	const uint32_t n = S->d.n;
+	std::vector<uint32_t> idx(n);
+	std::iota(idx.begin(), idx.end(), 0u);
+	rsk_search_opts o;
+	memset(&o, 0, sizeof(o));
+	o.keep = RSK_KEEP_ALL;
+	o.skip_evalue = 1;  // only m_AlnFwdScore is used (alignpair.cpp:24)
+	rsk_results *res = nullptr;
+	int rc = rsk_search_pairs(ctx, S, Srev, n, idx.data(), idx.data(), &o, &res);
+	if (rc)
+		return rc;
+	std::vector<float> sr(n);
+	for (uint32_t i = 0; i < n; ++i)
+		sr[i] = res->hits[i].score;
+	rsk_results_free(res);
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMemcpyAsync(S->d.selfrev, sr.data(), sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (scores_out)
+		memcpy(scores_out, sr.data(), sizeof(float) * n);
+	return RSK_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -194,6 +194,16 @@ struct MkfArgs {
 int launch_mkf(const MkfArgs &args, uint32_t nhash, cudaStream_t stream);
 size_t mkf_hash_bytes();
 
+// K5: gapless Mu pre-scores
+struct GaplessArgs {
+	const uint8_t *muA; const uint64_t *offA; const uint32_t *lenA;
+	const uint8_t *muB; const uint64_t *offB; const uint32_t *lenB;
+	uint32_t npairs; const uint32_t *pair_a, *pair_b;
+	const float *mu_f32; const int *mu_i32;
+	float *out_f; int *out_i;
+};
+int launch_mu_gapless(const GaplessArgs &args, cudaStream_t stream);
+
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();

@@ -104,6 +104,8 @@ def load_library():
     L.rsk_search_self.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
     L.rsk_search_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                    C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
+    L.rsk_mu_gapless_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rsk_chainset_selfrev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rsk_search_cross_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts)]
     for fn in (L.rsk_results_count, L.rsk_results_hits, L.rsk_results_paths, L.rsk_results_paths_bytes):
         fn.argtypes = [C.c_void_p]
@@ -293,6 +295,21 @@ class Context:
         _check(load_library().rsk_search_pairs(self.handle, A.handle, B.handle, len(ia), _ptr(ia), _ptr(ib),
                                                C.byref(o), C.byref(r)))
         return Results(r)
+
+    def selfrev(self, S, Srev):
+        """GetSelfRevScore for every chain of S (see rsk_chainset_selfrev); returns the float32 scores."""
+        out = np.zeros(S.n, np.float32)
+        _check(load_library().rsk_chainset_selfrev(self.handle, S.handle, Srev.handle, _ptr(out)))
+        return out
+
+    def mu_gapless_scores(self, A, B, ia, ib):
+        """(SWFastGaplessProfb float scores, SWFastPinopGapless int scores) for the listed pairs."""
+        ia = np.ascontiguousarray(ia, np.uint32)
+        ib = np.ascontiguousarray(ib, np.uint32)
+        f = np.zeros(len(ia), np.float32)
+        i = np.zeros(len(ia), np.int32)
+        _check(load_library().rsk_mu_gapless_scores(self.handle, A.handle, B.handle, len(ia), _ptr(ia), _ptr(ib), _ptr(f), _ptr(i)))
+        return f, i
 
     def stats(self):
         s = Stats()

@@ -203,3 +203,47 @@ def test_long_chain_path_matches_oracle(rb, port, mode):
     for f in ("score", "lo_a", "lo_b", "hi_a", "hi_b", "ts", "flags", "path_len", "mu_fwd", "mu_rev"):
         assert np.array_equal(res.hits[f], res2.hits[f]), f
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", [3, 2, 1])
+def test_selfrev_scores_match_reference(rb, mode):
+    """GetSelfRevScore (alignpair.cpp:7-25) under ProfileLoader parameters (omega = 0, profileloader.cpp:22-26):
+    chain vs its coordinate-reversed self (reference-made reversed profiles in the fixtures, forward Mu letters)."""
+    from tests.golden_util import GOLDEN, load_chains, load_pairs
+    from tests.util import bits
+    g = load_pairs(mode)
+    chains = load_chains()
+    d = np.load(GOLDEN / "golden_chains.npz")
+    params = rb.params_preset(mode)
+    params.omega = 0.0
+    ctx = rb.Context(0, params=params)
+    if mode == 3:
+        for c in chains:
+            c.mu = None
+    S = ctx.upload_chains(chains)
+    lens = np.array([c.L for c in chains], np.uint32)
+    mu = None if mode == 3 else np.concatenate([c.mu for c in chains])
+    xyz_rev = np.concatenate([c.xyz[:, ::-1] for c in chains], axis=1)
+    Srev = ctx.upload(lens, d["rev_prof"], mu, xyz_rev, None)
+    sr = ctx.selfrev(S, Srev)
+    assert np.array_equal(bits(sr), bits(g["selfrev"])), (sr, g["selfrev"])
+    ctx.close()
+
+
+def test_gapless_mu_prescores_match_oracle(rb, port):
+    from reseek_b200 import synth
+    from tests.util import bits
+    a = synth.make_chains(9, 120, seed=71, length_jitter=0.6)
+    b = synth.make_chains(14, 150, seed=72, length_jitter=0.6)
+    synth.plant_homologs(b, a, 0.5, seed=73, sub=0.2)
+    ctx = rb.Context(0, rb.MODE_SENSITIVE)
+    A = ctx.upload(a.lens, a.prof, a.mu, a.xyz, a.selfrev)
+    B = ctx.upload(b.lens, b.prof, b.mu, b.xyz, b.selfrev)
+    ia = np.repeat(np.arange(a.n, dtype=np.uint32), b.n)
+    ib = np.tile(np.arange(b.n, dtype=np.uint32), a.n)
+    f, i = ctx.mu_gapless_scores(A, B, ia, ib)
+    p = port(2)
+    for k in range(len(ia)):
+        of, oi = p.mu_gapless(a.chain(int(ia[k]))[1], b.chain(int(ib[k]))[1])
+        assert bits(f[k]) == bits(of) and int(i[k]) == oi, (k, f[k], of, i[k], oi)
+    ctx.close()

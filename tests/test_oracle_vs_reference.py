@@ -91,3 +91,19 @@ def test_mkf_xdrop_path_random_long_chains(port, built_lib, mode):
                 npath += 1
                 assert (r.lo_a, r.lo_b, r.hi_a, r.hi_b) == (rr.lo_a, rr.lo_b, rr.hi_a, rr.hi_b)
     assert nmkf == len(ca) * len(cb) and npath >= 5
+
+
+def test_gapless_variants_random(port):
+    """SWFastGaplessProfb / SWFastPinopGapless against the live reference functions."""
+    ref = Ref(2)
+    p = port(2)
+    rng = np.random.default_rng(11)
+    for t in range(200):
+        la, lb = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        a = rng.integers(0, 36, la).astype(np.uint8)
+        b = rng.integers(0, 36, lb).astype(np.uint8)
+        if t % 3 == 0:
+            n = min(la, lb)
+            b[:n] = a[:n]
+        x, y = p.mu_gapless(a, b), ref.mu_gapless(a, b)
+        assert bits(x[0]) == bits(y[0]) and x[1] == y[1], (la, lb, x, y)

@@ -58,7 +58,10 @@ def main():
     for i in longs:
         chains.append(ref.load_chain(i, loader_selfrev=True))
     print("chains:", [(c.label, c.L) for c in chains])
-    np.savez_compressed(OUT / "golden_chains.npz", **pack_chains(chains))
+    packed = pack_chains(chains)
+    # profiles of the coordinate-reversed chains (PDBChain::GetReverse + DSS): inputs of the self-reverse score (alignpair.cpp:7-25)
+    packed["rev_prof"] = np.concatenate([ref.rev_profile(c.seq, c.xyz) for c in chains], axis=1)
+    np.savez_compressed(OUT / "golden_chains.npz", **packed)
 
     nc = len(chains)
     for mode in (1, 2, 3):
