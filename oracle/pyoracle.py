@@ -192,6 +192,45 @@ class Port:
         return (float(np.float32(self.lib.orc_mu_gapless_profb(pa, len(a), pb, len(b)))),
                 int(self.lib.orc_mu_gapless_int(pa, len(a), pb, len(b))))
 
+    def prefilter(self, mu_queries, mu_targets, query_neighborhood=True, rsb_size=1500, swap_kl=True):
+        """MuPreFilter (muprefilter.cpp:64-133): returns {target index: [query indices]} as written to the
+        prefilter TSV (rankedscoresbag.cpp:185-232), plus the raw per-(target, query) diagonal scores."""
+        L = self.lib
+        L.orc_rsb_new.restype = C.c_void_p
+        L.orc_rsb_targets.restype = C.POINTER(C.c_uint32)
+        L.orc_rsb_scores.restype = C.POINTER(C.c_uint16)
+        qs = []
+        for m in mu_queries:
+            m = np.array(m, np.uint8)
+            if swap_kl:  # the query side goes through g_CharToLetterMu, which exchanges letters 10 and 11 (SURVEY a9)
+                k, l = m == 10, m == 11
+                m[k], m[l] = 11, 10
+            qs.append(np.ascontiguousarray(m))
+        nQ = len(qs)
+        qptr = (C.c_void_p * nQ)(*[q.ctypes.data for q in qs])
+        LQ = np.array([len(q) for q in qs], np.uint32)
+        rsb = C.c_void_p(L.orc_rsb_new(nQ, int(rsb_size)))
+        best = np.zeros(nQ, np.uint16)
+        raw = {}
+        for t, mt in enumerate(mu_targets):
+            mt = np.ascontiguousarray(mt, np.uint8)
+            if len(mt) == 0:
+                continue
+            L.orc_prefilter_target(qptr, LQ.ctypes.data_as(C.c_void_p), nQ, mt.ctypes.data_as(C.c_void_p), len(mt),
+                                   int(query_neighborhood), best.ctypes.data_as(C.c_void_p))
+            for q in np.nonzero(best)[0]:
+                raw[(t, int(q))] = int(best[q])
+                L.orc_rsb_add(rsb, int(q), t, int(best[q]))
+        L.orc_rsb_finish(rsb)
+        out = {}
+        for q in range(nQ):
+            n = L.orc_rsb_count(rsb, q)
+            tg = L.orc_rsb_targets(rsb, q)
+            for k in range(n):
+                out.setdefault(int(tg[k]), []).append(q)
+        L.orc_rsb_free(rsb)
+        return out, raw
+
     def lddt(self, A, B, posA, posB):
         posA = np.ascontiguousarray(posA, np.uint32)
         posB = np.ascontiguousarray(posB, np.uint32)

@@ -825,6 +825,177 @@ void orc_align_pair(const orc_params *p, const orc_chain *A, const orc_chain *B,
 		free(tmp);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * -fast -db prefilter
+ * ------------------------------------------------------------------------------------------------ */
+static const int k5_off[5] = {0, 1, 2, 5, 6};
+
+uint32_t orc_kmer5(const uint8_t *w)
+{
+	uint32_t k = 0;
+	int self = 0;
+	for (int c = 0; c < 5; ++c) {
+		const uint8_t x = w[k5_off[c]];
+		k = k * 36 + x;
+		self += rsk_tbl_mu_kmer_i8[36 * x + x];
+	}
+	return self < 36 ? UINT32_MAX : k;
+}
+
+int orc_kmer5_pair_score(uint32_t k1, uint32_t k2)
+{
+	int s = 0;
+	for (int c = 0; c < 5; ++c) {
+		s += rsk_tbl_mu_kmer_i8[36 * (k1 % 36) + (k2 % 36)];
+		k1 /= 36; k2 /= 36;
+	}
+	return s;
+}
+
+int orc_find_hsp(const uint8_t *q, uint32_t LQ, const uint8_t *t, uint32_t LT, int d)
+{
+	int i = (int)LQ - d - 1, j = 0;
+	if (i < 0) { j = -i; i = 0; }
+	int B = 0, F = 0;
+	for (; i < (int)LQ && j < (int)LT; ++i, ++j) {
+		F += rsk_tbl_mu_kmer_i8[36 * q[i] + t[j]];
+		if (F > B) B = F;
+		else if (F < 0) F = 0;
+	}
+	return B;
+}
+
+void orc_prefilter_target(const uint8_t *const *muQ, const uint32_t *LQ, uint32_t nQ, const uint8_t *muT, uint32_t LT,
+		int query_neighborhood, uint16_t *best)
+{
+	for (uint32_t q = 0; q < nQ; ++q)
+		best[q] = 0;
+	if (LT < 7)
+		return;
+	const uint32_t nkt = LT - 6;
+	uint32_t *kt = (uint32_t *)malloc(sizeof(uint32_t) * nkt);
+	for (uint32_t j = 0; j < nkt; ++j)
+		kt[j] = orc_kmer5(muT + j);
+	for (uint32_t q = 0; q < nQ; ++q) {
+		const uint32_t lq = LQ[q];
+		if (lq < 7)
+			continue;
+		const uint32_t nkq = lq - 6;
+		uint32_t *kq = (uint32_t *)malloc(sizeof(uint32_t) * nkq);
+		for (uint32_t i = 0; i < nkq; ++i)
+			kq[i] = orc_kmer5(muQ[q] + i);
+		int bestq = 0;
+		/* k-mer start positions (i, j) on diagonal d = lq + j - i - 1 */
+		for (int d = 0; d <= (int)(lq + LT) - 2 && d <= 16383; ++d) { /* diag > 0x3fff is dropped (prefiltermu.cpp:254) */
+			int i = (int)lq - d - 1, j = 0;
+			if (i < 0) { j = -i; i = 0; }
+			int seeds = 0;
+			for (; i < (int)nkq && j < (int)nkt; ++i, ++j) {
+				if (kq[i] == UINT32_MAX || kt[j] == UINT32_MAX)
+					continue;
+				if (orc_kmer5_pair_score(kq[i], kt[j]) >= 36)
+					seeds += (query_neighborhood && kq[i] == kt[j]) ? 2 : 1;
+			}
+			if (seeds >= 2) {
+				const int sc = orc_find_hsp(muQ[q], lq, muT, LT, d);
+				if (sc > bestq)
+					bestq = sc;
+			}
+		}
+		free(kq);
+		if (bestq >= 65535)
+			bestq = 65534;
+		best[q] = (uint16_t)bestq;
+	}
+	free(kt);
+}
+
+struct orc_rsb {
+	uint32_t nQ, B;
+	uint32_t *n, *cap;
+	uint32_t **t;
+	uint16_t **s;
+	uint16_t *lo;
+};
+
+orc_rsb *orc_rsb_new(uint32_t nQ, uint32_t B)
+{
+	orc_rsb *r = (orc_rsb *)calloc(1, sizeof(orc_rsb));
+	r->nQ = nQ; r->B = B;
+	r->n = (uint32_t *)calloc(nQ, sizeof(uint32_t));
+	r->cap = (uint32_t *)calloc(nQ, sizeof(uint32_t));
+	r->t = (uint32_t **)calloc(nQ, sizeof(uint32_t *));
+	r->s = (uint16_t **)calloc(nQ, sizeof(uint16_t *));
+	r->lo = (uint16_t *)calloc(nQ, sizeof(uint16_t));
+	return r;
+}
+
+/* sort.h:71-108: Hoare partition around the middle element, descending, on an index array */
+static void order_desc(const uint16_t *v, int left, int right, uint32_t *order)
+{
+	int i = left, j = right;
+	const uint16_t pivot = v[order[(left + right) / 2]];
+	while (i <= j) {
+		while (v[order[i]] > pivot) i++;
+		while (v[order[j]] < pivot) j--;
+		if (i <= j) {
+			const uint32_t tmp = order[i]; order[i] = order[j]; order[j] = tmp;
+			i++; j--;
+		}
+	}
+	if (left < j) order_desc(v, left, j, order);
+	if (i < right) order_desc(v, i, right, order);
+}
+
+static void rsb_truncate(orc_rsb *r, uint32_t q)
+{
+	const uint32_t n = r->n[q];
+	if (n < r->B)
+		return;
+	uint32_t *order = (uint32_t *)malloc(sizeof(uint32_t) * n);
+	for (uint32_t i = 0; i < n; ++i) order[i] = i;
+	order_desc(r->s[q], 0, (int)n - 1, order);
+	uint32_t *nt = (uint32_t *)malloc(sizeof(uint32_t) * r->cap[q]);
+	uint16_t *ns = (uint16_t *)malloc(sizeof(uint16_t) * r->cap[q]);
+	for (uint32_t k = 0; k < r->B; ++k) { nt[k] = r->t[q][order[k]]; ns[k] = r->s[q][order[k]]; }
+	free(r->t[q]); free(r->s[q]); free(order);
+	r->t[q] = nt; r->s[q] = ns;
+	r->n[q] = r->B;
+	r->lo[q] = ns[r->B - 1];
+}
+
+void orc_rsb_add(orc_rsb *r, uint32_t q, uint32_t t, uint16_t score)
+{
+	if (score < r->lo[q])
+		return;
+	if (r->n[q] == r->cap[q]) {
+		r->cap[q] = r->cap[q] ? 2 * r->cap[q] : 64;
+		r->t[q] = (uint32_t *)realloc(r->t[q], sizeof(uint32_t) * r->cap[q]);
+		r->s[q] = (uint16_t *)realloc(r->s[q], sizeof(uint16_t) * r->cap[q]);
+	}
+	r->t[q][r->n[q]] = t;
+	r->s[q][r->n[q]] = score;
+	r->n[q]++;
+	if (r->n[q] >= 2 * r->B)
+		rsb_truncate(r, q);
+}
+
+void orc_rsb_finish(orc_rsb *r)
+{
+	for (uint32_t q = 0; q < r->nQ; ++q)
+		rsb_truncate(r, q);
+}
+
+uint32_t orc_rsb_count(const orc_rsb *r, uint32_t q) { return r->n[q]; }
+const uint32_t *orc_rsb_targets(const orc_rsb *r, uint32_t q) { return r->t[q]; }
+const uint16_t *orc_rsb_scores(const orc_rsb *r, uint32_t q) { return r->s[q]; }
+
+void orc_rsb_free(orc_rsb *r)
+{
+	for (uint32_t q = 0; q < r->nQ; ++q) { free(r->t[q]); free(r->s[q]); }
+	free(r->n); free(r->cap); free(r->t); free(r->s); free(r->lo); free(r);
+}
+
 void orc_align_pairs(const orc_params *p, const orc_chain *chainsA, const orc_chain *chainsB,
 		const uint32_t *ia, const uint32_t *ib, size_t npairs, orc_result *out)
 {

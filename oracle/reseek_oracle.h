@@ -151,6 +151,31 @@ void orc_align_mkf(const orc_params *p, const orc_chain *A, const orc_chain *B, 
 /* dssaligner.cpp:715-732 DoMKF (k-mers exist iff the chain has >= 3 residues) */
 int orc_do_mkf(const orc_params *p, const orc_chain *A, const orc_chain *B);
 
+/* ---- -fast -db prefilter ---- */
+/* Spaced 5-mer over offsets {0,1,2,5,6} of a 7-window, base-36 big-endian (mudex.cpp:517-538); self score on
+ * Mu_S_ij_i8 (mermx.cpp:725); k-mers with self score < 36 are masked (UINT32_MAX). */
+uint32_t orc_kmer5(const uint8_t *window7);
+int orc_kmer5_pair_score(uint32_t k1, uint32_t k2);
+/* prefiltermu.cpp:12-48 FindHSP: best ungapped segment on a whole diagonal d = LQ + j - i - 1 (diag.h:22-25) */
+int orc_find_hsp(const uint8_t *q, uint32_t LQ, const uint8_t *t, uint32_t LT, int diag);
+/* PrefilterMu::Search for one target (prefiltermu.cpp:382-393), stated without the index: a seed is a pair of
+ * unmasked 5-mers scoring >= 36; in query-neighbourhood mode an exact seed counts twice (the k-mer is indexed as
+ * itself and as a member of its own neighbourhood, mudex.cpp:146-174); a (query, diagonal) with >= 2 seeds is
+ * extended with FindHSP; best[q] = max over its diagonals, clamped to 65534, 0 = no candidate.
+ * Query letters must already carry the K/L swap of the reference. */
+void orc_prefilter_target(const uint8_t *const *muQ, const uint32_t *LQ, uint32_t nQ, const uint8_t *muT, uint32_t LT,
+		int query_neighborhood, uint16_t *best);
+/* RankedScoresBag (rankedscoresbag.cpp:5-51): per query keep the top-B targets, lazy truncation at 2B with the
+ * reference's own quicksort (sort.h:71-108), admission score >= lo.  Feed scores in target order. */
+typedef struct orc_rsb orc_rsb;
+orc_rsb *orc_rsb_new(uint32_t nQ, uint32_t B);
+void orc_rsb_add(orc_rsb *r, uint32_t q, uint32_t t, uint16_t score);
+void orc_rsb_finish(orc_rsb *r); /* the final TruncateVecs of ToTsv (rankedscoresbag.cpp:190-194) */
+uint32_t orc_rsb_count(const orc_rsb *r, uint32_t q);
+const uint32_t *orc_rsb_targets(const orc_rsb *r, uint32_t q);
+const uint16_t *orc_rsb_scores(const orc_rsb *r, uint32_t q);
+void orc_rsb_free(orc_rsb *r);
+
 /* Batch helpers for the CPU baseline timing (scalar port, one thread). */
 void orc_align_pairs(const orc_params *p, const orc_chain *chainsA, const orc_chain *chainsB,
 		const uint32_t *ia, const uint32_t *ib, size_t npairs, orc_result *out);

@@ -83,3 +83,23 @@ def test_statsig_formulas(port):
     assert p.statsig(0.7)[2] == 1.0  # logE < -20
     pv, _, _ = p.statsig(0.05)
     assert pv == 10 ** (-80 * 0.05 - 0.58)
+
+
+def _prefilter_fixture():
+    g = np.load(GOLDEN / "golden_prefilter.npz")
+    qo = np.concatenate([[0], np.cumsum(g["q_len"])]).astype(np.int64)
+    to = np.concatenate([[0], np.cumsum(g["t_len"])]).astype(np.int64)
+    mq = [g["q_mu"][qo[i]:qo[i + 1]] for i in range(len(g["q_len"]))]
+    mt = [g["t_mu"][to[i]:to[i + 1]] for i in range(len(g["t_len"]))]
+    return g, mq, mt
+
+
+@pytest.mark.parametrize("name,kw", [("idxq", {}), ("idxt", {"query_neighborhood": False}), ("rsb5", {"rsb_size": 5})])
+def test_prefilter_matches_reference_candidate_lists(port, name, kw):
+    """MuPreFilter (5-mer index probe, two-hit diagonals, FindHSP, top-B bag) against the candidate TSV the reference
+    binary wrote for q10.bca vs q100.bca at -threads 1: query-neighbourhood, target-neighbourhood and a tiny bag."""
+    g, mq, mt = _prefilter_fixture()
+    got, _ = port(1).prefilter(mq, mt, **kw)
+    pairs = [(t, q) for t in sorted(got) for q in got[t]]
+    want = list(zip(g[f"{name}_t"].tolist(), g[f"{name}_q"].tolist()))
+    assert pairs == want and len(want) >= 50

@@ -115,6 +115,36 @@ def main():
         np.savez_compressed(OUT / f"golden_pairs_mode{mode}.npz", **out)
         print(f"mode {mode}: {nc * nc} pairs, with path {sum(1 for p in paths if p)}, mkf {int(np.sum(out['mkf']))}")
 
+    # -fast -db prefilter: the reference binary's own candidate TSV (search.cpp:87-89, -keeptmp) at -threads 1
+    import os, re, subprocess
+    from oracle.pyoracle import REF_BIN
+
+    def mus(fn):
+        n = ref.bca_open(fn)
+        out = []
+        for i in range(n):
+            label, seq, xyz = ref.bca_chain(i)
+            out.append(ref.dss(seq, xyz)[1])
+        return out
+    mq, mt = mus(TD / "q10.bca"), mus(TD / "q100.bca")
+    pf = {"q_len": np.array([len(m) for m in mq], np.uint32), "q_mu": np.concatenate(mq),
+          "t_len": np.array([len(m) for m in mt], np.uint32), "t_mu": np.concatenate(mt)}
+    for name, extra in (("idxq", []), ("idxt", ["-idxt"]), ("rsb5", ["-rsb_size", "5"])):
+        subprocess.run([str(REF_BIN), "-search", str(TD / "q10.bca"), "-db", str(TD / "q100.bca"), "-fast", "-keeptmp",
+                        "-threads", "1", "-output", "/tmp/_pf_hits.tsv", "-log", "/tmp/_pf.log"] + extra,
+                       capture_output=True, check=True)
+        fn = re.search(r"MuFilterTsvFN=(\S+)", open("/tmp/_pf.log").read()).group(1)
+        tg, qs = [], []
+        for ln in open(fn).read().splitlines()[1:]:
+            f = ln.split("\t")
+            for x in f[2:]:
+                tg.append(int(f[0])); qs.append(int(x))
+        os.remove(fn)
+        pf[f"{name}_t"] = np.array(tg, np.uint32)
+        pf[f"{name}_q"] = np.array(qs, np.uint32)
+        print("prefilter", name, len(tg), "candidate pairs")
+    np.savez_compressed(OUT / "golden_prefilter.npz", **pf)
+
     # raw parasail
     rng = np.random.default_rng(42)
     r = Ref(2)
