@@ -193,6 +193,43 @@ int rsk_search_cross_device(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chain
 int rsk_mu_gapless_scores(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
 		const uint32_t *ia, const uint32_t *ib, float *out_profb, int32_t *out_int);
 
+/* ---- `-search Q -db DB -fast`: 5-mer prefilter + post-filter (search.cpp:76-111) ----
+ * rsk_prefilter replaces MuPreFilter (muprefilter.cpp:64-133): query index MuDex::FromSeqDB incl. k-mer neighbourhoods
+ * (mudex.cpp:386-442, mermx.cpp:484-584), PrefilterMu::Search (prefiltermu.cpp:382-393: index probe, two-hit diagonals
+ * twohitdiag.cpp:47/389, FindHSP :12-48) and the per-query top-B bag RankedScoresBag (rankedscoresbag.cpp:34/5/185).
+ * Q = the `-search` chains (query index side), T = the `-db` chains streamed in order (target index = position in T,
+ * i.e. the reference at -threads 1).  Both sets need Mu letters.  The result is the content of the reference's
+ * temporary candidate TSV: targets ascending, and for each target its queries ascending. */
+typedef struct rsk_prefilter_opts {
+	int32_t index_mode;   /* 0: as the reference (<= 100 queries: neighbourhoods in the query index, else on the target
+	                         side; prefiltermu.cpp / mudex.cpp:146), 1: force -idxq, 2: force -idxt */
+	uint32_t rsb_size;    /* per-query bag size B (-rsb_size); 0 = 1500 (prefiltermuparams.h) */
+	int32_t no_kl_swap;   /* 0: exchange Mu letters 10 and 11 on the query side, as `-search -fast -db` does through
+	                         g_CharToLetterMu (muprefilter.cpp:88, alpha.cpp:3291); 1: use the letters as given */
+	int32_t reserved;
+} rsk_prefilter_opts;
+typedef struct rsk_prefilter_result rsk_prefilter_result;
+int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *opts,
+		rsk_prefilter_result **out);
+uint64_t rsk_prefilter_count(const rsk_prefilter_result *r);          /* candidate (target, query) pairs */
+const uint32_t *rsk_prefilter_targets(const rsk_prefilter_result *r); /* [count] */
+const uint32_t *rsk_prefilter_queries(const rsk_prefilter_result *r); /* [count] */
+const uint16_t *rsk_prefilter_scores(const rsk_prefilter_result *r);  /* [count] best two-hit diagonal score */
+uint64_t rsk_prefilter_raw_count(const rsk_prefilter_result *r);      /* (target, query) pairs with a two-hit diagonal, before the bag */
+void rsk_prefilter_free(rsk_prefilter_result *r);
+/* The candidate TSV itself (rankedscoresbag.cpp:219-232): "prefilter\t<#targets>\n" then "<t>\t<K>\t<q1>...\n".
+ * Returns the length written (excluding the NUL) or, when cap is too small, the length needed as a negative number - 1. */
+long long rsk_prefilter_to_tsv(const rsk_prefilter_result *r, char *out, size_t cap);
+
+/* PostMuFilter (postmufilter.cpp:211-301, scan loop :116-208) over a prefilter result: every candidate line is aligned
+ * with A = the query chain, B = the DB chain (AlignBags, chainbag.cpp:44-84) under the *sensitive* preset whatever the
+ * context's mode (search.cpp:106-108) and reported with Up = true (hit.a = query index, hit.b = target index). */
+int rsk_postfilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_result *cands,
+		const rsk_search_opts *opts, rsk_results **out);
+/* Both stages: what `reseek -search Q -db DB -fast` computes. */
+int rsk_search_fast_db(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *popts,
+		const rsk_search_opts *opts, rsk_results **out);
+
 /* ---- results ---- */
 uint64_t rsk_results_count(const rsk_results *r);
 const rsk_hit *rsk_results_hits(const rsk_results *r);  /* [count], host memory owned by r */

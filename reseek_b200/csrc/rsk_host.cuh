@@ -1,0 +1,138 @@
+// rsk_host.cuh - host-side objects shared by the API translation units (context, chain sets, grow-only buffers).
+#pragma once
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "rsk_internal.cuh"
+
+int rsk_fail(int code, const char *fmt, ...);
+#define fail rsk_fail
+
+#define CK(call)                                                                                     \
+	do {                                                                                             \
+		cudaError_t e_ = (call);                                                                     \
+		if (e_ != cudaSuccess)                                                                       \
+			return fail(RSK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+using namespace rsk;
+
+// ------------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------------
+struct rsk_chainset {
+	rsk_ctx *ctx = nullptr;  // identity only (never dereferenced by rsk_chainset_free: the context may be gone)
+	int device = 0;
+	DevChains d;
+	std::vector<uint32_t> hlen;
+	std::vector<uint64_t> hoff;
+	uint32_t maxlen = 0;
+	bool has_mu = false;
+};
+
+template <typename T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0;  // elements
+	int ensure(size_t n)
+	{
+		if (n <= cap)
+			return 0;
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 16;
+		if (cudaMalloc((void **)&p, want * sizeof(T)) != cudaSuccess) {
+			cudaGetLastError();
+			if (cudaMalloc((void **)&p, n * sizeof(T)) != cudaSuccess)
+				return -1;
+			want = n;
+		}
+		cap = want;
+		return 0;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+template <typename T>
+struct PinBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t n)
+	{
+		if (n <= cap)
+			return 0;
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 16;
+		if (cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess)
+			return -1;
+		cap = want;
+		return 0;
+	}
+	void release()
+	{
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct rsk_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	int num_sms = 0;
+	rsk_params params;
+	float *d_tables = nullptr;
+	unsigned long long *d_pool_cursor = nullptr;
+	cudaEvent_t ev[8] = {};
+	// grow-only scratch
+	DevBuf<uint4> trace;
+	DevBuf<float2> bnd;
+	DevBuf<uint8_t> stage;
+	DevBuf<PairRec> rec;
+	DevBuf<uint8_t> pool;
+	DevBuf<uint32_t> blist, bslot, task_a, task_begin, task_cnt, pair_a, pair_b;
+	// Mu filter (K3) state
+	int *d_mu_mx = nullptr;                 // IntScoreMx_Mu widened to int32
+	float *d_mu_f32 = nullptr;              // ScoreMx_Mu
+	DevBuf<uint8_t> keep;
+	DevBuf<int2> mu_bnd;
+	DevBuf<uint32_t> c_blist, c_bslot, c_task_a, c_task_begin, c_task_cnt;  // compacted survivors
+	size_t filt_explicit_pairs = 0; uint64_t filt_explicit_cells = 0; uint32_t filt_explicit_tasks = 0; bool batch_cross = true;
+	struct Counters { uint32_t task_count[4]; uint32_t sw_task_counter[4]; uint32_t sat_count, mu_task_counter; unsigned long long pair_count, cell_count; };
+	DevBuf<uint32_t> rowlist, colsort;
+	// long-chain path (K4)
+	DevBuf<uint32_t> mk_a, mk_b, mk_slot, mk_hash, mk_hchain;
+	DevBuf<unsigned long long> mk_off;
+	DevBuf<uint16_t> mk_ht;
+	DevBuf<MkfSeed> mk_seed;
+	DevBuf<MkfXdrop> mk_x;
+	DevBuf<unsigned char> mk_scratch;
+	Counters *d_counters = nullptr;
+	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU
+	PinBuf<uint8_t> h_pool[2];
+	int host_threads = 1;
+	rsk_stats stats;
+	bool batch_filtered = false;
+	size_t max_batch_pairs = 2u << 20;
+	size_t scratch_budget = (size_t)24 << 30;
+};
+

@@ -204,6 +204,39 @@ struct GaplessArgs {
 };
 int launch_mu_gapless(const GaplessArgs &args, cudaStream_t stream);
 
+// K6..K8: `-fast -db` 5-mer prefilter, see prefilter_kernel.cu
+struct PfArgs {
+	const int *kmer_mx;          // Mu_S_ij_i8 widened to int32 [36*36]
+	// query side (letters already K/L-swapped when the caller asks for it)
+	uint32_t nQ; uint32_t nqk;   // queries, total 5-mer slots (sum of max(L-6, 0))
+	const uint8_t *muQ; const uint64_t *offQ; const uint32_t *lenQ;
+	const uint32_t *qk_off;      // [nQ+1] first 5-mer slot of each query
+	uint32_t *qk_code, *qk_val;  // [nqk] code (0xffffffff = masked), value = query<<16 | position
+	uint32_t *nb_count; const unsigned long long *nb_off;  // [nqk] index entries contributed by each query 5-mer
+	uint32_t *ix_key, *ix_val;   // index entries (unsorted while filling; ix_val sorted by key when probing)
+	uint32_t exact_twice;        // query-neighbourhood mode: the k-mer itself is entered a second time
+	const uint32_t *row_start, *row_end;  // [36^5] dense row table over the sorted index
+	// target side
+	uint32_t t_begin;            // first target of the batch
+	const uint8_t *muT; const uint64_t *offT; const uint32_t *lenT;
+	unsigned long long *hit_count; const unsigned long long *hit_off;  // per target of the batch ([ntl], [ntl+1])
+	uint32_t *hit_key; const uint32_t *hit_sorted;
+	unsigned *best;              // [ntl * nQ] best two-hit diagonal score per (target, query), 0 = none
+	uint32_t *cand_count; const unsigned long long *cand_off;
+	uint32_t *cand_t, *cand_q; uint16_t *cand_s;
+};
+int pf_launch_swap_kl(const uint8_t *in, uint8_t *out, uint64_t n, cudaStream_t st);
+int pf_launch_query_kmers(const PfArgs &a, cudaStream_t st);
+int pf_launch_neighborhood(const PfArgs &a, bool fill, cudaStream_t st);
+int pf_launch_mark_rows(const uint32_t *key, unsigned long long n, uint32_t *row_start, uint32_t *row_end, cudaStream_t st);
+int pf_launch_probe(const PfArgs &a, uint32_t ntl, bool fill, cudaStream_t st);
+int pf_launch_extend(const PfArgs &a, uint32_t ntl, cudaStream_t st);
+int pf_launch_cands(const PfArgs &a, uint32_t ntl, bool write, cudaStream_t st);
+int pf_sort_pairs(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, unsigned long long n, void *tmp,
+		size_t &tmp_bytes, cudaStream_t st);
+int pf_segmented_sort(const uint32_t *kin, uint32_t *kout, unsigned long long n, uint32_t nseg, const unsigned long long *off,
+		void *tmp, size_t &tmp_bytes, cudaStream_t st);
+
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();

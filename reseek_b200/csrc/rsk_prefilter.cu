@@ -1,0 +1,390 @@
+// rsk_prefilter.cu - host side of the `-search Q -db DB -fast` pipeline (search.cpp:76-111):
+//   rsk_prefilter      = MuPreFilter (muprefilter.cpp:64-133): GPU index build / probe / two-hit extension (prefilter_kernel.cu)
+//                        + the per-query top-B bag RankedScoresBag (rankedscoresbag.cpp), which is order dependent and tiny
+//                        and therefore runs here on the host over the (target, query, score) triples the GPU produced.
+//   rsk_postfilter     = PostMuFilter's scan loop (postmufilter.cpp:116-208) as one explicit-pair batch of the SW path.
+//   rsk_search_fast_db = both.
+// No CPU fallback: the triples only ever come from the kernels.
+#include <algorithm>
+#include <map>
+#include <memory>
+
+#include "rsk_host.cuh"
+
+struct rsk_prefilter_result {
+	std::vector<uint32_t> t, q;
+	std::vector<uint16_t> s;
+	uint64_t raw = 0;
+	uint32_t ntargets = 0;
+};
+
+namespace {
+
+// ---- RankedScoresBag (rankedscoresbag.cpp:5-51): per query keep the top B targets; lazy truncation at 2B ----
+struct Bag {
+	std::vector<uint32_t> t;
+	std::vector<uint16_t> s;
+	uint16_t lo = 0;
+};
+
+// QuickSortOrderDesc (sort.h:71-108): Hoare partition around the middle element on an index array.  Not stable; ties at
+// the cut-off are resolved by exactly this recursion, so it is restated rather than replaced by std::sort.
+void order_desc(const uint16_t *v, int left, int right, uint32_t *order)
+{
+	int i = left, j = right;
+	const uint16_t pivot = v[order[(left + right) / 2]];
+	while (i <= j) {
+		while (v[order[i]] > pivot)
+			i++;
+		while (v[order[j]] < pivot)
+			j--;
+		if (i <= j) {
+			std::swap(order[i], order[j]);
+			i++;
+			j--;
+		}
+	}
+	if (left < j)
+		order_desc(v, left, j, order);
+	if (i < right)
+		order_desc(v, i, right, order);
+}
+
+void bag_truncate(Bag &b, uint32_t B)  // TruncateVecs
+{
+	const uint32_t n = (uint32_t)b.s.size();
+	if (n < B)
+		return;
+	std::vector<uint32_t> order(n);
+	for (uint32_t i = 0; i < n; ++i)
+		order[i] = i;
+	order_desc(b.s.data(), 0, (int)n - 1, order.data());
+	std::vector<uint32_t> nt(B);
+	std::vector<uint16_t> ns(B);
+	for (uint32_t k = 0; k < B; ++k) {
+		nt[k] = b.t[order[k]];
+		ns[k] = b.s[order[k]];
+	}
+	b.t.swap(nt);
+	b.s.swap(ns);
+	b.lo = b.s[B - 1];
+}
+
+void bag_add(Bag &b, uint32_t B, uint32_t t, uint16_t score)  // AddScore
+{
+	if (score < b.lo)
+		return;
+	b.s.push_back(score);
+	b.t.push_back(t);
+	if (b.s.size() >= (size_t)2 * B)
+		bag_truncate(b, B);
+}
+
+struct PfScratch {
+	DevBuf<uint8_t> muq, tmp;
+	DevBuf<uint32_t> qk_off, qk_code, qk_val, nb_count, key_a, key_b, val_a, val_b, row_start, row_end;
+	DevBuf<unsigned long long> nb_off, hit_count, hit_off, cand_off;
+	DevBuf<uint32_t> hit_key, hit_sorted, cand_count, cand_t, cand_q;
+	DevBuf<unsigned> best;
+	DevBuf<uint16_t> cand_s;
+	int *kmer_mx = nullptr;
+	~PfScratch()
+	{
+		muq.release(); tmp.release(); qk_off.release(); qk_code.release(); qk_val.release(); nb_count.release();
+		key_a.release(); key_b.release(); val_a.release(); val_b.release(); row_start.release(); row_end.release();
+		nb_off.release(); hit_count.release(); hit_off.release(); cand_off.release(); hit_key.release();
+		hit_sorted.release(); cand_count.release(); cand_t.release(); cand_q.release(); best.release(); cand_s.release();
+		if (kmer_mx)
+			cudaFree(kmer_mx);
+	}
+};
+
+constexpr uint32_t kDict = 36u * 36 * 36 * 36 * 36;  // DICT_SIZE (prefiltermuparams.h)
+
+#define PFL(call)                                                                 \
+	do {                                                                          \
+		const int n_ = (call);                                                    \
+		if (n_ < 0)                                                               \
+			return fail(RSK_ERR_CUDA, "%s: launch failed: %s", #call, cudaGetErrorString(cudaGetLastError())); \
+		launches += (uint64_t)n_;                                                 \
+	} while (0)
+#define NOMEM(x)                                                                  \
+	do {                                                                          \
+		if ((x) != 0)                                                             \
+			return fail(RSK_ERR_NOMEM, "rsk_prefilter: out of device memory (%s)", #x); \
+	} while (0)
+
+}  // namespace
+
+extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *opts_in,
+		rsk_prefilter_result **out)
+{
+	if (!ctx || !Q || !T || !out)
+		return fail(RSK_ERR_ARG, "rsk_prefilter: null argument");
+	*out = nullptr;
+	if (Q->ctx != ctx || T->ctx != ctx)
+		return fail(RSK_ERR_ARG, "rsk_prefilter: chain sets belong to a different context");
+	if (!Q->has_mu || !T->has_mu)
+		return fail(RSK_ERR_ARG, "rsk_prefilter: both chain sets need Mu letters");
+	rsk_prefilter_opts o = {};
+	if (opts_in)
+		o = *opts_in;
+	const uint32_t B = o.rsb_size ? o.rsb_size : 1500u;
+	const uint32_t nQ = Q->d.n, nT = T->d.n;
+	if (nQ >= (1u << 16))
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter: at most 65535 queries per call (got %u); split the query set", nQ);
+	if (Q->maxlen > 0xffffu)
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter: query chains are limited to 65535 residues (uint16 position, mudex.h:19-49)");
+	// <= 100 queries: neighbourhoods go into the query index and exact k-mers are therefore entered twice (mudex.cpp:146-174)
+	const bool qhood = o.index_mode == 1 || (o.index_mode == 0 && nQ <= 100);
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	uint64_t launches = 0;
+	auto *res = new rsk_prefilter_result();
+	std::unique_ptr<rsk_prefilter_result> guard(res);
+	if (nQ == 0 || nT == 0) {
+		*out = guard.release();
+		return RSK_OK;
+	}
+	PfScratch S;
+	PfArgs a = {};
+	{
+		std::vector<int> mx(36 * 36);
+		const int8_t *m8 = rsk_mu_kmer_matrix_i8();
+		for (int k = 0; k < 36 * 36; ++k)
+			mx[k] = m8[k];
+		CK(cudaMalloc((void **)&S.kmer_mx, sizeof(int) * 36 * 36));
+		CK(cudaMemcpyAsync(S.kmer_mx, mx.data(), sizeof(int) * 36 * 36, cudaMemcpyHostToDevice, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	a.kmer_mx = S.kmer_mx;
+	a.nQ = nQ;
+	a.offQ = Q->d.off; a.lenQ = Q->d.len;
+	a.muT = T->d.mu; a.offT = T->d.off; a.lenT = T->d.len;
+	a.exact_twice = qhood ? 1u : 0u;
+	// query letters, K/L exchanged unless told otherwise
+	if (!o.no_kl_swap) {
+		NOMEM(S.muq.ensure(Q->d.total));
+		PFL(pf_launch_swap_kl(Q->d.mu, S.muq.p, Q->d.total, st));
+		a.muQ = S.muq.p;
+	} else {
+		a.muQ = Q->d.mu;
+	}
+	// ---- K6: query index ----
+	std::vector<uint32_t> qk_off(nQ + 1, 0);
+	for (uint32_t q = 0; q < nQ; ++q)
+		qk_off[q + 1] = qk_off[q] + (Q->hlen[q] >= 7 ? Q->hlen[q] - 6 : 0);
+	const uint32_t nqk = qk_off[nQ];
+	a.nqk = nqk;
+	unsigned long long nindex = 0;
+	NOMEM(S.row_start.ensure(kDict));
+	NOMEM(S.row_end.ensure(kDict));
+	CK(cudaMemsetAsync(S.row_start.p, 0, sizeof(uint32_t) * kDict, st));
+	CK(cudaMemsetAsync(S.row_end.p, 0, sizeof(uint32_t) * kDict, st));
+	if (nqk) {
+		NOMEM(S.qk_off.ensure(nQ + 1));
+		NOMEM(S.qk_code.ensure(nqk));
+		NOMEM(S.qk_val.ensure(nqk));
+		NOMEM(S.nb_count.ensure(nqk));
+		NOMEM(S.nb_off.ensure(nqk + 1));
+		CK(cudaMemcpyAsync(S.qk_off.p, qk_off.data(), sizeof(uint32_t) * (nQ + 1), cudaMemcpyHostToDevice, st));
+		a.qk_off = S.qk_off.p; a.qk_code = S.qk_code.p; a.qk_val = S.qk_val.p; a.nb_count = S.nb_count.p; a.nb_off = S.nb_off.p;
+		PFL(pf_launch_query_kmers(a, st));
+		PFL(pf_launch_neighborhood(a, false, st));
+		// sizes -> offsets (host scan: nqk is the query residue count, small)
+		std::vector<uint32_t> cnt(nqk);
+		CK(cudaMemcpyAsync(cnt.data(), S.nb_count.p, sizeof(uint32_t) * nqk, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		std::vector<unsigned long long> off(nqk + 1, 0);
+		for (uint32_t i = 0; i < nqk; ++i)
+			off[i + 1] = off[i] + cnt[i];
+		nindex = off[nqk];
+		if (nindex >= 0xffffffffull)
+			return fail(RSK_ERR_LIMIT, "rsk_prefilter: query index of %llu entries exceeds 2^32; split the query set", nindex);
+		CK(cudaMemcpyAsync(S.nb_off.p, off.data(), sizeof(unsigned long long) * (nqk + 1), cudaMemcpyHostToDevice, st));
+		if (nindex) {
+			NOMEM(S.key_a.ensure(nindex));
+			NOMEM(S.key_b.ensure(nindex));
+			NOMEM(S.val_a.ensure(nindex));
+			NOMEM(S.val_b.ensure(nindex));
+			a.ix_key = S.key_a.p; a.ix_val = S.val_a.p;
+			PFL(pf_launch_neighborhood(a, true, st));
+			size_t tb = 0;
+			if (pf_sort_pairs(S.key_a.p, S.key_b.p, S.val_a.p, S.val_b.p, nindex, nullptr, tb, st))
+				return fail(RSK_ERR_CUDA, "rsk_prefilter: cub sort sizing failed");
+			NOMEM(S.tmp.ensure(tb));
+			if (pf_sort_pairs(S.key_a.p, S.key_b.p, S.val_a.p, S.val_b.p, nindex, S.tmp.p, tb, st))
+				return fail(RSK_ERR_CUDA, "rsk_prefilter: cub sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+			launches += 4;
+			PFL(pf_launch_mark_rows(S.key_b.p, nindex, S.row_start.p, S.row_end.p, st));
+			a.ix_key = S.key_b.p; a.ix_val = S.val_b.p;
+		}
+	}
+	a.row_start = S.row_start.p; a.row_end = S.row_end.p;
+
+	// ---- K7 count pass over all targets, then batches sized by hits ----
+	std::vector<Bag> bags(nQ);
+	std::vector<unsigned long long> hcnt(nT, 0);
+	if (nindex) {
+		NOMEM(S.hit_count.ensure(nT));
+		a.t_begin = 0;
+		a.hit_count = S.hit_count.p;
+		PFL(pf_launch_probe(a, nT, false, st));
+		CK(cudaMemcpyAsync(hcnt.data(), S.hit_count.p, sizeof(unsigned long long) * nT, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	const unsigned long long kMaxHits = 1ull << 28;              // 1 GB of keys + 1 GB sorted per batch
+	const uint32_t kMaxT = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(1u << 16, ((uint64_t)1 << 26) / nQ));
+	std::vector<unsigned long long> hoff, coff;
+	std::vector<uint32_t> ccnt, ct, cq;
+	std::vector<uint16_t> cs;
+	for (uint32_t t0 = 0; nindex && t0 < nT;) {
+		uint32_t t1 = t0;
+		unsigned long long tot = 0;
+		while (t1 < nT && t1 - t0 < kMaxT && (t1 == t0 || tot + hcnt[t1] <= kMaxHits))
+			tot += hcnt[t1++];
+		const uint32_t ntl = t1 - t0;
+		if (tot >= (1ull << 32))
+			return fail(RSK_ERR_LIMIT, "rsk_prefilter: target %u alone produces %llu index hits", t0, tot);
+		if (tot == 0) {  // nothing to extend in this batch
+			t0 = t1;
+			continue;
+		}
+		hoff.assign(ntl + 1, 0);
+		for (uint32_t k = 0; k < ntl; ++k)
+			hoff[k + 1] = hoff[k] + hcnt[t0 + k];
+		NOMEM(S.hit_off.ensure(ntl + 1));
+		NOMEM(S.hit_key.ensure(tot));
+		NOMEM(S.hit_sorted.ensure(tot));
+		NOMEM(S.best.ensure((size_t)ntl * nQ));
+		NOMEM(S.cand_count.ensure(ntl));
+		NOMEM(S.cand_off.ensure(ntl + 1));
+		CK(cudaMemcpyAsync(S.hit_off.p, hoff.data(), sizeof(unsigned long long) * (ntl + 1), cudaMemcpyHostToDevice, st));
+		CK(cudaMemsetAsync(S.best.p, 0, sizeof(unsigned) * (size_t)ntl * nQ, st));
+		a.t_begin = t0;
+		a.hit_off = S.hit_off.p; a.hit_key = S.hit_key.p; a.hit_sorted = S.hit_sorted.p; a.best = S.best.p;
+		a.cand_count = S.cand_count.p; a.cand_off = S.cand_off.p;
+		PFL(pf_launch_probe(a, ntl, true, st));
+		size_t tb = 0;
+		if (pf_segmented_sort(S.hit_key.p, S.hit_sorted.p, tot, ntl, S.hit_off.p, nullptr, tb, st))
+			return fail(RSK_ERR_CUDA, "rsk_prefilter: cub segmented sort sizing failed");
+		NOMEM(S.tmp.ensure(tb));
+		if (pf_segmented_sort(S.hit_key.p, S.hit_sorted.p, tot, ntl, S.hit_off.p, S.tmp.p, tb, st))
+			return fail(RSK_ERR_CUDA, "rsk_prefilter: cub segmented sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+		launches += 3;
+		PFL(pf_launch_extend(a, ntl, st));
+		PFL(pf_launch_cands(a, ntl, false, st));
+		ccnt.resize(ntl);
+		CK(cudaMemcpyAsync(ccnt.data(), S.cand_count.p, sizeof(uint32_t) * ntl, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		coff.assign(ntl + 1, 0);
+		for (uint32_t k = 0; k < ntl; ++k)
+			coff[k + 1] = coff[k] + ccnt[k];
+		const unsigned long long nc = coff[ntl];
+		if (nc) {
+			NOMEM(S.cand_t.ensure(nc));
+			NOMEM(S.cand_q.ensure(nc));
+			NOMEM(S.cand_s.ensure(nc));
+			CK(cudaMemcpyAsync(S.cand_off.p, coff.data(), sizeof(unsigned long long) * (ntl + 1), cudaMemcpyHostToDevice, st));
+			a.cand_t = S.cand_t.p; a.cand_q = S.cand_q.p; a.cand_s = S.cand_s.p;
+			PFL(pf_launch_cands(a, ntl, true, st));
+			ct.resize(nc); cq.resize(nc); cs.resize(nc);
+			CK(cudaMemcpyAsync(ct.data(), S.cand_t.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(cq.data(), S.cand_q.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(cs.data(), S.cand_s.p, sizeof(uint16_t) * nc, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			// stream order of the reference at -threads 1: targets ascending (AddTwoHitDiag -> AddScore, prefiltermu.cpp:288-313)
+			for (unsigned long long k = 0; k < nc; ++k)
+				bag_add(bags[cq[k]], B, ct[k], cs[k]);
+			res->raw += nc;
+		}
+		t0 = t1;
+	}
+	// ---- RankedScoresBag::ToTsv (rankedscoresbag.cpp:185-232): final truncation, then target -> queries (ascending) ----
+	std::map<uint32_t, std::vector<std::pair<uint32_t, uint16_t>>> inv;
+	for (uint32_t q = 0; q < nQ; ++q) {
+		bag_truncate(bags[q], B);
+		for (size_t k = 0; k < bags[q].t.size(); ++k)
+			inv[bags[q].t[k]].emplace_back(q, bags[q].s[k]);
+	}
+	for (auto &kv : inv) {
+		for (auto &e : kv.second) {
+			res->t.push_back(kv.first);
+			res->q.push_back(e.first);
+			res->s.push_back(e.second);
+		}
+	}
+	res->ntargets = (uint32_t)inv.size();
+	ctx->stats.kernel_launches += launches;
+	*out = guard.release();
+	return RSK_OK;
+}
+
+extern "C" uint64_t rsk_prefilter_count(const rsk_prefilter_result *r) { return r ? r->t.size() : 0; }
+extern "C" const uint32_t *rsk_prefilter_targets(const rsk_prefilter_result *r) { return (r && !r->t.empty()) ? r->t.data() : nullptr; }
+extern "C" const uint32_t *rsk_prefilter_queries(const rsk_prefilter_result *r) { return (r && !r->q.empty()) ? r->q.data() : nullptr; }
+extern "C" const uint16_t *rsk_prefilter_scores(const rsk_prefilter_result *r) { return (r && !r->s.empty()) ? r->s.data() : nullptr; }
+extern "C" uint64_t rsk_prefilter_raw_count(const rsk_prefilter_result *r) { return r ? r->raw : 0; }
+extern "C" void rsk_prefilter_free(rsk_prefilter_result *r) { delete r; }
+
+extern "C" long long rsk_prefilter_to_tsv(const rsk_prefilter_result *r, char *out, size_t cap)
+{
+	if (!r)
+		return RSK_ERR_ARG;
+	std::string s = "prefilter\t" + std::to_string(r->ntargets) + "\n";
+	for (size_t k = 0; k < r->t.size();) {
+		size_t e = k;
+		while (e < r->t.size() && r->t[e] == r->t[k])
+			++e;
+		s += std::to_string(r->t[k]) + "\t" + std::to_string(e - k);
+		for (size_t i = k; i < e; ++i)
+			s += "\t" + std::to_string(r->q[i]);
+		s += "\n";
+		k = e;
+	}
+	if (!out || cap < s.size() + 1)
+		return -(long long)s.size() - 1;
+	memcpy(out, s.c_str(), s.size() + 1);
+	return (long long)s.size();
+}
+
+extern "C" int rsk_postfilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_result *cands,
+		const rsk_search_opts *opts, rsk_results **out)
+{
+	if (!ctx || !Q || !T || !cands || !out)
+		return fail(RSK_ERR_ARG, "rsk_postfilter: null argument");
+	// DM_AlwaysSensitive (search.cpp:106-108); everything the caller customised (tables, weights, gaps) is kept
+	const rsk_params saved = ctx->params;
+	rsk_params sens;
+	int rc = rsk_params_preset(&sens, RSK_MODE_SENSITIVE);
+	if (rc)
+		return rc;
+	rsk_params p = saved;
+	p.omega = sens.omega; p.omega_fwd = sens.omega_fwd; p.mkfl = sens.mkfl; p.min_fwd_score = sens.min_fwd_score;
+	p.mkf_x1 = sens.mkf_x1; p.mkf_x2 = sens.mkf_x2; p.mkf_min_hsp_score = sens.mkf_min_hsp_score;
+	p.mkf_min_mega_hsp_score = sens.mkf_min_mega_hsp_score; p.max_evalue = sens.max_evalue;
+	rc = rsk_ctx_set_params(ctx, &p);
+	if (rc)
+		return rc;
+	// A = query bag, B = DB chain (postmufilter.cpp:190-194); line order of the TSV
+	rc = rsk_search_pairs(ctx, Q, T, cands->q.size(), cands->q.data(), cands->t.data(), opts, out);
+	const int rc2 = rsk_ctx_set_params(ctx, &saved);
+	return rc ? rc : rc2;
+}
+
+extern "C" int rsk_search_fast_db(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *popts,
+		const rsk_search_opts *opts, rsk_results **out)
+{
+	if (!out)
+		return fail(RSK_ERR_ARG, "rsk_search_fast_db: null argument");
+	*out = nullptr;
+	rsk_prefilter_result *pf = nullptr;
+	int rc = rsk_prefilter(ctx, Q, T, popts, &pf);
+	if (rc)
+		return rc;
+	const uint64_t launches = ctx->stats.kernel_launches;
+	rc = rsk_postfilter(ctx, Q, T, pf, opts, out);
+	ctx->stats.kernel_launches += launches;  // the search call restarts the counters; keep the prefilter's launches in the sum
+	rsk_prefilter_free(pf);
+	return rc;
+}

@@ -42,6 +42,10 @@ class SearchOpts(C.Structure):
     _fields_ = [("keep", C.c_int32), ("want_paths", C.c_int32), ("skip_evalue", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PrefilterOpts(C.Structure):
+    _fields_ = [("index_mode", C.c_int32), ("rsb_size", C.c_uint32), ("no_kl_swap", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("mu_filter_in", C.c_uint64), ("mu_filter_rejected", C.c_uint64),
                 ("mu_saturated", C.c_uint64), ("sw_pairs", C.c_uint64), ("sw_cells", C.c_uint64),
@@ -113,6 +117,20 @@ def load_library():
     L.rsk_path_to_cigar.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]
     L.rsk_results_free.argtypes = [C.c_void_p]
     L.rsk_results_free.restype = None
+    L.rsk_prefilter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrefilterOpts), C.POINTER(C.c_void_p)]
+    for fn in (L.rsk_prefilter_count, L.rsk_prefilter_raw_count):
+        fn.argtypes = [C.c_void_p]
+        fn.restype = C.c_uint64
+    for fn in (L.rsk_prefilter_targets, L.rsk_prefilter_queries, L.rsk_prefilter_scores):
+        fn.argtypes = [C.c_void_p]
+        fn.restype = C.c_void_p
+    L.rsk_prefilter_free.argtypes = [C.c_void_p]
+    L.rsk_prefilter_free.restype = None
+    L.rsk_prefilter_to_tsv.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.rsk_prefilter_to_tsv.restype = C.c_longlong
+    L.rsk_postfilter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
+    L.rsk_search_fast_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrefilterOpts), C.POINTER(SearchOpts),
+                                     C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -202,6 +220,54 @@ class Results:
 
     def __len__(self):
         return len(self.hits)
+
+
+class PrefilterResult:
+    """Candidate (target, query, score) lists of rsk_prefilter, in the order of the reference's candidate TSV."""
+
+    def __init__(self, handle):
+        L = load_library()
+        self._handle = handle
+        n = L.rsk_prefilter_count(handle)
+        self.raw_count = int(L.rsk_prefilter_raw_count(handle))
+
+        def view(fn, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(fn(handle))
+            return np.frombuffer(buf, dtype=dt, count=n).copy()
+        self.targets = view(L.rsk_prefilter_targets, np.uint32)
+        self.queries = view(L.rsk_prefilter_queries, np.uint32)
+        self.scores = view(L.rsk_prefilter_scores, np.uint16)
+
+    def tsv(self):
+        L = load_library()
+        need = -L.rsk_prefilter_to_tsv(self._handle, None, 0)
+        buf = C.create_string_buffer(int(need))
+        n = L.rsk_prefilter_to_tsv(self._handle, buf, int(need))
+        if n < 0:
+            raise ReseekB200Error("rsk_prefilter_to_tsv failed")
+        return buf.value.decode()
+
+    def as_dict(self):
+        out = {}
+        for t, q in zip(self.targets.tolist(), self.queries.tolist()):
+            out.setdefault(t, []).append(q)
+        return out
+
+    def close(self):
+        if self._handle:
+            load_library().rsk_prefilter_free(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return len(self.targets)
 
 
 class ChainSet:
@@ -294,6 +360,27 @@ class Context:
         r = C.c_void_p()
         _check(load_library().rsk_search_pairs(self.handle, A.handle, B.handle, len(ia), _ptr(ia), _ptr(ib),
                                                C.byref(o), C.byref(r)))
+        return Results(r)
+
+    def prefilter(self, Q, T, index_mode=0, rsb_size=0, kl_swap=True):
+        """MuPreFilter (muprefilter.cpp:64-133) on the GPU; Q = -search chains, T = -db chains."""
+        o = PrefilterOpts(int(index_mode), int(rsb_size), int(not kl_swap), 0)
+        r = C.c_void_p()
+        _check(load_library().rsk_prefilter(self.handle, Q.handle, T.handle, C.byref(o), C.byref(r)))
+        return PrefilterResult(r)
+
+    def postfilter(self, Q, T, cands, keep=KEEP_HITS, want_paths=True):
+        o = self._opts(keep, want_paths, False)
+        r = C.c_void_p()
+        _check(load_library().rsk_postfilter(self.handle, Q.handle, T.handle, cands._handle, C.byref(o), C.byref(r)))
+        return Results(r)
+
+    def search_fast_db(self, Q, T, index_mode=0, rsb_size=0, kl_swap=True, keep=KEEP_HITS, want_paths=True):
+        """`reseek -search Q -db T -fast` (search.cpp:76-111): prefilter + post-filter; hit.a = query, hit.b = target."""
+        po = PrefilterOpts(int(index_mode), int(rsb_size), int(not kl_swap), 0)
+        o = self._opts(keep, want_paths, False)
+        r = C.c_void_p()
+        _check(load_library().rsk_search_fast_db(self.handle, Q.handle, T.handle, C.byref(po), C.byref(o), C.byref(r)))
         return Results(r)
 
     def selfrev(self, S, Srev):
