@@ -232,7 +232,7 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 		return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->trace.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
+	ctx->ckpt.release(); ctx->tile.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
 	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();
 	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
 	ctx->h_rec[0].release(); ctx->h_rec[1].release(); ctx->h_pool[0].release(); ctx->h_pool[1].release();
@@ -398,22 +398,23 @@ struct SearchPlan {
 	uint64_t npairs = 0;
 };
 
-int ensure_scratch(rsk_ctx *ctx, uint32_t maxRow, uint32_t maxCol, int &grid, uint64_t &trace_stride, uint32_t &bnd_stride,
-		uint32_t &stage_stride)
+int ensure_scratch(rsk_ctx *ctx, uint32_t maxRow, uint32_t maxCol, int &grid, uint64_t &ckpt_stride, uint64_t &bnd_stride,
+		uint32_t &bnd_pass_stride, uint32_t &stage_stride)
 {
 	int npass, R;
 	sw_geometry(maxRow, npass, R);
 	// every pair of the batch has npass(rows) <= npass(maxRow) and columns <= maxCol
-	trace_stride = sw_trace_units(npass, maxCol);  // uint4 units
-	bnd_stride = ((maxCol + 3) & ~3u) + 4;
+	ckpt_stride = sw_ckpt_units(npass, maxCol);  // float4 units
+	bnd_pass_stride = ((maxCol + 3) & ~3u) + 4;
+	bnd_stride = (uint64_t)bnd_pass_stride * (uint64_t)npass;
 	stage_stride = ((maxRow + maxCol + 16) + 15) & ~15u;
-	const uint64_t per_cta = (trace_stride * 16 + (uint64_t)bnd_stride * 8 + stage_stride) * kSwMaxWarps;
+	const uint64_t per_cta = (ckpt_stride * 16 + bnd_stride * 8 + stage_stride + kSwStripSteps * 32 * 8) * kSwMaxWarps;
 	grid = ctx->num_sms;
 	if (per_cta * (uint64_t)grid > ctx->scratch_budget)
 		grid = (int)std::max<uint64_t>(1, ctx->scratch_budget / per_cta);
 	const size_t warps = (size_t)grid * kSwMaxWarps;
-	if (ctx->trace.ensure(trace_stride * warps) || ctx->bnd.ensure((size_t)bnd_stride * warps) ||
-		ctx->stage.ensure((size_t)stage_stride * warps)) {
+	if (ctx->ckpt.ensure(ckpt_stride * warps) || ctx->bnd.ensure((size_t)bnd_stride * warps) ||
+		ctx->tile.ensure((size_t)kSwStripSteps * 32 * warps) || ctx->stage.ensure((size_t)stage_stride * warps)) {
 		cudaGetLastError();
 		return fail(RSK_ERR_NOMEM, "SW scratch allocation failed (rows=%u cols=%u)", maxRow, maxCol);
 	}
@@ -554,9 +555,9 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	const rsk_chainset *Rw = tr ? B : A, *Cl = tr ? A : B;
 	const uint32_t maxRow = tr ? b.maxLB : b.maxLA, maxCol = tr ? b.maxLA : b.maxLB;
 	int grid;
-	uint64_t trace_stride;
-	uint32_t bnd_stride, stage_stride;
-	int rc = ensure_scratch(ctx, maxRow, maxCol, grid, trace_stride, bnd_stride, stage_stride);
+	uint64_t ckpt_stride, bnd_stride;
+	uint32_t bnd_pass_stride, stage_stride;
+	int rc = ensure_scratch(ctx, maxRow, maxCol, grid, ckpt_stride, bnd_stride, bnd_pass_stride, stage_stride);
 	if (rc)
 		return rc;
 	if ((rc = ensure_coloff(ctx, Cl)))
@@ -573,7 +574,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 
 	// ---- row lists per kernel class and the column list (cross mode) ----
 	std::vector<uint32_t> rowlist;            // rows grouped by class
-	uint32_t row_off[kSwClasses + 1] = {0, 0, 0, 0};
+	uint32_t row_off[kSwClasses + 1] = {};
 	uint32_t ncols = 0;
 	if (b.cross) {
 		std::vector<uint32_t> byclass[kSwClasses];
@@ -670,7 +671,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	// ---- explicit pair lists: tasks per class are built on the host (lists are small: PostMuFilter, -alignpair, self) ----
 	std::vector<uint32_t> e_row[kSwClasses], e_begin[kSwClasses], e_cnt[kSwClasses];
 	std::vector<uint32_t> e_clist, e_cslot;
-	uint32_t e_off[kSwClasses + 1] = {0, 0, 0, 0};
+	uint32_t e_off[kSwClasses + 1] = {};
 	if (!b.cross) {
 		std::vector<uint8_t> keep;
 		if (filter) {
@@ -724,8 +725,9 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	sa.coloff_col = Cl->d.coloff; sa.off_col = Cl->d.off; sa.len_col = Cl->d.len;
 	sa.tr = tr ? 1 : 0;
 	sa.a_begin = b.a0; sa.nB = B->d.n;
-	sa.trace = ctx->trace.p; sa.trace_stride = trace_stride;
-	sa.bnd = ctx->bnd.p; sa.bnd_stride = bnd_stride;
+	sa.ckpt = ctx->ckpt.p; sa.ckpt_stride = ckpt_stride;
+	sa.tile = ctx->tile.p;
+	sa.bnd = ctx->bnd.p; sa.bnd_stride = bnd_stride; sa.bnd_pass_stride = bnd_pass_stride;
 	sa.stage = ctx->stage.p; sa.stage_stride = stage_stride;
 	sa.rec = ctx->rec.p;
 	sa.pool = ctx->pool.p; sa.pool_cursor = ctx->d_pool_cursor;

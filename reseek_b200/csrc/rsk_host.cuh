@@ -104,7 +104,8 @@ struct rsk_ctx {
 	unsigned long long *d_pool_cursor = nullptr;
 	cudaEvent_t ev[8] = {};
 	// grow-only scratch
-	DevBuf<uint4> trace;
+	DevBuf<float4> ckpt;
+	DevBuf<unsigned long long> tile;
 	DevBuf<float2> bnd;
 	DevBuf<uint8_t> stage;
 	DevBuf<PairRec> rec;

@@ -48,10 +48,11 @@ static_assert(sizeof(PairRec) == 64, "PairRec layout");
 // ---- SW kernel geometry ----
 constexpr int kSwWarps = 16;                 // warps per CTA of the Mu filter kernel
 constexpr int kSwThreads = kSwWarps * 32;
-constexpr int kMaxRowsPerLane = 8;           // R: DP rows owned by one lane within a pass
+constexpr int kMaxRowsPerLane = 12;          // R: DP rows owned by one lane within a pass
 constexpr int kRowsPerPassMax = 32 * kMaxRowsPerLane;
-// SW kernel classes by rows per lane: R <= 5 | R == 6 | R >= 7, with the warps per CTA (= pairs per task) of each
-constexpr int kSwClasses = 3;
+constexpr int kSwStripSteps = 16;            // wavefront steps between two checkpoints of the forward sweep
+// SW kernel classes by rows per lane: R <= 5 | R == 6 | R = 7..8 | R = 9..12, with the warps per CTA (= pairs per task) of each
+constexpr int kSwClasses = 4;
 #ifndef RSK_CLASS_W0
 #define RSK_CLASS_W0 20
 #endif
@@ -61,10 +62,13 @@ constexpr int kSwClasses = 3;
 #ifndef RSK_CLASS_W2
 #define RSK_CLASS_W2 16
 #endif
-constexpr int kClassWarps[kSwClasses] = {RSK_CLASS_W0, RSK_CLASS_W1, RSK_CLASS_W2};
-constexpr int kSwMaxWarps = 20;
-__host__ __device__ inline int sw_class_of_R(int R) { return R <= 5 ? 0 : R == 6 ? 1 : 2; }
-__host__ __device__ inline int sw_class_warps(int c) { return c == 0 ? RSK_CLASS_W0 : c == 1 ? RSK_CLASS_W1 : RSK_CLASS_W2; }
+#ifndef RSK_CLASS_W3
+#define RSK_CLASS_W3 16
+#endif
+constexpr int kClassWarps[kSwClasses] = {RSK_CLASS_W0, RSK_CLASS_W1, RSK_CLASS_W2, RSK_CLASS_W3};
+constexpr int kSwMaxWarps = RSK_CLASS_W0 > 20 ? RSK_CLASS_W0 : 20;
+__host__ __device__ inline int sw_class_of_R(int R) { return R <= 5 ? 0 : R == 6 ? 1 : R <= 8 ? 2 : 3; }
+__host__ __device__ inline int sw_class_warps(int c) { return c == 0 ? RSK_CLASS_W0 : c == 1 ? RSK_CLASS_W1 : c == 2 ? RSK_CLASS_W2 : RSK_CLASS_W3; }
 
 // How a chain of LA rows is cut into passes of 32*R rows (R rows per lane).
 __host__ __device__ inline void sw_geometry(uint32_t LA, int &npass, int &R)
@@ -98,8 +102,10 @@ struct SwArgs {
 	const uint32_t *cslot;   // explicit mode: record slot of each clist entry
 	uint32_t a_begin, nB;    // cross mode: slot = (a - a_begin)*nB + b with (a,b) the reference indices
 	// scratch (per warp of the grid)
-	uint4 *trace; uint64_t trace_stride;   // uint4 units per warp
-	float2 *bnd; uint32_t bnd_stride;      // pass-boundary row (M, vertical gap) per column
+	float4 *ckpt; uint64_t ckpt_stride;    // wavefront checkpoints, float4 units per warp
+	unsigned long long *tile;              // re-computed trace strip: kSwStripSteps*32 words per warp
+	float2 *bnd; uint64_t bnd_stride;      // pass-boundary rows (M, vertical gap) per column: per warp, one row per pass
+	uint32_t bnd_pass_stride;
 	uint8_t *stage; uint32_t stage_stride; // reversed path staging
 	// outputs
 	PairRec *rec;
@@ -240,7 +246,7 @@ int pf_segmented_sort(const uint32_t *kin, uint32_t *kout, unsigned long long n,
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();
-uint64_t sw_trace_units(int npass, uint32_t LB);
+uint64_t sw_ckpt_units(int npass, uint32_t LB);
 int launch_make_coloff(const uint64_t *prof8, uint64_t total, uint4 *coloff, cudaStream_t stream);
 int launch_lddt(const LddtArgs &args, cudaStream_t stream);
 int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);

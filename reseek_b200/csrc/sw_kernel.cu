@@ -1,31 +1,34 @@
 // sw_kernel.cu - K1: float affine-gap local Smith-Waterman with traceback over the on-the-fly 8-feature
-// DSS score, one warp per (A,B) pair, one CTA per A chain (16 pairs at a time).
+// DSS score, one warp per (A,B) pair, one CTA per row chain (W pairs at a time).
 //
 // Replaces, per pair: DSSAligner::SetSMx_NoRev (dssaligner.cpp:529-596) + SWFast (sw.cpp:79-212) +
-// TraceBackBitSW (sw.cpp:8-77).  Results are bit-identical: every cell performs exactly the reference's
-// fp32 adds and compares (sw.cpp:119-197), only the order in which independent cells are visited differs.
+// TraceBackBitSW (sw.cpp:8-77).  Results are bit-identical: every cell performs the reference's fp32 adds
+// and maxima (sw.cpp:119-197), only the order in which independent cells are visited differs.
 //
-// Design (B200, sm_100a):
-//  * The score matrix S is never materialised.  For the CTA's A chain a "row table" is staged in shared
-//    memory for the current pass of 32*R rows: plane 0 holds rows 0..3 of every lane as float4
-//    P0[e][lane], plane 1 rows 4..R-1 as float/float2/float4 P1[e][lane], e = (feature,letter) code 0..131,
-//    both with a 512-byte stride per code.  A lane's vector sits in its own bank group, so every LDS is
-//    conflict-free.  The B chain supplies, per DP column, 8 ready-made table offsets (32 bytes, prepared
-//    once per chain set), so a cell's score costs 8 table reads + 7 fp32 adds in the reference's order.
-//  * DP wavefront: lane L owns R consecutive rows (R = 1..8), lanes are skewed by one column per step, the
-//    last row's (M,D) travels to the next lane by warp shuffle.  A chain longer than 32*R rows is cut into
-//    passes; the bottom row of a pass is parked in a small global (L2-resident) boundary buffer.
-//    Steps whose 32 lanes are all inside the matrix run a predicate-free body (the steady state).
-//  * Traceback bits: 4 bits per cell (2 bits match-source, MD, MI) -> one 32-bit word per lane and step,
-//    four steps -> one fully coalesced 16-byte store per lane ("step-major", i.e. anti-diagonal, layout).
-//    The in-kernel traceback reads it back through a 2 KB shared-memory tile.
-//  * The running maximum is tracked per lane with one FMNMX3 chain per step; the exact first-maximum rule of
+// Design (B200, sm_100a), v4 "checkpointed forward, strip-recomputed traceback":
+//  * The score matrix S is never materialised.  For the CTA's row chain a "row table" is staged in shared
+//    memory for the current pass of 32*R rows (R = 1..12 rows per lane): plane 0 holds rows 0..3 of every lane
+//    as float4 P0[e][lane], plane 1 rows 4..7, plane 2 rows 8..11 (float/float2/float4 by need), e =
+//    (feature,letter) code 0..131, 512-byte stride per code.  A lane's vector sits in its own bank group, so
+//    every LDS is conflict-free.  The column chain supplies, per DP column, 8 ready-made table offsets
+//    (32 bytes, prepared once per chain set), so a cell's score costs 8 table reads + 7 fp32 adds in the
+//    reference's order.
+//  * DP wavefront: lane L owns R consecutive rows, lanes are skewed by one column per step, the last row's
+//    (M,D) travels to the next lane by warp shuffle.  A chain longer than 32*12 rows is cut into passes; the
+//    bottom row of a pass is parked in a small global (L2-resident) boundary row per pass.
+//  * The forward sweep writes NO per-cell trace.  It keeps values only (FMNMX/FADD, about half the
+//    instructions of a trace-producing cell) and every 16 steps parks the wavefront state of the warp
+//    (2R+3 floats per lane) as a checkpoint.  The traceback (sw.cpp:8-77) then re-runs just the 16-step
+//    strips its path crosses, this time producing the reference's 4 trace bits per cell (match source,
+//    MD, MI) into a 4 KB L1-resident tile; random pairs align over a handful of columns, so this is
+//    about one strip per pair.  Values are identical in both sweeps (same operations on the same inputs).
+//  * The running maximum is tracked per lane with one FMNMX chain per step; the exact first-maximum rule of
 //    the reference (row-major order, strict >) is restored in a rarely taken slow path and in the final
 //    (score desc, row asc) warp reduction.
 //  * Either chain of a pair can supply the rows (template TR): the scheduler puts the side with fewer chains on
 //    the rows so that a CTA's row table is shared by a full set of warps.
 //  * Persistent CTAs (one per SM) pull tasks from an atomic counter; one kernel per row-length class so that
-//    short row blocks (few registers) run with 24 warps per SM and long ones with 16.
+//    short row blocks (few registers) run with more warps per SM than long ones.
 #include <type_traits>
 
 #include "rsk_internal.cuh"
@@ -36,27 +39,27 @@ namespace {
 
 constexpr int kNLet = RSK_NLETTERS;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kStrip = kSwStripSteps;  // steps between two checkpoints
 
 // shared memory carve-up
 constexpr size_t kSmemTab = 0;                          // float[2192] weighted tables
 constexpr size_t kSmemP0 = 8768;                        // plane 0: float4[132][32], rows 0..3 of each lane
 constexpr size_t kPlaneBytes = (size_t)kNLet * 512;     // 67584
-constexpr size_t kSmemP1 = kSmemP0 + kPlaneBytes;       // plane 1: rows 4..R-1, same 512-byte stride per code
-constexpr size_t kSmemTiles = kSmemP1 + kPlaneBytes;    // uint4[warps][4][32] traceback tiles
-constexpr size_t kSmemBcast = kSmemTiles + (size_t)kSwMaxWarps * 4 * 32 * 16;
-constexpr size_t kSmemTotal = kSmemBcast + 16;
+constexpr int kPlaneFloats = kNLet * 128;
+__host__ __device__ constexpr int class_planes(int C) { return C >= 3 ? 3 : 2; }
+__host__ __device__ constexpr size_t class_smem(int C) { return kSmemP0 + (size_t)class_planes(C) * kPlaneBytes + 16; }
 
-// floats per lane in plane 1 for R rows per lane (R-4 rounded up to a vector width)
-__host__ __device__ constexpr int plane1_width(int R) { return R <= 4 ? 0 : R == 5 ? 1 : R == 6 ? 2 : 4; }
+// floats per lane in plane 1 / 2 for n rows living there (rounded up to a vector width)
+__host__ __device__ constexpr int plane_width(int n) { return n <= 0 ? 0 : n == 1 ? 1 : n == 2 ? 2 : 4; }
 
 // table value of rows beyond the end of the chain: such cells are hugely negative and can never be a maximum
 constexpr float kPadScore = -1e30f;
 
 template <int R, int NTHREADS>
-__device__ __forceinline__ void build_rowtab(float *p0, float *p1, const float *tab, const uint64_t *__restrict__ profA,
+__device__ __forceinline__ void build_rowtab(float *planes, const float *tab, const uint64_t *__restrict__ profA,
 		uint32_t LA, int pass)
 {
-	constexpr int W1 = plane1_width(R);
+	constexpr int W1 = plane_width(R - 4), W2 = plane_width(R - 8);
 	constexpr int ROWS = 32 * R;
 	const uint32_t rowbase = (uint32_t)pass * ROWS;
 	for (int idx = threadIdx.x; idx < kNLet * ROWS; idx += NTHREADS) {
@@ -74,9 +77,11 @@ __device__ __forceinline__ void build_rowtab(float *p0, float *p1, const float *
 			v = tab[feat_table_off(f) + a * feat_alpha(f) + b];
 		}
 		if (r < 4)
-			p0[e * 128 + l * 4 + r] = v;
+			planes[e * 128 + l * 4 + r] = v;
+		else if (r < 8)
+			planes[kPlaneFloats + e * 128 + l * W1 + (r - 4)] = v;
 		else
-			p1[e * 128 + l * W1 + (r - 4)] = v;
+			planes[2 * kPlaneFloats + e * 128 + l * W2 + (r - 8)] = v;
 	}
 }
 
@@ -108,7 +113,7 @@ __device__ __forceinline__ void add_const(float (&out)[N], const float (&in)[N],
 
 // acc[r] += v[r] for r < N, two rows per instruction
 template <int N>
-__device__ __forceinline__ void add_vec(float (&acc)[N], const float (&v)[8])
+__device__ __forceinline__ void add_vec(float (&acc)[N], const float (&v)[12])
 {
 #pragma unroll
 	for (int r = 0; r + 1 < N; r += 2) {
@@ -120,55 +125,105 @@ __device__ __forceinline__ void add_vec(float (&acc)[N], const float (&v)[8])
 		acc[N - 1] = acc[N - 1] + v[N - 1];
 }
 
-// One pass: rows [pass*32R, (pass+1)*32R) of A against all LB columns of B.
+// float4 units of one checkpoint per lane: M[R], I[R], M diagonal, (M, D) handed to the next lane
+__host__ __device__ constexpr int ckpt_words(int R) { return (2 * R + 3 + 3) / 4; }
+
+// One sweep over rows [pass*32R, (pass+1)*32R) of the row chain.
+//   TRACE = false: the forward sweep over all LB columns.  Values only; saves a checkpoint every kStrip steps
+//                  and tracks the lane's first maximum (lbest, lbi, lbj in kernel coordinates).
+//   TRACE = true : re-run of strip `strip` (steps kStrip*strip .. s_last) from its checkpoint, writing one 64-bit
+//                  trace word per lane and step (4 bits per row) into `tile[(step % kStrip)*32 + lane]`.
 // colB: two uint4 per column = the column's 8 table offsets in units of 16 bytes (code * 32).
 // TR = false: kernel rows are the reference's A chain (index i), columns its B chain (j).
 // TR = true : rows are the reference's B chain, columns its A chain.  The recurrence is the same with the
 //             roles of the two gap states exchanged: the reference tests D (gap that consumes A) before I
 //             (sw.cpp:136-147), and its first-maximum rule prefers the smaller i, then the smaller j.
-// lbi/lbj are in kernel coordinates (row, column).
-template <int R, bool TR>
-__device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int lane, const int pass, const int npass,
-		const uint32_t LA, const uint4 *__restrict__ colB, const int LB, float2 *__restrict__ bnd,
-		uint4 *__restrict__ trace_pass, const float open, const float ext, float &lbest, int &lbi, int &lbj)
+// bnd_in / bnd_out: boundary row written by the previous pass / to be written by this one.
+template <int R, bool TR, bool TRACE>
+__device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int lane, const bool first, const bool last,
+		const uint32_t row0, const uint32_t LA, const uint4 *__restrict__ colB, const int LB,
+		const float2 *__restrict__ bnd_in, float2 *__restrict__ bnd_out, float4 *__restrict__ ck, const float open,
+		const float ext, float &lbest, int &lbi, int &lbj, const int strip, const int s_last,
+		unsigned long long *__restrict__ tile)
 {
-	constexpr int W1 = plane1_width(R);
-	// Per-lane byte offsets into the two planes.  They are made opaque to the optimiser so that "offset*16 + lane
+	constexpr int W1 = plane_width(R - 4), W2 = plane_width(R - 8);
+	constexpr int NW4 = ckpt_words(R);
+	// Per-lane byte offsets into the planes.  They are made opaque to the optimiser so that "offset*16 + lane
 	// term" stays one IMAD; the loads themselves are ordinary shared-memory loads (LDS with the plane base folded into
 	// the immediate) which the scheduler may hoist above the warp shuffles of the next step.
 	uint32_t base0 = (uint32_t)lane * 16u;
 	uint32_t base1 = (uint32_t)lane * (uint32_t)(W1 * 4);
+	uint32_t base2 = (uint32_t)lane * (uint32_t)(W2 * 4);
 	asm volatile("" : "+r"(base0));
 	asm volatile("" : "+r"(base1));
+	asm volatile("" : "+r"(base2));
 	const unsigned char *const plane0 = smem_p0;
 	const unsigned char *const plane1 = smem_p0 + kPlaneBytes;
+	const unsigned char *const plane2 = smem_p0 + 2 * kPlaneBytes;
 	float Mrow[R], Irow[R];
 #pragma unroll
 	for (int r = 0; r < R; ++r) {
 		Mrow[r] = kNegInf;  // M[i_r+1][0]
 		Irow[r] = kNegInf;  // I[i_r][0]
 	}
-	const bool first = (pass == 0), last = (pass == npass - 1);
 	const bool lane0 = (lane == 0);
 	const bool use_bnd = lane0 && !first;
 	const bool put_bnd = (lane == 31) && !last;
 	float mdiag_next = (lane0 && first) ? 0.0f : kNegInf;  // M[i0][0]; M[0][0] = 0 (sw.cpp:116)
 	float outM = kNegInf, outD = kNegInf;
-	const uint32_t row0 = (uint32_t)pass * 32 * R + (uint32_t)lane * R;
 	const int nsteps = LB + 31;
 	const int ngroups = (nsteps + 3) >> 2;
+
+	auto save = [&](const int k) {
+		float t[NW4 * 4];
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			t[r] = Mrow[r];
+			t[R + r] = Irow[r];
+		}
+		t[2 * R] = mdiag_next;
+		t[2 * R + 1] = outM;
+		t[2 * R + 2] = outD;
+#pragma unroll
+		for (int w = 2 * R + 3; w < NW4 * 4; ++w)
+			t[w] = 0.0f;
+#pragma unroll
+		for (int w = 0; w < NW4; ++w)
+			ck[((size_t)k * NW4 + w) * 32 + lane] = make_float4(t[4 * w], t[4 * w + 1], t[4 * w + 2], t[4 * w + 3]);
+	};
+	auto load = [&](const int k) {
+		float t[NW4 * 4];
+#pragma unroll
+		for (int w = 0; w < NW4; ++w) {
+			const float4 v = ck[((size_t)k * NW4 + w) * 32 + lane];
+			t[4 * w] = v.x; t[4 * w + 1] = v.y; t[4 * w + 2] = v.z; t[4 * w + 3] = v.w;
+		}
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			Mrow[r] = t[r];
+			Irow[r] = t[R + r];
+		}
+		mdiag_next = t[2 * R];
+		outM = t[2 * R + 1];
+		outD = t[2 * R + 2];
+	};
+
 	int j = -lane;
+	if (TRACE) {
+		load(strip);
+		j = kStrip * strip - lane;
+	}
 	uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
 	if (j >= 0 && j < LB) {
 		c0 = __ldg(colB + 2 * j);
 		c1 = __ldg(colB + 2 * j + 1);
 	}
 	float2 bn = make_float2(kNegInf, kNegInf);
-	if (use_bnd)
-		bn = bnd[0];
+	if (use_bnd && j < LB)
+		bn = bnd_in[j];
 
 	// CHECK = false: every lane is inside the matrix at this step and at the next one (no range predicates)
-	auto step = [&](auto check_tag) -> uint32_t {
+	auto step = [&](auto check_tag) -> unsigned long long {
 		constexpr bool CHECK = decltype(check_tag)::value;
 		const float inM = __shfl_up_sync(kFull, outM, 1);
 		const float inD = __shfl_up_sync(kFull, outD, 1);
@@ -180,8 +235,8 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 		}
 		float2 bn_next = bn;
 		if (use_bnd && (!CHECK || jn < LB))
-			bn_next = bnd[jn];
-		uint32_t tw = 0;
+			bn_next = bnd_in[jn];
+		uint32_t tw0 = 0, tw1 = 0;
 		if (!CHECK || (j >= 0 && j < LB)) {
 			float d = lane0 ? bn.y : inD;  // D[i0][j]   (bn = -inf pair in the first pass)
 			const float mdiag = mdiag_next;  // M[i0][j]
@@ -192,9 +247,11 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 			for (int f = 0; f < RSK_NFEAT; ++f) {
 				const uint32_t a0 = co[f] * 16u + base0;
 				const float4 v0 = *reinterpret_cast<const float4 *>(plane0 + a0);
-				float v[8];
+				float v[12];
 				v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
-				v[4] = v[5] = v[6] = v[7] = 0.0f;
+#pragma unroll
+				for (int r = 4; r < 12; ++r)
+					v[r] = 0.0f;
 				if (W1 == 1) {
 					v[4] = *reinterpret_cast<const float *>(plane1 + (co[f] * 16u + base1));
 				} else if (W1 == 2) {
@@ -203,6 +260,15 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 				} else if (W1 == 4) {
 					const float4 t = *reinterpret_cast<const float4 *>(plane1 + a0);
 					v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w;
+				}
+				if (W2 == 1) {
+					v[8] = *reinterpret_cast<const float *>(plane2 + (co[f] * 16u + base2));
+				} else if (W2 == 2) {
+					const float2 t = *reinterpret_cast<const float2 *>(plane2 + (co[f] * 16u + base2));
+					v[8] = t.x; v[9] = t.y;
+				} else if (W2 == 4) {
+					const float4 t = *reinterpret_cast<const float4 *>(plane2 + a0);
+					v[8] = t.x; v[9] = t.y; v[10] = t.z; v[11] = t.w;
 				}
 				// feature 0 assigns, 1..7 accumulate in this order (dssaligner.cpp:557-595)
 				if (f == 0) {
@@ -236,47 +302,63 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 			for (int r = 0; r < R; ++r) {
 				const float m = Mdg[r];  // M[i][j]
 				const float ii = Irow[r];
-				float x = m;
-				uint32_t code = 0;
-				// code: 1 = reference D state (consumes A), 2 = reference I state; D is tested first
-				if (!TR) {
-					if (d > x) { x = d; code = 1; }
-					if (ii > x) { x = ii; code = 2; }
-				} else {
-					if (ii > x) { x = ii; code = 1; }
-					if (d > x) { x = d; code = 2; }
-				}
-				if (0.0f >= x) { x = 0.0f; code = 3; }
-				x += S[r];
-				xmax = fmaxf(xmax, x);
-				Mrow[r] = x;  // M[row+1][col+1]
 				const float mo = Mo[r];
-				float dn = d + ext;
-				if (mo >= dn) { dn = mo; code |= TR ? 8u : 4u; }
-				d = dn;  // vertical gap state entering the next row
-				float in2 = Ie[r];
-				if (mo >= in2) { in2 = mo; code |= TR ? 4u : 8u; }
-				Irow[r] = in2;  // horizontal gap state entering the next column
-				tw |= code << (4 * r);
+				if (TRACE) {
+					// the reference's compare-and-record form (sw.cpp:129-190)
+					float x = m;
+					uint32_t code = 0;
+					// code: 1 = reference D state (consumes A), 2 = reference I state; D is tested first
+					if (!TR) {
+						if (d > x) { x = d; code = 1; }
+						if (ii > x) { x = ii; code = 2; }
+					} else {
+						if (ii > x) { x = ii; code = 1; }
+						if (d > x) { x = d; code = 2; }
+					}
+					if (0.0f >= x) { x = 0.0f; code = 3; }
+					x += S[r];
+					Mrow[r] = x;  // M[row+1][col+1]
+					float dn = d + ext;
+					if (mo >= dn) { dn = mo; code |= TR ? 8u : 4u; }
+					d = dn;  // vertical gap state entering the next row
+					float in2 = Ie[r];
+					if (mo >= in2) { in2 = mo; code |= TR ? 4u : 8u; }
+					Irow[r] = in2;  // horizontal gap state entering the next column
+					if (r < 8)
+						tw0 |= code << (4 * (r & 7));
+					else
+						tw1 |= code << (4 * (r & 7));
+				} else {
+					// same values without the bookkeeping: the selected value of each compare chain is the maximum
+					// (no -0.0 can arise: 0 is only ever produced as +0.0 and sums of non-zero terms round to +0.0)
+					float x = fmaxf(fmaxf(m, d), fmaxf(ii, 0.0f));
+					x += S[r];
+					xmax = fmaxf(xmax, x);
+					Mrow[r] = x;
+					d = fmaxf(mo, d + ext);
+					Irow[r] = fmaxf(mo, Ie[r]);
+				}
 			}
 			outM = Mrow[R - 1];
 			outD = d;
-			if (put_bnd)
-				bnd[j] = make_float2(outM, outD);
-			if (TR ? (xmax > lbest) : (xmax >= lbest)) {
-				// rare: a cell reached the lane's running maximum.  Keep the reference's first-maximum rule
-				// (row-major over (i,j), strict >).  !TR: higher score wins; equal score -> smaller row i; same row ->
-				// the earlier column (already stored).  TR: columns are i and are visited in ascending order, rows (j)
-				// ascending within a step, so the first cell seen with a score is already the right one: strict > only.
+			if (!TRACE) {
+				if (put_bnd)
+					bnd_out[j] = make_float2(outM, outD);
+				if (TR ? (xmax > lbest) : (xmax >= lbest)) {
+					// rare: a cell reached the lane's running maximum.  Keep the reference's first-maximum rule
+					// (row-major over (i,j), strict >).  !TR: higher score wins; equal score -> smaller row i; same row ->
+					// the earlier column (already stored).  TR: columns are i and are visited in ascending order, rows (j)
+					// ascending within a step, so the first cell seen with a score is already the right one: strict > only.
 #pragma unroll
-				for (int r = 0; r < R; ++r) {
-					const float x = Mrow[r];
-					const int row = (int)(row0 + r);
-					const bool better = TR ? (x > lbest) : (x > lbest || (x == lbest && row < lbi));
-					if (better && (uint32_t)row < LA) {
-						lbest = x;
-						lbi = row;
-						lbj = j;
+					for (int r = 0; r < R; ++r) {
+						const float x = Mrow[r];
+						const int row = (int)(row0 + r);
+						const bool better = TR ? (x > lbest) : (x > lbest || (x == lbest && row < lbi));
+						if (better && (uint32_t)row < LA) {
+							lbest = x;
+							lbi = row;
+							lbj = j;
+						}
 					}
 				}
 			}
@@ -285,85 +367,103 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 		c0 = n0;
 		c1 = n1;
 		bn = bn_next;
-		return tw;
+		return (unsigned long long)tw0 | ((unsigned long long)tw1 << 32);
 	};
 
-	for (int g = 0; g < ngroups; ++g) {
-		const int s0 = 4 * g;
-		uint32_t t0, t1, t2, t3;
-		if (s0 >= 31 && s0 + 4 < LB) {
-			t0 = step(std::false_type{});
-			t1 = step(std::false_type{});
-			t2 = step(std::false_type{});
-			t3 = step(std::false_type{});
-		} else {
-			t0 = step(std::true_type{});
-			t1 = step(std::true_type{});
-			t2 = step(std::true_type{});
-			t3 = step(std::true_type{});
+	if (TRACE) {
+		for (int s = kStrip * strip; s <= s_last; ++s) {
+			const unsigned long long tw = step(std::true_type{});
+			tile[(s & (kStrip - 1)) * 32 + lane] = tw;
 		}
-		trace_pass[g * 32 + lane] = make_uint4(t0, t1, t2, t3);
+	} else {
+		for (int g = 0; g < ngroups; ++g) {
+			const int s0 = 4 * g;
+			if ((g & (kStrip / 4 - 1)) == 0)
+				save(g / (kStrip / 4));
+			if (s0 >= 31 && s0 + 4 < LB) {
+				step(std::false_type{});
+				step(std::false_type{});
+				step(std::false_type{});
+				step(std::false_type{});
+			} else {
+				step(std::true_type{});
+				step(std::true_type{});
+				step(std::true_type{});
+				step(std::true_type{});
+			}
+		}
 	}
 }
 
-// Warp-cooperative traceback (sw.cpp:8-77) through a 2 KB shared tile of the packed trace.
-// Trace word of cell (row, col): pass p = row / (32R), lane l = (row % 32R) / R, nibble r = row % R,
-// step s = col + l, group g = s / 4, word s % 4 of uint4 trace[(p*ngroups + g)*32 + l].
-// bi/bj and the walk are in reference coordinates (i over A, j over B); tr maps them onto the kernel's (row, column).
-__device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int lane, const int R, const int LB, const bool tr,
-		const uint4 *__restrict__ trace, uint4 *tile, uint8_t *stage, const float score, const int bi, const int bj,
-		PairRec *rec)
+// Resumable warp-cooperative traceback (sw.cpp:8-77).  The walk is in reference coordinates (i over A, j over B); TR maps
+// them onto the kernel's (row, column).  Trace nibble of cell (row, col): pass p = row / (32R), lane l = (row % 32R) / R,
+// nibble r = row % R, step s = col + l, strip k = s / kStrip, word tile[(s % kStrip)*32 + l].  Within a pass the step of
+// the walk never increases, so a strip is re-run once, up to the step at which the walk enters it.
+struct TbState {
+	int i, j;      // reference DP coordinates of the walk (1-based cell indices as in sw.cpp)
+	int state;     // 0 = M, 1 = D, 2 = I
+	uint32_t n;    // columns emitted so far
+	int cur_p, cur_k;
+};
+
+// Walks while the path stays in pass `pass` (whose row table is the one in shared memory).  Returns true when the path is
+// complete, false when it continues in the pass above.
+template <int R, bool TR>
+__device__ __forceinline__ bool traceback_in_pass(const unsigned char *smem_p0, const int lane, const int pass, const int npass,
+		const uint32_t LA, const uint4 *__restrict__ colB, const int LB, float2 *__restrict__ bnd, const uint32_t bnd_pass_stride,
+		float4 *__restrict__ ck, const int nstrips, const float open, const float ext, unsigned long long *__restrict__ tile,
+		uint8_t *__restrict__ stage, TbState &t)
 {
-	const int rows_per_pass = 32 * R;
-	const int ngroups = (LB + 31 + 3) >> 2;
-	const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
-	int i = bi + 1, j = bj + 1;
-	int state = 0;  // 0 = M, 1 = D, 2 = I
-	uint32_t n = 0;
-	int cur_p = -1, cur_G = -1;
+	constexpr int rows_per_pass = 32 * R;
 	for (;;) {
-		if (lane == 0)
-			stage[n] = (uint8_t)(state == 0 ? 'M' : state == 1 ? 'D' : 'I');
-		++n;
-		const int ci = (state == 2) ? i : i - 1;
-		const int cj = (state == 1) ? j : j - 1;
-		const int krow = tr ? cj : ci, kcol = tr ? ci : cj;
+		const int ci = (t.state == 2) ? t.i : t.i - 1;
+		const int cj = (t.state == 1) ? t.j : t.j - 1;
+		const int krow = TR ? cj : ci, kcol = TR ? ci : cj;
 		const int p = krow / rows_per_pass;
+		if (p != pass)
+			return false;
+		if (lane == 0)
+			stage[t.n] = (uint8_t)(t.state == 0 ? 'M' : t.state == 1 ? 'D' : 'I');
+		++t.n;
 		const int rr = krow - p * rows_per_pass;
 		const int srcl = rr / R;
 		const int r = rr - srcl * R;
 		const int s = kcol + srcl;
-		const int g = s >> 2;
-		const int G = g >> 2;
-		if (p != cur_p || G != cur_G) {
+		const int k = s / kStrip;
+		if (p != t.cur_p || k != t.cur_k) {
 			__syncwarp();
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const int gg = 4 * G + k;
-				if (gg < ngroups)
-					tile[k * 32 + lane] = trace[((size_t)p * ngroups + gg) * 32 + lane];
-			}
+			float lb = 0.0f;
+			int li = 0, lj = 0;
+			sw_pass<R, TR, true>(smem_p0, lane, p == 0, p == npass - 1, (uint32_t)p * rows_per_pass + (uint32_t)lane * R, LA, colB, LB,
+					bnd + (size_t)(p > 0 ? p - 1 : 0) * bnd_pass_stride, nullptr, ck + (size_t)p * nstrips * ckpt_words(R) * 32, open,
+					ext, lb, li, lj, k, s, tile);
 			__syncwarp();
-			cur_p = p;
-			cur_G = G;
+			t.cur_p = p;
+			t.cur_k = k;
 		}
-		const uint32_t w = tile32[(((g & 3) * 32 + srcl) << 2) + (s & 3)];
-		const uint32_t nib = (w >> (4 * r)) & 15u;
-		if (state == 0) {
-			--i; --j;
+		const unsigned long long w = tile[(s & (kStrip - 1)) * 32 + srcl];
+		const uint32_t nib = (uint32_t)(w >> (4 * r)) & 15u;
+		if (t.state == 0) {
+			--t.i; --t.j;
 			const uint32_t src = nib & 3u;
 			if (src == 3u)
-				break;
-			state = (int)src;  // 0 M, 1 D, 2 I
-		} else if (state == 1) {
-			--i;
-			state = (nib & 4u) ? 0 : 1;
+				return true;
+			t.state = (int)src;  // 0 M, 1 D, 2 I
+		} else if (t.state == 1) {
+			--t.i;
+			t.state = (nib & 4u) ? 0 : 1;
 		} else {
-			--j;
-			state = (nib & 8u) ? 0 : 2;
+			--t.j;
+			t.state = (nib & 8u) ? 0 : 2;
 		}
 	}
-	// publish: reserve pool space, copy the staged (reversed) path forward
+}
+
+// publish: reserve pool space, copy the staged (reversed) path forward, fill the record
+__device__ __forceinline__ void emit_path(const SwArgs &a, const int lane, const uint8_t *stage, const float score, const TbState &t,
+		PairRec *rec)
+{
+	const uint32_t n = t.n;
 	unsigned long long off = 0;
 	if (lane == 0)
 		off = atomicAdd(a.pool_cursor, (unsigned long long)n);
@@ -373,8 +473,8 @@ __device__ __forceinline__ void traceback_and_emit(const SwArgs &a, const int la
 		a.pool[off + k] = stage[n - 1 - k];
 	if (lane == 0) {
 		rec->score = score;
-		rec->lo_a = (uint32_t)i;
-		rec->lo_b = (uint32_t)j;
+		rec->lo_a = (uint32_t)t.i;
+		rec->lo_b = (uint32_t)t.j;
 		rec->path_len = n;
 		rec->path_off = off;
 	}
@@ -386,10 +486,8 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const float *tab = reinterpret_cast<const float *>(smem + kSmemTab);
-	float *p0 = reinterpret_cast<float *>(smem + kSmemP0);
-	float *p1 = reinterpret_cast<float *>(smem + kSmemP1);
+	float *planes = reinterpret_cast<float *>(smem + kSmemP0);
 	const unsigned char *smem_p0 = smem + kSmemP0;
-	uint4 *tile = reinterpret_cast<uint4 *>(smem + kSmemTiles) + warp * 128;
 
 	const uint32_t LA = a.len_row[rowchain];  // kernel rows
 	const uint64_t *profA = a.prof_row + a.off_row[rowchain];
@@ -410,63 +508,89 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 		LB = (int)a.len_col[cidx];
 		colB = a.coloff_col + 2 * a.off_col[cidx];
 	}
-	const int ngroups = (LB + 31 + 3) >> 2;
+	const int nstrips = (((LB + 31 + 3) >> 2) + kStrip / 4 - 1) / (kStrip / 4);
 	const size_t gw = (size_t)blockIdx.x * W + warp;
-	uint4 *trace = a.trace + gw * a.trace_stride;
+	float4 *ck = a.ckpt + gw * a.ckpt_stride;
 	float2 *bnd = a.bnd + gw * a.bnd_stride;
 	uint8_t *stage = a.stage + gw * a.stage_stride;
+	unsigned long long *tile = a.tile + gw * (kStrip * 32);
 
 	float lbest = 0.0f;
 	int lbi = 0x7fffffff, lbj = 0x7fffffff;  // kernel (row, column) of the best cell
 	for (int pass = 0; pass < npass; ++pass) {
-		__syncthreads();  // every warp is done with the previous pass's row table
-		build_rowtab<R, W * 32>(p0, p1, tab, profA, LA, pass);
+		__syncthreads();  // every warp is done with the previous row table
+		build_rowtab<R, W * 32>(planes, tab, profA, LA, pass);
 		__syncthreads();
 		if (have)
-			sw_pass<R, TR>(smem_p0, lane, pass, npass, LA, colB, LB, bnd, trace + (size_t)pass * ngroups * 32,
-					a.open, a.ext, lbest, lbi, lbj);
+			sw_pass<R, TR, false>(smem_p0, lane, pass == 0, pass == npass - 1, (uint32_t)pass * 32 * R + (uint32_t)lane * R, LA, colB,
+					LB, bnd + (size_t)(pass > 0 ? pass - 1 : 0) * a.bnd_pass_stride, bnd + (size_t)pass * a.bnd_pass_stride,
+					ck + (size_t)pass * nstrips * ckpt_words(R) * 32, a.open, a.ext, lbest, lbi, lbj, 0, 0, nullptr);
 	}
-	if (!have)
-		return;
-	// first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j
-#pragma unroll
-	for (int o = 16; o >= 1; o >>= 1) {
-		const float os = __shfl_xor_sync(kFull, lbest, o);
-		const int oi = __shfl_xor_sync(kFull, lbi, o);
-		const int oj = __shfl_xor_sync(kFull, lbj, o);
-		bool take;
-		if (!TR)  // i = row (unique per lane), j = column
-			take = os > lbest || (os == lbest && oi < lbi);
-		else      // i = column, j = row
-			take = os > lbest || (os == lbest && (oj < lbj || (oj == lbj && oi < lbi)));
-		if (take) {
-			lbest = os; lbi = oi; lbj = oj;
-		}
-	}
+	bool active = false;
 	PairRec *rec = a.rec + slot;
-	if (lbest == 0.0f) {  // sw.cpp:200-201: no positive cell -> score 0, empty path
-		if (lane == 0) {
-			rec->score = 0.0f;
-			rec->lo_a = 0xffffffffu;
-			rec->lo_b = 0xffffffffu;
-			rec->path_len = 0;
-			rec->path_off = 0;
+	if (have) {
+		// first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j
+#pragma unroll
+		for (int o = 16; o >= 1; o >>= 1) {
+			const float os = __shfl_xor_sync(kFull, lbest, o);
+			const int oi = __shfl_xor_sync(kFull, lbi, o);
+			const int oj = __shfl_xor_sync(kFull, lbj, o);
+			bool take;
+			if (!TR)  // i = row (unique per lane), j = column
+				take = os > lbest || (os == lbest && oi < lbi);
+			else      // i = column, j = row
+				take = os > lbest || (os == lbest && (oj < lbj || (oj == lbj && oi < lbi)));
+			if (take) {
+				lbest = os; lbi = oi; lbj = oj;
+			}
 		}
-		return;
+		if (lbest == 0.0f) {  // sw.cpp:200-201: no positive cell -> score 0, empty path
+			if (lane == 0) {
+				rec->score = 0.0f;
+				rec->lo_a = 0xffffffffu;
+				rec->lo_b = 0xffffffffu;
+				rec->path_len = 0;
+				rec->path_off = 0;
+			}
+		} else {
+			active = true;
+		}
 	}
-	__syncwarp();  // trace words written by other lanes of this warp are visible
-	traceback_and_emit(a, lane, R, LB, TR, trace, tile, stage, lbest, TR ? lbj : lbi, TR ? lbi : lbj, rec);
+	TbState t;
+	t.i = (TR ? lbj : lbi) + 1;
+	t.j = (TR ? lbi : lbj) + 1;
+	t.state = 0;
+	t.n = 0;
+	t.cur_p = -1;
+	t.cur_k = -1;
+	__syncwarp();  // checkpoints and boundary rows written by other lanes of this warp are visible
+	for (int p = npass - 1; p >= 0; --p) {
+		if (p != npass - 1) {
+			// the path of some warp continues above this pass: restage that pass's row table for the whole CTA
+			build_rowtab<R, W * 32>(planes, tab, profA, LA, p);
+			__syncthreads();
+		}
+		if (active) {
+			if (traceback_in_pass<R, TR>(smem_p0, lane, p, npass, LA, colB, LB, bnd, a.bnd_pass_stride, ck, nstrips, a.open, a.ext,
+						tile, stage, t)) {
+				emit_path(a, lane, stage, lbest, t, rec);
+				active = false;
+			}
+		}
+		if (p > 0 && !__syncthreads_or(active ? 1 : 0))
+			break;
+	}
 }
 
-// One kernel per (row-length class, orientation).  Class C handles R in [kClassRLo[C], kClassRHi[C]] with
-// kClassWarps[C] warps: fewer rows per lane need fewer registers, so more warps fit and hide latency better.
+// One kernel per (row-length class, orientation).  Class C handles a range of R with kClassWarps[C] warps: fewer rows
+// per lane need fewer registers, so more warps fit and hide latency better.
 template <int C, bool TR>
 __global__ void __launch_bounds__(kClassWarps[C] * 32, 1) sw_affine_f32_tb_kernel(const SwArgs a)
 {
 	constexpr int W = kClassWarps[C];
 	extern __shared__ __align__(16) unsigned char smem[];
 	float *tab = reinterpret_cast<float *>(smem + kSmemTab);
-	volatile int *bcast = reinterpret_cast<volatile int *>(smem + kSmemBcast);
+	volatile int *bcast = reinterpret_cast<volatile int *>(smem + kSmemP0 + class_planes(C) * kPlaneBytes);
 	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += W * 32)
 		tab[k] = a.tables[k];
 	__syncthreads();
@@ -503,11 +627,18 @@ __global__ void __launch_bounds__(kClassWarps[C] * 32, 1) sw_affine_f32_tb_kerne
 			}
 		} else if (C == 1) {
 			process_task<6, TR, W>(a, smem, rowchain, begin, cnt);
-		} else {
+		} else if (C == 2) {
 			if (R == 7)
 				process_task<7, TR, W>(a, smem, rowchain, begin, cnt);
 			else
 				process_task<8, TR, W>(a, smem, rowchain, begin, cnt);
+		} else {
+			switch (R) {
+			case 9: process_task<9, TR, W>(a, smem, rowchain, begin, cnt); break;
+			case 10: process_task<10, TR, W>(a, smem, rowchain, begin, cnt); break;
+			case 11: process_task<11, TR, W>(a, smem, rowchain, begin, cnt); break;
+			default: process_task<12, TR, W>(a, smem, rowchain, begin, cnt); break;
+			}
 		}
 	}
 }
@@ -547,17 +678,21 @@ __global__ void make_coloff_kernel(const uint64_t *__restrict__ prof8, uint64_t 
 
 }  // namespace
 
-size_t sw_smem_bytes() { return kSmemTotal; }
+size_t sw_smem_bytes() { return class_smem(kSwClasses - 1); }
 
-// uint4 units of packed trace one warp needs for a pair with npass passes and LB columns
-uint64_t sw_trace_units(int npass, uint32_t LB) { return (uint64_t)npass * ((LB + 31 + 3) >> 2) * 32; }
+// float4 units of checkpoints one warp needs for a pair with npass passes and LB columns (any R)
+uint64_t sw_ckpt_units(int npass, uint32_t LB)
+{
+	const uint64_t nstrips = (((LB + 31 + 3) >> 2) + kStrip / 4 - 1) / (kStrip / 4);
+	return (uint64_t)npass * nstrips * ckpt_words(kMaxRowsPerLane) * 32;
+}
 
 template <int C, bool TR>
 static int launch_sw_ct(const SwArgs &args, int grid, cudaStream_t stream)
 {
-	if (cudaFuncSetAttribute(sw_affine_f32_tb_kernel<C, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal) != cudaSuccess)
+	if (cudaFuncSetAttribute(sw_affine_f32_tb_kernel<C, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)class_smem(C)) != cudaSuccess)
 		return -1;
-	sw_affine_f32_tb_kernel<C, TR><<<grid, kClassWarps[C] * 32, kSmemTotal, stream>>>(args);
+	sw_affine_f32_tb_kernel<C, TR><<<grid, kClassWarps[C] * 32, class_smem(C), stream>>>(args);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -567,7 +702,8 @@ int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream)
 	switch (cls) {
 	case 0: return tr ? launch_sw_ct<0, true>(args, grid, stream) : launch_sw_ct<0, false>(args, grid, stream);
 	case 1: return tr ? launch_sw_ct<1, true>(args, grid, stream) : launch_sw_ct<1, false>(args, grid, stream);
-	default: return tr ? launch_sw_ct<2, true>(args, grid, stream) : launch_sw_ct<2, false>(args, grid, stream);
+	case 2: return tr ? launch_sw_ct<2, true>(args, grid, stream) : launch_sw_ct<2, false>(args, grid, stream);
+	default: return tr ? launch_sw_ct<3, true>(args, grid, stream) : launch_sw_ct<3, false>(args, grid, stream);
 	}
 }
 
