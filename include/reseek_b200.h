@@ -133,7 +133,7 @@ typedef struct rsk_stats {
 	float lddt_kernel_ms;
 	float total_ms;          /* device time of the whole call on the context stream */
 	float mkf_kernel_ms;     /* long-chain path kernels */
-	uint32_t reserved;
+	uint32_t sw_kernel_launches; /* launches of the SW kernel (one per batch and row-length class) */
 	uint64_t mkf_pairs;      /* pairs that took the k-mer / x-drop path (DoMKF) */
 } rsk_stats;
 

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <numeric>
 #include <thread>
 #include <string>
@@ -33,15 +34,68 @@ int rsk_fail(int code, const char *fmt, ...)
 	return code;
 }
 
+// Large host blocks (hit arrays, path pools) are recycled through a small process-wide cache: a 10^7-hit result is
+// ~1 GB, and handing such blocks back to the OS and faulting fresh ones in on every search call costs more host time
+// than converting the records.
+namespace {
+struct HostBlockCache {
+	static constexpr size_t kMinBytes = (size_t)16 << 20, kMaxBlocks = 6, kMaxTotal = (size_t)6 << 30;
+	std::mutex mu;
+	std::vector<std::pair<void *, size_t>> blocks;
+	size_t total = 0;
+	void *get(size_t bytes, size_t &cap)
+	{
+		if (bytes >= kMinBytes) {
+			std::lock_guard<std::mutex> g(mu);
+			int best = -1;
+			for (int k = 0; k < (int)blocks.size(); ++k)
+				if (blocks[k].second >= bytes && blocks[k].second <= 2 * bytes + kMinBytes && (best < 0 || blocks[k].second < blocks[best].second))
+					best = k;
+			if (best >= 0) {
+				void *p = blocks[best].first;
+				cap = blocks[best].second;
+				total -= cap;
+				blocks.erase(blocks.begin() + best);
+				return p;
+			}
+		}
+		cap = std::max<size_t>(bytes, 64);
+		return malloc(cap);
+	}
+	void put(void *p, size_t cap)
+	{
+		if (!p)
+			return;
+		if (cap >= kMinBytes) {
+			std::lock_guard<std::mutex> g(mu);
+			if (blocks.size() < kMaxBlocks && total + cap <= kMaxTotal) {
+				blocks.push_back({p, cap});
+				total += cap;
+				return;
+			}
+		}
+		free(p);
+	}
+	~HostBlockCache()
+	{
+		for (auto &b : blocks)
+			free(b.first);
+	}
+};
+HostBlockCache g_blocks;
+}  // namespace
+
 struct rsk_results {
-	rsk_hit *hits = nullptr;   // malloc'ed, never value-initialised (filled by the conversion workers)
+	rsk_hit *hits = nullptr;   // never value-initialised (filled by the conversion workers)
 	uint64_t nhits = 0;
+	size_t hits_cap = 0;       // bytes
 	char *paths = nullptr;
 	uint64_t npath = 0;
+	size_t paths_cap = 0;      // bytes
 	~rsk_results()
 	{
-		free(hits);
-		free(paths);
+		g_blocks.put(hits, hits_cap);
+		g_blocks.put(paths, paths_cap);
 	}
 };
 
@@ -277,7 +331,7 @@ extern "C" void rsk_chainset_free(rsk_chainset *cs)
 		return;
 	cudaSetDevice(cs->device);
 	DevChains &d = cs->d;
-	cudaFree(d.len); cudaFree(d.off); cudaFree(d.prof8); cudaFree(d.mu); cudaFree(d.coloff);
+	cudaFree(d.len); cudaFree(d.off); cudaFree(d.prof8); cudaFree(d.mu);
 	cudaFree(d.x); cudaFree(d.y); cudaFree(d.z); cudaFree(d.selfrev);
 	delete cs;
 }
@@ -421,23 +475,6 @@ int ensure_scratch(rsk_ctx *ctx, uint32_t maxRow, uint32_t maxCol, int &grid, ui
 	return RSK_OK;
 }
 
-int ensure_coloff(rsk_ctx *ctx, const rsk_chainset *Cs)
-{
-	if (Cs->d.coloff)
-		return RSK_OK;
-	// first use of this set as the column side: derive the per-residue table offsets (32 B/residue)
-	rsk_chainset *Cm = const_cast<rsk_chainset *>(Cs);
-	if (cudaMalloc((void **)&Cm->d.coloff, (size_t)Cs->d.total * 32) != cudaSuccess) {
-		cudaGetLastError();
-		return fail(RSK_ERR_NOMEM, "column-offset table for %llu residues", (unsigned long long)Cs->d.total);
-	}
-	int nl = launch_make_coloff(Cs->d.prof8, Cs->d.total, Cm->d.coloff, ctx->stream);
-	if (nl < 0)
-		return fail(RSK_ERR_CUDA, "make_coloff launch failed");
-	ctx->stats.kernel_launches += nl;
-	return RSK_OK;
-}
-
 template <typename T>
 int upload_vec(rsk_ctx *ctx, DevBuf<T> &dst, const std::vector<T> &src)
 {
@@ -559,8 +596,6 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	uint32_t bnd_pass_stride, stage_stride;
 	int rc = ensure_scratch(ctx, maxRow, maxCol, grid, ckpt_stride, bnd_stride, bnd_pass_stride, stage_stride);
 	if (rc)
-		return rc;
-	if ((rc = ensure_coloff(ctx, Cl)))
 		return rc;
 	if (ctx->rec.ensure(b.npairs) || ctx->pool.ensure((size_t)b.pool_bound + 64)) {
 		cudaGetLastError();
@@ -722,7 +757,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	SwArgs sa;
 	memset(&sa, 0, sizeof(sa));
 	sa.prof_row = Rw->d.prof8; sa.off_row = Rw->d.off; sa.len_row = Rw->d.len;
-	sa.coloff_col = Cl->d.coloff; sa.off_col = Cl->d.off; sa.len_col = Cl->d.len;
+	sa.prof_col = Cl->d.prof8; sa.off_col = Cl->d.off; sa.len_col = Cl->d.len;
 	sa.tr = tr ? 1 : 0;
 	sa.a_begin = b.a0; sa.nB = B->d.n;
 	sa.ckpt = ctx->ckpt.p; sa.ckpt_stride = ckpt_stride;
@@ -775,6 +810,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		if (nl < 0)
 			return fail(RSK_ERR_CUDA, "SW kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->stats.kernel_launches += nl;
+		ctx->stats.sw_kernel_launches += (uint32_t)nl;
 	}
 	CK(cudaEventRecord(ctx->ev[1], st));
 
@@ -856,9 +892,10 @@ void fill_hit(const rsk_params &P, const PairRec &r, uint32_t a, uint32_t b, uin
 	if (r.flags & RSK_HIT_HAS_EVALUE) {
 		h.hi_a = r.hi_a; h.hi_b = r.hi_b; h.ids = r.ids; h.gaps = r.gaps;
 		h.lddt = r.lddt; h.ts = r.ts;
-		h.pvalue = (float)rsk_pvalue(r.ts);   // dssaligner.cpp:891-893: (float) of the double result
+		const double P = rsk_pvalue(r.ts);    // dssaligner.cpp:891-893: (float) of the double results
+		h.pvalue = (float)P;
 		h.qual = (float)rsk_qual(r.ts);
-		h.evalue = (float)rsk_evalue(r.ts);
+		h.evalue = (float)(P * 8340);         // statsig.cpp: E = P * DBSize, the same double product as rsk_evalue()
 	} else {
 		// ClearAlign values (dssaligner.cpp:906-927)
 		h.hi_a = h.hi_b = h.ids = h.gaps = 0xffffffffu;
@@ -950,7 +987,7 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 	if (!device_only) {
 		res = new rsk_results();
 		if (keep_all) {
-			res->hits = (rsk_hit *)malloc(std::max<uint64_t>(1, plan.npairs) * sizeof(rsk_hit));
+			res->hits = (rsk_hit *)g_blocks.get(std::max<uint64_t>(1, plan.npairs) * sizeof(rsk_hit), res->hits_cap);
 			if (!res->hits) {
 				delete res;
 				return fail(RSK_ERR_NOMEM, "host memory for %llu hit records", (unsigned long long)plan.npairs);
@@ -960,43 +997,97 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 	}
 
 	// Host conversion jobs (PairRec -> rsk_hit incl. the libm P/E/Qual of statsig.cpp) run on worker threads while the
-	// next batch occupies the GPU.  Hits of RSK_KEEP_HITS and the path bytes are collected as chunks and concatenated once.
+	// next batch occupies the GPU.  Path bytes go straight from the pinned staging pool to their final place; the hits of
+	// RSK_KEEP_HITS are gathered per worker and appended to the result array when the job is collected (also overlapped,
+	// except for the last batch).
 	struct Job {
 		std::vector<std::thread> threads;
 		std::vector<std::vector<rsk_hit>> kept;  // per thread (KEEP_HITS)
 		std::vector<uint64_t> n_eval, n_hit, n_rej;
-		char *paths = nullptr;
-		uint64_t npath = 0;
+		size_t npairs = 0;
 		bool active = false;
 	};
 	Job jobs[2];
-	std::vector<std::vector<rsk_hit>> hit_chunks;
-	std::vector<std::pair<char *, uint64_t>> path_chunks;
+	double keep_ratio = (ctx->params.omega > 0) ? 0.02 : 1.0;  // expected share of reported pairs, refined per batch
+	uint64_t batches_left = batches.size();
+	bool nomem = false;
+	auto parallel_copy = [&](char *dst, const char *src, size_t bytes) {
+		const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->host_threads, bytes >> 22));
+		if (T == 1) {
+			memcpy(dst, src, bytes);
+			return;
+		}
+		std::vector<std::thread> th;
+		for (int t = 0; t < T; ++t)
+			th.emplace_back([=]() {
+				const size_t b0 = bytes * (size_t)t / T, b1 = bytes * (size_t)(t + 1) / T;
+				memcpy(dst + b0, src + b0, b1 - b0);
+			});
+		for (auto &t : th)
+			t.join();
+	};
+	// grow-only result storage; growing moves the block, so no worker may be writing into it at that moment
+	auto ensure_hits = [&](uint64_t need, uint64_t hint) -> bool {
+		if (need * sizeof(rsk_hit) <= res->hits_cap)
+			return true;
+		size_t cap = 0;
+		const uint64_t want = std::max<uint64_t>(std::max<uint64_t>(need, hint), 2 * (res->hits_cap / sizeof(rsk_hit)));
+		rsk_hit *nh = (rsk_hit *)g_blocks.get(want * sizeof(rsk_hit), cap);
+		if (!nh)
+			return false;
+		if (res->nhits)
+			parallel_copy((char *)nh, (const char *)res->hits, res->nhits * sizeof(rsk_hit));
+		g_blocks.put(res->hits, res->hits_cap);
+		res->hits = nh;
+		res->hits_cap = cap;
+		return true;
+	};
 	auto wait_job = [&](Job &J) {
 		if (!J.active)
 			return;
 		for (auto &t : J.threads)
 			t.join();
 		J.threads.clear();
+		uint64_t kept_n = 0;
 		for (size_t t = 0; t < J.n_eval.size(); ++t) {
 			S.evalue_pairs += J.n_eval[t];
 			S.hits += J.n_hit[t];
 			S.mu_filter_rejected += J.n_rej[t];
 		}
-		if (!keep_all)
-			for (auto &v : J.kept)
-				hit_chunks.push_back(std::move(v));
+		for (auto &v : J.kept)
+			kept_n += v.size();
+		--batches_left;
+		if (!keep_all) {
+			if (J.npairs)
+				keep_ratio = std::min(1.0, (double)kept_n / (double)J.npairs * 1.05 + 1e-3);
+			// capacity hint: what is there plus this batch's yield for every batch still to come
+			if (kept_n && !ensure_hits(res->nhits + kept_n, res->nhits + kept_n * (batches_left + 1) + 1024)) {
+				nomem = true;
+			} else if (kept_n) {
+				std::vector<std::thread> th;
+				uint64_t off = res->nhits;
+				for (auto &v : J.kept) {
+					if (v.empty())
+						continue;
+					rsk_hit *dst = res->hits + off;
+					const std::vector<rsk_hit> *src = &v;
+					off += v.size();
+					if (v.size() < 16384)
+						memcpy(dst, src->data(), src->size() * sizeof(rsk_hit));
+					else
+						th.emplace_back([dst, src]() { memcpy(dst, src->data(), src->size() * sizeof(rsk_hit)); });
+				}
+				for (auto &t : th)
+					t.join();
+				res->nhits = off;
+			}
+		}
 		J.kept.clear();
-		if (J.paths)
-			path_chunks.push_back({J.paths, J.npath});
-		J.paths = nullptr;
 		J.active = false;
 	};
 	auto abort_all = [&]() {
 		wait_job(jobs[0]);
 		wait_job(jobs[1]);
-		for (auto &pc : path_chunks)
-			free(pc.first);
 		delete res;
 	};
 
@@ -1026,7 +1117,8 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			b.ntasks = (uint32_t)t_a.size();
 			if (ctx->blist.ensure(n) || ctx->bslot.ensure(n) || ctx->pair_a.ensure(n) || ctx->pair_b.ensure(n) ||
 				ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks)) {
-				abort_all();
+				if (!device_only)
+					abort_all();
 				return fail(RSK_ERR_NOMEM, "task buffers");
 			}
 			CK(cudaMemcpyAsync(ctx->blist.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
@@ -1054,6 +1146,10 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		// the GPU is busy with this batch: now make sure the host buffer we are about to overwrite is free
 		Job &J = jobs[buf];
 		wait_job(J);
+		if (nomem) {
+			abort_all();
+			return fail(RSK_ERR_NOMEM, "host memory for the hit records");
+		}
 		// ---- D2H: records (+ paths) of this batch ----
 		if (ctx->h_rec[buf].ensure(b.npairs)) {
 			abort_all();
@@ -1074,7 +1170,25 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			CK(cudaMemcpyAsync(ctx->h_pool[buf].p, ctx->pool.p, pool_used, cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
 			S.d2h_bytes += pool_used;
+			if (pool_total + pool_used > res->paths_cap) {
+				// grow the path pool (rare: the first batch sizes it for the whole call); nobody may be writing into it
+				wait_job(jobs[buf ^ 1]);
+				size_t cap = 0;
+				const uint64_t want = std::max<uint64_t>(pool_total + pool_used * (batches.size() - (bi - 1)) + (pool_used >> 3) + 4096,
+						2 * (uint64_t)res->paths_cap);
+				char *np = (char *)g_blocks.get(want, cap);
+				if (!np) {
+					abort_all();
+					return fail(RSK_ERR_NOMEM, "host memory for %llu path bytes", (unsigned long long)want);
+				}
+				if (pool_total)
+					parallel_copy(np, res->paths, pool_total);
+				g_blocks.put(res->paths, res->paths_cap);
+				res->paths = np;
+				res->paths_cap = cap;
+			}
 			pool_total += pool_used;
+			res->npath = pool_total;
 		}
 		rc = finish_batch_timing(ctx);
 		if (rc) {
@@ -1084,25 +1198,29 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		// ---- records -> rsk_hit on worker threads (overlaps the next batch's kernels) ----
 		const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->host_threads, b.npairs / 4096 + 1));
 		J.active = true;
+		J.npairs = b.npairs;
 		J.kept.assign(T, {});
 		J.n_eval.assign(T, 0); J.n_hit.assign(T, 0); J.n_rej.assign(T, 0);
-		J.npath = copy_paths ? pool_used : 0;
-		J.paths = copy_paths ? (char *)malloc(pool_used) : nullptr;
 		const PairRec *hrec = ctx->h_rec[buf].p;
 		const uint8_t *hpool = ctx->h_pool[buf].p;
+		char *path_dst = copy_paths ? res->paths + pool_base : nullptr;
+		const uint64_t npath = copy_paths ? pool_used : 0;
 		const rsk_params *P = &ctx->params;
 		const uint32_t nB = B->d.n;
 		rsk_hit *all = keep_all ? res->hits : nullptr;
 		const SearchPlan *pl = &plan;
+		const double ratio = keep_ratio;
 		for (int t = 0; t < T; ++t) {
 			J.threads.emplace_back([=, &J]() {
 				const size_t k0 = b.npairs * (size_t)t / T, k1 = b.npairs * (size_t)(t + 1) / T;
-				if (J.paths) {  // path bytes: each worker copies its share of the pinned pool
-					const uint64_t p0 = J.npath * (uint64_t)t / T, p1 = J.npath * (uint64_t)(t + 1) / T;
-					memcpy(J.paths + p0, hpool + p0, p1 - p0);
+				if (path_dst) {  // path bytes: each worker copies its share of the pinned pool to its final place
+					const uint64_t p0 = npath * (uint64_t)t / T, p1 = npath * (uint64_t)(t + 1) / T;
+					memcpy(path_dst + p0, hpool + p0, p1 - p0);
 				}
 				uint64_t ne = 0, nh = 0, nr = 0;
 				std::vector<rsk_hit> &kept = J.kept[t];
+				if (!all)
+					kept.reserve((size_t)((double)(k1 - k0) * ratio) + 64);
 				for (size_t k = k0; k < k1; ++k) {
 					uint32_t a, bb;
 					uint64_t orig;
@@ -1130,51 +1248,12 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		}
 	}
 	if (!device_only) {
-		// explicit-mode KEEP_HITS chunks arrive in sorted-pair order; cross-mode chunks in (a, b) order
+		// explicit-mode KEEP_HITS hits arrive in sorted-pair order; cross-mode hits in (a, b) order
 		wait_job(jobs[bi & 1]);
 		wait_job(jobs[(bi + 1) & 1]);
-		if (!keep_all) {
-			uint64_t n = 0;
-			for (auto &c : hit_chunks)
-				n += c.size();
-			res->hits = (rsk_hit *)malloc(std::max<uint64_t>(1, n) * sizeof(rsk_hit));
-			res->nhits = n;
-			if (!res->hits) {
-				abort_all();
-				return fail(RSK_ERR_NOMEM, "host memory for %llu hits", (unsigned long long)n);
-			}
-			std::vector<std::thread> cp;
-			uint64_t off = 0;
-			for (auto &c : hit_chunks) {
-				if (!c.empty()) {
-					rsk_hit *dst = res->hits + off;
-					const std::vector<rsk_hit> *src = &c;
-					cp.emplace_back([dst, src]() { memcpy(dst, src->data(), src->size() * sizeof(rsk_hit)); });
-					if ((int)cp.size() >= ctx->host_threads) {
-						for (auto &t : cp) t.join();
-						cp.clear();
-					}
-				}
-				off += c.size();
-			}
-			for (auto &t : cp) t.join();
-		}
-		uint64_t np = 0;
-		for (auto &pc : path_chunks)
-			np += pc.second;
-		if (np) {
-			if (path_chunks.size() == 1) {
-				res->paths = path_chunks[0].first;
-			} else {
-				res->paths = (char *)malloc(np);
-				uint64_t off = 0;
-				for (auto &pc : path_chunks) {
-					memcpy(res->paths + off, pc.first, pc.second);
-					off += pc.second;
-					free(pc.first);
-				}
-			}
-			res->npath = np;
+		if (nomem) {
+			delete res;
+			return fail(RSK_ERR_NOMEM, "host memory for the hit records");
 		}
 	}
 	CK(cudaEventRecord(ctx->ev[7], st));

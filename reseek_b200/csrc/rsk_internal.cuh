@@ -26,7 +26,6 @@ struct DevChains {
 	uint32_t *len = nullptr;    // [n]
 	uint64_t *off = nullptr;    // [n] residue offset of each chain
 	uint64_t *prof8 = nullptr;  // [total] 8 e-letter bytes per residue (byte f = feature f)
-	uint4 *coloff = nullptr;    // [2*total] per-residue row-table offsets (made on first use as the column side)
 	uint8_t *mu = nullptr;      // [total] or null
 	float *x = nullptr, *y = nullptr, *z = nullptr;  // [total] each
 	float *selfrev = nullptr;   // [n]
@@ -63,7 +62,7 @@ constexpr int kSwClasses = 4;
 #define RSK_CLASS_W2 16
 #endif
 #ifndef RSK_CLASS_W3
-#define RSK_CLASS_W3 16
+#define RSK_CLASS_W3 20
 #endif
 constexpr int kClassWarps[kSwClasses] = {RSK_CLASS_W0, RSK_CLASS_W1, RSK_CLASS_W2, RSK_CLASS_W3};
 constexpr int kSwMaxWarps = RSK_CLASS_W0 > 20 ? RSK_CLASS_W0 : 20;
@@ -88,7 +87,7 @@ __host__ __device__ inline int sw_class_of_len(uint32_t L)
 // K1 arguments.  "row"/"col" are the kernel's view; tr says which reference slot supplies the rows.
 struct SwArgs {
 	const uint64_t *prof_row; const uint64_t *off_row; const uint32_t *len_row;
-	const uint4 *coloff_col; const uint64_t *off_col; const uint32_t *len_col;
+	const uint64_t *prof_col; const uint64_t *off_col; const uint32_t *len_col;
 	uint32_t tr;             // 0: rows = reference A (DSSAligner query slot), 1: rows = reference B
 	// tasks: one task = one row chain x up to W column chains (W = warps of the kernel class)
 	uint32_t ntasks;
@@ -247,7 +246,6 @@ int pf_segmented_sort(const uint32_t *kin, uint32_t *kout, unsigned long long n,
 int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();
 uint64_t sw_ckpt_units(int npass, uint32_t LB);
-int launch_make_coloff(const uint64_t *prof8, uint64_t total, uint4 *coloff, cudaStream_t stream);
 int launch_lddt(const LddtArgs &args, cudaStream_t stream);
 int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);
 size_t mu_smem_bytes();

@@ -10,9 +10,9 @@
 //    memory for the current pass of 32*R rows (R = 1..12 rows per lane): plane 0 holds rows 0..3 of every lane
 //    as float4 P0[e][lane], plane 1 rows 4..7, plane 2 rows 8..11 (float/float2/float4 by need), e =
 //    (feature,letter) code 0..131, 512-byte stride per code.  A lane's vector sits in its own bank group, so
-//    every LDS is conflict-free.  The column chain supplies, per DP column, 8 ready-made table offsets
-//    (32 bytes, prepared once per chain set), so a cell's score costs 8 table reads + 7 fp32 adds in the
-//    reference's order.
+//    every LDS is conflict-free.  The column chain supplies, per DP column, its 8 e-letter bytes (one 64-bit
+//    load; a PRMT + IMAD per feature turns a byte into a table address), so a cell's score costs 8 table
+//    reads + 7 fp32 adds in the reference's order.
 //  * DP wavefront: lane L owns R consecutive rows, lanes are skewed by one column per step, the last row's
 //    (M,D) travels to the next lane by warp shuffle.  A chain longer than 32*12 rows is cut into passes; the
 //    bottom row of a pass is parked in a small global (L2-resident) boundary row per pass.
@@ -133,7 +133,7 @@ __host__ __device__ constexpr int ckpt_words(int R) { return (2 * R + 3 + 3) / 4
 //                  and tracks the lane's first maximum (lbest, lbi, lbj in kernel coordinates).
 //   TRACE = true : re-run of strip `strip` (steps kStrip*strip .. s_last) from its checkpoint, writing one 64-bit
 //                  trace word per lane and step (4 bits per row) into `tile[(step % kStrip)*32 + lane]`.
-// colB: two uint4 per column = the column's 8 table offsets in units of 16 bytes (code * 32).
+// colB: the column chain's residues, 8 e-letter bytes each (DevChains::prof8).
 // TR = false: kernel rows are the reference's A chain (index i), columns its B chain (j).
 // TR = true : rows are the reference's B chain, columns its A chain.  The recurrence is the same with the
 //             roles of the two gap states exchanged: the reference tests D (gap that consumes A) before I
@@ -141,7 +141,7 @@ __host__ __device__ constexpr int ckpt_words(int R) { return (2 * R + 3 + 3) / 4
 // bnd_in / bnd_out: boundary row written by the previous pass / to be written by this one.
 template <int R, bool TR, bool TRACE>
 __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int lane, const bool first, const bool last,
-		const uint32_t row0, const uint32_t LA, const uint4 *__restrict__ colB, const int LB,
+		const uint32_t row0, const uint32_t LA, const uint64_t *__restrict__ colB, const int LB,
 		const float2 *__restrict__ bnd_in, float2 *__restrict__ bnd_out, float4 *__restrict__ ck, const float open,
 		const float ext, float &lbest, int &lbi, int &lbj, const int strip, const int s_last,
 		unsigned long long *__restrict__ tile)
@@ -213,11 +213,9 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 		load(strip);
 		j = kStrip * strip - lane;
 	}
-	uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-	if (j >= 0 && j < LB) {
-		c0 = __ldg(colB + 2 * j);
-		c1 = __ldg(colB + 2 * j + 1);
-	}
+	uint64_t cv = 0;
+	if (j >= 0 && j < LB)
+		cv = __ldg(colB + j);
 	float2 bn = make_float2(kNegInf, kNegInf);
 	if (use_bnd && j < LB)
 		bn = bnd_in[j];
@@ -228,11 +226,9 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 		const float inM = __shfl_up_sync(kFull, outM, 1);
 		const float inD = __shfl_up_sync(kFull, outD, 1);
 		const int jn = j + 1;
-		uint4 n0 = c0, n1 = c1;
-		if (!CHECK || (jn >= 0 && jn < LB)) {
-			n0 = __ldg(colB + 2 * jn);
-			n1 = __ldg(colB + 2 * jn + 1);
-		}
+		uint64_t cn = cv;
+		if (!CHECK || (jn >= 0 && jn < LB))
+			cn = __ldg(colB + jn);
 		float2 bn_next = bn;
 		if (use_bnd && (!CHECK || jn < LB))
 			bn_next = bnd_in[jn];
@@ -241,11 +237,15 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 			float d = lane0 ? bn.y : inD;  // D[i0][j]   (bn = -inf pair in the first pass)
 			const float mdiag = mdiag_next;  // M[i0][j]
 			mdiag_next = lane0 ? bn.x : inM;  // M[i0][j+1]
-			const uint32_t co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+			const uint32_t clo = (uint32_t)cv, chi = (uint32_t)(cv >> 32);
+			uint32_t co[8];  // e-letter of each feature
+#pragma unroll
+			for (int f = 0; f < RSK_NFEAT; ++f)
+				co[f] = __byte_perm(f < 4 ? clo : chi, 0u, 0x4440u | (uint32_t)(f & 3));
 			float S[R];
 #pragma unroll
 			for (int f = 0; f < RSK_NFEAT; ++f) {
-				const uint32_t a0 = co[f] * 16u + base0;
+				const uint32_t a0 = co[f] * 512u + base0;
 				const float4 v0 = *reinterpret_cast<const float4 *>(plane0 + a0);
 				float v[12];
 				v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
@@ -253,18 +253,18 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 				for (int r = 4; r < 12; ++r)
 					v[r] = 0.0f;
 				if (W1 == 1) {
-					v[4] = *reinterpret_cast<const float *>(plane1 + (co[f] * 16u + base1));
+					v[4] = *reinterpret_cast<const float *>(plane1 + (co[f] * 512u + base1));
 				} else if (W1 == 2) {
-					const float2 t = *reinterpret_cast<const float2 *>(plane1 + (co[f] * 16u + base1));
+					const float2 t = *reinterpret_cast<const float2 *>(plane1 + (co[f] * 512u + base1));
 					v[4] = t.x; v[5] = t.y;
 				} else if (W1 == 4) {
 					const float4 t = *reinterpret_cast<const float4 *>(plane1 + a0);
 					v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w;
 				}
 				if (W2 == 1) {
-					v[8] = *reinterpret_cast<const float *>(plane2 + (co[f] * 16u + base2));
+					v[8] = *reinterpret_cast<const float *>(plane2 + (co[f] * 512u + base2));
 				} else if (W2 == 2) {
-					const float2 t = *reinterpret_cast<const float2 *>(plane2 + (co[f] * 16u + base2));
+					const float2 t = *reinterpret_cast<const float2 *>(plane2 + (co[f] * 512u + base2));
 					v[8] = t.x; v[9] = t.y;
 				} else if (W2 == 4) {
 					const float4 t = *reinterpret_cast<const float4 *>(plane2 + a0);
@@ -364,8 +364,7 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 			}
 		}
 		j = jn;
-		c0 = n0;
-		c1 = n1;
+		cv = cn;
 		bn = bn_next;
 		return (unsigned long long)tw0 | ((unsigned long long)tw1 << 32);
 	};
@@ -410,7 +409,7 @@ struct TbState {
 // complete, false when it continues in the pass above.
 template <int R, bool TR>
 __device__ __forceinline__ bool traceback_in_pass(const unsigned char *smem_p0, const int lane, const int pass, const int npass,
-		const uint32_t LA, const uint4 *__restrict__ colB, const int LB, float2 *__restrict__ bnd, const uint32_t bnd_pass_stride,
+		const uint32_t LA, const uint64_t *__restrict__ colB, const int LB, float2 *__restrict__ bnd, const uint32_t bnd_pass_stride,
 		float4 *__restrict__ ck, const int nstrips, const float open, const float ext, unsigned long long *__restrict__ tile,
 		uint8_t *__restrict__ stage, TbState &t)
 {
@@ -496,7 +495,7 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 	const bool have = (uint32_t)warp < cnt;
 	uint32_t cidx = 0, slot = 0;
 	int LB = 0;  // kernel columns
-	const uint4 *colB = nullptr;
+	const uint64_t *colB = nullptr;
 	if (have) {
 		cidx = a.clist[begin + warp];
 		if (a.cross) {
@@ -506,7 +505,7 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 			slot = a.cslot[begin + warp];
 		}
 		LB = (int)a.len_col[cidx];
-		colB = a.coloff_col + 2 * a.off_col[cidx];
+		colB = a.prof_col + a.off_col[cidx];
 	}
 	const int nstrips = (((LB + 31 + 3) >> 2) + kStrip / 4 - 1) / (kStrip / 4);
 	const size_t gw = (size_t)blockIdx.x * W + warp;
@@ -661,21 +660,6 @@ __global__ void pack_profiles_kernel(const uint8_t *__restrict__ planes, uint64_
 	prof8[i] = v;
 }
 
-// e-letters -> per-column row-table offsets in units of 16 bytes (code * 512 bytes / 16)
-__global__ void make_coloff_kernel(const uint64_t *__restrict__ prof8, uint64_t total, uint4 *__restrict__ coloff)
-{
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= total)
-		return;
-	const uint64_t v = prof8[i];
-	uint32_t o[8];
-#pragma unroll
-	for (int f = 0; f < 8; ++f)
-		o[f] = (uint32_t)((v >> (8 * f)) & 0xff) * 32u;
-	coloff[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
-	coloff[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
-}
-
 }  // namespace
 
 size_t sw_smem_bytes() { return class_smem(kSwClasses - 1); }
@@ -714,16 +698,6 @@ int launch_pack_profiles(const uint8_t *planes, uint64_t total, uint64_t *prof8,
 	const int threads = 256;
 	const unsigned blocks = (unsigned)((total + threads - 1) / threads);
 	pack_profiles_kernel<<<blocks, threads, 0, stream>>>(planes, total, prof8);
-	return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-int launch_make_coloff(const uint64_t *prof8, uint64_t total, uint4 *coloff, cudaStream_t stream)
-{
-	if (total == 0)
-		return 0;
-	const int threads = 256;
-	const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-	make_coloff_kernel<<<blocks, threads, 0, stream>>>(prof8, total, coloff);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -52,7 +52,7 @@ class Stats(C.Structure):
                 ("evalue_pairs", C.c_uint64), ("hits", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sw_kernel_ms", C.c_float),
                 ("mu_kernel_ms", C.c_float), ("lddt_kernel_ms", C.c_float), ("total_ms", C.c_float),
-                ("mkf_kernel_ms", C.c_float), ("reserved", C.c_uint32), ("mkf_pairs", C.c_uint64)]
+                ("mkf_kernel_ms", C.c_float), ("sw_kernel_launches", C.c_uint32), ("mkf_pairs", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
