@@ -1,0 +1,339 @@
+// dbsearcher.cpp - DBSearcher look-alike and the `-fast -db` drivers over the C ABI (see dbsearcher.h).
+#include "dbsearcher.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+namespace reseek_b200 {
+
+static void Check(int rc)
+	{
+	if (rc != RSK_OK)
+		Die("reseek_b200: %s", rsk_last_error());
+	}
+
+bool VectorChainSource::GetNext(ChainData &CD)
+	{
+	if (m_Next >= m_Chains->size())
+		return false;
+	CD = (*m_Chains)[m_Next++];
+	return true;
+	}
+
+// dbsearcher.cpp:12-22
+DBSearcher::~DBSearcher()
+	{
+	for (DSSAligner *DA : m_DAs)
+		delete DA;
+	rsk_chainset_free(m_DBSet);
+	if (m_Ctx != 0)
+		rsk_ctx_destroy(m_Ctx);
+	if (m_OwnsChains)
+		{
+		for (PDBChain *C : m_DBChains) delete C;
+		for (auto *P : m_DBProfiles) delete P;
+		for (auto *M : m_DBMuLettersVec) delete M;
+		for (auto *K : m_DBMuKmersVec) delete K;
+		}
+	}
+
+rsk_ctx *DBSearcher::GetContext()
+	{
+	if (m_Ctx != 0)
+		return m_Ctx;
+	rsk_asserta(m_Params != 0);
+	rsk_params R;
+	m_Params->ToRsk(R, m_MaxEvalue);
+	Check(rsk_ctx_create(m_Device, &R, 0, &m_Ctx));  // Die()s when there is no CUDA device: no CPU fallback
+	return m_Ctx;
+	}
+
+// dbsearcher.cpp:73-121.  -evalue is not visible here: set m_MaxEvalue before Setup() to override the default.
+void DBSearcher::Setup()
+	{
+	rsk_asserta(m_Params != 0);
+	rsk_asserta(m_DAs.empty());
+	if (m_MaxEvalue == 10 && m_Params->m_Mode == AM_VerySensitive)
+		m_MaxEvalue = DBL_MAX;
+	m_ProcessedQueryCount = 0;
+	m_ProcessedPairCount = 0;
+	m_HitCount = 0;
+	m_ThreadCount = 1;  // one GPU context replaces the reference's pool of per-thread aligners
+	DSSAligner *DA = new DSSAligner;
+	DA->SetParams(*m_Params);
+	DA->UseContext(GetContext());
+	m_DAs.push_back(DA);
+	OnSetup();
+	}
+
+void DBSearcher::AddChain(PDBChain *ptrChain, vector<vector<byte> > *ptrProfile, vector<byte> *ptrMuLetters)
+	{
+	m_DBChains.push_back(ptrChain);
+	m_DBProfiles.push_back(ptrProfile);
+	m_DBMuLettersVec.push_back(ptrMuLetters);
+	}
+
+ChainData DBSearcher::GetDBChainData(uint Idx) const
+	{
+	ChainData CD;
+	CD.Chain = m_DBChains[Idx];
+	CD.Profile = m_DBProfiles[Idx];
+	CD.MuLetters = m_DBMuLettersVec.empty() ? 0 : m_DBMuLettersVec[Idx];
+	CD.SelfRevScore = m_DBSelfRevScores.empty() ? FLT_MAX : m_DBSelfRevScores[Idx];
+	return CD;
+	}
+
+void DBSearcher::UploadDB()
+	{
+	if (m_DBSet != 0)
+		return;
+	const uint N = GetDBChainCount();
+	if (N == 0)
+		Die("DBSearcher: empty database");
+	rsk_asserta(RSK_SIZE(m_DBProfiles) == N);
+	vector<ChainData> Chains(N);
+	for (uint i = 0; i < N; ++i)
+		Chains[i] = GetDBChainData(i);
+	m_DBSet = UploadChains(GetContext(), Chains, !m_DBMuLettersVec.empty());
+	}
+
+void DBSearcher::AddStats()
+	{
+	Check(rsk_ctx_stats(m_Ctx, &m_LastStats));
+	const rsk_stats &S = m_LastStats;
+	DSSAligner::m_AlnCount += (uint)S.pairs;
+	DSSAligner::m_SWCount += (uint)S.sw_pairs;
+	DSSAligner::m_MuFilterInputCount += (uint)S.mu_filter_in;
+	DSSAligner::m_MuFilterDiscardCount += (uint)S.mu_filter_rejected;
+	DSSAligner::m_ParasailSaturateCount += (uint)S.mu_saturated;
+	DSSAligner::m_XDropAlnCount += (uint)S.mkf_pairs;
+	m_ProcessedPairCount += (uint)S.pairs;
+	}
+
+// dbsearcher.cpp:258-265 (-mints / -scores_are_not_evalues are command-line switches of the reference)
+bool DBSearcher::Reject(DSSAligner &DA, bool Up) const
+	{
+	if (DA.GetEvalue(Up) > m_MaxEvalue)
+		return true;
+	return false;
+	}
+
+// dbsearcher.cpp:267-278
+void DBSearcher::BaseOnAln(DSSAligner &DA, bool Up)
+	{
+	if (Reject(DA, Up))
+		return;
+	m_Lock.lock();
+	++m_HitCount;
+	DA.ToTsvColumns(m_fTsv, Up, m_Columns);
+	OnAln(DA, Up);
+	m_Lock.unlock();
+	}
+
+// runself.cpp:72-145: pairs (i, j >= i), A = chain i, B = chain j, both directions emitted (runself.cpp:60-66)
+void DBSearcher::RunSelf()
+	{
+	rsk_asserta(!m_DAs.empty());
+	DSSAligner &DA = *m_DAs[0];
+	DA.SetParams(*m_Params);
+	time_t t_start = time(0);
+	rsk_ctx *C = GetContext();
+	rsk_params R;
+	m_Params->ToRsk(R, m_MaxEvalue);
+	Check(rsk_ctx_set_params(C, &R));
+	UploadDB();
+	rsk_search_opts O;
+	memset(&O, 0, sizeof(O));
+	O.keep = RSK_KEEP_HITS;
+	O.want_paths = 1;
+	rsk_results *Res = 0;
+	Check(rsk_search_self(C, m_DBSet, &O, &Res));
+	AddStats();
+	const uint64_t N = rsk_results_count(Res);
+	const rsk_hit *Hits = rsk_results_hits(Res);
+	const char *Pool = rsk_results_paths(Res);
+	for (uint64_t k = 0; k < N; ++k)
+		{
+		const rsk_hit &H = Hits[k];
+		DA.FromHit(H, Pool, GetDBChainData(H.a), GetDBChainData(H.b));
+		if (DA.m_Path.empty())
+			continue;
+		BaseOnAln(DA, true);
+		if (H.a != H.b)
+			BaseOnAln(DA, false);
+		}
+	rsk_results_free(Res);
+	m_ProcessedQueryCount = GetDBChainCount();
+	m_Secs = (uint)(time(0) - t_start);
+	if (m_Secs == 0)
+		m_Secs = 1;
+	RunStats();
+	}
+
+// runquery.cpp:18-130: every streamed chain (A, "query" slot) against every in-memory chain (B); hits are emitted
+// with Up = false (runquery.cpp:72-73).  The stream is consumed in blocks of m_BlockChains chains.
+void DBSearcher::RunQuery(ChainSource &QCR)
+	{
+	rsk_asserta(!m_DAs.empty());
+	DSSAligner &DA = *m_DAs[0];
+	DA.SetParams(*m_Params);
+	time_t t_start = time(0);
+	rsk_ctx *C = GetContext();
+	rsk_params R;
+	m_Params->ToRsk(R, m_MaxEvalue);
+	Check(rsk_ctx_set_params(C, &R));
+	UploadDB();
+	rsk_search_opts O;
+	memset(&O, 0, sizeof(O));
+	O.keep = RSK_KEEP_HITS;
+	O.want_paths = 1;
+	const bool WithMu = !m_DBMuLettersVec.empty();
+	vector<ChainData> Block;
+	for (;;)
+		{
+		Block.clear();
+		ChainData CD;
+		while (RSK_SIZE(Block) < m_BlockChains && QCR.GetNext(CD))
+			Block.push_back(CD);
+		if (Block.empty())
+			break;
+		rsk_chainset *A = UploadChains(C, Block, WithMu);
+		rsk_results *Res = 0;
+		Check(rsk_search_cross(C, A, m_DBSet, &O, &Res));
+		AddStats();
+		const uint64_t N = rsk_results_count(Res);
+		const rsk_hit *Hits = rsk_results_hits(Res);
+		const char *Pool = rsk_results_paths(Res);
+		for (uint64_t k = 0; k < N; ++k)
+			{
+			const rsk_hit &H = Hits[k];
+			DA.FromHit(H, Pool, Block[H.a], GetDBChainData(H.b));
+			if (!DA.m_Path.empty())
+				BaseOnAln(DA, false);
+			}
+		rsk_results_free(Res);
+		rsk_chainset_free(A);
+		m_ProcessedQueryCount += RSK_SIZE(Block);
+		}
+	m_Secs = (uint)(time(0) - t_start);
+	if (m_Secs == 0)
+		m_Secs = 1;
+	RunStats();
+	}
+
+// dbsearcher.cpp:29-56
+void DBSearcher::RunStats() const
+	{
+	uint Secs = m_Secs == 0 ? 1 : m_Secs;
+	fprintf(stderr, "\n");
+	if (m_MaxEvalue == DBL_MAX)
+		fprintf(stderr, "%10u  Hits\n", (uint)m_HitCount);
+	else
+		fprintf(stderr, "%10u  Hits (max E-value %.3g)\n", (uint)m_HitCount, m_MaxEvalue);
+	if (m_ProcessedQueryCount < 100)
+		return;
+	fprintf(stderr, "%10u  DB chains\n", (uint)m_ProcessedQueryCount);
+	fprintf(stderr, "%10u  Query chains\n", GetDBChainCount());
+	fprintf(stderr, "%10.1f  Chains/sec\n", (double)m_ProcessedQueryCount / Secs);
+	fprintf(stderr, "%10.3g  Comparisons/sec\n", (double)m_ProcessedPairCount / Secs);
+	DSSAligner::Stats();
+	}
+
+// ---- `-search Q -db DB -fast` (search.cpp:76-111) ----
+void MuPreFilter(const DSSParams &Params, const vector<ChainData> &Query, const vector<ChainData> &DB,
+  const string &OutputFN, int Device)
+	{
+	rsk_params R;
+	Params.ToRsk(R, 10);
+	rsk_ctx *C = 0;
+	Check(rsk_ctx_create(Device, &R, 0, &C));
+	rsk_chainset *Q = UploadChains(C, Query, true);
+	rsk_chainset *T = UploadChains(C, DB, true);
+	rsk_prefilter_opts PO;
+	memset(&PO, 0, sizeof(PO));
+	rsk_prefilter_result *PR = 0;
+	Check(rsk_prefilter(C, Q, T, &PO, &PR));
+	long long n = rsk_prefilter_to_tsv(PR, 0, 0);
+	vector<char> Buf((size_t)(-n) + 1);
+	n = rsk_prefilter_to_tsv(PR, Buf.data(), Buf.size());
+	if (n < 0)
+		Die("rsk_prefilter_to_tsv failed");
+	FILE *f = fopen(OutputFN.c_str(), "w");
+	if (f == 0)
+		Die("Cannot create %s", OutputFN.c_str());
+	fwrite(Buf.data(), 1, (size_t)n, f);
+	fclose(f);
+	rsk_prefilter_free(PR);
+	rsk_chainset_free(Q);
+	rsk_chainset_free(T);
+	rsk_ctx_destroy(C);
+	}
+
+// postmufilter.cpp:211-301; scan loop :116-208; Accept :105-114 with the default thresholds (E <= 10)
+void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const vector<ChainData> &Query,
+  const vector<ChainData> &DB, const string &HitsFN, const char *Columns, int Device)
+	{
+	FILE *fIn = fopen(MuFilterTsvFN.c_str(), "r");
+	if (fIn == 0)
+		Die("Cannot open %s", MuFilterTsvFN.c_str());
+	vector<uint32_t> ia, ib;
+	char Tag[64];
+	uint TargetCount = 0;
+	if (fscanf(fIn, "%63s %u", Tag, &TargetCount) != 2 || strcmp(Tag, "prefilter") != 0)
+		Die("%s: bad prefilter TSV header", MuFilterTsvFN.c_str());  // postmufilter.cpp:236-242
+	for (uint t = 0; t < TargetCount; ++t)
+		{
+		uint TargetIdx, FilHitCount;
+		if (fscanf(fIn, "%u %u", &TargetIdx, &FilHitCount) != 2)
+			Die("%s: truncated", MuFilterTsvFN.c_str());
+		rsk_asserta(TargetIdx < RSK_SIZE(DB));
+		for (uint k = 0; k < FilHitCount; ++k)
+			{
+			uint QueryIdx;
+			if (fscanf(fIn, "%u", &QueryIdx) != 1)
+				Die("%s: truncated", MuFilterTsvFN.c_str());
+			rsk_asserta(QueryIdx < RSK_SIZE(Query));
+			ia.push_back(QueryIdx);   // A = the query bag, B = the DB chain (postmufilter.cpp:190)
+			ib.push_back(TargetIdx);
+			}
+		}
+	fclose(fIn);
+
+	rsk_params R;
+	Params.ToRsk(R, 10);
+	rsk_ctx *C = 0;
+	Check(rsk_ctx_create(Device, &R, 0, &C));
+	rsk_chainset *Q = UploadChains(C, Query, true);
+	rsk_chainset *T = UploadChains(C, DB, true);
+	rsk_search_opts O;
+	memset(&O, 0, sizeof(O));
+	O.keep = RSK_KEEP_ALL;   // line order of the TSV, as the reference's single-threaded scan emits
+	O.want_paths = 1;
+	rsk_results *Res = 0;
+	Check(rsk_search_pairs(C, Q, T, ia.size(), ia.data(), ib.data(), &O, &Res));
+	FILE *fOut = HitsFN.empty() ? 0 : fopen(HitsFN.c_str(), "w");
+	if (!HitsFN.empty() && fOut == 0)
+		Die("Cannot create %s", HitsFN.c_str());
+	DSSAligner DA;
+	DA.SetParams(Params);
+	DA.UseContext(C);
+	const uint64_t N = rsk_results_count(Res);
+	const rsk_hit *Hits = rsk_results_hits(Res);
+	const char *Pool = rsk_results_paths(Res);
+	for (uint64_t k = 0; k < N; ++k)
+		{
+		const rsk_hit &H = Hits[k];
+		DA.FromHit(H, Pool, Query[H.a], DB[H.b]);
+		if (DA.m_EvalueA <= 10)  // Accept(): s_MaxEvalue = 10, s_MaxPvalue = -1, s_MinTS = 9e9
+			DA.ToTsvColumns(fOut, true, Columns);
+		}
+	if (fOut != 0)
+		fclose(fOut);
+	rsk_results_free(Res);
+	rsk_chainset_free(Q);
+	rsk_chainset_free(T);
+	rsk_ctx_destroy(C);
+	}
+
+}  // namespace reseek_b200

@@ -1,0 +1,107 @@
+// dbsearcher.h - DBSearcher look-alike over libreseek_b200 (reference: dbsearcher.h:14-109).
+//
+// Same public surface: the per-chain vectors (m_DBChains, m_DBProfiles, m_DBMuLettersVec, m_DBSelfRevScores),
+// m_Params, m_MaxEvalue, Setup / RunSelf / RunQuery, the virtual hooks OnSetup / OnAln and BaseOnAln / Reject.
+// The pair loops of ThreadBodySelf / ThreadBodyQuery (runself.cpp:13-70, runquery.cpp:18-80) become one
+// rsk_search_self / one rsk_search_cross per streamed block; every reported pair is then replayed through BaseOnAln
+// with a DSSAligner filled from the hit record, so subclasses (scop40bench.cpp) keep working.
+// LoadDB is not here: reading structures and running DSS is upstream of this layer; fill the vectors (AddChain).
+#pragma once
+
+#include <atomic>
+#include <mutex>
+
+#include "dssaligner.h"
+
+namespace reseek_b200 {
+
+// What ChainReader2 + DSS deliver to ThreadBodyQuery (runquery.cpp:33-43), as a pull interface:
+// GetNext returns false at the end of the stream.  The pointers in ChainData must stay valid until the next call
+// with Release = true (the searcher reads a block of chains, aligns it, then releases it).
+class ChainSource
+	{
+public:
+	virtual ~ChainSource() {}
+	virtual bool GetNext(ChainData &CD) = 0;
+	};
+
+class VectorChainSource : public ChainSource
+	{
+public:
+	const vector<ChainData> *m_Chains = 0;
+	size_t m_Next = 0;
+	explicit VectorChainSource(const vector<ChainData> &Chains) : m_Chains(&Chains) {}
+	bool GetNext(ChainData &CD) override;
+	};
+
+class DBSearcher
+	{
+public:
+	virtual ~DBSearcher();
+
+public:
+	std::mutex m_Lock;
+	const DSSParams *m_Params = 0;
+	uint m_ThreadCount = UINT_MAX;
+	vector<DSSAligner *> m_DAs;
+
+	vector<PDBChain *> m_DBChains;
+	bool m_QuerySelf = false;
+
+// Per-chain vectors [ChainIdx]
+	vector<vector<vector<byte> > *> m_DBProfiles;
+	vector<vector<byte> *> m_DBMuLettersVec;
+	vector<vector<uint> *> m_DBMuKmersVec;
+	vector<float> m_DBSelfRevScores;
+
+	std::atomic<uint> m_ProcessedQueryCount{0};
+	std::atomic<uint> m_ProcessedPairCount{0};
+	std::atomic<uint> m_HitCount{0};
+	double m_MaxEvalue = 10;
+	uint m_Secs = UINT_MAX;
+
+// where BaseOnAln writes (g_fTsv in the reference, set from -output)
+	FILE *m_fTsv = 0;
+	const char *m_Columns = 0;   // -columns, 0 = default
+	bool m_OwnsChains = false;   // the reference's destructor deletes chains/profiles (dbsearcher.cpp:12-22)
+	uint m_BlockChains = 100000; // streamed chains per device block in RunQuery
+	int m_Device = 0;
+
+public:
+	void Setup();
+	uint GetDBChainCount() const { return RSK_SIZE(m_DBChains); }
+	uint GetDBSize() const { return GetDBChainCount(); }
+	void AddChain(PDBChain *ptrChain, vector<vector<byte> > *ptrProfile, vector<byte> *ptrMuLetters);
+
+	void RunQuery(ChainSource &QCR);
+	void RunSelf();
+	void RunStats() const;
+	bool Reject(DSSAligner &DA, bool Up) const;
+
+public:
+	virtual void OnSetup() {}
+	void BaseOnAln(DSSAligner &DA, bool Up);
+	virtual void OnAln(DSSAligner &DA, bool Up) {}
+
+// shim plumbing
+	rsk_ctx *GetContext();
+	const rsk_stats &GetLastStats() const { return m_LastStats; }
+
+private:
+	rsk_ctx *m_Ctx = 0;
+	rsk_chainset *m_DBSet = 0;
+	rsk_stats m_LastStats;
+	void UploadDB();
+	ChainData GetDBChainData(uint Idx) const;
+	void AddStats();
+	};
+
+// search.cpp:76-111 (`-search Q -db DB -fast`): MuPreFilter (muprefilter.cpp:64-133) writes the candidate TSV,
+// PostMuFilter (postmufilter.cpp:211-301) aligns every listed (query, target) pair with the sensitive preset and
+// writes the hits with Up = true.  The reference passes file names for the chains; here the chains come in memory.
+void MuPreFilter(const DSSParams &Params, const vector<ChainData> &Query, const vector<ChainData> &DB,
+  const string &OutputFN, int Device = 0);
+void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const vector<ChainData> &Query,
+  const vector<ChainData> &DB, const string &HitsFN, const char *Columns = 0, int Device = 0);
+
+}  // namespace reseek_b200

@@ -1,0 +1,197 @@
+// host_driver.cpp - small command-line harness over the DSSAligner / DBSearcher look-alikes.
+// It exists for the parity tests (tests/test_host_shim.py) and as a usage example of the drop-in surface; it is not
+// the reference's CLI.  Chains are read from ".rskc" dumps (feature letters, Mu letters, coordinates: the output of
+// the reference's DSS stage, written by reseek_b200/chainio.py) because structure I/O and DSS are upstream of this layer.
+//
+//   rsk_host_demo self  <mode> <set.rskc> <out.tsv> [columns]       DBSearcher::RunSelf           (-search X)
+//   rsk_host_demo query <mode> <stream.rskc> <db.rskc> <out.tsv>    DBSearcher::RunQuery          (-search Q -db DB)
+//   rsk_host_demo pair  <mode> <set.rskc> <i> <j> <out.tsv>         DSSAligner::AlignQueryTarget  (-alignpair)
+//   rsk_host_demo fastdb <q.rskc> <db.rskc> <cands.tsv> <out.tsv>   MuPreFilter + PostMuFilter    (-search Q -db DB -fast)
+#include <stdlib.h>
+#include <string.h>
+
+#include "dbsearcher.h"
+
+using namespace reseek_b200;
+
+struct LoadedSet
+	{
+	vector<PDBChain> Chains;
+	vector<vector<vector<byte> > > Profiles;
+	vector<vector<byte> > Mus;
+	vector<vector<uint> > Kmers;   // non-empty marker vectors: the k-mers themselves are derived on the device
+	vector<float> SelfRevs;
+	vector<ChainData> Data;
+	};
+
+static void ReadOrDie(void *p, size_t n, FILE *f, const char *fn)
+	{
+	if (n != 0 && fread(p, 1, n, f) != n)
+		Die("%s: truncated", fn);
+	}
+
+static void Load(const char *fn, LoadedSet &S)
+	{
+	FILE *f = fopen(fn, "rb");
+	if (f == 0)
+		Die("Cannot open %s", fn);
+	char magic[4];
+	uint32_t ver, n, has_mu, has_sr;
+	uint64_t total;
+	ReadOrDie(magic, 4, f, fn);
+	if (memcmp(magic, "RSKC", 4) != 0)
+		Die("%s: not a .rskc file", fn);
+	ReadOrDie(&ver, 4, f, fn); ReadOrDie(&n, 4, f, fn); ReadOrDie(&total, 8, f, fn);
+	ReadOrDie(&has_mu, 4, f, fn); ReadOrDie(&has_sr, 4, f, fn);
+	vector<uint32_t> len(n);
+	ReadOrDie(len.data(), 4 * (size_t)n, f, fn);
+	vector<uint8_t> prof(8 * total), mu(has_mu ? total : 0), seq(total);
+	vector<float> xyz(3 * total), sr(n, FLT_MAX);
+	ReadOrDie(prof.data(), prof.size(), f, fn);
+	ReadOrDie(mu.data(), mu.size(), f, fn);
+	ReadOrDie(xyz.data(), 4 * xyz.size(), f, fn);
+	if (has_sr)
+		ReadOrDie(sr.data(), 4 * (size_t)n, f, fn);
+	ReadOrDie(seq.data(), total, f, fn);
+	S.Chains.resize(n); S.Profiles.resize(n); S.Mus.resize(n); S.Kmers.resize(n); S.SelfRevs = sr; S.Data.resize(n);
+	uint64_t off = 0;
+	for (uint32_t i = 0; i < n; ++i)
+		{
+		string Label;
+		for (int c; (c = fgetc(f)) > 0;)
+			Label.push_back((char)c);
+		const uint32_t L = len[i];
+		PDBChain &C = S.Chains[i];
+		C.m_Label = Label;
+		C.m_Seq.assign((const char *)&seq[off], L);
+		C.m_Xs.assign(&xyz[off], &xyz[off] + L);
+		C.m_Ys.assign(&xyz[total + off], &xyz[total + off] + L);
+		C.m_Zs.assign(&xyz[2 * total + off], &xyz[2 * total + off] + L);
+		S.Profiles[i].resize(8);
+		for (int ft = 0; ft < 8; ++ft)
+			S.Profiles[i][ft].assign(&prof[ft * total + off], &prof[ft * total + off] + L);
+		if (has_mu)
+			{
+			S.Mus[i].assign(&mu[off], &mu[off] + L);
+			S.Kmers[i].assign(L >= 3 ? L - 2 : 0, 0u);
+			}
+		off += L;
+		}
+	fclose(f);
+	for (uint32_t i = 0; i < n; ++i)
+		{
+		S.Data[i].Chain = &S.Chains[i];
+		S.Data[i].Profile = &S.Profiles[i];
+		S.Data[i].MuLetters = has_mu ? &S.Mus[i] : 0;
+		S.Data[i].SelfRevScore = S.SelfRevs[i];
+		}
+	}
+
+static ALGO_MODE ParseMode(const char *s)
+	{
+	if (!strcmp(s, "fast")) return AM_Fast;
+	if (!strcmp(s, "sensitive")) return AM_Sensitive;
+	if (!strcmp(s, "verysensitive")) return AM_VerySensitive;
+	Die("Must set -fast, -sensitive or -verysensitive");
+	}
+
+static void FillSearcher(DBSearcher &DBS, LoadedSet &S)
+	{
+	const bool HasMu = !S.Mus.empty() && S.Data[0].MuLetters != 0;
+	for (size_t i = 0; i < S.Chains.size(); ++i)
+		{
+		DBS.m_DBChains.push_back(&S.Chains[i]);
+		DBS.m_DBProfiles.push_back(&S.Profiles[i]);
+		if (HasMu)
+			{
+			DBS.m_DBMuLettersVec.push_back(&S.Mus[i]);
+			DBS.m_DBMuKmersVec.push_back(&S.Kmers[i]);
+			}
+		DBS.m_DBSelfRevScores.push_back(S.SelfRevs[i]);
+		}
+	}
+
+// an OnAln subclass in the style of scop40bench.cpp: counts what the searcher reports
+class CountingSearcher : public DBSearcher
+	{
+public:
+	uint m_OnAlnCount = 0;
+	void OnAln(DSSAligner &DA, bool Up) override { ++m_OnAlnCount; }
+	};
+
+int main(int argc, char **argv)
+	{
+	if (argc < 2)
+		Die("usage: rsk_host_demo self|query|pair|fastdb ...");
+	const string Cmd = argv[1];
+	if (Cmd == "self" && argc >= 5)
+		{
+		DSSParams Params;
+		Params.SetMode(ParseMode(argv[2]));
+		LoadedSet S;
+		Load(argv[3], S);
+		CountingSearcher DBS;
+		DBS.m_Params = &Params;
+		FillSearcher(DBS, S);
+		DBS.m_fTsv = fopen(argv[4], "w");
+		if (argc > 5)
+			DBS.m_Columns = argv[5];
+		DBS.Setup();
+		DBS.RunSelf();
+		fclose(DBS.m_fTsv);
+		fprintf(stderr, "OnAln calls %u, hits %u\n", DBS.m_OnAlnCount, (uint)DBS.m_HitCount);
+		return 0;
+		}
+	if (Cmd == "query" && argc >= 6)
+		{
+		DSSParams Params;
+		Params.SetMode(ParseMode(argv[2]));
+		LoadedSet Stream, DB;
+		Load(argv[3], Stream);
+		Load(argv[4], DB);
+		CountingSearcher DBS;
+		DBS.m_Params = &Params;
+		FillSearcher(DBS, DB);
+		DBS.m_fTsv = fopen(argv[5], "w");
+		DBS.m_BlockChains = 7;  // several blocks even on the small test sets
+		DBS.Setup();
+		VectorChainSource Src(Stream.Data);
+		DBS.RunQuery(Src);
+		fclose(DBS.m_fTsv);
+		fprintf(stderr, "OnAln calls %u, hits %u\n", DBS.m_OnAlnCount, (uint)DBS.m_HitCount);
+		return 0;
+		}
+	if (Cmd == "pair" && argc >= 7)
+		{
+		DSSParams Params;
+		Params.SetMode(ParseMode(argv[2]));
+		LoadedSet S;
+		Load(argv[3], S);
+		const uint i = (uint)atoi(argv[4]), j = (uint)atoi(argv[5]);
+		rsk_asserta(i < S.Chains.size() && j < S.Chains.size());
+		DSSAligner DA;
+		DA.SetParams(Params);
+		DA.SetQuery(S.Chains[i], &S.Profiles[i], S.Data[i].MuLetters, S.Data[i].MuLetters ? &S.Kmers[i] : 0, S.SelfRevs[i]);
+		DA.SetTarget(S.Chains[j], &S.Profiles[j], S.Data[j].MuLetters, S.Data[j].MuLetters ? &S.Kmers[j] : 0, S.SelfRevs[j]);
+		DA.AlignQueryTarget();
+		FILE *f = fopen(argv[6], "w");
+		if (!DA.m_Path.empty())   // alignpair.cpp:110-117
+			DA.ToTsv(f, true);
+		fclose(f);
+		return 0;
+		}
+	if (Cmd == "fastdb" && argc >= 6)
+		{
+		LoadedSet Q, DB;
+		Load(argv[2], Q);
+		Load(argv[3], DB);
+		DSSParams Params;
+		Params.SetMode(AM_Fast);
+		MuPreFilter(Params, Q.Data, DB.Data, argv[4]);
+		DSSParams Params2;
+		Params2.SetDSSParams(DM_AlwaysSensitive);  // search.cpp:106-108
+		PostMuFilter(Params2, argv[4], Q.Data, DB.Data, argv[5]);
+		return 0;
+		}
+	Die("bad command line");
+	}
