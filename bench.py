@@ -265,8 +265,11 @@ def main():
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    io = torch.tensor([float(h2d), float(d2h), float(nhits)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)  # bytes moved and hits of the whole job
+    h2d, d2h, nhits = io.tolist()
     e2e_value = cells_all / te.item()
 
     if rank == 0:

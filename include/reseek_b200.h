@@ -206,11 +206,19 @@ typedef struct rsk_prefilter_opts {
 	uint32_t rsb_size;    /* per-query bag size B (-rsb_size); 0 = 1500 (prefiltermuparams.h) */
 	int32_t no_kl_swap;   /* 0: exchange Mu letters 10 and 11 on the query side, as `-search -fast -db` does through
 	                         g_CharToLetterMu (muprefilter.cpp:88, alpha.cpp:3291); 1: use the letters as given */
-	int32_t reserved;
+	int32_t raw_only;     /* 1: skip the per-query bag and return every (target, query, score) triple with a two-hit
+	                         diagonal in stream order (DB-sharded searches merge the ranks' triples, then rsk_prefilter_bag) */
 } rsk_prefilter_opts;
 typedef struct rsk_prefilter_result rsk_prefilter_result;
 int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *opts,
 		rsk_prefilter_result **out);
+/* RankedScoresBag alone (rankedscoresbag.cpp:34/5/185) over triples in stream order (targets ascending); host only.
+ * Multi-GPU: every rank runs rsk_prefilter(raw_only) on its block of the DB, the triples are concatenated in rank order
+ * (target indices shifted to the unsharded DB) and every rank applies the bag: the result equals the single-GPU one. */
+int rsk_prefilter_bag(uint32_t nq, uint64_t n, const uint32_t *t, const uint32_t *q, const uint16_t *s, uint32_t rsb_size,
+		rsk_prefilter_result **out);
+/* the candidates with t_lo <= target < t_hi, targets re-based to t_lo (one rank's share of a merged list); host only */
+int rsk_prefilter_select(const rsk_prefilter_result *r, uint32_t t_lo, uint32_t t_hi, rsk_prefilter_result **out);
 uint64_t rsk_prefilter_count(const rsk_prefilter_result *r);          /* candidate (target, query) pairs */
 const uint32_t *rsk_prefilter_targets(const rsk_prefilter_result *r); /* [count] */
 const uint32_t *rsk_prefilter_queries(const rsk_prefilter_result *r); /* [count] */

@@ -80,6 +80,25 @@ void bag_add(Bag &b, uint32_t B, uint32_t t, uint16_t score)  // AddScore
 		bag_truncate(b, B);
 }
 
+// RankedScoresBag::ToTsv (rankedscoresbag.cpp:185-232): final truncation, then target -> queries (ascending)
+void finish_bags(std::vector<Bag> &bags, uint32_t B, rsk_prefilter_result &res)
+{
+	std::map<uint32_t, std::vector<std::pair<uint32_t, uint16_t>>> inv;
+	for (uint32_t q = 0; q < (uint32_t)bags.size(); ++q) {
+		bag_truncate(bags[q], B);
+		for (size_t k = 0; k < bags[q].t.size(); ++k)
+			inv[bags[q].t[k]].emplace_back(q, bags[q].s[k]);
+	}
+	for (auto &kv : inv) {
+		for (auto &e : kv.second) {
+			res.t.push_back(kv.first);
+			res.q.push_back(e.first);
+			res.s.push_back(e.second);
+		}
+	}
+	res.ntargets = (uint32_t)inv.size();
+}
+
 struct PfScratch {
 	DevBuf<uint8_t> muq, tmp;
 	DevBuf<uint32_t> qk_off, qk_code, qk_val, nb_count, key_a, key_b, val_a, val_b, row_start, row_end;
@@ -294,29 +313,70 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 			CK(cudaMemcpyAsync(cs.data(), S.cand_s.p, sizeof(uint16_t) * nc, cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
 			// stream order of the reference at -threads 1: targets ascending (AddTwoHitDiag -> AddScore, prefiltermu.cpp:288-313)
-			for (unsigned long long k = 0; k < nc; ++k)
-				bag_add(bags[cq[k]], B, ct[k], cs[k]);
+			if (o.raw_only) {
+				res->t.insert(res->t.end(), ct.begin(), ct.end());
+				res->q.insert(res->q.end(), cq.begin(), cq.end());
+				res->s.insert(res->s.end(), cs.begin(), cs.end());
+			} else {
+				for (unsigned long long k = 0; k < nc; ++k)
+					bag_add(bags[cq[k]], B, ct[k], cs[k]);
+			}
 			res->raw += nc;
 		}
 		t0 = t1;
 	}
-	// ---- RankedScoresBag::ToTsv (rankedscoresbag.cpp:185-232): final truncation, then target -> queries (ascending) ----
-	std::map<uint32_t, std::vector<std::pair<uint32_t, uint16_t>>> inv;
-	for (uint32_t q = 0; q < nQ; ++q) {
-		bag_truncate(bags[q], B);
-		for (size_t k = 0; k < bags[q].t.size(); ++k)
-			inv[bags[q].t[k]].emplace_back(q, bags[q].s[k]);
+	if (o.raw_only) {
+		uint32_t nt = 0;
+		for (size_t k = 0; k < res->t.size(); ++k)
+			nt += (k == 0 || res->t[k] != res->t[k - 1]);
+		res->ntargets = nt;
+	} else {
+		finish_bags(bags, B, *res);
 	}
-	for (auto &kv : inv) {
-		for (auto &e : kv.second) {
-			res->t.push_back(kv.first);
-			res->q.push_back(e.first);
-			res->s.push_back(e.second);
-		}
-	}
-	res->ntargets = (uint32_t)inv.size();
 	ctx->stats.kernel_launches += launches;
 	*out = guard.release();
+	return RSK_OK;
+}
+
+// The bag alone, over (target, query, score) triples in stream order: the merge step of a DB-sharded prefilter, where
+// every rank produced the triples of its own target block (raw_only) and the blocks were concatenated in rank order.
+extern "C" int rsk_prefilter_bag(uint32_t nq, uint64_t n, const uint32_t *t, const uint32_t *q, const uint16_t *s, uint32_t rsb_size,
+		rsk_prefilter_result **out)
+{
+	if (!out || (n && (!t || !q || !s)))
+		return fail(RSK_ERR_ARG, "rsk_prefilter_bag: null argument");
+	*out = nullptr;
+	const uint32_t B = rsb_size ? rsb_size : 1500u;
+	std::vector<Bag> bags(nq);
+	for (uint64_t k = 0; k < n; ++k) {
+		if (q[k] >= nq)
+			return fail(RSK_ERR_ARG, "rsk_prefilter_bag: triple %llu names query %u of %u", (unsigned long long)k, q[k], nq);
+		bag_add(bags[q[k]], B, t[k], s[k]);
+	}
+	auto *res = new rsk_prefilter_result();
+	res->raw = n;
+	finish_bags(bags, B, *res);
+	*out = res;
+	return RSK_OK;
+}
+
+// Candidates whose target lies in [t_lo, t_hi), re-based to t_lo: the share of a merged candidate list that one rank of a
+// DB-sharded search post-filters against its own block.
+extern "C" int rsk_prefilter_select(const rsk_prefilter_result *r, uint32_t t_lo, uint32_t t_hi, rsk_prefilter_result **out)
+{
+	if (!r || !out || t_hi < t_lo)
+		return fail(RSK_ERR_ARG, "rsk_prefilter_select: bad argument");
+	auto *res = new rsk_prefilter_result();
+	for (size_t k = 0; k < r->t.size(); ++k) {
+		if (r->t[k] < t_lo || r->t[k] >= t_hi)
+			continue;
+		res->ntargets += (res->t.empty() || res->t.back() != r->t[k] - t_lo);
+		res->t.push_back(r->t[k] - t_lo);
+		res->q.push_back(r->q[k]);
+		res->s.push_back(r->s[k]);
+	}
+	res->raw = res->t.size();
+	*out = res;
 	return RSK_OK;
 }
 

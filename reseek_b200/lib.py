@@ -43,7 +43,7 @@ class SearchOpts(C.Structure):
 
 
 class PrefilterOpts(C.Structure):
-    _fields_ = [("index_mode", C.c_int32), ("rsb_size", C.c_uint32), ("no_kl_swap", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("index_mode", C.c_int32), ("rsb_size", C.c_uint32), ("no_kl_swap", C.c_int32), ("raw_only", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -124,6 +124,8 @@ def load_library():
     for fn in (L.rsk_prefilter_targets, L.rsk_prefilter_queries, L.rsk_prefilter_scores):
         fn.argtypes = [C.c_void_p]
         fn.restype = C.c_void_p
+    L.rsk_prefilter_bag.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.rsk_prefilter_select.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.rsk_prefilter_free.argtypes = [C.c_void_p]
     L.rsk_prefilter_free.restype = None
     L.rsk_prefilter_to_tsv.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
@@ -249,6 +251,12 @@ class PrefilterResult:
             raise ReseekB200Error("rsk_prefilter_to_tsv failed")
         return buf.value.decode()
 
+    def select(self, t_lo, t_hi):
+        """Candidates with t_lo <= target < t_hi, re-based to t_lo (one rank's share of a merged list)."""
+        r = C.c_void_p()
+        _check(load_library().rsk_prefilter_select(self._handle, int(t_lo), int(t_hi), C.byref(r)))
+        return PrefilterResult(r)
+
     def as_dict(self):
         out = {}
         for t, q in zip(self.targets.tolist(), self.queries.tolist()):
@@ -268,6 +276,17 @@ class PrefilterResult:
 
     def __len__(self):
         return len(self.targets)
+
+
+def prefilter_bag(nq, targets, queries, scores, rsb_size=0):
+    """RankedScoresBag over (target, query, score) triples in stream order (rsk_prefilter_bag; host only)."""
+    t = np.ascontiguousarray(targets, np.uint32)
+    q = np.ascontiguousarray(queries, np.uint32)
+    s = np.ascontiguousarray(scores, np.uint16)
+    assert len(t) == len(q) == len(s)
+    r = C.c_void_p()
+    _check(load_library().rsk_prefilter_bag(int(nq), len(t), _ptr(t), _ptr(q), _ptr(s), int(rsb_size), C.byref(r)))
+    return PrefilterResult(r)
 
 
 class ChainSet:
@@ -362,9 +381,10 @@ class Context:
                                                C.byref(o), C.byref(r)))
         return Results(r)
 
-    def prefilter(self, Q, T, index_mode=0, rsb_size=0, kl_swap=True):
-        """MuPreFilter (muprefilter.cpp:64-133) on the GPU; Q = -search chains, T = -db chains."""
-        o = PrefilterOpts(int(index_mode), int(rsb_size), int(not kl_swap), 0)
+    def prefilter(self, Q, T, index_mode=0, rsb_size=0, kl_swap=True, raw_only=False):
+        """MuPreFilter (muprefilter.cpp:64-133) on the GPU; Q = -search chains, T = -db chains.
+        raw_only: every (target, query, score) triple with a two-hit diagonal, before the per-query bag."""
+        o = PrefilterOpts(int(index_mode), int(rsb_size), int(not kl_swap), int(bool(raw_only)))
         r = C.c_void_p()
         _check(load_library().rsk_prefilter(self.handle, Q.handle, T.handle, C.byref(o), C.byref(r)))
         return PrefilterResult(r)
