@@ -653,8 +653,11 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		ma.tr = tr ? 1 : 0;
 		ma.cross = b.cross ? 1 : 0;
 		ma.a_begin = b.a0; ma.nB = B->d.n;
+		// packed 16-bit lanes (two column chains per warp) unless a pair could exceed their range
+		const bool mu16 = std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32");
+		const uint32_t task_cols = mu16 ? (uint32_t)kMuTaskCols : (uint32_t)kSwWarps;
 		if (b.cross) {
-			ma.nseg = (ncols + kSwWarps - 1) / kSwWarps;
+			ma.nseg = (ncols + task_cols - 1) / task_cols;
 			ma.ncols = ncols;
 			ma.rowlist = ctx->rowlist.p;
 			ma.ntasks = (uint32_t)rowlist.size() * ma.nseg;
@@ -672,7 +675,8 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		ma.open = ctx->params.mu_gap_open; ma.ext = ctx->params.mu_gap_ext;
 		ma.omega = ctx->params.omega; ma.omega_fwd = ctx->params.omega_fwd;
 		ma.mkfl = ctx->params.mkfl;
-		int nlm = launch_mu_filter(ma, (int)std::min<uint64_t>((uint64_t)ctx->num_sms * 2, std::max<uint32_t>(1, ma.ntasks)), st);
+		const int mu_grid = (int)std::min<uint64_t>((uint64_t)ctx->num_sms * 2, std::max<uint32_t>(1, ma.ntasks));
+		int nlm = mu16 ? launch_mu_filter16(ma, mu_grid, st) : launch_mu_filter(ma, mu_grid, st);
 		if (nlm < 0)
 			return fail(RSK_ERR_CUDA, "Mu filter kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->stats.kernel_launches += nlm;
@@ -1098,7 +1102,8 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		Batch b = b0;
 		const int buf = (int)(bi++ & 1);
 		if (!b.cross) {
-			// build tasks for sorted pairs [k0,k1): runs of equal A, chunks of kSwWarps
+			// build the Mu filter's tasks for sorted pairs [k0,k1): runs of equal A, chunks of one task's column count
+			const size_t task_cols = (std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32")) ? (size_t)kMuTaskCols : (size_t)kSwWarps;
 			t_a.clear(); t_begin.clear(); t_cnt.clear();
 			const size_t n = b.k1 - b.k0;
 			slots.resize(n);
@@ -1107,7 +1112,7 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			size_t k = 0;
 			while (k < n) {
 				size_t e = k + 1;
-				while (e < n && e - k < (size_t)kSwWarps && plan.sa[b.k0 + e] == plan.sa[b.k0 + k])
+				while (e < n && e - k < task_cols && plan.sa[b.k0 + e] == plan.sa[b.k0 + k])
 					++e;
 				t_a.push_back(plan.sa[b.k0 + k]);
 				t_begin.push_back((uint32_t)k);

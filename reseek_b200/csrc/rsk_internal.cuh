@@ -47,6 +47,8 @@ static_assert(sizeof(PairRec) == 64, "PairRec layout");
 // ---- SW kernel geometry ----
 constexpr int kSwWarps = 16;                 // warps per CTA of the Mu filter kernel
 constexpr int kSwThreads = kSwWarps * 32;
+constexpr int kMuTaskCols = 2 * kSwWarps;     // column chains per task of the packed 16-bit Mu filter (two per warp)
+constexpr uint32_t kMu16MaxLen = 8000;       // 4*L must stay below 2^15 for the 16-bit lanes
 constexpr int kMaxRowsPerLane = 12;          // R: DP rows owned by one lane within a pass
 constexpr int kRowsPerPassMax = 32 * kMaxRowsPerLane;
 constexpr int kSwStripSteps = 16;            // wavefront steps between two checkpoints of the forward sweep
@@ -248,6 +250,7 @@ size_t sw_smem_bytes();
 uint64_t sw_ckpt_units(int npass, uint32_t LB);
 int launch_lddt(const LddtArgs &args, cudaStream_t stream);
 int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);
+int launch_mu_filter16(const MuArgs &args, int grid, cudaStream_t stream);
 size_t mu_smem_bytes();
 int launch_compact_survivors(const CompactArgs &args, uint32_t nrows, cudaStream_t stream);
 int launch_pack_profiles(const uint8_t *planes, uint64_t total, uint64_t *prof8, cudaStream_t stream);
