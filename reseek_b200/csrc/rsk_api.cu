@@ -1290,25 +1290,77 @@ extern "C" int rsk_search_cross_device(rsk_ctx *ctx, const rsk_chainset *A, cons
 	return search_impl(ctx, plan, opts, nullptr, true);
 }
 
+// Explicit pair lists are scheduled a-major with the longest B first inside every run of equal A (the chains of one task
+// then have similar lengths).  perm[k] = caller's index of the k-th scheduled pair.  A counting sort by A followed by an
+// independent (stable) sort of every run by B length, runs spread over the host threads: an all-vs-all of 11 k chains is
+// 6.3e7 pairs, for which one comparison sort over the whole list took longer than all kernels together.
 static int build_explicit_plan(SearchPlan &plan, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
-		const uint32_t *ia, const uint32_t *ib)
+		const uint32_t *ia, const uint32_t *ib, int nthreads)
 {
 	plan.A = A; plan.B = B; plan.cross = false; plan.npairs = npairs;
-	plan.perm.resize(npairs);
-	std::iota(plan.perm.begin(), plan.perm.end(), (uint64_t)0);
-	for (uint64_t k = 0; k < npairs; ++k)
-		if (ia[k] >= A->d.n || ib[k] >= B->d.n)
+	const uint32_t nA = A->d.n, nB = B->d.n;
+	std::vector<uint64_t> start((size_t)nA + 1, 0);
+	for (uint64_t k = 0; k < npairs; ++k) {
+		if (ia[k] >= nA || ib[k] >= nB)
 			return fail(RSK_ERR_ARG, "pair %llu: chain index out of range (%u,%u)", (unsigned long long)k, ia[k], ib[k]);
-	std::stable_sort(plan.perm.begin(), plan.perm.end(), [&](uint64_t x, uint64_t y) {
-		if (ia[x] != ia[y])
-			return ia[x] < ia[y];
-		return B->hlen[ib[x]] > B->hlen[ib[y]];
-	});
+		++start[ia[k] + 1];
+	}
+	for (uint32_t a = 0; a < nA; ++a)
+		start[a + 1] += start[a];
+	plan.perm.resize(npairs);
+	{
+		std::vector<uint64_t> cur(start.begin(), start.end() - 1);
+		for (uint64_t k = 0; k < npairs; ++k)
+			plan.perm[cur[ia[k]]++] = k;  // stable: caller order inside a run
+	}
 	plan.sa.resize(npairs);
 	plan.sb.resize(npairs);
-	for (uint64_t k = 0; k < npairs; ++k) {
-		plan.sa[k] = ia[plan.perm[k]];
-		plan.sb[k] = ib[plan.perm[k]];
+	const uint32_t maxlen = B->maxlen;
+	const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, nthreads), npairs >> 16));
+	std::atomic<uint32_t> next_a{0};
+	auto work = [&]() {
+		std::vector<uint32_t> bucket;
+		std::vector<uint64_t> tmp;
+		for (;;) {
+			const uint32_t a0 = next_a.fetch_add(64);
+			if (a0 >= nA)
+				break;
+			for (uint32_t a = a0; a < std::min(nA, a0 + 64); ++a) {
+				const uint64_t lo = start[a], hi = start[a + 1], n = hi - lo;
+				if (n == 0)
+					continue;
+				uint64_t *pp = plan.perm.data() + lo;
+				if (n > 1) {
+					if (n >= 4096 && n >= (uint64_t)maxlen / 4) {
+						// stable counting sort by B length, descending
+						bucket.assign((size_t)maxlen + 2, 0);
+						for (uint64_t k = 0; k < n; ++k)
+							++bucket[maxlen - B->hlen[ib[pp[k]]] + 1];
+						for (uint32_t l = 0; l <= maxlen; ++l)
+							bucket[l + 1] += bucket[l];
+						tmp.resize(n);
+						for (uint64_t k = 0; k < n; ++k)
+							tmp[bucket[maxlen - B->hlen[ib[pp[k]]]]++] = pp[k];
+						memcpy(pp, tmp.data(), n * sizeof(uint64_t));
+					} else {
+						std::stable_sort(pp, pp + n, [&](uint64_t x, uint64_t y) { return B->hlen[ib[x]] > B->hlen[ib[y]]; });
+					}
+				}
+				for (uint64_t k = 0; k < n; ++k) {
+					plan.sa[lo + k] = a;
+					plan.sb[lo + k] = ib[pp[k]];
+				}
+			}
+		}
+	};
+	if (T == 1) {
+		work();
+	} else {
+		std::vector<std::thread> th;
+		for (int t = 0; t < T; ++t)
+			th.emplace_back(work);
+		for (auto &t : th)
+			t.join();
 	}
 	return RSK_OK;
 }
@@ -1324,7 +1376,7 @@ extern "C" int rsk_search_pairs(rsk_ctx *ctx, const rsk_chainset *A, const rsk_c
 		return RSK_OK;
 	}
 	SearchPlan plan;
-	int rc = build_explicit_plan(plan, A, B, npairs, ia, ib);
+	int rc = build_explicit_plan(plan, A, B, npairs, ia, ib, ctx->host_threads);
 	if (rc)
 		return rc;
 	return search_impl(ctx, plan, opts, out, false);
@@ -1337,16 +1389,17 @@ extern "C" int rsk_search_self(rsk_ctx *ctx, const rsk_chainset *Sx, const rsk_s
 	*out = nullptr;
 	const uint64_t n = Sx->d.n;
 	const uint64_t np = n * (n + 1) / 2;
-	std::vector<uint32_t> ia, ib;
-	ia.reserve(np);
-	ib.reserve(np);
-	for (uint32_t i = 0; i < n; ++i)  // runself.cpp:72-99: (i, j >= i), A = chain i, B = chain j
-		for (uint32_t j = i; j < n; ++j) {
-			ia.push_back(i);
-			ib.push_back(j);
-		}
+	std::vector<uint32_t> ia(np), ib(np);
+	{
+		uint64_t k = 0;
+		for (uint32_t i = 0; i < n; ++i)  // runself.cpp:72-99: (i, j >= i), A = chain i, B = chain j
+			for (uint32_t j = i; j < n; ++j, ++k) {
+				ia[k] = i;
+				ib[k] = j;
+			}
+	}
 	SearchPlan plan;
-	int rc = build_explicit_plan(plan, Sx, Sx, np, ia.data(), ib.data());
+	int rc = build_explicit_plan(plan, Sx, Sx, np, ia.data(), ib.data(), ctx->host_threads);
 	if (rc)
 		return rc;
 	return search_impl(ctx, plan, opts, out, false);

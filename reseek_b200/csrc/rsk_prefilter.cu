@@ -6,6 +6,7 @@
 //   rsk_search_fast_db = both.
 // No CPU fallback: the triples only ever come from the kernels.
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <memory>
 
@@ -120,6 +121,22 @@ struct PfScratch {
 
 constexpr uint32_t kDict = 36u * 36 * 36 * 36 * 36;  // DICT_SIZE (prefiltermuparams.h)
 
+// RSK_TIMING=1: wall-clock phases of rsk_prefilter on stderr (developer aid)
+struct PhaseTimer {
+	bool on = getenv("RSK_TIMING") != nullptr;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	cudaStream_t st = nullptr;
+	void mark(const char *what)
+	{
+		if (!on)
+			return;
+		cudaStreamSynchronize(st);
+		const auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[rsk_prefilter] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	}
+};
+
 #define PFL(call)                                                                 \
 	do {                                                                          \
 		const int n_ = (call);                                                    \
@@ -167,6 +184,8 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 	}
 	PfScratch S;
 	PfArgs a = {};
+	PhaseTimer tm;
+	tm.st = st;
 	{
 		std::vector<int> mx(36 * 36);
 		const int8_t *m8 = rsk_mu_kmer_matrix_i8();
@@ -189,6 +208,7 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 	} else {
 		a.muQ = Q->d.mu;
 	}
+	tm.mark("setup");
 	// ---- K6: query index ----
 	std::vector<uint32_t> qk_off(nQ + 1, 0);
 	for (uint32_t q = 0; q < nQ; ++q)
@@ -240,6 +260,7 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 		}
 	}
 	a.row_start = S.row_start.p; a.row_end = S.row_end.p;
+	tm.mark("K6 query index");
 
 	// ---- K7 count pass over all targets, then batches sized by hits ----
 	std::vector<Bag> bags(nQ);
@@ -252,6 +273,7 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 		CK(cudaMemcpyAsync(hcnt.data(), S.hit_count.p, sizeof(unsigned long long) * nT, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 	}
+	tm.mark("K7 count pass");
 	const unsigned long long kMaxHits = 1ull << 28;              // 1 GB of keys + 1 GB sorted per batch
 	const uint32_t kMaxT = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(1u << 16, ((uint64_t)1 << 26) / nQ));
 	std::vector<unsigned long long> hoff, coff;
@@ -291,8 +313,10 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 		if (pf_segmented_sort(S.hit_key.p, S.hit_sorted.p, tot, ntl, S.hit_off.p, S.tmp.p, tb, st))
 			return fail(RSK_ERR_CUDA, "rsk_prefilter: cub segmented sort failed: %s", cudaGetErrorString(cudaGetLastError()));
 		launches += 3;
+		tm.mark("K7 probe+sort");
 		PFL(pf_launch_extend(a, ntl, st));
 		PFL(pf_launch_cands(a, ntl, false, st));
+		tm.mark("K8 extend+count");
 		ccnt.resize(ntl);
 		CK(cudaMemcpyAsync(ccnt.data(), S.cand_count.p, sizeof(uint32_t) * ntl, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
@@ -323,6 +347,7 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 			}
 			res->raw += nc;
 		}
+		tm.mark("candidates D2H + bag");
 		t0 = t1;
 	}
 	if (o.raw_only) {
@@ -333,6 +358,7 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 	} else {
 		finish_bags(bags, B, *res);
 	}
+	tm.mark("finish bags");
 	ctx->stats.kernel_launches += launches;
 	*out = guard.release();
 	return RSK_OK;
