@@ -155,6 +155,7 @@ const float *rsk_mu_matrix_f32(void);     /* ScoreMx_Mu [36][36] (mumx_data.cpp:
 /* ---- context: DBSearcher::Setup (dbsearcher.cpp:73) + DSSAligner::SetParams (dssaligner.h:106) ---- */
 int rsk_ctx_create(int device, const rsk_params *params, void *cuda_stream /* cudaStream_t or NULL */, rsk_ctx **out);
 int rsk_ctx_set_params(rsk_ctx *ctx, const rsk_params *params);
+int rsk_ctx_get_params(const rsk_ctx *ctx, rsk_params *out);
 void rsk_ctx_destroy(rsk_ctx *ctx);
 int rsk_ctx_stats(const rsk_ctx *ctx, rsk_stats *out);
 int rsk_ctx_sync(rsk_ctx *ctx);

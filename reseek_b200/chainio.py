@@ -47,3 +47,48 @@ def write_rskc(path, chains, labels=None, seq=None):
         for lab in labels:
             f.write(lab.encode() + b"\0")
     return labels, seq
+
+
+def read_rskc(path):
+    """Inverse of write_rskc: returns (SynthChains-like dict of arrays, labels, seq bytes)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    assert buf[:4] == b"RSKC"
+    ver, n, total, has_mu, has_sr = struct.unpack_from("<IIQII", buf, 4)
+    pos = 4 + 24
+    lens = np.frombuffer(buf, np.uint32, n, pos); pos += 4 * n
+    prof = np.frombuffer(buf, np.uint8, 8 * total, pos).reshape(8, total); pos += 8 * total
+    mu = None
+    if has_mu:
+        mu = np.frombuffer(buf, np.uint8, total, pos); pos += total
+    xyz = np.frombuffer(buf, np.float32, 3 * total, pos).reshape(3, total); pos += 12 * total
+    selfrev = None
+    if has_sr:
+        selfrev = np.frombuffer(buf, np.float32, n, pos); pos += 4 * n
+    seq = np.frombuffer(buf, np.uint8, total, pos); pos += total
+    labels = buf[pos:].split(b"\0")[:n]
+    return dict(lens=lens, prof=prof, mu=mu, xyz=xyz, selfrev=selfrev), [x.decode() for x in labels], seq
+
+
+def write_bca(path, labels, seqs, xyzs):
+    """The reference's binary C-alpha format (bcadata.cpp:15-58, 147-175): magic, 3 x u64 header, per chain L amino-acid
+    chars + 3L uint16 integer coordinates uint16((x + 1000) * 10 + 0.5) (pdbchain.h:89), u32 lengths, NUL-terminated labels.
+    seqs: list of bytes; xyzs: list of float32 [3][L] arrays."""
+    n = len(labels)
+    body = bytearray()
+    lens = []
+    for seq, xyz in zip(seqs, xyzs):
+        L = len(seq)
+        assert xyz.shape == (3, L)
+        ic = ((xyz.astype(np.float32) + np.float32(1000)) * np.float32(10) + 0.5).astype(np.float64)
+        ic = np.floor(ic).astype(np.uint16).T.reshape(-1)  # x0 y0 z0 x1 ...
+        body += bytes(seq) + ic.tobytes()
+        lens.append(L)
+    lens_pos = 4 + 24 + len(body)
+    labeldata = b"".join(lab.encode() + b"\0" for lab in labels)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", 0xBCABCA))
+        f.write(struct.pack("<QQQ", n, lens_pos, len(labeldata)))
+        f.write(bytes(body))
+        f.write(np.asarray(lens, np.uint32).tobytes())
+        f.write(labeldata)

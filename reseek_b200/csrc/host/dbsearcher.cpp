@@ -222,6 +222,71 @@ void DBSearcher::RunQuery(ChainSource &QCR)
 	RunStats();
 	}
 
+// dbsearcher.cpp:242-256: Mu letters only when the filter is on; self-reverse scores with omega = 0 (profileloader.cpp:22-26)
+void DBSearcher::LoadDB(const string &DBFN)
+	{
+	rsk_asserta(m_Params != 0);
+	rsk_asserta(m_DBChains.empty());
+	ChainReader2 CR;
+	CR.Open(DBFN);
+	DSSParams LoaderParams = *m_Params;
+	LoaderParams.m_UsePara = false;
+	LoaderParams.m_Omega = 0;
+	ChainFeatures F;
+	const bool WithMu = m_Params->m_Omega > 0;
+	ProfileLoader::Load(*m_Params, CR, 0, WithMu, GetContext(), LoaderParams, m_MaxEvalue, F);
+	m_DBChains = F.Chains;
+	m_DBProfiles = F.Profiles;
+	if (WithMu)
+		{
+		m_DBMuLettersVec = F.MuLetters;
+		m_DBMuKmersVec = F.MuKmers;
+		}
+	else
+		{
+		for (auto *p : F.MuLetters) delete p;
+		for (auto *p : F.MuKmers) delete p;
+		}
+	m_DBSelfRevScores = F.SelfRevScores;
+	F.Release();
+	m_OwnsChains = true;
+	}
+
+// runquery.cpp:18-80 with the chains coming from a file: per block DSS on host threads, self-reverse scores with the
+// search parameters (runquery.cpp:43), then the generic cross search
+void DBSearcher::RunQuery(ChainReader2 &QCR)
+	{
+	rsk_asserta(!m_DAs.empty());
+	const bool WithMu = !m_DBMuLettersVec.empty();
+	time_t t_start = time(0);
+	uint Secs = 0;
+	for (;;)
+		{
+		ChainFeatures F;
+		const uint N = ProfileLoader::Load(*m_Params, QCR, m_BlockChains, WithMu, GetContext(), *m_Params, m_MaxEvalue, F);
+		if (N == 0)
+			break;
+		vector<ChainData> Block(N);
+		for (uint i = 0; i < N; ++i)
+			{
+			Block[i].Chain = F.Chains[i];
+			Block[i].Profile = F.Profiles[i];
+			Block[i].MuLetters = WithMu ? F.MuLetters[i] : 0;
+			Block[i].SelfRevScore = F.SelfRevScores[i];
+			}
+		VectorChainSource Src(Block);
+		const uint SavedBlock = m_BlockChains;
+		m_BlockChains = N;
+		RunQuery(Src);
+		m_BlockChains = SavedBlock;
+		Secs += m_Secs;
+		F.Free();
+		}
+	m_Secs = (uint)(time(0) - t_start);
+	if (m_Secs == 0)
+		m_Secs = 1;
+	}
+
 // dbsearcher.cpp:29-56
 void DBSearcher::RunStats() const
 	{

@@ -5,13 +5,15 @@
 // The pair loops of ThreadBodySelf / ThreadBodyQuery (runself.cpp:13-70, runquery.cpp:18-80) become one
 // rsk_search_self / one rsk_search_cross per streamed block; every reported pair is then replayed through BaseOnAln
 // with a DSSAligner filled from the hit record, so subclasses (scop40bench.cpp) keep working.
-// LoadDB is not here: reading structures and running DSS is upstream of this layer; fill the vectors (AddChain).
+// LoadDB / RunQuery(ChainReader2&) read .bca files and run the DSS look-alike (dss.h) on host threads; other structure
+// formats are upstream of this layer: fill the vectors (AddChain) or stream ChainData through a ChainSource.
 #pragma once
 
 #include <atomic>
 #include <mutex>
 
 #include "dssaligner.h"
+#include "profileloader.h"
 
 namespace reseek_b200 {
 
@@ -69,11 +71,13 @@ public:
 
 public:
 	void Setup();
+	void LoadDB(const string &DBFN);   // dbsearcher.cpp:242-256 (.bca input): chains, DSS profiles, Mu letters, self-reverse scores
 	uint GetDBChainCount() const { return RSK_SIZE(m_DBChains); }
 	uint GetDBSize() const { return GetDBChainCount(); }
 	void AddChain(PDBChain *ptrChain, vector<vector<byte> > *ptrProfile, vector<byte> *ptrMuLetters);
 
 	void RunQuery(ChainSource &QCR);
+	void RunQuery(ChainReader2 &QCR);  // runquery.cpp:82-130: streamed chains read from a .bca, DSS + self-reverse per block
 	void RunSelf();
 	void RunStats() const;
 	bool Reject(DSSAligner &DA, bool Up) const;

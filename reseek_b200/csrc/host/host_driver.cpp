@@ -7,6 +7,11 @@
 //   rsk_host_demo query <mode> <stream.rskc> <db.rskc> <out.tsv>    DBSearcher::RunQuery          (-search Q -db DB)
 //   rsk_host_demo pair  <mode> <set.rskc> <i> <j> <out.tsv>         DSSAligner::AlignQueryTarget  (-alignpair)
 //   rsk_host_demo fastdb <q.rskc> <db.rskc> <cands.tsv> <out.tsv>   MuPreFilter + PostMuFilter    (-search Q -db DB -fast)
+// From the reference's own .bca files, through the DSS look-alike (no precomputed features):
+//   rsk_host_demo features   <in.bca> <out.rskc>                               DSS only (runs without a GPU)
+//   rsk_host_demo selfsearch <mode> <x.bca> <out.tsv> [columns]                search.cpp:20-38   (-search X)
+//   rsk_host_demo search     <mode> <q.bca> <db.bca> <out.tsv> [columns]       search.cpp:40-63   (-search Q -db DB)
+//   rsk_host_demo searchfast <q.bca> <db.bca> <cands.tsv> <out.tsv> [columns]  search.cpp:76-111  (-search Q -db DB -fast)
 #include <stdlib.h>
 #include <string.h>
 
@@ -119,11 +124,143 @@ public:
 	void OnAln(DSSAligner &DA, bool Up) override { ++m_OnAlnCount; }
 	};
 
+static void WriteRskc(const char *fn, const ChainFeatures &F, bool HasMu, bool HasSelfRev)
+	{
+	FILE *f = fopen(fn, "wb");
+	if (f == 0)
+		Die("Cannot create %s", fn);
+	const uint32_t n = RSK_SIZE(F.Chains), ver = 1, has_mu = HasMu, has_sr = HasSelfRev;
+	uint64_t total = 0;
+	vector<uint32_t> len(n);
+	for (uint32_t i = 0; i < n; ++i)
+		total += (len[i] = F.Chains[i]->GetSeqLength());
+	fwrite("RSKC", 1, 4, f);
+	fwrite(&ver, 4, 1, f); fwrite(&n, 4, 1, f); fwrite(&total, 8, 1, f); fwrite(&has_mu, 4, 1, f); fwrite(&has_sr, 4, 1, f);
+	fwrite(len.data(), 4, n, f);
+	for (int ft = 0; ft < 8; ++ft)
+		for (uint32_t i = 0; i < n; ++i)
+			fwrite((*F.Profiles[i])[ft].data(), 1, len[i], f);
+	if (HasMu)
+		for (uint32_t i = 0; i < n; ++i)
+			fwrite(F.MuLetters[i]->data(), 1, len[i], f);
+	for (int c = 0; c < 3; ++c)
+		for (uint32_t i = 0; i < n; ++i)
+			{
+			const vector<float> &v = c == 0 ? F.Chains[i]->m_Xs : c == 1 ? F.Chains[i]->m_Ys : F.Chains[i]->m_Zs;
+			fwrite(v.data(), 4, len[i], f);
+			}
+	if (HasSelfRev)
+		fwrite(F.SelfRevScores.data(), 4, n, f);
+	for (uint32_t i = 0; i < n; ++i)
+		fwrite(F.Chains[i]->m_Seq.data(), 1, len[i], f);
+	for (uint32_t i = 0; i < n; ++i)
+		fwrite(F.Chains[i]->m_Label.c_str(), 1, F.Chains[i]->m_Label.size() + 1, f);
+	fclose(f);
+	}
+
+static vector<ChainData> ToChainData(const ChainFeatures &F)
+	{
+	vector<ChainData> v(F.Chains.size());
+	for (size_t i = 0; i < v.size(); ++i)
+		{
+		v[i].Chain = F.Chains[i];
+		v[i].Profile = F.Profiles[i];
+		v[i].MuLetters = F.MuLetters[i];
+		v[i].SelfRevScore = F.SelfRevScores.empty() ? FLT_MAX : F.SelfRevScores[i];
+		}
+	return v;
+	}
+
 int main(int argc, char **argv)
 	{
 	if (argc < 2)
-		Die("usage: rsk_host_demo self|query|pair|fastdb ...");
+		Die("usage: rsk_host_demo self|query|pair|fastdb|features|selfsearch|search|searchfast ...");
 	const string Cmd = argv[1];
+	if (Cmd == "features" && argc >= 4)
+		{
+		// DSS stage only: no device is touched (no self-reverse scores)
+		ChainReader2 CR;
+		CR.Open(argv[2]);
+		ChainFeatures F;
+		DSSParams Params;
+		DSS D;
+		D.SetParams(Params);
+		while (PDBChain *Chain = CR.GetNext())
+			{
+			F.Chains.push_back(Chain);
+			F.Profiles.push_back(new vector<vector<byte> >);
+			F.MuLetters.push_back(new vector<byte>);
+			F.MuKmers.push_back(new vector<uint>);
+			D.Init(*Chain);
+			D.GetProfile(*F.Profiles.back());
+			D.GetMuLetters(*F.MuLetters.back());
+			}
+		WriteRskc(argv[3], F, true, false);
+		F.Free();
+		return 0;
+		}
+	if (Cmd == "selfsearch" && argc >= 5)
+		{
+		DSSParams Params;
+		Params.SetMode(ParseMode(argv[2]));
+		CountingSearcher DBS;
+		DBS.m_Params = &Params;
+		DBS.LoadDB(argv[3]);
+		DBS.Setup();
+		DBS.m_fTsv = fopen(argv[4], "w");
+		if (argc > 5)
+			DBS.m_Columns = argv[5];
+		DBS.RunSelf();
+		fclose(DBS.m_fTsv);
+		fprintf(stderr, "OnAln calls %u, hits %u\n", DBS.m_OnAlnCount, (uint)DBS.m_HitCount);
+		return 0;
+		}
+	if (Cmd == "search" && argc >= 6)
+		{
+		DSSParams Params;
+		Params.SetMode(ParseMode(argv[2]));
+		CountingSearcher DBS;
+		DBS.m_Params = &Params;
+		DBS.LoadDB(argv[3]);       // the -search file is the in-memory side (search.cpp:53)
+		DBS.Setup();
+		DBS.m_fTsv = fopen(argv[5], "w");
+		if (argc > 6)
+			DBS.m_Columns = argv[6];
+		DBS.m_BlockChains = 40;    // several blocks even on the small test sets
+		ChainReader2 CR;
+		CR.Open(argv[4]);          // the -db file is streamed (search.cpp:57-59)
+		DBS.RunQuery(CR);
+		fclose(DBS.m_fTsv);
+		fprintf(stderr, "OnAln calls %u, hits %u\n", DBS.m_OnAlnCount, (uint)DBS.m_HitCount);
+		return 0;
+		}
+	if (Cmd == "searchfast" && argc >= 6)
+		{
+		DSSParams Params;
+		Params.SetMode(AM_Fast);
+		DSSParams Params2;
+		Params2.SetDSSParams(DM_AlwaysSensitive);  // search.cpp:106-108
+		rsk_params R;
+		Params2.ToRsk(R, 10);
+		rsk_ctx *C = 0;
+		if (rsk_ctx_create(0, &R, 0, &C) != RSK_OK)
+			Die("reseek_b200: %s", rsk_last_error());
+		// queries and targets with the self-reverse scores PostMuFilter computes for them (postmufilter.cpp:79-81, 166-167:
+		// the sensitive parameters)
+		ChainReader2 QR, TR;
+		QR.Open(argv[2]);
+		TR.Open(argv[3]);
+		ChainFeatures Q, T;
+		ProfileLoader::Load(Params2, QR, 0, true, C, Params2, 10, Q);
+		ProfileLoader::Load(Params2, TR, 0, true, C, Params2, 10, T);
+		const vector<ChainData> QD = ToChainData(Q), TD = ToChainData(T);
+		MuPreFilter(Params, QD, TD, argv[4]);
+		PostMuFilter(Params2, argv[4], QD, TD, argv[5], argc > 6 ? argv[6] : 0);
+		Q.Free();
+		T.Free();
+		rsk_ctx_destroy(C);
+		return 0;
+		}
 	if (Cmd == "self" && argc >= 5)
 		{
 		DSSParams Params;

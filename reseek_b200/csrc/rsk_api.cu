@@ -217,6 +217,14 @@ extern "C" int rsk_ctx_set_params(rsk_ctx *ctx, const rsk_params *params)
 	return RSK_OK;
 }
 
+extern "C" int rsk_ctx_get_params(const rsk_ctx *ctx, rsk_params *out)
+{
+	if (!ctx || !out)
+		return fail(RSK_ERR_ARG, "rsk_ctx_get_params: null argument");
+	*out = ctx->params;
+	return RSK_OK;
+}
+
 extern "C" int rsk_ctx_create(int device, const rsk_params *params, void *cuda_stream, rsk_ctx **out)
 {
 	if (!out)

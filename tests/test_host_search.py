@@ -1,0 +1,118 @@
+"""Whole searches from .bca files through the host C++ layer: .bca reader -> DSS look-alike (feature extraction) ->
+GPU search -> hit writer, against golden outputs of the reference BINARY on the same files (tools/make_golden_search.py).
+
+CPU part: the .bca reader and the DSS stage reproduce the reference's feature letters exactly (no GPU involved).
+GPU part: `-search X`, `-search Q -db DB` and `-search Q -db DB -fast` give the reference's TSV, line for line."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests.golden_util import GOLDEN, SEARCH_COLUMNS, golden_bca
+
+ROOT = Path(__file__).resolve().parent.parent
+DEMO = ROOT / "reseek_b200" / "rsk_host_demo"
+HOSTLIB = ROOT / "reseek_b200" / "libreseek_b200_host.so"
+
+
+def _run(*args):
+    return subprocess.run([str(DEMO), *map(str, args)], capture_output=True, text=True, timeout=900)
+
+
+def _golden(name):
+    return (GOLDEN / name).read_text().splitlines()
+
+
+def test_dss_lookalike_reproduces_reference_letters(built_lib):
+    """rskh_dss_features (DSS::GetProfile / GetMuLetters restated on the host) on 21 real chains (49..1231 residues):
+    all 8 feature planes, the Mu letters and the profile of the coordinate-reversed chain, letter for letter."""
+    H = C.CDLL(str(HOSTLIB))
+    g = np.load(GOLDEN / "golden_chains.npz", allow_pickle=True)
+    lens = g["lens"].astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for i in range(len(lens)):
+        s, e = int(off[i]), int(off[i + 1])
+        n = e - s
+        x, y, z = (np.ascontiguousarray(g["xyz"][k, s:e], np.float32) for k in range(3))
+        prof, mu, rev = np.zeros((8, n), np.uint8), np.zeros(n, np.uint8), np.zeros((8, n), np.uint8)
+        rc = H.rskh_dss_features(bytes(g["seq"][s:e]), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                 z.ctypes.data_as(C.c_void_p), n, prof.ctypes.data_as(C.c_void_p),
+                                 mu.ctypes.data_as(C.c_void_p), rev.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        assert np.array_equal(prof, g["prof"][:, s:e]), f"chain {i}: profile"
+        assert np.array_equal(mu, g["mu"][s:e]), f"chain {i}: Mu letters"
+        assert np.array_equal(rev, g["rev_prof"][:, s:e]), f"chain {i}: reversed-chain profile"
+
+
+def test_dss_lookalike_vs_live_reference(built_lib):
+    """Same check against the compiled reference on 300 SCOP40 chains (build container only)."""
+    from oracle.pyoracle import Ref
+    bca = Path("/root/reference/test_data/scop40.bca")
+    if not Ref.available() or not bca.exists():
+        pytest.skip("needs oracle/_ref and the reference's test data")
+    H = C.CDLL(str(HOSTLIB))
+    ref = Ref(2)
+    n = ref.bca_open(bca)
+    rng = np.random.default_rng(7)
+    for i in sorted(rng.choice(n, 300, replace=False).tolist()):
+        label, seq, xyz = ref.bca_chain(i)
+        L = xyz.shape[1]
+        p_ref, mu_ref, _ = ref.dss(seq, xyz)
+        rp_ref = ref.rev_profile(seq, xyz)
+        x, y, z = (np.ascontiguousarray(xyz[k]) for k in range(3))
+        prof, mu, rev = np.zeros((8, L), np.uint8), np.zeros(L, np.uint8), np.zeros((8, L), np.uint8)
+        assert H.rskh_dss_features(seq, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), L,
+                                   prof.ctypes.data_as(C.c_void_p), mu.ctypes.data_as(C.c_void_p), rev.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(prof, p_ref) and np.array_equal(mu, mu_ref) and np.array_equal(rev, rp_ref), label
+
+
+def test_bca_reader_and_features_command(built_lib, tmp_path):
+    """.bca written by reseek_b200.chainio -> BCAData::Open/ReadChain -> DSS -> .rskc dump; no GPU is touched."""
+    from reseek_b200 import chainio
+    g6, g21 = golden_bca(tmp_path)
+    r = _run("features", g21, tmp_path / "g21.rskc")
+    assert r.returncode == 0, r.stderr
+    d, labels, seq = chainio.read_rskc(tmp_path / "g21.rskc")
+    g = np.load(GOLDEN / "golden_chains.npz", allow_pickle=True)
+    assert np.array_equal(d["lens"], g["lens"]) and labels == [str(x) for x in g["labels"]] and np.array_equal(seq, g["seq"])
+    assert np.array_equal(d["xyz"], g["xyz"]), "integer coordinates decode like PDBChain::ICToCoord"
+    assert np.array_equal(d["prof"], g["prof"]) and np.array_equal(d["mu"], g["mu"])
+    r = _run("features", tmp_path / "missing.bca", tmp_path / "x.rskc")
+    assert r.returncode == 1 and "---Fatal error---" in r.stderr
+    (tmp_path / "bad.bca").write_bytes(b"\0" * 64)
+    r = _run("features", tmp_path / "bad.bca", tmp_path / "x.rskc")
+    assert r.returncode == 1 and "Bad magic" in r.stderr  # bcadata.cpp:73-75
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fast", "sensitive", "verysensitive"])
+def test_selfsearch_matches_reference_binary(built_lib, tmp_path, mode):
+    g6, g21 = golden_bca(tmp_path)
+    r = _run("selfsearch", mode, g21, tmp_path / "out.tsv", SEARCH_COLUMNS)
+    assert r.returncode == 0, r.stderr
+    got = sorted((tmp_path / "out.tsv").read_text().splitlines())
+    want = _golden(f"golden_search_self_{mode}.tsv")
+    assert len(want) > 30 and got == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["sensitive", "verysensitive"])
+def test_search_db_matches_reference_binary(built_lib, tmp_path, mode):
+    g6, g21 = golden_bca(tmp_path)
+    r = _run("search", mode, g6, g21, tmp_path / "out.tsv", SEARCH_COLUMNS)
+    assert r.returncode == 0, r.stderr
+    got = sorted((tmp_path / "out.tsv").read_text().splitlines())
+    want = _golden(f"golden_search_db_{mode}.tsv")
+    assert len(want) >= 8 and got == want
+
+
+@pytest.mark.gpu
+def test_search_fast_db_matches_reference_binary(built_lib, tmp_path):
+    g6, g21 = golden_bca(tmp_path)
+    r = _run("searchfast", g6, g21, tmp_path / "cands.tsv", tmp_path / "out.tsv", SEARCH_COLUMNS)
+    assert r.returncode == 0, r.stderr
+    got = sorted((tmp_path / "out.tsv").read_text().splitlines())
+    want = _golden("golden_search_fastdb.tsv")
+    assert len(want) >= 6 and got == want
