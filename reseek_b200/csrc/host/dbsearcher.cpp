@@ -171,24 +171,51 @@ void DBSearcher::RunSelf()
 	RunStats();
 	}
 
-// runquery.cpp:18-130: every streamed chain (A, "query" slot) against every in-memory chain (B); hits are emitted
-// with Up = false (runquery.cpp:72-73).  The stream is consumed in blocks of m_BlockChains chains.
-void DBSearcher::RunQuery(ChainSource &QCR)
+// runquery.cpp:18-80 for one block of streamed chains: every chain of the block (A, "query" slot) against every
+// in-memory chain (B); hits are emitted with Up = false (runquery.cpp:72-73)
+void DBSearcher::RunQueryBlock(const vector<ChainData> &Block)
 	{
-	rsk_asserta(!m_DAs.empty());
 	DSSAligner &DA = *m_DAs[0];
-	DA.SetParams(*m_Params);
-	time_t t_start = time(0);
 	rsk_ctx *C = GetContext();
-	rsk_params R;
-	m_Params->ToRsk(R, m_MaxEvalue);
-	Check(rsk_ctx_set_params(C, &R));
-	UploadDB();
 	rsk_search_opts O;
 	memset(&O, 0, sizeof(O));
 	O.keep = RSK_KEEP_HITS;
 	O.want_paths = 1;
 	const bool WithMu = !m_DBMuLettersVec.empty();
+	rsk_chainset *A = UploadChains(C, Block, WithMu);
+	rsk_results *Res = 0;
+	Check(rsk_search_cross(C, A, m_DBSet, &O, &Res));
+	AddStats();
+	const uint64_t N = rsk_results_count(Res);
+	const rsk_hit *Hits = rsk_results_hits(Res);
+	const char *Pool = rsk_results_paths(Res);
+	for (uint64_t k = 0; k < N; ++k)
+		{
+		const rsk_hit &H = Hits[k];
+		DA.FromHit(H, Pool, Block[H.a], GetDBChainData(H.b));
+		if (!DA.m_Path.empty())
+			BaseOnAln(DA, false);
+		}
+	rsk_results_free(Res);
+	rsk_chainset_free(A);
+	m_ProcessedQueryCount += RSK_SIZE(Block);
+	}
+
+void DBSearcher::BeginRun()
+	{
+	rsk_asserta(!m_DAs.empty());
+	m_DAs[0]->SetParams(*m_Params);
+	rsk_params R;
+	m_Params->ToRsk(R, m_MaxEvalue);
+	Check(rsk_ctx_set_params(GetContext(), &R));
+	UploadDB();
+	}
+
+// runquery.cpp:82-130.  The stream is consumed in blocks of m_BlockChains chains.
+void DBSearcher::RunQuery(ChainSource &QCR)
+	{
+	time_t t_start = time(0);
+	BeginRun();
 	vector<ChainData> Block;
 	for (;;)
 		{
@@ -198,23 +225,7 @@ void DBSearcher::RunQuery(ChainSource &QCR)
 			Block.push_back(CD);
 		if (Block.empty())
 			break;
-		rsk_chainset *A = UploadChains(C, Block, WithMu);
-		rsk_results *Res = 0;
-		Check(rsk_search_cross(C, A, m_DBSet, &O, &Res));
-		AddStats();
-		const uint64_t N = rsk_results_count(Res);
-		const rsk_hit *Hits = rsk_results_hits(Res);
-		const char *Pool = rsk_results_paths(Res);
-		for (uint64_t k = 0; k < N; ++k)
-			{
-			const rsk_hit &H = Hits[k];
-			DA.FromHit(H, Pool, Block[H.a], GetDBChainData(H.b));
-			if (!DA.m_Path.empty())
-				BaseOnAln(DA, false);
-			}
-		rsk_results_free(Res);
-		rsk_chainset_free(A);
-		m_ProcessedQueryCount += RSK_SIZE(Block);
+		RunQueryBlock(Block);
 		}
 	m_Secs = (uint)(time(0) - t_start);
 	if (m_Secs == 0)
@@ -252,14 +263,13 @@ void DBSearcher::LoadDB(const string &DBFN)
 	m_OwnsChains = true;
 	}
 
-// runquery.cpp:18-80 with the chains coming from a file: per block DSS on host threads, self-reverse scores with the
-// search parameters (runquery.cpp:43), then the generic cross search
+// runquery.cpp:18-130 with the chains coming from a file: per block DSS on host threads, self-reverse scores with the
+// search parameters (runquery.cpp:43), then the cross search of the block
 void DBSearcher::RunQuery(ChainReader2 &QCR)
 	{
-	rsk_asserta(!m_DAs.empty());
-	const bool WithMu = !m_DBMuLettersVec.empty();
 	time_t t_start = time(0);
-	uint Secs = 0;
+	BeginRun();
+	const bool WithMu = !m_DBMuLettersVec.empty();
 	for (;;)
 		{
 		ChainFeatures F;
@@ -274,17 +284,13 @@ void DBSearcher::RunQuery(ChainReader2 &QCR)
 			Block[i].MuLetters = WithMu ? F.MuLetters[i] : 0;
 			Block[i].SelfRevScore = F.SelfRevScores[i];
 			}
-		VectorChainSource Src(Block);
-		const uint SavedBlock = m_BlockChains;
-		m_BlockChains = N;
-		RunQuery(Src);
-		m_BlockChains = SavedBlock;
-		Secs += m_Secs;
+		RunQueryBlock(Block);
 		F.Free();
 		}
 	m_Secs = (uint)(time(0) - t_start);
 	if (m_Secs == 0)
 		m_Secs = 1;
+	RunStats();
 	}
 
 // dbsearcher.cpp:29-56

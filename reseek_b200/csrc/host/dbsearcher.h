@@ -96,6 +96,8 @@ private:
 	rsk_chainset *m_DBSet = 0;
 	rsk_stats m_LastStats;
 	void UploadDB();
+	void BeginRun();
+	void RunQueryBlock(const vector<ChainData> &Block);
 	ChainData GetDBChainData(uint Idx) const;
 	void AddStats();
 	};

@@ -226,7 +226,8 @@ int main(int argc, char **argv)
 		DBS.m_fTsv = fopen(argv[5], "w");
 		if (argc > 6)
 			DBS.m_Columns = argv[6];
-		DBS.m_BlockChains = 40;    // several blocks even on the small test sets
+		if (const char *e = getenv("RSK_BLOCK_CHAINS"))  // the tests ask for several blocks even on small sets
+			DBS.m_BlockChains = (uint)atoi(e);
 		ChainReader2 CR;
 		CR.Open(argv[4]);          // the -db file is streamed (search.cpp:57-59)
 		DBS.RunQuery(CR);
@@ -290,7 +291,8 @@ int main(int argc, char **argv)
 		DBS.m_Params = &Params;
 		FillSearcher(DBS, DB);
 		DBS.m_fTsv = fopen(argv[5], "w");
-		DBS.m_BlockChains = 7;  // several blocks even on the small test sets
+		if (const char *e = getenv("RSK_BLOCK_CHAINS"))  // the tests ask for several blocks even on small sets
+			DBS.m_BlockChains = (uint)atoi(e);
 		DBS.Setup();
 		VectorChainSource Src(Stream.Data);
 		DBS.RunQuery(Src);

@@ -4,6 +4,7 @@ GPU search -> hit writer, against golden outputs of the reference BINARY on the 
 CPU part: the .bca reader and the DSS stage reproduce the reference's feature letters exactly (no GPU involved).
 GPU part: `-search X`, `-search Q -db DB` and `-search Q -db DB -fast` give the reference's TSV, line for line."""
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -18,7 +19,8 @@ HOSTLIB = ROOT / "reseek_b200" / "libreseek_b200_host.so"
 
 
 def _run(*args):
-    return subprocess.run([str(DEMO), *map(str, args)], capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, RSK_BLOCK_CHAINS="8")  # streamed side in several blocks
+    return subprocess.run([str(DEMO), *map(str, args)], capture_output=True, text=True, timeout=900, env=env)
 
 
 def _golden(name):

@@ -3,6 +3,7 @@
 CPU part: the shim library builds, exports the reference's class surface and dies loudly (Die(): message + exit 1) without
 a GPU.  GPU part: the harness drives RunSelf / RunQuery / AlignQueryTarget / the -fast -db pair of functions and its TSV
 output must equal, byte for byte, the lines formatted from the C-ABI results that the other parity tests pin to the oracle."""
+import os
 import subprocess
 from pathlib import Path
 
@@ -29,7 +30,8 @@ def _seqs(chains, seq):
 
 
 def _run(*args):
-    return subprocess.run([str(DEMO), *map(str, args)], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, RSK_BLOCK_CHAINS="7")  # streamed side in several blocks
+    return subprocess.run([str(DEMO), *map(str, args)], capture_output=True, text=True, timeout=600, env=env)
 
 
 def test_host_library_exports_reference_surface(built_lib):
