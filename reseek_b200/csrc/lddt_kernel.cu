@@ -33,7 +33,12 @@ __global__ void __launch_bounds__(kLddtThreads) lddt_ts_kernel(const LddtArgs a)
 		const float score = rec->score;
 		const uint32_t plen = rec->path_len;
 		__syncthreads();  // smem reuse across pairs
-		if (plen == 0 || score < a.min_fwd_score) {
+		// CalcEvalue is reached by every pair that went through Align_NoAccel, also when SWFast found nothing (empty path,
+		// score 0): with MinFwdScore <= 0 (-verysensitive) the reference then still sets Hi = Lo - 1 (= UINT_MAX - 1),
+		// Ids = Gaps = 0, LDDT = 0 and a test statistic (dssaligner.cpp:861-904).  Pairs the Mu filter dropped and long-chain
+		// pairs without an x-drop alignment never get there (dssaligner.cpp:819-829, 1395-1417).
+		const bool no_aln = plen == 0 && (rec->flags & (RSK_HIT_MU_REJECTED | RSK_HIT_MKF)) != 0;
+		if (no_aln || score < a.min_fwd_score) {
 			// dssaligner.cpp:861-862: nothing is computed; members keep their ClearAlign values
 			if (tid == 0) {
 				rec->hi_a = rec->hi_b = rec->ids = rec->gaps = 0xffffffffu;
