@@ -1390,27 +1390,111 @@ extern "C" int rsk_search_pairs(rsk_ctx *ctx, const rsk_chainset *A, const rsk_c
 	return search_impl(ctx, plan, opts, out, false);
 }
 
+static void add_stats(rsk_stats &acc, const rsk_stats &s)
+{
+	acc.pairs += s.pairs; acc.mu_filter_in += s.mu_filter_in; acc.mu_filter_rejected += s.mu_filter_rejected;
+	acc.mu_saturated += s.mu_saturated; acc.sw_pairs += s.sw_pairs; acc.sw_cells += s.sw_cells;
+	acc.evalue_pairs += s.evalue_pairs; acc.hits += s.hits; acc.kernel_launches += s.kernel_launches;
+	acc.h2d_bytes += s.h2d_bytes; acc.d2h_bytes += s.d2h_bytes; acc.sw_kernel_ms += s.sw_kernel_ms;
+	acc.mu_kernel_ms += s.mu_kernel_ms; acc.lddt_kernel_ms += s.lddt_kernel_ms; acc.total_ms += s.total_ms;
+	acc.mkf_kernel_ms += s.mkf_kernel_ms; acc.sw_kernel_launches += s.sw_kernel_launches; acc.mkf_pairs += s.mkf_pairs;
+}
+
+// append the hits and paths of `src` to `dst` (path offsets re-based); src is consumed
+static int append_results(rsk_results *dst, rsk_results *src)
+{
+	const uint64_t nh = dst->nhits + src->nhits, np = dst->npath + src->npath;
+	if (nh * sizeof(rsk_hit) > dst->hits_cap) {
+		size_t cap = 0;
+		rsk_hit *p = (rsk_hit *)g_blocks.get(std::max<uint64_t>(nh, 2 * dst->nhits) * sizeof(rsk_hit), cap);
+		if (!p) {
+			delete src;
+			return fail(RSK_ERR_NOMEM, "host memory for %llu hit records", (unsigned long long)nh);
+		}
+		if (dst->nhits)
+			memcpy(p, dst->hits, dst->nhits * sizeof(rsk_hit));
+		g_blocks.put(dst->hits, dst->hits_cap);
+		dst->hits = p;
+		dst->hits_cap = cap;
+	}
+	if (np > dst->paths_cap) {
+		size_t cap = 0;
+		char *p = (char *)g_blocks.get(std::max<uint64_t>(np, 2 * dst->npath), cap);
+		if (!p) {
+			delete src;
+			return fail(RSK_ERR_NOMEM, "host memory for %llu path bytes", (unsigned long long)np);
+		}
+		if (dst->npath)
+			memcpy(p, dst->paths, dst->npath);
+		g_blocks.put(dst->paths, dst->paths_cap);
+		dst->paths = p;
+		dst->paths_cap = cap;
+	}
+	for (uint64_t k = 0; k < src->nhits; ++k) {
+		rsk_hit h = src->hits[k];
+		h.path_off += dst->npath;
+		dst->hits[dst->nhits + k] = h;
+	}
+	if (src->npath)
+		memcpy(dst->paths + dst->npath, src->paths, src->npath);
+	dst->nhits = nh;
+	dst->npath = np;
+	delete src;
+	return RSK_OK;
+}
+
+// runself.cpp:72-99: pairs (i, j >= i), A = chain i, B = chain j.  The pair list of a large set does not fit the host
+// (1e5 chains = 5e9 pairs), so the rows are processed in chunks of at most RSK_SELF_CHUNK_PAIRS pairs (default 2^26) and the
+// chunks' results are concatenated; the order of RSK_KEEP_ALL records is the enumeration order either way.
 extern "C" int rsk_search_self(rsk_ctx *ctx, const rsk_chainset *Sx, const rsk_search_opts *opts, rsk_results **out)
 {
 	if (!ctx || !Sx || !out)
 		return fail(RSK_ERR_ARG, "rsk_search_self: null argument");
 	*out = nullptr;
 	const uint64_t n = Sx->d.n;
-	const uint64_t np = n * (n + 1) / 2;
-	std::vector<uint32_t> ia(np), ib(np);
-	{
-		uint64_t k = 0;
-		for (uint32_t i = 0; i < n; ++i)  // runself.cpp:72-99: (i, j >= i), A = chain i, B = chain j
-			for (uint32_t j = i; j < n; ++j, ++k) {
-				ia[k] = i;
-				ib[k] = j;
-			}
+	uint64_t chunk_pairs = (uint64_t)1 << 26;
+	if (const char *e = getenv("RSK_SELF_CHUNK_PAIRS")) {
+		const long long v = atoll(e);
+		if (v > 0)
+			chunk_pairs = (uint64_t)v;
 	}
-	SearchPlan plan;
-	int rc = build_explicit_plan(plan, Sx, Sx, np, ia.data(), ib.data(), ctx->host_threads);
-	if (rc)
-		return rc;
-	return search_impl(ctx, plan, opts, out, false);
+	rsk_results *total = nullptr;
+	rsk_stats acc;
+	memset(&acc, 0, sizeof(acc));
+	std::vector<uint32_t> ia, ib;
+	for (uint64_t i0 = 0; i0 < n;) {
+		uint64_t i1 = i0, np = 0;
+		while (i1 < n && (i1 == i0 || np + (n - i1) <= chunk_pairs))
+			np += n - i1++;
+		ia.resize(np);
+		ib.resize(np);
+		uint64_t k = 0;
+		for (uint64_t i = i0; i < i1; ++i)
+			for (uint64_t j = i; j < n; ++j, ++k) {
+				ia[k] = (uint32_t)i;
+				ib[k] = (uint32_t)j;
+			}
+		SearchPlan plan;
+		int rc = build_explicit_plan(plan, Sx, Sx, np, ia.data(), ib.data(), ctx->host_threads);
+		rsk_results *part = nullptr;
+		if (!rc)
+			rc = search_impl(ctx, plan, opts, &part, false);
+		if (!rc) {
+			add_stats(acc, ctx->stats);
+			if (!total)
+				total = part;
+			else
+				rc = append_results(total, part);
+		}
+		if (rc) {
+			delete total;
+			return rc;
+		}
+		i0 = i1;
+	}
+	ctx->stats = acc;
+	*out = total ? total : new rsk_results();
+	return RSK_OK;
 }
 
 extern "C" int rsk_mu_gapless_scores(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,

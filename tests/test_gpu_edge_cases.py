@@ -131,3 +131,28 @@ def test_empty_requests_and_bad_arguments(rb):
         ctx.set_params(p)  # dssparams.cpp:106-108
     other.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("mode,keep", [(3, 1), (2, 0)])
+def test_self_search_in_row_chunks_equals_one_piece(rb, mode, keep, monkeypatch):
+    """rsk_search_self cuts large sets into row chunks (the pair list of 1e5 chains would not fit the host): same records,
+    same order, same paths, summed statistics."""
+    from reseek_b200 import synth
+    s = synth.make_chains(60, 90, seed=941, length_jitter=0.5)
+    synth.plant_homologs(s, s.subset(range(6)), 0.3, seed=942)
+    ctx = rb.Context(0, mode)
+    S = ctx.upload(s.lens, s.prof, s.mu, s.xyz, s.selfrev)
+    whole = ctx.search_self(S, keep=keep, want_paths=True)
+    st0 = ctx.stats()
+    monkeypatch.setenv("RSK_SELF_CHUNK_PAIRS", "200")
+    parts = ctx.search_self(S, keep=keep, want_paths=True)
+    st1 = ctx.stats()
+    assert len(whole.hits) == len(parts.hits) > 0
+    for f in whole.hits.dtype.names:
+        if f != "path_off":
+            assert np.array_equal(whole.hits[f], parts.hits[f]), f
+    assert [whole.path(k) for k in range(len(whole.hits))] == [parts.path(k) for k in range(len(parts.hits))]
+    for k in ("pairs", "sw_pairs", "sw_cells", "evalue_pairs", "hits", "mu_filter_in", "mu_filter_rejected"):
+        assert st0[k] == st1[k], k
+    assert st1["sw_kernel_launches"] > st0["sw_kernel_launches"]
+    ctx.close()
