@@ -294,7 +294,7 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 		return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->ckpt.release(); ctx->tile.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
+	ctx->ckpt.release(); ctx->tile.release(); ctx->best.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
 	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();
 	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
 	ctx->h_rec[0].release(); ctx->h_rec[1].release(); ctx->h_pool[0].release(); ctx->h_pool[1].release();
@@ -461,22 +461,26 @@ struct SearchPlan {
 };
 
 int ensure_scratch(rsk_ctx *ctx, uint32_t maxRow, uint32_t maxCol, int &grid, uint64_t &ckpt_stride, uint64_t &bnd_stride,
-		uint32_t &bnd_pass_stride, uint32_t &stage_stride)
+		uint32_t &bnd_pass_stride, uint32_t &stage_stride, uint32_t &stage_chain_stride)
 {
 	int npass, R;
 	sw_geometry(maxRow, npass, R);
-	// every pair of the batch has npass(rows) <= npass(maxRow) and columns <= maxCol
-	ckpt_stride = sw_ckpt_units(npass, maxCol);  // float4 units
-	bnd_pass_stride = ((maxCol + 3) & ~3u) + 4;
+	// every pair of the batch has npass(rows) <= npass(maxRow) and columns <= maxCol; a warp sweeps up to kSwChain column
+	// chains as one concatenated wavefront
+	const uint64_t cols = (uint64_t)maxCol * kSwChain;
+	ckpt_stride = sw_ckpt_units(npass, cols);  // float4 units
+	bnd_pass_stride = (uint32_t)(((cols + 3) & ~(uint64_t)3) + 4);
 	bnd_stride = (uint64_t)bnd_pass_stride * (uint64_t)npass;
-	stage_stride = ((maxRow + maxCol + 16) + 15) & ~15u;
-	const uint64_t per_cta = (ckpt_stride * 16 + bnd_stride * 8 + stage_stride + kSwStripSteps * 32 * 8) * kSwMaxWarps;
+	stage_chain_stride = ((maxRow + maxCol + 16) + 15) & ~15u;
+	stage_stride = stage_chain_stride * kSwChain;
+	const uint64_t per_cta = (ckpt_stride * 16 + bnd_stride * 8 + stage_stride + kSwStripSteps * 32 * 8 + kSwChain * 32 * 16) * kSwMaxWarps;
 	grid = ctx->num_sms;
 	if (per_cta * (uint64_t)grid > ctx->scratch_budget)
 		grid = (int)std::max<uint64_t>(1, ctx->scratch_budget / per_cta);
 	const size_t warps = (size_t)grid * kSwMaxWarps;
 	if (ctx->ckpt.ensure(ckpt_stride * warps) || ctx->bnd.ensure((size_t)bnd_stride * warps) ||
-		ctx->tile.ensure((size_t)kSwStripSteps * 32 * warps) || ctx->stage.ensure((size_t)stage_stride * warps)) {
+		ctx->tile.ensure((size_t)kSwStripSteps * 32 * warps) || ctx->stage.ensure((size_t)stage_stride * warps) ||
+		ctx->best.ensure((size_t)kSwChain * 32 * warps)) {
 		cudaGetLastError();
 		return fail(RSK_ERR_NOMEM, "SW scratch allocation failed (rows=%u cols=%u)", maxRow, maxCol);
 	}
@@ -601,8 +605,8 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	const uint32_t maxRow = tr ? b.maxLB : b.maxLA, maxCol = tr ? b.maxLA : b.maxLB;
 	int grid;
 	uint64_t ckpt_stride, bnd_stride;
-	uint32_t bnd_pass_stride, stage_stride;
-	int rc = ensure_scratch(ctx, maxRow, maxCol, grid, ckpt_stride, bnd_stride, bnd_pass_stride, stage_stride);
+	uint32_t bnd_pass_stride, stage_stride, stage_chain_stride;
+	int rc = ensure_scratch(ctx, maxRow, maxCol, grid, ckpt_stride, bnd_stride, bnd_pass_stride, stage_stride, stage_chain_stride);
 	if (rc)
 		return rc;
 	if (ctx->rec.ensure(b.npairs) || ctx->pool.ensure((size_t)b.pool_bound + 64)) {
@@ -732,7 +736,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		while (k < b.npairs) {
 			const uint32_t a0 = plan.sa[b.k0 + k];
 			const int cls = sw_class_of_len(A->hlen[a0]);
-			const uint32_t W = (uint32_t)kClassWarps[cls];
+			const uint32_t W = (uint32_t)kClassWarps[cls] * kSwChain;  // column chains per SW task
 			const uint32_t begin = (uint32_t)e_clist.size();
 			uint32_t cnt = 0;
 			while (k < b.npairs && plan.sa[b.k0 + k] == a0 && cnt < W) {
@@ -775,7 +779,8 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	sa.ckpt = ctx->ckpt.p; sa.ckpt_stride = ckpt_stride;
 	sa.tile = ctx->tile.p;
 	sa.bnd = ctx->bnd.p; sa.bnd_stride = bnd_stride; sa.bnd_pass_stride = bnd_pass_stride;
-	sa.stage = ctx->stage.p; sa.stage_stride = stage_stride;
+	sa.stage = ctx->stage.p; sa.stage_stride = stage_stride; sa.stage_chain_stride = stage_chain_stride;
+	sa.best = ctx->best.p;
 	sa.rec = ctx->rec.p;
 	sa.pool = ctx->pool.p; sa.pool_cursor = ctx->d_pool_cursor;
 	sa.tables = ctx->d_tables;
@@ -793,7 +798,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 			sc.cross = 1;
 			sc.rowlist = ctx->rowlist.p + row_off[c];
 			sc.ncols = ncols;
-			sc.nseg = (ncols + kClassWarps[c] - 1) / kClassWarps[c];
+			sc.nseg = (ncols + kClassWarps[c] * kSwChain - 1) / (kClassWarps[c] * kSwChain);
 			sc.clist = tr ? ctx->colsort.p : ctx->blist.p;
 			sc.ntasks = nrows * sc.nseg;
 			g = (int)std::min<uint64_t>((uint64_t)grid, sc.ntasks);

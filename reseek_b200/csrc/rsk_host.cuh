@@ -106,6 +106,7 @@ struct rsk_ctx {
 	// grow-only scratch
 	DevBuf<float4> ckpt;
 	DevBuf<unsigned long long> tile;
+	DevBuf<float4> best;
 	DevBuf<float2> bnd;
 	DevBuf<uint8_t> stage;
 	DevBuf<PairRec> rec;

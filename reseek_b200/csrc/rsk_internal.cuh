@@ -52,6 +52,10 @@ constexpr uint32_t kMu16MaxLen = 8000;       // 4*L must stay below 2^15 for the
 constexpr int kMaxRowsPerLane = 12;          // R: DP rows owned by one lane within a pass
 constexpr int kRowsPerPassMax = 32 * kMaxRowsPerLane;
 constexpr int kSwStripSteps = 16;            // wavefront steps between two checkpoints of the forward sweep
+#ifndef RSK_SW_CHAIN
+#define RSK_SW_CHAIN 4
+#endif
+constexpr int kSwChain = RSK_SW_CHAIN;       // column chains a warp aligns back to back as one wavefront (one ramp per list)
 // SW kernel classes by rows per lane: R <= 5 | R == 6 | R = 7..8 | R = 9..12, with the warps per CTA (= pairs per task) of each
 constexpr int kSwClasses = 4;
 #ifndef RSK_CLASS_W0
@@ -107,7 +111,9 @@ struct SwArgs {
 	unsigned long long *tile;              // re-computed trace strip: kSwStripSteps*32 words per warp
 	float2 *bnd; uint64_t bnd_stride;      // pass-boundary rows (M, vertical gap) per column: per warp, one row per pass
 	uint32_t bnd_pass_stride;
-	uint8_t *stage; uint32_t stage_stride; // reversed path staging
+	uint8_t *stage; uint32_t stage_stride; // reversed path staging: per warp, one region of stage_chain_stride per chain
+	uint32_t stage_chain_stride;
+	float4 *best;                          // per warp kSwChain*32 parked (score, row, column) maxima
 	// outputs
 	PairRec *rec;
 	uint8_t *pool; unsigned long long *pool_cursor;
@@ -247,7 +253,7 @@ int pf_segmented_sort(const uint32_t *kin, uint32_t *kout, unsigned long long n,
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();
-uint64_t sw_ckpt_units(int npass, uint32_t LB);
+uint64_t sw_ckpt_units(int npass, uint64_t LB);
 int launch_lddt(const LddtArgs &args, cudaStream_t stream);
 int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);
 int launch_mu_filter16(const MuArgs &args, int grid, cudaStream_t stream);

@@ -47,7 +47,10 @@ constexpr size_t kSmemP0 = 8768;                        // plane 0: float4[132][
 constexpr size_t kPlaneBytes = (size_t)kNLet * 512;     // 67584
 constexpr int kPlaneFloats = kNLet * 128;
 __host__ __device__ constexpr int class_planes(int C) { return C >= 3 ? 3 : 2; }
-__host__ __device__ constexpr size_t class_smem(int C) { return kSmemP0 + (size_t)class_planes(C) * kPlaneBytes + 16; }
+// after the planes: 16 bytes for the task broadcast, then the warps' column-chain lists (kSwMaxWarps x kSwChain x 24 B)
+__host__ __device__ constexpr size_t smem_bcast_off(int planes) { return kSmemP0 + (size_t)planes * kPlaneBytes; }
+__host__ __device__ constexpr size_t smem_chains_off(int planes) { return smem_bcast_off(planes) + 16; }
+__host__ __device__ constexpr size_t class_smem(int C) { return smem_chains_off(class_planes(C)) + (size_t)kSwMaxWarps * kSwChain * 24; }
 
 // floats per lane in plane 1 / 2 for n rows living there (rounded up to a vector width)
 __host__ __device__ constexpr int plane_width(int n) { return n <= 0 ? 0 : n == 1 ? 1 : n == 2 ? 2 : 4; }
@@ -128,22 +131,35 @@ __device__ __forceinline__ void add_vec(float (&acc)[N], const float (&v)[12])
 // float4 units of one checkpoint per lane: M[R], I[R], M diagonal, (M, D) handed to the next lane
 __host__ __device__ constexpr int ckpt_words(int R) { return (2 * R + 3 + 3) / 4; }
 
-// One sweep over rows [pass*32R, (pass+1)*32R) of the row chain.
-//   TRACE = false: the forward sweep over all LB columns.  Values only; saves a checkpoint every kStrip steps
-//                  and tracks the lane's first maximum (lbest, lbi, lbj in kernel coordinates).
+// One column chain of a warp's work list (kept in shared memory): a warp aligns up to kSwChain column chains against the
+// CTA's row chain back to back, as ONE wavefront over their concatenated columns, so that the 31-step ramp is paid once per
+// list instead of once per pair.  `base` = first concatenated column of the chain.
+struct ColChain {
+	const uint64_t *col;  // the chain's residues, 8 e-letter bytes each (DevChains::prof8)
+	int LB;
+	int base;
+	uint32_t slot;        // record slot of the pair
+	uint32_t pad;
+};
+
+// One sweep over rows [pass*32R, (pass+1)*32R) of the row chain and the concatenated columns of the warp's chains.
+//   TRACE = false: the forward sweep.  Values only; saves a checkpoint every kStrip steps and tracks, per chain, the
+//                  lane's first maximum (kernel coordinates), parked in `best` when the lane moves on to the next chain.
 //   TRACE = true : re-run of strip `strip` (steps kStrip*strip .. s_last) from its checkpoint, writing one 64-bit
 //                  trace word per lane and step (4 bits per row) into `tile[(step % kStrip)*32 + lane]`.
-// colB: the column chain's residues, 8 e-letter bytes each (DevChains::prof8).
+// A lane that has consumed the last column of a chain re-initialises its row state and continues with column 0 of the
+// next chain at the very next step; its (M, D) hand-over registers keep serving the lane behind it, which is still one
+// column back in the old chain - each chain therefore sees exactly the values of a sweep of its own.
 // TR = false: kernel rows are the reference's A chain (index i), columns its B chain (j).
 // TR = true : rows are the reference's B chain, columns its A chain.  The recurrence is the same with the
 //             roles of the two gap states exchanged: the reference tests D (gap that consumes A) before I
 //             (sw.cpp:136-147), and its first-maximum rule prefers the smaller i, then the smaller j.
-// bnd_in / bnd_out: boundary row written by the previous pass / to be written by this one.
+// bnd_in / bnd_out: boundary row (indexed by concatenated column) written by the previous pass / by this one.
 template <int R, bool TR, bool TRACE>
 __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int lane, const bool first, const bool last,
-		const uint32_t row0, const uint32_t LA, const uint64_t *__restrict__ colB, const int LB,
+		const uint32_t row0, const uint32_t LA, const ColChain *chs, const int nch, const int total,
 		const float2 *__restrict__ bnd_in, float2 *__restrict__ bnd_out, float4 *__restrict__ ck, const float open,
-		const float ext, float &lbest, int &lbi, int &lbj, const int strip, const int s_last,
+		const float ext, float4 *__restrict__ best, const int strip, const int s_last,
 		unsigned long long *__restrict__ tile)
 {
 	constexpr int W1 = plane_width(R - 4), W2 = plane_width(R - 8);
@@ -169,9 +185,10 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 	const bool lane0 = (lane == 0);
 	const bool use_bnd = lane0 && !first;
 	const bool put_bnd = (lane == 31) && !last;
-	float mdiag_next = (lane0 && first) ? 0.0f : kNegInf;  // M[i0][0]; M[0][0] = 0 (sw.cpp:116)
+	const float mdiag_init = (lane0 && first) ? 0.0f : kNegInf;  // M[i0][0]; M[0][0] = 0 (sw.cpp:116)
+	float mdiag_next = mdiag_init;
 	float outM = kNegInf, outD = kNegInf;
-	const int nsteps = LB + 31;
+	const int nsteps = total + 31;
 	const int ngroups = (nsteps + 3) >> 2;
 
 	auto save = [&](const int k) {
@@ -208,32 +225,46 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 		outD = t[2 * R + 2];
 	};
 
-	int j = -lane;
+	// position of this lane: concatenated column v, chain c, column j of that chain
+	int v = -lane;
+	int c = 0;
 	if (TRACE) {
 		load(strip);
-		j = kStrip * strip - lane;
+		v = kStrip * strip - lane;
+		while (c + 1 < nch && v >= chs[c + 1].base)
+			++c;
 	}
+	int LBc = chs[c].LB;
+	const uint64_t *colp = chs[c].col;
+	int j = v - chs[c].base;
 	uint64_t cv = 0;
-	if (j >= 0 && j < LB)
-		cv = __ldg(colB + j);
+	if (j >= 0 && j < LBc)
+		cv = __ldg(colp + j);
 	float2 bn = make_float2(kNegInf, kNegInf);
-	if (use_bnd && j < LB)
-		bn = bnd_in[j];
+	if (use_bnd && v < total)
+		bn = bnd_in[v];
+	// running first maximum of the current chain
+	float lbest = 0.0f;
+	int lbi = 0x7fffffff, lbj = 0x7fffffff;
+	if (!TRACE && !first) {
+		const float4 b = best[c * 32 + lane];
+		lbest = b.x; lbi = __float_as_int(b.y); lbj = __float_as_int(b.z);
+	}
 
-	// CHECK = false: every lane is inside the matrix at this step and at the next one (no range predicates)
+	// CHECK = false: every lane is inside its matrix at this step and at the next one (no range predicates)
 	auto step = [&](auto check_tag) -> unsigned long long {
 		constexpr bool CHECK = decltype(check_tag)::value;
 		const float inM = __shfl_up_sync(kFull, outM, 1);
 		const float inD = __shfl_up_sync(kFull, outD, 1);
 		const int jn = j + 1;
 		uint64_t cn = cv;
-		if (!CHECK || (jn >= 0 && jn < LB))
-			cn = __ldg(colB + jn);
+		if (jn >= 0 && jn < LBc)
+			cn = __ldg(colp + jn);
 		float2 bn_next = bn;
-		if (use_bnd && (!CHECK || jn < LB))
-			bn_next = bnd_in[jn];
+		if (use_bnd && (!CHECK || v + 1 < total))
+			bn_next = bnd_in[v + 1];
 		uint32_t tw0 = 0, tw1 = 0;
-		if (!CHECK || (j >= 0 && j < LB)) {
+		if (!CHECK || (j >= 0 && j < LBc)) {
 			float d = lane0 ? bn.y : inD;  // D[i0][j]   (bn = -inf pair in the first pass)
 			const float mdiag = mdiag_next;  // M[i0][j]
 			mdiag_next = lane0 ? bn.x : inM;  // M[i0][j+1]
@@ -247,36 +278,36 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 			for (int f = 0; f < RSK_NFEAT; ++f) {
 				const uint32_t a0 = co[f] * 512u + base0;
 				const float4 v0 = *reinterpret_cast<const float4 *>(plane0 + a0);
-				float v[12];
-				v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+				float vv[12];
+				vv[0] = v0.x; vv[1] = v0.y; vv[2] = v0.z; vv[3] = v0.w;
 #pragma unroll
 				for (int r = 4; r < 12; ++r)
-					v[r] = 0.0f;
+					vv[r] = 0.0f;
 				if (W1 == 1) {
-					v[4] = *reinterpret_cast<const float *>(plane1 + (co[f] * 512u + base1));
+					vv[4] = *reinterpret_cast<const float *>(plane1 + (co[f] * 512u + base1));
 				} else if (W1 == 2) {
 					const float2 t = *reinterpret_cast<const float2 *>(plane1 + (co[f] * 512u + base1));
-					v[4] = t.x; v[5] = t.y;
+					vv[4] = t.x; vv[5] = t.y;
 				} else if (W1 == 4) {
 					const float4 t = *reinterpret_cast<const float4 *>(plane1 + a0);
-					v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w;
+					vv[4] = t.x; vv[5] = t.y; vv[6] = t.z; vv[7] = t.w;
 				}
 				if (W2 == 1) {
-					v[8] = *reinterpret_cast<const float *>(plane2 + (co[f] * 512u + base2));
+					vv[8] = *reinterpret_cast<const float *>(plane2 + (co[f] * 512u + base2));
 				} else if (W2 == 2) {
 					const float2 t = *reinterpret_cast<const float2 *>(plane2 + (co[f] * 512u + base2));
-					v[8] = t.x; v[9] = t.y;
+					vv[8] = t.x; vv[9] = t.y;
 				} else if (W2 == 4) {
 					const float4 t = *reinterpret_cast<const float4 *>(plane2 + a0);
-					v[8] = t.x; v[9] = t.y; v[10] = t.z; v[11] = t.w;
+					vv[8] = t.x; vv[9] = t.y; vv[10] = t.z; vv[11] = t.w;
 				}
 				// feature 0 assigns, 1..7 accumulate in this order (dssaligner.cpp:557-595)
 				if (f == 0) {
 #pragma unroll
 					for (int r = 0; r < R; ++r)
-						S[r] = v[r];
+						S[r] = vv[r];
 				} else {
-					add_vec<R>(S, v);
+					add_vec<R>(S, vv);
 				}
 			}
 			// the adds that do not depend on this column's gap chain, two rows at a time
@@ -343,7 +374,7 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 			outD = d;
 			if (!TRACE) {
 				if (put_bnd)
-					bnd_out[j] = make_float2(outM, outD);
+					bnd_out[v] = make_float2(outM, outD);
 				if (TR ? (xmax > lbest) : (xmax >= lbest)) {
 					// rare: a cell reached the lane's running maximum.  Keep the reference's first-maximum rule
 					// (row-major over (i,j), strict >).  !TR: higher score wins; equal score -> smaller row i; same row ->
@@ -364,8 +395,34 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 			}
 		}
 		j = jn;
+		++v;
 		cv = cn;
 		bn = bn_next;
+		if (j == LBc) {
+			// this lane has consumed its chain: park the chain's maximum and start the next chain with a fresh row state
+			if (!TRACE)
+				best[c * 32 + lane] = make_float4(lbest, __int_as_float(lbi), __int_as_float(lbj), 0.0f);
+			if (c + 1 < nch) {
+				++c;
+				LBc = chs[c].LB;
+				colp = chs[c].col;
+				j = 0;
+				cv = __ldg(colp);
+#pragma unroll
+				for (int r = 0; r < R; ++r) {
+					Mrow[r] = kNegInf;
+					Irow[r] = kNegInf;
+				}
+				mdiag_next = mdiag_init;
+				if (!TRACE) {
+					lbest = 0.0f; lbi = 0x7fffffff; lbj = 0x7fffffff;
+					if (!first) {
+						const float4 b = best[c * 32 + lane];
+						lbest = b.x; lbi = __float_as_int(b.y); lbj = __float_as_int(b.z);
+					}
+				}
+			}
+		}
 		return (unsigned long long)tw0 | ((unsigned long long)tw1 << 32);
 	};
 
@@ -379,7 +436,7 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 			const int s0 = 4 * g;
 			if ((g & (kStrip / 4 - 1)) == 0)
 				save(g / (kStrip / 4));
-			if (s0 >= 31 && s0 + 4 < LB) {
+			if (s0 >= 31 && s0 + 4 < total) {
 				step(std::false_type{});
 				step(std::false_type{});
 				step(std::false_type{});
@@ -395,23 +452,26 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 }
 
 // Resumable warp-cooperative traceback (sw.cpp:8-77).  The walk is in reference coordinates (i over A, j over B); TR maps
-// them onto the kernel's (row, column).  Trace nibble of cell (row, col): pass p = row / (32R), lane l = (row % 32R) / R,
-// nibble r = row % R, step s = col + l, strip k = s / kStrip, word tile[(s % kStrip)*32 + l].  Within a pass the step of
-// the walk never increases, so a strip is re-run once, up to the step at which the walk enters it.
+// them onto the kernel's (row, column).  Trace nibble of cell (row, col) of the chain whose first concatenated column is
+// `cbase`: pass p = row / (32R), lane l = (row % 32R) / R, nibble r = row % R, step s = cbase + col + l, strip k = s / kStrip,
+// word tile[(s % kStrip)*32 + l].  Within a pass the step of a walk never increases, so a strip is re-run up to the step
+// at which the walk enters it (a later chain of the same warp may need a few more steps of the same strip).
 struct TbState {
 	int i, j;      // reference DP coordinates of the walk (1-based cell indices as in sw.cpp)
 	int state;     // 0 = M, 1 = D, 2 = I
 	uint32_t n;    // columns emitted so far
-	int cur_p, cur_k;
+};
+struct TileCache {
+	int p, k, last;  // pass, strip and last step the tile currently holds
 };
 
 // Walks while the path stays in pass `pass` (whose row table is the one in shared memory).  Returns true when the path is
 // complete, false when it continues in the pass above.
 template <int R, bool TR>
 __device__ __forceinline__ bool traceback_in_pass(const unsigned char *smem_p0, const int lane, const int pass, const int npass,
-		const uint32_t LA, const uint64_t *__restrict__ colB, const int LB, float2 *__restrict__ bnd, const uint32_t bnd_pass_stride,
-		float4 *__restrict__ ck, const int nstrips, const float open, const float ext, unsigned long long *__restrict__ tile,
-		uint8_t *__restrict__ stage, TbState &t)
+		const uint32_t LA, const ColChain *chs, const int nch, const int total, const int cbase, float2 *__restrict__ bnd,
+		const uint32_t bnd_pass_stride, float4 *__restrict__ ck, const int nstrips, const float open, const float ext,
+		unsigned long long *__restrict__ tile, uint8_t *__restrict__ stage, TbState &t, TileCache &tc)
 {
 	constexpr int rows_per_pass = 32 * R;
 	for (;;) {
@@ -427,18 +487,17 @@ __device__ __forceinline__ bool traceback_in_pass(const unsigned char *smem_p0, 
 		const int rr = krow - p * rows_per_pass;
 		const int srcl = rr / R;
 		const int r = rr - srcl * R;
-		const int s = kcol + srcl;
+		const int s = cbase + kcol + srcl;
 		const int k = s / kStrip;
-		if (p != t.cur_p || k != t.cur_k) {
+		if (p != tc.p || k != tc.k || s > tc.last) {
 			__syncwarp();
-			float lb = 0.0f;
-			int li = 0, lj = 0;
-			sw_pass<R, TR, true>(smem_p0, lane, p == 0, p == npass - 1, (uint32_t)p * rows_per_pass + (uint32_t)lane * R, LA, colB, LB,
-					bnd + (size_t)(p > 0 ? p - 1 : 0) * bnd_pass_stride, nullptr, ck + (size_t)p * nstrips * ckpt_words(R) * 32, open,
-					ext, lb, li, lj, k, s, tile);
+			sw_pass<R, TR, true>(smem_p0, lane, p == 0, p == npass - 1, (uint32_t)p * rows_per_pass + (uint32_t)lane * R, LA, chs, nch,
+					total, bnd + (size_t)(p > 0 ? p - 1 : 0) * bnd_pass_stride, nullptr, ck + (size_t)p * nstrips * ckpt_words(R) * 32, open,
+					ext, nullptr, k, s, tile);
 			__syncwarp();
-			t.cur_p = p;
-			t.cur_k = k;
+			tc.p = p;
+			tc.k = k;
+			tc.last = s;
 		}
 		const unsigned long long w = tile[(s & (kStrip - 1)) * 32 + srcl];
 		const uint32_t nib = (uint32_t)(w >> (4 * r)) & 15u;
@@ -487,81 +546,102 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 	const float *tab = reinterpret_cast<const float *>(smem + kSmemTab);
 	float *planes = reinterpret_cast<float *>(smem + kSmemP0);
 	const unsigned char *smem_p0 = smem + kSmemP0;
+	ColChain *chs = reinterpret_cast<ColChain *>(smem + smem_chains_off(class_planes(sw_class_of_R(R)))) + warp * kSwChain;
 
 	const uint32_t LA = a.len_row[rowchain];  // kernel rows
 	const uint64_t *profA = a.prof_row + a.off_row[rowchain];
 	const int npass = (int)((LA + 32 * R - 1) / (32 * R));
 
-	const bool have = (uint32_t)warp < cnt;
-	uint32_t cidx = 0, slot = 0;
-	int LB = 0;  // kernel columns
-	const uint64_t *colB = nullptr;
-	if (have) {
-		cidx = a.clist[begin + warp];
-		if (a.cross) {
-			const uint32_t ra = TR ? cidx : rowchain, rb = TR ? rowchain : cidx;  // reference (a, b)
-			slot = (ra - a.a_begin) * a.nB + rb;
-		} else {
-			slot = a.cslot[begin + warp];
+	// this warp's column chains: entries warp, warp + W, warp + 2W ... of the task's list (the list is sorted by length, so
+	// every warp gets a similar total)
+	int nch = 0, total = 0;
+#pragma unroll
+	for (int k = 0; k < kSwChain; ++k) {
+		const uint32_t e = (uint32_t)(k * W + warp);
+		if (e < cnt) {
+			const uint32_t cidx = a.clist[begin + e];
+			const int LB = (int)a.len_col[cidx];
+			uint32_t slot;
+			if (a.cross) {
+				const uint32_t ra = TR ? cidx : rowchain, rb = TR ? rowchain : cidx;  // reference (a, b)
+				slot = (ra - a.a_begin) * a.nB + rb;
+			} else {
+				slot = a.cslot[begin + e];
+			}
+			if (lane == 0) {
+				chs[nch].col = a.prof_col + a.off_col[cidx];
+				chs[nch].LB = LB;
+				chs[nch].base = total;
+				chs[nch].slot = slot;
+			}
+			total += LB;
+			++nch;
 		}
-		LB = (int)a.len_col[cidx];
-		colB = a.prof_col + a.off_col[cidx];
 	}
-	const int nstrips = (((LB + 31 + 3) >> 2) + kStrip / 4 - 1) / (kStrip / 4);
+	__syncwarp();
+	const bool have = nch > 0;
+	const int nstrips = (((total + 31 + 3) >> 2) + kStrip / 4 - 1) / (kStrip / 4);
 	const size_t gw = (size_t)blockIdx.x * W + warp;
 	float4 *ck = a.ckpt + gw * a.ckpt_stride;
 	float2 *bnd = a.bnd + gw * a.bnd_stride;
 	uint8_t *stage = a.stage + gw * a.stage_stride;
 	unsigned long long *tile = a.tile + gw * (kStrip * 32);
+	float4 *best = a.best + gw * (kSwChain * 32);
 
-	float lbest = 0.0f;
-	int lbi = 0x7fffffff, lbj = 0x7fffffff;  // kernel (row, column) of the best cell
 	for (int pass = 0; pass < npass; ++pass) {
 		__syncthreads();  // every warp is done with the previous row table
 		build_rowtab<R, W * 32>(planes, tab, profA, LA, pass);
 		__syncthreads();
 		if (have)
-			sw_pass<R, TR, false>(smem_p0, lane, pass == 0, pass == npass - 1, (uint32_t)pass * 32 * R + (uint32_t)lane * R, LA, colB,
-					LB, bnd + (size_t)(pass > 0 ? pass - 1 : 0) * a.bnd_pass_stride, bnd + (size_t)pass * a.bnd_pass_stride,
-					ck + (size_t)pass * nstrips * ckpt_words(R) * 32, a.open, a.ext, lbest, lbi, lbj, 0, 0, nullptr);
+			sw_pass<R, TR, false>(smem_p0, lane, pass == 0, pass == npass - 1, (uint32_t)pass * 32 * R + (uint32_t)lane * R, LA, chs,
+					nch, total, bnd + (size_t)(pass > 0 ? pass - 1 : 0) * a.bnd_pass_stride, bnd + (size_t)pass * a.bnd_pass_stride,
+					ck + (size_t)pass * nstrips * ckpt_words(R) * 32, a.open, a.ext, best, 0, 0, nullptr);
 	}
-	bool active = false;
-	PairRec *rec = a.rec + slot;
-	if (have) {
-		// first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j
+	// per chain: first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j
+	float score[kSwChain];
+	TbState tb[kSwChain];
+	unsigned active = 0;
 #pragma unroll
-		for (int o = 16; o >= 1; o >>= 1) {
-			const float os = __shfl_xor_sync(kFull, lbest, o);
-			const int oi = __shfl_xor_sync(kFull, lbi, o);
-			const int oj = __shfl_xor_sync(kFull, lbj, o);
-			bool take;
-			if (!TR)  // i = row (unique per lane), j = column
-				take = os > lbest || (os == lbest && oi < lbi);
-			else      // i = column, j = row
-				take = os > lbest || (os == lbest && (oj < lbj || (oj == lbj && oi < lbi)));
-			if (take) {
-				lbest = os; lbi = oi; lbj = oj;
+	for (int k = 0; k < kSwChain; ++k) {
+		score[k] = 0.0f;
+		tb[k].i = tb[k].j = 0; tb[k].state = 0; tb[k].n = 0;
+		if (k < nch) {
+			const float4 b = best[k * 32 + lane];
+			float lbest = b.x;
+			int lbi = __float_as_int(b.y), lbj = __float_as_int(b.z);
+#pragma unroll
+			for (int o = 16; o >= 1; o >>= 1) {
+				const float os = __shfl_xor_sync(kFull, lbest, o);
+				const int oi = __shfl_xor_sync(kFull, lbi, o);
+				const int oj = __shfl_xor_sync(kFull, lbj, o);
+				bool take;
+				if (!TR)  // i = row (unique per lane), j = column
+					take = os > lbest || (os == lbest && oi < lbi);
+				else      // i = column, j = row
+					take = os > lbest || (os == lbest && (oj < lbj || (oj == lbj && oi < lbi)));
+				if (take) {
+					lbest = os; lbi = oi; lbj = oj;
+				}
 			}
-		}
-		if (lbest == 0.0f) {  // sw.cpp:200-201: no positive cell -> score 0, empty path
-			if (lane == 0) {
-				rec->score = 0.0f;
-				rec->lo_a = 0xffffffffu;
-				rec->lo_b = 0xffffffffu;
-				rec->path_len = 0;
-				rec->path_off = 0;
+			PairRec *rec = a.rec + chs[k].slot;
+			if (lbest == 0.0f) {  // sw.cpp:200-201: no positive cell -> score 0, empty path
+				if (lane == 0) {
+					rec->score = 0.0f;
+					rec->lo_a = 0xffffffffu;
+					rec->lo_b = 0xffffffffu;
+					rec->path_len = 0;
+					rec->path_off = 0;
+				}
+			} else {
+				active |= 1u << k;
+				score[k] = lbest;
+				tb[k].i = (TR ? lbj : lbi) + 1;
+				tb[k].j = (TR ? lbi : lbj) + 1;
 			}
-		} else {
-			active = true;
 		}
 	}
-	TbState t;
-	t.i = (TR ? lbj : lbi) + 1;
-	t.j = (TR ? lbi : lbj) + 1;
-	t.state = 0;
-	t.n = 0;
-	t.cur_p = -1;
-	t.cur_k = -1;
+	TileCache tc;
+	tc.p = -1; tc.k = -1; tc.last = -1;
 	__syncwarp();  // checkpoints and boundary rows written by other lanes of this warp are visible
 	for (int p = npass - 1; p >= 0; --p) {
 		if (p != npass - 1) {
@@ -569,16 +649,20 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 			build_rowtab<R, W * 32>(planes, tab, profA, LA, p);
 			__syncthreads();
 		}
-		if (active) {
-			if (traceback_in_pass<R, TR>(smem_p0, lane, p, npass, LA, colB, LB, bnd, a.bnd_pass_stride, ck, nstrips, a.open, a.ext,
-						tile, stage, t)) {
-				emit_path(a, lane, stage, lbest, t, rec);
-				active = false;
+#pragma unroll
+		for (int k = 0; k < kSwChain; ++k) {
+			if (active & (1u << k)) {
+				if (traceback_in_pass<R, TR>(smem_p0, lane, p, npass, LA, chs, nch, total, chs[k].base, bnd, a.bnd_pass_stride, ck, nstrips,
+							a.open, a.ext, tile, stage + (size_t)k * a.stage_chain_stride, tb[k], tc)) {
+					emit_path(a, lane, stage + (size_t)k * a.stage_chain_stride, score[k], tb[k], a.rec + chs[k].slot);
+					active &= ~(1u << k);
+				}
 			}
 		}
-		if (p > 0 && !__syncthreads_or(active ? 1 : 0))
+		if (p > 0 && !__syncthreads_or(active != 0 ? 1 : 0))
 			break;
 	}
+	__syncwarp();  // the chain list in shared memory is rewritten by the next task
 }
 
 // One kernel per (row-length class, orientation).  Class C handles a range of R with kClassWarps[C] warps: fewer rows
@@ -589,7 +673,7 @@ __global__ void __launch_bounds__(kClassWarps[C] * 32, 1) sw_affine_f32_tb_kerne
 	constexpr int W = kClassWarps[C];
 	extern __shared__ __align__(16) unsigned char smem[];
 	float *tab = reinterpret_cast<float *>(smem + kSmemTab);
-	volatile int *bcast = reinterpret_cast<volatile int *>(smem + kSmemP0 + class_planes(C) * kPlaneBytes);
+	volatile int *bcast = reinterpret_cast<volatile int *>(smem + smem_bcast_off(class_planes(C)));
 	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += W * 32)
 		tab[k] = a.tables[k];
 	__syncthreads();
@@ -607,8 +691,8 @@ __global__ void __launch_bounds__(kClassWarps[C] * 32, 1) sw_affine_f32_tb_kerne
 			const uint32_t ridx = task / a.nseg;
 			const uint32_t seg = task - ridx * a.nseg;
 			rowchain = a.rowlist[ridx];
-			begin = seg * W;
-			cnt = min((uint32_t)W, a.ncols - begin);
+			begin = seg * (W * kSwChain);
+			cnt = min((uint32_t)(W * kSwChain), a.ncols - begin);
 		} else {
 			rowchain = a.task_row[task];
 			begin = a.task_begin[task];
@@ -664,8 +748,8 @@ __global__ void pack_profiles_kernel(const uint8_t *__restrict__ planes, uint64_
 
 size_t sw_smem_bytes() { return class_smem(kSwClasses - 1); }
 
-// float4 units of checkpoints one warp needs for a pair with npass passes and LB columns (any R)
-uint64_t sw_ckpt_units(int npass, uint32_t LB)
+// float4 units of checkpoints one warp needs for npass passes over `LB` concatenated columns (any R)
+uint64_t sw_ckpt_units(int npass, uint64_t LB)
 {
 	const uint64_t nstrips = (((LB + 31 + 3) >> 2) + kStrip / 4 - 1) / (kStrip / 4);
 	return (uint64_t)npass * nstrips * ckpt_words(kMaxRowsPerLane) * 32;
