@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <numeric>
 #include <thread>
@@ -1025,6 +1026,10 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		bool active = false;
 	};
 	Job jobs[2];
+	const bool timing = getenv("RSK_TIMING") != nullptr;  // developer aid: host-side phases of the call on stderr
+	double t_wait = 0, t_d2h = 0, t_launch = 0;
+	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t_call0 = now();
 	double keep_ratio = (ctx->params.omega > 0) ? 0.02 : 1.0;  // expected share of reported pairs, refined per batch
 	uint64_t batches_left = batches.size();
 	bool nomem = false;
@@ -1148,7 +1153,9 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			CK(cudaMemcpyAsync(ctx->task_cnt.p, t_cnt.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
 			S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks;
 		}
+		const double tl0 = now();
 		int rc = run_batch(ctx, plan, b, opts);
+		t_launch += now() - tl0;
 		if (rc) {
 			if (!device_only)
 				abort_all();
@@ -1163,7 +1170,9 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		}
 		// the GPU is busy with this batch: now make sure the host buffer we are about to overwrite is free
 		Job &J = jobs[buf];
+		const double tw0 = now();
 		wait_job(J);
+		t_wait += now() - tw0;
 		if (nomem) {
 			abort_all();
 			return fail(RSK_ERR_NOMEM, "host memory for the hit records");
@@ -1174,6 +1183,7 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			return fail(RSK_ERR_NOMEM, "pinned record buffer");
 		}
 		unsigned long long pool_used = 0;
+		const double td0 = now();
 		CK(cudaMemcpyAsync(ctx->h_rec[buf].p, ctx->rec.p, b.npairs * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(&pool_used, ctx->d_pool_cursor, sizeof(pool_used), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
@@ -1208,6 +1218,7 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			pool_total += pool_used;
 			res->npath = pool_total;
 		}
+		t_d2h += now() - td0;  // includes waiting for the batch's kernels
 		rc = finish_batch_timing(ctx);
 		if (rc) {
 			abort_all();
@@ -1267,8 +1278,12 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 	}
 	if (!device_only) {
 		// explicit-mode KEEP_HITS hits arrive in sorted-pair order; cross-mode hits in (a, b) order
+		const double tt0 = now();
 		wait_job(jobs[bi & 1]);
 		wait_job(jobs[(bi + 1) & 1]);
+		if (timing)
+			fprintf(stderr, "[rsk_search] %zu batches: launch %.1f ms, kernels+D2H %.1f ms, waiting for host conversion %.1f ms, tail %.1f ms, call %.1f ms\n",
+					batches.size(), t_launch, t_d2h, t_wait, now() - tt0, now() - t_call0);
 		if (nomem) {
 			delete res;
 			return fail(RSK_ERR_NOMEM, "host memory for the hit records");

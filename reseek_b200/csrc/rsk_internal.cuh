@@ -59,7 +59,7 @@ constexpr int kSwChain = RSK_SW_CHAIN;       // column chains a warp aligns back
 // SW kernel classes by rows per lane: R <= 5 | R == 6 | R = 7..8 | R = 9..12, with the warps per CTA (= pairs per task) of each
 constexpr int kSwClasses = 4;
 #ifndef RSK_CLASS_W0
-#define RSK_CLASS_W0 20
+#define RSK_CLASS_W0 32
 #endif
 #ifndef RSK_CLASS_W1
 #define RSK_CLASS_W1 16
