@@ -190,6 +190,10 @@ extern "C" double rsk_qual(double ts)
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+// live contexts (a chain set may outlive its context; it may only hand memory back to a context that still exists)
+static std::mutex g_ctx_mu;
+static std::vector<rsk_ctx *> g_live_ctx;
+
 static int check_params(const rsk_params *p)
 {
 	if (!p)
@@ -285,6 +289,10 @@ extern "C" int rsk_ctx_create(int device, const rsk_params *params, void *cuda_s
 		rsk_ctx_destroy(ctx);
 		return rc;
 	}
+	{
+		std::lock_guard<std::mutex> g(g_ctx_mu);
+		g_live_ctx.push_back(ctx);
+	}
 	*out = ctx;
 	return RSK_OK;
 }
@@ -295,6 +303,14 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 		return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	{
+		std::lock_guard<std::mutex> g(g_ctx_mu);
+		g_live_ctx.erase(std::remove(g_live_ctx.begin(), g_live_ctx.end(), ctx), g_live_ctx.end());
+	}
+	for (auto &sl : ctx->slabs)
+		cudaFree(sl.first);
+	ctx->slabs.clear();
+	ctx->upload_stage.release();
 	ctx->ckpt.release(); ctx->tile.release(); ctx->best.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
 	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();
 	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
@@ -334,14 +350,70 @@ extern "C" int rsk_ctx_sync(rsk_ctx *ctx)
 // ------------------------------------------------------------------------------------------------
 // chain sets
 // ------------------------------------------------------------------------------------------------
+// Device memory of a chain set is ONE slab, recycled through its context: streaming a database through
+// upload -> search -> free (DBSearcher::RunQuery's blocks) would otherwise pay a dozen cudaMalloc / cudaFree round trips
+// (each cudaFree synchronises the device) per block.  A freed slab goes back to the context that made it, if that
+// context is still alive, and is handed to the next upload that fits.
+namespace {
+constexpr size_t kSlabCacheMax = 3;
+
+void *slab_get(rsk_ctx *ctx, size_t bytes, size_t &cap)
+{
+	{
+		std::lock_guard<std::mutex> g(g_ctx_mu);
+		int best = -1;
+		for (int k = 0; k < (int)ctx->slabs.size(); ++k)
+			if (ctx->slabs[k].second >= bytes && ctx->slabs[k].second <= bytes + bytes / 4 + (1 << 20) &&
+				(best < 0 || ctx->slabs[k].second < ctx->slabs[best].second))
+				best = k;
+		if (best >= 0) {
+			void *p = ctx->slabs[best].first;
+			cap = ctx->slabs[best].second;
+			ctx->slabs.erase(ctx->slabs.begin() + best);
+			return p;
+		}
+	}
+	void *p = nullptr;
+	cap = bytes;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) {
+		cudaGetLastError();
+		// make room: drop the cached slabs and try once more
+		std::vector<std::pair<void *, size_t>> drop;
+		{
+			std::lock_guard<std::mutex> g(g_ctx_mu);
+			drop.swap(ctx->slabs);
+		}
+		for (auto &sl : drop)
+			cudaFree(sl.first);
+		if (cudaMalloc(&p, bytes) != cudaSuccess) {
+			cudaGetLastError();
+			return nullptr;
+		}
+	}
+	return p;
+}
+
+void slab_put(rsk_ctx *ctx, void *p, size_t cap)
+{
+	if (!p)
+		return;
+	{
+		std::lock_guard<std::mutex> g(g_ctx_mu);
+		if (std::find(g_live_ctx.begin(), g_live_ctx.end(), ctx) != g_live_ctx.end() && ctx->slabs.size() < kSlabCacheMax) {
+			ctx->slabs.push_back({p, cap});
+			return;
+		}
+	}
+	cudaFree(p);
+}
+}  // namespace
+
 extern "C" void rsk_chainset_free(rsk_chainset *cs)
 {
 	if (!cs)
 		return;
 	cudaSetDevice(cs->device);
-	DevChains &d = cs->d;
-	cudaFree(d.len); cudaFree(d.off); cudaFree(d.prof8); cudaFree(d.mu);
-	cudaFree(d.x); cudaFree(d.y); cudaFree(d.z); cudaFree(d.selfrev);
+	slab_put(cs->ctx, cs->slab, cs->slab_bytes);  // cs->ctx is only compared against the live contexts, never dereferenced if gone
 	delete cs;
 }
 
@@ -379,22 +451,22 @@ extern "C" int rsk_chainset_upload(rsk_ctx *ctx, const rsk_chains_host *h, rsk_c
 	d.n = h->n;
 	d.total = tot;
 	cs->has_mu = h->mu != nullptr;
-	uint8_t *d_planes = nullptr;
-	bool ok = cudaMalloc((void **)&d.len, sizeof(uint32_t) * d.n) == cudaSuccess &&
-			  cudaMalloc((void **)&d.off, sizeof(uint64_t) * d.n) == cudaSuccess &&
-			  cudaMalloc((void **)&d.prof8, sizeof(uint64_t) * tot) == cudaSuccess &&
-			  cudaMalloc((void **)&d.x, sizeof(float) * tot) == cudaSuccess &&
-			  cudaMalloc((void **)&d.y, sizeof(float) * tot) == cudaSuccess &&
-			  cudaMalloc((void **)&d.z, sizeof(float) * tot) == cudaSuccess &&
-			  cudaMalloc((void **)&d.selfrev, sizeof(float) * d.n) == cudaSuccess &&
-			  cudaMalloc((void **)&d_planes, (size_t)RSK_NFEAT * tot) == cudaSuccess &&
-			  (!h->mu || cudaMalloc((void **)&d.mu, tot) == cudaSuccess);
-	if (!ok) {
+	// slab layout: every array on a 256-byte boundary
+	auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+	size_t o_len = 0, o_off = o_len + up(sizeof(uint32_t) * d.n), o_prof = o_off + up(sizeof(uint64_t) * d.n),
+		   o_x = o_prof + up(sizeof(uint64_t) * tot), o_y = o_x + up(sizeof(float) * tot), o_z = o_y + up(sizeof(float) * tot),
+		   o_sr = o_z + up(sizeof(float) * tot), o_mu = o_sr + up(sizeof(float) * d.n), o_end = o_mu + (h->mu ? up(tot) : 0);
+	cs->slab = slab_get(ctx, o_end, cs->slab_bytes);
+	if (!cs->slab || ctx->upload_stage.ensure((size_t)RSK_NFEAT * tot)) {
 		cudaGetLastError();
-		cudaFree(d_planes);
 		rsk_chainset_free(cs);
-		return fail(RSK_ERR_NOMEM, "rsk_chainset_upload: cudaMalloc failed for %llu residues", (unsigned long long)tot);
+		return fail(RSK_ERR_NOMEM, "rsk_chainset_upload: device memory for %llu residues", (unsigned long long)tot);
 	}
+	unsigned char *base = (unsigned char *)cs->slab;
+	d.len = (uint32_t *)(base + o_len); d.off = (uint64_t *)(base + o_off); d.prof8 = (uint64_t *)(base + o_prof);
+	d.x = (float *)(base + o_x); d.y = (float *)(base + o_y); d.z = (float *)(base + o_z); d.selfrev = (float *)(base + o_sr);
+	d.mu = h->mu ? (uint8_t *)(base + o_mu) : nullptr;
+	uint8_t *d_planes = ctx->upload_stage.p;
 	cudaStream_t st = ctx->stream;
 	std::vector<float> sr(d.n, FLT_MAX);
 	if (h->selfrev)
@@ -421,7 +493,6 @@ extern "C" int rsk_chainset_upload(rsk_ctx *ctx, const rsk_chains_host *h, rsk_c
 	}
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(st);
-	cudaFree(d_planes);
 	if (e != cudaSuccess) {
 		rsk_chainset_free(cs);
 		return fail(RSK_ERR_CUDA, "rsk_chainset_upload: %s", cudaGetErrorString(e));

@@ -29,7 +29,9 @@ using namespace rsk;
 struct rsk_chainset {
 	rsk_ctx *ctx = nullptr;  // identity only (never dereferenced by rsk_chainset_free: the context may be gone)
 	int device = 0;
-	DevChains d;
+	DevChains d;               // pointers into `slab`
+	void *slab = nullptr;      // the set's device memory (one allocation, recycled through the context)
+	size_t slab_bytes = 0;
 	std::vector<uint32_t> hlen;
 	std::vector<uint64_t> hoff;
 	uint32_t maxlen = 0;
@@ -104,6 +106,8 @@ struct rsk_ctx {
 	unsigned long long *d_pool_cursor = nullptr;
 	cudaEvent_t ev[8] = {};
 	// grow-only scratch
+	std::vector<std::pair<void *, size_t>> slabs;  // freed chain-set slabs waiting for reuse (guarded by the context registry lock)
+	DevBuf<uint8_t> upload_stage;                  // plane-major profile bytes of the upload in flight
 	DevBuf<float4> ckpt;
 	DevBuf<unsigned long long> tile;
 	DevBuf<float4> best;
