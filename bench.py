@@ -160,10 +160,24 @@ def run_reference(args):
                       "mode": "verysensitive", "sample": sample},
            "cpu_baseline": {"value": cps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": cps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout (see main)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    # Libraries chat on stdout (NCCL prints its version banner there): keep stdout for the JSON line alone by pointing
+    # file descriptor 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -353,7 +367,7 @@ def main():
             cps, pps, kind, cores, sample, ms = cpu_sample_run(q, db, steps=1, warmup=0)
             out["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                                    "chain_pairs_per_s": pps}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
