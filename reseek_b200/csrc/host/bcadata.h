@@ -16,28 +16,34 @@ const uint32_t BCA_MAGIC = 0xBCABCA;
 class BCAData
 	{
 public:
-	vector<string> m_Labels;
-	vector<uint64_t> m_Offsets;      // start of each chain record in the file
-	vector<uint32_t> m_SeqLengths;
-	string m_FN;
-	FILE *m_f = 0;
-	bool m_Writing = false;
-	bool m_Reading = false;
-	mutable std::mutex m_ReadLock;
+	// integer <-> float coordinates (pdbchain.h:89-90): 0.1 A resolution, offset 1000 A
+	static uint16_t CoordToIC(float X) { return uint16_t((X + 1000)*10 + 0.5); }
+	static float ICToCoord(uint16_t IC) { return float(IC/10.0f) - 1000; }
 
-public:
 	~BCAData() { Clear(); }
-	void Clear();
-	void Create(const string &FN);
+
+	// reading
 	void Open(const string &FN);
-	void WriteChain(const PDBChain &Chain);
 	void ReadChain(uint64_t ChainIdx, PDBChain &Chain) const;
-	void Close();
 	uint GetChainCount() const { return RSK_SIZE(m_Labels); }
 	uint GetSeqLength(uint64_t ChainIdx) const { return m_SeqLengths[ChainIdx]; }
 
-	static uint16_t CoordToIC(float X) { return uint16_t((X + 1000)*10 + 0.5); }  // pdbchain.h:89
-	static float ICToCoord(uint16_t IC) { return float(IC/10.0f) - 1000; }        // pdbchain.h:90
+	// writing
+	void Create(const string &FN);
+	void WriteChain(const PDBChain &Chain);
+
+	void Close();
+	void Clear();
+
+public:
+	string m_FN;
+	FILE *m_f = 0;
+	bool m_Reading = false;
+	bool m_Writing = false;
+	vector<string> m_Labels;         // one per chain
+	vector<uint32_t> m_SeqLengths;   // one per chain
+	vector<uint64_t> m_Offsets;      // file offset of each chain record (sequence, then integer coordinates)
+	mutable std::mutex m_ReadLock;   // ReadChain may be called from several loader threads
 	};
 
 }  // namespace reseek_b200
