@@ -5,12 +5,27 @@
 #include <string.h>
 #include <time.h>
 
+#include <chrono>
+
 namespace reseek_b200 {
 
 static void Check(int rc)
 	{
 	if (rc != RSK_OK)
 		Die("reseek_b200: %s", rsk_last_error());
+	}
+
+// RSK_TIMING=1: wall-clock phases of the host layer on stderr (developer aid)
+static double NowMs()
+	{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+	}
+static void Phase(const char *What, double &t0)
+	{
+	const double t1 = NowMs();
+	if (getenv("RSK_TIMING") != 0)
+		fprintf(stderr, "[reseek_b200 host] %-34s %9.1f ms\n", What, t1 - t0);
+	t0 = t1;
 	}
 
 bool VectorChainSource::GetNext(ChainData &CD)
@@ -148,7 +163,9 @@ void DBSearcher::RunSelf()
 	O.keep = RSK_KEEP_HITS;
 	O.want_paths = 1;
 	rsk_results *Res = 0;
+	double tp = NowMs();
 	Check(rsk_search_self(C, m_DBSet, &O, &Res));
+	Phase("RunSelf: rsk_search_self", tp);
 	AddStats();
 	const uint64_t N = rsk_results_count(Res);
 	const rsk_hit *Hits = rsk_results_hits(Res);
@@ -163,6 +180,7 @@ void DBSearcher::RunSelf()
 		if (H.a != H.b)
 			BaseOnAln(DA, false);
 		}
+	Phase("RunSelf: BaseOnAln over the hits", tp);
 	rsk_results_free(Res);
 	m_ProcessedQueryCount = GetDBChainCount();
 	m_Secs = (uint)(time(0) - t_start);
@@ -245,7 +263,11 @@ void DBSearcher::LoadDB(const string &DBFN)
 	LoaderParams.m_Omega = 0;
 	ChainFeatures F;
 	const bool WithMu = m_Params->m_Omega > 0;
-	ProfileLoader::Load(*m_Params, CR, 0, WithMu, GetContext(), LoaderParams, m_MaxEvalue, F);
+	double tp = NowMs();
+	rsk_ctx *C = GetContext();
+	Phase("LoadDB: context (CUDA init)", tp);
+	ProfileLoader::Load(*m_Params, CR, 0, WithMu, C, LoaderParams, m_MaxEvalue, F);
+	Phase("LoadDB: read + DSS + self-reverse", tp);
 	m_DBChains = F.Chains;
 	m_DBProfiles = F.Profiles;
 	if (WithMu)

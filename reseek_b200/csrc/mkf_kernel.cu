@@ -12,6 +12,8 @@
 // mapped as: one CTA per query chain for the hash table, one warp per pair for seeding/chaining/re-scoring, and
 // ONE THREAD per (pair, direction) for the banded DP, thousands of pairs in flight.  Every float operation is
 // performed in the reference's order, so scores and paths are bit-identical.
+#include <algorithm>
+
 #include "rsk_internal.cuh"
 
 namespace rsk {
@@ -268,24 +270,61 @@ __global__ void __launch_bounds__(kSeedWarps * 32) mkf_seed_kernel(const MkfArgs
 enum { XB_DM = 1, XB_IM = 2, XB_MD = 4, XB_MI = 8 };
 constexpr uint32_t kNone = 0xffffffffu;
 
+// Work list of the x-drop kernel: only (pair, direction) items whose seed is valid, ordered by the number of DP rows
+// (4 bins, longest first) so that the 32 sequential DPs of a warp have similar lengths.  Most pairs of a long chain with
+// an unrelated chain have no chain of HSPs at all; without the list their threads idle beside the few that work.
+constexpr int kXBins = 4;
+__device__ __forceinline__ int xdrop_bin(uint32_t rows) { return rows >= 512 ? 0 : rows >= 192 ? 1 : rows >= 64 ? 2 : 3; }
+__device__ __forceinline__ uint32_t xdrop_rows(const MkfArgs &a, uint32_t pair, uint32_t dir, const MkfSeed &sd)
+{
+	return dir ? sd.lo_a : a.lenA[a.pair_a[pair]] - sd.lo_a;
+}
+
+// cnt[0..3] = items per bin, cnt[4..7] = fill cursors
+__global__ void __launch_bounds__(256) mkf_bin_kernel(const MkfArgs a, const int fill)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= 2 * a.npairs)
+		return;
+	const uint32_t pair = t >> 1, dir = t & 1;
+	const MkfSeed sd = a.seeds[pair];
+	if (!fill) {
+		a.xres[t].score = 0.0f;
+		a.xres[t].path_len = 0;
+	}
+	if (!sd.valid)
+		return;
+	const int b = xdrop_bin(xdrop_rows(a, pair, dir, sd));
+	if (!fill) {
+		atomicAdd(a.xcnt + b, 1u);
+	} else {
+		uint32_t base = 0;
+		for (int k = 0; k < b; ++k)
+			base += a.xcnt[k];
+		a.xwork[base + atomicAdd(a.xcnt + kXBins + b, 1u)] = t;
+	}
+}
+
 // One thread per (pair, direction): xdropfwd.cpp:71-386.  dir 0 = forward from the seed, dir 1 = backward
 // (XDropBwd: the same DP on mirrored coordinates, xdropbwd.cpp:16-26).
+__device__ __forceinline__ void xdrop_item(const MkfArgs &a, const float *s_tab, const uint32_t t);
+
 __global__ void __launch_bounds__(64) mkf_xdrop_kernel(const MkfArgs a)
 {
 	__shared__ float s_tab[RSK_TABLE_FLOATS];
 	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += blockDim.x)
 		s_tab[k] = a.tables[k];
 	__syncthreads();
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= 2 * a.npairs)
-		return;
+	const uint32_t n = a.xcnt[0] + a.xcnt[1] + a.xcnt[2] + a.xcnt[3];
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x)
+		xdrop_item(a, s_tab, a.xwork[w]);
+}
+
+__device__ __forceinline__ void xdrop_item(const MkfArgs &a, const float *s_tab, const uint32_t t)
+{
 	const uint32_t pair = t >> 1, dir = t & 1;
 	MkfXdrop &res = a.xres[t];
-	res.score = 0.0f;
-	res.path_len = 0;
 	const MkfSeed sd = a.seeds[pair];
-	if (!sd.valid)
-		return;
 	const uint32_t qa = a.pair_a[pair], tb_ = a.pair_b[pair];
 	const uint64_t *PA = a.profA + a.offA[qa];
 	const uint64_t *PB = a.profB + a.offB[tb_];
@@ -496,15 +535,20 @@ __global__ void __launch_bounds__(128) mkf_finish_kernel(const MkfArgs a)
 
 }  // namespace
 
-int launch_mkf(const MkfArgs &args, uint32_t nhash, cudaStream_t stream)
+int launch_mkf(const MkfArgs &args, uint32_t nhash, int xgrid_blocks, cudaStream_t stream)
 {
 	if (args.npairs == 0)
 		return 0;
 	mkf_hash_kernel<<<nhash, 256, 0, stream>>>(args);
 	mkf_seed_kernel<<<(args.npairs + kSeedWarps - 1) / kSeedWarps, kSeedWarps * 32, 0, stream>>>(args);
-	mkf_xdrop_kernel<<<(2 * args.npairs + 63) / 64, 64, 0, stream>>>(args);
+	if (cudaMemsetAsync(args.xcnt, 0, 2 * kXBins * sizeof(uint32_t), stream) != cudaSuccess)
+		return -1;
+	mkf_bin_kernel<<<(2 * args.npairs + 255) / 256, 256, 0, stream>>>(args, 0);
+	mkf_bin_kernel<<<(2 * args.npairs + 255) / 256, 256, 0, stream>>>(args, 1);
+	const unsigned xblocks = (unsigned)std::min<uint64_t>(((uint64_t)2 * args.npairs + 63) / 64, (uint64_t)xgrid_blocks);
+	mkf_xdrop_kernel<<<xblocks, 64, 0, stream>>>(args);
 	mkf_finish_kernel<<<(args.npairs + 3) / 4, 128, 0, stream>>>(args);
-	return cudaGetLastError() == cudaSuccess ? 4 : -1;
+	return cudaGetLastError() == cudaSuccess ? 6 : -1;
 }
 
 size_t mkf_hash_bytes() { return (size_t)kDict * kHashW * sizeof(uint16_t); }

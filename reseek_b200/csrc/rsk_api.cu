@@ -190,6 +190,10 @@ extern "C" double rsk_qual(double ts)
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+// RSK_TIMING=1 accumulators of host-side phases (developer aid; single search thread assumed)
+static double g_t_plan = 0, g_t_tasks = 0, g_t_explicit = 0, g_t_keepwait = 0;
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // live contexts (a chain set may outlive its context; it may only hand memory back to a context that still exists)
 static std::mutex g_ctx_mu;
 static std::vector<rsk_ctx *> g_live_ctx;
@@ -318,7 +322,7 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->keep.release(); ctx->mu_bnd.release(); ctx->c_blist.release(); ctx->c_bslot.release();
 	ctx->c_task_a.release(); ctx->c_task_begin.release(); ctx->c_task_cnt.release(); ctx->rowlist.release(); ctx->colsort.release();
 	ctx->mk_a.release(); ctx->mk_b.release(); ctx->mk_slot.release(); ctx->mk_hash.release(); ctx->mk_hchain.release();
-	ctx->mk_off.release(); ctx->mk_ht.release(); ctx->mk_seed.release(); ctx->mk_x.release(); ctx->mk_scratch.release();
+	ctx->mk_off.release(); ctx->mk_work.release(); ctx->mk_cnt.release(); ctx->mk_ht.release(); ctx->mk_seed.release(); ctx->mk_x.release(); ctx->mk_scratch.release();
 	if (ctx->d_mu_mx) cudaFree(ctx->d_mu_mx);
 	if (ctx->d_mu_f32) cudaFree(ctx->d_mu_f32);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -606,10 +610,21 @@ int run_mkf(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b)
 	if (n == 0)
 		return RSK_OK;
 	ctx->stats.mkf_pairs += n;
-	const size_t scratch_cap = std::min<size_t>(ctx->scratch_budget / 2, (size_t)12 << 30);
-	const size_t max_hash = 1024;
+	const bool timing = getenv("RSK_TIMING") != nullptr;
+	auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_prep = 0, t_sync = 0, t_pre = 0;
+	size_t nchunks = 0;
+	if (timing) {
+		const double t0 = now();
+		cudaStreamSynchronize(st);  // what was queued before (Mu filter, SW): keep it out of the long-chain figures
+		t_pre = now() - t0;
+	}
+	const size_t scratch_cap = (size_t)40 << 30;  // trace matrices of the pairs in flight
+	const size_t max_hash = 4096;
 	size_t k0 = 0;
 	while (k0 < n) {
+		const double tc0 = now();
+		++nchunks;
 		std::vector<uint32_t> hidx, hchain;
 		std::vector<unsigned long long> off;
 		size_t bytes = 0, k1 = k0;
@@ -627,7 +642,7 @@ int run_mkf(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b)
 		}
 		const size_t m = k1 - k0;
 		if (ctx->mk_a.ensure(m) || ctx->mk_b.ensure(m) || ctx->mk_slot.ensure(m) || ctx->mk_hash.ensure(m) ||
-			ctx->mk_hchain.ensure(hchain.size()) || ctx->mk_off.ensure(m) || ctx->mk_seed.ensure(m) || ctx->mk_x.ensure(2 * m) ||
+			ctx->mk_hchain.ensure(hchain.size()) || ctx->mk_off.ensure(m) || ctx->mk_seed.ensure(m) || ctx->mk_x.ensure(2 * m) || ctx->mk_work.ensure(2 * m) || ctx->mk_cnt.ensure(8) ||
 			ctx->mk_ht.ensure(hchain.size() * (mkf_hash_bytes() / 2)) || ctx->mk_scratch.ensure(bytes + 256)) {
 			cudaGetLastError();
 			return fail(RSK_ERR_NOMEM, "long-chain path buffers (%zu pairs, %zu MB scratch)", m, bytes >> 20);
@@ -647,20 +662,26 @@ int run_mkf(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b)
 		ma.npairs = (uint32_t)m;
 		ma.pair_a = ctx->mk_a.p; ma.pair_b = ctx->mk_b.p; ma.pair_slot = ctx->mk_slot.p; ma.pair_hash = ctx->mk_hash.p;
 		ma.hash_chain = ctx->mk_hchain.p; ma.hash = ctx->mk_ht.p;
-		ma.seeds = ctx->mk_seed.p; ma.xres = ctx->mk_x.p;
+		ma.seeds = ctx->mk_seed.p; ma.xres = ctx->mk_x.p; ma.xwork = ctx->mk_work.p; ma.xcnt = ctx->mk_cnt.p;
 		ma.scratch = ctx->mk_scratch.p; ma.scratch_off = ctx->mk_off.p;
 		ma.rec = ctx->rec.p; ma.pool = ctx->pool.p; ma.pool_cursor = ctx->d_pool_cursor;
 		ma.mu_mx = ctx->d_mu_mx; ma.tables = ctx->d_tables;
 		ma.x1 = ctx->params.mkf_x1; ma.min_hsp_score = ctx->params.mkf_min_hsp_score;
 		ma.x2 = (float)ctx->params.mkf_x2; ma.min_mega_hsp_score = ctx->params.mkf_min_mega_hsp_score;
 		ma.open = ctx->params.gap_open; ma.ext = ctx->params.gap_ext;
-		int nl = launch_mkf(ma, (uint32_t)hchain.size(), st);
+		int nl = launch_mkf(ma, (uint32_t)hchain.size(), ctx->num_sms * 24, st);
 		if (nl < 0)
 			return fail(RSK_ERR_CUDA, "long-chain kernels failed to launch: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->stats.kernel_launches += nl;
+		const double ts0 = now();
+		t_prep += ts0 - tc0;
 		CK(cudaStreamSynchronize(st));  // the host vectors of this chunk are reused
+		t_sync += now() - ts0;
 		k0 = k1;
 	}
+	if (timing)
+		fprintf(stderr, "[rsk run_mkf] %zu pairs in %zu chunks: earlier kernels %.1f ms, host prep + launches %.1f ms, waiting for the long-chain kernels %.1f ms\n",
+				n, nchunks, t_pre, t_prep, t_sync);
 	return RSK_OK;
 }
 
@@ -797,12 +818,15 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	uint32_t e_off[kSwClasses + 1] = {};
 	if (!b.cross) {
 		std::vector<uint8_t> keep;
+		const double tk0 = now_ms();
 		if (filter) {
 			keep.resize(b.npairs);
 			CK(cudaMemcpyAsync(keep.data(), ctx->keep.p, b.npairs, cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
 			ctx->stats.d2h_bytes += b.npairs;
 		}
+		const double tk1 = now_ms();
+		g_t_keepwait += tk1 - tk0;
 		size_t k = 0;
 		uint64_t cells = 0;
 		while (k < b.npairs) {
@@ -839,6 +863,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		CK(cudaStreamSynchronize(st));  // the host vectors die at the end of this scope
 		ctx->filt_explicit_pairs = e_clist.size();
 		ctx->filt_explicit_cells = cells;
+		g_t_explicit += now_ms() - tk1;
 	}
 
 	// ---- K1: one launch per kernel class ----
@@ -1190,6 +1215,7 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 	for (const Batch &b0 : batches) {
 		Batch b = b0;
 		const int buf = (int)(bi++ & 1);
+		const double tt_0 = now_ms();
 		if (!b.cross) {
 			// build the Mu filter's tasks for sorted pairs [k0,k1): runs of equal A, chunks of one task's column count
 			const size_t task_cols = (std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32")) ? (size_t)kMuTaskCols : (size_t)kSwWarps;
@@ -1224,6 +1250,7 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			CK(cudaMemcpyAsync(ctx->task_cnt.p, t_cnt.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
 			S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks;
 		}
+		g_t_tasks += now_ms() - tt_0;
 		const double tl0 = now();
 		int rc = run_batch(ctx, plan, b, opts);
 		t_launch += now() - tl0;
@@ -1352,6 +1379,11 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		const double tt0 = now();
 		wait_job(jobs[bi & 1]);
 		wait_job(jobs[(bi + 1) & 1]);
+		if (timing) {
+			fprintf(stderr, "[rsk_search] host phases: task lists + H2D %.1f ms, waiting for the Mu filter (keep flags) %.1f ms, SW task lists + H2D %.1f ms, plan %.1f ms\n",
+					g_t_tasks, g_t_keepwait, g_t_explicit, g_t_plan);
+			g_t_tasks = g_t_keepwait = g_t_explicit = g_t_plan = 0;
+		}
 		if (timing)
 			fprintf(stderr, "[rsk_search] %zu batches: launch %.1f ms, kernels+D2H %.1f ms, waiting for host conversion %.1f ms, tail %.1f ms, call %.1f ms\n",
 					batches.size(), t_launch, t_d2h, t_wait, now() - tt0, now() - t_call0);
@@ -1393,24 +1425,35 @@ extern "C" int rsk_search_cross_device(rsk_ctx *ctx, const rsk_chainset *A, cons
 // then have similar lengths).  perm[k] = caller's index of the k-th scheduled pair.  A counting sort by A followed by an
 // independent (stable) sort of every run by B length, runs spread over the host threads: an all-vs-all of 11 k chains is
 // 6.3e7 pairs, for which one comparison sort over the whole list took longer than all kernels together.
+//
+// Long-chain pairs (DoMKF: a chain >= mkfl, Mu letters on both sides) are scheduled after all other pairs, again a-major:
+// their banded x-drop DPs are sequential per pair, so a batch must hold as many of them as possible to keep the GPU
+// busy behind the longest one; sprinkled over all batches (3 % of each) every batch would wait for its own straggler.
 static int build_explicit_plan(SearchPlan &plan, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
-		const uint32_t *ia, const uint32_t *ib, int nthreads)
+		const uint32_t *ia, const uint32_t *ib, int nthreads, uint32_t mkfl)
 {
 	plan.A = A; plan.B = B; plan.cross = false; plan.npairs = npairs;
 	const uint32_t nA = A->d.n, nB = B->d.n;
-	std::vector<uint64_t> start((size_t)nA + 1, 0);
+	const bool mkf_possible = A->has_mu && B->has_mu;
+	auto is_mkf = [&](uint32_t a, uint32_t b) {
+		const uint32_t la = A->hlen[a], lb = B->hlen[b];
+		return mkf_possible && la >= 3 && lb >= 3 && (la >= mkfl || lb >= mkfl);
+	};
+	// runs: key a for ordinary pairs, nA + a for long-chain pairs
+	const size_t nruns = (size_t)2 * nA;
+	std::vector<uint64_t> start(nruns + 1, 0);
 	for (uint64_t k = 0; k < npairs; ++k) {
 		if (ia[k] >= nA || ib[k] >= nB)
 			return fail(RSK_ERR_ARG, "pair %llu: chain index out of range (%u,%u)", (unsigned long long)k, ia[k], ib[k]);
-		++start[ia[k] + 1];
+		++start[(is_mkf(ia[k], ib[k]) ? (size_t)nA : 0) + ia[k] + 1];
 	}
-	for (uint32_t a = 0; a < nA; ++a)
-		start[a + 1] += start[a];
+	for (size_t r = 0; r < nruns; ++r)
+		start[r + 1] += start[r];
 	plan.perm.resize(npairs);
 	{
 		std::vector<uint64_t> cur(start.begin(), start.end() - 1);
 		for (uint64_t k = 0; k < npairs; ++k)
-			plan.perm[cur[ia[k]]++] = k;  // stable: caller order inside a run
+			plan.perm[cur[(is_mkf(ia[k], ib[k]) ? (size_t)nA : 0) + ia[k]]++] = k;  // stable: caller order inside a run
 	}
 	plan.sa.resize(npairs);
 	plan.sb.resize(npairs);
@@ -1421,11 +1464,12 @@ static int build_explicit_plan(SearchPlan &plan, const rsk_chainset *A, const rs
 		std::vector<uint32_t> bucket;
 		std::vector<uint64_t> tmp;
 		for (;;) {
-			const uint32_t a0 = next_a.fetch_add(64);
-			if (a0 >= nA)
+			const uint32_t r0 = next_a.fetch_add(64);
+			if (r0 >= nruns)
 				break;
-			for (uint32_t a = a0; a < std::min(nA, a0 + 64); ++a) {
-				const uint64_t lo = start[a], hi = start[a + 1], n = hi - lo;
+			for (uint32_t r = r0; r < std::min<size_t>(nruns, (size_t)r0 + 64); ++r) {
+				const uint32_t a = r >= nA ? r - nA : r;
+				const uint64_t lo = start[r], hi = start[r + 1], n = hi - lo;
 				if (n == 0)
 					continue;
 				uint64_t *pp = plan.perm.data() + lo;
@@ -1475,7 +1519,7 @@ extern "C" int rsk_search_pairs(rsk_ctx *ctx, const rsk_chainset *A, const rsk_c
 		return RSK_OK;
 	}
 	SearchPlan plan;
-	int rc = build_explicit_plan(plan, A, B, npairs, ia, ib, ctx->host_threads);
+	int rc = build_explicit_plan(plan, A, B, npairs, ia, ib, ctx->host_threads, ctx->params.mkfl);
 	if (rc)
 		return rc;
 	return search_impl(ctx, plan, opts, out, false);
@@ -1566,7 +1610,9 @@ extern "C" int rsk_search_self(rsk_ctx *ctx, const rsk_chainset *Sx, const rsk_s
 				ib[k] = (uint32_t)j;
 			}
 		SearchPlan plan;
-		int rc = build_explicit_plan(plan, Sx, Sx, np, ia.data(), ib.data(), ctx->host_threads);
+		const double tp0 = now_ms();
+		int rc = build_explicit_plan(plan, Sx, Sx, np, ia.data(), ib.data(), ctx->host_threads, ctx->params.mkfl);
+		g_t_plan += now_ms() - tp0;
 		rsk_results *part = nullptr;
 		if (!rc)
 			rc = search_impl(ctx, plan, opts, &part, false);

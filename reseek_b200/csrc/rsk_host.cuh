@@ -131,6 +131,7 @@ struct rsk_ctx {
 	DevBuf<uint16_t> mk_ht;
 	DevBuf<MkfSeed> mk_seed;
 	DevBuf<MkfXdrop> mk_x;
+	DevBuf<uint32_t> mk_work, mk_cnt;
 	DevBuf<unsigned char> mk_scratch;
 	Counters *d_counters = nullptr;
 	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU

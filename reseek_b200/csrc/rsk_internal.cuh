@@ -197,6 +197,8 @@ struct MkfArgs {
 	uint16_t *hash;
 	MkfSeed *seeds;              // [npairs]
 	MkfXdrop *xres;              // [2*npairs]
+	uint32_t *xwork;             // [2*npairs] work list of the x-drop kernel (valid items, longest first)
+	uint32_t *xcnt;              // [8] items per size bin + fill cursors
 	unsigned char *scratch; const unsigned long long *scratch_off;  // per pair
 	PairRec *rec;
 	uint8_t *pool; unsigned long long *pool_cursor;
@@ -204,7 +206,7 @@ struct MkfArgs {
 	int x1, min_hsp_score; float x2, min_mega_hsp_score;
 	float open, ext;
 };
-int launch_mkf(const MkfArgs &args, uint32_t nhash, cudaStream_t stream);
+int launch_mkf(const MkfArgs &args, uint32_t nhash, int xgrid_blocks, cudaStream_t stream);
 size_t mkf_hash_bytes();
 
 // K5: gapless Mu pre-scores
