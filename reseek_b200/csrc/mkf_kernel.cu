@@ -12,6 +12,8 @@
 // mapped as: one CTA per query chain for the hash table, one warp per pair for seeding/chaining/re-scoring, and
 // ONE THREAD per (pair, direction) for the banded DP, thousands of pairs in flight.  Every float operation is
 // performed in the reference's order, so scores and paths are bit-identical.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "rsk_internal.cuh"
@@ -470,6 +472,204 @@ __device__ __forceinline__ void xdrop_item(const MkfArgs &a, const float *s_tab,
 	res.path_len = n;  // stage[] holds the path from its end to its start
 }
 
+// The same DP as xdrop_item, flattened into a per-lane state machine: every trip of the loop computes ONE cell of the lane's
+// current item (or one traceback step, or the row / item bookkeeping), and a lane that has finished its item takes the next
+// one from the work list inside the same loop.  The 32 lanes of a warp therefore stay in the cell code together whatever
+// the lengths and band widths of their items are, and no warp waits for a straggler: on real SCOP40 data the
+// thread-per-item kernel ran with 7.8 of 32 lanes active and 9 % of the warp slots occupied (profiles/r1_mkf_xdrop_ncu.md).
+// Cells are visited in exactly the order of xdropfwd.cpp:71-386 with the same operations, so results are unchanged.
+__global__ void __launch_bounds__(64) mkf_xdrop_flat_kernel(const MkfArgs a)
+{
+	__shared__ float s_tab[RSK_TABLE_FLOATS];
+	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += blockDim.x)
+		s_tab[k] = a.tables[k];
+	__syncthreads();
+	const uint32_t nwork = a.xcnt[0] + a.xcnt[1] + a.xcnt[2] + a.xcnt[3];
+	const float open = a.open, ext = a.ext, X = a.x2;
+	const float absopen = -open, absext = -ext;
+	enum { P_FETCH, P_ROW_START, P_CELL, P_ROW_END, P_TB_INIT, P_TB_STEP };
+	int phase = P_FETCH;
+	// item
+	uint32_t t = 0, dir = 0, lo_a = 0, lo_b = 0, LA = 0, LB = 0;
+	const uint64_t *PA = nullptr, *PB = nullptr;
+	float *M = nullptr, *Dr = nullptr;
+	uint8_t *stage = nullptr, *tbm = nullptr, *row = nullptr;
+	size_t W = 0;
+	// DP
+	uint32_t i = 0, j = 0, jlo = 0, jhi = 0, prev_jlo = 0, prev_jhi = 0, next_jlo = 0, next_jhi = 0, endj = 0, besti = 0, bestj = 0;
+	float best = 0.0f, M0 = 0.0f, I0 = 0.0f;
+	uint64_t ea = 0;
+	// traceback
+	uint32_t ti = 0, tj = 0, tn = 0;
+	int st = 0;
+	for (;;) {
+		if (phase == P_FETCH) {
+			const uint32_t w = atomicAdd(a.xcnt + 2 * kXBins, 1u);
+			if (w >= nwork)
+				break;
+			t = a.xwork[w];
+			const uint32_t pair = t >> 1;
+			dir = t & 1;
+			const MkfSeed sd = a.seeds[pair];
+			lo_a = sd.lo_a; lo_b = sd.lo_b;
+			const uint32_t qa = a.pair_a[pair], tb_ = a.pair_b[pair];
+			PA = a.profA + a.offA[qa];
+			PB = a.profB + a.offB[tb_];
+			LA = dir ? lo_a : a.lenA[qa] - lo_a;
+			LB = dir ? lo_b : a.lenB[tb_] - lo_b;
+			unsigned char *base = a.scratch + a.scratch_off[pair];
+			if (!dir)
+				base += xdrop_region_bytes(lo_a, lo_b);
+			float *Mbuf = reinterpret_cast<float *>(base);
+			M = Mbuf + 1;
+			Dr = Mbuf + (LB + 4);
+			stage = reinterpret_cast<uint8_t *>(Mbuf + 2 * (LB + 4));
+			W = (size_t)LB + 3;
+			tbm = stage + (((size_t)LA + LB + 4 + 15) & ~(size_t)15);
+			a.xres[t].stage_off = (unsigned long long)(stage - a.scratch);
+			if (LA == 1 || LB == 1) {  // xdropfwd.cpp:87-93
+				const float sc = dir ? subst(s_tab, PA[lo_a - 1], PB[lo_b - 1]) : subst(s_tab, PA[lo_a], PB[lo_b]);
+				if (sc > 0) {
+					stage[0] = 'M';
+					a.xres[t].path_len = 1;
+				}
+				a.xres[t].score = sc;
+				continue;  // next item
+			}
+			M[-1] = kNegInf;
+			Dr[0] = kNegInf;
+			Dr[1] = kNegInf;
+			best = 0.0f; besti = 0; bestj = 0;
+			prev_jlo = 0; prev_jhi = 0; jlo = 1; jhi = 1;
+			M0 = best;
+			i = 1;
+			phase = P_ROW_START;
+		}
+		if (phase == P_ROW_START) {
+			if (jlo == prev_jlo) {
+				M[jlo - 1] = kNegInf;
+				Dr[jlo] = kNegInf;
+			}
+			endj = min(prev_jhi + 1, LB);
+			for (uint32_t j2 = endj + 1; j2 <= min(jhi + 1, LB); ++j2) {
+				M[j2 - 1] = kNegInf;
+				Dr[j2] = kNegInf;
+			}
+			next_jlo = kNone; next_jhi = kNone;
+			I0 = kNegInf;
+			row = tbm + (size_t)i * W;
+			ea = dir ? PA[lo_a - i] : PA[lo_a + i - 1];
+			j = jlo;
+			phase = P_CELL;
+		}
+		if (phase == P_CELL) {
+			uint8_t bits = 0;
+			const float saved = M0;
+			float x = M0;
+			const float dj = Dr[j];
+			if (dj > x) { x = dj; bits = XB_DM; }
+			if (I0 > x) { x = I0; bits = XB_IM; }
+			M0 = M[j];
+			const uint64_t eb = dir ? PB[lo_b - j] : PB[lo_b + j - 1];
+			float s = subst(s_tab, ea, eb);
+			s += x;
+			M[j] = s;
+			float h = s - best + X;
+			if (h > 0) { next_jlo = min(next_jlo, j + 1); next_jhi = j + 1; }
+			if (h > absopen) next_jlo = min(next_jlo, j);
+			if (h > absext && j == jhi && jhi + 1 < LB) {
+				++jhi;
+				const uint32_t ne = max(min(jhi + 1, LB), endj);
+				for (uint32_t j2 = endj + 1; j2 <= ne; ++j2) {
+					if (j2 - 1 > j) M[j2 - 1] = kNegInf;
+					Dr[j2] = kNegInf;
+				}
+				endj = ne;
+			}
+			if (s >= best) { best = s; besti = i; bestj = j; }
+			if (j != jlo) {
+				const float md = saved + open;
+				float dn = Dr[j] + ext;
+				if (md >= dn) { dn = md; bits |= XB_MD; }
+				Dr[j] = dn;
+				h = dn - best + X;
+				if (h > 0) { next_jlo = min(next_jlo, j - 1); next_jhi = max(next_jhi, j - 1); }
+			}
+			const float mi = saved + open;
+			I0 += ext;
+			if (mi >= I0) { I0 = mi; bits |= XB_MI; }
+			h = I0 - best + X;
+			if (h > 0) { next_jlo = min(next_jlo, j + 1); next_jhi = max(next_jhi, j + 1); }
+			if (h > absext && j == jhi && jhi + 1 < LB) {
+				++jhi;
+				const uint32_t ne = max(min(jhi + 1, LB), endj);
+				for (uint32_t j2 = endj + 1; j2 <= ne; ++j2) {
+					M[j2 - 1] = kNegInf;
+					Dr[j2] = kNegInf;
+				}
+				endj = ne;
+			}
+			row[j] = bits;
+			++j;
+			if (j > jhi)
+				phase = P_ROW_END;
+		}
+		if (phase == P_ROW_END) {
+			if (jhi < LB) {
+				const uint32_t j1 = jhi + 1;
+				uint8_t b1 = 0;
+				const float md = M0 + open;
+				float dn = Dr[j1] + ext;
+				if (md >= dn) { dn = md; b1 = XB_MD; }
+				Dr[j1] = dn;
+				row[j1] = b1;
+			}
+			if (next_jlo == kNone) {
+				phase = P_TB_INIT;
+			} else {
+				prev_jlo = jlo; prev_jhi = jhi;
+				jlo = next_jlo; jhi = next_jhi;
+				if (jlo > LB) jlo = LB;
+				if (jhi > LB) jhi = LB;
+				if (jlo == prev_jlo) { M0 = kNegInf; Dr[jlo] = kNegInf; }
+				else M0 = M[jlo - 1];
+				++i;
+				phase = (i > LA) ? P_TB_INIT : P_ROW_START;
+			}
+		}
+		if (phase == P_TB_INIT) {
+			if (!(best > 0.0f)) {
+				phase = P_FETCH;
+			} else {
+				a.xres[t].score = best;
+				ti = besti; tj = bestj; tn = 0; st = 0;
+				phase = P_TB_STEP;
+			}
+		}
+		if (phase == P_TB_STEP) {
+			stage[tn++] = (uint8_t)(st == 0 ? 'M' : st == 1 ? 'D' : 'I');
+			if (ti == 1 || tj == 1) {
+				a.xres[t].path_len = tn;  // stage[] holds the path from its end to its start
+				phase = P_FETCH;
+			} else {
+				int nx;
+				if (st == 0) {
+					const uint8_t c = tbm[(size_t)ti * W + tj];
+					nx = (c & XB_DM) ? 1 : (c & XB_IM) ? 2 : 0;
+					--ti; --tj;
+				} else if (st == 1) {
+					nx = (tbm[(size_t)ti * W + tj + 1] & XB_MD) ? 0 : 1;
+					--ti;
+				} else {
+					nx = (tbm[(size_t)(ti + 1) * W + tj] & XB_MI) ? 0 : 2;
+					--tj;
+				}
+				st = nx;
+			}
+		}
+	}
+}
+
 // One warp per pair: total score test, MergeFwdBwd, publish record + path.
 __global__ void __launch_bounds__(128) mkf_finish_kernel(const MkfArgs a)
 {
@@ -541,12 +741,16 @@ int launch_mkf(const MkfArgs &args, uint32_t nhash, int xgrid_blocks, cudaStream
 		return 0;
 	mkf_hash_kernel<<<nhash, 256, 0, stream>>>(args);
 	mkf_seed_kernel<<<(args.npairs + kSeedWarps - 1) / kSeedWarps, kSeedWarps * 32, 0, stream>>>(args);
-	if (cudaMemsetAsync(args.xcnt, 0, 2 * kXBins * sizeof(uint32_t), stream) != cudaSuccess)
+	if (cudaMemsetAsync(args.xcnt, 0, (2 * kXBins + 1) * sizeof(uint32_t), stream) != cudaSuccess)
 		return -1;
 	mkf_bin_kernel<<<(2 * args.npairs + 255) / 256, 256, 0, stream>>>(args, 0);
 	mkf_bin_kernel<<<(2 * args.npairs + 255) / 256, 256, 0, stream>>>(args, 1);
 	const unsigned xblocks = (unsigned)std::min<uint64_t>(((uint64_t)2 * args.npairs + 63) / 64, (uint64_t)xgrid_blocks);
-	mkf_xdrop_kernel<<<xblocks, 64, 0, stream>>>(args);
+	static const bool thread_per_item = getenv("RSK_XDROP_SEQ") != nullptr;  // the round-1 kernel, kept for A/B timing
+	if (thread_per_item)
+		mkf_xdrop_kernel<<<xblocks, 64, 0, stream>>>(args);
+	else
+		mkf_xdrop_flat_kernel<<<xblocks, 64, 0, stream>>>(args);
 	mkf_finish_kernel<<<(args.npairs + 3) / 4, 128, 0, stream>>>(args);
 	return cudaGetLastError() == cudaSuccess ? 6 : -1;
 }

@@ -642,7 +642,7 @@ int run_mkf(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b)
 		}
 		const size_t m = k1 - k0;
 		if (ctx->mk_a.ensure(m) || ctx->mk_b.ensure(m) || ctx->mk_slot.ensure(m) || ctx->mk_hash.ensure(m) ||
-			ctx->mk_hchain.ensure(hchain.size()) || ctx->mk_off.ensure(m) || ctx->mk_seed.ensure(m) || ctx->mk_x.ensure(2 * m) || ctx->mk_work.ensure(2 * m) || ctx->mk_cnt.ensure(8) ||
+			ctx->mk_hchain.ensure(hchain.size()) || ctx->mk_off.ensure(m) || ctx->mk_seed.ensure(m) || ctx->mk_x.ensure(2 * m) || ctx->mk_work.ensure(2 * m) || ctx->mk_cnt.ensure(16) ||
 			ctx->mk_ht.ensure(hchain.size() * (mkf_hash_bytes() / 2)) || ctx->mk_scratch.ensure(bytes + 256)) {
 			cudaGetLastError();
 			return fail(RSK_ERR_NOMEM, "long-chain path buffers (%zu pairs, %zu MB scratch)", m, bytes >> 20);
@@ -669,7 +669,7 @@ int run_mkf(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b)
 		ma.x1 = ctx->params.mkf_x1; ma.min_hsp_score = ctx->params.mkf_min_hsp_score;
 		ma.x2 = (float)ctx->params.mkf_x2; ma.min_mega_hsp_score = ctx->params.mkf_min_mega_hsp_score;
 		ma.open = ctx->params.gap_open; ma.ext = ctx->params.gap_ext;
-		int nl = launch_mkf(ma, (uint32_t)hchain.size(), ctx->num_sms * 24, st);
+		int nl = launch_mkf(ma, (uint32_t)hchain.size(), ctx->num_sms * 16, st);
 		if (nl < 0)
 			return fail(RSK_ERR_CUDA, "long-chain kernels failed to launch: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->stats.kernel_launches += nl;

@@ -198,7 +198,7 @@ struct MkfArgs {
 	MkfSeed *seeds;              // [npairs]
 	MkfXdrop *xres;              // [2*npairs]
 	uint32_t *xwork;             // [2*npairs] work list of the x-drop kernel (valid items, longest first)
-	uint32_t *xcnt;              // [8] items per size bin + fill cursors
+	uint32_t *xcnt;              // [9] items per size bin, fill cursors, work-list cursor of the x-drop kernel
 	unsigned char *scratch; const unsigned long long *scratch_off;  // per pair
 	PairRec *rec;
 	uint8_t *pool; unsigned long long *pool_cursor;
