@@ -156,3 +156,26 @@ def test_self_search_in_row_chunks_equals_one_piece(rb, mode, keep, monkeypatch)
         assert st0[k] == st1[k], k
     assert st1["sw_kernel_launches"] > st0["sw_kernel_launches"]
     ctx.close()
+
+
+def test_mu_filter_32bit_kernel_equals_packed_kernel(rb, monkeypatch):
+    """The packed 16-bit Mu filter (two chains per warp) is exact up to 8 000 residues; beyond that the host routes the batch
+    to the 32-bit kernel (RSK_MU32 forces it).  Both must give the same records."""
+    from reseek_b200 import synth
+    a = synth.make_chains(9, 170, seed=951, length_jitter=0.5)
+    b = synth.make_chains(70, 150, seed=952, length_jitter=0.6)
+    synth.plant_homologs(b, a, 0.5, seed=953)
+    ctx = rb.Context(0, rb.MODE_SENSITIVE)
+    A = ctx.upload(a.lens, a.prof, a.mu, a.xyz, a.selfrev)
+    B = ctx.upload(b.lens, b.prof, b.mu, b.xyz, b.selfrev)
+    r16 = ctx.search_cross(A, B, keep=rb.KEEP_ALL, want_paths=True)
+    s16 = ctx.search_self(B, keep=rb.KEEP_ALL, want_paths=False)
+    monkeypatch.setenv("RSK_MU32", "1")
+    r32 = ctx.search_cross(A, B, keep=rb.KEEP_ALL, want_paths=True)
+    s32 = ctx.search_self(B, keep=rb.KEEP_ALL, want_paths=False)
+    for x, y in ((r16, r32), (s16, s32)):
+        assert ((x.hits["flags"] & rb.HIT_MU_REJECTED) != 0).sum() > 10
+        for f in x.hits.dtype.names:
+            if f != "path_off":
+                assert np.array_equal(x.hits[f], y.hits[f]), f
+    ctx.close()
