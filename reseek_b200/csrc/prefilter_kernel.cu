@@ -218,38 +218,60 @@ __global__ void __launch_bounds__(128) pf_probe_kernel(const PfArgs a)
 }
 
 // ---- K8: two-hit diagonals -> FindHSP -> best score per (target, query) ----
+// Two phases per CTA (= per target): the sorted hit keys are scanned for the first element of every run of length >= 2 (a
+// two-hit diagonal) and those are queued in shared memory; then every thread of the CTA pulls diagonals from the queue and
+// runs the Kadane scan.  Scanning and walking in one loop left most threads idle (only run starts walk).
+constexpr int kPfQueue = 2048;
 __global__ void __launch_bounds__(128) pf_extend_kernel(const PfArgs a)
 {
 	__shared__ int S[36 * 36];
+	__shared__ uint32_t s_queue[kPfQueue];
+	__shared__ unsigned s_n, s_next;
 	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
 		S[k] = a.kmer_mx[k];
-	__syncthreads();
 	const uint32_t tl = blockIdx.x;
 	const uint32_t t = a.t_begin + tl;
 	const unsigned long long s0 = a.hit_off[tl], s1 = a.hit_off[tl + 1];
 	const uint32_t LT = a.lenT[t];
 	const uint8_t *T = a.muT + a.offT[t];
-	for (unsigned long long i = s0 + threadIdx.x; i + 1 < s1; i += blockDim.x) {
-		const uint32_t k = a.hit_sorted[i];
-		// first element of a run of length >= 2
-		if (a.hit_sorted[i + 1] != k || (i > s0 && a.hit_sorted[i - 1] == k))
-			continue;
-		const uint32_t q = k >> 14;
-		const int d = (int)(k & 0x3fffu);
-		const uint32_t LQ = a.lenQ[q];
-		const uint8_t *Q = a.muQ + a.offQ[q];
-		int qi = (int)LQ - d - 1, tj = 0;
-		if (qi < 0) { tj = -qi; qi = 0; }
-		int B = 0, F = 0;
-		for (; qi < (int)LQ && tj < (int)LT; ++qi, ++tj) {  // prefiltermu.cpp:27-46
-			F += S[36 * Q[qi] + T[tj]];
-			if (F > B) B = F;
-			else if (F < 0) F = 0;
+	// the scan advances in windows; a window ends early when the queue is full
+	unsigned long long base = s0;
+	while (base + 1 < s1) {
+		if (threadIdx.x == 0) { s_n = 0; s_next = 0; }
+		__syncthreads();
+		const unsigned long long wend = min(s1 - 1, base + (unsigned long long)kPfQueue);  // at most kPfQueue candidates per window
+		for (unsigned long long i = base + threadIdx.x; i < wend; i += blockDim.x) {
+			const uint32_t k = a.hit_sorted[i];
+			// first element of a run of length >= 2
+			if (a.hit_sorted[i + 1] == k && !(i > s0 && a.hit_sorted[i - 1] == k))
+				s_queue[atomicAdd(&s_n, 1u)] = k;
 		}
-		if (B > 0) {
-			if (B >= 65535) B = 65534;  // prefiltermu.cpp:294-295
-			atomicMax(&a.best[(size_t)tl * a.nQ + q], (unsigned)B);
+		__syncthreads();
+		const unsigned n = s_n;
+		for (;;) {
+			const unsigned w = atomicAdd(&s_next, 1u);
+			if (w >= n)
+				break;
+			const uint32_t k = s_queue[w];
+			const uint32_t q = k >> 14;
+			const int d = (int)(k & 0x3fffu);
+			const uint32_t LQ = a.lenQ[q];
+			const uint8_t *Q = a.muQ + a.offQ[q];
+			int qi = (int)LQ - d - 1, tj = 0;
+			if (qi < 0) { tj = -qi; qi = 0; }
+			int B = 0, F = 0;
+			for (; qi < (int)LQ && tj < (int)LT; ++qi, ++tj) {  // prefiltermu.cpp:27-46
+				F += S[36 * Q[qi] + T[tj]];
+				if (F > B) B = F;
+				else if (F < 0) F = 0;
+			}
+			if (B > 0) {
+				if (B >= 65535) B = 65534;  // prefiltermu.cpp:294-295
+				atomicMax(&a.best[(size_t)tl * a.nQ + q], (unsigned)B);
+			}
 		}
+		__syncthreads();
+		base = wend;
 	}
 }
 

@@ -314,6 +314,9 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	for (auto &sl : ctx->slabs)
 		cudaFree(sl.first);
 	ctx->slabs.clear();
+	if (ctx->pf_scratch && ctx->pf_scratch_free)
+		ctx->pf_scratch_free(ctx->pf_scratch);
+	ctx->pf_scratch = nullptr;
 	ctx->upload_stage.release();
 	ctx->ckpt.release(); ctx->tile.release(); ctx->best.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
 	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();

@@ -106,6 +106,8 @@ struct rsk_ctx {
 	unsigned long long *d_pool_cursor = nullptr;
 	cudaEvent_t ev[8] = {};
 	// grow-only scratch
+	void *pf_scratch = nullptr;                    // prefilter scratch (rsk_prefilter.cu), freed through pf_scratch_free
+	void (*pf_scratch_free)(void *) = nullptr;
 	std::vector<std::pair<void *, size_t>> slabs;  // freed chain-set slabs waiting for reuse (guarded by the context registry lock)
 	DevBuf<uint8_t> upload_stage;                  // plane-major profile bytes of the upload in flight
 	DevBuf<float4> ckpt;

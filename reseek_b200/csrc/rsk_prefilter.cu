@@ -9,6 +9,7 @@
 #include <chrono>
 #include <map>
 #include <memory>
+#include <thread>
 
 #include "rsk_host.cuh"
 
@@ -81,23 +82,66 @@ void bag_add(Bag &b, uint32_t B, uint32_t t, uint16_t score)  // AddScore
 		bag_truncate(b, B);
 }
 
-// RankedScoresBag::ToTsv (rankedscoresbag.cpp:185-232): final truncation, then target -> queries (ascending)
-void finish_bags(std::vector<Bag> &bags, uint32_t B, rsk_prefilter_result &res)
+// A query's bag only ever sees that query's triples, in stream order: the bags are independent, so the stream is replayed by
+// several host threads, each feeding the queries q % T == t.  Results are those of the single-threaded loop.
+void feed_bags(std::vector<Bag> &bags, uint32_t B, const uint32_t *t, const uint32_t *q, const uint16_t *s, uint64_t n, int nthreads)
 {
-	std::map<uint32_t, std::vector<std::pair<uint32_t, uint16_t>>> inv;
-	for (uint32_t q = 0; q < (uint32_t)bags.size(); ++q) {
-		bag_truncate(bags[q], B);
+	const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, nthreads), std::min<uint64_t>(bags.size(), n >> 14)));
+	if (T == 1) {
+		for (uint64_t k = 0; k < n; ++k)
+			bag_add(bags[q[k]], B, t[k], s[k]);
+		return;
+	}
+	std::vector<std::thread> th;
+	for (int w = 0; w < T; ++w)
+		th.emplace_back([&, w]() {
+			for (uint64_t k = 0; k < n; ++k)
+				if ((int)(q[k] % (uint32_t)T) == w)
+					bag_add(bags[q[k]], B, t[k], s[k]);
+		});
+	for (auto &x : th)
+		x.join();
+}
+
+// RankedScoresBag::ToTsv (rankedscoresbag.cpp:185-232): final truncation, then target -> queries (ascending)
+void finish_bags(std::vector<Bag> &bags, uint32_t B, rsk_prefilter_result &res, int nthreads)
+{
+	const uint32_t nQ = (uint32_t)bags.size();
+	const int T = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)std::max(1, nthreads), nQ / 4));
+	if (T == 1) {
+		for (uint32_t q = 0; q < nQ; ++q)
+			bag_truncate(bags[q], B);
+	} else {
+		std::vector<std::thread> th;
+		for (int w = 0; w < T; ++w)
+			th.emplace_back([&, w]() {
+				for (uint32_t q = (uint32_t)w; q < nQ; q += (uint32_t)T)
+					bag_truncate(bags[q], B);
+			});
+		for (auto &x : th)
+			x.join();
+	}
+	// invert: (target, query) ascending; a (target, query) pair occurs at most once
+	std::vector<uint64_t> key;
+	std::vector<uint16_t> sc;
+	size_t tot = 0;
+	for (auto &b : bags)
+		tot += b.t.size();
+	key.reserve(tot);
+	for (uint32_t q = 0; q < nQ; ++q)
 		for (size_t k = 0; k < bags[q].t.size(); ++k)
-			inv[bags[q].t[k]].emplace_back(q, bags[q].s[k]);
+			key.push_back(((uint64_t)bags[q].t[k] << 32) | ((uint64_t)q << 16) | bags[q].s[k]);
+	std::sort(key.begin(), key.end());
+	res.t.reserve(tot); res.q.reserve(tot); res.s.reserve(tot);
+	uint32_t nt = 0;
+	for (size_t k = 0; k < key.size(); ++k) {
+		const uint32_t tt = (uint32_t)(key[k] >> 32);
+		nt += (k == 0 || tt != (uint32_t)(key[k - 1] >> 32));
+		res.t.push_back(tt);
+		res.q.push_back((uint32_t)(key[k] >> 16) & 0xffffu);
+		res.s.push_back((uint16_t)(key[k] & 0xffffu));
 	}
-	for (auto &kv : inv) {
-		for (auto &e : kv.second) {
-			res.t.push_back(kv.first);
-			res.q.push_back(e.first);
-			res.s.push_back(e.second);
-		}
-	}
-	res.ntargets = (uint32_t)inv.size();
+	res.ntargets = nt;
 }
 
 struct PfScratch {
@@ -182,7 +226,12 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 		*out = guard.release();
 		return RSK_OK;
 	}
-	PfScratch S;
+	// grow-only device scratch kept in the context: a streamed database calls this once per block of targets
+	if (!ctx->pf_scratch) {
+		ctx->pf_scratch = new PfScratch();
+		ctx->pf_scratch_free = [](void *p) { delete static_cast<PfScratch *>(p); };
+	}
+	PfScratch &S = *static_cast<PfScratch *>(ctx->pf_scratch);
 	PfArgs a = {};
 	PhaseTimer tm;
 	tm.st = st;
@@ -191,7 +240,8 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 		const int8_t *m8 = rsk_mu_kmer_matrix_i8();
 		for (int k = 0; k < 36 * 36; ++k)
 			mx[k] = m8[k];
-		CK(cudaMalloc((void **)&S.kmer_mx, sizeof(int) * 36 * 36));
+		if (!S.kmer_mx)
+			CK(cudaMalloc((void **)&S.kmer_mx, sizeof(int) * 36 * 36));
 		CK(cudaMemcpyAsync(S.kmer_mx, mx.data(), sizeof(int) * 36 * 36, cudaMemcpyHostToDevice, st));
 		CK(cudaStreamSynchronize(st));
 	}
@@ -342,8 +392,7 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 				res->q.insert(res->q.end(), cq.begin(), cq.end());
 				res->s.insert(res->s.end(), cs.begin(), cs.end());
 			} else {
-				for (unsigned long long k = 0; k < nc; ++k)
-					bag_add(bags[cq[k]], B, ct[k], cs[k]);
+				feed_bags(bags, B, ct.data(), cq.data(), cs.data(), nc, ctx->host_threads);
 			}
 			res->raw += nc;
 		}
@@ -356,7 +405,7 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 			nt += (k == 0 || res->t[k] != res->t[k - 1]);
 		res->ntargets = nt;
 	} else {
-		finish_bags(bags, B, *res);
+		finish_bags(bags, B, *res, ctx->host_threads);
 	}
 	tm.mark("finish bags");
 	ctx->stats.kernel_launches += launches;
@@ -373,15 +422,17 @@ extern "C" int rsk_prefilter_bag(uint32_t nq, uint64_t n, const uint32_t *t, con
 		return fail(RSK_ERR_ARG, "rsk_prefilter_bag: null argument");
 	*out = nullptr;
 	const uint32_t B = rsb_size ? rsb_size : 1500u;
+	if (nq >= (1u << 16))
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter_bag: at most 65535 queries (got %u)", nq);
 	std::vector<Bag> bags(nq);
-	for (uint64_t k = 0; k < n; ++k) {
+	for (uint64_t k = 0; k < n; ++k)
 		if (q[k] >= nq)
 			return fail(RSK_ERR_ARG, "rsk_prefilter_bag: triple %llu names query %u of %u", (unsigned long long)k, q[k], nq);
-		bag_add(bags[q[k]], B, t[k], s[k]);
-	}
+	const int nthreads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+	feed_bags(bags, B, t, q, s, n, nthreads);
 	auto *res = new rsk_prefilter_result();
 	res->raw = n;
-	finish_bags(bags, B, *res);
+	finish_bags(bags, B, *res, nthreads);
 	*out = res;
 	return RSK_OK;
 }
