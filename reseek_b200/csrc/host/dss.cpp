@@ -20,6 +20,44 @@ void DSS::Init(const PDBChain &Chain)
 	m_SSE_Mids.clear();
 	m_SSE_cs.clear();
 	m_SSEsSet = false;
+	m_ExpBand.clear();
+	m_DistBand.clear();
+	m_ConfLetters.clear();
+	}
+
+// d(i, j) for every residue pair up to m_NEN_W apart, computed once per chain: the neighbour searches (CalcNEN, CalcREN)
+// and the density sums all ask for these same float distances, several times each.
+void DSS::SetDistBand()
+	{
+	if (!m_DistBand.empty())
+		return;
+	const uint L = GetSeqLength();
+	const uint Wd = (uint) m_NEN_W;
+	m_DistBand.assign((size_t) L*Wd + 1, 0.0f);
+	for (uint i = 0; i < L; ++i)
+		for (uint k = 0; k < Wd && i + 1 + k < L; ++k)
+			m_DistBand[(size_t) i*Wd + k] = GetDist(*m_Chain, i, i + 1 + k);
+	}
+
+// exp(-d(i,j)/Radius) for every residue pair up to 50 apart, computed once per chain.  GetDensity and GetSSDensity of the
+// reference evaluate this same expression for (Pos, Pos2) and again for (Pos2, Pos) and again for the second feature
+// (dss.cpp:236-241, 362-367); d(i,j) is symmetric to the bit (float subtraction, squares) and exp is a function, so the
+// stored factor is the value the reference computes each time, and the sums below add them in the reference's order.
+void DSS::SetExpBand()
+	{
+	if (!m_ExpBand.empty())
+		return;
+	const uint L = GetSeqLength();
+	const uint Wd = (uint) (m_Density_W > m_SSDensity_W ? m_Density_W : m_SSDensity_W);
+	m_ExpBandW = Wd;
+	SetDistBand();
+	m_ExpBand.assign((size_t) L*Wd + 1, 0.0);
+	for (uint i = 0; i < L; ++i)
+		for (uint k = 0; k < Wd && i + 1 + k < L; ++k)
+			{
+			const double Dist = BandDist(i, i + 1 + k);
+			m_ExpBand[(size_t) i*Wd + k] = exp(-Dist/m_Density_Radius);
+			}
 	}
 
 // float subtraction, float sum of squares (left to right), float sqrt
@@ -92,7 +130,7 @@ uint DSS::CalcNEN(uint Pos) const
 		{
 		if (Pos2 + m_NEN_w >= Pos && Pos2 <= Pos + m_NEN_w)
 			continue;
-		const double Dist = GetDist(*m_Chain, Pos, Pos2);
+		const double Dist = BandDist(Pos, Pos2);
 		if (Dist < MinDist)
 			{
 			MinDist = Dist;
@@ -131,7 +169,7 @@ uint DSS::CalcREN(uint Pos, uint NEN) const
 		{
 		if (Pos2 + m_NEN_w >= Pos && Pos2 <= Pos + m_NEN_w)
 			continue;
-		const double Dist = GetDist(*m_Chain, Pos, Pos2);
+		const double Dist = BandDist(Pos, Pos2);
 		if (Dist < MinDist)
 			{
 			MinDist = Dist;
@@ -145,6 +183,7 @@ void DSS::SetNENs()
 	{
 	if (!m_NENs.empty())
 		return;
+	SetDistBand();
 	const uint L = GetSeqLength();
 	m_NENs.reserve(L);
 	m_RENs.reserve(L);
@@ -205,15 +244,31 @@ static uint ConfLetter(const PDBChain &Chain, uint Pos)
 	return Best;
 	}
 
-uint DSS::Get_Conf(uint Pos) { return ConfLetter(*m_Chain, Pos); }  // myss.cpp:185-193
+// the conformation letter of a position is asked for by Conf (its own) and by NENConf (its neighbour's): once per position
+void DSS::SetConfLetters()
+	{
+	if (!m_ConfLetters.empty())
+		return;
+	const uint L = GetSeqLength();
+	m_ConfLetters.resize(L);
+	for (uint Pos = 0; Pos < L; ++Pos)
+		m_ConfLetters[Pos] = byte(ConfLetter(*m_Chain, Pos));
+	}
+
+uint DSS::Get_Conf(uint Pos)  // myss.cpp:185-193
+	{
+	SetConfLetters();
+	return m_ConfLetters[Pos];
+	}
 
 uint DSS::Get_NENConf(uint Pos)  // myss.cpp:195-210
 	{
 	SetNENs();
+	SetConfLetters();
 	const uint NEN = m_NENs[Pos];
 	if (NEN == UINT_MAX)
 		return WILDCARD;
-	return ConfLetter(*m_Chain, NEN);
+	return m_ConfLetters[NEN];
 	}
 
 // dss.cpp:217-244: sum of exp(-d/20) over +-50 residues excluding +-3; undefined (DBL_MAX) at the chain ends
@@ -233,8 +288,7 @@ double DSS::GetDensity(uint Pos) const
 		{
 		if (Pos2 + m_Density_w >= Pos && Pos2 <= Pos + m_Density_w)
 			continue;
-		const double Dist = GetDist(*m_Chain, Pos, Pos2);
-		D += exp(-Dist/m_Density_Radius);
+		D += ExpFactor(Pos, Pos2);
 		}
 	return D;
 	}
@@ -244,6 +298,7 @@ void DSS::SetDensity_ScaledValues()
 	{
 	if (!m_Density_ScaledValues.empty())
 		return;
+	SetExpBand();
 	const uint L = GetSeqLength();
 	vector<double> Values;
 	Values.reserve(L);
@@ -274,6 +329,7 @@ void DSS::SetDensity_ScaledValues()
 double DSS::GetSSDensity(uint Pos, char c)
 	{
 	SetSS();
+	SetExpBand();
 	const uint L = GetSeqLength();
 	if (Pos == 0 || Pos + 1 >= L)
 		return DBL_MAX;
@@ -289,8 +345,7 @@ double DSS::GetSSDensity(uint Pos, char c)
 		{
 		if (Pos2 + m_SSDensity_w >= Pos && Pos2 <= Pos + m_SSDensity_w)
 			continue;
-		const double Dist = GetDist(*m_Chain, Pos, Pos2);
-		const double DistFactor = exp(-Dist/m_Density_Radius);
+		const double DistFactor = ExpFactor(Pos, Pos2);
 		D += DistFactor;
 		if (m_SS[Pos2] == c)
 			Dc += DistFactor;

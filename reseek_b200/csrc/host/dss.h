@@ -38,6 +38,10 @@ public:
 	vector<double> m_Density_ScaledValues;
 	vector<uint> m_SSE_Mids;
 	vector<char> m_SSE_cs;
+	vector<double> m_ExpBand;     // exp(-d(i, i+1+k)/Radius), k < m_ExpBandW (see SetExpBand)
+	uint m_ExpBandW = 0;
+	vector<float> m_DistBand;     // d(i, i+1+k), k < m_NEN_W (see SetDistBand)
+	vector<byte> m_ConfLetters;   // conformation letter of every position
 
 	// dss.h:23-37
 	int m_Density_W = 50;
@@ -70,6 +74,19 @@ public:
 	void SetNENs();
 	void SetSSEs();
 	void SetDensity_ScaledValues();
+	void SetExpBand();
+	void SetDistBand();
+	void SetConfLetters();
+	float BandDist(uint Pos, uint Pos2) const   // |Pos - Pos2| in 1..m_NEN_W
+		{
+		const uint lo = Pos < Pos2 ? Pos : Pos2, d = Pos < Pos2 ? Pos2 - Pos : Pos - Pos2;
+		return m_DistBand[(size_t) lo*(uint) m_NEN_W + (d - 1)];
+		}
+	double ExpFactor(uint Pos, uint Pos2) const
+		{
+		const uint lo = Pos < Pos2 ? Pos : Pos2, d = Pos < Pos2 ? Pos2 - Pos : Pos - Pos2;
+		return m_ExpBand[(size_t) lo*m_ExpBandW + (d - 1)];
+		}
 	double GetDensity(uint Pos) const;
 	double GetSSDensity(uint Pos, char c);
 	uint CalcNEN(uint Pos) const;
