@@ -672,7 +672,12 @@ int run_mkf(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b)
 		ma.x1 = ctx->params.mkf_x1; ma.min_hsp_score = ctx->params.mkf_min_hsp_score;
 		ma.x2 = (float)ctx->params.mkf_x2; ma.min_mega_hsp_score = ctx->params.mkf_min_mega_hsp_score;
 		ma.open = ctx->params.gap_open; ma.ext = ctx->params.gap_ext;
-		int nl = launch_mkf(ma, (uint32_t)hchain.size(), ctx->num_sms * 16, st);
+		// x-drop grid: the lanes balance their load by pulling items from the work list, which needs several items per
+		// thread; too few threads on the other hand cannot hide the memory latency of the DP rows
+		static const int xgrid_env = getenv("RSK_XGRID") ? std::max(1, atoi(getenv("RSK_XGRID"))) : 0;  // blocks per SM (A/B switch)
+		int xblocks = xgrid_env ? ctx->num_sms * xgrid_env
+				: (int)std::min<uint64_t>((uint64_t)ctx->num_sms * 16, std::max<uint64_t>((uint64_t)ctx->num_sms * 2, (uint64_t)2 * m / (64 * 16)));
+		int nl = launch_mkf(ma, (uint32_t)hchain.size(), xblocks, st);
 		if (nl < 0)
 			return fail(RSK_ERR_CUDA, "long-chain kernels failed to launch: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->stats.kernel_launches += nl;
