@@ -277,6 +277,16 @@ extern "C" int rsk_ctx_create(int device, const rsk_params *params, void *cuda_s
 	}
 	for (auto &e : ctx->ev)
 		cudaEventCreate(&e);
+	for (auto &e : ctx->alt.ev)
+		cudaEventCreate(&e);
+	cudaEventCreateWithFlags(&ctx->done, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->alt.done, cudaEventDisableTiming);
+	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+		cudaMalloc((void **)&ctx->alt.d_pool_cursor, sizeof(unsigned long long)) != cudaSuccess ||
+		cudaMalloc((void **)&ctx->alt.d_counters, sizeof(rsk_ctx::Counters)) != cudaSuccess) {
+		rsk_ctx_destroy(ctx);
+		return fail(RSK_ERR_NOMEM, "rsk_ctx_create: second batch set");
+	}
 	ctx->host_threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
 	if (const char *s = getenv("RSK_HOST_THREADS")) {
 		const int v = atoi(s);
@@ -333,6 +343,14 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	if (ctx->d_pool_cursor) cudaFree(ctx->d_pool_cursor);
 	for (auto &e : ctx->ev)
 		if (e) cudaEventDestroy(e);
+	for (auto &e : ctx->alt.ev)
+		if (e) cudaEventDestroy(e);
+	if (ctx->done) cudaEventDestroy(ctx->done);
+	if (ctx->alt.done) cudaEventDestroy(ctx->alt.done);
+	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+	ctx->alt.rec.release(); ctx->alt.pool.release();
+	if (ctx->alt.d_counters) cudaFree(ctx->alt.d_counters);
+	if (ctx->alt.d_pool_cursor) cudaFree(ctx->alt.d_pool_cursor);
 	if (ctx->own_stream && ctx->stream)
 		cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -1217,63 +1235,16 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		delete res;
 	};
 
-	std::vector<uint32_t> t_a, t_begin, t_cnt, slots;
 	uint64_t pool_total = 0;
-	size_t bi = 0;
-	for (const Batch &b0 : batches) {
-		Batch b = b0;
-		const int buf = (int)(bi++ & 1);
-		const double tt_0 = now_ms();
-		if (!b.cross) {
-			// build the Mu filter's tasks for sorted pairs [k0,k1): runs of equal A, chunks of one task's column count
-			const size_t task_cols = (std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32")) ? (size_t)kMuTaskCols : (size_t)kSwWarps;
-			t_a.clear(); t_begin.clear(); t_cnt.clear();
-			const size_t n = b.k1 - b.k0;
-			slots.resize(n);
-			for (size_t k = 0; k < n; ++k)
-				slots[k] = (uint32_t)k;
-			size_t k = 0;
-			while (k < n) {
-				size_t e = k + 1;
-				while (e < n && e - k < task_cols && plan.sa[b.k0 + e] == plan.sa[b.k0 + k])
-					++e;
-				t_a.push_back(plan.sa[b.k0 + k]);
-				t_begin.push_back((uint32_t)k);
-				t_cnt.push_back((uint32_t)(e - k));
-				k = e;
-			}
-			b.ntasks = (uint32_t)t_a.size();
-			if (ctx->blist.ensure(n) || ctx->bslot.ensure(n) || ctx->pair_a.ensure(n) || ctx->pair_b.ensure(n) ||
-				ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks)) {
-				if (!device_only)
-					abort_all();
-				return fail(RSK_ERR_NOMEM, "task buffers");
-			}
-			CK(cudaMemcpyAsync(ctx->blist.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->bslot.p, slots.data(), 4 * n, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->pair_a.p, plan.sa.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->pair_b.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->task_a.p, t_a.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->task_begin.p, t_begin.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->task_cnt.p, t_cnt.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
-			S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks;
-		}
-		g_t_tasks += now_ms() - tt_0;
-		const double tl0 = now();
-		int rc = run_batch(ctx, plan, b, opts);
-		t_launch += now() - tl0;
-		if (rc) {
-			if (!device_only)
-				abort_all();
-			return rc;
-		}
-		if (device_only) {
-			CK(cudaStreamSynchronize(st));
-			rc = finish_batch_timing(ctx);
-			if (rc)
-				return rc;
-			continue;
-		}
+	size_t bi = 0, collected = 0;
+	// D2H of one finished batch (the batch set currently swapped in) and the launch of its host conversion job
+	Batch pending;
+	int pending_buf = 0;
+	bool have_pending = false;
+	auto collect = [&](const Batch &b, const int buf) -> int {
+		int rc = RSK_OK;
+		cudaStream_t cst = ctx->copy_stream;
+		CK(cudaStreamWaitEvent(cst, ctx->done, 0));
 		// the GPU is busy with this batch: now make sure the host buffer we are about to overwrite is free
 		Job &J = jobs[buf];
 		const double tw0 = now();
@@ -1290,9 +1261,9 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		}
 		unsigned long long pool_used = 0;
 		const double td0 = now();
-		CK(cudaMemcpyAsync(ctx->h_rec[buf].p, ctx->rec.p, b.npairs * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(&pool_used, ctx->d_pool_cursor, sizeof(pool_used), cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK(cudaMemcpyAsync(ctx->h_rec[buf].p, ctx->rec.p, b.npairs * sizeof(PairRec), cudaMemcpyDeviceToHost, cst));
+		CK(cudaMemcpyAsync(&pool_used, ctx->d_pool_cursor, sizeof(pool_used), cudaMemcpyDeviceToHost, cst));
+		CK(cudaStreamSynchronize(cst));
 		S.d2h_bytes += b.npairs * sizeof(PairRec) + 8;
 		const uint64_t pool_base = pool_total;
 		const bool copy_paths = opts.want_paths && pool_used > 0;
@@ -1301,14 +1272,14 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 				abort_all();
 				return fail(RSK_ERR_NOMEM, "pinned path buffer");
 			}
-			CK(cudaMemcpyAsync(ctx->h_pool[buf].p, ctx->pool.p, pool_used, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
+			CK(cudaMemcpyAsync(ctx->h_pool[buf].p, ctx->pool.p, pool_used, cudaMemcpyDeviceToHost, cst));
+			CK(cudaStreamSynchronize(cst));
 			S.d2h_bytes += pool_used;
 			if (pool_total + pool_used > res->paths_cap) {
 				// grow the path pool (rare: the first batch sizes it for the whole call); nobody may be writing into it
 				wait_job(jobs[buf ^ 1]);
 				size_t cap = 0;
-				const uint64_t want = std::max<uint64_t>(pool_total + pool_used * (batches.size() - (bi - 1)) + (pool_used >> 3) + 4096,
+				const uint64_t want = std::max<uint64_t>(pool_total + pool_used * (batches.size() - collected) + (pool_used >> 3) + 4096,
 						2 * (uint64_t)res->paths_cap);
 				char *np = (char *)g_blocks.get(want, cap);
 				if (!np) {
@@ -1324,6 +1295,7 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			pool_total += pool_used;
 			res->npath = pool_total;
 		}
+		++collected;
 		t_d2h += now() - td0;  // includes waiting for the batch's kernels
 		rc = finish_batch_timing(ctx);
 		if (rc) {
@@ -1381,6 +1353,83 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 				J.n_eval[t] = ne; J.n_hit[t] = nh; J.n_rej[t] = nr;
 			});
 		}
+			return RSK_OK;
+	};
+
+	std::vector<uint32_t> t_a, t_begin, t_cnt, slots;
+	for (const Batch &b0 : batches) {
+		Batch b = b0;
+		const int buf = (int)(bi++ & 1);
+		const double tt_0 = now_ms();
+		if (!b.cross) {
+			// build the Mu filter's tasks for sorted pairs [k0,k1): runs of equal A, chunks of one task's column count
+			const size_t task_cols = (std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32")) ? (size_t)kMuTaskCols : (size_t)kSwWarps;
+			t_a.clear(); t_begin.clear(); t_cnt.clear();
+			const size_t n = b.k1 - b.k0;
+			slots.resize(n);
+			for (size_t k = 0; k < n; ++k)
+				slots[k] = (uint32_t)k;
+			size_t k = 0;
+			while (k < n) {
+				size_t e = k + 1;
+				while (e < n && e - k < task_cols && plan.sa[b.k0 + e] == plan.sa[b.k0 + k])
+					++e;
+				t_a.push_back(plan.sa[b.k0 + k]);
+				t_begin.push_back((uint32_t)k);
+				t_cnt.push_back((uint32_t)(e - k));
+				k = e;
+			}
+			b.ntasks = (uint32_t)t_a.size();
+			if (ctx->blist.ensure(n) || ctx->bslot.ensure(n) || ctx->pair_a.ensure(n) || ctx->pair_b.ensure(n) ||
+				ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks)) {
+				if (!device_only)
+					abort_all();
+				return fail(RSK_ERR_NOMEM, "task buffers");
+			}
+			CK(cudaMemcpyAsync(ctx->blist.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->bslot.p, slots.data(), 4 * n, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->pair_a.p, plan.sa.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->pair_b.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->task_a.p, t_a.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->task_begin.p, t_begin.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(ctx->task_cnt.p, t_cnt.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+			S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks;
+		}
+		g_t_tasks += now_ms() - tt_0;
+		const double tl0 = now();
+		int rc = run_batch(ctx, plan, b, opts);
+		t_launch += now() - tl0;
+		if (rc) {
+			if (!device_only)
+				abort_all();
+			return rc;
+		}
+		if (device_only) {
+			CK(cudaStreamSynchronize(st));
+			rc = finish_batch_timing(ctx);
+			if (rc)
+				return rc;
+			continue;
+		}
+		// the GPU is busy with this batch: collect the previous one (its device outputs live in the other batch set; the copies
+		// run on copy_stream next to this batch's kernels), then make this batch's set the pending one
+		CK(cudaEventRecord(ctx->done, st));
+		ctx->swap_batch_set();
+		if (have_pending) {
+			rc = collect(pending, pending_buf);
+			if (rc)
+				return rc;
+		}
+		pending = b;
+		pending_buf = buf;
+		have_pending = true;
+	}
+	if (!device_only && have_pending) {
+		ctx->swap_batch_set();
+		int rc = collect(pending, pending_buf);
+		ctx->swap_batch_set();
+		if (rc)
+			return rc;
 	}
 	if (!device_only) {
 		// explicit-mode KEEP_HITS hits arrive in sorted-pair order; cross-mode hits in (a, b) order

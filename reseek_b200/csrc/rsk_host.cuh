@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rsk_internal.cuh"
@@ -136,6 +137,35 @@ struct rsk_ctx {
 	DevBuf<uint32_t> mk_work, mk_cnt;
 	DevBuf<unsigned char> mk_scratch;
 	Counters *d_counters = nullptr;
+	// Second set of the per-batch device outputs: batch i+1 computes into one set while the records and paths of batch i
+	// are copied out of the other on copy_stream.  swap_batch_set() exchanges the set the members above refer to.
+	struct BatchSet {
+		DevBuf<PairRec> rec;
+		DevBuf<uint8_t> pool;
+		unsigned long long *d_pool_cursor = nullptr;
+		Counters *d_counters = nullptr;
+		cudaEvent_t ev[5] = {};
+		cudaEvent_t done = nullptr;
+		bool batch_filtered = false, batch_cross = true;
+		size_t filt_explicit_pairs = 0;
+		uint64_t filt_explicit_cells = 0;
+	} alt;
+	cudaEvent_t done = nullptr;    // all kernels of the batch in the current set have been queued before this event
+	cudaStream_t copy_stream = nullptr;
+	void swap_batch_set()
+	{
+		std::swap(rec, alt.rec);
+		std::swap(pool, alt.pool);
+		std::swap(d_pool_cursor, alt.d_pool_cursor);
+		std::swap(d_counters, alt.d_counters);
+		for (int k = 0; k < 5; ++k)
+			std::swap(ev[k], alt.ev[k]);
+		std::swap(done, alt.done);
+		std::swap(batch_filtered, alt.batch_filtered);
+		std::swap(batch_cross, alt.batch_cross);
+		std::swap(filt_explicit_pairs, alt.filt_explicit_pairs);
+		std::swap(filt_explicit_cells, alt.filt_explicit_cells);
+	}
 	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU
 	PinBuf<uint8_t> h_pool[2];
 	int host_threads = 1;
