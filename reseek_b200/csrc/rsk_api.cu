@@ -1074,11 +1074,23 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		uint64_t sumLB = B->d.total;
 		uint32_t maxLB = B->maxlen;
 		const uint32_t per = (uint32_t)std::max<uint64_t>(1, ctx->max_batch_pairs / nB);
-		for (uint32_t a0 = 0; a0 < nA; a0 += per) {
+		// The host converts the records of a batch while the next one computes; nothing hides the conversion of the LAST
+		// batch, so the tail of a multi-batch search is cut into a short final batch (a quarter of a full one).
+		std::vector<uint32_t> cuts;
+		for (uint32_t a0 = 0; a0 < nA; a0 += per)
+			cuts.push_back(a0);
+		if (cuts.size() >= 2 && !device_only) {
+			const uint32_t last0 = cuts.back(), rows = nA - last0, tail = std::max(1u, per / 4);
+			if (rows > tail)
+				cuts.push_back(nA - tail);
+		}
+		cuts.push_back(nA);
+		for (size_t ci = 0; ci + 1 < cuts.size(); ++ci) {
+			const uint32_t a0 = cuts[ci];
 			Batch b;
 			b.cross = true;
 			b.a0 = a0;
-			b.a1 = std::min(nA, a0 + per);
+			b.a1 = cuts[ci + 1];
 			b.npairs = (size_t)(b.a1 - b.a0) * nB;
 			b.ntasks = (b.a1 - b.a0) * ((nB + kSwWarps - 1) / kSwWarps);
 			uint64_t sumLA = 0;
