@@ -10,6 +10,8 @@
 // the per-column scores are summed sequentially in column order exactly like lddt.cpp:110-123.
 #include <float.h>
 
+#include <algorithm>
+
 #include "rsk_internal.cuh"
 
 namespace rsk {
@@ -131,12 +133,125 @@ __global__ void __launch_bounds__(kLddtThreads) lddt_ts_kernel(const LddtArgs a)
 	}
 }
 
+// The same computation with one WARP per pair (8 pairs per CTA, no block barriers): used when every alignment of the batch
+// fits kLddtWarpCols columns, which is every batch of chains up to that length.  The typical alignment of a random pair has
+// a handful of columns; a 128-thread CTA per pair then spends its time in barriers.
+constexpr int kLddtWarpCols = 512;
+constexpr int kLddtWarps = 8;
+__global__ void __launch_bounds__(kLddtWarps * 32) lddt_ts_warp_kernel(const LddtArgs a)
+{
+	extern __shared__ __align__(16) float sm[];
+	const uint32_t mc = a.maxcols;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	float *xa = sm + (size_t)warp * 7 * mc, *ya = xa + mc, *za = ya + mc, *xb = za + mc, *yb = xb + mc, *zb = yb + mc;
+	float *colscore = zb + mc;
+	const uint32_t nwarps = gridDim.x * kLddtWarps;
+	for (uint32_t pair = blockIdx.x * kLddtWarps + warp; pair < a.npairs; pair += nwarps) {
+		PairRec *rec = a.rec + pair;
+		const float score = rec->score;
+		const uint32_t plen = rec->path_len;
+		const bool no_aln = plen == 0 && (rec->flags & (RSK_HIT_MU_REJECTED | RSK_HIT_MKF)) != 0;  // see lddt_ts_kernel
+		__syncwarp();  // smem reuse across pairs
+		if (no_aln || score < a.min_fwd_score) {
+			if (lane == 0) {
+				rec->hi_a = rec->hi_b = rec->ids = rec->gaps = 0xffffffffu;
+				rec->lddt = 0.0f;
+				rec->ts = -FLT_MAX;
+			}
+			continue;
+		}
+		uint32_t ai, bi;
+		if (a.cross) {
+			const uint32_t arel = pair / a.nB;
+			ai = a.a_begin + arel;
+			bi = pair - arel * a.nB;
+		} else {
+			ai = a.pair_a[pair];
+			bi = a.pair_b[pair];
+		}
+		const uint64_t oa = a.offA[ai], ob = a.offB[bi];
+		const uint8_t *path = a.pool + rec->path_off;
+		uint32_t nM = 0, nD = 0, nI = 0;
+		const uint32_t lo_a = rec->lo_a, lo_b = rec->lo_b;
+		for (uint32_t k0 = 0; k0 < plen; k0 += 32) {
+			const uint32_t k = k0 + lane;
+			const uint8_t c = (k < plen) ? path[k] : 0;
+			const unsigned mM = __ballot_sync(kFull, c == 'M');
+			const unsigned mD = __ballot_sync(kFull, c == 'D');
+			const unsigned mI = __ballot_sync(kFull, c == 'I');
+			const unsigned below = (1u << lane) - 1u;
+			if (c == 'M') {
+				const uint32_t idx = nM + __popc(mM & below);
+				const uint32_t pa = lo_a + idx + nD + __popc(mD & below);
+				const uint32_t pb = lo_b + idx + nI + __popc(mI & below);
+				xa[idx] = a.xA[oa + pa]; ya[idx] = a.yA[oa + pa]; za[idx] = a.zA[oa + pa];
+				xb[idx] = a.xB[ob + pb]; yb[idx] = a.yB[ob + pb]; zb[idx] = a.zB[ob + pb];
+			}
+			nM += __popc(mM); nD += __popc(mD); nI += __popc(mI);
+		}
+		__syncwarp();
+		const uint32_t n = nM;
+		for (uint32_t ci = lane; ci < n; ci += 32) {
+			const float x1 = xa[ci], y1 = ya[ci], z1 = za[ci];
+			const float x2 = xb[ci], y2 = yb[ci], z2 = zb[ci];
+			uint32_t cons = 0, pres = 0;
+			for (uint32_t cj = 0; cj < n; ++cj) {
+				if (cj == ci)
+					continue;
+				const float dxa = x1 - xa[cj], dya = y1 - ya[cj], dza = z1 - za[cj];
+				const float d1s = dxa * dxa + dya * dya + dza * dza;
+				const float dxb = x2 - xb[cj], dyb = y2 - yb[cj], dzb = z2 - zb[cj];
+				const float d2s = dxb * dxb + dyb * dyb + dzb * dzb;
+				if (d1s > 225.0f && d2s > 225.0f)
+					continue;
+				const float diff = fabsf(sqrtf(d1s) - sqrtf(d2s));
+				pres += (diff <= 0.5f) + (diff <= 1.0f) + (diff <= 2.0f) + (diff <= 4.0f);
+				cons += 4;
+			}
+			float sc = 0.0f;
+			if (cons > 0)
+				sc = (float)pres / (float)cons;
+			colscore[ci] = sc;
+		}
+		__syncwarp();
+		if (lane == 0) {
+			float total = 0.0f;
+			for (uint32_t c = 0; c < n; ++c)  // sequential, in column order (lddt.cpp:110-123)
+				total += colscore[c];
+			const float lddt = (n == 0) ? 0.0f : total / (float)n;
+			const float sa = a.selfrevA[ai], sb = a.selfrevB[bi];
+			float rev = 0.0f;
+			if (sa != FLT_MAX && sb != FLT_MAX)
+				rev = (sa + sb) / 2;
+			const float L = (float)(a.lenA[ai] + a.lenB[bi]) / 2;
+			float ts = 0.13f * lddt;
+			ts += (1.7f * score - 2.0f * rev) / (L + 250.0f);
+			rec->hi_a = rec->lo_a + n + nD - 1;
+			rec->hi_b = rec->lo_b + n + nI - 1;
+			rec->ids = n;
+			rec->gaps = nD + nI;
+			rec->lddt = lddt;
+			rec->ts = ts;
+			rec->flags |= RSK_HIT_HAS_EVALUE;
+		}
+	}
+}
+
 }  // namespace
 
 int launch_lddt(const LddtArgs &args, cudaStream_t stream)
 {
 	if (args.npairs == 0)
 		return 0;
+	if (args.maxcols <= (uint32_t)kLddtWarpCols) {
+		const size_t wsmem = (size_t)kLddtWarps * args.maxcols * 7 * sizeof(float);
+		if (wsmem > 48 * 1024 &&
+			cudaFuncSetAttribute(lddt_ts_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem) != cudaSuccess)
+			return -1;
+		const unsigned wgrid = (unsigned)std::min<uint64_t>(((uint64_t)args.npairs + kLddtWarps - 1) / kLddtWarps, 148u * 64u);
+		lddt_ts_warp_kernel<<<wgrid, kLddtWarps * 32, wsmem, stream>>>(args);
+		return cudaGetLastError() == cudaSuccess ? 1 : -1;
+	}
 	const size_t smem = (size_t)args.maxcols * 7 * sizeof(float);
 	if (smem > 48 * 1024) {
 		if (cudaFuncSetAttribute(lddt_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
