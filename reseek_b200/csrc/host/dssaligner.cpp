@@ -421,7 +421,9 @@ void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
 	V.seq_b = m_ChainB->m_Seq.c_str();
 	V.len_a = m_ChainA->GetSeqLength();
 	V.len_b = m_ChainB->GetSeqLength();
-	vector<char> Buf(4096 + 16 * m_Path.size());
+	static thread_local vector<char> Buf;  // reused: a search emits up to millions of lines
+	if (Buf.size() < 4096 + 16 * m_Path.size())
+		Buf.resize(4096 + 16 * m_Path.size());
 	int n = rsk_format_tsv(&V, Up ? 1 : 0, Columns, Buf.data(), Buf.size());
 	if (n < 0)
 		Die("reseek_b200: %s", rsk_last_error());
