@@ -6,6 +6,8 @@
 #include <time.h>
 
 #include <chrono>
+#include <future>
+#include <memory>
 
 namespace reseek_b200 {
 
@@ -42,6 +44,8 @@ DBSearcher::~DBSearcher()
 	for (DSSAligner *DA : m_DAs)
 		delete DA;
 	rsk_chainset_free(m_DBSet);
+	if (m_LoaderCtx != 0)
+		rsk_ctx_destroy(m_LoaderCtx);
 	if (m_Ctx != 0)
 		rsk_ctx_destroy(m_Ctx);
 	if (m_OwnsChains)
@@ -142,6 +146,9 @@ void DBSearcher::BaseOnAln(DSSAligner &DA, bool Up)
 	m_Lock.lock();
 	++m_HitCount;
 	DA.ToTsvColumns(m_fTsv, Up, m_Columns);
+	DA.m_RowLen = m_RowLen;
+	DA.ToAln(m_fAln, Up);
+	DA.ToFasta2(m_fFasta2, m_Unaligned, Up);
 	OnAln(DA, Up);
 	m_Lock.unlock();
 	}
@@ -292,22 +299,50 @@ void DBSearcher::RunQuery(ChainReader2 &QCR)
 	time_t t_start = time(0);
 	BeginRun();
 	const bool WithMu = !m_DBMuLettersVec.empty();
-	for (;;)
+	// The next block is read, run through DSS and given its self-reverse scores (on a context of its own) while the
+	// current one is being searched and its hits written.  RSK_NO_OVERLAP=1: one block at a time on the search context.
+	const bool Overlap = getenv("RSK_NO_OVERLAP") == 0;
+	rsk_ctx *LoadCtx = GetContext();
+	if (Overlap)
+		{
+		if (m_LoaderCtx == 0)
+			{
+			rsk_params R;
+			m_Params->ToRsk(R, m_MaxEvalue);
+			Check(rsk_ctx_create(m_Device, &R, 0, &m_LoaderCtx));
+			}
+		LoadCtx = m_LoaderCtx;
+		}
+	struct Loaded
 		{
 		ChainFeatures F;
-		const uint N = ProfileLoader::Load(*m_Params, QCR, m_BlockChains, WithMu, GetContext(), *m_Params, m_MaxEvalue, F);
+		vector<ChainData> Block;
+		};
+	auto LoadNext = [&]() -> std::unique_ptr<Loaded>
+		{
+		std::unique_ptr<Loaded> L(new Loaded);
+		const uint N = ProfileLoader::Load(*m_Params, QCR, m_BlockChains, WithMu, LoadCtx, *m_Params, m_MaxEvalue, L->F);
 		if (N == 0)
-			break;
-		vector<ChainData> Block(N);
+			return nullptr;
+		L->Block.resize(N);
 		for (uint i = 0; i < N; ++i)
 			{
-			Block[i].Chain = F.Chains[i];
-			Block[i].Profile = F.Profiles[i];
-			Block[i].MuLetters = WithMu ? F.MuLetters[i] : 0;
-			Block[i].SelfRevScore = F.SelfRevScores[i];
+			L->Block[i].Chain = L->F.Chains[i];
+			L->Block[i].Profile = L->F.Profiles[i];
+			L->Block[i].MuLetters = WithMu ? L->F.MuLetters[i] : 0;
+			L->Block[i].SelfRevScore = L->F.SelfRevScores[i];
 			}
-		RunQueryBlock(Block);
-		F.Free();
+		return L;
+		};
+	std::unique_ptr<Loaded> Cur = LoadNext();
+	while (Cur)
+		{
+		std::future<std::unique_ptr<Loaded> > Next;
+		if (Overlap)
+			Next = std::async(std::launch::async, LoadNext);
+		RunQueryBlock(Cur->Block);
+		Cur->F.Free();
+		Cur = Overlap ? Next.get() : LoadNext();
 		}
 	m_Secs = (uint)(time(0) - t_start);
 	if (m_Secs == 0)
@@ -365,7 +400,7 @@ void MuPreFilter(const DSSParams &Params, const vector<ChainData> &Query, const 
 
 // postmufilter.cpp:211-301; scan loop :116-208; Accept :105-114 with the default thresholds (E <= 10)
 void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const vector<ChainData> &Query,
-  const vector<ChainData> &DB, const string &HitsFN, const char *Columns, int Device)
+  const vector<ChainData> &DB, const string &HitsFN, const char *Columns, int Device, const string &AlnFN)
 	{
 	FILE *fIn = fopen(MuFilterTsvFN.c_str(), "r");
 	if (fIn == 0)
@@ -408,6 +443,9 @@ void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const ve
 	FILE *fOut = HitsFN.empty() ? 0 : fopen(HitsFN.c_str(), "w");
 	if (!HitsFN.empty() && fOut == 0)
 		Die("Cannot create %s", HitsFN.c_str());
+	FILE *fAln = AlnFN.empty() ? 0 : fopen(AlnFN.c_str(), "w");
+	if (!AlnFN.empty() && fAln == 0)
+		Die("Cannot create %s", AlnFN.c_str());
 	DSSAligner DA;
 	DA.SetParams(Params);
 	DA.UseContext(C);
@@ -419,10 +457,15 @@ void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const ve
 		const rsk_hit &H = Hits[k];
 		DA.FromHit(H, Pool, Query[H.a], DB[H.b]);
 		if (DA.m_EvalueA <= 10)  // Accept(): s_MaxEvalue = 10, s_MaxPvalue = -1, s_MinTS = 9e9
+			{
 			DA.ToTsvColumns(fOut, true, Columns);
+			DA.ToAln(fAln, true);
+			}
 		}
 	if (fOut != 0)
 		fclose(fOut);
+	if (fAln != 0)
+		fclose(fAln);
 	rsk_results_free(Res);
 	rsk_chainset_free(Q);
 	rsk_chainset_free(T);

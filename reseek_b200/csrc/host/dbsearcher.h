@@ -64,6 +64,10 @@ public:
 
 // where BaseOnAln writes (g_fTsv in the reference, set from -output)
 	FILE *m_fTsv = 0;
+	FILE *m_fAln = 0;            // g_fAln (-aln), g_fFasta2 (-fasta2), opt(unaligned), opt(rowlen)
+	FILE *m_fFasta2 = 0;
+	bool m_Unaligned = false;
+	uint m_RowLen = 0;
 	const char *m_Columns = 0;   // -columns, 0 = default
 	bool m_OwnsChains = false;   // the reference's destructor deletes chains/profiles (dbsearcher.cpp:12-22)
 	uint m_BlockChains = 100000; // streamed chains per device block in RunQuery
@@ -93,6 +97,7 @@ public:
 
 private:
 	rsk_ctx *m_Ctx = 0;
+	rsk_ctx *m_LoaderCtx = 0;    // second context: the next block's self-reverse scores while the current block is searched
 	rsk_chainset *m_DBSet = 0;
 	rsk_stats m_LastStats;
 	void UploadDB();
@@ -108,6 +113,7 @@ private:
 void MuPreFilter(const DSSParams &Params, const vector<ChainData> &Query, const vector<ChainData> &DB,
   const string &OutputFN, int Device = 0);
 void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const vector<ChainData> &Query,
-  const vector<ChainData> &DB, const string &HitsFN, const char *Columns = 0, int Device = 0);
+  const vector<ChainData> &DB, const string &HitsFN, const char *Columns = 0, int Device = 0,
+  const string &AlnFN = string());  // AlnFN: -aln (postmufilter.cpp:194, 244)
 
 }  // namespace reseek_b200

@@ -296,6 +296,7 @@ void DSSAligner::ClearAlign()
 	m_AlnFwdScore = 0;
 	m_LDDT = 0;
 	m_MuFwdScore = m_MuRevScore = m_BestHSPScore = m_BestChainScore = 0;
+	m_MuFwdMinusRevScore = 0;
 	m_Flags = 0;
 	}
 
@@ -320,6 +321,7 @@ void DSSAligner::FromHit(const rsk_hit &H, const char *PathPool, const ChainData
 		{
 		m_MuFwdScore = H.mu_fwd;
 		m_MuRevScore = H.mu_rev;
+		m_MuFwdMinusRevScore = H.mu_score;
 		}
 	if (H.flags & RSK_HIT_MU_REJECTED)
 		return;
@@ -395,11 +397,9 @@ void DSSAligner::AlignOne(bool NoAccel)
 void DSSAligner::AlignQueryTarget() { AlignOne(false); }
 void DSSAligner::Align_NoAccel() { AlignOne(true); }
 
-void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
+// the aligner's result members as the record + view the C-ABI writers take
+void DSSAligner::GetHitView(rsk_hit &H, rsk_hit_view &V) const
 	{
-	if (f == 0)
-		return;
-	rsk_hit H;
 	memset(&H, 0, sizeof(H));
 	H.score = m_AlnFwdScore;
 	H.lo_a = m_LoA; H.lo_b = m_LoB; H.hi_a = m_HiA; H.hi_b = m_HiB;
@@ -410,9 +410,9 @@ void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
 	const bool Mkf = (m_Flags & RSK_HIT_MKF) != 0;
 	H.mu_fwd = Mkf ? m_BestHSPScore : m_MuFwdScore;
 	H.mu_rev = Mkf ? m_BestChainScore : m_MuRevScore;
+	H.mu_score = m_MuFwdMinusRevScore;
 	H.flags = m_Flags;
 	H.path_len = RSK_SIZE(m_Path);
-	rsk_hit_view V;
 	V.hit = &H;
 	V.path = m_Path.c_str();
 	V.label_a = m_ChainA->m_Label.c_str();
@@ -421,6 +421,15 @@ void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
 	V.seq_b = m_ChainB->m_Seq.c_str();
 	V.len_a = m_ChainA->GetSeqLength();
 	V.len_b = m_ChainB->GetSeqLength();
+	}
+
+void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
+	{
+	if (f == 0)
+		return;
+	rsk_hit H;
+	rsk_hit_view V;
+	GetHitView(H, V);
 	static thread_local vector<char> Buf;  // reused: a search emits up to millions of lines
 	if (Buf.size() < 4096 + 16 * m_Path.size())
 		Buf.resize(4096 + 16 * m_Path.size());
@@ -432,6 +441,37 @@ void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
 	fputc('\n', f);
 	m_OutputLock.unlock();
 	}
+
+// dssaligner.cpp:965-979 (PrettyAln) and :981-1014; the text itself comes from the C ABI
+void DSSAligner::WriteBlock(FILE *f, bool Up, int Kind, bool Global) const
+	{
+	if (f == 0)
+		return;
+	rsk_hit H;
+	rsk_hit_view V;
+	GetHitView(H, V);
+	static thread_local vector<char> Buf;
+	if (Buf.size() < 4096)
+		Buf.resize(4096);
+	for (;;)
+		{
+		long long n = Kind == 0 ? rsk_format_aln(&V, Up ? 1 : 0, m_RowLen, Buf.data(), Buf.size())
+		  : rsk_format_fasta2(&V, Up ? 1 : 0, Global ? 1 : 0, Buf.data(), Buf.size());
+		if (n >= 0)
+			{
+			if (Kind == 1) m_OutputLock.lock();  // ToFasta2 locks, ToAln relies on the caller's lock
+			fwrite(Buf.data(), 1, (size_t)n, f);
+			if (Kind == 1) m_OutputLock.unlock();
+			return;
+			}
+		if (n >= -8)  // an rsk_status, not a size
+			Die("reseek_b200: alignment writer failed (%lld)", n);
+		Buf.resize((size_t)(-n) + 64);
+		}
+	}
+
+void DSSAligner::ToAln(FILE *f, bool Up) const { WriteBlock(f, Up, 0, false); }
+void DSSAligner::ToFasta2(FILE *f, bool Global, bool Up) const { WriteBlock(f, Up, 1, Global); }
 
 void DSSAligner::ToTsv(FILE *f, bool Up) { ToTsvColumns(f, Up, 0); }
 

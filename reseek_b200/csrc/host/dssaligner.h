@@ -58,6 +58,7 @@ public:
 	// Mu filter / k-mer path by-products (m_MKF.m_BestHSPScore, m_MKF.m_BestChainScore, GetMuScore in the reference)
 	int m_MuFwdScore = 0;
 	int m_MuRevScore = 0;
+	float m_MuFwdMinusRevScore = 0;  // what GetMuScore() returns (dssaligner.cpp:613-617)
 	int m_BestHSPScore = 0;
 	int m_BestChainScore = 0;
 	uint m_Flags = 0;           // RSK_HIT_* of the last alignment
@@ -94,6 +95,10 @@ public:
 // Up is false if alignment is Query=B, Target=A
 	void ToTsv(FILE *f, bool Up);
 	void ToTsvColumns(FILE *f, bool Up, const char *Columns);  // -columns a+b+c (userfieldnames.h)
+	void ToAln(FILE *f, bool Up) const;                         // -aln (dssaligner.cpp:965-979)
+	void ToFasta2(FILE *f, bool Global, bool Up) const;         // -fasta2 [-unaligned] (dssaligner.cpp:981-1014)
+	float GetMuScore() const { return m_MuFwdMinusRevScore; }
+	uint m_RowLen = 0;           // -rowlen (0: 80 columns)
 	const char *GetLabel(bool Top) const { return Top ? m_ChainA->m_Label.c_str() : m_ChainB->m_Label.c_str(); }
 	uint GetLo(bool Top) const { return Top ? m_LoA : m_LoB; }
 	uint GetHi(bool Top) const { return Top ? m_HiA : m_HiB; }
@@ -107,6 +112,8 @@ public:
 
 // shim plumbing
 	void UseContext(rsk_ctx *Ctx);   // share a DBSearcher's context instead of creating one
+	void GetHitView(rsk_hit &H, rsk_hit_view &V) const;
+	void WriteBlock(FILE *f, bool Up, int Kind, bool Global) const;
 	void FromHit(const rsk_hit &H, const char *PathPool, const ChainData &A, const ChainData &B);
 
 private:

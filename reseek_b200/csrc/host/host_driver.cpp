@@ -171,6 +171,25 @@ static vector<ChainData> ToChainData(const ChainFeatures &F)
 	return v;
 	}
 
+// -aln / -fasta2 / -unaligned / -rowlen of the reference, taken from the environment (the positional arguments are the
+// files the tests always need)
+static void OpenAlnOutputs(DBSearcher &DBS)
+	{
+	if (const char *e = getenv("RSK_ALN"))
+		if ((DBS.m_fAln = fopen(e, "w")) == 0) Die("Cannot create %s", e);
+	if (const char *e = getenv("RSK_FASTA2"))
+		if ((DBS.m_fFasta2 = fopen(e, "w")) == 0) Die("Cannot create %s", e);
+	if (const char *e = getenv("RSK_UNALIGNED"))
+		DBS.m_Unaligned = atoi(e) != 0;
+	if (const char *e = getenv("RSK_ROWLEN"))
+		DBS.m_RowLen = (uint)atoi(e);
+	}
+static void CloseAlnOutputs(DBSearcher &DBS)
+	{
+	if (DBS.m_fAln) fclose(DBS.m_fAln);
+	if (DBS.m_fFasta2) fclose(DBS.m_fFasta2);
+	}
+
 int main(int argc, char **argv)
 	{
 	if (argc < 2)
@@ -210,8 +229,10 @@ int main(int argc, char **argv)
 		DBS.m_fTsv = fopen(argv[4], "w");
 		if (argc > 5)
 			DBS.m_Columns = argv[5];
+		OpenAlnOutputs(DBS);
 		DBS.RunSelf();
 		fclose(DBS.m_fTsv);
+		CloseAlnOutputs(DBS);
 		fprintf(stderr, "OnAln calls %u, hits %u\n", DBS.m_OnAlnCount, (uint)DBS.m_HitCount);
 		return 0;
 		}
@@ -230,8 +251,10 @@ int main(int argc, char **argv)
 			DBS.m_BlockChains = (uint)atoi(e);
 		ChainReader2 CR;
 		CR.Open(argv[4]);          // the -db file is streamed (search.cpp:57-59)
+		OpenAlnOutputs(DBS);
 		DBS.RunQuery(CR);
 		fclose(DBS.m_fTsv);
+		CloseAlnOutputs(DBS);
 		fprintf(stderr, "OnAln calls %u, hits %u\n", DBS.m_OnAlnCount, (uint)DBS.m_HitCount);
 		return 0;
 		}
@@ -256,7 +279,7 @@ int main(int argc, char **argv)
 		ProfileLoader::Load(Params2, TR, 0, true, C, Params2, 10, T);
 		const vector<ChainData> QD = ToChainData(Q), TD = ToChainData(T);
 		MuPreFilter(Params, QD, TD, argv[4]);
-		PostMuFilter(Params2, argv[4], QD, TD, argv[5], argc > 6 ? argv[6] : 0);
+		PostMuFilter(Params2, argv[4], QD, TD, argv[5], argc > 6 ? argv[6] : 0, 0, getenv("RSK_ALN") ? getenv("RSK_ALN") : "");
 		Q.Free();
 		T.Free();
 		rsk_ctx_destroy(C);
@@ -275,8 +298,10 @@ int main(int argc, char **argv)
 		if (argc > 5)
 			DBS.m_Columns = argv[5];
 		DBS.Setup();
+		OpenAlnOutputs(DBS);
 		DBS.RunSelf();
 		fclose(DBS.m_fTsv);
+		CloseAlnOutputs(DBS);
 		fprintf(stderr, "OnAln calls %u, hits %u\n", DBS.m_OnAlnCount, (uint)DBS.m_HitCount);
 		return 0;
 		}

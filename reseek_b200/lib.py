@@ -115,6 +115,10 @@ def load_library():
         fn.argtypes = [C.c_void_p]
     L.rsk_format_tsv.argtypes = [C.POINTER(HitView), C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
     L.rsk_path_to_cigar.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]
+    L.rsk_format_aln.argtypes = [C.POINTER(HitView), C.c_int, C.c_uint32, C.c_char_p, C.c_size_t]
+    L.rsk_format_aln.restype = C.c_longlong
+    L.rsk_format_fasta2.argtypes = [C.POINTER(HitView), C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.rsk_format_fasta2.restype = C.c_longlong
     L.rsk_results_free.argtypes = [C.c_void_p]
     L.rsk_results_free.restype = None
     L.rsk_prefilter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrefilterOpts), C.POINTER(C.c_void_p)]
@@ -167,6 +171,32 @@ def format_tsv(hit, path, label_a, label_b, len_a, len_b, up=True, columns=None,
     if n < 0:
         raise ReseekB200Error(f"rsk_format_tsv failed ({n})")
     return out.value.decode()
+
+
+def _format_block(fn, name, hit, path, label_a, label_b, seq_a, seq_b, up, arg):
+    rec = np.array([hit], dtype=HIT_DTYPE)
+    v = HitView(rec.ctypes.data, path.encode() if isinstance(path, str) else path, label_a.encode(), label_b.encode(),
+                seq_a, seq_b, len(seq_a), len(seq_b))
+    cap = 1 << 14
+    while True:
+        out = C.create_string_buffer(cap)
+        n = fn(C.byref(v), int(bool(up)), arg, out, cap)
+        if n >= 0:
+            return out.raw[:n].decode()
+        if n >= -8:
+            raise ReseekB200Error(f"{name} failed ({n})")
+        cap = -n + 64
+
+
+def format_aln(hit, path, label_a, label_b, seq_a, seq_b, up=True, rowlen=0):
+    """The block DSSAligner::ToAln appends to the -aln file for this hit."""
+    return _format_block(load_library().rsk_format_aln, "rsk_format_aln", hit, path, label_a, label_b, seq_a, seq_b, up, int(rowlen))
+
+
+def format_fasta2(hit, path, label_a, label_b, seq_a, seq_b, up=True, unaligned=False):
+    """The record DSSAligner::ToFasta2 appends to the -fasta2 file for this hit."""
+    return _format_block(load_library().rsk_format_fasta2, "rsk_format_fasta2", hit, path, label_a, label_b, seq_a, seq_b, up,
+                         int(bool(unaligned)))
 
 
 def path_to_cigar(path, up=True):

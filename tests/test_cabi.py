@@ -84,3 +84,70 @@ def test_tsv_writer_matches_reference_lines(built_lib, mode):
                 continue  # the reference prints whatever the previous long-chain alignment left in m_MKF
             assert w == m, f"pair {k} up={up} column {nm}: reference '{w}' vs '{m}'"
     assert rb.path_to_cigar("MMDDIM", up=True) == "2M2D1I1M" and rb.path_to_cigar("MMDDIM", up=False) == "2M2I1D1M"
+
+
+def _oracle_self_hits(mode, max_len=500):
+    """(hit record, path, A, B) for every pair (i <= j) of the short golden chains the reference's RunSelf would report
+    (E <= 10, dbsearcher.cpp:258-265), computed by the CPU oracle."""
+    import reseek_b200 as rb
+    from oracle.pyoracle import Port
+    from tests.golden_util import load_chains
+    chains = [c for c in load_chains() if c.L < max_len]
+    port = Port(mode=mode)
+    out = []
+    for i in range(len(chains)):
+        for j in range(i, len(chains)):
+            r, path = port.align_pair(chains[i], chains[j])
+            if r.filtered or r.path_len == 0 or not r.evalue <= 10:
+                continue
+            h = np.zeros(1, rb.HIT_DTYPE)[0]
+            for f in ("score", "lo_a", "lo_b", "hi_a", "hi_b", "ids", "gaps", "lddt", "ts", "pvalue", "evalue", "qual",
+                      "mu_score", "mu_fwd", "mu_rev", "path_len"):
+                h[f] = getattr(r, f)
+            out.append((h, path, chains[i], chains[j]))
+    return out
+
+
+def test_aln_fasta2_and_row_columns_match_reference_files(built_lib):
+    """rsk_format_aln / rsk_format_fasta2 / the qrow, trow, qrowg, trowg, ts, muscore, aq, qcovpct, tcovpct columns against the
+    files the reference binary wrote for `-search gshort.bca -sensitive -aln -fasta2 -columns ...` (tools/make_golden_aln.py);
+    the alignments themselves come from the CPU oracle here (the GPU path writes the same files in tests/test_host_search.py).
+    Both directions of every off-diagonal hit, as runself.cpp:60-66 emits them."""
+    import reseek_b200 as rb
+    from tests.golden_util import ALN_COLUMNS, GOLDEN, aln_blocks, fasta2_records
+    alns, recs, lines = [], [], []
+    for h, path, A, B in _oracle_self_hits(2):
+        for up in ([True] if A is B else [True, False]):
+            alns.append(rb.format_aln(h, path, A.label, B.label, A.seq, B.seq, up=up))
+            recs.append(rb.format_fasta2(h, path, A.label, B.label, A.seq, B.seq, up=up))
+            lines.append(rb.format_tsv(h, path, A.label, B.label, A.L, B.L, up=up, columns=ALN_COLUMNS, seq_a=A.seq, seq_b=B.seq))
+    assert len(lines) >= 18
+    assert sorted(lines) == (GOLDEN / "golden_aln_self_sensitive.tsv").read_text().splitlines()
+    assert aln_blocks("".join(alns)) == aln_blocks((GOLDEN / "golden_aln_self_sensitive.aln").read_text())
+    assert fasta2_records("".join(recs)) == fasta2_records((GOLDEN / "golden_aln_self_sensitive.fa2").read_text())
+
+
+def test_aln_writer_rowlen_and_unaligned_flanks(built_lib):
+    """-rowlen 60 blocks and -unaligned rows (lower-case flanks, '.' padding) against the reference binary's files for
+    `-search g4.bca -db gshort.bca -verysensitive`."""
+    import reseek_b200 as rb
+    from oracle.pyoracle import Port
+    from tests.golden_util import GOLDEN, SHORT_QUERIES, aln_blocks, fasta2_records, load_chains
+    chains = load_chains()
+    query = [chains[i] for i in SHORT_QUERIES]
+    db = [c for c in chains if c.L < 500]
+    port = Port(mode=3)
+    alns, recs = [], []
+    for q in query:
+        for t in db:
+            r, path = port.align_pair(q, t)
+            if r.path_len == 0:
+                continue
+            h = np.zeros(1, rb.HIT_DTYPE)[0]
+            for f in ("score", "lo_a", "lo_b", "hi_a", "hi_b", "ids", "gaps", "lddt", "ts", "pvalue", "evalue", "qual", "path_len"):
+                h[f] = getattr(r, f)
+            alns.append(rb.format_aln(h, path, q.label, t.label, q.seq, t.seq, up=True, rowlen=60))
+            recs.append(rb.format_fasta2(h, path, q.label, t.label, q.seq, t.seq, up=True, unaligned=True))
+    assert len(alns) >= 50
+    assert aln_blocks("".join(alns)) == aln_blocks((GOLDEN / "golden_aln_db_verysensitive.aln").read_text())
+    assert fasta2_records("".join(recs)) == fasta2_records((GOLDEN / "golden_aln_db_verysensitive.fa2").read_text())

@@ -11,15 +11,15 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from tests.golden_util import GOLDEN, SEARCH_COLUMNS, golden_bca
+from tests.golden_util import ALN_COLUMNS, GOLDEN, SEARCH_COLUMNS, aln_blocks, fasta2_records, golden_bca, golden_bca_short
 
 ROOT = Path(__file__).resolve().parent.parent
 DEMO = ROOT / "reseek_b200" / "rsk_host_demo"
 HOSTLIB = ROOT / "reseek_b200" / "libreseek_b200_host.so"
 
 
-def _run(*args):
-    env = dict(os.environ, RSK_BLOCK_CHAINS="8")  # streamed side in several blocks
+def _run(*args, **extra_env):
+    env = dict(os.environ, RSK_BLOCK_CHAINS="8", **{k: str(v) for k, v in extra_env.items()})  # streamed side in several blocks
     return subprocess.run([str(DEMO), *map(str, args)], capture_output=True, text=True, timeout=900, env=env)
 
 
@@ -118,3 +118,27 @@ def test_search_fast_db_matches_reference_binary(built_lib, tmp_path):
     got = sorted((tmp_path / "out.tsv").read_text().splitlines())
     want = _golden("golden_search_fastdb.tsv")
     assert len(want) >= 6 and got == want
+
+
+@pytest.mark.gpu
+def test_selfsearch_aln_fasta2_and_row_columns_match_reference_binary(built_lib, tmp_path):
+    """-aln, -fasta2 and the row columns (qrow, trow, qrowg, trowg, muscore, ...) of a whole `-search X -sensitive` run:
+    identical to the reference binary's files (tools/make_golden_aln.py), hits in canonical order."""
+    g4, gs = golden_bca_short(tmp_path)
+    r = _run("selfsearch", "sensitive", gs, tmp_path / "out.tsv", ALN_COLUMNS, RSK_ALN=tmp_path / "out.aln", RSK_FASTA2=tmp_path / "out.fa2")
+    assert r.returncode == 0, r.stderr
+    assert sorted((tmp_path / "out.tsv").read_text().splitlines()) == _golden("golden_aln_self_sensitive.tsv")
+    assert aln_blocks((tmp_path / "out.aln").read_text()) == aln_blocks((GOLDEN / "golden_aln_self_sensitive.aln").read_text())
+    assert fasta2_records((tmp_path / "out.fa2").read_text()) == fasta2_records((GOLDEN / "golden_aln_self_sensitive.fa2").read_text())
+
+
+@pytest.mark.gpu
+def test_search_db_aln_rowlen_unaligned_match_reference_binary(built_lib, tmp_path):
+    """`-search g4 -db gshort -verysensitive -aln -fasta2 -unaligned -rowlen 60` through the streamed-DB path."""
+    g4, gs = golden_bca_short(tmp_path)
+    r = _run("search", "verysensitive", g4, gs, tmp_path / "out.tsv", SEARCH_COLUMNS, RSK_ALN=tmp_path / "out.aln",
+             RSK_FASTA2=tmp_path / "out.fa2", RSK_UNALIGNED=1, RSK_ROWLEN=60)
+    assert r.returncode == 0, r.stderr
+    got = aln_blocks((tmp_path / "out.aln").read_text())
+    assert len(got) >= 50 and got == aln_blocks((GOLDEN / "golden_aln_db_verysensitive.aln").read_text())
+    assert fasta2_records((tmp_path / "out.fa2").read_text()) == fasta2_records((GOLDEN / "golden_aln_db_verysensitive.fa2").read_text())
