@@ -99,8 +99,9 @@ enum {
 	RSK_HIT_MU_REJECTED = 1u, /* dropped by the Mu filter: no SW was run */
 	RSK_HIT_HAS_EVALUE = 2u,  /* CalcEvalue ran (score >= min_fwd_score) */
 	RSK_HIT_REPORTED = 4u,    /* passes DBSearcher::Reject (E <= max_evalue) */
-	RSK_HIT_MKF = 8u          /* DoMKF() pair (a chain >= mkfl, dssaligner.cpp:715-732): aligned by the k-mer / x-drop path
+	RSK_HIT_MKF = 8u,         /* DoMKF() pair (a chain >= mkfl, dssaligner.cpp:715-732): aligned by the k-mer / x-drop path
 	                             (AlignMKF); mu_fwd = m_MKF.m_BestHSPScore, mu_rev = m_MKF.m_BestChainScore */
+	RSK_HIT_GLOBAL = 16u      /* record of rsk_align_global: score = m_GlobalScore, path = m_GlobalPath over both whole chains */
 };
 
 /* which pairs come back from a search call */
@@ -238,6 +239,15 @@ int rsk_postfilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, c
 /* Both stages: what `reseek -search Q -db DB -fast` computes. */
 int rsk_search_fast_db(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *popts,
 		const rsk_search_opts *opts, rsk_results **out);
+
+/* -global: DSSAligner::AlignQueryTarget_Global (global.cpp:7-33) for explicit pairs (alignpair.cpp:110-114, runself.cpp:48-57,
+ * scop40bench.cpp:313): the Mu filter when omega > 0, then ViterbiFastMem (viterbifastmem.cpp:33-193: three-state global
+ * alignment, gap open -1, extend -0.05, terminal gaps free) with TraceBackBitMem.  One record per pair, in pair order:
+ * flags has RSK_HIT_GLOBAL (and RSK_HIT_MU_REJECTED, score -9999, no path when the filter said no); score = m_GlobalScore,
+ * lo_a = lo_b = 0, the path covers both chains completely; E-value fields stay at their ClearAlign values (FLT_MAX) as in
+ * the reference, which does not compute them on this path.  LA*LB <= 1e8 per pair (the reference dies above that). */
+int rsk_align_global(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib, rsk_results **out);
 
 /* ---- results ---- */
 uint64_t rsk_results_count(const rsk_results *r);

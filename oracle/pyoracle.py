@@ -248,6 +248,14 @@ class Port:
         self.lib.orc_align_pair(C.byref(self.params), C.byref(ca), C.byref(cb), C.byref(r), path)
         return r, path.value.decode()
 
+    def align_pair_global(self, A, B):
+        """DSSAligner::AlignQueryTarget_Global: r.score = m_GlobalScore, lo = 0, whole-chain path."""
+        ca, cb = A.as_orc(), B.as_orc()
+        r = OrcResult()
+        path = C.create_string_buffer(A.L + B.L + 2)
+        self.lib.orc_align_pair_global(C.byref(self.params), C.byref(ca), C.byref(cb), C.byref(r), path)
+        return r, path.value.decode()
+
     def align_pairs(self, chainsA, chainsB, ia, ib):
         """Batch (scalar, one thread) - used for the cpu_baseline timing.  Returns the OrcResult array."""
         arrA = (OrcChain * len(chainsA))(*[c.as_orc() for c in chainsA])

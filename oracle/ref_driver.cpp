@@ -211,7 +211,8 @@ int ref_rev_profile(uint L, const char *seq, const float *x, const float *y, con
 
 // ---- the per-pair aligner, driven exactly like runquery.cpp:45,70-71 ----
 // mu / kmers may be NULL (then the Mu filter and MKF are skipped as in the reference).
-// noaccel != 0 calls Align_NoAccel() directly (alignpair / self-rev style).
+// noaccel == 1 calls Align_NoAccel() directly (alignpair / self-rev style); noaccel == 2 calls
+// AlignQueryTarget_Global() and reports m_GlobalScore as the score.
 int ref_align_pair(
   uint LA, const uint8_t *profA, const uint8_t *muA, const uint32_t *kmA, uint nkA,
   const float *xA, const float *yA, const float *zA, float selfrevA,
@@ -236,11 +237,13 @@ int ref_align_pair(
 	DA.SetTarget(CB, &PB, muB ? &MuB : 0, kmB ? &KB : 0, selfrevB);
 	memset(out, 0, sizeof(*out));
 	out->mkf = DA.DoMKF() ? 1 : 0;
-	if (noaccel)
+	if (noaccel == 2)
+		DA.AlignQueryTarget_Global();  // global.cpp:7-33 (-global)
+	else if (noaccel)
 		DA.Align_NoAccel();
 	else
 		DA.AlignQueryTarget();
-	out->score = DA.m_AlnFwdScore;
+	out->score = noaccel == 2 ? DA.m_GlobalScore : DA.m_AlnFwdScore;
 	out->lo_a = DA.m_LoA; out->lo_b = DA.m_LoB; out->hi_a = DA.m_HiA; out->hi_b = DA.m_HiB;
 	out->ids = DA.m_Ids; out->gaps = DA.m_Gaps;
 	out->ts = DA.m_NewTestStatisticA; out->pvalue = DA.m_PvalueA; out->evalue = DA.m_EvalueA;

@@ -826,6 +826,127 @@ void orc_align_pair(const orc_params *p, const orc_chain *A, const orc_chain *B,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * -global: DSSAligner::AlignQueryTarget_Global (global.cpp:7-33) = Mu filter, then ViterbiFastMem
+ * (viterbifastmem.cpp:33-193) over the per-cell score of xdrophsp.cpp:8-33, traced back by TraceBackBitMem
+ * (tracebackbitmem.cpp:8-69).  Three states with prefix-length indices: M[i][j] ends in a match of A[i-1], B[j-1];
+ * D[i][j] in a deletion (A residue alone), I[i][j] in an insertion.  Gap parameters are file statics of the reference:
+ * open -1, extend -0.05, terminal 0; the terminal values apply to column 0, to the column after the last B residue
+ * (deletions only) and to the row after the last A residue (insertions only) - nowhere else, which is what the code does
+ * rather than what the names suggest.  "Minus infinity" is the finite -9e9f (xdpmem.h:6).
+ * ------------------------------------------------------------------------------------------------ */
+#define VIT_NEG (-9e9f)
+static const float vit_open = -1.0f, vit_ext = -0.05f, vit_topen = 0.0f, vit_text = 0.0f;
+
+float orc_viterbi_global(const orc_params *p, const uint8_t *profA, uint32_t LA, const uint8_t *profB, uint32_t LB,
+		char *path, uint32_t *path_len)
+{
+	*path_len = 0;
+	if (path)
+		path[0] = 0;
+	if (LA == 0 || LB == 0)
+		return 0; /* the reference reads Mrow[LB-1] out of range here; callers never pass empty chains */
+	const size_t W = (size_t)LB + 1;
+	uint8_t *tb = (uint8_t *)calloc((size_t)(LA + 1) * W, 1);
+	float *m = (float *)malloc(sizeof(float) * W);   /* m[j] = M[i][j+1] while row i is open */
+	float *d = (float *)malloc(sizeof(float) * W);   /* d[j] = D[i][j] */
+	for (uint32_t j = 0; j <= LB; ++j)
+		m[j] = d[j] = VIT_NEG;
+	float mcorner = 0.0f; /* M[i][0]: 0 for the first row, "minus infinity" below */
+	for (uint32_t i = 0; i < LA; ++i) {
+		float open = vit_topen, ext = vit_text; /* column 0 only */
+		float ins = VIT_NEG;                    /* I[i][j] */
+		float mdiag = mcorner;                  /* M[i][j] */
+		uint8_t *row = tb + (size_t)i * W;
+		for (uint32_t j = 0; j < LB; ++j) {
+			uint8_t bits = 0;
+			const float mhere = mdiag;
+			float best = mhere;
+			if (d[j] > best) { best = d[j]; bits = XB_DM; }
+			if (ins > best) { best = ins; bits = XB_IM; }
+			mdiag = m[j];
+			m[j] = best + subst(p, profA, LA, profB, LB, i, j);
+			const float md = mhere + open;
+			d[j] += ext;
+			if (md >= d[j]) { d[j] = md; bits |= XB_MD; }
+			const float mi = mhere + open;
+			ins += ext;
+			if (mi >= ins) { ins = mi; bits |= XB_MI; }
+			open = vit_open;
+			ext = vit_ext;
+			row[j] = bits;
+		}
+		/* the column after the last B residue: deletions at the terminal price (:129-143) */
+		row[LB] = 0;
+		{
+			const float md = mdiag + vit_topen;
+			d[LB] += vit_text;
+			if (md >= d[LB]) { d[LB] = md; row[LB] = XB_MD; }
+		}
+		mcorner = VIT_NEG;
+	}
+	/* the row after the last A residue: insertions at the terminal price, strict comparison (:151-167) */
+	uint8_t *last = tb + (size_t)LA * W;
+	float ins = VIT_NEG;
+	for (uint32_t j = 1; j < LB; ++j) {
+		last[j] = 0;
+		const float mi = m[j - 1] + vit_topen;
+		ins += vit_text;
+		if (mi > ins) { ins = mi; last[j] = XB_MI; }
+	}
+	float score = m[LB - 1];
+	char state = 'M';
+	if (d[LB] > score) { score = d[LB]; state = 'D'; }
+	if (ins > score) { score = ins; state = 'I'; }
+	/* TraceBackBitMem */
+	if (path) {
+		size_t i = LA, j = LB;
+		uint32_t n = 0;
+		while (i != 0 || j != 0) {
+			path[n++] = state;
+			if (state == 'M') {
+				const uint8_t t = tb[(i - 1) * W + (j - 1)];
+				state = (t & XB_DM) ? 'D' : (t & XB_IM) ? 'I' : 'M';
+				--i; --j;
+			} else if (state == 'D') {
+				const uint8_t t = tb[(i - 1) * W + j];
+				state = (t & XB_MD) ? 'M' : 'D';
+				--i;
+			} else {
+				const uint8_t t = tb[i * W + (j - 1)];
+				state = (t & XB_MI) ? 'M' : 'I';
+				--j;
+			}
+		}
+		for (uint32_t a = 0, b = n ? n - 1 : 0; a < b; ++a, --b) {
+			const char c = path[a]; path[a] = path[b]; path[b] = c;
+		}
+		path[n] = 0;
+		*path_len = n;
+	}
+	free(tb); free(m); free(d);
+	return score;
+}
+
+/* global.cpp:7-33.  r->score carries m_GlobalScore (-9999 after ClearAlign when the filter rejects), lo = 0 */
+void orc_align_pair_global(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path)
+{
+	clear_result(r);
+	r->score = -9999.0f;
+	if (path)
+		path[0] = 0;
+	if (p->omega > 0 && A->mu && B->mu) {
+		r->mu_score = orc_mu_filter_score(p, A->mu, A->L, B->mu, B->L, &r->mu_fwd, &r->mu_rev);
+		if (r->mu_score < p->omega) {
+			r->filtered = 1;
+			return;
+		}
+	}
+	r->score = orc_viterbi_global(p, A->prof, A->L, B->prof, B->L, path, &r->path_len);
+	r->lo_a = 0;
+	r->lo_b = 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * -fast -db prefilter
  * ------------------------------------------------------------------------------------------------ */
 static const int k5_off[5] = {0, 1, 2, 5, 6};

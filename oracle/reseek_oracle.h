@@ -116,6 +116,12 @@ void orc_calc_evalue(const orc_params *p, const orc_chain *A, const orc_chain *B
  * ClearAlign -> (omega>0 && mu present: MuFilter :619) -> Align_NoAccel :929.  path: LA+LB+1 bytes. */
 void orc_align_pair(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path);
 
+/* -global: ViterbiFastMem (viterbifastmem.cpp:33-193) + TraceBackBitMem (tracebackbitmem.cpp:8-69); path needs LA+LB+1 bytes */
+float orc_viterbi_global(const orc_params *p, const uint8_t *profA, uint32_t LA, const uint8_t *profB, uint32_t LB,
+		char *path, uint32_t *path_len);
+/* DSSAligner::AlignQueryTarget_Global (global.cpp:7-33): r->score = m_GlobalScore, lo_a = lo_b = 0 */
+void orc_align_pair_global(const orc_params *p, const orc_chain *A, const orc_chain *B, orc_result *r, char *path);
+
 /* ---- alternative gapless Mu pre-scores (not reachable from the reference CLI) ---- */
 /* swgaplessprofb.cpp:6-61 SWFastGaplessProfb: best gapless local run on ScoreMx_Mu, forward minus reversed-A */
 float orc_mu_gapless_profb(const uint8_t *a, uint32_t LA, const uint8_t *b, uint32_t LB);

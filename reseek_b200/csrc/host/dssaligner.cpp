@@ -297,6 +297,8 @@ void DSSAligner::ClearAlign()
 	m_LDDT = 0;
 	m_MuFwdScore = m_MuRevScore = m_BestHSPScore = m_BestChainScore = 0;
 	m_MuFwdMinusRevScore = 0;
+	m_GlobalScore = -9999;
+	m_GlobalPath.clear();
 	m_Flags = 0;
 	}
 
@@ -394,6 +396,52 @@ void DSSAligner::AlignOne(bool NoAccel)
 	m_XDropAlnCount += (uint)S.mkf_pairs;
 	}
 
+// global.cpp:7-33: Mu filter (when omega > 0), then the global Viterbi alignment; sets m_GlobalScore, m_GlobalPath,
+// m_LoA = m_LoB = 0 and m_Path = m_GlobalPath
+void DSSAligner::AlignQueryTarget_Global()
+	{
+	rsk_asserta(m_Params != 0);
+	rsk_asserta(m_ChainA != 0 && m_ChainB != 0 && m_ProfileA != 0 && m_ProfileB != 0);
+	rsk_ctx *C = Ctx();
+	ChainData A, B;
+	A.Chain = m_ChainA; A.Profile = m_ProfileA; A.MuLetters = m_MuLettersA; A.SelfRevScore = m_SelfRevScoreA;
+	B.Chain = m_ChainB; B.Profile = m_ProfileB; B.MuLetters = m_MuLettersB; B.SelfRevScore = m_SelfRevScoreB;
+	const bool WithMu = (m_MuLettersA != 0 && m_MuLettersB != 0);
+	if (m_SetA == 0)
+		m_SetA = UploadChains(C, vector<ChainData>(1, A), WithMu);
+	if (m_SetB == 0)
+		m_SetB = UploadChains(C, vector<ChainData>(1, B), WithMu);
+	rsk_params R;
+	m_Params->ToRsk(R, DBL_MAX);
+	Check(rsk_ctx_set_params(C, &R));
+	const uint32_t Zero = 0;
+	rsk_results *Res = 0;
+	Check(rsk_align_global(C, m_SetA, m_SetB, 1, &Zero, &Zero, &Res));
+	rsk_asserta(rsk_results_count(Res) == 1);
+	const rsk_hit &H = rsk_results_hits(Res)[0];
+	ClearAlign();
+	m_Flags = H.flags;
+	m_MuFwdScore = H.mu_fwd;
+	m_MuRevScore = H.mu_rev;
+	m_MuFwdMinusRevScore = H.mu_score;
+	++m_AlnCount;
+	if (R.omega > 0 && WithMu)
+		{
+		++m_MuFilterInputCount;
+		if (H.flags & RSK_HIT_MU_REJECTED)
+			++m_MuFilterDiscardCount;
+		}
+	if (!(H.flags & RSK_HIT_MU_REJECTED))
+		{
+		m_GlobalScore = H.score;
+		m_GlobalPath.assign(rsk_results_paths(Res) + H.path_off, H.path_len);
+		m_LoA = 0;
+		m_LoB = 0;
+		m_Path = m_GlobalPath;
+		}
+	rsk_results_free(Res);
+	}
+
 void DSSAligner::AlignQueryTarget() { AlignOne(false); }
 void DSSAligner::Align_NoAccel() { AlignOne(true); }
 
@@ -401,7 +449,7 @@ void DSSAligner::Align_NoAccel() { AlignOne(true); }
 void DSSAligner::GetHitView(rsk_hit &H, rsk_hit_view &V) const
 	{
 	memset(&H, 0, sizeof(H));
-	H.score = m_AlnFwdScore;
+	H.score = (m_Flags & RSK_HIT_GLOBAL) ? m_GlobalScore : m_AlnFwdScore;
 	H.lo_a = m_LoA; H.lo_b = m_LoB; H.hi_a = m_HiA; H.hi_b = m_HiB;
 	H.ids = m_Ids; H.gaps = m_Gaps;
 	H.lddt = m_LDDT;

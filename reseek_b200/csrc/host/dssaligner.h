@@ -55,6 +55,8 @@ public:
 	float m_SelfRevScoreB = FLT_MAX;
 	float m_AlnFwdScore = FLT_MAX;
 	float m_LDDT = 0;
+	float m_GlobalScore = FLT_MAX;   // -global (global.cpp:27-32)
+	string m_GlobalPath;
 	// Mu filter / k-mer path by-products (m_MKF.m_BestHSPScore, m_MKF.m_BestChainScore, GetMuScore in the reference)
 	int m_MuFwdScore = 0;
 	int m_MuRevScore = 0;
@@ -88,6 +90,7 @@ public:
 	bool DoMKF() const;          // dssaligner.cpp:715-732
 	void ClearAlign();           // dssaligner.cpp:906-927
 	void AlignQueryTarget();     // dssaligner.cpp:793-831
+	void AlignQueryTarget_Global();  // global.cpp:7-33
 	void Align_NoAccel();        // dssaligner.cpp:833-850: no Mu filter, no k-mer path
 	const DSSParams &GetParams() const { return *m_Params; }
 

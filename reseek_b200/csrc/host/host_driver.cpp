@@ -6,6 +6,7 @@
 //   rsk_host_demo self  <mode> <set.rskc> <out.tsv> [columns]       DBSearcher::RunSelf           (-search X)
 //   rsk_host_demo query <mode> <stream.rskc> <db.rskc> <out.tsv>    DBSearcher::RunQuery          (-search Q -db DB)
 //   rsk_host_demo pair  <mode> <set.rskc> <i> <j> <out.tsv>         DSSAligner::AlignQueryTarget  (-alignpair)
+//   rsk_host_demo pairglobal <mode> <set.rskc> <i> <j> <out.tsv> [columns]  AlignQueryTarget_Global (-global)
 //   rsk_host_demo fastdb <q.rskc> <db.rskc> <cands.tsv> <out.tsv>   MuPreFilter + PostMuFilter    (-search Q -db DB -fast)
 // From the reference's own .bca files, through the DSS look-alike (no precomputed features):
 //   rsk_host_demo features   <in.bca> <out.rskc>                               DSS only (runs without a GPU)
@@ -341,6 +342,25 @@ int main(int argc, char **argv)
 		FILE *f = fopen(argv[6], "w");
 		if (!DA.m_Path.empty())   // alignpair.cpp:110-117
 			DA.ToTsv(f, true);
+		fclose(f);
+		return 0;
+		}
+	if (Cmd == "pairglobal" && argc >= 7)   // alignpair.cpp:110-114 with -global
+		{
+		DSSParams Params;
+		Params.SetMode(ParseMode(argv[2]));
+		LoadedSet S;
+		Load(argv[3], S);
+		const uint i = (uint)atoi(argv[4]), j = (uint)atoi(argv[5]);
+		rsk_asserta(i < S.Chains.size() && j < S.Chains.size());
+		DSSAligner DA;
+		DA.SetParams(Params);
+		DA.SetQuery(S.Chains[i], &S.Profiles[i], S.Data[i].MuLetters, S.Data[i].MuLetters ? &S.Kmers[i] : 0, S.SelfRevs[i]);
+		DA.SetTarget(S.Chains[j], &S.Profiles[j], S.Data[j].MuLetters, S.Data[j].MuLetters ? &S.Kmers[j] : 0, S.SelfRevs[j]);
+		DA.AlignQueryTarget_Global();
+		FILE *f = fopen(argv[6], "w");
+		if (!DA.m_GlobalPath.empty())   // runself.cpp:50-56
+			DA.ToTsvColumns(f, true, argc > 7 ? argv[7] : "query+target+gscore+dpscore+cigar");
 		fclose(f);
 		return 0;
 		}

@@ -1753,6 +1753,173 @@ extern "C" int rsk_mu_gapless_scores(rsk_ctx *ctx, const rsk_chainset *A, const 
 	return RSK_OK;
 }
 
+// -global: DSSAligner::AlignQueryTarget_Global (global.cpp:7-33) for explicit pairs.  One record per pair, in pair order.
+extern "C" int rsk_align_global(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib, rsk_results **out)
+{
+	if (!ctx || !A || !B || !out || (npairs && (!ia || !ib)))
+		return fail(RSK_ERR_ARG, "rsk_align_global: null argument");
+	*out = nullptr;
+	if (npairs > 0xffffffffull)
+		return fail(RSK_ERR_LIMIT, "rsk_align_global: too many pairs");
+	uint32_t maxLA = 1, maxLB = 1;
+	for (uint64_t k = 0; k < npairs; ++k) {
+		if (ia[k] >= A->d.n || ib[k] >= B->d.n)
+			return fail(RSK_ERR_ARG, "pair %llu: chain index out of range", (unsigned long long)k);
+		const uint64_t la = A->hlen[ia[k]], lb = B->hlen[ib[k]];
+		if (la * lb > 100ull * 1000 * 1000)  // viterbifastmem.cpp:36-37 dies here
+			return fail(RSK_ERR_LIMIT, "rsk_align_global: pair %llu too long (LA=%llu, LB=%llu)", (unsigned long long)k,
+					(unsigned long long)la, (unsigned long long)lb);
+		maxLA = std::max<uint32_t>(maxLA, (uint32_t)la);
+		maxLB = std::max<uint32_t>(maxLB, (uint32_t)lb);
+	}
+	rsk_results *res = new rsk_results();
+	if (npairs == 0) {
+		*out = res;
+		return RSK_OK;
+	}
+	// Mu filter first when it is on (global.cpp:11-22).  MuFilter() does not look at the chain lengths, so the k-mer path
+	// of the local search must not divert long chains here: the filter stage of the pair search runs with mkfl = infinity.
+	std::vector<uint8_t> skip;
+	std::vector<rsk_hit> filt;
+	const bool filter = ctx->params.omega > 0 && A->has_mu && B->has_mu;
+	if (filter) {
+		const rsk_params saved = ctx->params;
+		rsk_params p = saved;
+		p.mkfl = 0xffffffffu;
+		int rc = rsk_ctx_set_params(ctx, &p);
+		rsk_results *fr = nullptr;
+		if (rc == RSK_OK) {
+			rsk_search_opts o;
+			memset(&o, 0, sizeof(o));
+			o.keep = RSK_KEEP_ALL;
+			o.skip_evalue = 1;
+			rc = rsk_search_pairs(ctx, A, B, npairs, ia, ib, &o, &fr);
+		}
+		const int rc2 = rsk_ctx_set_params(ctx, &saved);
+		if (rc != RSK_OK || rc2 != RSK_OK || !fr || fr->nhits != npairs) {
+			delete fr;
+			delete res;
+			return rc != RSK_OK ? rc : fail(RSK_ERR_CUDA, "rsk_align_global: filter stage failed");
+		}
+		skip.resize(npairs);
+		filt.assign(fr->hits, fr->hits + npairs);
+		for (uint64_t k = 0; k < npairs; ++k)
+			skip[k] = (filt[k].flags & RSK_HIT_MU_REJECTED) ? 1 : 0;
+		delete fr;
+	}
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	// work order: largest matrices first; path slots of LA+LB bytes
+	std::vector<uint32_t> order(npairs);
+	std::iota(order.begin(), order.end(), 0u);
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+		return (uint64_t)A->hlen[ia[x]] * B->hlen[ib[x]] > (uint64_t)A->hlen[ia[y]] * B->hlen[ib[y]];
+	});
+	std::vector<unsigned long long> poff(npairs);
+	unsigned long long pool_bytes = 0;
+	for (uint64_t k = 0; k < npairs; ++k) {
+		poff[k] = pool_bytes;
+		pool_bytes += (unsigned long long)A->hlen[ia[k]] + B->hlen[ib[k]];
+	}
+	const size_t tb_stride = (global_tb_bytes(maxLA, maxLB) + 15) & ~(size_t)15;
+	const uint32_t bnd_stride = (maxLB + 1 + 3) & ~3u;
+	const int wpb = global_warps_per_block();
+	size_t warps = std::min<size_t>((size_t)ctx->num_sms * 2 * wpb, (size_t)npairs);
+	warps = std::min<size_t>(warps, std::max<size_t>(1, ((size_t)8 << 30) / tb_stride));  // at most 8 GB of trace scratch
+	const int blocks = (int)((warps + wpb - 1) / wpb);
+	warps = (size_t)blocks * wpb;
+	uint32_t *d_a = nullptr, *d_b = nullptr, *d_order = nullptr;
+	uint8_t *d_skip = nullptr, *d_tb = nullptr;
+	unsigned long long *d_poff = nullptr;
+	char *d_pool = nullptr;
+	GlobalRec *d_rec = nullptr;
+	float *d_bnd = nullptr;
+	unsigned int *d_cnt = nullptr;
+	auto cleanup = [&]() {
+		cudaFree(d_a); cudaFree(d_b); cudaFree(d_order); cudaFree(d_skip); cudaFree(d_tb); cudaFree(d_poff);
+		cudaFree(d_pool); cudaFree(d_rec); cudaFree(d_bnd); cudaFree(d_cnt);
+	};
+	if (cudaMalloc((void **)&d_a, 4 * npairs) != cudaSuccess || cudaMalloc((void **)&d_b, 4 * npairs) != cudaSuccess ||
+		cudaMalloc((void **)&d_order, 4 * npairs) != cudaSuccess || cudaMalloc((void **)&d_skip, npairs) != cudaSuccess ||
+		cudaMalloc((void **)&d_poff, 8 * npairs) != cudaSuccess || cudaMalloc((void **)&d_pool, pool_bytes + 16) != cudaSuccess ||
+		cudaMalloc((void **)&d_rec, sizeof(GlobalRec) * npairs) != cudaSuccess ||
+		cudaMalloc((void **)&d_tb, tb_stride * warps) != cudaSuccess ||
+		cudaMalloc((void **)&d_bnd, sizeof(float) * 2 * bnd_stride * warps) != cudaSuccess ||
+		cudaMalloc((void **)&d_cnt, sizeof(unsigned int)) != cudaSuccess) {
+		cudaGetLastError();
+		cleanup();
+		delete res;
+		return fail(RSK_ERR_NOMEM, "rsk_align_global: device buffers (%zu warps x %zu trace bytes)", warps, tb_stride);
+	}
+	cudaMemcpyAsync(d_a, ia, 4 * npairs, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(d_b, ib, 4 * npairs, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(d_order, order.data(), 4 * npairs, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(d_poff, poff.data(), 8 * npairs, cudaMemcpyHostToDevice, st);
+	if (filter)
+		cudaMemcpyAsync(d_skip, skip.data(), npairs, cudaMemcpyHostToDevice, st);
+	cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), st);
+	GlobalArgs ga;
+	memset(&ga, 0, sizeof(ga));
+	ga.profA = A->d.prof8; ga.offA = A->d.off; ga.lenA = A->d.len;
+	ga.profB = B->d.prof8; ga.offB = B->d.off; ga.lenB = B->d.len;
+	ga.npairs = (uint32_t)npairs;
+	ga.pair_a = d_a; ga.pair_b = d_b; ga.order = d_order;
+	ga.skip = filter ? d_skip : nullptr;
+	ga.path_off = d_poff; ga.pool = d_pool; ga.rec = d_rec;
+	ga.tb = d_tb; ga.tb_stride = tb_stride;
+	ga.bnd = d_bnd; ga.bnd_stride = bnd_stride;
+	ga.counter = d_cnt;
+	ga.tables = ctx->d_tables;
+	const int nl = launch_global(ga, blocks, st);
+	std::vector<GlobalRec> recs(npairs);
+	size_t cap = 0;
+	res->paths = (char *)g_blocks.get(pool_bytes + 16, cap);
+	res->paths_cap = cap;
+	res->hits = (rsk_hit *)g_blocks.get(npairs * sizeof(rsk_hit), cap);
+	res->hits_cap = cap;
+	cudaError_t e = nl < 0 ? cudaErrorLaunchFailure : cudaSuccess;
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(recs.data(), d_rec, sizeof(GlobalRec) * npairs, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(res->paths, d_pool, pool_bytes, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(st);
+	cleanup();
+	if (e != cudaSuccess || !res->paths || !res->hits) {
+		delete res;
+		return fail(RSK_ERR_CUDA, "rsk_align_global: %s", cudaGetErrorString(e));
+	}
+	for (uint64_t k = 0; k < npairs; ++k) {
+		rsk_hit &h = res->hits[k];
+		memset(&h, 0, sizeof(h));
+		h.a = ia[k]; h.b = ib[k];
+		// ClearAlign values (dssaligner.cpp:906-927) for everything the global path does not set
+		h.hi_a = h.hi_b = h.ids = h.gaps = 0xffffffffu;
+		h.ts = -FLT_MAX;
+		h.pvalue = h.evalue = h.qual = FLT_MAX;
+		h.flags = RSK_HIT_GLOBAL;
+		if (filter) {
+			h.mu_fwd = filt[k].mu_fwd; h.mu_rev = filt[k].mu_rev; h.mu_score = filt[k].mu_score;
+		}
+		h.score = recs[k].score;  // m_GlobalScore
+		if (filter && skip[k]) {
+			h.flags |= RSK_HIT_MU_REJECTED;
+			h.lo_a = h.lo_b = 0xffffffffu;
+			continue;
+		}
+		h.lo_a = h.lo_b = 0;      // global.cpp:30-31
+		h.path_len = recs[k].path_len;
+		h.path_off = poff[k];
+	}
+	res->nhits = npairs;
+	res->npath = pool_bytes;
+	ctx->stats.kernel_launches += nl;
+	ctx->stats.pairs = npairs;
+	*out = res;
+	return RSK_OK;
+}
+
 extern "C" int rsk_chainset_selfrev(rsk_ctx *ctx, rsk_chainset *S, const rsk_chainset *Srev, float *scores_out)
 {
 	if (!ctx || !S || !Srev)

@@ -237,14 +237,16 @@ extern "C" int rsk_format_tsv(const rsk_hit_view *v, int up_, const char *column
 			line += row;
 		}
 		else if (name == "newts") fmt(line, "%.3g", h.ts);
-		else if (name == "raw") fmt(line, "%.3g", h.score);
-		else if (name == "dpscore") fmt(line, "%.4g", h.score);
+		// m_AlnFwdScore; a record of rsk_align_global carries m_GlobalScore in score, and the local score stays 0 there
+		else if (name == "raw") fmt(line, "%.3g", (h.flags & RSK_HIT_GLOBAL) ? 0.0f : h.score);
+		else if (name == "dpscore") fmt(line, "%.4g", (h.flags & RSK_HIT_GLOBAL) ? 0.0f : h.score);
 		else if (name == "lddt") fmt(line, "%.4g", h.lddt);
 		else if (name == "ids") fmtu(line, h.ids);
 		else if (name == "gaps") fmtu(line, h.gaps);
 		else if (name == "aq") fmt(line, "%.4f", h.qual);
 		else if (name == "muhsp") { char b[32]; snprintf(b, sizeof(b), "%d", (h.flags & RSK_HIT_MKF) ? h.mu_fwd : 0); line += b; }
 		else if (name == "muchain") { char b[32]; snprintf(b, sizeof(b), "%d", (h.flags & RSK_HIT_MKF) ? h.mu_rev : 0); line += b; }
+		else if (name == "gscore") fmt(line, "%.1f", (h.flags & RSK_HIT_GLOBAL) ? h.score : -9999.0f);  // m_GlobalScore; ClearAlign leaves -9999 (dssaligner.cpp:925)
 		else if (name == "cigar") {
 			std::string c;
 			path_to_cigar(v->path, v->path ? h.path_len : 0, up, c);

@@ -219,6 +219,27 @@ struct GaplessArgs {
 };
 int launch_mu_gapless(const GaplessArgs &args, cudaStream_t stream);
 
+// K9: global alignment of explicit pairs (-global), see global_kernel.cu
+struct GlobalRec { float score; uint32_t path_len; };
+struct GlobalArgs {
+	const uint64_t *profA; const uint64_t *offA; const uint32_t *lenA;
+	const uint64_t *profB; const uint64_t *offB; const uint32_t *lenB;
+	uint32_t npairs;
+	const uint32_t *pair_a, *pair_b;   // [npairs]
+	const uint32_t *order;             // [npairs] work order (largest matrices first)
+	const uint8_t *skip;               // [npairs] 1 = rejected by the Mu filter, or null
+	const unsigned long long *path_off;  // [npairs] slot of LA+LB bytes in pool
+	char *pool;
+	GlobalRec *rec;                    // [npairs]
+	uint8_t *tb; size_t tb_stride;     // per-warp trace matrix (bytes; stride a multiple of 4)
+	float *bnd; uint32_t bnd_stride;   // per-warp 2 x bnd_stride floats
+	unsigned int *counter;
+	const float *tables;
+};
+size_t global_tb_bytes(uint32_t maxLA, uint32_t maxLB);
+int global_warps_per_block();
+int launch_global(const GlobalArgs &args, int blocks, cudaStream_t stream);
+
 // K6..K8: `-fast -db` 5-mer prefilter, see prefilter_kernel.cu
 struct PfArgs {
 	const int *kmer_mx;          // Mu_S_ij_i8 widened to int32 [36*36]

@@ -12,7 +12,7 @@ NFEAT = 8
 TABLE_FLOATS = 2192
 MODE_FAST, MODE_SENSITIVE, MODE_VERYSENSITIVE = 1, 2, 3
 KEEP_HITS, KEEP_ALL = 0, 1
-HIT_MU_REJECTED, HIT_HAS_EVALUE, HIT_REPORTED, HIT_MKF = 1, 2, 4, 8
+HIT_MU_REJECTED, HIT_HAS_EVALUE, HIT_REPORTED, HIT_MKF, HIT_GLOBAL = 1, 2, 4, 8, 16
 FLT_MAX = float(np.finfo(np.float32).max)
 
 
@@ -108,6 +108,7 @@ def load_library():
     L.rsk_search_self.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
     L.rsk_search_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                    C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
+    L.rsk_align_global.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     L.rsk_mu_gapless_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rsk_chainset_selfrev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rsk_search_cross_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts)]
@@ -409,6 +410,16 @@ class Context:
         r = C.c_void_p()
         _check(load_library().rsk_search_pairs(self.handle, A.handle, B.handle, len(ia), _ptr(ia), _ptr(ib),
                                                C.byref(o), C.byref(r)))
+        return Results(r)
+
+    def align_global(self, A, B, ia, ib):
+        """-global: DSSAligner::AlignQueryTarget_Global (global.cpp:7-33) for explicit pairs; one record per pair, in order,
+        score = m_GlobalScore, whole-chain path."""
+        ia = np.ascontiguousarray(ia, np.uint32)
+        ib = np.ascontiguousarray(ib, np.uint32)
+        assert len(ia) == len(ib)
+        r = C.c_void_p()
+        _check(load_library().rsk_align_global(self.handle, A.handle, B.handle, len(ia), _ptr(ia), _ptr(ib), C.byref(r)))
         return Results(r)
 
     def prefilter(self, Q, T, index_mode=0, rsb_size=0, kl_swap=True, raw_only=False):

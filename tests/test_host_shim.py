@@ -139,3 +139,19 @@ def test_fastdb_prefilter_postfilter_matches_cabi(built_lib, tmp_path):
             for k, h in enumerate(res.hits) if float(h["evalue"]) <= 10]
     assert (tmp_path / "hits.tsv").read_text().splitlines() == want
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_alignquerytarget_global_batch_of_one(built_lib, tmp_path, port):
+    """DSSAligner::AlignQueryTarget_Global of the look-alike (alignpair.cpp:110-114 with -global): gscore, dpscore (stays 0
+    on this path) and CIGAR as the reference's writer prints them, from the oracle's global alignment."""
+    import reseek_b200 as rb
+    from tests.util import to_oracle_chains
+    q, db, lq, ld, sq, sd = _sets(tmp_path)
+    oc = to_oracle_chains(db)
+    for i, j in ((0, 1), (3, 3), (5, 2)):
+        r = _run("pairglobal", "verysensitive", tmp_path / "db.rskc", i, j, tmp_path / "g.tsv")
+        assert r.returncode == 0, r.stderr
+        orc, opath = port(3).align_pair_global(oc[i], oc[j])
+        want = "\t".join([ld[i], ld[j], "%.1f" % orc.score, "0", rb.path_to_cigar(opath, up=True)])
+        assert (tmp_path / "g.tsv").read_text().splitlines() == [want]

@@ -103,3 +103,23 @@ def test_prefilter_matches_reference_candidate_lists(port, name, kw):
     pairs = [(t, q) for t in sorted(got) for q in got[t]]
     want = list(zip(g[f"{name}_t"].tolist(), g[f"{name}_q"].tolist()))
     assert pairs == want and len(want) >= 50
+
+
+@pytest.mark.parametrize("mode", [3, 2])
+def test_global_alignment_matches_reference_fixtures(port, mode):
+    """-global: the restatement of ViterbiFastMem + TraceBackBitMem under AlignQueryTarget_Global (global.cpp:7-33) against
+    the reference's results (tools/make_golden_global.py): m_GlobalScore bit for bit and the same path; under -sensitive the
+    Mu filter rejects first (score stays -9999, no path)."""
+    g = np.load(GOLDEN / "golden_global.npz")
+    chains = load_chains()
+    p = port(mode)
+    paths = bytes(g[f"paths_mode{mode}"]).decode()
+    off = g[f"path_off_mode{mode}"].astype(np.int64)
+    step = 1 if mode == 2 else 3  # every third pair without the filter keeps the CPU suite short
+    n = 0
+    for k in range(0, len(g["a"]), step):
+        r, path = p.align_pair_global(chains[int(g["a"][k])], chains[int(g["b"][k])])
+        assert bits(r.score) == bits(g[f"score_mode{mode}"][k]), f"pair {k}"
+        assert path == paths[off[k]:off[k + 1]], f"pair {k} path"
+        n += 1
+    assert n >= 100
