@@ -153,6 +153,51 @@ void DBSearcher::BaseOnAln(DSSAligner &DA, bool Up)
 	m_Lock.unlock();
 	}
 
+// runself.cpp:48-57 (-global): the same pairs through AlignQueryTarget_Global, emitted when the global path is not empty
+// (i.e. unless the Mu filter rejected the pair).  Rows of the pair triangle go to the GPU in chunks of about a million pairs.
+void DBSearcher::RunSelfGlobal()
+	{
+	DSSAligner &DA = *m_DAs[0];
+	rsk_ctx *C = GetContext();
+	const uint N = GetDBChainCount();
+	vector<uint32_t> ia, ib;
+	auto Flush = [&]()
+		{
+		if (ia.empty())
+			return;
+		rsk_results *Res = 0;
+		Check(rsk_align_global(C, m_DBSet, m_DBSet, ia.size(), ia.data(), ib.data(), &Res));
+		const uint64_t n = rsk_results_count(Res);
+		const rsk_hit *Hits = rsk_results_hits(Res);
+		const char *Pool = rsk_results_paths(Res);
+		DSSAligner::m_AlnCount += (uint)n;
+		for (uint64_t k = 0; k < n; ++k)
+			{
+			const rsk_hit &H = Hits[k];
+			DA.FromHit(H, Pool, GetDBChainData(H.a), GetDBChainData(H.b));
+			if (DA.m_GlobalPath.empty())
+				continue;
+			BaseOnAln(DA, true);
+			if (H.a != H.b)
+				BaseOnAln(DA, false);
+			}
+		rsk_results_free(Res);
+		ia.clear();
+		ib.clear();
+		};
+	for (uint i = 0; i < N; ++i)
+		{
+		for (uint j = i; j < N; ++j)
+			{
+			ia.push_back(i);
+			ib.push_back(j);
+			}
+		if (ia.size() >= (1u << 20))
+			Flush();
+		}
+	Flush();
+	}
+
 // runself.cpp:72-145: pairs (i, j >= i), A = chain i, B = chain j, both directions emitted (runself.cpp:60-66)
 void DBSearcher::RunSelf()
 	{
@@ -165,6 +210,16 @@ void DBSearcher::RunSelf()
 	m_Params->ToRsk(R, m_MaxEvalue);
 	Check(rsk_ctx_set_params(C, &R));
 	UploadDB();
+	if (m_Global)
+		{
+		RunSelfGlobal();
+		m_ProcessedQueryCount = GetDBChainCount();
+		m_Secs = (uint)(time(0) - t_start);
+		if (m_Secs == 0)
+			m_Secs = 1;
+		RunStats();
+		return;
+		}
 	rsk_search_opts O;
 	memset(&O, 0, sizeof(O));
 	O.keep = RSK_KEEP_HITS;

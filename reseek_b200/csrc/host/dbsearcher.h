@@ -67,6 +67,7 @@ public:
 	FILE *m_fAln = 0;            // g_fAln (-aln), g_fFasta2 (-fasta2), opt(unaligned), opt(rowlen)
 	FILE *m_fFasta2 = 0;
 	bool m_Unaligned = false;
+	bool m_Global = false;       // opt(global): RunSelf aligns globally (runself.cpp:48-57)
 	uint m_RowLen = 0;
 	const char *m_Columns = 0;   // -columns, 0 = default
 	bool m_OwnsChains = false;   // the reference's destructor deletes chains/profiles (dbsearcher.cpp:12-22)
@@ -83,6 +84,7 @@ public:
 	void RunQuery(ChainSource &QCR);
 	void RunQuery(ChainReader2 &QCR);  // runquery.cpp:82-130: streamed chains read from a .bca, DSS + self-reverse per block
 	void RunSelf();
+	void RunSelfGlobal();
 	void RunStats() const;
 	bool Reject(DSSAligner &DA, bool Up) const;
 

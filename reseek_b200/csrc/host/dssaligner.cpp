@@ -327,6 +327,16 @@ void DSSAligner::FromHit(const rsk_hit &H, const char *PathPool, const ChainData
 		}
 	if (H.flags & RSK_HIT_MU_REJECTED)
 		return;
+	if (H.flags & RSK_HIT_GLOBAL)   // a record of rsk_align_global: what AlignQueryTarget_Global leaves (global.cpp:27-32)
+		{
+		m_GlobalScore = H.score;
+		if (PathPool != 0)
+			m_GlobalPath.assign(PathPool + H.path_off, H.path_len);
+		m_LoA = 0;
+		m_LoB = 0;
+		m_Path = m_GlobalPath;
+		return;
+		}
 	m_AlnFwdScore = H.score;
 	if (H.path_len == 0)
 		return;

@@ -184,6 +184,8 @@ static void OpenAlnOutputs(DBSearcher &DBS)
 		DBS.m_Unaligned = atoi(e) != 0;
 	if (const char *e = getenv("RSK_ROWLEN"))
 		DBS.m_RowLen = (uint)atoi(e);
+	if (const char *e = getenv("RSK_GLOBAL"))
+		DBS.m_Global = atoi(e) != 0;
 	}
 static void CloseAlnOutputs(DBSearcher &DBS)
 	{

@@ -11,7 +11,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from tests.golden_util import ALN_COLUMNS, GOLDEN, SEARCH_COLUMNS, aln_blocks, fasta2_records, golden_bca, golden_bca_short
+from tests.golden_util import ALN_COLUMNS, GLOBAL_COLUMNS, GOLDEN, SEARCH_COLUMNS, aln_blocks, fasta2_records, golden_bca, golden_bca_short
 
 ROOT = Path(__file__).resolve().parent.parent
 DEMO = ROOT / "reseek_b200" / "rsk_host_demo"
@@ -142,3 +142,15 @@ def test_search_db_aln_rowlen_unaligned_match_reference_binary(built_lib, tmp_pa
     got = aln_blocks((tmp_path / "out.aln").read_text())
     assert len(got) >= 50 and got == aln_blocks((GOLDEN / "golden_aln_db_verysensitive.aln").read_text())
     assert fasta2_records((tmp_path / "out.fa2").read_text()) == fasta2_records((GOLDEN / "golden_aln_db_verysensitive.fa2").read_text())
+
+
+@pytest.mark.gpu
+def test_selfsearch_global_matches_reference_binary(built_lib, tmp_path):
+    """`-search gshort.bca -global -verysensitive` (runself.cpp:48-57): global score, coordinates as the reference prints
+    them on this path (hi unset) and CIGAR, line for line."""
+    g4, gs = golden_bca_short(tmp_path)
+    r = _run("selfsearch", "verysensitive", gs, tmp_path / "out.tsv", GLOBAL_COLUMNS, RSK_GLOBAL=1)
+    assert r.returncode == 0, r.stderr
+    got = sorted((tmp_path / "out.tsv").read_text().splitlines())
+    want = _golden("golden_global_self.tsv")
+    assert len(want) == 196 and got == want

@@ -24,3 +24,16 @@ for rep in range(3):
     res = ctx.align_global(A, A, ia, ib)
     dt = time.time() - t0
     print(f"rep {rep}: {npairs} pairs, {cells:.3e} cells, wall {dt:.3f}s, {cells / dt:.3e} cells/s (end to end), hits {len(res.hits)}")
+
+# CPU side of the same thing: the oracle port (one thread) on a bounded sample of the same pairs
+from oracle.pyoracle import Port  # noqa: E402
+from tests.util import to_oracle_chains  # noqa: E402
+oc = to_oracle_chains(a)
+port = Port(mode=3)
+m = min(300, npairs)
+t0 = time.time()
+for k in range(m):
+    port.align_pair_global(oc[int(ia[k])], oc[int(ib[k])])
+dt = time.time() - t0
+c = float(np.sum(a.lens[ia[:m]].astype(np.float64) * a.lens[ib[:m]]))
+print(f"cpu oracle (1 thread): {m} pairs, {c:.3e} cells, {dt:.3f}s, {c / dt:.3e} cells/s")
