@@ -22,15 +22,24 @@ constexpr unsigned TB_DM = 1, TB_IM = 2, TB_MD = 4, TB_MI = 8;          // trace
 constexpr int kGlobalWarps = 8;
 constexpr unsigned kFull = 0xffffffffu;
 
-// xdrophsp.cpp:8-33: starts from 0, features 0..7 in order
-__device__ __forceinline__ float cell_score(const float *tab, const uint64_t ea, const uint64_t eb)
+// xdrophsp.cpp:8-33: starts from 0, features 0..7 in order.  rowbase[f] = index of the table row of this lane's A letter of
+// feature f, minus the feature's e-letter base, so that a B e-letter byte indexes it directly.
+__device__ __forceinline__ void row_bases(const uint64_t ea, int (&rowbase)[RSK_NFEAT])
 {
-	float t = 0.0f;
 #pragma unroll
 	for (int f = 0; f < RSK_NFEAT; ++f) {
 		const int a = (int)((ea >> (8 * f)) & 0xff) - feat_base(f);
-		const int b = (int)((eb >> (8 * f)) & 0xff) - feat_base(f);
-		t += tab[feat_table_off(f) + a * feat_alpha(f) + b];
+		rowbase[f] = feat_table_off(f) + a * feat_alpha(f) - feat_base(f);
+	}
+}
+__device__ __forceinline__ float cell_score(const float *tab, const int (&rowbase)[RSK_NFEAT], const uint64_t eb)
+{
+	const unsigned lo = (unsigned)eb, hi = (unsigned)(eb >> 32);
+	float t = 0.0f;
+#pragma unroll
+	for (int f = 0; f < RSK_NFEAT; ++f) {
+		const unsigned w = f < 4 ? lo : hi;
+		t += tab[rowbase[f] + (int)((w >> (8 * (f & 3))) & 0xffu)];
 	}
 	return t;
 }
@@ -77,7 +86,8 @@ __global__ void __launch_bounds__(kGlobalWarps * 32) global_viterbi_kernel(const
 		for (int pass = 0; pass < npass; ++pass) {
 			const int i = (pass << 5) + lane;
 			const bool row = i < LA;
-			const uint64_t ea = row ? PA[i] : 0;
+			int rowbase[RSK_NFEAT];
+			row_bases(row ? PA[i] : 0, rowbase);
 			uint32_t *trow = reinterpret_cast<uint32_t *>(tb + (size_t)i * W);
 			float ins = kNeg;                       // I[i][j]
 			float mout = kNeg, dout = kNeg;          // M[i+1][j+1], D[i+1][j] of the cell just computed
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(kGlobalWarps * 32) global_viterbi_kernel(const
 						float best = mhere;
 						if (recvD > best) { best = recvD; bits = TB_DM; }
 						if (ins > best) { best = ins; bits = TB_IM; }
-						mout = best + cell_score(s_tab, ea, PB[j]);
+						mout = best + cell_score(s_tab, rowbase, PB[j]);
 						const float open = j == 0 ? kTermOpen : kOpen, ext = j == 0 ? kTermExt : kExt;
 						const float md = mhere + open;
 						float dn = recvD + ext;

@@ -1825,7 +1825,7 @@ extern "C" int rsk_align_global(rsk_ctx *ctx, const rsk_chainset *A, const rsk_c
 	const size_t tb_stride = (global_tb_bytes(maxLA, maxLB) + 15) & ~(size_t)15;
 	const uint32_t bnd_stride = (maxLB + 1 + 3) & ~3u;
 	const int wpb = global_warps_per_block();
-	size_t warps = std::min<size_t>((size_t)ctx->num_sms * 2 * wpb, (size_t)npairs);
+	size_t warps = std::min<size_t>((size_t)ctx->num_sms * 4 * wpb, (size_t)npairs);  // 62 registers: four 8-warp CTAs per SM
 	warps = std::min<size_t>(warps, std::max<size_t>(1, ((size_t)8 << 30) / tb_stride));  // at most 8 GB of trace scratch
 	const int blocks = (int)((warps + wpb - 1) / wpb);
 	warps = (size_t)blocks * wpb;
