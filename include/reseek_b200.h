@@ -279,6 +279,15 @@ long long rsk_format_aln(const rsk_hit_view *v, int up, uint32_t rowlen, char *o
  * convention as rsk_format_aln. */
 long long rsk_format_fasta2(const rsk_hit_view *v, int up, int global, char *out, size_t cap);
 
+/* ---- superposition: DSSAligner::GetKabsch (dssaligner.cpp:1371-1385) -> Kabsch (kabsch.cpp:330-387) ----
+ * Host code in double precision, as in the reference.  xyz_* = [3][len] coordinate planes of the two chains (the layout of
+ * rsk_chains_host for one chain), path/lo_* from the hit.  On return y ~ u x + t maps a QUERY residue x onto its target
+ * partner (up != 0: query = A), u row-major 3x3; *msd = residual sum of squares / number of M columns, the value the
+ * reference's Kabsch() returns.  Horn's quaternion method instead of the reference's TM-align routine: same optimum, results
+ * agree to ~1e-6 (tests/test_cabi.py).  Applying it to PDB ATOM lines (-alignpair -output) is left to the caller. */
+int rsk_kabsch(const float *xyz_a, uint32_t len_a, const float *xyz_b, uint32_t len_b, uint32_t lo_a, uint32_t lo_b,
+		const char *path, uint32_t path_len, int up, double t[3], double u[9], double *msd);
+
 /* ---- host-side statistics: StatSig (statsig.cpp:27-50, statsig.h:8-23); libm double pow, as the reference ---- */
 double rsk_pvalue(double ts);
 double rsk_evalue(double ts);

@@ -364,6 +364,18 @@ class Ref:
             C.c_float(B.selfrev), int(noaccel), C.byref(r), path, A.L + B.L + 2)
         return r, path.value.decode()
 
+    def kabsch(self, A, B, lo_a, lo_b, path):
+        """Kabsch(ChainA, ChainB, LoA, LoB, Path, t, u) of the reference: returns (msd, t[3], u[3][3])."""
+        t = (C.c_double * 3)()
+        u = (C.c_double * 9)()
+
+        def p(a):
+            return a.ctypes.data_as(C.c_void_p)
+        self.lib.ref_kabsch.restype = C.c_double
+        r = self.lib.ref_kabsch(A.L, p(A.xyz[0]), p(A.xyz[1]), p(A.xyz[2]), B.L, p(B.xyz[0]), p(B.xyz[1]), p(B.xyz[2]),
+                                int(lo_a), int(lo_b), path.encode(), t, u)
+        return float(r), np.array(t[:]), np.array(u[:]).reshape(3, 3)
+
     def align_batch(self, A, B, ia, ib, nthreads):
         """A, B: SoA chain sets (objects with lens/prof/mu/xyz/selfrev numpy arrays).  Multi-threaded reference loop."""
         ia = np.ascontiguousarray(ia, np.uint32)

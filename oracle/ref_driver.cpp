@@ -73,6 +73,10 @@ struct ref_result
 	uint32_t path_len;
 	};
 
+// kabsch.cpp:330 (C++ linkage)
+double Kabsch(const PDBChain &ChainA, const PDBChain &ChainB, uint LoA, uint LoB, const string &Path,
+  double t[3], double u[3][3]);
+
 extern "C" {
 
 // mode: 1 fast, 2 sensitive, 3 verysensitive (dssparams.cpp:52-81)
@@ -389,6 +393,23 @@ double ref_lddt(uint LA, const float *xA, const float *yA, const float *zA,
 // SetQuery when the A chain changes, SetTarget + AlignQueryTarget per pair - runquery.cpp:45,70-71), std::thread
 // over contiguous pair ranges like dbsearcher's thread pool.  Chains are SoA: len[], prof [8][total] plane-major,
 // mu [total] (may be NULL), xyz [3][total], selfrev[].  out_score / out_evalue: per pair.
+// The reference's superposition (kabsch.cpp:330-387 over :21-327): rotation u, translation t mapping the aligned A residues
+// onto their B partners; returns the residual sum of squares divided by the number of M columns.
+double ref_kabsch(uint LA, const float *xA, const float *yA, const float *zA,
+  uint LB, const float *xB, const float *yB, const float *zB,
+  uint LoA, uint LoB, const char *path, double *t, double *u)
+	{
+	PDBChain CA, CB;
+	MakeChain(CA, "A", LA, 0, xA, yA, zA);
+	MakeChain(CB, "B", LB, 0, xB, yB, zB);
+	double uu[3][3];
+	double r = Kabsch(CA, CB, LoA, LoB, string(path), t, uu);
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+			u[3*i + j] = uu[i][j];
+	return r;
+	}
+
 int ref_align_batch(int nthreads,
   uint nA, const uint32_t *lenA, const uint8_t *profA, const uint8_t *muA, const float *xyzA, const float *selfrevA,
   uint nB, const uint32_t *lenB, const uint8_t *profB, const uint8_t *muB, const float *xyzB, const float *selfrevB,

@@ -528,6 +528,33 @@ void DSSAligner::WriteBlock(FILE *f, bool Up, int Kind, bool Global) const
 		}
 	}
 
+// dssaligner.cpp:1371-1385: rotation u and translation t that put the query's aligned residues onto the target's
+float DSSAligner::GetKabsch(double t[3], double u[3][3], bool Up) const
+	{
+	rsk_asserta(m_ChainA != 0 && m_ChainB != 0 && !m_Path.empty());
+	auto Planes = [](const PDBChain &C, vector<float> &P)
+		{
+		const uint L = C.GetSeqLength();
+		P.resize(3 * (size_t)L);
+		for (uint i = 0; i < L; ++i)
+			{
+			P[i] = C.m_Xs[i];
+			P[(size_t)L + i] = C.m_Ys[i];
+			P[2 * (size_t)L + i] = C.m_Zs[i];
+			}
+		};
+	vector<float> PA, PB;
+	Planes(*m_ChainA, PA);
+	Planes(*m_ChainB, PB);
+	double uu[9], msd = 0;
+	Check(rsk_kabsch(PA.data(), m_ChainA->GetSeqLength(), PB.data(), m_ChainB->GetSeqLength(), m_LoA, m_LoB, m_Path.c_str(),
+	  RSK_SIZE(m_Path), Up ? 1 : 0, t, uu, &msd));
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+			u[i][j] = uu[3 * i + j];
+	return (float)msd;
+	}
+
 void DSSAligner::ToAln(FILE *f, bool Up) const { WriteBlock(f, Up, 0, false); }
 void DSSAligner::ToFasta2(FILE *f, bool Global, bool Up) const { WriteBlock(f, Up, 1, Global); }
 

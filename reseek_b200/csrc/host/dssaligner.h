@@ -101,6 +101,7 @@ public:
 	void ToAln(FILE *f, bool Up) const;                         // -aln (dssaligner.cpp:965-979)
 	void ToFasta2(FILE *f, bool Global, bool Up) const;         // -fasta2 [-unaligned] (dssaligner.cpp:981-1014)
 	float GetMuScore() const { return m_MuFwdMinusRevScore; }
+	float GetKabsch(double t[3], double u[3][3], bool Up) const;  // dssaligner.cpp:1371-1385
 	uint m_RowLen = 0;           // -rowlen (0: 80 columns)
 	const char *GetLabel(bool Top) const { return Top ? m_ChainA->m_Label.c_str() : m_ChainB->m_Label.c_str(); }
 	uint GetLo(bool Top) const { return Top ? m_LoA : m_LoB; }

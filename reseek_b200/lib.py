@@ -116,6 +116,8 @@ def load_library():
         fn.argtypes = [C.c_void_p]
     L.rsk_format_tsv.argtypes = [C.POINTER(HitView), C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
     L.rsk_path_to_cigar.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]
+    L.rsk_kabsch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int,
+                             C.c_void_p, C.c_void_p, C.c_void_p]
     L.rsk_format_aln.argtypes = [C.POINTER(HitView), C.c_int, C.c_uint32, C.c_char_p, C.c_size_t]
     L.rsk_format_aln.restype = C.c_longlong
     L.rsk_format_fasta2.argtypes = [C.POINTER(HitView), C.c_int, C.c_int, C.c_char_p, C.c_size_t]
@@ -198,6 +200,19 @@ def format_fasta2(hit, path, label_a, label_b, seq_a, seq_b, up=True, unaligned=
     """The record DSSAligner::ToFasta2 appends to the -fasta2 file for this hit."""
     return _format_block(load_library().rsk_format_fasta2, "rsk_format_fasta2", hit, path, label_a, label_b, seq_a, seq_b, up,
                          int(bool(unaligned)))
+
+
+def kabsch(xyz_a, xyz_b, lo_a, lo_b, path, up=True):
+    """Superposition of the aligned residue pairs (DSSAligner::GetKabsch): returns (msd, t[3], u[3][3]) with y ~ u x + t."""
+    xa = np.ascontiguousarray(xyz_a, np.float32)
+    xb = np.ascontiguousarray(xyz_b, np.float32)
+    t = np.zeros(3, np.float64)
+    u = np.zeros(9, np.float64)
+    msd = C.c_double()
+    p = path.encode() if isinstance(path, str) else path
+    _check(load_library().rsk_kabsch(xa.ctypes.data, xa.shape[1], xb.ctypes.data, xb.shape[1], int(lo_a), int(lo_b), p, len(p),
+                                     int(bool(up)), t.ctypes.data, u.ctypes.data, C.addressof(msd)))
+    return msd.value, t, u.reshape(3, 3)
 
 
 def path_to_cigar(path, up=True):

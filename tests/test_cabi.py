@@ -151,3 +151,36 @@ def test_aln_writer_rowlen_and_unaligned_flanks(built_lib):
     assert len(alns) >= 50
     assert aln_blocks("".join(alns)) == aln_blocks((GOLDEN / "golden_aln_db_verysensitive.aln").read_text())
     assert fasta2_records("".join(recs)) == fasta2_records((GOLDEN / "golden_aln_db_verysensitive.fa2").read_text())
+
+
+def test_kabsch_matches_reference_superpositions(built_lib):
+    """rsk_kabsch (Horn's quaternion method) against the reference's Kabsch() (tools/make_golden_kabsch.py): the same optimum,
+    so rotation, translation and residual agree to rounding.  Tolerances: |du| <= 1e-8, |dt| <= 1e-6 A, residual within
+    1e-6 * max(1, msd); the applied transform must also reproduce the residual it reports."""
+    import reseek_b200 as rb
+    from tests.golden_util import GOLDEN, load_chains
+    g = np.load(GOLDEN / "golden_kabsch.npz")
+    ch = load_chains()
+    assert len(g["a"]) >= 100
+    for k in range(len(g["a"])):
+        A, B = ch[int(g["a"][k])], ch[int(g["b"][k])]
+        path, up = str(g["paths"][k]), bool(g["up"][k])
+        msd, t, u = rb.kabsch(A.xyz, B.xyz, g["lo_a"][k], g["lo_b"][k], path, up=up)
+        assert np.abs(u - g["u"][k]).max() <= 1e-8, f"case {k} rotation"
+        assert np.abs(t - g["t"][k]).max() <= 1e-6, f"case {k} translation"
+        assert abs(msd - g["msd"][k]) <= 1e-6 * max(1.0, g["msd"][k]), f"case {k} residual"
+        assert abs(np.linalg.det(u) - 1) < 1e-12
+        i, j, X, Y = int(g["lo_a"][k]), int(g["lo_b"][k]), [], []
+        for c in path:
+            if c == "M":
+                X.append(A.xyz[:, i]); Y.append(B.xyz[:, j]); i += 1; j += 1
+            elif c == "D":
+                i += 1
+            else:
+                j += 1
+        X, Y = np.array(X, np.float64), np.array(Y, np.float64)
+        if not up:
+            X, Y = Y, X
+        assert abs(((X @ u.T + t - Y) ** 2).sum() / len(X) - msd) <= 1e-9 * max(1.0, msd)
+    with pytest.raises(rb.ReseekB200Error):
+        rb.kabsch(ch[0].xyz, ch[1].xyz, 0, 0, "DDII")  # no aligned pair
