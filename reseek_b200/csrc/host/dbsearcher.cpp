@@ -527,4 +527,53 @@ void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const ve
 	rsk_ctx_destroy(C);
 	}
 
+namespace {
+// both files as in-memory chains: DSS on host threads, self-reverse scores on the GPU with the given parameters
+struct LoadedFiles
+	{
+	ChainFeatures Q, T;
+	vector<ChainData> QD, TD;
+	LoadedFiles(const DSSParams &Params, const string &QueryFN, const string &DBFN)
+		{
+		rsk_params R;
+		Params.ToRsk(R, 10);
+		rsk_ctx *C = 0;
+		Check(rsk_ctx_create(0, &R, 0, &C));
+		ChainReader2 QR, TR;
+		QR.Open(QueryFN);
+		TR.Open(DBFN);
+		ProfileLoader::Load(Params, QR, 0, true, C, Params, 10, Q);
+		ProfileLoader::Load(Params, TR, 0, true, C, Params, 10, T);
+		rsk_ctx_destroy(C);
+		Fill(Q, QD);
+		Fill(T, TD);
+		}
+	~LoadedFiles() { Q.Free(); T.Free(); }
+	static void Fill(const ChainFeatures &F, vector<ChainData> &v)
+		{
+		v.resize(F.Chains.size());
+		for (size_t i = 0; i < v.size(); ++i)
+			{
+			v[i].Chain = F.Chains[i];
+			v[i].Profile = F.Profiles[i];
+			v[i].MuLetters = F.MuLetters[i];
+			v[i].SelfRevScore = F.SelfRevScores.empty() ? FLT_MAX : F.SelfRevScores[i];
+			}
+		}
+	};
+}  // namespace
+
+void MuPreFilter(const DSSParams &Params, const string &QueryCAFN, const string &DBBCAFN, const string &OutputFN)
+	{
+	LoadedFiles L(Params, QueryCAFN, DBBCAFN);
+	MuPreFilter(Params, L.QD, L.TD, OutputFN);
+	}
+
+void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const string &QueryCAFN, const string &DBBCAFN,
+  const string &HitsFN)
+	{
+	LoadedFiles L(Params, QueryCAFN, DBBCAFN);
+	PostMuFilter(Params, MuFilterTsvFN, L.QD, L.TD, HitsFN);
+	}
+
 }  // namespace reseek_b200

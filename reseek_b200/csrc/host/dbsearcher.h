@@ -118,4 +118,12 @@ void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const ve
   const vector<ChainData> &DB, const string &HitsFN, const char *Columns = 0, int Device = 0,
   const string &AlnFN = string());  // AlnFN: -aln (postmufilter.cpp:194, 244)
 
+// The same two stages with the chains named by file, PostMuFilter with the reference's own argument list
+// (search.cpp:14-18, postmufilter.cpp:211-216): the .bca files are read, run through DSS and given the self-reverse scores
+// of the sensitive preset (postmufilter.cpp:79-81, 166-167) before the in-memory versions above take over.  The reference's
+// MuPreFilter takes a SeqDB and a MuSeqSource of Mu-letter sequences made from the same two files (search.cpp:82-101).
+void MuPreFilter(const DSSParams &Params, const string &QueryCAFN, const string &DBBCAFN, const string &OutputFN);
+void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const string &QueryCAFN, const string &DBBCAFN,
+  const string &HitsFN);
+
 }  // namespace reseek_b200

@@ -298,7 +298,7 @@ void DSSAligner::ClearAlign()
 	m_MuFwdScore = m_MuRevScore = m_BestHSPScore = m_BestChainScore = 0;
 	m_MuFwdMinusRevScore = 0;
 	m_GlobalScore = -9999;
-	m_GlobalPath.clear();
+	m_GlobalPath.clear();   // (m_XDropScore is not reset, as in the reference: it keeps the last long-chain score)
 	m_Flags = 0;
 	}
 
@@ -338,6 +338,8 @@ void DSSAligner::FromHit(const rsk_hit &H, const char *PathPool, const ChainData
 		return;
 		}
 	m_AlnFwdScore = H.score;
+	if (H.flags & RSK_HIT_MKF)
+		m_XDropScore = H.score;   // dssaligner.cpp:1427-1429
 	if (H.path_len == 0)
 		return;
 	m_LoA = H.lo_a;
@@ -360,7 +362,7 @@ void DSSAligner::FromHit(const rsk_hit &H, const char *PathPool, const ChainData
 		}
 	}
 
-void DSSAligner::AlignOne(bool NoAccel)
+void DSSAligner::AlignOne(bool NoAccel, bool Bags)
 	{
 	rsk_asserta(m_Params != 0);
 	rsk_asserta(m_ChainA != 0 && m_ChainB != 0 && m_ProfileA != 0 && m_ProfileB != 0);
@@ -380,7 +382,8 @@ void DSSAligner::AlignOne(bool NoAccel)
 	m_Params->ToRsk(R, DBL_MAX);
 	if (NoAccel)
 		R.omega = 0;
-	if (NoAccel || m_MuKmersA == 0 || m_MuKmersB == 0 || m_MuKmersA->empty() || m_MuKmersB->empty())
+	// (AlignBags decides on the Mu letters and the lengths alone, chainbag.cpp:6-21)
+	if (NoAccel || (!Bags && (m_MuKmersA == 0 || m_MuKmersB == 0 || m_MuKmersA->empty() || m_MuKmersB->empty())))
 		R.mkfl = UINT_MAX;
 	Check(rsk_ctx_set_params(C, &R));
 
@@ -453,6 +456,22 @@ void DSSAligner::AlignQueryTarget_Global()
 	}
 
 void DSSAligner::AlignQueryTarget() { AlignOne(false); }
+
+bool DSSAligner::DoMKF_Bags(const ChainBag &BagA, const ChainBag &BagB) const
+	{
+	if (BagA.m_ptrMuLetters == 0 || BagB.m_ptrMuLetters == 0)
+		return false;
+	const uint LA = BagA.m_ptrChain->GetSeqLength(), LB = BagB.m_ptrChain->GetSeqLength();
+	return LA >= m_Params->m_MKFL || LB >= m_Params->m_MKFL;
+	}
+
+void DSSAligner::AlignBags(const ChainBag &BagA, const ChainBag &BagB)
+	{
+	rsk_asserta(BagA.m_ptrChain != 0 && BagB.m_ptrChain != 0);
+	SetQuery(*BagA.m_ptrChain, BagA.m_ptrProfile, BagA.m_ptrMuLetters, BagA.m_ptrMuLetters ? BagA.m_ptrMuKmers : 0, BagA.m_SelfRevScore);
+	SetTarget(*BagB.m_ptrChain, BagB.m_ptrProfile, BagB.m_ptrMuLetters, BagB.m_ptrMuLetters ? BagB.m_ptrMuKmers : 0, BagB.m_SelfRevScore);
+	AlignOne(false, true);
+	}
 void DSSAligner::Align_NoAccel() { AlignOne(true); }
 
 // the aligner's result members as the record + view the C-ABI writers take

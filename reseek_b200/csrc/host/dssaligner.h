@@ -17,6 +17,21 @@ namespace reseek_b200 {
 
 class DBSearcher;
 
+// chainbag.h:5-20: what PostMuFilter keeps per chain.  Only the borrowed chain data matter on the GPU path; the parasail
+// profiles and the k-mer hash table of the reference's bags are per-pair scratch that the library builds on the device.
+class ChainBag
+	{
+public:
+	const PDBChain *m_ptrChain = 0;
+	const vector<vector<byte> > *m_ptrProfile = 0;
+	const vector<byte> *m_ptrMuLetters = 0;
+	const vector<uint> *m_ptrMuKmers = 0;
+	const void *m_ptrProfPara = 0;               // unused here
+	const void *m_ptrProfParaRev = 0;            // unused here
+	const uint16_t *m_ptrKmerHashTableQ = 0;     // unused here
+	float m_SelfRevScore = FLT_MAX;
+	};
+
 class DSSAligner
 	{
 private:
@@ -54,6 +69,7 @@ public:
 	float m_SelfRevScoreA = FLT_MAX;
 	float m_SelfRevScoreB = FLT_MAX;
 	float m_AlnFwdScore = FLT_MAX;
+	float m_XDropScore = 0;      // score of the banded x-drop alignment of a long-chain pair (dssaligner.cpp:1427-1429)
 	float m_LDDT = 0;
 	float m_GlobalScore = FLT_MAX;   // -global (global.cpp:27-32)
 	string m_GlobalPath;
@@ -91,6 +107,8 @@ public:
 	void ClearAlign();           // dssaligner.cpp:906-927
 	void AlignQueryTarget();     // dssaligner.cpp:793-831
 	void AlignQueryTarget_Global();  // global.cpp:7-33
+	void AlignBags(const ChainBag &BagA, const ChainBag &BagB);  // chainbag.cpp:44-84 (PostMuFilter's per-candidate call)
+	bool DoMKF_Bags(const ChainBag &BagA, const ChainBag &BagB) const;  // chainbag.cpp:6-21
 	void Align_NoAccel();        // dssaligner.cpp:833-850: no Mu filter, no k-mer path
 	const DSSParams &GetParams() const { return *m_Params; }
 
@@ -122,7 +140,7 @@ public:
 
 private:
 	rsk_ctx *Ctx();
-	void AlignOne(bool NoAccel);
+	void AlignOne(bool NoAccel, bool Bags = false);
 	};
 
 // alignpair.cpp:7-25.  The reference re-runs DSS on the coordinate-reversed chain; feature extraction is not part of

@@ -6,6 +6,7 @@
 //   rsk_host_demo self  <mode> <set.rskc> <out.tsv> [columns]       DBSearcher::RunSelf           (-search X)
 //   rsk_host_demo query <mode> <stream.rskc> <db.rskc> <out.tsv>    DBSearcher::RunQuery          (-search Q -db DB)
 //   rsk_host_demo pair  <mode> <set.rskc> <i> <j> <out.tsv>         DSSAligner::AlignQueryTarget  (-alignpair)
+//   rsk_host_demo pairbags <mode> <set.rskc> <i> <j> <out.tsv>            DSSAligner::AlignBags (PostMuFilter's call)
 //   rsk_host_demo pairglobal <mode> <set.rskc> <i> <j> <out.tsv> [columns]  AlignQueryTarget_Global (-global)
 //   rsk_host_demo fastdb <q.rskc> <db.rskc> <cands.tsv> <out.tsv>   MuPreFilter + PostMuFilter    (-search Q -db DB -fast)
 // From the reference's own .bca files, through the DSS look-alike (no precomputed features):
@@ -288,6 +289,16 @@ int main(int argc, char **argv)
 		rsk_ctx_destroy(C);
 		return 0;
 		}
+	if (Cmd == "searchfastfiles" && argc >= 6)   // search.cpp:76-111 through the file-name signatures
+		{
+		DSSParams Params;
+		Params.SetMode(AM_Fast);
+		DSSParams Params2;
+		Params2.SetDSSParams(DM_AlwaysSensitive);
+		MuPreFilter(Params, string(argv[2]), string(argv[3]), string(argv[4]));
+		PostMuFilter(Params2, string(argv[4]), string(argv[2]), string(argv[3]), string(argv[5]));
+		return 0;
+		}
 	if (Cmd == "self" && argc >= 5)
 		{
 		DSSParams Params;
@@ -343,6 +354,28 @@ int main(int argc, char **argv)
 		DA.AlignQueryTarget();
 		FILE *f = fopen(argv[6], "w");
 		if (!DA.m_Path.empty())   // alignpair.cpp:110-117
+			DA.ToTsv(f, true);
+		fclose(f);
+		return 0;
+		}
+	if (Cmd == "pairbags" && argc >= 7)   // postmufilter.cpp:185-195: one candidate through DSSAligner::AlignBags
+		{
+		DSSParams Params;
+		Params.SetMode(ParseMode(argv[2]));
+		LoadedSet S;
+		Load(argv[3], S);
+		const uint i = (uint)atoi(argv[4]), j = (uint)atoi(argv[5]);
+		rsk_asserta(i < S.Chains.size() && j < S.Chains.size());
+		ChainBag BagA, BagB;
+		BagA.m_ptrChain = &S.Chains[i]; BagA.m_ptrProfile = &S.Profiles[i]; BagA.m_ptrMuLetters = S.Data[i].MuLetters;
+		BagA.m_ptrMuKmers = S.Data[i].MuLetters ? &S.Kmers[i] : 0; BagA.m_SelfRevScore = S.SelfRevs[i];
+		BagB.m_ptrChain = &S.Chains[j]; BagB.m_ptrProfile = &S.Profiles[j]; BagB.m_ptrMuLetters = S.Data[j].MuLetters;
+		BagB.m_ptrMuKmers = S.Data[j].MuLetters ? &S.Kmers[j] : 0; BagB.m_SelfRevScore = S.SelfRevs[j];
+		DSSAligner DA;
+		DA.SetParams(Params);
+		DA.AlignBags(BagA, BagB);
+		FILE *f = fopen(argv[6], "w");
+		if (!DA.m_Path.empty())
 			DA.ToTsv(f, true);
 		fclose(f);
 		return 0;

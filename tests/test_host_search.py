@@ -154,3 +154,16 @@ def test_selfsearch_global_matches_reference_binary(built_lib, tmp_path):
     got = sorted((tmp_path / "out.tsv").read_text().splitlines())
     want = _golden("golden_global_self.tsv")
     assert len(want) == 196 and got == want
+
+
+@pytest.mark.gpu
+def test_file_name_signatures_of_the_fast_db_stages(built_lib, tmp_path):
+    """MuPreFilter / PostMuFilter called with file names (PostMuFilter's reference argument list, search.cpp:14-18) give
+    the candidate TSV and the hit lines of the in-memory versions."""
+    g6, g21 = golden_bca(tmp_path)
+    a = _run("searchfast", g6, g21, tmp_path / "c1.tsv", tmp_path / "o1.tsv")
+    b = _run("searchfastfiles", g6, g21, tmp_path / "c2.tsv", tmp_path / "o2.tsv")
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    assert (tmp_path / "c1.tsv").read_text() == (tmp_path / "c2.tsv").read_text()
+    lines = (tmp_path / "o1.tsv").read_text()
+    assert len(lines.splitlines()) >= 6 and lines == (tmp_path / "o2.tsv").read_text()

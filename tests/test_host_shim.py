@@ -40,6 +40,8 @@ def test_host_library_exports_reference_surface(built_lib):
     for name in ("reseek_b200::DSSAligner::SetParams(", "reseek_b200::DSSAligner::SetQuery(", "reseek_b200::DSSAligner::SetTarget(",
                  "reseek_b200::DSSAligner::UnsetQuery(", "reseek_b200::DSSAligner::AlignQueryTarget(", "reseek_b200::DSSAligner::Align_NoAccel(",
                  "reseek_b200::DSSAligner::ToTsv(", "reseek_b200::DSSAligner::DoMKF(", "reseek_b200::DSSAligner::ClearAlign(",
+                 "reseek_b200::DSSAligner::ToAln(", "reseek_b200::DSSAligner::ToFasta2(", "reseek_b200::DSSAligner::GetKabsch(",
+                 "reseek_b200::DSSAligner::AlignBags(", "reseek_b200::DSSAligner::AlignQueryTarget_Global(",
                  "reseek_b200::DSSAligner::Stats(", "reseek_b200::DBSearcher::Setup(", "reseek_b200::DBSearcher::RunSelf(",
                  "reseek_b200::DBSearcher::RunQuery(", "reseek_b200::DBSearcher::BaseOnAln(", "reseek_b200::DBSearcher::Reject(",
                  "reseek_b200::DBSearcher::AddChain(", "reseek_b200::MuPreFilter(", "reseek_b200::PostMuFilter(",
@@ -155,3 +157,16 @@ def test_alignquerytarget_global_batch_of_one(built_lib, tmp_path, port):
         orc, opath = port(3).align_pair_global(oc[i], oc[j])
         want = "\t".join([ld[i], ld[j], "%.1f" % orc.score, "0", rb.path_to_cigar(opath, up=True)])
         assert (tmp_path / "g.tsv").read_text().splitlines() == [want]
+
+
+@pytest.mark.gpu
+def test_alignbags_equals_alignquerytarget(built_lib, tmp_path):
+    """DSSAligner::AlignBags (chainbag.cpp:44-84, what PostMuFilter calls per candidate) gives the record AlignQueryTarget
+    gives for the same two chains."""
+    _sets(tmp_path)
+    for mode in ("sensitive", "verysensitive"):
+        for i, j in ((0, 1), (3, 3), (5, 2), (2, 7)):
+            a = _run("pair", mode, tmp_path / "db.rskc", i, j, tmp_path / "p.tsv")
+            b = _run("pairbags", mode, tmp_path / "db.rskc", i, j, tmp_path / "b.tsv")
+            assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+            assert (tmp_path / "p.tsv").read_text() == (tmp_path / "b.tsv").read_text()
