@@ -174,6 +174,8 @@ void DBSearcher::RunSelfGlobal()
 		for (uint64_t k = 0; k < n; ++k)
 			{
 			const rsk_hit &H = Hits[k];
+			if (DSSAligner::m_NoSelf && H.a == H.b)
+				continue;
 			DA.FromHit(H, Pool, GetDBChainData(H.a), GetDBChainData(H.b));
 			if (DA.m_GlobalPath.empty())
 				continue;
@@ -235,6 +237,8 @@ void DBSearcher::RunSelf()
 	for (uint64_t k = 0; k < N; ++k)
 		{
 		const rsk_hit &H = Hits[k];
+		if (DSSAligner::m_NoSelf && H.a == H.b)
+			continue;   // runself.cpp:39-40
 		DA.FromHit(H, Pool, GetDBChainData(H.a), GetDBChainData(H.b));
 		if (DA.m_Path.empty())
 			continue;

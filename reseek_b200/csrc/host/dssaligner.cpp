@@ -170,6 +170,7 @@ rsk_chainset *UploadChains(rsk_ctx *Ctx, const vector<ChainData> &Chains, bool W
 
 // ---- DSSAligner ----
 std::mutex DSSAligner::m_OutputLock;
+bool DSSAligner::m_NoSelf = false;
 std::atomic<uint> DSSAligner::m_AlnCount{0};
 std::atomic<uint> DSSAligner::m_SWCount{0};
 std::atomic<uint> DSSAligner::m_MuFilterDiscardCount{0};
@@ -503,6 +504,8 @@ void DSSAligner::GetHitView(rsk_hit &H, rsk_hit_view &V) const
 void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
 	{
 	if (f == 0)
+		return;
+	if (m_NoSelf && m_ChainA->m_Label == m_ChainB->m_Label)
 		return;
 	rsk_hit H;
 	rsk_hit_view V;

@@ -83,6 +83,7 @@ public:
 
 public:
 	static std::mutex m_OutputLock;
+	static bool m_NoSelf;        // opt(noself): ToTsv skips pairs of equally labelled chains (dssaligner.cpp:1020-1021)
 	static std::atomic<uint> m_AlnCount;
 	static std::atomic<uint> m_SWCount;
 	static std::atomic<uint> m_MuFilterDiscardCount;

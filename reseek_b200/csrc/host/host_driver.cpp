@@ -194,11 +194,118 @@ static void CloseAlnOutputs(DBSearcher &DBS)
 	if (DBS.m_fFasta2) fclose(DBS.m_fFasta2);
 	}
 
+// The search command with the reference's own command line (cmd_search, search.cpp:20-111; options from myopts.h):
+//   rsk_host_demo -search Q.bca [-db DB.bca] -fast|-sensitive|-verysensitive [-output hits.tsv] [-columns a+b+c]
+//                 [-aln FILE] [-fasta2 FILE] [-unaligned] [-rowlen N] [-global] [-evalue E] [-noself] [-threads N]
+// .bca inputs only; -threads is accepted and ignored (one GPU context does the aligning).
+static int ReseekSearch(int argc, char **argv)
+	{
+	string QFN, DBFN, OutFN, Columns, AlnFN, Fasta2FN;
+	bool Unaligned = false, Global = false, NoSelf = false, HaveEvalue = false;
+	uint RowLen = 0;
+	double Evalue = 10;
+	int Mode = -1;
+	for (int i = 1; i < argc; ++i)
+		{
+		const string a = argv[i];
+		auto Value = [&]() -> const char *
+			{
+			if (i + 1 >= argc)
+				Die("Missing value for %s", a.c_str());
+			return argv[++i];
+			};
+		if (a == "-search") QFN = Value();
+		else if (a == "-db") DBFN = Value();
+		else if (a == "-output") OutFN = Value();
+		else if (a == "-columns") Columns = Value();
+		else if (a == "-aln") AlnFN = Value();
+		else if (a == "-fasta2") Fasta2FN = Value();
+		else if (a == "-rowlen") RowLen = (uint)atoi(Value());
+		else if (a == "-evalue") { Evalue = atof(Value()); HaveEvalue = true; }
+		else if (a == "-threads") Value();
+		else if (a == "-unaligned") Unaligned = true;
+		else if (a == "-global") Global = true;
+		else if (a == "-noself") NoSelf = true;
+		else if (a == "-fast") Mode = AM_Fast;
+		else if (a == "-sensitive") Mode = AM_Sensitive;
+		else if (a == "-verysensitive") Mode = AM_VerySensitive;
+		else
+			Die("Unknown option %s", a.c_str());
+		}
+	if (Mode < 0)
+		Die("Must set -fast, -sensitive or -verysensitive");  // dssparams.cpp:90
+	DSSAligner::m_NoSelf = NoSelf;
+	DSSParams Params;
+	Params.SetMode((ALGO_MODE)Mode);
+	if (!DBFN.empty() && Mode == AM_Fast)
+		{
+		// search.cpp:76-111: prefilter, then the post-filter under the sensitive preset
+		if (DBFN.size() < 4 || DBFN.compare(DBFN.size() - 4, 4, ".bca") != 0)
+			Die(".bca format required for -db");
+		const string TmpFN = OutFN.empty() ? string("/tmp/rsk_prefilter.tsv") : OutFN + ".prefilter.tmp";
+		DSSParams Params2;
+		Params2.SetDSSParams(DM_AlwaysSensitive);
+		MuPreFilter(Params, QFN, DBFN, TmpFN);
+		{
+		// the writers' options reach PostMuFilter through the in-memory signature
+		rsk_params R;
+		Params2.ToRsk(R, 10);
+		rsk_ctx *C = 0;
+		if (rsk_ctx_create(0, &R, 0, &C) != RSK_OK)
+			Die("reseek_b200: %s", rsk_last_error());
+		ChainReader2 QR, TR;
+		QR.Open(QFN);
+		TR.Open(DBFN);
+		ChainFeatures Q, T;
+		ProfileLoader::Load(Params2, QR, 0, true, C, Params2, 10, Q);
+		ProfileLoader::Load(Params2, TR, 0, true, C, Params2, 10, T);
+		const vector<ChainData> QD = ToChainData(Q), TD = ToChainData(T);
+		PostMuFilter(Params2, TmpFN, QD, TD, OutFN, Columns.empty() ? 0 : Columns.c_str(), 0, AlnFN);
+		Q.Free();
+		T.Free();
+		rsk_ctx_destroy(C);
+		}
+		remove(TmpFN.c_str());
+		return 0;
+		}
+	CountingSearcher DBS;
+	DBS.m_Params = &Params;
+	if (HaveEvalue)
+		DBS.m_MaxEvalue = (float)Evalue;   // dbsearcher.cpp:75-76
+	DBS.LoadDB(QFN);               // the -search file is the in-memory side (search.cpp:53)
+	DBS.Setup();
+	if (HaveEvalue)
+		DBS.m_MaxEvalue = (float)Evalue;
+	if (!OutFN.empty() && (DBS.m_fTsv = fopen(OutFN.c_str(), "w")) == 0) Die("Cannot create %s", OutFN.c_str());
+	if (!AlnFN.empty() && (DBS.m_fAln = fopen(AlnFN.c_str(), "w")) == 0) Die("Cannot create %s", AlnFN.c_str());
+	if (!Fasta2FN.empty() && (DBS.m_fFasta2 = fopen(Fasta2FN.c_str(), "w")) == 0) Die("Cannot create %s", Fasta2FN.c_str());
+	if (!Columns.empty())
+		DBS.m_Columns = Columns.c_str();
+	DBS.m_Unaligned = Unaligned;
+	DBS.m_RowLen = RowLen;
+	DBS.m_Global = Global;
+	if (const char *e = getenv("RSK_BLOCK_CHAINS"))
+		DBS.m_BlockChains = (uint)atoi(e);
+	if (DBFN.empty())
+		DBS.RunSelf();             // SelfSearch, search.cpp:20-40
+	else
+		{
+		ChainReader2 CR;
+		CR.Open(DBFN);             // Search_NoMuFilter, search.cpp:42-63
+		DBS.RunQuery(CR);
+		}
+	if (DBS.m_fTsv) fclose(DBS.m_fTsv);
+	CloseAlnOutputs(DBS);
+	return 0;
+	}
+
 int main(int argc, char **argv)
 	{
 	if (argc < 2)
 		Die("usage: rsk_host_demo self|query|pair|fastdb|features|selfsearch|search|searchfast ...");
 	const string Cmd = argv[1];
+	if (Cmd == "-search")
+		return ReseekSearch(argc, argv);
 	if (Cmd == "features" && argc >= 4)
 		{
 		// DSS stage only: no device is touched (no self-reverse scores)

@@ -167,3 +167,44 @@ def test_file_name_signatures_of_the_fast_db_stages(built_lib, tmp_path):
     assert (tmp_path / "c1.tsv").read_text() == (tmp_path / "c2.tsv").read_text()
     lines = (tmp_path / "o1.tsv").read_text()
     assert len(lines.splitlines()) >= 6 and lines == (tmp_path / "o2.tsv").read_text()
+
+
+def _cli(*args):
+    return subprocess.run([str(DEMO), *map(str, args)], capture_output=True, text=True, timeout=900,
+                          env=dict(os.environ, RSK_BLOCK_CHAINS="8"))
+
+
+@pytest.mark.gpu
+def test_reseek_command_line_is_a_drop_in(built_lib, tmp_path):
+    """The reference's own command lines (`reseek -search ...`, search.cpp:20-111) given to rsk_host_demo: self search,
+    streamed -db search, -fast -db, -noself/-evalue, -global, -aln/-fasta2 — outputs equal the reference binary's."""
+    from tests.golden_util import NOSELF_COLUMNS
+    g6, g21 = golden_bca(tmp_path)
+    g4, gs = golden_bca_short(tmp_path)
+    out = tmp_path / "o.tsv"
+
+    def lines():
+        return sorted(out.read_text().splitlines())
+    r = _cli("-search", g21, "-sensitive", "-output", out, "-columns", SEARCH_COLUMNS, "-threads", 1)
+    assert r.returncode == 0, r.stderr
+    assert lines() == _golden("golden_search_self_sensitive.tsv")
+    r = _cli("-search", g6, "-db", g21, "-verysensitive", "-output", out, "-columns", SEARCH_COLUMNS)
+    assert r.returncode == 0, r.stderr
+    assert lines() == _golden("golden_search_db_verysensitive.tsv")
+    r = _cli("-search", g6, "-db", g21, "-fast", "-output", out, "-columns", SEARCH_COLUMNS)
+    assert r.returncode == 0, r.stderr
+    assert lines() == _golden("golden_search_fastdb.tsv")
+    r = _cli("-search", g21, "-sensitive", "-noself", "-evalue", 1, "-output", out, "-columns", NOSELF_COLUMNS)
+    assert r.returncode == 0, r.stderr
+    want = _golden("golden_search_self_noself_evalue.tsv")
+    assert len(want) >= 2 and lines() == want
+    r = _cli("-search", gs, "-global", "-verysensitive", "-output", out, "-columns", GLOBAL_COLUMNS)
+    assert r.returncode == 0, r.stderr
+    assert lines() == _golden("golden_global_self.tsv")
+    r = _cli("-search", g4, "-db", gs, "-verysensitive", "-output", out, "-aln", tmp_path / "o.aln", "-fasta2", tmp_path / "o.fa2",
+             "-unaligned", "-rowlen", 60)
+    assert r.returncode == 0, r.stderr
+    assert aln_blocks((tmp_path / "o.aln").read_text()) == aln_blocks((GOLDEN / "golden_aln_db_verysensitive.aln").read_text())
+    assert fasta2_records((tmp_path / "o.fa2").read_text()) == fasta2_records((GOLDEN / "golden_aln_db_verysensitive.fa2").read_text())
+    r = _cli("-search", g21, "-output", out)
+    assert r.returncode == 1 and "Must set -fast, -sensitive or -verysensitive" in r.stderr

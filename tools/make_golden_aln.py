@@ -4,6 +4,7 @@
     -search gshort.bca -sensitive -columns <ALN_COLUMNS> -aln -fasta2        -> golden_aln_self_sensitive.{tsv,aln,fa2}
     -search g4.bca -db gshort.bca -verysensitive -aln -fasta2 -unaligned -rowlen 60
                                                                              -> golden_aln_db_verysensitive.{aln,fa2}
+    -search g21.bca -sensitive -noself -evalue 1                             -> golden_search_self_noself_evalue.tsv
 
 gshort.bca holds the golden chains shorter than 500 residues, g4.bca four of them (tests/golden_util.golden_bca_short).  Hits are put into a
 canonical order (sorted lines / blocks / records) because the reference's order depends on thread timing.
@@ -15,7 +16,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from tests.golden_util import ALN_COLUMNS, ALN_RULE, GOLDEN, aln_blocks, fasta2_records, golden_bca_short  # noqa: E402
+from tests.golden_util import ALN_COLUMNS, NOSELF_COLUMNS, ALN_RULE, GOLDEN, aln_blocks, fasta2_records, golden_bca, golden_bca_short  # noqa: E402
 
 REF = ROOT / "oracle" / "_ref" / "reseek_ref"
 
@@ -51,6 +52,11 @@ def main():
         (GOLDEN / "golden_aln_db_verysensitive.aln").write_text(canon_aln(tmp / "o2.aln"))
         (GOLDEN / "golden_aln_db_verysensitive.fa2").write_text(canon_fa2(tmp / "o2.fa2"))
         print("db verysensitive", len((tmp / "o2.tsv").read_text().splitlines()))
+        # -noself and -evalue (dssaligner.cpp:1020-1021, runself.cpp:39-40, dbsearcher.cpp:75-76)
+        run(["-search", golden_bca(tmp)[1], "-sensitive", "-noself", "-evalue", "1", "-output", tmp / "o3.tsv", "-columns", NOSELF_COLUMNS])
+        lines = sorted((tmp / "o3.tsv").read_text().splitlines())
+        (GOLDEN / "golden_search_self_noself_evalue.tsv").write_text("\n".join(lines) + "\n")
+        print("self -noself -evalue 1", len(lines))
 
 
 if __name__ == "__main__":
