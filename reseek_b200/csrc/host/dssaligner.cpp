@@ -290,8 +290,8 @@ void DSSAligner::ClearAlign()
 	m_PvalueB = FLT_MAX;
 	m_EvalueA = FLT_MAX;
 	m_EvalueB = FLT_MAX;
-	m_QualityA = FLT_MAX;
-	m_QualityB = FLT_MAX;
+	// (m_QualityA/B are not cleared, as in the reference: dssaligner.cpp:906-927 leaves them, and -alignpair -global prints
+	// the quality of the last local alignment, prettyaln.cpp:93)
 	m_NewTestStatisticA = -FLT_MAX;
 	m_NewTestStatisticB = -FLT_MAX;
 	m_AlnFwdScore = 0;

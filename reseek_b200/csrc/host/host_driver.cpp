@@ -299,6 +299,131 @@ static int ReseekSearch(int argc, char **argv)
 	return 0;
 	}
 
+// cmd_alignpair (alignpair.cpp:164-228) with the reference's command line:
+//   rsk_host_demo -alignpair Q.bca -input2 T.bca [-aln FILE] [-global] [-output FILE] [-output2 FILE]
+// Sensitive preset with the Mu filter off (alignpair.cpp:177-185); every chain of Q against every chain of T, the best
+// scoring pair (first maximum, Q-major) is reported.  All pairs are one GPU batch here.  -output / -output2 carry the
+// query's ATOM lines after the superposition; .bca files have no ATOM lines, so those files come out empty, as they do
+// from the reference for .bca inputs.
+static int ReseekAlignPair(int argc, char **argv)
+	{
+	string QFN, TFN, AlnFN, OutFN, Out2FN;
+	bool Global = false;
+	for (int i = 1; i < argc; ++i)
+		{
+		const string a = argv[i];
+		auto Value = [&]() -> const char *
+			{
+			if (i + 1 >= argc)
+				Die("Missing value for %s", a.c_str());
+			return argv[++i];
+			};
+		if (a == "-alignpair") QFN = Value();
+		else if (a == "-input2") TFN = Value();
+		else if (a == "-aln") AlnFN = Value();
+		else if (a == "-output") OutFN = Value();
+		else if (a == "-output2") Out2FN = Value();
+		else if (a == "-threads") Value();
+		else if (a == "-global") Global = true;
+		else if (a == "-fast" || a == "-sensitive" || a == "-verysensitive") {}  // overridden (alignpair.cpp:177-181)
+		else
+			Die("Unknown option %s", a.c_str());
+		}
+	if (TFN.empty())
+		Die("Must specify -input2");
+	DSSParams Params;
+	Params.SetDSSParams(DM_AlwaysSensitive);
+	Params.m_UsePara = false;
+	Params.m_Omega = 0;
+	rsk_params R;
+	Params.ToRsk(R, DBL_MAX);
+	rsk_ctx *C = 0;
+	if (rsk_ctx_create(0, &R, 0, &C) != RSK_OK)
+		Die("reseek_b200: %s", rsk_last_error());
+	ChainReader2 QR, TR;
+	QR.Open(QFN);
+	TR.Open(TFN);
+	ChainFeatures Q, T;
+	ProfileLoader::Load(Params, QR, 0, false, C, Params, DBL_MAX, Q);
+	ProfileLoader::Load(Params, TR, 0, false, C, Params, DBL_MAX, T);
+	if (Q.Chains.empty()) Die("No chains found in %s", QFN.c_str());
+	if (T.Chains.empty()) Die("No chains found in %s", TFN.c_str());
+	const vector<ChainData> QD = ToChainData(Q), TD = ToChainData(T);
+	rsk_chainset *QS = UploadChains(C, QD, false), *TS = UploadChains(C, TD, false);
+	rsk_results *Res = 0;
+	int rc;
+	if (Global)
+		{
+		vector<uint32_t> ia, ib;
+		for (uint32_t q = 0; q < QD.size(); ++q)
+			for (uint32_t t = 0; t < TD.size(); ++t)
+				{
+				ia.push_back(q);
+				ib.push_back(t);
+				}
+		rc = rsk_align_global(C, QS, TS, ia.size(), ia.data(), ib.data(), &Res);
+		}
+	else
+		{
+		rsk_search_opts O;
+		memset(&O, 0, sizeof(O));
+		O.keep = RSK_KEEP_ALL;
+		O.want_paths = 1;
+		rc = rsk_search_cross(C, QS, TS, &O, &Res);
+		}
+	if (rc != RSK_OK)
+		Die("reseek_b200: %s", rsk_last_error());
+	const uint64_t N = rsk_results_count(Res);
+	const rsk_hit *Hits = rsk_results_hits(Res);
+	float BestScore = -9999;
+	uint64_t Best = 0;
+	rsk_asserta(N == (uint64_t)QD.size() * TD.size());
+	for (uint64_t k = 0; k < N; ++k)   // alignpair.cpp:203-218: Q-major order, first strict maximum
+		{
+		rsk_asserta(Hits[k].a == k / TD.size() && Hits[k].b == k % TD.size());
+		if (Hits[k].score > BestScore)
+			{
+			BestScore = Hits[k].score;
+			Best = k;
+			}
+		}
+	if (BestScore == 0)
+		Die("No alignment found");
+	DSSAligner DA;
+	DA.SetParams(Params);
+	DA.UseContext(C);
+	// AlignPair1 (alignpair.cpp:77-105) aligns each chain against its reversed self right before the pair; on the -global
+	// path that is where the AQ of the printed block comes from (ClearAlign does not reset the quality)
+	const uint bq = Hits[Best].a, bt = Hits[Best].b;
+	GetSelfRevScore(DA, *Q.Chains[bq], *Q.Profiles[bq], Q.RevProfiles[bq], 0, 0);
+	GetSelfRevScore(DA, *T.Chains[bt], *T.Profiles[bt], T.RevProfiles[bt], 0, 0);
+	DA.FromHit(Hits[Best], rsk_results_paths(Res), QD[bq], TD[bt]);
+	if (!AlnFN.empty())
+		{
+		FILE *f = fopen(AlnFN.c_str(), "w");
+		if (f == 0) Die("Cannot create %s", AlnFN.c_str());
+		DA.ToAln(f, true);
+		fclose(f);
+		}
+	double t3[3], u[3][3];
+	DA.GetKabsch(t3, u, true);     // alignpair.cpp:129-131
+	fprintf(stderr, "%s %s score %.4g, superposition t = %.3f %.3f %.3f\n", DA.GetLabel(true), DA.GetLabel(false), BestScore, t3[0], t3[1], t3[2]);
+	for (const string *FN : {&OutFN, &Out2FN})
+		if (!FN->empty())
+			{
+			FILE *f = fopen(FN->c_str(), "w");  // no ATOM lines in a .bca file
+			if (f == 0) Die("Cannot create %s", FN->c_str());
+			fclose(f);
+			}
+	rsk_results_free(Res);
+	rsk_chainset_free(QS);
+	rsk_chainset_free(TS);
+	Q.Free();
+	T.Free();
+	rsk_ctx_destroy(C);
+	return 0;
+	}
+
 int main(int argc, char **argv)
 	{
 	if (argc < 2)
@@ -306,6 +431,8 @@ int main(int argc, char **argv)
 	const string Cmd = argv[1];
 	if (Cmd == "-search")
 		return ReseekSearch(argc, argv);
+	if (Cmd == "-alignpair")
+		return ReseekAlignPair(argc, argv);
 	if (Cmd == "features" && argc >= 4)
 		{
 		// DSS stage only: no device is touched (no self-reverse scores)

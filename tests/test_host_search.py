@@ -208,3 +208,17 @@ def test_reseek_command_line_is_a_drop_in(built_lib, tmp_path):
     assert fasta2_records((tmp_path / "o.fa2").read_text()) == fasta2_records((GOLDEN / "golden_aln_db_verysensitive.fa2").read_text())
     r = _cli("-search", g21, "-output", out)
     assert r.returncode == 1 and "Must set -fast, -sensitive or -verysensitive" in r.stderr
+
+
+@pytest.mark.gpu
+def test_alignpair_command_line_matches_reference_binary(built_lib, tmp_path):
+    """`reseek -alignpair Q.bca -input2 T.bca -aln F [-global]` (cmd_alignpair, alignpair.cpp:164-228): the best pair of two
+    chain files and its alignment block, byte for byte (tools/make_golden_aln.py)."""
+    from tests.golden_util import golden_bca_disjoint
+    q4, gsx = golden_bca_disjoint(tmp_path)
+    for name, extra in (("golden_alignpair.aln", []), ("golden_alignpair_global.aln", ["-global"])):
+        r = _cli("-alignpair", q4, "-input2", gsx, "-aln", tmp_path / "ap.aln", *extra)
+        assert r.returncode == 0, r.stderr
+        assert (tmp_path / "ap.aln").read_text() == (GOLDEN / name).read_text(), name
+    r = _cli("-alignpair", q4)
+    assert r.returncode == 1 and "Must specify -input2" in r.stderr

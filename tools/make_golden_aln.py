@@ -4,6 +4,7 @@
     -search gshort.bca -sensitive -columns <ALN_COLUMNS> -aln -fasta2        -> golden_aln_self_sensitive.{tsv,aln,fa2}
     -search g4.bca -db gshort.bca -verysensitive -aln -fasta2 -unaligned -rowlen 60
                                                                              -> golden_aln_db_verysensitive.{aln,fa2}
+    -alignpair g4.bca -input2 gsx.bca [-global] -aln                          -> golden_alignpair[_global].aln
     -search g21.bca -sensitive -noself -evalue 1                             -> golden_search_self_noself_evalue.tsv
 
 gshort.bca holds the golden chains shorter than 500 residues, g4.bca four of them (tests/golden_util.golden_bca_short).  Hits are put into a
@@ -16,7 +17,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from tests.golden_util import ALN_COLUMNS, NOSELF_COLUMNS, ALN_RULE, GOLDEN, aln_blocks, fasta2_records, golden_bca, golden_bca_short  # noqa: E402
+from tests.golden_util import ALN_COLUMNS, NOSELF_COLUMNS, ALN_RULE, GOLDEN, aln_blocks, fasta2_records, golden_bca, golden_bca_disjoint, golden_bca_short  # noqa: E402
 
 REF = ROOT / "oracle" / "_ref" / "reseek_ref"
 
@@ -52,6 +53,15 @@ def main():
         (GOLDEN / "golden_aln_db_verysensitive.aln").write_text(canon_aln(tmp / "o2.aln"))
         (GOLDEN / "golden_aln_db_verysensitive.fa2").write_text(canon_fa2(tmp / "o2.fa2"))
         print("db verysensitive", len((tmp / "o2.tsv").read_text().splitlines()))
+        # -alignpair (cmd_alignpair, alignpair.cpp:164-228) on two files without a common chain, local and -global
+        q4, gsx = golden_bca_disjoint(tmp)
+        for name, extra in (("golden_alignpair.aln", []), ("golden_alignpair_global.aln", ["-global"])):
+            r = subprocess.run([str(REF), "-alignpair", str(q4), "-input2", str(gsx), "-aln", str(tmp / "ap.aln")] + extra,
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise SystemExit(r.stdout[-2000:] + r.stderr[-2000:])
+            (GOLDEN / name).write_text((tmp / "ap.aln").read_text())
+            print(name, len((tmp / "ap.aln").read_text().splitlines()), "lines")
         # -noself and -evalue (dssaligner.cpp:1020-1021, runself.cpp:39-40, dbsearcher.cpp:75-76)
         run(["-search", golden_bca(tmp)[1], "-sensitive", "-noself", "-evalue", "1", "-output", tmp / "o3.tsv", "-columns", NOSELF_COLUMNS])
         lines = sorted((tmp / "o3.tsv").read_text().splitlines())
