@@ -184,3 +184,28 @@ def test_kabsch_matches_reference_superpositions(built_lib):
         assert abs(((X @ u.T + t - Y) ** 2).sum() / len(X) - msd) <= 1e-9 * max(1.0, msd)
     with pytest.raises(rb.ReseekB200Error):
         rb.kabsch(ch[0].xyz, ch[1].xyz, 0, 0, "DDII")  # no aligned pair
+
+
+def test_global_record_columns_match_reference_binary(built_lib):
+    """A record of the -global path through rsk_format_tsv (gscore; dpscore stays 0; hi unset, so qhi/thi print 0; E-value
+    unset prints 99.0) against the reference binary's `-search gshort.bca -global -verysensitive` output
+    (tools/make_golden_global.py); the alignments come from the CPU oracle here, from the GPU in tests/test_host_search.py."""
+    import reseek_b200 as rb
+    from oracle.pyoracle import Port
+    from tests.golden_util import GLOBAL_COLUMNS, GOLDEN, load_chains
+    chains = [c for c in load_chains() if c.L < 500]
+    port = Port(mode=3)
+    FLT_MAX = np.finfo(np.float32).max
+    lines = []
+    for i in range(len(chains)):
+        for j in range(i, len(chains)):
+            r, path = port.align_pair_global(chains[i], chains[j])
+            h = np.zeros(1, rb.HIT_DTYPE)[0]
+            h["score"], h["lo_a"], h["lo_b"], h["path_len"], h["flags"] = r.score, 0, 0, len(path), rb.HIT_GLOBAL
+            h["hi_a"] = h["hi_b"] = h["ids"] = h["gaps"] = 0xFFFFFFFF
+            h["evalue"] = h["pvalue"] = h["qual"] = FLT_MAX
+            h["ts"] = -FLT_MAX
+            A, B = chains[i], chains[j]
+            for up in ([True] if i == j else [True, False]):
+                lines.append(rb.format_tsv(h, path, A.label, B.label, A.L, B.L, up=up, columns=GLOBAL_COLUMNS, seq_a=A.seq, seq_b=B.seq))
+    assert sorted(lines) == (GOLDEN / "golden_global_self.tsv").read_text().splitlines()
