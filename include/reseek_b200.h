@@ -271,8 +271,8 @@ int rsk_path_to_cigar(const char *path, uint32_t path_len, int up, char *out, si
 int rsk_format_tsv(const rsk_hit_view *v, int up, const char *columns, char *out, size_t cap);
 /* The block DSSAligner::ToAln appends to the -aln file for one hit (dssaligner.cpp:965-979 -> PrettyAln prettyaln.cpp:26-99,
  * WriteLocalAln writelocalaln.cpp:65-100); rowlen = 0 means the default of 80 columns (-rowlen).  Needs path, labels and both
- * sequences.  Returns the length written (excluding the NUL) or, when cap is too small, the length needed as a negative
- * number - 1 (as rsk_prefilter_to_tsv); RSK_ERR_ARG (-1) cannot be confused with it because a block is never empty. */
+ * sequences.  Returns the length written (excluding the NUL); when cap is too small, -(bytes needed) - 1, which is
+ * never above -17; a negative rsk_status (-1 .. -4) on bad arguments. */
 long long rsk_format_aln(const rsk_hit_view *v, int up, uint32_t rowlen, char *out, size_t cap);
 /* The record DSSAligner::ToFasta2 appends to the -fasta2 file (dssaligner.cpp:981-1014): target row first, then the query
  * row, 80 residues per line, one empty line after; global != 0 is -unaligned (lower-case flanks, '.' padding).  Same return

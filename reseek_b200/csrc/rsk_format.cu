@@ -152,8 +152,8 @@ void seq_to_fasta(std::string &out, const std::string &label, const std::string 
 
 long long hand_over(const std::string &text, char *out, size_t cap)
 {
-	if (text.size() + 1 > cap)
-		return -(long long)text.size() - 1;
+	if (text.size() + 1 > cap)  // "need this many bytes": at most -17, so that it cannot be taken for an rsk_status
+		return -(long long)(text.size() < 16 ? 16 : text.size()) - 1;
 	memcpy(out, text.c_str(), text.size() + 1);
 	return (long long)text.size();
 }
