@@ -240,6 +240,51 @@ int rsk_postfilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, c
 int rsk_search_fast_db(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *popts,
 		const rsk_search_opts *opts, rsk_results **out);
 
+/* ---- multi-GPU: the -db side block-partitioned over the GPUs of one box ----
+ * The reference parallelises the search loop over std::threads that pull chains from one reader (runquery.cpp:82-125, body
+ * :18-80; `-fast -db`: muprefilter.cpp:64-133 + postmufilter.cpp:116-208) and serialises hit emission under DBSearcher::m_Lock
+ * (dbsearcher.cpp:267-278).  Here every rank (one per GPU; one process per GPU under torchrun, or one host thread per GPU inside
+ * one process) owns a CONTIGUOUS block of the -db chains, queries and parameters are replicated, and the DP needs no exchange.
+ * The data-path collectives are (1) the hit gather to the root rank - device-compacted hit records and path bytes travel as
+ * exact-size NCCL point-to-point transfers over NVLink - and (2) for `-fast -db` the all-gather of the per-block prefilter
+ * triples in rank order, which IS the stream order of the unsharded DB, so that every rank replays the same RankedScoresBag
+ * stream (rankedscoresbag.cpp:34-51) and the merged top-B lists equal the single-GPU ones, ties at the cut-off included.
+ * A communicator belongs to one context; all ranks must make the same sharded calls in the same order (collective semantics).
+ * comm == NULL means "one rank": the same device-compacted path without any transfer. */
+typedef struct rsk_comm rsk_comm;
+#define RSK_COMM_ID_BYTES 128
+int rsk_comm_unique_id(void *id /* [RSK_COMM_ID_BYTES], made on one rank and given to all (ncclGetUniqueId) */);
+int rsk_comm_create(rsk_ctx *ctx, int nranks, int rank, const void *id, rsk_comm **out);
+/* one process, several GPUs: communicators for n contexts on n different devices (ncclCommInitAll); out[n] */
+int rsk_comm_create_all(rsk_ctx *const *ctxs, int n, rsk_comm **out);
+void rsk_comm_destroy(rsk_comm *comm);
+int rsk_comm_rank(const rsk_comm *comm);
+int rsk_comm_nranks(const rsk_comm *comm);
+typedef struct rsk_comm_stats {
+	uint64_t bytes_sent, bytes_recv;   /* payload this rank put on / took from NVLink (its own block is a device-local copy) */
+	float collective_ms;               /* device time of the gather / all-gather rounds (CUDA events on the context stream) */
+	uint32_t collectives;
+} rsk_comm_stats;
+int rsk_comm_get_stats(const rsk_comm *comm, rsk_comm_stats *out);
+int rsk_comm_reset_stats(rsk_comm *comm);
+/* contiguous blocks with (nearly) equal residue totals: rank r owns chains bounds[r] .. bounds[r+1]-1; bounds[nranks+1] */
+int rsk_partition_by_residues(const uint32_t *len, uint32_t n, int nranks, uint32_t *bounds);
+
+/* DBSearcher::RunQuery over this rank's block of the -db chains (A_local; NULL = empty block) against the replicated in-memory
+ * chains B; a_base = index of the block's first chain in the unsharded DB.  The records the reference would emit (opts->keep ==
+ * RSK_KEEP_HITS) or all of them (RSK_KEEP_ALL) are compacted on the device, gathered on `root` and returned there in the order
+ * of the unsharded search (hit.a = DB chain index in the whole DB); *out is NULL on the other ranks. */
+int rsk_search_cross_sharded(rsk_ctx *ctx, rsk_comm *comm, const rsk_chainset *A_local, const rsk_chainset *B, uint32_t a_base,
+		const rsk_search_opts *opts, int root, rsk_results **out);
+/* `reseek -search Q -db DB -fast` with T_local = this rank's block of the DB (t_base = its first target index): local prefilter
+ * kernels, triples all-gathered in rank order, the bag replayed on the merged stream, the candidates of the own block
+ * post-filtered, hits gathered on `root` (hit.a = query, hit.b = target index in the whole DB).  cands_out (optional, every
+ * rank) receives the merged candidate list = the reference's candidate TSV content. */
+int rsk_search_fast_db_sharded(rsk_ctx *ctx, rsk_comm *comm, const rsk_chainset *Q, const rsk_chainset *T_local, uint32_t t_base,
+		const rsk_prefilter_opts *popts, const rsk_search_opts *opts, int root, rsk_results **out, rsk_prefilter_result **cands_out);
+/* order-independent 64-bit digest of a result set (records and path bytes): equal for the single-GPU and the sharded search */
+uint64_t rsk_results_digest(const rsk_results *r);
+
 /* -global: DSSAligner::AlignQueryTarget_Global (global.cpp:7-33) for explicit pairs (alignpair.cpp:110-114, runself.cpp:48-57,
  * scop40bench.cpp:313): the Mu filter when omega > 0, then ViterbiFastMem (viterbifastmem.cpp:33-193: three-state global
  * alignment, gap open -1, extend -0.05, terminal gaps free) with TraceBackBitMem.  One record per pair, in pair order:

@@ -8,4 +8,4 @@ no CPU fallback: importing :mod:`reseek_b200.lib` raises if the library has not 
 from .lib import (  # noqa: F401
     ChainSet, Context, HIT_DTYPE, MODE_FAST, MODE_SENSITIVE, MODE_VERYSENSITIVE, KEEP_ALL, KEEP_HITS,
     HIT_MU_REJECTED, HIT_HAS_EVALUE, HIT_REPORTED, HIT_MKF, HIT_GLOBAL, Params, ReseekB200Error, device_count, format_aln, format_fasta2, format_tsv, kabsch, load_library, path_to_cigar,
-    params_preset, prefilter_bag, version)
+    params_preset, prefilter_bag, version, Comm, comm_unique_id, partition_by_residues)

@@ -5,9 +5,12 @@
 #include <string.h>
 #include <time.h>
 
+#include <algorithm>
 #include <chrono>
 #include <future>
 #include <memory>
+#include <numeric>
+#include <thread>
 
 namespace reseek_b200 {
 
@@ -43,6 +46,12 @@ DBSearcher::~DBSearcher()
 	{
 	for (DSSAligner *DA : m_DAs)
 		delete DA;
+	for (rsk_chainset *S : m_RankDB)
+		rsk_chainset_free(S);
+	for (rsk_comm *C : m_RankComm)
+		rsk_comm_destroy(C);
+	for (size_t r = 1; r < m_RankCtx.size(); ++r)
+		rsk_ctx_destroy(m_RankCtx[r]);
 	rsk_chainset_free(m_DBSet);
 	if (m_LoaderCtx != 0)
 		rsk_ctx_destroy(m_LoaderCtx);
@@ -259,6 +268,11 @@ void DBSearcher::RunSelf()
 // in-memory chain (B); hits are emitted with Up = false (runquery.cpp:72-73)
 void DBSearcher::RunQueryBlock(const vector<ChainData> &Block)
 	{
+	if (m_RankCtx.size() > 1)
+		{
+		RunQueryBlockSharded(Block);
+		return;
+		}
 	DSSAligner &DA = *m_DAs[0];
 	rsk_ctx *C = GetContext();
 	rsk_search_opts O;
@@ -293,6 +307,120 @@ void DBSearcher::BeginRun()
 	m_Params->ToRsk(R, m_MaxEvalue);
 	Check(rsk_ctx_set_params(GetContext(), &R));
 	UploadDB();
+	SetupRanks();
+	}
+
+uint ResolveGpuCount(uint Requested, int FirstDevice)
+	{
+	const int Visible = rsk_device_count();
+	uint N = Requested;
+	if (N == 0)
+		{
+		const char *e = getenv("RSK_GPUS");
+		N = (e != 0 && atoi(e) > 0) ? (uint)atoi(e) : (uint)std::max(1, Visible - FirstDevice);
+		}
+	if ((int)N + FirstDevice > Visible)
+		Die("%u GPUs requested from device %d on, %d visible", N, FirstDevice, Visible);
+	return N;
+	}
+
+// One context + communicator + replica of the in-memory chains per additional GPU (rank 0 = the searcher's own context)
+void DBSearcher::SetupRanks()
+	{
+	if (!m_RankCtx.empty())
+		return;
+	const uint N = ResolveGpuCount(m_GpuCount, m_Device);
+	m_RankCtx.assign(1, GetContext());
+	if (N <= 1)
+		return;
+	rsk_params R;
+	m_Params->ToRsk(R, m_MaxEvalue);
+	const uint NC = GetDBChainCount();
+	vector<ChainData> Chains(NC);
+	for (uint i = 0; i < NC; ++i)
+		Chains[i] = GetDBChainData(i);
+	m_RankDB.assign(N, (rsk_chainset *)0);
+	for (uint r = 1; r < N; ++r)
+		{
+		rsk_ctx *C = 0;
+		Check(rsk_ctx_create(m_Device + (int)r, &R, 0, &C));
+		m_RankCtx.push_back(C);
+		m_RankDB[r] = UploadChains(C, Chains, !m_DBMuLettersVec.empty());
+		}
+	m_RankComm.assign(N, (rsk_comm *)0);
+	Check(rsk_comm_create_all(m_RankCtx.data(), (int)N, m_RankComm.data()));
+	}
+
+// runquery.cpp:82-125 sharded: rank r searches its share of the block against its replica of the in-memory chains; rank 0
+// receives every rank's hits (indices in the numbering of the whole block) and replays them through BaseOnAln.
+void DBSearcher::RunQueryBlockSharded(const vector<ChainData> &Block)
+	{
+	const uint N = RSK_SIZE(m_RankCtx);
+	const uint NB = RSK_SIZE(Block);
+	vector<uint32_t> Len(NB);
+	for (uint i = 0; i < NB; ++i)
+		Len[i] = Block[i].Chain->GetSeqLength();
+	vector<uint32_t> Bounds(N + 1);
+	Check(rsk_partition_by_residues(Len.data(), NB, (int)N, Bounds.data()));
+	const bool WithMu = !m_DBMuLettersVec.empty();
+	rsk_results *Res = 0;
+	vector<rsk_stats> Stats(N);
+	vector<string> Errors(N);
+	auto Work = [&](uint r)
+		{
+		rsk_ctx *C = m_RankCtx[r];
+		rsk_chainset *A = 0;
+		if (Bounds[r + 1] > Bounds[r])
+			{
+			vector<ChainData> Mine(Block.begin() + Bounds[r], Block.begin() + Bounds[r + 1]);
+			A = UploadChains(C, Mine, WithMu);
+			}
+		rsk_search_opts O;
+		memset(&O, 0, sizeof(O));
+		O.keep = RSK_KEEP_HITS;
+		O.want_paths = 1;
+		rsk_results *Mine = 0;
+		if (rsk_search_cross_sharded(C, m_RankComm[r], A, r == 0 ? m_DBSet : m_RankDB[r], Bounds[r], &O, 0, &Mine) != RSK_OK)
+			Errors[r] = rsk_last_error();
+		rsk_ctx_stats(C, &Stats[r]);
+		if (r == 0)
+			Res = Mine;
+		rsk_chainset_free(A);
+		};
+	vector<std::thread> Threads;
+	for (uint r = 1; r < N; ++r)
+		Threads.emplace_back(Work, r);
+	Work(0);
+	for (std::thread &t : Threads)
+		t.join();
+	for (uint r = 0; r < N; ++r)
+		if (!Errors[r].empty())
+			Die("reseek_b200 (GPU %u): %s", r, Errors[r].c_str());
+	for (uint r = 0; r < N; ++r)
+		{
+		const rsk_stats &S = Stats[r];
+		DSSAligner::m_AlnCount += (uint)S.pairs;
+		DSSAligner::m_SWCount += (uint)S.sw_pairs;
+		DSSAligner::m_MuFilterInputCount += (uint)S.mu_filter_in;
+		DSSAligner::m_MuFilterDiscardCount += (uint)S.mu_filter_rejected;
+		DSSAligner::m_ParasailSaturateCount += (uint)S.mu_saturated;
+		DSSAligner::m_XDropAlnCount += (uint)S.mkf_pairs;
+		m_ProcessedPairCount += (uint)S.pairs;
+		}
+	m_LastStats = Stats[0];
+	DSSAligner &DA = *m_DAs[0];
+	const uint64_t NH = rsk_results_count(Res);
+	const rsk_hit *Hits = rsk_results_hits(Res);
+	const char *Pool = rsk_results_paths(Res);
+	for (uint64_t k = 0; k < NH; ++k)
+		{
+		const rsk_hit &H = Hits[k];
+		DA.FromHit(H, Pool, Block[H.a], GetDBChainData(H.b));
+		if (!DA.m_Path.empty())
+			BaseOnAln(DA, false);
+		}
+	rsk_results_free(Res);
+	m_ProcessedQueryCount += NB;
 	}
 
 // runquery.cpp:82-130.  The stream is consumed in blocks of m_BlockChains chains.
@@ -459,7 +587,7 @@ void MuPreFilter(const DSSParams &Params, const vector<ChainData> &Query, const 
 
 // postmufilter.cpp:211-301; scan loop :116-208; Accept :105-114 with the default thresholds (E <= 10)
 void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const vector<ChainData> &Query,
-  const vector<ChainData> &DB, const string &HitsFN, const char *Columns, int Device, const string &AlnFN)
+  const vector<ChainData> &DB, const string &HitsFN, const char *Columns, int Device, const string &AlnFN, double MaxEvalue)
 	{
 	FILE *fIn = fopen(MuFilterTsvFN.c_str(), "r");
 	if (fIn == 0)
@@ -488,7 +616,7 @@ void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const ve
 	fclose(fIn);
 
 	rsk_params R;
-	Params.ToRsk(R, 10);
+	Params.ToRsk(R, MaxEvalue);
 	rsk_ctx *C = 0;
 	Check(rsk_ctx_create(Device, &R, 0, &C));
 	rsk_chainset *Q = UploadChains(C, Query, true);
@@ -515,7 +643,7 @@ void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const ve
 		{
 		const rsk_hit &H = Hits[k];
 		DA.FromHit(H, Pool, Query[H.a], DB[H.b]);
-		if (DA.m_EvalueA <= 10)  // Accept(): s_MaxEvalue = 10, s_MaxPvalue = -1, s_MinTS = 9e9
+		if (DA.m_EvalueA <= MaxEvalue)  // Accept(): s_MaxEvalue = opt(evalue) or 10 (postmufilter.cpp:105-114, 217-220)
 			{
 			DA.ToTsvColumns(fOut, true, Columns);
 			DA.ToAln(fAln, true);
@@ -529,6 +657,115 @@ void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const ve
 	rsk_chainset_free(Q);
 	rsk_chainset_free(T);
 	rsk_ctx_destroy(C);
+	}
+
+// `-search Q -db DB -fast` with the DB block-partitioned over the GPUs (see dbsearcher.h)
+void SearchFastDB(const DSSParams &Params, const vector<ChainData> &Query, const vector<ChainData> &DB, const string &HitsFN,
+  const char *Columns, const string &AlnFN, double MaxEvalue, uint GpuCount, const string &CandTsvFN)
+	{
+	const uint N = ResolveGpuCount(GpuCount, 0);
+	const uint NT = RSK_SIZE(DB);
+	vector<uint32_t> Len(NT);
+	for (uint i = 0; i < NT; ++i)
+		Len[i] = DB[i].Chain->GetSeqLength();
+	vector<uint32_t> Bounds(N + 1);
+	Check(rsk_partition_by_residues(Len.data(), NT, (int)N, Bounds.data()));
+	rsk_params R;
+	Params.ToRsk(R, MaxEvalue);
+	vector<rsk_ctx *> Ctx(N, (rsk_ctx *)0);
+	vector<rsk_comm *> Comm(N, (rsk_comm *)0);
+	for (uint r = 0; r < N; ++r)
+		Check(rsk_ctx_create((int)r, &R, 0, &Ctx[r]));
+	Check(rsk_comm_create_all(Ctx.data(), (int)N, Comm.data()));
+	rsk_results *Res = 0;
+	rsk_prefilter_result *Cands = 0;
+	vector<string> Errors(N);
+	auto Work = [&](uint r)
+		{
+		rsk_chainset *Q = UploadChains(Ctx[r], Query, true);
+		rsk_chainset *T = 0;
+		if (Bounds[r + 1] > Bounds[r])
+			{
+			vector<ChainData> Mine(DB.begin() + Bounds[r], DB.begin() + Bounds[r + 1]);
+			T = UploadChains(Ctx[r], Mine, true);
+			}
+		rsk_prefilter_opts PO;
+		memset(&PO, 0, sizeof(PO));
+		rsk_search_opts O;
+		memset(&O, 0, sizeof(O));
+		O.keep = RSK_KEEP_HITS;
+		O.want_paths = 1;
+		rsk_results *Mine = 0;
+		rsk_prefilter_result *MyCands = 0;
+		if (rsk_search_fast_db_sharded(Ctx[r], Comm[r], Q, T, Bounds[r], &PO, &O, 0, &Mine, r == 0 ? &MyCands : 0) != RSK_OK)
+			Errors[r] = rsk_last_error();
+		if (r == 0)
+			{
+			Res = Mine;
+			Cands = MyCands;
+			}
+		rsk_chainset_free(T);
+		rsk_chainset_free(Q);
+		};
+	vector<std::thread> Threads;
+	for (uint r = 1; r < N; ++r)
+		Threads.emplace_back(Work, r);
+	Work(0);
+	for (std::thread &t : Threads)
+		t.join();
+	for (uint r = 0; r < N; ++r)
+		if (!Errors[r].empty())
+			Die("reseek_b200 (GPU %u): %s", r, Errors[r].c_str());
+	if (!CandTsvFN.empty() && Cands != 0)
+		{
+		long long n = rsk_prefilter_to_tsv(Cands, 0, 0);
+		vector<char> Buf((size_t)(-n) + 1);
+		n = rsk_prefilter_to_tsv(Cands, Buf.data(), Buf.size());
+		FILE *f = fopen(CandTsvFN.c_str(), "w");
+		if (f == 0 || n < 0)
+			Die("Cannot create %s", CandTsvFN.c_str());
+		fwrite(Buf.data(), 1, (size_t)n, f);
+		fclose(f);
+		}
+	rsk_prefilter_free(Cands);
+	FILE *fOut = HitsFN.empty() ? 0 : fopen(HitsFN.c_str(), "w");
+	if (!HitsFN.empty() && fOut == 0)
+		Die("Cannot create %s", HitsFN.c_str());
+	FILE *fAln = AlnFN.empty() ? 0 : fopen(AlnFN.c_str(), "w");
+	if (!AlnFN.empty() && fAln == 0)
+		Die("Cannot create %s", AlnFN.c_str());
+	DSSAligner DA;
+	DA.SetParams(Params);
+	DA.UseContext(Ctx[0]);
+	const uint64_t NH = rsk_results_count(Res);
+	const rsk_hit *Hits = rsk_results_hits(Res);
+	const char *Pool = rsk_results_paths(Res);
+	// line order of the candidate TSV: target ascending, query ascending
+	vector<uint64_t> Order(NH);
+	std::iota(Order.begin(), Order.end(), (uint64_t)0);
+	std::sort(Order.begin(), Order.end(), [&](uint64_t x, uint64_t y)
+		{
+		return Hits[x].b != Hits[y].b ? Hits[x].b < Hits[y].b : Hits[x].a < Hits[y].a;
+		});
+	for (uint64_t k = 0; k < NH; ++k)
+		{
+		const rsk_hit &H = Hits[Order[k]];
+		DA.FromHit(H, Pool, Query[H.a], DB[H.b]);
+		if (DA.m_EvalueA <= MaxEvalue)
+			{
+			DA.ToTsvColumns(fOut, true, Columns);
+			DA.ToAln(fAln, true);
+			}
+		}
+	if (fOut != 0)
+		fclose(fOut);
+	if (fAln != 0)
+		fclose(fAln);
+	rsk_results_free(Res);
+	for (uint r = 0; r < N; ++r)
+		rsk_comm_destroy(Comm[r]);
+	for (uint r = 0; r < N; ++r)
+		rsk_ctx_destroy(Ctx[r]);
 	}
 
 namespace {

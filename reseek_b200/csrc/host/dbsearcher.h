@@ -73,6 +73,11 @@ public:
 	bool m_OwnsChains = false;   // the reference's destructor deletes chains/profiles (dbsearcher.cpp:12-22)
 	uint m_BlockChains = 100000; // streamed chains per device block in RunQuery
 	int m_Device = 0;
+	// GPUs RunQuery shards every streamed block over (devices m_Device .. m_Device + m_GpuCount - 1).  0 = all visible
+	// devices (RSK_GPUS in the environment overrides).  The reference's counterpart is m_ThreadCount worker threads pulling
+	// chains from one reader (runquery.cpp:82-125); here one host thread per GPU takes a contiguous, residue-balanced share
+	// of the block and the hits are gathered on the first GPU over NVLink (rsk_search_cross_sharded).
+	uint m_GpuCount = 0;
 
 public:
 	void Setup();
@@ -102,6 +107,12 @@ private:
 	rsk_ctx *m_LoaderCtx = 0;    // second context: the next block's self-reverse scores while the current block is searched
 	rsk_chainset *m_DBSet = 0;
 	rsk_stats m_LastStats;
+	// ranks 1 .. m_GpuCount-1 (rank 0 is m_Ctx / m_DBSet): context, communicator, replica of the in-memory chains
+	vector<rsk_ctx *> m_RankCtx;
+	vector<rsk_comm *> m_RankComm;
+	vector<rsk_chainset *> m_RankDB;
+	void SetupRanks();
+	void RunQueryBlockSharded(const vector<ChainData> &Block);
 	void UploadDB();
 	void BeginRun();
 	void RunQueryBlock(const vector<ChainData> &Block);
@@ -116,7 +127,16 @@ void MuPreFilter(const DSSParams &Params, const vector<ChainData> &Query, const 
   const string &OutputFN, int Device = 0);
 void PostMuFilter(const DSSParams &Params, const string &MuFilterTsvFN, const vector<ChainData> &Query,
   const vector<ChainData> &DB, const string &HitsFN, const char *Columns = 0, int Device = 0,
-  const string &AlnFN = string());  // AlnFN: -aln (postmufilter.cpp:194, 244)
+  const string &AlnFN = string(), double MaxEvalue = 10);  // AlnFN: -aln (postmufilter.cpp:194, 244); MaxEvalue: -evalue (:217-220)
+
+// Both stages on a DB block-partitioned over GpuCount GPUs (0 = all visible): one host thread per GPU, prefilter triples
+// all-gathered and the merged bag replayed on every GPU, hits gathered on the first (rsk_search_fast_db_sharded).  Hits are
+// written in the candidate TSV's line order (targets ascending, queries ascending), as the reference at -threads 1.
+// CandTsvFN (optional) receives the merged candidate list.
+void SearchFastDB(const DSSParams &Params, const vector<ChainData> &Query, const vector<ChainData> &DB, const string &HitsFN,
+  const char *Columns = 0, const string &AlnFN = string(), double MaxEvalue = 10, uint GpuCount = 0,
+  const string &CandTsvFN = string());
+uint ResolveGpuCount(uint Requested, int FirstDevice);
 
 // The same two stages with the chains named by file, PostMuFilter with the reference's own argument list
 // (search.cpp:14-18, postmufilter.cpp:211-216): the .bca files are read, run through DSS and given the self-reverse scores

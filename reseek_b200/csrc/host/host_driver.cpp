@@ -196,13 +196,14 @@ static void CloseAlnOutputs(DBSearcher &DBS)
 
 // The search command with the reference's own command line (cmd_search, search.cpp:20-111; options from myopts.h):
 //   rsk_host_demo -search Q.bca [-db DB.bca] -fast|-sensitive|-verysensitive [-output hits.tsv] [-columns a+b+c]
-//                 [-aln FILE] [-fasta2 FILE] [-unaligned] [-rowlen N] [-global] [-evalue E] [-noself] [-threads N]
-// .bca inputs only; -threads is accepted and ignored (one GPU context does the aligning).
+//                 [-aln FILE] [-fasta2 FILE] [-unaligned] [-rowlen N] [-global] [-evalue E] [-noself] [-threads N] [-gpus N]
+// .bca inputs only; -threads is accepted and ignored (GPU contexts do the aligning); -gpus N shards the -db side over N GPUs
+// (default: all visible devices).
 static int ReseekSearch(int argc, char **argv)
 	{
 	string QFN, DBFN, OutFN, Columns, AlnFN, Fasta2FN;
 	bool Unaligned = false, Global = false, NoSelf = false, HaveEvalue = false;
-	uint RowLen = 0;
+	uint RowLen = 0, Gpus = 0;
 	double Evalue = 10;
 	int Mode = -1;
 	for (int i = 1; i < argc; ++i)
@@ -223,6 +224,7 @@ static int ReseekSearch(int argc, char **argv)
 		else if (a == "-rowlen") RowLen = (uint)atoi(Value());
 		else if (a == "-evalue") { Evalue = atof(Value()); HaveEvalue = true; }
 		else if (a == "-threads") Value();
+		else if (a == "-gpus") Gpus = (uint)atoi(Value());
 		else if (a == "-unaligned") Unaligned = true;
 		else if (a == "-global") Global = true;
 		else if (a == "-noself") NoSelf = true;
@@ -242,14 +244,15 @@ static int ReseekSearch(int argc, char **argv)
 		// search.cpp:76-111: prefilter, then the post-filter under the sensitive preset
 		if (DBFN.size() < 4 || DBFN.compare(DBFN.size() - 4, 4, ".bca") != 0)
 			Die(".bca format required for -db");
-		const string TmpFN = OutFN.empty() ? string("/tmp/rsk_prefilter.tsv") : OutFN + ".prefilter.tmp";
+		// options this branch cannot honour are refused rather than dropped (the reference's PostMuFilter writes -output and
+		// -aln only, postmufilter.cpp:190-194, 244)
+		if (!Fasta2FN.empty() || NoSelf || Global)
+			Die("-fasta2, -noself and -global are not supported with -db ... -fast");
 		DSSParams Params2;
 		Params2.SetDSSParams(DM_AlwaysSensitive);
-		MuPreFilter(Params, QFN, DBFN, TmpFN);
 		{
-		// the writers' options reach PostMuFilter through the in-memory signature
 		rsk_params R;
-		Params2.ToRsk(R, 10);
+		Params2.ToRsk(R, Evalue);
 		rsk_ctx *C = 0;
 		if (rsk_ctx_create(0, &R, 0, &C) != RSK_OK)
 			Die("reseek_b200: %s", rsk_last_error());
@@ -257,15 +260,15 @@ static int ReseekSearch(int argc, char **argv)
 		QR.Open(QFN);
 		TR.Open(DBFN);
 		ChainFeatures Q, T;
-		ProfileLoader::Load(Params2, QR, 0, true, C, Params2, 10, Q);
-		ProfileLoader::Load(Params2, TR, 0, true, C, Params2, 10, T);
+		ProfileLoader::Load(Params2, QR, 0, true, C, Params2, Evalue, Q);
+		ProfileLoader::Load(Params2, TR, 0, true, C, Params2, Evalue, T);
+		rsk_ctx_destroy(C);
 		const vector<ChainData> QD = ToChainData(Q), TD = ToChainData(T);
-		PostMuFilter(Params2, TmpFN, QD, TD, OutFN, Columns.empty() ? 0 : Columns.c_str(), 0, AlnFN);
+		// prefilter + merged bag + post-filter, the DB block-partitioned over the GPUs (-gpus N; default: all visible)
+		SearchFastDB(Params2, QD, TD, OutFN, Columns.empty() ? 0 : Columns.c_str(), AlnFN, Evalue, Gpus);
 		Q.Free();
 		T.Free();
-		rsk_ctx_destroy(C);
 		}
-		remove(TmpFN.c_str());
 		return 0;
 		}
 	CountingSearcher DBS;
@@ -284,6 +287,7 @@ static int ReseekSearch(int argc, char **argv)
 	DBS.m_Unaligned = Unaligned;
 	DBS.m_RowLen = RowLen;
 	DBS.m_Global = Global;
+	DBS.m_GpuCount = Gpus;
 	if (const char *e = getenv("RSK_BLOCK_CHAINS"))
 		DBS.m_BlockChains = (uint)atoi(e);
 	if (DBFN.empty())

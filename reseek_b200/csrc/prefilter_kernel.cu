@@ -287,21 +287,195 @@ __global__ void pf_count_cands_kernel(const PfArgs a, uint32_t ntl)
 	a.cand_count[tl] = n;
 }
 
+// triples leave as (query, target<<16 | score): the form the bag kernels sort and replay (target index in the numbering of
+// the whole DB: t_base = first target of this rank's block)
 __global__ void pf_write_cands_kernel(const PfArgs a, uint32_t ntl)
 {
 	const uint32_t tl = blockIdx.x * blockDim.x + threadIdx.x;
 	if (tl >= ntl)
 		return;
-	unsigned long long o = a.cand_off[tl];
+	unsigned long long o = a.raw_base + a.cand_off[tl];
 	for (uint32_t q = 0; q < a.nQ; ++q) {
 		const unsigned b = a.best[(size_t)tl * a.nQ + q];
 		if (b) {
-			a.cand_t[o] = a.t_begin + tl;
-			a.cand_q[o] = q;
-			a.cand_s[o] = (uint16_t)b;
+			a.raw_q[o] = q;
+			a.raw_v[o] = ((unsigned long long)(a.t_base + a.t_begin + tl) << 16) | (unsigned long long)b;
 			++o;
 		}
 	}
+}
+
+// ---- RankedScoresBag on the device (rankedscoresbag.cpp:5-51, :185-232) ----
+// The triples, stably sorted by query, are replayed one warp per query in stream order: AddScore admits `score >= lo` until
+// the vectors hold 2B entries, TruncateVecs then keeps the first B of QuickSortOrderDesc (sort.h:71-108).  That quicksort is
+// unstable, and which of the tied entries survive at the cut-off - and how the survivors are arranged for the NEXT
+// truncation - is decided by its exact swap sequence, so it is restated (Hoare partition around the middle element) and run
+// by one lane on shared memory; the admission scan, the gather of the survivors and the output are warp-parallel.
+__device__ void bag_quicksort_desc(uint16_t *vs, uint32_t *order, int n)
+{
+	// vs[i] mirrors Values[Order[i]] and is swapped together with order[i]; sub-ranges are disjoint, so the order in which the
+	// recursion visits them is irrelevant: an explicit stack, larger half pushed, bounds the depth by log2(n)
+	int stack_l[32], stack_r[32];
+	int sp = 0;
+	int left = 0, right = n - 1;
+	for (;;) {
+		while (left < right) {
+			int i = left, j = right;
+			const uint16_t pivot = vs[(left + right) / 2];
+			while (i <= j) {
+				while (vs[i] > pivot)
+					i++;
+				while (vs[j] < pivot)
+					j--;
+				if (i <= j) {
+					const uint16_t tv = vs[i]; vs[i] = vs[j]; vs[j] = tv;
+					const uint32_t to = order[i]; order[i] = order[j]; order[j] = to;
+					i++;
+					j--;
+				}
+			}
+			// ranges (left, j) and (i, right)
+			const bool hasL = left < j, hasR = i < right;
+			if (hasL && hasR) {
+				if (j - left > right - i) {
+					stack_l[sp] = left; stack_r[sp] = j; ++sp;
+					left = i;
+				} else {
+					stack_l[sp] = i; stack_r[sp] = right; ++sp;
+					right = j;
+				}
+			} else if (hasL) {
+				right = j;
+			} else if (hasR) {
+				left = i;
+			} else {
+				break;
+			}
+		}
+		if (sp == 0)
+			break;
+		--sp;
+		left = stack_l[sp]; right = stack_r[sp];
+	}
+}
+
+__global__ void __launch_bounds__(32) pf_bag_kernel(const unsigned long long *__restrict__ val, const unsigned long long *__restrict__ seg_begin,
+		const unsigned long long *__restrict__ seg_end, uint32_t B, unsigned long long *out_key, uint32_t *out_n)
+{
+	extern __shared__ unsigned char bag_smem[];
+	uint32_t *t = (uint32_t *)bag_smem;         // [2B] target of entry i
+	uint32_t *order = t + 2 * B;                // [2B]
+	uint32_t *t2 = order + 2 * B;               // [B]
+	uint16_t *s = (uint16_t *)(t2 + B);         // [2B] score of entry i
+	uint16_t *vs = s + 2 * B;                   // [2B] s[order[i]]
+	const uint32_t q = blockIdx.x, lane = threadIdx.x;
+	unsigned long long pos = seg_begin[q];
+	const unsigned long long end = seg_end[q];
+	uint32_t n = 0, lo = 0;
+	auto truncate = [&]() {  // TruncateVecs
+		for (uint32_t k = lane; k < n; k += 32) {
+			order[k] = k;
+			vs[k] = s[k];
+		}
+		__syncwarp();
+		if (lane == 0)
+			bag_quicksort_desc(vs, order, (int)n);
+		__syncwarp();
+		for (uint32_t k = lane; k < B; k += 32)
+			t2[k] = t[order[k]];
+		__syncwarp();
+		for (uint32_t k = lane; k < B; k += 32) {
+			t[k] = t2[k];
+			s[k] = vs[k];
+		}
+		__syncwarp();
+		lo = s[B - 1];
+		n = B;
+	};
+	while (pos < end) {
+		const unsigned long long i = pos + lane;
+		uint32_t sc = 0, tt = 0;
+		bool ok = false;
+		if (i < end) {
+			const unsigned long long v = val[i];
+			sc = (uint32_t)(v & 0xffffu);
+			tt = (uint32_t)(v >> 16);
+			ok = sc >= lo;  // AddScore: Score >= LoScore
+		}
+		unsigned m = __ballot_sync(kFull, ok);
+		const uint32_t room = 2 * B - n;
+		uint32_t consumed = 32;
+		if ((uint32_t)__popc(m) >= room) {
+			unsigned mm = m;  // lane of the room-th admitted entry: the one that fills the vectors
+			for (uint32_t r = 1; r < room; ++r)
+				mm &= mm - 1;
+			const uint32_t last = (uint32_t)__ffs((int)mm) - 1u;
+			m &= (last == 31) ? kFull : ((2u << last) - 1u);
+			consumed = last + 1;
+		}
+		if ((m >> lane) & 1u) {
+			const uint32_t slot = n + __popc(m & ((1u << lane) - 1u));
+			s[slot] = (uint16_t)sc;
+			t[slot] = tt;
+		}
+		n += __popc(m);
+		pos += consumed;
+		__syncwarp();
+		if (n >= 2 * B)
+			truncate();
+	}
+	if (n >= B)  // ToTsv's final TruncateVecs (a vector below B entries is left as it is)
+		truncate();
+	for (uint32_t k = lane; k < n; k += 32)
+		out_key[(size_t)q * B + k] = ((unsigned long long)t[k] << 32) | ((unsigned long long)q << 16) | s[k];
+	if (lane == 0)
+		out_n[q] = n;
+}
+
+__global__ void pf_mark_segments_kernel(const uint32_t *__restrict__ key, unsigned long long n, unsigned long long *seg_begin, unsigned long long *seg_end)
+{
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const uint32_t k = key[i];
+	if (i == 0 || key[i - 1] != k)
+		seg_begin[k] = i;
+	if (i + 1 == n || key[i + 1] != k)
+		seg_end[k] = i + 1;
+}
+
+// gather the bags' entries (at most B per query, out_n[q] valid) into one dense key array
+__global__ void pf_bag_compact_kernel(const unsigned long long *__restrict__ key, const uint32_t *__restrict__ out_n,
+		const unsigned long long *__restrict__ out_off, uint32_t B, unsigned long long *dense)
+{
+	const uint32_t q = blockIdx.x;
+	const uint32_t n = out_n[q];
+	const unsigned long long o = out_off[q];
+	for (uint32_t k = threadIdx.x; k < n; k += blockDim.x)
+		dense[o + k] = key[(size_t)q * B + k];
+}
+
+__global__ void pf_unpack_triples_kernel(const uint32_t *__restrict__ q, const unsigned long long *__restrict__ v, unsigned long long n,
+		uint32_t *t_out, uint32_t *q_out, uint16_t *s_out)
+{
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const unsigned long long x = v[i];
+	t_out[i] = (uint32_t)(x >> 16);
+	q_out[i] = q[i];
+	s_out[i] = (uint16_t)(x & 0xffffu);
+}
+
+__global__ void pf_unpack_keys_kernel(const unsigned long long *__restrict__ key, unsigned long long n, uint32_t *t_out, uint32_t *q_out, uint16_t *s_out)
+{
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const unsigned long long x = key[i];
+	t_out[i] = (uint32_t)(x >> 32);
+	q_out[i] = (uint32_t)(x >> 16) & 0xffffu;
+	s_out[i] = (uint16_t)(x & 0xffffu);
 }
 
 // K/L swap of the query letters (the query side goes through g_CharToLetterMu, alpha.cpp:3291)
@@ -378,6 +552,70 @@ int pf_launch_cands(const PfArgs &a, uint32_t ntl, bool write, cudaStream_t st)
 		pf_write_cands_kernel<<<(ntl + 127) / 128, 128, 0, st>>>(a, ntl);
 	else
 		pf_count_cands_kernel<<<(ntl + 127) / 128, 128, 0, st>>>(a, ntl);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+size_t pf_bag_smem_bytes(uint32_t B) { return (size_t)B * (4 * 2 + 4 * 2 + 4 + 2 * 2 + 2 * 2) + 16; }
+
+// stable sort of the triples by query (16 key bits), value = target<<16 | score
+int pf_sort_by_query(const uint32_t *qin, uint32_t *qout, const unsigned long long *vin, unsigned long long *vout, unsigned long long n,
+		void *tmp, size_t &tmp_bytes, cudaStream_t st)
+{
+	return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, qin, qout, vin, vout, (long long)n, 0, 16, st) == cudaSuccess ? 0 : -1;
+}
+
+int pf_sort_keys64(const unsigned long long *kin, unsigned long long *kout, unsigned long long n, void *tmp, size_t &tmp_bytes, cudaStream_t st)
+{
+	return cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, kin, kout, (long long)n, 0, 64, st) == cudaSuccess ? 0 : -1;
+}
+
+int pf_launch_mark_segments(const uint32_t *key, unsigned long long n, unsigned long long *seg_begin, unsigned long long *seg_end, cudaStream_t st)
+{
+	if (n == 0)
+		return 0;
+	pf_mark_segments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, seg_begin, seg_end);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int pf_launch_bag(const unsigned long long *val, const unsigned long long *seg_begin, const unsigned long long *seg_end, uint32_t nQ, uint32_t B,
+		unsigned long long *out_key, uint32_t *out_n, cudaStream_t st)
+{
+	if (nQ == 0)
+		return 0;
+	const size_t smem = pf_bag_smem_bytes(B);
+	static size_t configured = 0;
+	if (smem > 48 * 1024 && smem > configured) {
+		if (cudaFuncSetAttribute(pf_bag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+			return -1;
+		configured = smem;
+	}
+	pf_bag_kernel<<<nQ, 32, smem, st>>>(val, seg_begin, seg_end, B, out_key, out_n);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int pf_launch_bag_compact(const unsigned long long *key, const uint32_t *out_n, const unsigned long long *out_off, uint32_t nQ, uint32_t B,
+		unsigned long long *dense, cudaStream_t st)
+{
+	if (nQ == 0)
+		return 0;
+	pf_bag_compact_kernel<<<nQ, 128, 0, st>>>(key, out_n, out_off, B, dense);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int pf_launch_unpack_triples(const uint32_t *q, const unsigned long long *v, unsigned long long n, uint32_t *t_out, uint32_t *q_out,
+		uint16_t *s_out, cudaStream_t st)
+{
+	if (n == 0)
+		return 0;
+	pf_unpack_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, v, n, t_out, q_out, s_out);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int pf_launch_unpack_keys(const unsigned long long *key, unsigned long long n, uint32_t *t_out, uint32_t *q_out, uint16_t *s_out, cudaStream_t st)
+{
+	if (n == 0)
+		return 0;
+	pf_unpack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, t_out, q_out, s_out);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

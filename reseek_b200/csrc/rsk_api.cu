@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "rsk_host.cuh"
+#include "rsk_multi.cuh"
 #include "score_tables_data.inc"
 
 // ------------------------------------------------------------------------------------------------
@@ -328,6 +329,7 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 		ctx->pf_scratch_free(ctx->pf_scratch);
 	ctx->pf_scratch = nullptr;
 	ctx->upload_stage.release();
+	ctx->sink.release(); ctx->h_sink[0].release(); ctx->h_sink[1].release();
 	ctx->ckpt.release(); ctx->tile.release(); ctx->best.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
 	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();
 	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
@@ -811,7 +813,29 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		if (nlm < 0)
 			return fail(RSK_ERR_CUDA, "Mu filter kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->stats.kernel_launches += nlm;
-		ctx->stats.mu_filter_in += b.npairs;
+		{
+			// DoMKF() pairs return from AlignQueryTarget before ++m_MuFilterInputCount (dssaligner.cpp:811-820)
+			uint64_t nmkf = 0;
+			const uint32_t mkfl = ctx->params.mkfl;
+			if (b.maxLA >= mkfl || b.maxLB >= mkfl) {
+				if (b.cross) {
+					uint64_t longB = 0, okB = 0;
+					for (uint32_t j = 0; j < B->d.n; ++j) {
+						longB += B->hlen[j] >= mkfl && B->hlen[j] >= 3;
+						okB += B->hlen[j] >= 3;
+					}
+					for (uint32_t a = b.a0; a < b.a1; ++a)
+						if (A->hlen[a] >= 3)
+							nmkf += A->hlen[a] >= mkfl ? okB : longB;
+				} else {
+					for (size_t k = 0; k < b.npairs; ++k) {
+						const uint32_t la = A->hlen[plan.sa[b.k0 + k]], lb = B->hlen[plan.sb[b.k0 + k]];
+						nmkf += la >= 3 && lb >= 3 && (la >= mkfl || lb >= mkfl);
+					}
+				}
+			}
+			ctx->stats.mu_filter_in += b.npairs - nmkf;
+		}
 		if (b.cross) {
 			const uint32_t nrows = (uint32_t)rowlist.size();
 			task_cap = nrows * (ncols / kClassWarps[kSwClasses - 1] + 1);
@@ -1048,7 +1072,50 @@ void fill_hit(const rsk_params &P, const PairRec &r, uint32_t a, uint32_t b, uin
 		h.flags |= RSK_HIT_REPORTED;
 }
 
-int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, rsk_results **out, bool device_only)
+// Explicit pair lists: build and upload the Mu filter's tasks for the batch's sorted pairs [k0,k1) - runs of equal A, chunks
+// of one task's column count - plus the pair index arrays the LDDT kernel and the hit sink read.
+int upload_explicit_tasks(rsk_ctx *ctx, const SearchPlan &plan, Batch &b)
+{
+	cudaStream_t st = ctx->stream;
+	rsk_stats &S = ctx->stats;
+	static thread_local std::vector<uint32_t> t_a, t_begin, t_cnt, slots;
+	// (cudaMemcpyAsync from pageable memory returns once the source has been staged, so the vectors can be reused per batch)
+	const size_t task_cols = (std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32")) ? (size_t)kMuTaskCols : (size_t)kSwWarps;
+	t_a.clear(); t_begin.clear(); t_cnt.clear();
+	const size_t n = b.k1 - b.k0;
+	slots.resize(n);
+	for (size_t k = 0; k < n; ++k)
+		slots[k] = (uint32_t)k;
+	size_t k = 0;
+	while (k < n) {
+		size_t e = k + 1;
+		while (e < n && e - k < task_cols && plan.sa[b.k0 + e] == plan.sa[b.k0 + k])
+			++e;
+		t_a.push_back(plan.sa[b.k0 + k]);
+		t_begin.push_back((uint32_t)k);
+		t_cnt.push_back((uint32_t)(e - k));
+		k = e;
+	}
+	b.ntasks = (uint32_t)t_a.size();
+	if (ctx->blist.ensure(n) || ctx->bslot.ensure(n) || ctx->pair_a.ensure(n) || ctx->pair_b.ensure(n) ||
+		ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks)) {
+		return fail(RSK_ERR_NOMEM, "task buffers");
+	}
+	CK(cudaMemcpyAsync(ctx->blist.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->bslot.p, slots.data(), 4 * n, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->pair_a.p, plan.sa.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->pair_b.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->task_a.p, t_a.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->task_begin.p, t_begin.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->task_cnt.p, t_cnt.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
+	S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks;
+	return RSK_OK;
+}
+
+struct SinkOpts { uint32_t a_base = 0, b_base = 0; };
+int run_to_sink(rsk_ctx *ctx, SearchPlan &plan, std::vector<Batch> &batches, const rsk_search_opts &opts, const SinkOpts &so);
+
+int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, rsk_results **out, bool device_only, const SinkOpts *sink = nullptr)
 {
 	rsk_search_opts opts;
 	memset(&opts, 0, sizeof(opts));
@@ -1134,16 +1201,21 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 	}
 	S.pairs = plan.npairs;
 
+	if (sink)
+		return run_to_sink(ctx, plan, batches, opts, *sink);
+
 	rsk_results *res = nullptr;
+	struct ResGuard {
+		rsk_results *&r;
+		~ResGuard() { delete r; r = nullptr; }
+	} res_guard{res};  // `res` is handed to the caller by setting it to nullptr after copying the pointer out
 	const bool keep_all = opts.keep == RSK_KEEP_ALL;
 	if (!device_only) {
 		res = new rsk_results();
 		if (keep_all) {
 			res->hits = (rsk_hit *)g_blocks.get(std::max<uint64_t>(1, plan.npairs) * sizeof(rsk_hit), res->hits_cap);
-			if (!res->hits) {
-				delete res;
+			if (!res->hits)
 				return fail(RSK_ERR_NOMEM, "host memory for %llu hit records", (unsigned long long)plan.npairs);
-			}
 			res->nhits = plan.npairs;
 		}
 	}
@@ -1152,12 +1224,20 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 	// next batch occupies the GPU.  Path bytes go straight from the pinned staging pool to their final place; the hits of
 	// RSK_KEEP_HITS are gathered per worker and appended to the result array when the job is collected (also overlapped,
 	// except for the last batch).
+	// Declared after `res_guard`, so that on ANY early return (CK, NOMEM) the workers are joined first and the result they
+	// write into is deleted afterwards; a joinable std::thread must never reach its destructor.
 	struct Job {
 		std::vector<std::thread> threads;
 		std::vector<std::vector<rsk_hit>> kept;  // per thread (KEEP_HITS)
 		std::vector<uint64_t> n_eval, n_hit, n_rej;
 		size_t npairs = 0;
 		bool active = false;
+		~Job()
+		{
+			for (auto &t : threads)
+				if (t.joinable())
+					t.join();
+		}
 	};
 	Job jobs[2];
 	const bool timing = getenv("RSK_TIMING") != nullptr;  // developer aid: host-side phases of the call on stderr
@@ -1241,10 +1321,9 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		J.kept.clear();
 		J.active = false;
 	};
-	auto abort_all = [&]() {
+	auto abort_all = [&]() {  // explicit form of what the guards do on any other early return
 		wait_job(jobs[0]);
 		wait_job(jobs[1]);
-		delete res;
 	};
 
 	uint64_t pool_total = 0;
@@ -1368,44 +1447,14 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 			return RSK_OK;
 	};
 
-	std::vector<uint32_t> t_a, t_begin, t_cnt, slots;
 	for (const Batch &b0 : batches) {
 		Batch b = b0;
 		const int buf = (int)(bi++ & 1);
 		const double tt_0 = now_ms();
 		if (!b.cross) {
-			// build the Mu filter's tasks for sorted pairs [k0,k1): runs of equal A, chunks of one task's column count
-			const size_t task_cols = (std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32")) ? (size_t)kMuTaskCols : (size_t)kSwWarps;
-			t_a.clear(); t_begin.clear(); t_cnt.clear();
-			const size_t n = b.k1 - b.k0;
-			slots.resize(n);
-			for (size_t k = 0; k < n; ++k)
-				slots[k] = (uint32_t)k;
-			size_t k = 0;
-			while (k < n) {
-				size_t e = k + 1;
-				while (e < n && e - k < task_cols && plan.sa[b.k0 + e] == plan.sa[b.k0 + k])
-					++e;
-				t_a.push_back(plan.sa[b.k0 + k]);
-				t_begin.push_back((uint32_t)k);
-				t_cnt.push_back((uint32_t)(e - k));
-				k = e;
-			}
-			b.ntasks = (uint32_t)t_a.size();
-			if (ctx->blist.ensure(n) || ctx->bslot.ensure(n) || ctx->pair_a.ensure(n) || ctx->pair_b.ensure(n) ||
-				ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks)) {
-				if (!device_only)
-					abort_all();
-				return fail(RSK_ERR_NOMEM, "task buffers");
-			}
-			CK(cudaMemcpyAsync(ctx->blist.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->bslot.p, slots.data(), 4 * n, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->pair_a.p, plan.sa.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->pair_b.p, plan.sb.data() + b.k0, 4 * n, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->task_a.p, t_a.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->task_begin.p, t_begin.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
-			CK(cudaMemcpyAsync(ctx->task_cnt.p, t_cnt.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
-			S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks;
+			const int rce = upload_explicit_tasks(ctx, plan, b);
+			if (rce)
+				return rce;
 		}
 		g_t_tasks += now_ms() - tt_0;
 		const double tl0 = now();
@@ -1456,19 +1505,304 @@ int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, 
 		if (timing)
 			fprintf(stderr, "[rsk_search] %zu batches: launch %.1f ms, kernels+D2H %.1f ms, waiting for host conversion %.1f ms, tail %.1f ms, call %.1f ms\n",
 					batches.size(), t_launch, t_d2h, t_wait, now() - tt0, now() - t_call0);
-		if (nomem) {
-			delete res;
+		if (nomem)
 			return fail(RSK_ERR_NOMEM, "host memory for the hit records");
-		}
 	}
 	CK(cudaEventRecord(ctx->ev[7], st));
 	CK(cudaEventSynchronize(ctx->ev[7]));
 	CK(cudaEventElapsedTime(&S.total_ms, ctx->ev[6], ctx->ev[7]));
 	if (out)
 		*out = res;
+	res = nullptr;  // ownership passed to the caller (or there was no result object)
 	return RSK_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// device hit sink: search -> compacted hits on the device -> (gather over NVLink) -> host
+// ------------------------------------------------------------------------------------------------
+// Emit threshold on the test statistic.  E(ts) = (float)(P(ts) * 8340) (statsig.cpp:27-50, dssaligner.cpp:891-893) does not
+// increase with ts, so "E <= MaxEvalue" is "ts >= t*"; t* is found by bisection over the ordered float bit patterns with the
+// very functions the host applies afterwards, then lowered by a margin far above libm's error.  The device keeps a superset,
+// the exact test runs on what arrives.
+float sink_ts_threshold(double max_evalue)
+{
+	auto rejected = [&](float ts) { return (double)(float)(rsk_pvalue(ts) * 8340) > max_evalue; };
+	if (!rejected(-FLT_MAX))
+		return -FLT_MAX;
+	if (rejected(FLT_MAX))
+		return FLT_MAX;
+	auto f2o = [](float f) { int32_t i; memcpy(&i, &f, 4); return i >= 0 ? (int64_t)i : -(int64_t)(i & 0x7fffffff); };
+	auto o2f = [](int64_t o) { int32_t i = o >= 0 ? (int32_t)o : (int32_t)(0x80000000u | (uint32_t)(-o)); float f; memcpy(&f, &i, 4); return f; };
+	int64_t lo = f2o(-FLT_MAX), hi = f2o(FLT_MAX);  // lo rejected, hi accepted
+	while (hi - lo > 1) {
+		const int64_t mid = lo + (hi - lo) / 2;
+		if (rejected(o2f(mid)))
+			lo = mid;
+		else
+			hi = mid;
+	}
+	const float t = o2f(hi);
+	return t - fabsf(t) * 1e-5f - 1e-6f;
+}
+
+// capacity for `need_rec` records / `need_pool` path bytes; growing keeps what the finished batches wrote
+int sink_reserve(rsk_ctx *ctx, size_t need_rec, size_t need_pool)
+{
+	HitSink &K = ctx->sink;
+	if (need_rec <= K.rec_cap && need_pool <= K.pool_cap)
+		return RSK_OK;
+	cudaStream_t st = ctx->stream;
+	CK(cudaStreamSynchronize(st));
+	unsigned long long tot[4] = {0, 0, 0, 0};
+	CK(cudaMemcpy(tot, K.d_tot, sizeof(tot), cudaMemcpyDeviceToHost));
+	if (need_rec > K.rec_cap) {
+		const size_t want = std::max(need_rec, 2 * K.rec_cap) + 1024;
+		SinkRec *p = nullptr;
+		if (cudaMalloc((void **)&p, want * sizeof(SinkRec)) != cudaSuccess) {
+			cudaGetLastError();
+			return fail(RSK_ERR_NOMEM, "device hit sink: %zu records", want);
+		}
+		if (K.rec && tot[0])
+			CK(cudaMemcpy(p, K.rec, tot[0] * sizeof(SinkRec), cudaMemcpyDeviceToDevice));
+		if (K.rec)
+			cudaFree(K.rec);
+		K.rec = p;
+		K.rec_cap = want;
+	}
+	if (need_pool > K.pool_cap) {
+		const size_t want = std::max(need_pool, 2 * K.pool_cap) + 4096;
+		uint8_t *p = nullptr;
+		if (cudaMalloc((void **)&p, want) != cudaSuccess) {
+			cudaGetLastError();
+			return fail(RSK_ERR_NOMEM, "device hit sink: %zu path bytes", want);
+		}
+		if (K.pool && tot[1])
+			CK(cudaMemcpy(p, K.pool, tot[1], cudaMemcpyDeviceToDevice));
+		if (K.pool)
+			cudaFree(K.pool);
+		K.pool = p;
+		K.pool_cap = want;
+	}
+	return RSK_OK;
+}
+
+// The batches of a search call, their emitted records compacted into ctx->sink.  No D2H of per-pair records and no host
+// conversion per batch: the host only runs two batches ahead of the device (it needs the exact sink totals to bound the space
+// the next batch may take).  On return the stream is idle and ctx->sink.h_tot[0..3] holds the totals.
+int run_to_sink(rsk_ctx *ctx, SearchPlan &plan, std::vector<Batch> &batches, const rsk_search_opts &opts, const SinkOpts &so)
+{
+	HitSink &K = ctx->sink;
+	cudaStream_t st = ctx->stream;
+	rsk_stats &S = ctx->stats;
+	if (!K.d_tot) {
+		CK(cudaMalloc((void **)&K.d_tot, 4 * sizeof(unsigned long long)));
+		CK(cudaHostAlloc((void **)&K.h_tot, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+	}
+	CK(cudaMemsetAsync(K.d_tot, 0, 4 * sizeof(unsigned long long), st));
+	const float ts_lo = sink_ts_threshold(ctx->params.max_evalue);
+	const uint32_t report_no_evalue = !((double)FLT_MAX > ctx->params.max_evalue) ? 1u : 0u;
+	unsigned long long conf_rec = 0, conf_pool = 0;
+	size_t unconf_rec[2] = {0, 0}, unconf_pool[2] = {0, 0};
+	const size_t nb = batches.size();
+	int rc;
+	for (size_t i = 0; i < nb; ++i) {
+		Batch b = batches[i];
+		const int set = (int)(i & 1);
+		if (i >= 2) {  // batch i-2 ran in this batch set: its timing events and the exact totals after it
+			CK(cudaEventSynchronize(ctx->done));
+			if ((rc = finish_batch_timing(ctx)))
+				return rc;
+			conf_rec = K.h_tot[set * 4 + 0];
+			conf_pool = K.h_tot[set * 4 + 1];
+			unconf_rec[set] = unconf_pool[set] = 0;
+		}
+		if (!b.cross && (rc = upload_explicit_tasks(ctx, plan, b)))
+			return rc;
+		unconf_rec[set] = b.npairs;
+		unconf_pool[set] = opts.want_paths ? (size_t)b.pool_bound : 0;
+		if ((rc = sink_reserve(ctx, conf_rec + unconf_rec[0] + unconf_rec[1], conf_pool + unconf_pool[0] + unconf_pool[1] + 64)))
+			return rc;
+		if ((rc = run_batch(ctx, plan, b, opts)))
+			return rc;
+		if (b.npairs > 0x7fffffffull)
+			return fail(RSK_ERR_LIMIT, "hit sink: batch of %zu pairs", b.npairs);
+		const size_t tmp_bytes = sink_scan_tmp_bytes((uint32_t)b.npairs);
+		if (K.keep.ensure(b.npairs) || K.plen.ensure(b.npairs) || K.keep_scan.ensure(b.npairs) || K.plen_scan.ensure(b.npairs) ||
+			K.tmp.ensure(tmp_bytes)) {
+			cudaGetLastError();
+			return fail(RSK_ERR_NOMEM, "hit sink scratch for %zu pairs", b.npairs);
+		}
+		SinkArgs a;
+		memset(&a, 0, sizeof(a));
+		a.rec = ctx->rec.p; a.npairs = (uint32_t)b.npairs; a.pool = ctx->pool.p;
+		a.cross = b.cross ? 1 : 0; a.a_begin = b.a0; a.nB = plan.B->d.n;
+		a.pair_a = ctx->pair_a.p; a.pair_b = ctx->pair_b.p;
+		a.a_base = so.a_base; a.b_base = so.b_base;
+		a.keep_all = opts.keep == RSK_KEEP_ALL ? 1 : 0;
+		a.want_paths = opts.want_paths ? 1 : 0;
+		a.report_no_evalue = report_no_evalue;
+		a.ts_lo = ts_lo;
+		a.keep = K.keep.p; a.plen = K.plen.p; a.keep_scan = K.keep_scan.p; a.plen_scan = K.plen_scan.p;
+		a.out_rec = K.rec; a.out_pool = K.pool; a.totals = K.d_tot;
+		const int nl = launch_sink_append(a, K.tmp.p, tmp_bytes, st);
+		if (nl < 0)
+			return fail(RSK_ERR_CUDA, "hit sink kernels failed to launch: %s", cudaGetErrorString(cudaGetLastError()));
+		S.kernel_launches += nl;
+		CK(cudaMemcpyAsync(K.h_tot + set * 4, K.d_tot, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		CK(cudaEventRecord(ctx->done, st));
+		ctx->swap_batch_set();
+	}
+	if (nb >= 2) {  // batch nb-2 lives in the current set
+		CK(cudaEventSynchronize(ctx->done));
+		if ((rc = finish_batch_timing(ctx)))
+			return rc;
+	}
+	ctx->swap_batch_set();
+	if (nb >= 1) {
+		CK(cudaEventSynchronize(ctx->done));
+		if ((rc = finish_batch_timing(ctx)))
+			return rc;
+	}
+	CK(cudaMemcpyAsync(K.h_tot, K.d_tot, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CK(cudaEventRecord(ctx->ev[7], st));
+	CK(cudaEventSynchronize(ctx->ev[7]));
+	CK(cudaEventElapsedTime(&S.total_ms, ctx->ev[6], ctx->ev[7]));
+	S.evalue_pairs = K.h_tot[2];
+	S.mu_filter_rejected = K.h_tot[3];
+	return RSK_OK;
+}
+
+// Device -> host through the double-buffered pinned path staging of the context, the memcpy out of one buffer overlapping
+// the DMA into the other.
+int d2h_staged(rsk_ctx *ctx, char *dst, const unsigned char *src, size_t bytes)
+{
+	if (bytes == 0)
+		return RSK_OK;
+	const size_t chunk = (size_t)64 << 20;
+	cudaStream_t cst = ctx->copy_stream;
+	for (int k = 0; k < 2; ++k)
+		if (ctx->h_pool[k].ensure(std::min(bytes, chunk)))
+			return fail(RSK_ERR_NOMEM, "pinned staging buffer");
+	const size_t nchunks = (bytes + chunk - 1) / chunk;
+	std::thread copier;
+	struct Joiner {
+		std::thread &t;
+		~Joiner() { if (t.joinable()) t.join(); }
+	} joiner{copier};
+	for (size_t c = 0; c < nchunks; ++c) {
+		const size_t off = c * chunk, n = std::min(chunk, bytes - off);
+		const int buf = (int)(c & 1);
+		// the memcpy out of this buffer (chunk c-2) was joined one iteration ago; chunk c-1's runs next to this DMA
+		CK(cudaMemcpyAsync(ctx->h_pool[buf].p, src + off, n, cudaMemcpyDeviceToHost, cst));
+		CK(cudaStreamSynchronize(cst));
+		if (copier.joinable())
+			copier.join();
+		const uint8_t *hp = ctx->h_pool[buf].p;
+		char *d = dst + off;
+		copier = std::thread([hp, d, n]() { memcpy(d, hp, n); });
+	}
+	if (copier.joinable())
+		copier.join();
+	ctx->stats.d2h_bytes += bytes;
+	return RSK_OK;
+}
+
+// Read `nrec` sink records (device) and their path pool out to a result object: chunked D2H into pinned staging, conversion
+// to rsk_hit (libm P/E/Qual + the exact emit test) on worker threads while the next chunk is in flight.  pool_base[k] is
+// added to the path offsets of the records of segment k (segments = the ranks' blocks inside a gathered array).
+int sink_to_results(rsk_ctx *ctx, const SinkRec *d_rec, uint64_t nrec, const unsigned char *d_pool, uint64_t npool,
+		const std::vector<uint64_t> &seg_end, const std::vector<uint64_t> &pool_base, const rsk_search_opts &opts, rsk_results **out)
+{
+	rsk_results *res = new rsk_results();
+	struct ResGuard {
+		rsk_results *&r;
+		~ResGuard() { delete r; }
+	} guard{res};
+	const bool keep_all = opts.keep == RSK_KEEP_ALL;
+	res->hits = (rsk_hit *)g_blocks.get(std::max<uint64_t>(1, nrec) * sizeof(rsk_hit), res->hits_cap);
+	if (!res->hits)
+		return fail(RSK_ERR_NOMEM, "host memory for %llu hit records", (unsigned long long)nrec);
+	if (opts.want_paths && npool) {
+		res->paths = (char *)g_blocks.get(npool, res->paths_cap);
+		if (!res->paths)
+			return fail(RSK_ERR_NOMEM, "host memory for %llu path bytes", (unsigned long long)npool);
+	}
+	const size_t chunk = (size_t)1 << 20;  // records per chunk (72 MB)
+	cudaStream_t cst = ctx->copy_stream;
+	std::vector<std::thread> workers;
+	struct Joiner {
+		std::vector<std::thread> &t;
+		~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); }
+	} joiner{workers};
+	std::atomic<uint64_t> dropped{0};
+	const rsk_params *P = &ctx->params;
+	const size_t nchunks = (nrec + chunk - 1) / chunk;
+	for (size_t c = 0; c < nchunks; ++c) {
+		const uint64_t k0 = c * chunk, n = std::min<uint64_t>(chunk, nrec - k0);
+		const int buf = (int)(c & 1);
+		if (ctx->h_sink[buf].ensure(std::min<uint64_t>(chunk, nrec)))
+			return fail(RSK_ERR_NOMEM, "pinned record staging");
+		// the workers of chunk c-1 read the other buffer; those of chunk c-2 (this buffer) were joined one iteration ago
+		CK(cudaMemcpyAsync(ctx->h_sink[buf].p, d_rec + k0, n * sizeof(SinkRec), cudaMemcpyDeviceToHost, cst));
+		CK(cudaStreamSynchronize(cst));
+		for (auto &t : workers)
+			t.join();
+		workers.clear();
+		const SinkRec *hr = ctx->h_sink[buf].p;
+		rsk_hit *hits = res->hits;
+		const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->host_threads, n / 8192 + 1));
+		for (int t = 0; t < T; ++t)
+			workers.emplace_back([=, &dropped, &seg_end, &pool_base]() {
+				const uint64_t i0 = n * (uint64_t)t / T, i1 = n * (uint64_t)(t + 1) / T;
+				size_t seg = 0;
+				uint64_t nd = 0;
+				for (uint64_t i = i0; i < i1; ++i) {
+					const uint64_t k = k0 + i;
+					while (seg + 1 < seg_end.size() && k >= seg_end[seg])
+						++seg;
+					rsk_hit h;
+					fill_hit(*P, hr[i].r, hr[i].a, hr[i].b, pool_base[seg], h);
+					if (!keep_all && !(h.flags & RSK_HIT_REPORTED)) {
+						h.path_len = 0xffffffffu;  // marks a record the exact emit test drops (compacted away below)
+						++nd;
+					}
+					hits[k] = h;
+				}
+				if (nd)
+					dropped += nd;
+			});
+	}
+	for (auto &t : workers)
+		t.join();
+	workers.clear();
+	ctx->stats.d2h_bytes += nrec * sizeof(SinkRec);
+	res->nhits = nrec;
+	if (dropped.load()) {
+		uint64_t w = 0;
+		for (uint64_t k = 0; k < nrec; ++k)
+			if (res->hits[k].path_len != 0xffffffffu)
+				res->hits[w++] = res->hits[k];
+		res->nhits = w;
+	}
+	if (opts.want_paths && npool) {
+		int rc = d2h_staged(ctx, res->paths, d_pool, npool);
+		if (rc)
+			return rc;
+		res->npath = npool;
+	}
+	*out = res;
+	res = nullptr;
+	return RSK_OK;
+}
+
+uint64_t mix64(uint64_t x)
+{
+	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+	x ^= x >> 27; x *= 0x94d049bb133111ebull;
+	x ^= x >> 31;
+	return x;
+}
 }  // namespace
 
 extern "C" int rsk_search_cross(rsk_ctx *ctx, const rsk_chainset *A, const rsk_chainset *B, const rsk_search_opts *opts, rsk_results **out)
@@ -1488,6 +1822,165 @@ extern "C" int rsk_search_cross_device(rsk_ctx *ctx, const rsk_chainset *A, cons
 	SearchPlan plan;
 	plan.A = A; plan.B = B; plan.cross = true;
 	return search_impl(ctx, plan, opts, nullptr, true);
+}
+
+static int build_explicit_plan(SearchPlan &plan, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib, int nthreads, uint32_t mkfl);
+
+static int sink_reset_empty(rsk_ctx *ctx)
+{
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	CK(cudaSetDevice(ctx->device));
+	if (!ctx->sink.h_tot)
+		CK(cudaHostAlloc((void **)&ctx->sink.h_tot, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+	memset(ctx->sink.h_tot, 0, 8 * sizeof(unsigned long long));
+	return RSK_OK;
+}
+
+// Collect the context's hit sink: gather over the communicator (if any) and read out on the root.
+static int sink_finish(rsk_ctx *ctx, rsk_comm *comm, int root, const rsk_search_opts &opts, rsk_results **out)
+{
+	HitSink &K = ctx->sink;
+	const uint64_t nrec = K.h_tot ? K.h_tot[0] : 0, npool = (K.h_tot && opts.want_paths) ? K.h_tot[1] : 0;
+	const int N = comm_nranks(comm), me = comm_rank(comm);
+	if (N == 1) {
+		std::vector<uint64_t> seg_end{nrec}, pool_base{0};
+		int rc = sink_to_results(ctx, K.rec, nrec, K.pool, npool, seg_end, pool_base, opts, out);
+		if (!rc)
+			ctx->stats.hits = (*out)->nhits;
+		return rc;
+	}
+	const unsigned long long mine[kCommCountWords] = {nrec * sizeof(SinkRec), npool, 0, 0};
+	const unsigned long long *all = nullptr;
+	int rc = comm_exchange_counts(comm, mine, &all);
+	if (rc)
+		return rc;
+	std::vector<unsigned long long> bytes((size_t)N * 2);
+	for (int r = 0; r < N; ++r) {
+		bytes[(size_t)r * 2 + 0] = all[(size_t)r * kCommCountWords + 0];
+		bytes[(size_t)r * 2 + 1] = all[(size_t)r * kCommCountWords + 1];
+	}
+	const void *src[2] = {K.rec, K.pool};
+	unsigned char *g[2] = {nullptr, nullptr};
+	unsigned long long gtot[2] = {0, 0};
+	if ((rc = comm_gather_parts(comm, root, 2, src, bytes.data(), g, gtot)))
+		return rc;
+	ctx->stats.hits = nrec;  // this rank's device-compacted records (the exact count is the root's)
+	if (me != root) {
+		*out = nullptr;
+		return RSK_OK;
+	}
+	std::vector<uint64_t> seg_end(N), pool_base(N);
+	uint64_t racc = 0, pacc = 0;
+	for (int r = 0; r < N; ++r) {
+		pool_base[r] = pacc;
+		racc += bytes[(size_t)r * 2 + 0] / sizeof(SinkRec);
+		pacc += bytes[(size_t)r * 2 + 1];
+		seg_end[r] = racc;
+	}
+	rc = sink_to_results(ctx, (const SinkRec *)g[0], racc, g[1], pacc, seg_end, pool_base, opts, out);
+	if (!rc)
+		ctx->stats.hits = (*out)->nhits;
+	return rc;
+}
+
+extern "C" int rsk_search_cross_sharded(rsk_ctx *ctx, rsk_comm *comm, const rsk_chainset *A_local, const rsk_chainset *B, uint32_t a_base,
+		const rsk_search_opts *opts_in, int root, rsk_results **out)
+{
+	if (!ctx || !B || !out)
+		return fail(RSK_ERR_ARG, "rsk_search_cross_sharded: null argument");
+	*out = nullptr;
+	if (comm && comm_ctx(comm) != ctx)
+		return fail(RSK_ERR_ARG, "rsk_search_cross_sharded: the communicator belongs to a different context");
+	if (root < 0 || root >= comm_nranks(comm))
+		return fail(RSK_ERR_ARG, "rsk_search_cross_sharded: root %d of %d ranks", root, comm_nranks(comm));
+	rsk_search_opts opts;
+	memset(&opts, 0, sizeof(opts));
+	if (opts_in)
+		opts = *opts_in;
+	if (A_local && A_local->d.n) {
+		SearchPlan plan;
+		plan.A = A_local; plan.B = B; plan.cross = true;
+		SinkOpts so;
+		so.a_base = a_base;
+		int rc = search_impl(ctx, plan, &opts, nullptr, false, &so);
+		if (rc)
+			return rc;  // NB: the other ranks will wait in the gather; a failing rank is fatal for the job, as a Die() is
+	} else {
+		// an empty block (more ranks than chains): nothing to search, but the rank still takes part in the collective
+		int rc = sink_reset_empty(ctx);
+		if (rc)
+			return rc;
+	}
+	return sink_finish(ctx, comm, root, opts, out);
+}
+
+// Explicit pair list through the hit sink and the gather: PostMuFilter's scan over this rank's share of the candidate list
+// (postmufilter.cpp:185-195).  Hits arrive rank by rank, inside a rank in schedule order (A-major).
+int rsk::search_pairs_sharded(rsk_ctx *ctx, rsk_comm *comm, const rsk_chainset *A, const rsk_chainset *B, uint64_t npairs,
+		const uint32_t *ia, const uint32_t *ib, uint32_t a_base, uint32_t b_base, const rsk_search_opts *opts_in, int root, rsk_results **out)
+{
+	*out = nullptr;
+	rsk_search_opts opts;
+	memset(&opts, 0, sizeof(opts));
+	if (opts_in)
+		opts = *opts_in;
+	int rc;
+	if (npairs && A && B) {
+		SearchPlan plan;
+		if ((rc = build_explicit_plan(plan, A, B, npairs, ia, ib, ctx->host_threads, ctx->params.mkfl)))
+			return rc;
+		SinkOpts so;
+		so.a_base = a_base; so.b_base = b_base;
+		if ((rc = search_impl(ctx, plan, &opts, nullptr, false, &so)))
+			return rc;
+	} else if ((rc = sink_reset_empty(ctx))) {
+		return rc;
+	}
+	return sink_finish(ctx, comm, root, opts, out);
+}
+
+// Order-independent digest: the sum over hits of a hash of the record fields and the path bytes.
+extern "C" uint64_t rsk_results_digest(const rsk_results *r)
+{
+	if (!r || !r->nhits)
+		return 0;
+	const unsigned T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min(32u, std::max(1u, std::thread::hardware_concurrency())), r->nhits >> 14));
+	std::vector<uint64_t> part(T, 0);
+	auto work = [&](unsigned t) {
+		uint64_t acc = 0;
+		const uint64_t k0 = r->nhits * t / T, k1 = r->nhits * (uint64_t)(t + 1) / T;
+		for (uint64_t k = k0; k < k1; ++k) {
+			const rsk_hit &h = r->hits[k];
+			uint32_t w[19];
+			memcpy(w, &h, sizeof(uint32_t) * 19);  // every field up to and including path_len (path_off depends on the layout)
+			uint64_t x = 0x9e3779b97f4a7c15ull;
+			for (int i = 0; i < 19; ++i)
+				x = mix64(x ^ w[i]) + 0x9e3779b97f4a7c15ull * (uint64_t)(i + 1);
+			if (r->paths && h.path_len && h.path_off + h.path_len <= r->npath) {
+				const unsigned char *p = (const unsigned char *)r->paths + h.path_off;
+				uint64_t y = 1469598103934665603ull;
+				for (uint32_t i = 0; i < h.path_len; ++i)
+					y = (y ^ p[i]) * 1099511628211ull;
+				x = mix64(x ^ y);
+			}
+			acc += x;
+		}
+		part[t] = acc;
+	};
+	if (T == 1) {
+		work(0);
+	} else {
+		std::vector<std::thread> th;
+		for (unsigned t = 0; t < T; ++t)
+			th.emplace_back(work, t);
+		for (auto &t : th)
+			t.join();
+	}
+	uint64_t d = 0;
+	for (uint64_t v : part)
+		d += v;
+	return d;
 }
 
 // Explicit pair lists are scheduled a-major with the longest B first inside every run of equal A (the chains of one task

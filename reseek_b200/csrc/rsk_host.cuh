@@ -97,6 +97,28 @@ struct PinBuf {
 	}
 };
 
+// Device hit sink of a search call (sink_kernel.cu): compacted records + paths of all batches, grow-only, content preserved
+// when it grows.
+struct HitSink {
+	SinkRec *rec = nullptr; size_t rec_cap = 0;    // elements
+	uint8_t *pool = nullptr; size_t pool_cap = 0;  // bytes
+	DevBuf<uint32_t> keep, plen, keep_scan;
+	DevBuf<unsigned long long> plen_scan;
+	DevBuf<uint8_t> tmp;
+	unsigned long long *d_tot = nullptr;           // [4] records, path bytes, pairs with E-value, Mu-rejected pairs
+	unsigned long long *h_tot = nullptr;           // pinned [2][4]: totals after the batches of either batch set
+	void release()
+	{
+		if (rec) cudaFree(rec);
+		if (pool) cudaFree(pool);
+		rec = nullptr; pool = nullptr; rec_cap = pool_cap = 0;
+		keep.release(); plen.release(); keep_scan.release(); plen_scan.release(); tmp.release();
+		if (d_tot) cudaFree(d_tot);
+		if (h_tot) cudaFreeHost(h_tot);
+		d_tot = nullptr; h_tot = nullptr;
+	}
+};
+
 struct rsk_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -166,6 +188,8 @@ struct rsk_ctx {
 		std::swap(filt_explicit_pairs, alt.filt_explicit_pairs);
 		std::swap(filt_explicit_cells, alt.filt_explicit_cells);
 	}
+	HitSink sink;
+	PinBuf<SinkRec> h_sink[2];  // pinned staging of the sink read-out (chunked, double-buffered)
 	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU
 	PinBuf<uint8_t> h_pool[2];
 	int host_threads = 1;

@@ -44,6 +44,28 @@ struct PairRec {
 };
 static_assert(sizeof(PairRec) == 64, "PairRec layout");
 
+// Device hit sink (sink_kernel.cu): a kept record with its chain indices in the numbering of the whole (unsharded) search.
+struct SinkRec {
+	PairRec r;        // path_off re-based to the sink's path pool
+	uint32_t a, b;
+};
+static_assert(sizeof(SinkRec) == 72, "SinkRec layout");
+struct SinkArgs {
+	const PairRec *rec; uint32_t npairs;       // the batch
+	const uint8_t *pool;                       // the batch's path pool
+	uint32_t cross, a_begin, nB;               // cross: pair k = (a_begin + k / nB, k % nB); else pair_a/pair_b
+	const uint32_t *pair_a, *pair_b;
+	uint32_t a_base, b_base;                   // added to the local chain indices (this rank's block of the sharded side)
+	uint32_t keep_all, want_paths, report_no_evalue;
+	float ts_lo;                               // conservative emit test: TS >= ts_lo (the root re-applies the exact E-value test)
+	uint32_t *keep, *plen, *keep_scan;         // [npairs] scratch
+	unsigned long long *plen_scan;             // [npairs] scratch
+	SinkRec *out_rec; uint8_t *out_pool;
+	unsigned long long *totals;                // [4] device: records, path bytes, pairs with E-value, Mu-rejected pairs
+};
+size_t sink_scan_tmp_bytes(uint32_t npairs);
+int launch_sink_append(const SinkArgs &a, void *tmp, size_t tmp_bytes, cudaStream_t st);
+
 // ---- SW kernel geometry ----
 constexpr int kSwWarps = 16;                 // warps per CTA of the Mu filter kernel
 constexpr int kSwThreads = kSwWarps * 32;
@@ -259,7 +281,10 @@ struct PfArgs {
 	uint32_t *hit_key; const uint32_t *hit_sorted;
 	unsigned *best;              // [ntl * nQ] best two-hit diagonal score per (target, query), 0 = none
 	uint32_t *cand_count; const unsigned long long *cand_off;
-	uint32_t *cand_t, *cand_q; uint16_t *cand_s;
+	// (target, query, score) triples with a two-hit diagonal, accumulated over the target batches in stream order
+	uint32_t t_base;             // index of this rank's first target in the whole DB
+	unsigned long long raw_base; // triples written by the earlier batches
+	uint32_t *raw_q; unsigned long long *raw_v;  // query, target<<16 | score
 };
 int pf_launch_swap_kl(const uint8_t *in, uint8_t *out, uint64_t n, cudaStream_t st);
 int pf_launch_query_kmers(const PfArgs &a, cudaStream_t st);
@@ -268,6 +293,18 @@ int pf_launch_mark_rows(const uint32_t *key, unsigned long long n, uint32_t *row
 int pf_launch_probe(const PfArgs &a, uint32_t ntl, bool fill, cudaStream_t st);
 int pf_launch_extend(const PfArgs &a, uint32_t ntl, cudaStream_t st);
 int pf_launch_cands(const PfArgs &a, uint32_t ntl, bool write, cudaStream_t st);
+size_t pf_bag_smem_bytes(uint32_t B);
+int pf_sort_by_query(const uint32_t *qin, uint32_t *qout, const unsigned long long *vin, unsigned long long *vout, unsigned long long n,
+		void *tmp, size_t &tmp_bytes, cudaStream_t st);
+int pf_sort_keys64(const unsigned long long *kin, unsigned long long *kout, unsigned long long n, void *tmp, size_t &tmp_bytes, cudaStream_t st);
+int pf_launch_mark_segments(const uint32_t *key, unsigned long long n, unsigned long long *seg_begin, unsigned long long *seg_end, cudaStream_t st);
+int pf_launch_bag(const unsigned long long *val, const unsigned long long *seg_begin, const unsigned long long *seg_end, uint32_t nQ, uint32_t B,
+		unsigned long long *out_key, uint32_t *out_n, cudaStream_t st);
+int pf_launch_bag_compact(const unsigned long long *key, const uint32_t *out_n, const unsigned long long *out_off, uint32_t nQ, uint32_t B,
+		unsigned long long *dense, cudaStream_t st);
+int pf_launch_unpack_triples(const uint32_t *q, const unsigned long long *v, unsigned long long n, uint32_t *t_out, uint32_t *q_out,
+		uint16_t *s_out, cudaStream_t st);
+int pf_launch_unpack_keys(const unsigned long long *key, unsigned long long n, uint32_t *t_out, uint32_t *q_out, uint16_t *s_out, cudaStream_t st);
 int pf_sort_pairs(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, unsigned long long n, void *tmp,
 		size_t &tmp_bytes, cudaStream_t st);
 int pf_segmented_sort(const uint32_t *kin, uint32_t *kout, unsigned long long n, uint32_t nseg, const unsigned long long *off,

@@ -12,6 +12,7 @@
 #include <thread>
 
 #include "rsk_host.cuh"
+#include "rsk_multi.cuh"
 
 struct rsk_prefilter_result {
 	std::vector<uint32_t> t, q;
@@ -151,6 +152,8 @@ struct PfScratch {
 	DevBuf<uint32_t> hit_key, hit_sorted, cand_count, cand_t, cand_q;
 	DevBuf<unsigned> best;
 	DevBuf<uint16_t> cand_s;
+	DevBuf<uint32_t> raw_q, srt_q, bag_n;
+	DevBuf<unsigned long long> raw_v, srt_v, seg_begin, seg_end, bag_key, bag_off, dense_a, dense_b;
 	int *kmer_mx = nullptr;
 	~PfScratch()
 	{
@@ -158,6 +161,8 @@ struct PfScratch {
 		key_a.release(); key_b.release(); val_a.release(); val_b.release(); row_start.release(); row_end.release();
 		nb_off.release(); hit_count.release(); hit_off.release(); cand_off.release(); hit_key.release();
 		hit_sorted.release(); cand_count.release(); cand_t.release(); cand_q.release(); best.release(); cand_s.release();
+		raw_q.release(); srt_q.release(); bag_n.release(); raw_v.release(); srt_v.release(); seg_begin.release(); seg_end.release();
+		bag_key.release(); bag_off.release(); dense_a.release(); dense_b.release();
 		if (kmer_mx)
 			cudaFree(kmer_mx);
 	}
@@ -194,54 +199,70 @@ struct PhaseTimer {
 			return fail(RSK_ERR_NOMEM, "rsk_prefilter: out of device memory (%s)", #x); \
 	} while (0)
 
-}  // namespace
-
-extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *opts_in,
-		rsk_prefilter_result **out)
+// grow a device array to `need` elements keeping its first `used` elements (stream-ordered copy, then the old block is freed)
+template <typename T>
+int grow_keep(DevBuf<T> &b, size_t need, size_t used, cudaStream_t st)
 {
-	if (!ctx || !Q || !T || !out)
-		return fail(RSK_ERR_ARG, "rsk_prefilter: null argument");
-	*out = nullptr;
-	if (Q->ctx != ctx || T->ctx != ctx)
-		return fail(RSK_ERR_ARG, "rsk_prefilter: chain sets belong to a different context");
-	if (!Q->has_mu || !T->has_mu)
-		return fail(RSK_ERR_ARG, "rsk_prefilter: both chain sets need Mu letters");
-	rsk_prefilter_opts o = {};
-	if (opts_in)
-		o = *opts_in;
-	const uint32_t B = o.rsb_size ? o.rsb_size : 1500u;
-	const uint32_t nQ = Q->d.n, nT = T->d.n;
-	if (nQ >= (1u << 16))
-		return fail(RSK_ERR_LIMIT, "rsk_prefilter: at most 65535 queries per call (got %u); split the query set", nQ);
-	if (Q->maxlen > 0xffffu)
-		return fail(RSK_ERR_LIMIT, "rsk_prefilter: query chains are limited to 65535 residues (uint16 position, mudex.h:19-49)");
-	// <= 100 queries: neighbourhoods go into the query index and exact k-mers are therefore entered twice (mudex.cpp:146-174)
-	const bool qhood = o.index_mode == 1 || (o.index_mode == 0 && nQ <= 100);
-	CK(cudaSetDevice(ctx->device));
-	cudaStream_t st = ctx->stream;
-	uint64_t launches = 0;
-	auto *res = new rsk_prefilter_result();
-	std::unique_ptr<rsk_prefilter_result> guard(res);
-	if (nQ == 0 || nT == 0) {
-		*out = guard.release();
-		return RSK_OK;
+	if (need <= b.cap)
+		return 0;
+	const size_t want = std::max(need, 2 * b.cap) + 1024;
+	T *p = nullptr;
+	if (cudaMalloc((void **)&p, want * sizeof(T)) != cudaSuccess) {
+		cudaGetLastError();
+		return -1;
 	}
+	if (b.p && used) {
+		if (cudaMemcpyAsync(p, b.p, used * sizeof(T), cudaMemcpyDeviceToDevice, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+			cudaFree(p);
+			return -1;
+		}
+	}
+	if (b.p)
+		cudaFree(b.p);
+	b.p = p;
+	b.cap = want;
+	return 0;
+}
+
+PfScratch &pf_scratch(rsk_ctx *ctx)
+{
 	// grow-only device scratch kept in the context: a streamed database calls this once per block of targets
 	if (!ctx->pf_scratch) {
 		ctx->pf_scratch = new PfScratch();
 		ctx->pf_scratch_free = [](void *p) { delete static_cast<PfScratch *>(p); };
 	}
-	PfScratch &S = *static_cast<PfScratch *>(ctx->pf_scratch);
+	return *static_cast<PfScratch *>(ctx->pf_scratch);
+}
+
+// K6..K8 over all targets of T.  The (target, query, score) triples with a two-hit diagonal stay ON THE DEVICE, in stream
+// order (targets ascending), as S.raw_q[k] / S.raw_v[k] = target<<16 | score with target numbered from t_base.
+int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts &o, uint32_t t_base,
+		unsigned long long &nraw, uint64_t &launches)
+{
+	nraw = 0;
+	const uint32_t nQ = Q->d.n, nT = T ? T->d.n : 0;
+	if (nQ >= (1u << 16))
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter: at most 65535 queries per call (got %u); split the query set", nQ);
+	if (Q->maxlen > 0xffffu)
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter: query chains are limited to 65535 residues (uint16 position, mudex.h:19-49)");
+	if ((uint64_t)t_base + nT > 0xffffffffull)
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter: target index exceeds 32 bits");
+	if (nQ == 0 || nT == 0)
+		return RSK_OK;
+	// <= 100 queries: neighbourhoods go into the query index and exact k-mers are therefore entered twice (mudex.cpp:146-174)
+	const bool qhood = o.index_mode == 1 || (o.index_mode == 0 && nQ <= 100);
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	PfScratch &S = pf_scratch(ctx);
 	PfArgs a = {};
 	PhaseTimer tm;
 	tm.st = st;
-	{
+	if (!S.kmer_mx) {
 		std::vector<int> mx(36 * 36);
 		const int8_t *m8 = rsk_mu_kmer_matrix_i8();
 		for (int k = 0; k < 36 * 36; ++k)
 			mx[k] = m8[k];
-		if (!S.kmer_mx)
-			CK(cudaMalloc((void **)&S.kmer_mx, sizeof(int) * 36 * 36));
+		CK(cudaMalloc((void **)&S.kmer_mx, sizeof(int) * 36 * 36));
 		CK(cudaMemcpyAsync(S.kmer_mx, mx.data(), sizeof(int) * 36 * 36, cudaMemcpyHostToDevice, st));
 		CK(cudaStreamSynchronize(st));
 	}
@@ -250,6 +271,7 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 	a.offQ = Q->d.off; a.lenQ = Q->d.len;
 	a.muT = T->d.mu; a.offT = T->d.off; a.lenT = T->d.len;
 	a.exact_twice = qhood ? 1u : 0u;
+	a.t_base = t_base;
 	// query letters, K/L exchanged unless told otherwise
 	if (!o.no_kl_swap) {
 		NOMEM(S.muq.ensure(Q->d.total));
@@ -311,25 +333,23 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 	}
 	a.row_start = S.row_start.p; a.row_end = S.row_end.p;
 	tm.mark("K6 query index");
+	if (!nindex)
+		return RSK_OK;
 
 	// ---- K7 count pass over all targets, then batches sized by hits ----
-	std::vector<Bag> bags(nQ);
 	std::vector<unsigned long long> hcnt(nT, 0);
-	if (nindex) {
-		NOMEM(S.hit_count.ensure(nT));
-		a.t_begin = 0;
-		a.hit_count = S.hit_count.p;
-		PFL(pf_launch_probe(a, nT, false, st));
-		CK(cudaMemcpyAsync(hcnt.data(), S.hit_count.p, sizeof(unsigned long long) * nT, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-	}
+	NOMEM(S.hit_count.ensure(nT));
+	a.t_begin = 0;
+	a.hit_count = S.hit_count.p;
+	PFL(pf_launch_probe(a, nT, false, st));
+	CK(cudaMemcpyAsync(hcnt.data(), S.hit_count.p, sizeof(unsigned long long) * nT, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
 	tm.mark("K7 count pass");
 	const unsigned long long kMaxHits = 1ull << 28;              // 1 GB of keys + 1 GB sorted per batch
 	const uint32_t kMaxT = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(1u << 16, ((uint64_t)1 << 26) / nQ));
 	std::vector<unsigned long long> hoff, coff;
-	std::vector<uint32_t> ccnt, ct, cq;
-	std::vector<uint16_t> cs;
-	for (uint32_t t0 = 0; nindex && t0 < nT;) {
+	std::vector<uint32_t> ccnt;
+	for (uint32_t t0 = 0; t0 < nT;) {
 		uint32_t t1 = t0;
 		unsigned long long tot = 0;
 		while (t1 < nT && t1 - t0 < kMaxT && (t1 == t0 || tot + hcnt[t1] <= kMaxHits))
@@ -375,41 +395,144 @@ extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chai
 			coff[k + 1] = coff[k] + ccnt[k];
 		const unsigned long long nc = coff[ntl];
 		if (nc) {
-			NOMEM(S.cand_t.ensure(nc));
-			NOMEM(S.cand_q.ensure(nc));
-			NOMEM(S.cand_s.ensure(nc));
-			CK(cudaMemcpyAsync(S.cand_off.p, coff.data(), sizeof(unsigned long long) * (ntl + 1), cudaMemcpyHostToDevice, st));
-			a.cand_t = S.cand_t.p; a.cand_q = S.cand_q.p; a.cand_s = S.cand_s.p;
-			PFL(pf_launch_cands(a, ntl, true, st));
-			ct.resize(nc); cq.resize(nc); cs.resize(nc);
-			CK(cudaMemcpyAsync(ct.data(), S.cand_t.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToHost, st));
-			CK(cudaMemcpyAsync(cq.data(), S.cand_q.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToHost, st));
-			CK(cudaMemcpyAsync(cs.data(), S.cand_s.p, sizeof(uint16_t) * nc, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
 			// stream order of the reference at -threads 1: targets ascending (AddTwoHitDiag -> AddScore, prefiltermu.cpp:288-313)
-			if (o.raw_only) {
-				res->t.insert(res->t.end(), ct.begin(), ct.end());
-				res->q.insert(res->q.end(), cq.begin(), cq.end());
-				res->s.insert(res->s.end(), cs.begin(), cs.end());
-			} else {
-				feed_bags(bags, B, ct.data(), cq.data(), cs.data(), nc, ctx->host_threads);
-			}
-			res->raw += nc;
+			NOMEM(grow_keep(S.raw_q, nraw + nc, nraw, st));
+			NOMEM(grow_keep(S.raw_v, nraw + nc, nraw, st));
+			CK(cudaMemcpyAsync(S.cand_off.p, coff.data(), sizeof(unsigned long long) * (ntl + 1), cudaMemcpyHostToDevice, st));
+			a.raw_base = nraw; a.raw_q = S.raw_q.p; a.raw_v = S.raw_v.p;
+			PFL(pf_launch_cands(a, ntl, true, st));
+			CK(cudaStreamSynchronize(st));  // coff is reused by the next batch
+			nraw += nc;
 		}
-		tm.mark("candidates D2H + bag");
+		tm.mark("triples");
 		t0 = t1;
 	}
+	return RSK_OK;
+}
+
+// RankedScoresBag over device triples in stream order (pf_bag_kernel): stable sort by query, one warp per query replays
+// AddScore / TruncateVecs, the surviving entries are sorted (target, query) ascending and only that candidate list is read
+// back (rankedscoresbag.cpp:185-232).
+int bag_device(rsk_ctx *ctx, uint32_t nQ, uint32_t B, const uint32_t *d_q, const unsigned long long *d_v, unsigned long long n,
+		rsk_prefilter_result &res, uint64_t &launches)
+{
+	res.raw = n;
+	if (n == 0 || nQ == 0)
+		return RSK_OK;
+	if (pf_bag_smem_bytes(B) > 220 * 1024)
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter: -rsb_size %u exceeds the bag kernel's shared memory (max ~8000)", B);
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	PfScratch &S = pf_scratch(ctx);
+	PhaseTimer tm;
+	tm.st = st;
+	NOMEM(S.srt_q.ensure(n));
+	NOMEM(S.srt_v.ensure(n));
+	NOMEM(S.seg_begin.ensure(nQ));
+	NOMEM(S.seg_end.ensure(nQ));
+	NOMEM(S.bag_key.ensure((size_t)nQ * B));
+	NOMEM(S.bag_n.ensure(nQ));
+	NOMEM(S.bag_off.ensure(nQ + 1));
+	size_t tb = 0;
+	if (pf_sort_by_query(d_q, S.srt_q.p, d_v, S.srt_v.p, n, nullptr, tb, st))
+		return fail(RSK_ERR_CUDA, "rsk_prefilter: cub sort sizing failed");
+	NOMEM(S.tmp.ensure(tb));
+	if (pf_sort_by_query(d_q, S.srt_q.p, d_v, S.srt_v.p, n, S.tmp.p, tb, st))
+		return fail(RSK_ERR_CUDA, "rsk_prefilter: sort by query failed: %s", cudaGetErrorString(cudaGetLastError()));
+	launches += 3;
+	CK(cudaMemsetAsync(S.seg_begin.p, 0, sizeof(unsigned long long) * nQ, st));
+	CK(cudaMemsetAsync(S.seg_end.p, 0, sizeof(unsigned long long) * nQ, st));
+	PFL(pf_launch_mark_segments(S.srt_q.p, n, S.seg_begin.p, S.seg_end.p, st));
+	PFL(pf_launch_bag(S.srt_v.p, S.seg_begin.p, S.seg_end.p, nQ, B, S.bag_key.p, S.bag_n.p, st));
+	std::vector<uint32_t> bn(nQ);
+	CK(cudaMemcpyAsync(bn.data(), S.bag_n.p, sizeof(uint32_t) * nQ, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	tm.mark("bag (device)");
+	std::vector<unsigned long long> off(nQ + 1, 0);
+	for (uint32_t q = 0; q < nQ; ++q)
+		off[q + 1] = off[q] + bn[q];
+	const unsigned long long tot = off[nQ];
+	if (tot == 0)
+		return RSK_OK;
+	NOMEM(S.dense_a.ensure(tot));
+	NOMEM(S.dense_b.ensure(tot));
+	NOMEM(S.cand_t.ensure(tot));
+	NOMEM(S.cand_q.ensure(tot));
+	NOMEM(S.cand_s.ensure(tot));
+	CK(cudaMemcpyAsync(S.bag_off.p, off.data(), sizeof(unsigned long long) * (nQ + 1), cudaMemcpyHostToDevice, st));
+	PFL(pf_launch_bag_compact(S.bag_key.p, S.bag_n.p, S.bag_off.p, nQ, B, S.dense_a.p, st));
+	tb = 0;
+	if (pf_sort_keys64(S.dense_a.p, S.dense_b.p, tot, nullptr, tb, st))
+		return fail(RSK_ERR_CUDA, "rsk_prefilter: cub sort sizing failed");
+	NOMEM(S.tmp.ensure(tb));
+	if (pf_sort_keys64(S.dense_a.p, S.dense_b.p, tot, S.tmp.p, tb, st))
+		return fail(RSK_ERR_CUDA, "rsk_prefilter: candidate sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+	launches += 8;
+	PFL(pf_launch_unpack_keys(S.dense_b.p, tot, S.cand_t.p, S.cand_q.p, S.cand_s.p, st));
+	res.t.resize(tot); res.q.resize(tot); res.s.resize(tot);
+	CK(cudaMemcpyAsync(res.t.data(), S.cand_t.p, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(res.q.data(), S.cand_q.p, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(res.s.data(), S.cand_s.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.d2h_bytes += tot * 10 + nQ * 4;
+	uint32_t nt = 0;
+	for (size_t k = 0; k < res.t.size(); ++k)
+		nt += (k == 0 || res.t[k] != res.t[k - 1]);
+	res.ntargets = nt;
+	tm.mark("candidate list D2H");
+	return RSK_OK;
+}
+
+}  // namespace
+
+extern "C" int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, const rsk_prefilter_opts *opts_in,
+		rsk_prefilter_result **out)
+{
+	if (!ctx || !Q || !T || !out)
+		return fail(RSK_ERR_ARG, "rsk_prefilter: null argument");
+	*out = nullptr;
+	if (Q->ctx != ctx || T->ctx != ctx)
+		return fail(RSK_ERR_ARG, "rsk_prefilter: chain sets belong to a different context");
+	if (!Q->has_mu || !T->has_mu)
+		return fail(RSK_ERR_ARG, "rsk_prefilter: both chain sets need Mu letters");
+	rsk_prefilter_opts o = {};
+	if (opts_in)
+		o = *opts_in;
+	const uint32_t B = o.rsb_size ? o.rsb_size : 1500u;
+	uint64_t launches = 0;
+	std::unique_ptr<rsk_prefilter_result> res(new rsk_prefilter_result());
+	unsigned long long nraw = 0;
+	int rc = prefilter_raw_device(ctx, Q, T, o, 0, nraw, launches);
+	if (rc)
+		return rc;
+	PfScratch &S = pf_scratch(ctx);
+	cudaStream_t st = ctx->stream;
 	if (o.raw_only) {
+		// every triple, stream order (tests, and callers that merge blocks themselves)
+		res->raw = nraw;
+		if (nraw) {
+			NOMEM(S.cand_t.ensure(nraw));
+			NOMEM(S.cand_q.ensure(nraw));
+			NOMEM(S.cand_s.ensure(nraw));
+			PFL(pf_launch_unpack_triples(S.raw_q.p, S.raw_v.p, nraw, S.cand_t.p, S.cand_q.p, S.cand_s.p, st));
+			res->t.resize(nraw); res->q.resize(nraw); res->s.resize(nraw);
+			CK(cudaMemcpyAsync(res->t.data(), S.cand_t.p, sizeof(uint32_t) * nraw, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(res->q.data(), S.cand_q.p, sizeof(uint32_t) * nraw, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(res->s.data(), S.cand_s.p, sizeof(uint16_t) * nraw, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			ctx->stats.d2h_bytes += nraw * 10;
+		}
 		uint32_t nt = 0;
 		for (size_t k = 0; k < res->t.size(); ++k)
 			nt += (k == 0 || res->t[k] != res->t[k - 1]);
 		res->ntargets = nt;
 	} else {
-		finish_bags(bags, B, *res, ctx->host_threads);
+		rc = bag_device(ctx, Q->d.n, B, S.raw_q.p, S.raw_v.p, nraw, *res, launches);
+		if (rc)
+			return rc;
 	}
-	tm.mark("finish bags");
 	ctx->stats.kernel_launches += launches;
-	*out = guard.release();
+	*out = res.release();
 	return RSK_OK;
 }
 
@@ -499,7 +622,7 @@ extern "C" int rsk_postfilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_cha
 	rsk_params p = saved;
 	p.omega = sens.omega; p.omega_fwd = sens.omega_fwd; p.mkfl = sens.mkfl; p.min_fwd_score = sens.min_fwd_score;
 	p.mkf_x1 = sens.mkf_x1; p.mkf_x2 = sens.mkf_x2; p.mkf_min_hsp_score = sens.mkf_min_hsp_score;
-	p.mkf_min_mega_hsp_score = sens.mkf_min_mega_hsp_score; p.max_evalue = sens.max_evalue;
+	p.mkf_min_mega_hsp_score = sens.mkf_min_mega_hsp_score;  // max_evalue stays the caller's: -evalue is honoured (postmufilter.cpp:217-220)
 	rc = rsk_ctx_set_params(ctx, &p);
 	if (rc)
 		return rc;
@@ -524,4 +647,88 @@ extern "C" int rsk_search_fast_db(rsk_ctx *ctx, const rsk_chainset *Q, const rsk
 	ctx->stats.kernel_launches += launches;  // the search call restarts the counters; keep the prefilter's launches in the sum
 	rsk_prefilter_free(pf);
 	return rc;
+}
+
+// `-search Q -db DB -fast` on a block-partitioned DB (include/reseek_b200.h).  Exchange steps: the triples of the blocks are
+// all-gathered in rank order over NCCL (device to device), every rank replays the bag on the merged stream (same result on
+// every rank, equal to the unsharded one), post-filters the candidates of its own block and the hits are gathered on root.
+extern "C" int rsk_search_fast_db_sharded(rsk_ctx *ctx, rsk_comm *comm, const rsk_chainset *Q, const rsk_chainset *T_local, uint32_t t_base,
+		const rsk_prefilter_opts *popts, const rsk_search_opts *opts, int root, rsk_results **out, rsk_prefilter_result **cands_out)
+{
+	if (!ctx || !Q || !out)
+		return fail(RSK_ERR_ARG, "rsk_search_fast_db_sharded: null argument");
+	*out = nullptr;
+	if (cands_out)
+		*cands_out = nullptr;
+	if (comm && comm_ctx(comm) != ctx)
+		return fail(RSK_ERR_ARG, "rsk_search_fast_db_sharded: the communicator belongs to a different context");
+	if (Q->ctx != ctx || (T_local && T_local->ctx != ctx))
+		return fail(RSK_ERR_ARG, "rsk_search_fast_db_sharded: chain sets belong to a different context");
+	if (!Q->has_mu || (T_local && !T_local->has_mu))
+		return fail(RSK_ERR_ARG, "rsk_search_fast_db_sharded: both chain sets need Mu letters");
+	rsk_prefilter_opts o = {};
+	if (popts)
+		o = *popts;
+	const uint32_t B = o.rsb_size ? o.rsb_size : 1500u;
+	const uint32_t nT = T_local ? T_local->d.n : 0;
+	uint64_t launches = 0;
+	unsigned long long nraw = 0;
+	int rc = prefilter_raw_device(ctx, Q, T_local, o, t_base, nraw, launches);
+	if (rc)
+		return rc;
+	PfScratch &S = pf_scratch(ctx);
+	std::unique_ptr<rsk_prefilter_result> merged(new rsk_prefilter_result());
+	const int N = comm_nranks(comm);
+	if (N == 1) {
+		rc = bag_device(ctx, Q->d.n, B, S.raw_q.p, S.raw_v.p, nraw, *merged, launches);
+	} else {
+		const unsigned long long mine[kCommCountWords] = {nraw * sizeof(uint32_t), nraw * sizeof(unsigned long long), 0, 0};
+		const unsigned long long *all = nullptr;
+		if ((rc = comm_exchange_counts(comm, mine, &all)))
+			return rc;
+		std::vector<unsigned long long> bytes((size_t)N * 2);
+		for (int r = 0; r < N; ++r) {
+			bytes[(size_t)r * 2 + 0] = all[(size_t)r * kCommCountWords + 0];
+			bytes[(size_t)r * 2 + 1] = all[(size_t)r * kCommCountWords + 1];
+		}
+		const void *src[2] = {S.raw_q.p, S.raw_v.p};
+		unsigned char *g[2] = {nullptr, nullptr};
+		unsigned long long gtot[2] = {0, 0};
+		if ((rc = comm_allgather_parts(comm, 2, src, bytes.data(), g, gtot)))
+			return rc;
+		rc = bag_device(ctx, Q->d.n, B, (const uint32_t *)g[0], (const unsigned long long *)g[1], gtot[0] / sizeof(uint32_t), *merged, launches);
+	}
+	if (rc)
+		return rc;
+	// this rank's share of the candidate lines, targets re-based to the block
+	std::vector<uint32_t> lq, lt;
+	for (size_t k = 0; k < merged->t.size(); ++k)
+		if (merged->t[k] >= t_base && merged->t[k] - t_base < nT) {
+			lq.push_back(merged->q[k]);
+			lt.push_back(merged->t[k] - t_base);
+		}
+	// DM_AlwaysSensitive (search.cpp:106-108), as in rsk_postfilter
+	const rsk_params saved = ctx->params;
+	rsk_params sens;
+	if ((rc = rsk_params_preset(&sens, RSK_MODE_SENSITIVE)))
+		return rc;
+	rsk_params p = saved;
+	p.omega = sens.omega; p.omega_fwd = sens.omega_fwd; p.mkfl = sens.mkfl; p.min_fwd_score = sens.min_fwd_score;
+	p.mkf_x1 = sens.mkf_x1; p.mkf_x2 = sens.mkf_x2; p.mkf_min_hsp_score = sens.mkf_min_hsp_score;
+	p.mkf_min_mega_hsp_score = sens.mkf_min_mega_hsp_score;
+	if ((rc = rsk_ctx_set_params(ctx, &p)))
+		return rc;
+	rc = search_pairs_sharded(ctx, comm, Q, T_local, lq.size(), lq.data(), lt.data(), 0, t_base, opts, root, out);
+	const int rc2 = rsk_ctx_set_params(ctx, &saved);
+	ctx->stats.kernel_launches += launches;
+	if (rc || rc2) {
+		if (*out) {
+			rsk_results_free(*out);
+			*out = nullptr;
+		}
+		return rc ? rc : rc2;
+	}
+	if (cands_out)
+		*cands_out = merged.release();
+	return RSK_OK;
 }

@@ -58,6 +58,15 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CommStats(C.Structure):
+    _fields_ = [("bytes_sent", C.c_uint64), ("bytes_recv", C.c_uint64), ("collective_ms", C.c_float), ("collectives", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+COMM_ID_BYTES = 128
+
 # numpy view of rsk_hit (include/reseek_b200.h)
 HIT_DTYPE = np.dtype([
     ("a", np.uint32), ("b", np.uint32), ("score", np.float32), ("lo_a", np.uint32), ("lo_b", np.uint32),
@@ -140,6 +149,22 @@ def load_library():
     L.rsk_postfilter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
     L.rsk_search_fast_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrefilterOpts), C.POINTER(SearchOpts),
                                      C.POINTER(C.c_void_p)]
+    L.rsk_comm_unique_id.argtypes = [C.c_void_p]
+    L.rsk_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rsk_comm_create_all.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+    L.rsk_comm_destroy.argtypes = [C.c_void_p]
+    L.rsk_comm_destroy.restype = None
+    L.rsk_comm_rank.argtypes = [C.c_void_p]
+    L.rsk_comm_nranks.argtypes = [C.c_void_p]
+    L.rsk_comm_get_stats.argtypes = [C.c_void_p, C.POINTER(CommStats)]
+    L.rsk_comm_reset_stats.argtypes = [C.c_void_p]
+    L.rsk_partition_by_residues.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+    L.rsk_search_cross_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(SearchOpts),
+                                           C.c_int, C.POINTER(C.c_void_p)]
+    L.rsk_search_fast_db_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PrefilterOpts),
+                                             C.POINTER(SearchOpts), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.rsk_results_digest.argtypes = [C.c_void_p]
+    L.rsk_results_digest.restype = C.c_uint64
     _lib = L
     return L
 
@@ -268,6 +293,87 @@ class Results:
 
     def __len__(self):
         return len(self.hits)
+
+    def digest(self):
+        """Order-independent 64-bit digest of records + paths (rsk_results_digest)."""
+        return int(load_library().rsk_results_digest(self._handle))
+
+
+def partition_by_residues(lens, nranks):
+    """Contiguous blocks with (nearly) equal residue totals (rsk_partition_by_residues): list of (lo, hi) per rank."""
+    lens = np.ascontiguousarray(lens, np.uint32)
+    b = np.zeros(nranks + 1, np.uint32)
+    _check(load_library().rsk_partition_by_residues(_ptr(lens), len(lens), int(nranks), _ptr(b)))
+    return [(int(b[r]), int(b[r + 1])) for r in range(nranks)]
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(load_library().rsk_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """One rank's communicator (NCCL over NVLink) for the DB-sharded searches; nranks == 1 needs no id."""
+
+    def __init__(self, ctx, nranks=1, rank=0, unique_id=None, handle=None):
+        self.ctx = ctx
+        if handle is not None:
+            self.handle = handle
+            return
+        self.handle = C.c_void_p()
+        idbuf = C.create_string_buffer(unique_id, COMM_ID_BYTES) if unique_id is not None else None
+        _check(load_library().rsk_comm_create(ctx.handle, int(nranks), int(rank), idbuf, C.byref(self.handle)))
+
+    @classmethod
+    def from_torch_dist(cls, ctx, dist):
+        """Rank/size from an initialised torch.distributed group; the NCCL id is made on rank 0 and broadcast through it."""
+        import torch
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world == 1:
+            return cls(ctx, 1, 0)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(ctx, world, rank, bytes(t.cpu().numpy().tobytes()))
+
+    @classmethod
+    def create_all(cls, ctxs):
+        """One process driving several GPUs: communicators for contexts on different devices (ncclCommInitAll)."""
+        n = len(ctxs)
+        arr = (C.c_void_p * n)(*[c.handle for c in ctxs])
+        out = (C.c_void_p * n)()
+        _check(load_library().rsk_comm_create_all(arr, n, out))
+        return [cls(ctxs[k], handle=C.c_void_p(out[k])) for k in range(n)]
+
+    @property
+    def rank(self):
+        return load_library().rsk_comm_rank(self.handle)
+
+    @property
+    def nranks(self):
+        return load_library().rsk_comm_nranks(self.handle)
+
+    def stats(self):
+        s = CommStats()
+        _check(load_library().rsk_comm_get_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        _check(load_library().rsk_comm_reset_stats(self.handle))
+
+    def close(self):
+        if self.handle:
+            load_library().rsk_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PrefilterResult:
@@ -458,6 +564,29 @@ class Context:
         r = C.c_void_p()
         _check(load_library().rsk_search_fast_db(self.handle, Q.handle, T.handle, C.byref(po), C.byref(o), C.byref(r)))
         return Results(r)
+
+    def search_cross_sharded(self, comm, A_local, B, a_base, keep=KEEP_HITS, want_paths=True, root=0, skip_evalue=False):
+        """DBSearcher::RunQuery over this rank's block of the -db chains (rsk_search_cross_sharded): hits compacted on the
+        device and gathered on `root` over NVLink; returns Results on the root, None elsewhere.  comm=None: one rank."""
+        o = self._opts(keep, want_paths, skip_evalue)
+        r = C.c_void_p()
+        _check(load_library().rsk_search_cross_sharded(self.handle, comm.handle if comm else None,
+                                                        A_local.handle if A_local is not None else None, B.handle, int(a_base),
+                                                        C.byref(o), int(root), C.byref(r)))
+        return Results(r) if r else None
+
+    def search_fast_db_sharded(self, comm, Q, T_local, t_base, index_mode=0, rsb_size=0, kl_swap=True, keep=KEEP_HITS,
+                               want_paths=True, root=0, want_cands=True):
+        """`-search Q -db DB -fast` on this rank's block of the DB (rsk_search_fast_db_sharded).  Returns
+        (Results on the root / None, merged candidate list or None)."""
+        po = PrefilterOpts(int(index_mode), int(rsb_size), int(not kl_swap), 0)
+        o = self._opts(keep, want_paths, False)
+        r, c = C.c_void_p(), C.c_void_p()
+        _check(load_library().rsk_search_fast_db_sharded(self.handle, comm.handle if comm else None, Q.handle,
+                                                          T_local.handle if T_local is not None else None, int(t_base),
+                                                          C.byref(po), C.byref(o), int(root), C.byref(r),
+                                                          C.byref(c) if want_cands else None))
+        return (Results(r) if r else None), (PrefilterResult(c) if c else None)
 
     def selfrev(self, S, Srev):
         """GetSelfRevScore for every chain of S (see rsk_chainset_selfrev); returns the float32 scores."""

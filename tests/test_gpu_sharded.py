@@ -1,8 +1,10 @@
-"""GPU: DB-sharded searches give the single-GPU answer.
+"""GPU: DB-sharded searches through the product's C ABI (rsk_search_cross_sharded / rsk_search_fast_db_sharded: device hit
+sink + NCCL gather, device bag) give the single-GPU answer.
 
-One-GPU part (always runs at round end): the two blocks of a split DB are processed one after the other on the same
-device and merged with the same code the ranks use.  Two-GPU part (needs >= 2 devices, `gpurun --gpus 2`): two NCCL ranks,
-one block each, triples all-gathered over NVLink, hits gathered on rank 0."""
+One-GPU part (always runs at round end): the sink path with one rank against the host pipeline; the blocks of a split DB
+processed one after the other (incl. an empty block) and concatenated.  Two-GPU part (needs >= 2 devices, `gpurun --gpus
+2`): two NCCL ranks in two processes, and two host threads of one process over ncclCommInitAll; the root's gathered result
+must have the digest of the single-GPU search."""
 import os
 import socket
 
@@ -11,66 +13,117 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+FIELDS = ("a", "b", "score", "lo_a", "lo_b", "hi_a", "hi_b", "ids", "gaps", "lddt", "ts", "pvalue", "evalue", "qual",
+          "mu_score", "mu_fwd", "mu_rev", "flags", "path_len")
 
-def _sets():
+
+def _sets(nq=8, ndb=60):
     from reseek_b200 import synth
-    q = synth.make_chains(8, 150, seed=61, length_jitter=0.3)
-    db = synth.make_chains(60, 160, seed=62, length_jitter=0.5)
+    q = synth.make_chains(nq, 150, seed=61, length_jitter=0.3)
+    db = synth.make_chains(ndb, 160, seed=62, length_jitter=0.5)
     synth.plant_homologs(db, q, 0.4, seed=63)
     return q, db
 
 
-def _single(rb, q, db, rsb_size):
-    ctx = rb.Context(0, rb.MODE_FAST)
-    Q = ctx.upload(q.lens, q.prof, q.mu, q.xyz, q.selfrev)
-    T = ctx.upload(db.lens, db.prof, db.mu, db.xyz, db.selfrev)
-    pf = ctx.prefilter(Q, T, rsb_size=rsb_size)
-    res = ctx.postfilter(Q, T, pf, keep=rb.KEEP_HITS, want_paths=True)
-    out = (pf.targets.copy(), pf.queries.copy(), pf.scores.copy(), res.hits.copy(), [res.path(k) for k in range(len(res.hits))])
+def _up(ctx, s):
+    return ctx.upload(s.lens, s.prof, s.mu, s.xyz, s.selfrev)
+
+
+def _assert_same_hits(res, ref, ordered=True):
+    """Records and paths equal; unordered: compared in (a, b) order (explicit-pair schedules differ per block)."""
+    h, r = res.hits, ref.hits
+    assert len(h) == len(r), (len(h), len(r))
+    o = np.arange(len(h)) if ordered else np.lexsort((h["b"], h["a"]))
+    o_ref = np.arange(len(r)) if ordered else np.lexsort((r["b"], r["a"]))
+    for f in FIELDS:
+        assert np.array_equal(h[f][o].view(np.uint32), r[f][o_ref].view(np.uint32)), f
+    for k, kr in zip(o.tolist(), o_ref.tolist()):
+        assert res.path(k) == ref.path(kr)
+    assert res.digest() == ref.digest()
+
+
+@pytest.mark.parametrize("mode", ["verysensitive", "sensitive", "fast"])
+@pytest.mark.parametrize("batch_pairs", [0, 64])
+def test_sink_one_rank_equals_host_pipeline(built_lib, mode, batch_pairs, monkeypatch):
+    """comm = NULL: the device-compacted path alone.  batch_pairs=64 cuts the search into many small batches, so the sink
+    grows while batches are in flight."""
+    import reseek_b200 as rb
+    if batch_pairs:
+        monkeypatch.setenv("RSK_BATCH_PAIRS", str(batch_pairs))
+    q, db = _sets()
+    ctx = rb.Context(0, {"verysensitive": rb.MODE_VERYSENSITIVE, "sensitive": rb.MODE_SENSITIVE, "fast": rb.MODE_FAST}[mode])
+    Q, D = _up(ctx, q), _up(ctx, db)
+    ref = ctx.search_cross(D, Q, keep=rb.KEEP_HITS, want_paths=True)
+    assert len(ref.hits) > 0
+    res = ctx.search_cross_sharded(None, D, Q, 0, keep=rb.KEEP_HITS, want_paths=True)
+    _assert_same_hits(res, ref)
+    st = ctx.stats()
+    assert st["hits"] == len(ref.hits) and st["pairs"] == q.n * db.n
+    # KEEP_ALL through the sink: one record per scheduled pair, in schedule order = (a, b) order of a cross search
+    ref_all = ctx.search_cross(D, Q, keep=rb.KEEP_ALL, want_paths=True)
+    res_all = ctx.search_cross_sharded(None, D, Q, 0, keep=rb.KEEP_ALL, want_paths=True)
+    _assert_same_hits(res_all, ref_all)
+    # records only
+    res_np = ctx.search_cross_sharded(None, D, Q, 0, keep=rb.KEEP_HITS, want_paths=False)
+    assert np.array_equal(res_np.hits["score"].view(np.uint32), ref.hits["score"].view(np.uint32)) and len(res_np.paths) == 0
     ctx.close()
-    return out
+
+
+@pytest.mark.parametrize("nblocks", [2, 5])
+def test_blocks_on_one_gpu_equal_unsharded(built_lib, nblocks):
+    """The ranks' code path block after block on one device: a_base offsets, an empty block, one-rank communicators."""
+    import reseek_b200 as rb
+    q, db = _sets()
+    ctx = rb.Context(0, rb.MODE_SENSITIVE)
+    comm = rb.Comm(ctx, 1, 0)
+    Q, D = _up(ctx, q), _up(ctx, db)
+    ref = ctx.search_cross(D, Q, keep=rb.KEEP_HITS, want_paths=True)
+    parts = rb.partition_by_residues(db.lens, nblocks)
+    parts = parts[:1] + [(parts[0][1], parts[0][1])] + parts[1:]  # plus an empty block
+    hits, paths = [], []
+    for lo, hi in parts:
+        T = _up(ctx, db.subset(range(lo, hi))) if hi > lo else None
+        res = ctx.search_cross_sharded(comm, T, Q, lo, keep=rb.KEEP_HITS, want_paths=True)
+        hits.append(res.hits.copy())
+        paths += [res.path(k) for k in range(len(res.hits))]
+    hits = np.concatenate(hits)
+    assert len(hits) == len(ref.hits) > 0
+    for f in FIELDS:
+        assert np.array_equal(hits[f].view(np.uint32), ref.hits[f].view(np.uint32)), f
+    assert paths == [ref.path(k) for k in range(len(ref.hits))]
+    assert comm.stats()["bytes_sent"] == 0
+    comm.close()
+    ctx.close()
 
 
 @pytest.mark.parametrize("rsb_size", [0, 3])
-def test_two_blocks_on_one_gpu_equal_unsharded(built_lib, rsb_size):
+def test_fast_db_sharded_one_rank_and_blocks(built_lib, rsb_size):
+    """`-fast -db`: the sharded entry with one rank equals rsk_search_fast_db; the device bag over the concatenated raw
+    triples of two blocks (what the all-gather delivers) equals the unsharded candidate list, cut-off ties included."""
     import reseek_b200 as rb
-    from reseek_b200.shard import partition_by_residues
-    if rb.device_count() < 1:
-        pytest.fail("no CUDA device")
     q, db = _sets()
-    t_ref, q_ref, s_ref, hits_ref, paths_ref = _single(rb, q, db, rsb_size)
-    assert len(t_ref) > 0 and len(hits_ref) > 0
     ctx = rb.Context(0, rb.MODE_FAST)
-    Q = ctx.upload(q.lens, q.prof, q.mu, q.xyz, q.selfrev)
-    parts = partition_by_residues(db.lens, 2)
-    blocks, raws = [], []
+    Q, T = _up(ctx, q), _up(ctx, db)
+    pf = ctx.prefilter(Q, T, rsb_size=rsb_size)
+    ref = ctx.search_fast_db(Q, T, rsb_size=rsb_size, keep=rb.KEEP_HITS, want_paths=True)
+    assert len(pf.targets) > 0 and len(ref.hits) > 0
+    res, cands = ctx.search_fast_db_sharded(None, Q, T, 0, rsb_size=rsb_size, keep=rb.KEEP_HITS, want_paths=True)
+    assert np.array_equal(cands.targets, pf.targets) and np.array_equal(cands.queries, pf.queries) and np.array_equal(cands.scores, pf.scores)
+    _assert_same_hits(res, ref, ordered=False)
+    # host restatement of the bag on the raw triples (rsk_prefilter_bag) = device bag
+    raw = ctx.prefilter(Q, T, rsb_size=rsb_size, raw_only=True)
+    hb = rb.prefilter_bag(q.n, raw.targets, raw.queries, raw.scores, rsb_size)
+    assert np.array_equal(hb.targets, pf.targets) and np.array_equal(hb.queries, pf.queries) and np.array_equal(hb.scores, pf.scores)
+    # blocks: raw triples per block, concatenated in block order, equal the unsharded stream
+    parts = rb.partition_by_residues(db.lens, 3)
+    ts, qs, ss = [], [], []
     for lo, hi in parts:
-        d = db.subset(range(lo, hi))
-        T = ctx.upload(d.lens, d.prof, d.mu, d.xyz, d.selfrev)
-        blocks.append(T)
-        raws.append(ctx.prefilter(Q, T, rsb_size=rsb_size, raw_only=True))
-    merged = rb.prefilter_bag(q.n, np.concatenate([r.targets + np.uint32(lo) for r, (lo, hi) in zip(raws, parts)]),
-                              np.concatenate([r.queries for r in raws]), np.concatenate([r.scores for r in raws]), rsb_size)
-    assert np.array_equal(merged.targets, t_ref) and np.array_equal(merged.queries, q_ref) and np.array_equal(merged.scores, s_ref)
-    hits, paths = [], []
-    for T, (lo, hi) in zip(blocks, parts):
-        res = ctx.postfilter(Q, T, merged.select(lo, hi), keep=rb.KEEP_HITS, want_paths=True)
-        h = res.hits.copy()
-        h["b"] += np.uint32(lo)
-        hits.append(h)
-        paths += [res.path(k) for k in range(len(h))]
-    hits = np.concatenate(hits)
-    # KEEP_HITS lists come in the library's schedule order (per call: query-major), which differs between one call over
-    # the whole DB and one call per block: compare in the canonical (target, query) order
-    o, o_ref = _canon(hits), _canon(hits_ref)
-    for f in ("a", "b", "score", "lo_a", "lo_b", "hi_a", "hi_b", "ids", "gaps", "lddt", "ts", "evalue", "mu_fwd", "mu_rev", "flags", "path_len"):
-        assert np.array_equal(hits[f][o], hits_ref[f][o_ref]), f
-    assert [paths[k] for k in o] == [paths_ref[k] for k in o_ref]
+        Tb = _up(ctx, db.subset(range(lo, hi)))
+        r = ctx.prefilter(Q, Tb, rsb_size=rsb_size, raw_only=True)
+        ts.append(r.targets + np.uint32(lo)); qs.append(r.queries); ss.append(r.scores)
+    assert np.array_equal(np.concatenate(ts), raw.targets) and np.array_equal(np.concatenate(qs), raw.queries)
+    assert np.array_equal(np.concatenate(ss), raw.scores)
     ctx.close()
-
-
-def _canon(h):
-    return np.lexsort((h["a"], h["b"]))
 
 
 def _free_port():
@@ -85,50 +138,79 @@ def _nccl_worker(rank, world, port, out):
     import torch
     import torch.distributed as dist
     import reseek_b200 as rb
-    from reseek_b200.shard import partition_by_residues, search_fast_db_sharded, gather_hits
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     q, db = _sets()
-    lo, hi = partition_by_residues(db.lens, world)[rank]
-    d = db.subset(range(lo, hi))
+    lo, hi = rb.partition_by_residues(db.lens, world)[rank]
     ctx = rb.Context(rank, rb.MODE_FAST)
-    Q = ctx.upload(q.lens, q.prof, q.mu, q.xyz, q.selfrev)
-    T = ctx.upload(d.lens, d.prof, d.mu, d.xyz, d.selfrev)
-    merged, hits, res = search_fast_db_sharded(ctx, Q, T, lo, dist)
-    # RunQuery-style sharding too: streamed side = this rank's DB block (slot A), queries replicated
+    comm = rb.Comm.from_torch_dist(ctx, dist)
+    Q, T = _up(ctx, q), _up(ctx, db.subset(range(lo, hi)))
+    res, cands = ctx.search_fast_db_sharded(comm, Q, T, lo, keep=rb.KEEP_HITS, want_paths=True)
     ctx.set_params(rb.params_preset(rb.MODE_SENSITIVE))
-    r2 = ctx.search_cross(T, Q, keep=rb.KEEP_HITS, want_paths=False)
-    h2 = gather_hits(r2.hits, lo, dist, dst=0, field="a")
+    r2 = ctx.search_cross_sharded(comm, T, Q, lo, keep=rb.KEEP_HITS, want_paths=True)
     if rank == 0:
-        np.savez(out, t=merged.targets, q=merged.queries, s=merged.scores, hits=hits, h2=h2)
+        np.savez(out, t=cands.targets, q=cands.queries, s=cands.scores, hits=res.hits, h2=r2.hits,
+                 d1=np.uint64(res.digest()), d2=np.uint64(r2.digest()), moved=np.uint64(comm.stats()["bytes_recv"]))
+    else:
+        assert res is None and r2 is None
     dist.barrier()
+    comm.close()
     dist.destroy_process_group()
     ctx.close()
 
 
 def test_two_ranks_nccl_equal_single_gpu(built_lib, tmp_path):
-    import torch
     import torch.multiprocessing as mp
     import reseek_b200 as rb
     if rb.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2); bench.py --gpus N asserts the same digests on the driver's scaling run")
     out = str(tmp_path / "sharded.npz")
     mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     d = np.load(out)
     q, db = _sets()
-    t_ref, q_ref, s_ref, hits_ref, _ = _single(rb, q, db, 0)
-    assert np.array_equal(d["t"], t_ref) and np.array_equal(d["q"], q_ref) and np.array_equal(d["s"], s_ref)
-    o, o_ref = _canon(d["hits"]), _canon(hits_ref)
-    for f in ("a", "b", "score", "lo_a", "lo_b", "hi_a", "hi_b", "ts", "evalue", "path_len"):
-        assert np.array_equal(d["hits"][f][o], hits_ref[f][o_ref]), f
-    ctx = rb.Context(0, rb.MODE_SENSITIVE)
-    Q = ctx.upload(q.lens, q.prof, q.mu, q.xyz, q.selfrev)
-    T = ctx.upload(db.lens, db.prof, db.mu, db.xyz, db.selfrev)
-    res2 = ctx.search_cross(T, Q, keep=rb.KEEP_HITS, want_paths=False)  # keep the Results alive: .hits is a view of its memory
-    ref2 = res2.hits.copy()
-    o, o_ref = np.lexsort((d["h2"]["b"], d["h2"]["a"])), np.lexsort((ref2["b"], ref2["a"]))
-    assert len(ref2) > 0
-    for f in ("a", "b", "score", "ts", "evalue"):
-        assert np.array_equal(d["h2"][f][o], ref2[f][o_ref]), f
+    ctx = rb.Context(0, rb.MODE_FAST)
+    Q, T = _up(ctx, q), _up(ctx, db)
+    pf = ctx.prefilter(Q, T)
+    ref = ctx.search_fast_db(Q, T, keep=rb.KEEP_HITS, want_paths=True)
+    assert np.array_equal(d["t"], pf.targets) and np.array_equal(d["q"], pf.queries) and np.array_equal(d["s"], pf.scores)
+    assert int(d["d1"]) == ref.digest() and len(d["hits"]) == len(ref.hits) > 0
+    ctx.set_params(rb.params_preset(rb.MODE_SENSITIVE))
+    ref2 = ctx.search_cross(T, Q, keep=rb.KEEP_HITS, want_paths=True)
+    assert int(d["d2"]) == ref2.digest() and len(d["h2"]) == len(ref2.hits) > 0
+    for f in FIELDS:
+        assert np.array_equal(d["h2"][f].view(np.uint32), ref2.hits[f].view(np.uint32)), f
+    assert int(d["moved"]) > 0
     ctx.close()
+
+
+def test_two_gpus_one_process_comm_init_all(built_lib):
+    """DBSearcher's layout: one process, one host thread per GPU, communicators from ncclCommInitAll."""
+    import threading
+    import reseek_b200 as rb
+    if rb.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    q, db = _sets()
+    ctxs = [rb.Context(k, rb.MODE_SENSITIVE) for k in range(2)]
+    comms = rb.Comm.create_all(ctxs)
+    parts = rb.partition_by_residues(db.lens, 2)
+    out = [None, None]
+
+    def work(r):
+        lo, hi = parts[r]
+        Q, T = _up(ctxs[r], q), _up(ctxs[r], db.subset(range(lo, hi)))
+        out[r] = ctxs[r].search_cross_sharded(comms[r], T, Q, lo, keep=rb.KEEP_HITS, want_paths=True)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert out[1] is None and out[0] is not None
+    Q, T = _up(ctxs[0], q), _up(ctxs[0], db)
+    ref = ctxs[0].search_cross(T, Q, keep=rb.KEEP_HITS, want_paths=True)
+    _assert_same_hits(out[0], ref)
+    for c in comms:
+        c.close()
+    for c in ctxs:
+        c.close()
