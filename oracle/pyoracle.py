@@ -16,6 +16,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 PORT_SO = HERE / "_port" / "liboracle_port.so"
 REF_SO = HERE / "_ref" / "libreseek_ref.so"
+REF_FAST_SO = HERE / "_ref" / "libreseek_ref_fast.so"  # -O3 build of the same sources: timed only, never used for parity
 REF_BIN = HERE / "_ref" / "reseek_ref"
 
 NFEAT = 8
@@ -273,10 +274,11 @@ class Ref:
 
     _inited_mode = None
 
-    def __init__(self, mode=3):
-        if not REF_SO.exists():
-            raise FileNotFoundError(f"{REF_SO} missing - run `make -C oracle ref` in the build container")
-        L = self.lib = C.CDLL(str(REF_SO))
+    def __init__(self, mode=3, fast=False):
+        so = REF_FAST_SO if fast else REF_SO
+        if not so.exists():
+            raise FileNotFoundError(f"{so} missing - run `make -C oracle ref{'_fast' if fast else ''}` in the build container")
+        L = self.lib = C.CDLL(str(so))
         L.ref_selfrev.restype = C.c_float
         L.ref_mu_score.restype = C.c_float
         L.ref_swfast.restype = C.c_float
@@ -286,8 +288,8 @@ class Ref:
         self.mode = mode
 
     @staticmethod
-    def available():
-        return REF_SO.exists()
+    def available(fast=False):
+        return (REF_FAST_SO if fast else REF_SO).exists()
 
     def get_params(self):
         sc = np.zeros(12, np.float32)

@@ -13,6 +13,7 @@
 // ONE THREAD per (pair, direction) for the banded DP, thousands of pairs in flight.  Every float operation is
 // performed in the reference's order, so scores and paths are bit-identical.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -670,6 +671,269 @@ __global__ void __launch_bounds__(64) mkf_xdrop_flat_kernel(const MkfArgs a)
 	}
 }
 
+// The same DP with ONE WARP per (pair, direction): the lanes take 32 consecutive band columns of a row at a time.
+//
+// What makes xdropfwd.cpp sequential is (1) the insert state I0, a chain of float additions of Ext along the row, (2) the
+// running best score, which every x-drop test reads in row-major order, and (3) the band itself: a row can grow to the right
+// while its last cell is being computed, and the next row's extent is only known when the row is complete.  None of this is
+// changed; the cells of a row are only evaluated side by side:
+//  * I0 entering column j+1 is max(mi_j, I0_j + Ext) with mi_j = M[i-1][j-1] + Open, which depends on the PREVIOUS row only.
+//    f(x) = fl(x + Ext) is monotone, so I0 is a max-plus prefix scan; a Hillis-Steele step of distance 2^d applies f exactly
+//    2^d times (sequential float adds, never x + 2^d*Ext), which gives bit-for-bit the value of the serial chain.
+//  * the best score before a cell is an (exact) prefix maximum; "s >= best" updates resolve to the last lane that fires.
+//  * columns beyond the current right edge are evaluated speculatively (their previous-row inputs are -inf by the reference's
+//    own initialisation rule) and the row ends at the first edge cell whose extension test fails.
+//  * next_jlo is a minimum; next_jhi is folded as the reference does it: "= j+1" on a match test, max(...) otherwise, with the
+//    UINT_MAX start value sticking until a match test fires.
+// Previous-row values are read through the extents of the previous row (M valid on [prev_jlo, prev_jhi], D on (prev_jlo,
+// prev_jhi+1]); everything else is -inf, which is what the reference's in-place initialisation amounts to.
+// The traceback walks runs: 32 lanes fetch the next 32 trace cells along the current direction at once.
+constexpr int kXWarps = 4;
+__global__ void __launch_bounds__(kXWarps * 32) mkf_xdrop_warp_kernel(const MkfArgs a)
+{
+	__shared__ float s_tab[RSK_TABLE_FLOATS];
+	for (int k = threadIdx.x; k < RSK_TABLE_FLOATS; k += blockDim.x)
+		s_tab[k] = a.tables[k];
+	__syncthreads();
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t nwork = a.xcnt[0] + a.xcnt[1] + a.xcnt[2] + a.xcnt[3];
+	const float open = a.open, ext = a.ext, X = a.x2;
+	const float absopen = -open, absext = -ext;
+	for (;;) {
+		uint32_t w = 0;
+		if (lane == 0)
+			w = atomicAdd(a.xcnt + 2 * kXBins, 1u);
+		w = __shfl_sync(kFull, w, 0);
+		if (w >= nwork)
+			break;
+		const uint32_t t = a.xwork[w];
+		const uint32_t pair = t >> 1, dir = t & 1;
+		const MkfSeed sd = a.seeds[pair];
+		const uint32_t lo_a = sd.lo_a, lo_b = sd.lo_b;
+		const uint32_t qa = a.pair_a[pair], tb_ = a.pair_b[pair];
+		const uint64_t *PA = a.profA + a.offA[qa];
+		const uint64_t *PB = a.profB + a.offB[tb_];
+		const uint32_t LA = dir ? lo_a : a.lenA[qa] - lo_a;
+		const uint32_t LB = dir ? lo_b : a.lenB[tb_] - lo_b;
+		unsigned char *base = a.scratch + a.scratch_off[pair];
+		if (!dir)
+			base += xdrop_region_bytes(lo_a, lo_b);
+		float *Mbuf = reinterpret_cast<float *>(base);
+		float *M = Mbuf + 1;
+		float *Dr = Mbuf + (LB + 4);
+		uint8_t *stage = reinterpret_cast<uint8_t *>(Mbuf + 2 * (LB + 4));
+		const size_t W = (size_t)LB + 3;
+		uint8_t *tbm = stage + (((size_t)LA + LB + 4 + 15) & ~(size_t)15);
+		if (lane == 0)
+			a.xres[t].stage_off = (unsigned long long)(stage - a.scratch);
+		if (LA == 1 || LB == 1) {  // xdropfwd.cpp:87-93
+			if (lane == 0) {
+				const float sc = dir ? subst(s_tab, PA[lo_a - 1], PB[lo_b - 1]) : subst(s_tab, PA[lo_a], PB[lo_b]);
+				if (sc > 0) {
+					stage[0] = 'M';
+					a.xres[t].path_len = 1;
+				}
+				a.xres[t].score = sc;
+			}
+			continue;
+		}
+		if (lane == 0) {
+			M[-1] = kNegInf;
+			Dr[0] = kNegInf;
+			Dr[1] = kNegInf;
+		}
+		__syncwarp();
+		float best = 0.0f;
+		uint32_t besti = 0, bestj = 0;
+		uint32_t prev_jlo = 0, prev_jhi = 0, jlo = 1, jhi = 1;
+		float diag0 = 0.0f;  // M0 = BestScore before the first row
+		for (uint32_t i = 1; i <= LA; ++i) {
+			const uint64_t ea = dir ? PA[lo_a - i] : PA[lo_a + i - 1];
+			uint8_t *row = tbm + (size_t)i * W;
+			uint32_t next_jlo = kNone, next_jhi = kNone;
+			float I_carry = kNegInf, diag_carry = diag0, best_run = best;
+			uint32_t jhi_cur = jhi, j0 = jlo, jhi_final = jhi;
+			float M0_end = kNegInf;
+			for (;;) {
+				const uint32_t j = j0 + lane;
+				const bool inb = j <= LB;
+				const float oldM = (inb && j >= prev_jlo && j <= prev_jhi) ? M[j] : kNegInf;
+				const float oldD = (inb && j > prev_jlo && j <= prev_jhi + 1) ? Dr[j] : kNegInf;
+				float diag = __shfl_up_sync(kFull, oldM, 1);
+				if (lane == 0)
+					diag = diag_carry;
+				const float mi = diag + open;
+				// insert state after each cell: prefix scan of max(mi, f(.)), f applied by repeated addition
+				float A = mi;
+				if (lane == 0) {
+					const float ti0 = I_carry + ext;
+					A = (mi >= ti0) ? mi : ti0;
+				}
+#pragma unroll
+				for (int d = 0; d < 5; ++d) {
+					float v = __shfl_up_sync(kFull, A, 1u << d);
+#pragma unroll
+					for (int r = 0; r < (1 << d); ++r)
+						v += ext;
+					if (lane >= (1u << d))
+						A = fmaxf(A, v);
+				}
+				float I0 = __shfl_up_sync(kFull, A, 1);
+				if (lane == 0)
+					I0 = I_carry;
+				const float tI = I0 + ext;
+				const bool bMI = mi >= tI;
+				const float Inew = bMI ? mi : tI;
+				// match state
+				float x = diag;
+				uint32_t bits = 0;
+				if (oldD > x) { x = oldD; bits = XB_DM; }
+				if (I0 > x) { x = I0; bits = XB_IM; }
+				float s = kNegInf;
+				if (inb) {
+					const uint64_t eb = dir ? PB[lo_b - j] : PB[lo_b + j - 1];
+					s = subst(s_tab, ea, eb);
+					s += x;
+				}
+				// best score before / after each cell, row-major
+				float pm = s;
+#pragma unroll
+				for (int d = 0; d < 5; ++d) {
+					const float v = __shfl_up_sync(kFull, pm, 1u << d);
+					if (lane >= (1u << d))
+						pm = fmaxf(pm, v);
+				}
+				const float bb = __shfl_up_sync(kFull, pm, 1);
+				const float best_before = (lane == 0) ? best_run : fmaxf(best_run, bb);
+				const float best_after = fmaxf(best_before, s);
+				const float h1 = s - best_before + X;
+				// delete state
+				const bool hasD = j != jlo;
+				const float md = diag + open;
+				float dn = oldD + ext;
+				bool bMD = false;
+				if (md >= dn) { dn = md; bMD = true; }
+				const float h2 = dn - best_after + X;
+				const float h3 = Inew - best_after + X;
+				// where does the row end?  an edge cell (j >= current jhi) extends the row iff one of its insert tests fires
+				const bool E = (h1 > absext || h3 > absext) && (j + 1 < LB);
+				const unsigned stop = __ballot_sync(kFull, !inb || (j >= jhi_cur && !E));
+				const bool last_chunk = stop != 0;
+				const uint32_t f = last_chunk ? (uint32_t)__ffs((int)stop) - 1u : 31u;
+				const bool valid = lane <= f;
+				if (valid) {
+					M[j] = s;
+					uint32_t bt = bits | (bMI ? XB_MI : 0u);
+					if (hasD) {
+						Dr[j] = dn;
+						if (bMD)
+							bt |= XB_MD;
+					}
+					row[j] = (uint8_t)bt;
+				}
+				const unsigned upd = __ballot_sync(kFull, valid && s >= best_before);
+				if (upd) {
+					bestj = j0 + (31u - (uint32_t)__clz((int)upd));
+					besti = i;
+				}
+				best_run = fmaxf(best_run, __shfl_sync(kFull, pm, f));
+				uint32_t lo_c = kNone, mx = 0;
+				if (valid) {
+					if (h1 > 0) lo_c = j + 1;
+					if (h1 > absopen) lo_c = min(lo_c, j);
+					if (hasD && h2 > 0) { lo_c = min(lo_c, j - 1); mx = j - 1; }
+					if (h3 > 0) { lo_c = min(lo_c, j + 1); mx = j + 1; }
+				}
+				next_jlo = min(next_jlo, __reduce_min_sync(kFull, lo_c));
+				const unsigned mA = __ballot_sync(kFull, valid && h1 > 0);
+				if (mA) {
+					const uint32_t lA = 31u - (uint32_t)__clz((int)mA);
+					const uint32_t m = __reduce_max_sync(kFull, lane >= lA ? mx : 0u);
+					next_jhi = max(j0 + lA + 1, m);
+				} else {
+					const uint32_t m = __reduce_max_sync(kFull, mx);
+					if (m)
+						next_jhi = max(next_jhi, m);  // UINT_MAX sticks, as in the reference
+				}
+				if (last_chunk) {
+					jhi_final = j0 + f;
+					M0_end = __shfl_sync(kFull, oldM, f);
+					break;
+				}
+				I_carry = __shfl_sync(kFull, Inew, 31);
+				diag_carry = __shfl_sync(kFull, oldM, 31);
+				if (j0 + 32 > jhi_cur)
+					jhi_cur = j0 + 32;
+				j0 += 32;
+			}
+			if (jhi_final < LB && lane == 0) {  // special case for the end of Drow[] (xdropfwd.cpp:289-300)
+				const uint32_t j1 = jhi_final + 1;
+				const float pd = (j1 > prev_jlo && j1 <= prev_jhi + 1) ? Dr[j1] : kNegInf;
+				const float md = M0_end + open;
+				float dn = pd + ext;
+				uint8_t b1 = 0;
+				if (md >= dn) { dn = md; b1 = XB_MD; }
+				Dr[j1] = dn;
+				row[j1] = b1;
+			}
+			best = best_run;
+			if (next_jlo == kNone)
+				break;
+			prev_jlo = jlo; prev_jhi = jhi_final;
+			jlo = min(next_jlo, LB);
+			jhi = min(next_jhi, LB);
+			__syncwarp();  // this row's stores before the next row's loads
+			diag0 = (jlo == prev_jlo) ? kNegInf : M[jlo - 1];
+		}
+		if (!(best > 0.0f))
+			continue;
+		__syncwarp();
+		// traceback by runs (TraceBack, xdropfwd.cpp:14-67): state st at (ti, tj); the lanes read the next 32 trace cells along
+		// the direction of the state and the run ends at the first cell that changes state or touches row/column 1
+		uint32_t ti = besti, tj = bestj, tn = 0;
+		int st = 0;
+		for (;;) {
+			const uint32_t di = (st != 2) ? lane : 0u, dj = (st != 1) ? lane : 0u;
+			const bool inr = ti > di && tj > dj;
+			const uint32_t pi = ti - di, pj = tj - dj;
+			const bool boundary = inr && (pi == 1 || pj == 1);
+			int nx = st;
+			if (inr && !boundary) {
+				if (st == 0) {
+					const uint8_t c = tbm[(size_t)pi * W + pj];
+					nx = (c & XB_DM) ? 1 : (c & XB_IM) ? 2 : 0;
+				} else if (st == 1) {
+					nx = (tbm[(size_t)pi * W + pj + 1] & XB_MD) ? 0 : 1;
+				} else {
+					nx = (tbm[(size_t)(pi + 1) * W + pj] & XB_MI) ? 0 : 2;
+				}
+			}
+			const unsigned endm = __ballot_sync(kFull, !inr || boundary || nx != st);
+			const uint32_t e = endm ? (uint32_t)__ffs((int)endm) - 1u : 31u;
+			if (lane <= e)
+				stage[tn + lane] = (uint8_t)(st == 0 ? 'M' : st == 1 ? 'D' : 'I');
+			tn += e + 1;
+			if (!endm) {  // the run goes on
+				ti -= (st != 2) ? 32u : 0u;
+				tj -= (st != 1) ? 32u : 0u;
+				continue;
+			}
+			const bool fin = __shfl_sync(kFull, (int)boundary, e) != 0;
+			if (fin)
+				break;
+			const int nst = __shfl_sync(kFull, nx, e);
+			const uint32_t ei = ti - ((st != 2) ? e : 0u), ej = tj - ((st != 1) ? e : 0u);
+			ti = (st != 2) ? ei - 1 : ei;
+			tj = (st != 1) ? ej - 1 : ej;
+			st = nst;
+		}
+		if (lane == 0) {
+			a.xres[t].score = best;
+			a.xres[t].path_len = tn;  // stage[] holds the path from its end to its start
+		}
+	}
+}
+
 // One warp per pair: total score test, MergeFwdBwd, publish record + path.
 __global__ void __launch_bounds__(128) mkf_finish_kernel(const MkfArgs a)
 {
@@ -746,11 +1010,16 @@ int launch_mkf(const MkfArgs &args, uint32_t nhash, int xgrid_blocks, cudaStream
 	mkf_bin_kernel<<<(2 * args.npairs + 255) / 256, 256, 0, stream>>>(args, 0);
 	mkf_bin_kernel<<<(2 * args.npairs + 255) / 256, 256, 0, stream>>>(args, 1);
 	const unsigned xblocks = (unsigned)std::min<uint64_t>(((uint64_t)2 * args.npairs + 63) / 64, (uint64_t)xgrid_blocks);
-	static const bool thread_per_item = getenv("RSK_XDROP_SEQ") != nullptr;  // the round-1 kernel, kept for A/B timing
-	if (thread_per_item)
+	// RSK_XDROP=seq | flat: the round-1 kernels (one thread per item), kept for A/B timing and as a cross-check of the warp kernel
+	static const char *variant = getenv("RSK_XDROP");
+	if (variant && !strcmp(variant, "seq"))
 		mkf_xdrop_kernel<<<xblocks, 64, 0, stream>>>(args);
-	else
+	else if (variant && !strcmp(variant, "flat"))
 		mkf_xdrop_flat_kernel<<<xblocks, 64, 0, stream>>>(args);
+	else {
+		const unsigned wblocks = (unsigned)std::min<uint64_t>(((uint64_t)2 * args.npairs + kXWarps - 1) / kXWarps, (uint64_t)xgrid_blocks);
+		mkf_xdrop_warp_kernel<<<wblocks, kXWarps * 32, 0, stream>>>(args);
+	}
 	mkf_finish_kernel<<<(args.npairs + 3) / 4, 128, 0, stream>>>(args);
 	return cudaGetLastError() == cudaSuccess ? 6 : -1;
 }
