@@ -167,6 +167,28 @@ uint32_t rsk_chainset_count(const rsk_chainset *cs);
 uint64_t rsk_chainset_residues(const rsk_chainset *cs);
 void rsk_chainset_free(rsk_chainset *cs);
 
+/* ---- DSS on the device: structure -> feature letters ----
+ * rsk_chainset_from_coords replaces, for every chain, DSS::Init + GetProfile + GetMuLetters (dss.cpp:716-741, 700-714 and what
+ * they call: getss.cpp:6-63, myss.cpp:142-210, dss.cpp:179-244, 339-440, 78-155, 866-881, valuetoint.cpp) as ProfileLoader's
+ * threads run them (profileloader.cpp:17-70): the C-alpha coordinates and amino-acid characters go up (13 bytes per residue),
+ * the 8 feature planes and the Mu letters are computed by one CTA per chain and stay on the device.  Letter-exact: same types
+ * and operation order as the reference, exp() with the bits of the host's libm.  Self-reverse scores start "unset"
+ * (FLT_MAX); rsk_chainset_reversed + rsk_chainset_selfrev fill them. */
+typedef struct rsk_coords_host {
+	uint32_t n;            /* number of chains */
+	uint64_t total;        /* sum of len[] */
+	const uint32_t *len;   /* [n] */
+	const char *aa;        /* [total] amino-acid characters (PDBChain::m_Seq), chains concatenated */
+	const float *xyz;      /* [3][total] */
+} rsk_coords_host;
+int rsk_chainset_from_coords(rsk_ctx *ctx, const rsk_coords_host *chains, int with_mu, rsk_chainset **out);
+/* PDBChain::GetReverse (pdbchain.cpp:478) + DSS of every reversed chain of S, carrying S's FORWARD Mu letters (alignpair.cpp:22):
+ * the Srev argument of rsk_chainset_selfrev, made on the device. */
+int rsk_chainset_reversed(rsk_ctx *ctx, const rsk_chainset *S, rsk_chainset **out);
+/* feature letters of a device chain set back on the host (hit writers, OnAln subclasses, tests): prof [RSK_NFEAT][total]
+ * plane-major, mu [total], selfrev [n]; any pointer may be NULL */
+int rsk_chainset_download_features(rsk_ctx *ctx, const rsk_chainset *S, uint8_t *prof, uint8_t *mu, float *selfrev);
+
 /* Self-reverse scores: GetSelfRevScore (alignpair.cpp:7-25) for every chain of S.  Srev holds, chain by chain, the
  * profile of the coordinate-reversed chain (PDBChain::GetReverse + DSS, upstream of this library) together with the
  * FORWARD Mu letters (the reference passes the forward letters for the reversed chain, alignpair.cpp:22).  Chain i of S is

@@ -92,3 +92,23 @@ def write_bca(path, labels, seqs, xyzs):
         f.write(bytes(body))
         f.write(np.asarray(lens, np.uint32).tobytes())
         f.write(labeldata)
+
+
+def read_bca(path):
+    """Inverse of write_bca: returns (labels, seqs [bytes], xyzs [float32 [3][L]]), coordinates decoded as
+    PDBChain::ICToCoord does (pdbchain.h:89-90: float(ic / 10.0f) - 1000)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    magic, = struct.unpack_from("<I", buf, 0)
+    assert magic == 0xBCABCA, "not a .bca file"
+    n, lens_pos, label_bytes = struct.unpack_from("<QQQ", buf, 4)
+    lens = np.frombuffer(buf, np.uint32, n, lens_pos)
+    labels = buf[lens_pos + 4 * n:lens_pos + 4 * n + label_bytes].split(b"\0")[:n]
+    seqs, xyzs = [], []
+    pos = 4 + 24
+    for L in lens.tolist():
+        seqs.append(bytes(buf[pos:pos + L]))
+        ic = np.frombuffer(buf, np.uint16, 3 * L, pos + L).reshape(L, 3)
+        xyzs.append(np.ascontiguousarray((ic.astype(np.float32) / np.float32(10.0) - np.float32(1000.0)).T))
+        pos += L + 6 * L
+    return [x.decode() for x in labels], seqs, xyzs

@@ -1,4 +1,5 @@
-// host_cabi.cpp - plain-C entry points into the host layer (ctypes-friendly): the DSS feature stage for one chain.
+// host_cabi.cpp - plain-C entry points into the host layer (ctypes-friendly): the DSS feature stage for one chain (computed on
+// the GPU through the DSS look-alike; RSK_ERR_CUDA-style death without a device, as everywhere in this layer).
 // Declared here only (they are helpers of the host library, not part of the device ABI in include/reseek_b200.h).
 #include <string.h>
 

@@ -10,7 +10,7 @@
 //   rsk_host_demo pairglobal <mode> <set.rskc> <i> <j> <out.tsv> [columns]  AlignQueryTarget_Global (-global)
 //   rsk_host_demo fastdb <q.rskc> <db.rskc> <cands.tsv> <out.tsv>   MuPreFilter + PostMuFilter    (-search Q -db DB -fast)
 // From the reference's own .bca files, through the DSS look-alike (no precomputed features):
-//   rsk_host_demo features   <in.bca> <out.rskc>                               DSS only (runs without a GPU)
+//   rsk_host_demo features   <in.bca> <out.rskc>                               DSS only (device DSS, dss_kernel.cu)
 //   rsk_host_demo selfsearch <mode> <x.bca> <out.tsv> [columns]                search.cpp:20-38   (-search X)
 //   rsk_host_demo search     <mode> <q.bca> <db.bca> <out.tsv> [columns]       search.cpp:40-63   (-search Q -db DB)
 //   rsk_host_demo searchfast <q.bca> <db.bca> <cands.tsv> <out.tsv> [columns]  search.cpp:76-111  (-search Q -db DB -fast)
@@ -399,8 +399,20 @@ static int ReseekAlignPair(int argc, char **argv)
 	// AlignPair1 (alignpair.cpp:77-105) aligns each chain against its reversed self right before the pair; on the -global
 	// path that is where the AQ of the printed block comes from (ClearAlign does not reset the quality)
 	const uint bq = Hits[Best].a, bt = Hits[Best].b;
-	GetSelfRevScore(DA, *Q.Chains[bq], *Q.Profiles[bq], Q.RevProfiles[bq], 0, 0);
-	GetSelfRevScore(DA, *T.Chains[bt], *T.Profiles[bt], T.RevProfiles[bt], 0, 0);
+	{
+	DSS D;
+	D.UseContext(C);
+	PDBChain Rev;
+	vector<vector<byte> > RevProfile;
+	Q.Chains[bq]->GetReverse(Rev);
+	D.Init(Rev);
+	D.GetProfile(RevProfile);
+	GetSelfRevScore(DA, *Q.Chains[bq], *Q.Profiles[bq], RevProfile, 0, 0);
+	T.Chains[bt]->GetReverse(Rev);
+	D.Init(Rev);
+	D.GetProfile(RevProfile);
+	GetSelfRevScore(DA, *T.Chains[bt], *T.Profiles[bt], RevProfile, 0, 0);
+	}
 	DA.FromHit(Hits[Best], rsk_results_paths(Res), QD[bq], TD[bt]);
 	if (!AlnFN.empty())
 		{
@@ -439,7 +451,7 @@ int main(int argc, char **argv)
 		return ReseekAlignPair(argc, argv);
 	if (Cmd == "features" && argc >= 4)
 		{
-		// DSS stage only: no device is touched (no self-reverse scores)
+		// DSS stage only (on the GPU, chain by chain through the DSS look-alike; no self-reverse scores)
 		ChainReader2 CR;
 		CR.Open(argv[2]);
 		ChainFeatures F;

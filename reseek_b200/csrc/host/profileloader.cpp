@@ -1,8 +1,6 @@
 // profileloader.cpp - see profileloader.h
 #include "profileloader.h"
 
-#include <atomic>
-#include <thread>
 
 #include "dssaligner.h"
 
@@ -76,65 +74,26 @@ uint ProfileLoader::Load(const DSSParams &Params, ChainReader2 &CR, uint MaxChai
 	const uint N = RSK_SIZE(Out.Chains);
 	if (N == 0)
 		return 0;
-	Out.Profiles.resize(N, 0);
-	Out.MuLetters.resize(N, 0);
-	Out.MuKmers.resize(N, 0);
-	Out.RevProfiles.resize(N);
-	if (ThreadCount == 0)
-		ThreadCount = std::max(1u, std::thread::hardware_concurrency());
-	ThreadCount = std::min(ThreadCount, N);
-	std::atomic<uint> Next{0};
-	auto Body = [&]()
-		{
-		DSS D;
-		D.SetParams(Params);
-		for (;;)
-			{
-			const uint i = Next.fetch_add(1);
-			if (i >= N)
-				return;
-			const PDBChain &Chain = *Out.Chains[i];
-			D.Init(Chain);
-			Out.Profiles[i] = new vector<vector<byte> >;
-			D.GetProfile(*Out.Profiles[i]);
-			Out.MuLetters[i] = new vector<byte>;
-			Out.MuKmers[i] = new vector<uint>;
-			if (WithMu)
-				{
-				D.GetMuLetters(*Out.MuLetters[i]);
-				D.GetMuKmers(*Out.MuLetters[i], *Out.MuKmers[i], "111");  // m_MKFPatternStr (dssparams.cpp:88)
-				}
-			PDBChain Rev;
-			Chain.GetReverse(Rev);
-			D.Init(Rev);
-			D.GetProfile(Out.RevProfiles[i]);
-			}
-		};
-	vector<std::thread> ts;
-	for (uint t = 1; t < ThreadCount; ++t)
-		ts.emplace_back(Body);
-	Body();
-	for (auto &t : ts)
-		t.join();
-
-	// self-reverse scores (alignpair.cpp:7-25) for the whole block in one GPU call: chain i against its reversed self,
-	// which carries the FORWARD Mu letters (:22)
-	vector<ChainData> Fwd(N), Rev(N);
-	vector<PDBChain> RevChains(N);
+	(void) ThreadCount;  // the feature stage runs on the GPU: one CTA per chain instead of one host thread per chain
+	// DSS of the whole block on the device (dss_kernel.cu); the letters come back for the per-chain vectors of the reference's
+	// class surface, the device set stays for the self-reverse scores
+	rsk_chainset *S = 0;
+	DSS::GetFeaturesBatch(Ctx, Out.Chains, WithMu, Out.Profiles, Out.MuLetters, &S);
+	Out.MuKmers.assign(N, 0);
 	for (uint i = 0; i < N; ++i)
 		{
-		Fwd[i].Chain = Out.Chains[i];
-		Fwd[i].Profile = Out.Profiles[i];
-		Fwd[i].MuLetters = WithMu ? Out.MuLetters[i] : 0;
-		Out.Chains[i]->GetReverse(RevChains[i]);
-		Rev[i].Chain = &RevChains[i];
-		Rev[i].Profile = &Out.RevProfiles[i];
-		Rev[i].MuLetters = WithMu ? Out.MuLetters[i] : 0;
+		Out.MuKmers[i] = new vector<uint>;
+		if (WithMu)
+			DSS::GetMuKmers(*Out.MuLetters[i], *Out.MuKmers[i], "111");  // m_MKFPatternStr (dssparams.cpp:88)
 		}
+	Out.RevProfiles.clear();
+
+	// self-reverse scores (alignpair.cpp:7-25) for the whole block: chain i against its reversed self (PDBChain::GetReverse +
+	// DSS, on the device), which carries the FORWARD Mu letters (:22)
+	rsk_chainset *SR = 0;
+	Check(rsk_chainset_reversed(Ctx, S, &SR));
 	rsk_params Saved, R;
 	SelfRevParams.ToRsk(R, MaxEvalue);
-	rsk_chainset *S = UploadChains(Ctx, Fwd, WithMu);
-	rsk_chainset *SR = UploadChains(Ctx, Rev, WithMu);
 	Out.SelfRevScores.assign(N, FLT_MAX);
 	Check(rsk_ctx_get_params(Ctx, &Saved));
 	Check(rsk_ctx_set_params(Ctx, &R));

@@ -32,7 +32,7 @@ struct ChainFeatures
 	vector<vector<vector<byte> > *> Profiles;        // owned
 	vector<vector<byte> *> MuLetters;                // owned; empty vector when Mu letters were not requested
 	vector<vector<uint> *> MuKmers;                  // owned
-	vector<vector<vector<byte> > > RevProfiles;      // DSS of the coordinate-reversed chains (for the self-reverse scores)
+	vector<vector<vector<byte> > > RevProfiles;      // unused: the reversed chains' DSS stays on the device (rsk_chainset_reversed)
 	vector<float> SelfRevScores;
 	void Release();                                  // forget the pointers (ownership moved elsewhere)
 	void Free();
@@ -41,7 +41,7 @@ struct ChainFeatures
 class ProfileLoader
 	{
 public:
-	// Reads up to MaxChains chains from CR (all when 0), runs DSS on host threads and computes the self-reverse scores on
+	// Reads up to MaxChains chains from CR (all when 0), runs DSS on the GPU (one CTA per chain) and computes the self-reverse scores on
 	// the GPU with SelfRevParams (ProfileLoader: omega = 0, profileloader.cpp:22-26; RunQuery: the search parameters,
 	// runquery.cpp:43).  Returns the number of chains loaded.
 	static uint Load(const DSSParams &Params, ChainReader2 &CR, uint MaxChains, bool WithMu, rsk_ctx *Ctx,

@@ -754,6 +754,15 @@ __global__ void __launch_bounds__(kXWarps * 32) mkf_xdrop_warp_kernel(const MkfA
 			float I_carry = kNegInf, diag_carry = diag0, best_run = best;
 			uint32_t jhi_cur = jhi, j0 = jlo, jhi_final = jhi;
 			float M0_end = kNegInf;
+			// A quirk of the reference that has to be kept: `endj` is not advanced by the row-start initialisation
+			// (xdropfwd.cpp:142-147), so when the row starts wider than the previous one and then extends at its last start
+			// column jstar, the FIRST extension's initialisation loop (j2 = prev_jhi+2 ...) runs over columns of THIS row that
+			// are already done: the match-site extension (:190-205, Mrow guarded) resets Drow[prev_jhi+2 .. jstar] (Drow[jstar] is
+			// then recomputed from -inf by the cell's delete part), the insert-site extension (:262-276, no guard) resets
+			// Drow[prev_jhi+2 .. jstar] and Mrow[prev_jhi+1 .. jstar].  The next row sees those -inf values.
+			const uint32_t jstar = jhi;
+			const bool quirk_row = jstar >= prev_jhi + 1;
+			bool wipe = false, wipe_site1 = false;
 			for (;;) {
 				const uint32_t j = j0 + lane;
 				const bool inb = j <= LB;
@@ -813,10 +822,23 @@ __global__ void __launch_bounds__(kXWarps * 32) mkf_xdrop_warp_kernel(const MkfA
 				float dn = oldD + ext;
 				bool bMD = false;
 				if (md >= dn) { dn = md; bMD = true; }
-				const float h2 = dn - best_after + X;
+				float h2 = dn - best_after + X;
 				const float h3 = Inew - best_after + X;
 				// where does the row end?  an edge cell (j >= current jhi) extends the row iff one of its insert tests fires
 				const bool E = (h1 > absext || h3 > absext) && (j + 1 < LB);
+				if (quirk_row && jstar >= j0 && jstar < j0 + 32) {
+					const uint32_t ls = jstar - j0;
+					if (__shfl_sync(kFull, (int)E, ls)) {
+						wipe = true;
+						wipe_site1 = __shfl_sync(kFull, (int)(h1 > absext), ls) != 0;
+						if (wipe_site1 && jstar >= prev_jhi + 2 && lane == ls) {  // Drow[jstar] was reset before the delete part of the cell
+							dn = kNegInf + ext;
+							bMD = false;
+							if (md >= dn) { dn = md; bMD = true; }
+							h2 = dn - best_after + X;
+						}
+					}
+				}
 				const unsigned stop = __ballot_sync(kFull, !inb || (j >= jhi_cur && !E));
 				const bool last_chunk = stop != 0;
 				const uint32_t f = last_chunk ? (uint32_t)__ffs((int)stop) - 1u : 31u;
@@ -875,6 +897,14 @@ __global__ void __launch_bounds__(kXWarps * 32) mkf_xdrop_warp_kernel(const MkfA
 				if (md >= dn) { dn = md; b1 = XB_MD; }
 				Dr[j1] = dn;
 				row[j1] = b1;
+			}
+			if (wipe) {
+				__syncwarp();  // after the row's own stores
+				for (uint32_t jj = prev_jhi + 2 + lane; jj <= (wipe_site1 ? jstar - 1 : jstar); jj += 32)
+					Dr[jj] = kNegInf;
+				if (!wipe_site1)
+					for (uint32_t jj = prev_jhi + 1 + lane; jj <= jstar; jj += 32)
+						M[jj] = kNegInf;
 			}
 			best = best_run;
 			if (next_jlo == kNone)

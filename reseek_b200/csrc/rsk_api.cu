@@ -330,6 +330,8 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->pf_scratch = nullptr;
 	ctx->upload_stage.release();
 	ctx->sink.release(); ctx->h_sink[0].release(); ctx->h_sink[1].release();
+	ctx->dss_ss.release(); ctx->dss_conf.release(); ctx->dss_aa.release(); ctx->dss_dens.release(); ctx->dss_helix.release();
+	if (ctx->d_dss_tables) cudaFree(ctx->d_dss_tables);
 	ctx->ckpt.release(); ctx->tile.release(); ctx->best.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
 	ctx->blist.release(); ctx->bslot.release(); ctx->task_a.release(); ctx->task_begin.release();
 	ctx->task_cnt.release(); ctx->pair_a.release(); ctx->pair_b.release();
@@ -420,6 +422,10 @@ void *slab_get(rsk_ctx *ctx, size_t bytes, size_t &cap)
 	return p;
 }
 
+void slab_put(rsk_ctx *ctx, void *p, size_t cap);
+}  // namespace
+void *rsk_slab_get(rsk_ctx *ctx, size_t bytes, size_t &cap) { return slab_get(ctx, bytes, cap); }  // rsk_dss.cu
+namespace {
 void slab_put(rsk_ctx *ctx, void *p, size_t cap)
 {
 	if (!p)

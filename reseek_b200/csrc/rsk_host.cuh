@@ -188,6 +188,11 @@ struct rsk_ctx {
 		std::swap(filt_explicit_pairs, alt.filt_explicit_pairs);
 		std::swap(filt_explicit_cells, alt.filt_explicit_cells);
 	}
+	// DSS on the device (K10): trained tables and per-residue scratch
+	DssTables *d_dss_tables = nullptr;
+	DevBuf<uint8_t> dss_ss, dss_conf, dss_aa;
+	DevBuf<double> dss_dens;
+	DevBuf<uint32_t> dss_helix;
 	HitSink sink;
 	PinBuf<SinkRec> h_sink[2];  // pinned staging of the sink read-out (chunked, double-buffered)
 	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU

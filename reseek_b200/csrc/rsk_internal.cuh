@@ -310,6 +310,22 @@ int pf_sort_pairs(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint
 int pf_segmented_sort(const uint32_t *kin, uint32_t *kout, unsigned long long n, uint32_t nseg, const unsigned long long *off,
 		void *tmp, size_t &tmp_bytes, cudaStream_t st);
 
+// K10: DSS feature extraction, see dss_kernel.cu
+struct DssTables { double conf[16][9]; double bins[5][15]; unsigned char amino[256]; };  // bins: NENDist, RENDist, DstNxtHlx, StrandDens, NormDens
+struct DssArgs {
+	uint32_t n; uint64_t total;
+	const uint32_t *len; const uint64_t *off; const float *x, *y, *z;
+	const uint8_t *aa_char;    // [total] amino-acid characters, or null when ...
+	const uint64_t *aa_prof8;  // ... the AA letters come from byte 0 of an existing set's packed profile
+	uint32_t reverse;          // 1: every chain is read back to front (PDBChain::GetReverse, pdbchain.cpp:478)
+	uint8_t *ss, *conf; double *dens; uint32_t *helix_mid;  // per-residue scratch [total]
+	uint8_t *planes;           // out [8][total]
+	uint8_t *mu;               // out [total] or null
+	const DssTables *tab;
+};
+int launch_dss(const DssArgs &a, int grid, cudaStream_t st);
+int launch_dss_unpack(const uint64_t *prof8, uint64_t total, uint8_t *planes, cudaStream_t st);
+
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();

@@ -33,6 +33,10 @@ class ChainsHost(C.Structure):
                 ("mu", C.c_void_p), ("xyz", C.c_void_p), ("selfrev", C.c_void_p)]
 
 
+class CoordsHost(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("total", C.c_uint64), ("len", C.c_void_p), ("aa", C.c_void_p), ("xyz", C.c_void_p)]
+
+
 class HitView(C.Structure):
     _fields_ = [("hit", C.c_void_p), ("path", C.c_char_p), ("label_a", C.c_char_p), ("label_b", C.c_char_p),
                 ("seq_a", C.c_char_p), ("seq_b", C.c_char_p), ("len_a", C.c_uint32), ("len_b", C.c_uint32)]
@@ -149,6 +153,9 @@ def load_library():
     L.rsk_postfilter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts), C.POINTER(C.c_void_p)]
     L.rsk_search_fast_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrefilterOpts), C.POINTER(SearchOpts),
                                      C.POINTER(C.c_void_p)]
+    L.rsk_chainset_from_coords.argtypes = [C.c_void_p, C.POINTER(CoordsHost), C.c_int, C.POINTER(C.c_void_p)]
+    L.rsk_chainset_reversed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rsk_chainset_download_features.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rsk_comm_unique_id.argtypes = [C.c_void_p]
     L.rsk_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
     L.rsk_comm_create_all.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
@@ -460,8 +467,49 @@ class ChainSet:
         self.handle = C.c_void_p()
         _check(load_library().rsk_chainset_upload(ctx.handle, C.byref(h), C.byref(self.handle)))
 
+    @classmethod
+    def _from_handle(cls, ctx, handle, lens, has_mu):
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.handle = handle
+        self.lens = np.ascontiguousarray(lens, np.uint32)
+        self.n = len(self.lens)
+        self.total = int(self.lens.sum(dtype=np.uint64))
+        self.prof = self.xyz = self.selfrev = None
+        self.mu = True if has_mu else None
+        return self
+
+    @classmethod
+    def from_coords(cls, ctx, lens, aa, xyz, with_mu=True):
+        """DSS on the device (rsk_chainset_from_coords): aa = amino-acid characters [total] (bytes / uint8), xyz [3][total]."""
+        lens = np.ascontiguousarray(lens, np.uint32)
+        aa = np.ascontiguousarray(np.frombuffer(aa, np.uint8) if isinstance(aa, (bytes, bytearray)) else aa, np.uint8)
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        total = int(lens.sum(dtype=np.uint64))
+        assert len(aa) == total and xyz.shape == (3, total)
+        h = CoordsHost(len(lens), total, _ptr(lens), _ptr(aa), _ptr(xyz))
+        handle = C.c_void_p()
+        _check(load_library().rsk_chainset_from_coords(ctx.handle, C.byref(h), int(bool(with_mu)), C.byref(handle)))
+        return cls._from_handle(ctx, handle, lens, with_mu)
+
+    def reversed(self):
+        """PDBChain::GetReverse + DSS of every chain on the device, forward Mu letters (rsk_chainset_reversed)."""
+        handle = C.c_void_p()
+        _check(load_library().rsk_chainset_reversed(self.ctx.handle, self.handle, C.byref(handle)))
+        return ChainSet._from_handle(self.ctx, handle, self.lens, self.mu is not None)
+
+    def download_features(self, want_mu=True):
+        """(prof [8][total], mu [total] or None, selfrev [n]) read back from the device."""
+        prof = np.zeros((NFEAT, self.total), np.uint8)
+        mu = np.zeros(self.total, np.uint8) if (want_mu and self.mu is not None) else None
+        sr = np.zeros(self.n, np.float32)
+        _check(load_library().rsk_chainset_download_features(self.ctx.handle, self.handle, _ptr(prof), _ptr(mu), _ptr(sr)))
+        return prof, mu, sr
+
     @property
     def h2d_bytes(self):
+        if self.prof is None:
+            return 13 * self.total + 4 * self.n
         return self.lens.nbytes + self.prof.nbytes + (0 if self.mu is None else self.mu.nbytes) + self.xyz.nbytes + \
             (0 if self.selfrev is None else self.selfrev.nbytes)
 

@@ -27,6 +27,7 @@ def _golden(name):
     return (GOLDEN / name).read_text().splitlines()
 
 
+@pytest.mark.gpu
 def test_dss_lookalike_reproduces_reference_letters(built_lib):
     """rskh_dss_features (DSS::GetProfile / GetMuLetters restated on the host) on 21 real chains (49..1231 residues):
     all 8 feature planes, the Mu letters and the profile of the coordinate-reversed chain, letter for letter."""
@@ -48,6 +49,7 @@ def test_dss_lookalike_reproduces_reference_letters(built_lib):
         assert np.array_equal(rev, g["rev_prof"][:, s:e]), f"chain {i}: reversed-chain profile"
 
 
+@pytest.mark.gpu
 def test_dss_lookalike_vs_live_reference(built_lib):
     """Same check against the compiled reference on 300 SCOP40 chains (build container only)."""
     from oracle.pyoracle import Ref
@@ -70,6 +72,7 @@ def test_dss_lookalike_vs_live_reference(built_lib):
         assert np.array_equal(prof, p_ref) and np.array_equal(mu, mu_ref) and np.array_equal(rev, rp_ref), label
 
 
+@pytest.mark.gpu
 def test_bca_reader_and_features_command(built_lib, tmp_path):
     """.bca written by reseek_b200.chainio -> BCAData::Open/ReadChain -> DSS -> .rskc dump; no GPU is touched."""
     from reseek_b200 import chainio
