@@ -20,7 +20,7 @@ Printed JSON (one line, rank 0):
              c5_L100 / c5_L800 (weak), c4_strong (100 x ONE fixed 1e6-chain DB, -sensitive, block-partitioned over the
              ranks, hits gathered on rank 0 over NVLink INSIDE the timed region, digest compared with the single-GPU
              search), fastdb_sharded (-fast -db: prefilter triples all-gathered, merged bag, hits gathered; digest check),
-             c3 (SCOP40-length all-vs-all -fast on one GPU)
+             c3 (SCOP40-length all-vs-all -fast, rows of the pair triangle interleaved over the ranks; digest check)
 """
 import argparse
 import json
@@ -566,8 +566,9 @@ def leg_fastdb(B, q, blk, lo, steps, warmup):
 
 
 def leg_c3(B, steps, warmup):
-    """c3: all-vs-all `-search X -fast` on a SCOP40-sized synthetic set (11 211 chains, SCOP40-like lengths), one GPU."""
-    rb, ctx = B.rb, B.ctx
+    """c3: all-vs-all `-search X -fast` on a SCOP40-sized synthetic set (11 211 chains, SCOP40-like lengths).  Every rank holds
+    the set; the rows of the pair triangle are interleaved over the ranks, hits gathered on rank 0 (strong scaling)."""
+    rb, ctx, comm, args = B.rb, B.ctx, B.comm, B.args
     from reseek_b200 import synth
     rng = np.random.default_rng(SEED_C3)
     # SCOP40-like lengths: log-normal fitted to mean 174 / median 143, clipped to [30, 1419] (SURVEY §8 sizes)
@@ -576,30 +577,45 @@ def leg_c3(B, steps, warmup):
     B.mode(rb.MODE_FAST)
     S = B.upload_chains(s)
     npairs = s.n * (s.n + 1) // 2
-    info = {}
+    info = {"digest": None, "hits": 0}
 
     def step():
-        res = ctx.search_self(S, keep=rb.KEEP_HITS, want_paths=True)
+        res = ctx.search_self_sharded(comm, S, keep=rb.KEEP_HITS, want_paths=True)
         st = ctx.stats()
-        info.update(hits=len(res.hits), sw_pairs=st["sw_pairs"], sw_cells=st["sw_cells"], mkf_pairs=st["mkf_pairs"],
+        info.update(sw_pairs=st["sw_pairs"], sw_cells=st["sw_cells"], mkf_pairs=st["mkf_pairs"],
                     mu_ms=st["mu_kernel_ms"], sw_ms=st["sw_kernel_ms"], mkf_ms=st["mkf_kernel_ms"])
         B.launches += st["kernel_launches"]
+        if res is not None:
+            info["digest"], info["hits"] = res.digest(), len(res.hits)
         del res
 
-    t = []
-    for k in range(warmup + steps):
-        t0 = time.perf_counter()
-        step()
-        if k >= warmup:
-            t.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(t) / len(t)
+    comm.reset_stats()
+    dev_ms, wall_ms = B.timed(step, steps, warmup)
+    cs = comm.stats()
+    ncalls = steps + warmup
+    coll_ms = B.reduce([cs["collective_ms"] / ncalls])[0]
+    sent = B.reduce([float(cs["bytes_sent"]) / ncalls], "sum")[0]
+    tot = B.reduce([float(info.get("sw_pairs", 0)), float(info.get("sw_cells", 0)), float(info.get("mkf_pairs", 0))], "sum")
+    kms = B.reduce([info.get("mu_ms", 0.0), info.get("sw_ms", 0.0), info.get("mkf_ms", 0.0)])
+    check = None
+    if B.rank == 0 and not args.no_digest_check:
+        ref = ctx.search_self(S, keep=rb.KEEP_HITS, want_paths=True)
+        check = {"single_gpu_digest": "%016x" % ref.digest(), "sharded_digest": "%016x" % (info["digest"] or 0),
+                 "single_gpu_hits": len(ref.hits), "sharded_hits": info["hits"], "equal": ref.digest() == info["digest"] and len(ref.hits) == info["hits"]}
+        del ref
+        if not check["equal"]:
+            raise SystemExit(f"bench.py: c3 sharded digest differs from the single-GPU search: {check}")
+    B.barrier()
     S.free()
     B.mode(rb.MODE_VERYSENSITIVE)
     return {"workload": f"c3 all-vs-all -search X -fast: {s.n} chains, SCOP40-like lengths (mean {float(np.mean(lens)):.0f}, max {int(lens.max())}), "
-                        f"{npairs} pairs i<=j", "scaling": "single GPU", "metric": "chain_pairs_per_s", "value": npairs / (ms * 1e-3),
-            "unit": "pairs/s", "ms_per_step": ms, "steps": steps, "timing": "wall clock around rsk_search_self (plan + kernels + hit read-out)",
-            "sw_pairs": info.get("sw_pairs"), "sw_cells": info.get("sw_cells"), "long_chain_pairs": info.get("mkf_pairs"), "hits": info.get("hits"),
-            "kernel_ms": {"mu_filter": info.get("mu_ms"), "sw": info.get("sw_ms"), "long_chain": info.get("mkf_ms")}}
+                        f"{npairs} pairs i<=j, rows interleaved over {B.world} GPU(s)", "scaling": "strong", "metric": "chain_pairs_per_s",
+            "value": npairs / (wall_ms * 1e-3), "unit": "pairs/s", "ms_per_step": wall_ms, "device_ms_per_step": dev_ms, "steps": steps,
+            "timing": "wall clock around rsk_search_self_sharded (plan + kernels + hit gather + read-out on rank 0), max over ranks",
+            "sw_pairs": tot[0], "sw_cells": tot[1], "long_chain_pairs": tot[2], "hits": info["hits"],
+            "kernel_ms_max_over_ranks": {"mu_filter": kms[0], "sw": kms[1], "long_chain": kms[2]},
+            "collective": {"what": "hit gather on rank 0", "ms_per_step": coll_ms, "nvlink_bytes_per_step": sent},
+            "digest_check": check}
 
 
 def main():
@@ -663,9 +679,7 @@ def main():
             legs["fastdb_sharded"] = leg_fastdb(B, q4, blk, lo, ls, 1)
         del blk
     if "c3" in legs_wanted:
-        if B.rank == 0:
-            legs["c3"] = leg_c3(B, 1, 1)
-        B.barrier()
+        legs["c3"] = leg_c3(B, 1, 1)
 
     launches_all = B.reduce([float(B.launches)], "sum")[0]
     if B.rank == 0:

@@ -163,6 +163,12 @@ int rsk_ctx_sync(rsk_ctx *ctx);
 
 /* ---- chains: DBSearcher::LoadDB / the per-chain vectors (dbsearcher.cpp:242, dbsearcher.h:26-33) ---- */
 int rsk_chainset_upload(rsk_ctx *ctx, const rsk_chains_host *chains, rsk_chainset **out);
+/* Same, without waiting for the copies: they are queued on the context stream ahead of any later search call.  Arrays in
+ * pageable memory have been read when the call returns (they are staged through the context's own pinned buffers, worker
+ * threads filling one buffer while the other is on the bus); arrays in PINNED memory are read by the DMA itself and must stay
+ * untouched until rsk_ctx_sync() or the next call on this context that returns results.  The streamed side of RunQuery
+ * (runquery.cpp:82-125: the next block is read while the current one is aligned) uses this. */
+int rsk_chainset_upload_async(rsk_ctx *ctx, const rsk_chains_host *chains, rsk_chainset **out);
 uint32_t rsk_chainset_count(const rsk_chainset *cs);
 uint64_t rsk_chainset_residues(const rsk_chainset *cs);
 void rsk_chainset_free(rsk_chainset *cs);
@@ -241,6 +247,10 @@ int rsk_prefilter(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset *T, co
  * (target indices shifted to the unsharded DB) and every rank applies the bag: the result equals the single-GPU one. */
 int rsk_prefilter_bag(uint32_t nq, uint64_t n, const uint32_t *t, const uint32_t *q, const uint16_t *s, uint32_t rsb_size,
 		rsk_prefilter_result **out);
+/* The same bag replayed on the device over caller-supplied triples (one warp per query; the kernel the sharded search runs on the
+ * all-gathered stream).  Result identical to rsk_prefilter_bag. */
+int rsk_prefilter_bag_device(rsk_ctx *ctx, uint32_t nq, uint64_t n, const uint32_t *t, const uint32_t *q, const uint16_t *s,
+		uint32_t rsb_size, rsk_prefilter_result **out);
 /* the candidates with t_lo <= target < t_hi, targets re-based to t_lo (one rank's share of a merged list); host only */
 int rsk_prefilter_select(const rsk_prefilter_result *r, uint32_t t_lo, uint32_t t_hi, rsk_prefilter_result **out);
 uint64_t rsk_prefilter_count(const rsk_prefilter_result *r);          /* candidate (target, query) pairs */
@@ -298,6 +308,10 @@ int rsk_partition_by_residues(const uint32_t *len, uint32_t n, int nranks, uint3
  * of the unsharded search (hit.a = DB chain index in the whole DB); *out is NULL on the other ranks. */
 int rsk_search_cross_sharded(rsk_ctx *ctx, rsk_comm *comm, const rsk_chainset *A_local, const rsk_chainset *B, uint32_t a_base,
 		const rsk_search_opts *opts, int root, rsk_results **out);
+/* DBSearcher::RunSelf (runself.cpp:72-145) over several GPUs: every rank holds the whole set S and takes the rows i = rank,
+ * rank + nranks, ... of the pair triangle (i <= j); the hits are gathered on `root` and returned there in the order of
+ * rsk_search_self with RSK_KEEP_HITS (a ascending, then b); *out is NULL on the other ranks. */
+int rsk_search_self_sharded(rsk_ctx *ctx, rsk_comm *comm, const rsk_chainset *S, const rsk_search_opts *opts, int root, rsk_results **out);
 /* `reseek -search Q -db DB -fast` with T_local = this rank's block of the DB (t_base = its first target index): local prefilter
  * kernels, triples all-gathered in rank order, the bag replayed on the merged stream, the candidates of the own block
  * post-filtered, hits gathered on `root` (hit.a = query, hit.b = target index in the whole DB).  cands_out (optional, every

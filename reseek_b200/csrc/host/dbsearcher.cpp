@@ -237,9 +237,52 @@ void DBSearcher::RunSelf()
 	O.want_paths = 1;
 	rsk_results *Res = 0;
 	double tp = NowMs();
-	Check(rsk_search_self(C, m_DBSet, &O, &Res));
-	Phase("RunSelf: rsk_search_self", tp);
-	AddStats();
+	SetupRanks();
+	if (m_RankCtx.size() > 1)
+		{
+		// rows of the pair triangle interleaved over the GPUs, hits gathered on the first (rsk_search_self_sharded)
+		const uint N = RSK_SIZE(m_RankCtx);
+		vector<rsk_stats> Stats(N);
+		vector<string> Errors(N);
+		auto Work = [&](uint r)
+			{
+			rsk_results *Mine = 0;
+			if (rsk_ctx_set_params(m_RankCtx[r], &R) != RSK_OK ||
+			  rsk_search_self_sharded(m_RankCtx[r], m_RankComm[r], r == 0 ? m_DBSet : m_RankDB[r], &O, 0, &Mine) != RSK_OK)
+				Errors[r] = rsk_last_error();
+			rsk_ctx_stats(m_RankCtx[r], &Stats[r]);
+			if (r == 0)
+				Res = Mine;
+			};
+		vector<std::thread> Threads;
+		for (uint r = 1; r < N; ++r)
+			Threads.emplace_back(Work, r);
+		Work(0);
+		for (std::thread &t : Threads)
+			t.join();
+		for (uint r = 0; r < N; ++r)
+			if (!Errors[r].empty())
+				Die("reseek_b200 (GPU %u): %s", r, Errors[r].c_str());
+		for (uint r = 0; r < N; ++r)
+			{
+			const rsk_stats &S = Stats[r];
+			DSSAligner::m_AlnCount += (uint)S.pairs;
+			DSSAligner::m_SWCount += (uint)S.sw_pairs;
+			DSSAligner::m_MuFilterInputCount += (uint)S.mu_filter_in;
+			DSSAligner::m_MuFilterDiscardCount += (uint)S.mu_filter_rejected;
+			DSSAligner::m_ParasailSaturateCount += (uint)S.mu_saturated;
+			DSSAligner::m_XDropAlnCount += (uint)S.mkf_pairs;
+			m_ProcessedPairCount += (uint)S.pairs;
+			}
+		m_LastStats = Stats[0];
+		Phase("RunSelf: rsk_search_self_sharded", tp);
+		}
+	else
+		{
+		Check(rsk_search_self(C, m_DBSet, &O, &Res));
+		Phase("RunSelf: rsk_search_self", tp);
+		AddStats();
+		}
 	const uint64_t N = rsk_results_count(Res);
 	const rsk_hit *Hits = rsk_results_hits(Res);
 	const char *Pool = rsk_results_paths(Res);

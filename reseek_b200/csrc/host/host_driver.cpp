@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "dbsearcher.h"
+#include "scop40bench.h"
 
 using namespace reseek_b200;
 
@@ -449,6 +450,56 @@ int main(int argc, char **argv)
 		return ReseekSearch(argc, argv);
 	if (Cmd == "-alignpair")
 		return ReseekAlignPair(argc, argv);
+	if (Cmd == "-scop40bench" && argc >= 4)
+		{
+		// cmd_scop40bench (scop40bench.cpp:767-823): rsk_host_demo -scop40bench X.bca -lookup dom_scopid.tsv -fast|-sensitive|-verysensitive
+		string LookupFN;
+		int Mode = -1;
+		for (int i = 3; i < argc; ++i)
+			{
+			const string a = argv[i];
+			if (a == "-lookup" && i + 1 < argc) LookupFN = argv[++i];
+			else if (a == "-fast") Mode = AM_Fast;
+			else if (a == "-sensitive") Mode = AM_Sensitive;
+			else if (a == "-verysensitive") Mode = AM_VerySensitive;
+			else Die("Unknown option %s", a.c_str());
+			}
+		if (Mode < 0)
+			Die("Must set -fast, -sensitive or -verysensitive");
+		if (LookupFN.empty())
+			Die("-lookup FILE (domain <tab> scop id) required");
+		DSSParams Params;
+		Params.SetMode((ALGO_MODE) Mode);
+		SCOP40Bench SB;
+		SB.m_Params = &Params;
+		SB.ReadLookup(LookupFN);
+		SB.LoadDB(argv[2]);
+		SB.Setup();
+		SB.m_QuerySelf = true;
+		SB.RunSelf();
+		SB.SetStats();
+		SB.WriteSummary(stdout);
+		return 0;
+		}
+	if (Cmd == "bcarange" && argc >= 5)
+		{
+		// the block of a .bca that rank argv[3] of argv[4] processes reads (ChainReader2::OpenRange): "lo hi first-label last-label residues"
+		ChainReader2 CR;
+		CR.OpenRange(argv[2], (uint) atoi(argv[3]), (uint) atoi(argv[4]));
+		uint Count = 0;
+		uint64_t Residues = 0;
+		string First, Last;
+		while (PDBChain *Chain = CR.GetNext())
+			{
+			if (Count++ == 0)
+				First = Chain->m_Label;
+			Last = Chain->m_Label;
+			Residues += Chain->GetSeqLength();
+			delete Chain;
+			}
+		printf("%u %u %s %s %llu\n", CR.GetFirstIdx(), CR.GetFirstIdx() + Count, First.c_str(), Last.c_str(), (unsigned long long) Residues);
+		return 0;
+		}
 	if (Cmd == "features" && argc >= 4)
 		{
 		// DSS stage only (on the GPU, chain by chain through the DSS look-alike; no self-reverse scores)

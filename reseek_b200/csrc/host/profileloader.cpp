@@ -19,6 +19,19 @@ void ChainReader2::Open(const string &FN)
 		Die("%s: only .bca input is read by this layer (convert with `reseek -convert ... -bca`)", FN.c_str());
 	m_BCA.Open(FN);
 	m_NextIdx = 0;
+	m_FirstIdx = 0;
+	m_EndIdx = UINT_MAX;
+	}
+
+void ChainReader2::OpenRange(const string &FN, uint Rank, uint RankCount)
+	{
+	Open(FN);
+	rsk_asserta(RankCount > 0 && Rank < RankCount);
+	vector<uint32_t> Bounds(RankCount + 1);
+	Check(rsk_partition_by_residues(m_BCA.m_SeqLengths.data(), m_BCA.GetChainCount(), (int) RankCount, Bounds.data()));
+	m_FirstIdx = Bounds[Rank];
+	m_NextIdx = Bounds[Rank];
+	m_EndIdx = Bounds[Rank + 1];
 	}
 
 PDBChain *ChainReader2::GetNext()
@@ -28,7 +41,7 @@ PDBChain *ChainReader2::GetNext()
 		uint Idx;
 			{
 			std::lock_guard<std::mutex> Guard(m_Lock);
-			if (m_NextIdx >= m_BCA.GetChainCount())
+			if (m_NextIdx >= m_BCA.GetChainCount() || m_NextIdx >= m_EndIdx)
 				return 0;
 			Idx = m_NextIdx++;
 			}

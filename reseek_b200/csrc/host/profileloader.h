@@ -18,8 +18,16 @@ public:
 	std::mutex m_Lock;
 	uint m_NextIdx = 0;
 
+	uint m_EndIdx = UINT_MAX; // one past the last chain this reader delivers
+
 public:
 	void Open(const string &FN);
+	// Rank `Rank` of `RankCount` processes sharing one .bca: this reader delivers only the rank's contiguous, residue-balanced
+	// block of chains (rsk_partition_by_residues over the file's length table, bcadata.cpp:140-168 - no chain data is read to
+	// find it; each chain record is then fetched by its own file offset).  GetFirstIdx() is the block's a_base / t_base.
+	void OpenRange(const string &FN, uint Rank, uint RankCount);
+	uint GetFirstIdx() const { return m_FirstIdx; }
+	uint m_FirstIdx = 0;
 	PDBChain *GetNext();   // 0 at the end; chains of length 0 are skipped (chainreader2.cpp:103-107)
 	uint GetChainCount() const { return m_BCA.GetChainCount(); }
 	};

@@ -69,13 +69,21 @@ __global__ void pf_query_kmers_kernel(const PfArgs a)
 	a.qk_val[i] = (q << 16) | pos;
 }
 
-// ---- K6b/c: neighbourhoods.  One warp per query 5-mer; lanes split the first two letters, DFS with bounds. ----
+// ---- K6b/c: neighbourhoods.  One warp per query 5-mer X: every 5-mer Y with score(X, Y) >= 36. ----
+// Branch and bound over the letters of Y with the best achievable remainder as bound, breadth first and warp-wide: the lanes
+// scan the 36^3 prefixes (y0, y1, y2); survivors are compacted (ballot) into a shared-memory queue; a full queue is expanded
+// by y3 with ALL lanes working on flattened (entry, letter) pairs, its survivors are queued and expanded by y4 the same way.
+// (The depth-first form - each lane walking the subtree of its own prefixes - ran with 3 of 32 lanes active: subtree sizes
+// differ by orders of magnitude.)
+constexpr int kNbQ3 = 256, kNbQ4 = 1024, kNbWarps = 4;
 template <bool FILL>
-__global__ void __launch_bounds__(128) pf_neighborhood_kernel(const PfArgs a)
+__global__ void __launch_bounds__(kNbWarps * 32) pf_neighborhood_kernel(const PfArgs a)
 {
 	__shared__ int S[36 * 36];
 	__shared__ int rowmax[36];
-	__shared__ unsigned s_cursor[4];
+	__shared__ uint32_t s_q3[kNbWarps][kNbQ3];  // prefix3 << 8 | (p3 + 128)
+	__shared__ uint32_t s_q4[kNbWarps][kNbQ4];  // prefix4 << 8 | (p4 + 128)
+	__shared__ uint8_t s_ge4[kNbWarps][256];
 	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
 		S[k] = a.kmer_mx[k];
 	__syncthreads();
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(128) pf_neighborhood_kernel(const PfArgs a)
 	}
 	__syncthreads();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t i = blockIdx.x * 4 + warp;
+	const uint32_t i = blockIdx.x * kNbWarps + warp;
 	if (i >= a.nqk)
 		return;
 	const uint32_t code = a.qk_code[i];
@@ -102,57 +110,116 @@ __global__ void __launch_bounds__(128) pf_neighborhood_kernel(const PfArgs a)
 		for (int k = 4; k >= 0; --k) { x[k] = (int)(c % 36); c /= 36; }
 	}
 	const int *r0 = S + 36 * x[0], *r1 = S + 36 * x[1], *r2 = S + 36 * x[2], *r3 = S + 36 * x[3], *r4 = S + 36 * x[4];
-	const int m4 = rowmax[x[4]], m34 = rowmax[x[3]] + m4, m234 = rowmax[x[2]] + m34;
+	const int m4 = rowmax[x[4]], m34 = rowmax[x[3]] + m4;
 	const uint32_t val = a.qk_val[i];
-	unsigned long long base = 0;
-	if (FILL) {
-		base = a.nb_off[i];
-		if (lane == 0)
-			s_cursor[warp] = 0;
+	const unsigned long long base = FILL ? a.nb_off[i] : 0;
+	uint32_t *q3 = s_q3[warp], *q4 = s_q4[warp];
+	const unsigned lt = (1u << lane) - 1u;
+	unsigned n3 = 0, n4 = 0, nout = 0;
+
+	// counting pass: how many last letters reach the threshold is a function of the prefix score alone - one table look-up
+	// per queued prefix instead of 36 tests (s_ge4[k] = number of y4 with S[x4][y4] >= k - 128)
+	uint8_t *ge4 = s_ge4[warp];
+	if (!FILL) {
+		for (int k = lane; k < 256; k += 32) {
+			int c = 0;
+			for (int y = 0; y < 36; ++y)
+				c += r4[y] >= k - 128;
+			ge4[k] = (uint8_t)c;
+		}
 		__syncwarp();
 	}
-	unsigned cnt = 0;
-	for (int yy = lane; yy < 36 * 36; yy += 32) {
-		const int y0 = yy / 36, y1 = yy - 36 * y0;
-		const int p2 = r0[y0] + r1[y1];
-		if (p2 + m234 < kMinPair)
-			continue;
-		for (int y2 = 0; y2 < 36; ++y2) {
-			const int p3 = p2 + r2[y2];
-			if (p3 + m34 < kMinPair)
-				continue;
-			for (int y3 = 0; y3 < 36; ++y3) {
-				const int p4 = p3 + r3[y3];
-				if (p4 + m4 < kMinPair)
-					continue;
-				for (int y4 = 0; y4 < 36; ++y4) {
-					if (p4 + r4[y4] >= kMinPair) {
-						if (FILL) {
-							const unsigned slot = atomicAdd(&s_cursor[warp], 1u);
-							const uint32_t y = (((uint32_t)(y0 * 36 + y1) * 36 + y2) * 36 + y3) * 36 + y4;
-							a.ix_key[base + slot] = y;
-							a.ix_val[base + slot] = val;
-						} else {
-							++cnt;
-						}
-					}
+	unsigned acc = 0;  // counting pass: this lane's share of the neighbourhood size
+	auto drain4 = [&]() {  // expand the queued 4-letter prefixes by y4
+		const unsigned cnt4 = n4;
+		n4 = 0;
+		if (FILL) {
+			for (unsigned idx = lane; idx < ((cnt4 * 36 + 31) & ~31u); idx += 32) {
+				bool hit = false;
+				uint32_t y = 0;
+				if (idx < cnt4 * 36) {
+					const unsigned e = idx / 36, y4 = idx - e * 36;
+					const uint32_t q = q4[e];
+					hit = (int)(q & 0xffu) - 128 + r4[y4] >= kMinPair;
+					y = (q >> 8) * 36 + y4;
 				}
+				const unsigned m = __ballot_sync(kFull, hit);
+				if (hit) {
+					const unsigned slot = nout + __popc(m & lt);
+					a.ix_key[base + slot] = y;
+					a.ix_val[base + slot] = val;
+				}
+				nout += __popc(m);
+			}
+		} else {
+			for (unsigned e = lane; e < cnt4; e += 32)
+				acc += ge4[kMinPair + 256 - (int)(q4[e] & 0xffu)];
+		}
+		__syncwarp();
+	};
+	auto drain3 = [&]() {  // expand the queued 3-letter prefixes by y3
+		for (unsigned idx = lane; idx < ((n3 * 36 + 31) & ~31u); idx += 32) {
+			bool ok = false;
+			uint32_t q = 0;
+			if (idx < n3 * 36) {
+				const unsigned e = idx / 36, y3 = idx - e * 36;
+				const uint32_t q0 = q3[e];
+				const int p4 = (int)(q0 & 0xffu) - 128 + r3[y3];
+				ok = p4 + m4 >= kMinPair;
+				q = (((q0 >> 8) * 36 + y3) << 8) | (uint32_t)(p4 + 128);
+			}
+			const unsigned m = __ballot_sync(kFull, ok);
+			if (ok)
+				q4[n4 + __popc(m & lt)] = q;
+			n4 += __popc(m);
+			__syncwarp();
+			if (n4 > kNbQ4 - 32)
+				drain4();
+		}
+		n3 = 0;
+		__syncwarp();
+	};
+
+	int y0 = 0, y1 = 0, y2 = lane;  // lane < 36: prefix index = 32 * it + lane
+	for (int it = 0; it < (36 * 36 * 36 + 31) / 32; ++it) {
+		bool ok = false;
+		uint32_t q = 0;
+		if (y0 < 36) {
+			const int p3 = r0[y0] + r1[y1] + r2[y2];
+			ok = p3 + m34 >= kMinPair;
+			q = ((uint32_t)((y0 * 36 + y1) * 36 + y2) << 8) | (uint32_t)(p3 + 128);
+		}
+		const unsigned m = __ballot_sync(kFull, ok);
+		if (m) {
+			if (ok)
+				q3[n3 + __popc(m & lt)] = q;
+			n3 += __popc(m);
+			__syncwarp();
+			if (n3 > kNbQ3 - 32)
+				drain3();
+		}
+		y2 += 32;
+		if (y2 >= 36) {
+			y2 -= 36;
+			if (++y1 >= 36) {
+				y1 = 0;
+				++y0;
 			}
 		}
 	}
+	drain3();
+	drain4();
 	if (FILL) {
-		__syncwarp();
-		if (a.exact_twice && lane == 0) {  // the k-mer itself, entered before its neighbourhood (mudex.cpp:146-174)
-			const unsigned slot = s_cursor[warp];
-			a.ix_key[base + slot] = code;
-			a.ix_val[base + slot] = val;
+		if (a.exact_twice && lane == 0) {  // the k-mer itself is entered a second time (mudex.cpp:146-174)
+			a.ix_key[base + nout] = code;
+			a.ix_val[base + nout] = val;
 		}
 	} else {
 #pragma unroll
 		for (int o = 16; o >= 1; o >>= 1)
-			cnt += __shfl_xor_sync(kFull, cnt, o);
+			acc += __shfl_xor_sync(kFull, acc, o);
 		if (lane == 0)
-			a.nb_count[i] = cnt + (a.exact_twice ? 1u : 0u);
+			a.nb_count[i] = acc + (a.exact_twice ? 1u : 0u);
 	}
 }
 
@@ -260,8 +327,36 @@ __global__ void __launch_bounds__(128) pf_extend_kernel(const PfArgs a)
 			int qi = (int)LQ - d - 1, tj = 0;
 			if (qi < 0) { tj = -qi; qi = 0; }
 			int B = 0, F = 0;
-			for (; qi < (int)LQ && tj < (int)LT; ++qi, ++tj) {  // prefiltermu.cpp:27-46
-				F += S[36 * Q[qi] + T[tj]];
+			// prefiltermu.cpp:27-46, four positions per trip: the letters of both chains come as 32-bit words assembled from
+			// aligned loads (one new word per chain and trip) - the kernel was bound by its byte loads (L1 data pipe 88 % busy)
+			int n = min((int)LQ - qi, (int)LT - tj);
+			const uint8_t *qp = Q + qi, *tp = T + tj;
+			if (n >= 8) {
+				const uint32_t *qw = reinterpret_cast<const uint32_t *>((uintptr_t)qp & ~(uintptr_t)3);
+				const uint32_t *tw = reinterpret_cast<const uint32_t *>((uintptr_t)tp & ~(uintptr_t)3);
+				const unsigned qs = ((uintptr_t)qp & 3u) * 8u, ts = ((uintptr_t)tp & 3u) * 8u;
+				uint32_t q0 = __ldg(qw), t0 = __ldg(tw);
+				const int groups = n >> 2;
+				for (int g = 0; g < groups; ++g) {
+					// the next aligned word holds at least one letter of this group whenever the chain's pointer is unaligned
+					uint32_t q1 = q0, t1 = t0;
+					if (qs || g + 1 < groups) q1 = __ldg(++qw);
+					if (ts || g + 1 < groups) t1 = __ldg(++tw);
+					const uint32_t qv = qs ? __funnelshift_r(q0, q1, qs) : q0;
+					const uint32_t tv = ts ? __funnelshift_r(t0, t1, ts) : t0;
+					q0 = q1; t0 = t1;
+#pragma unroll
+					for (int b = 0; b < 4; ++b) {
+						F += S[36 * ((qv >> (8 * b)) & 0xffu) + ((tv >> (8 * b)) & 0xffu)];
+						if (F > B) B = F;
+						else if (F < 0) F = 0;
+					}
+				}
+				qp += 4 * groups; tp += 4 * groups;
+				n -= 4 * groups;
+			}
+			for (int k = 0; k < n; ++k) {
+				F += S[36 * qp[k] + tp[k]];
 				if (F > B) B = F;
 				else if (F < 0) F = 0;
 			}
@@ -310,14 +405,14 @@ __global__ void pf_write_cands_kernel(const PfArgs a, uint32_t ntl)
 // the vectors hold 2B entries, TruncateVecs then keeps the first B of QuickSortOrderDesc (sort.h:71-108).  That quicksort is
 // unstable, and which of the tied entries survive at the cut-off - and how the survivors are arranged for the NEXT
 // truncation - is decided by its exact swap sequence, so it is restated (Hoare partition around the middle element) and run
-// by one lane on shared memory; the admission scan, the gather of the survivors and the output are warp-parallel.
-__device__ void bag_quicksort_desc(uint16_t *vs, uint32_t *order, int n)
+// on shared memory: its partition steps by the whole warp with the serial loop's exact permutation (bag_partition_warp), the
+// small ranges serially, one lane each; the admission scan, the gather of the survivors and the output are warp-parallel too.
+__device__ void bag_quicksort_desc(uint16_t *vs, uint32_t *order, int left, int right)
 {
 	// vs[i] mirrors Values[Order[i]] and is swapped together with order[i]; sub-ranges are disjoint, so the order in which the
 	// recursion visits them is irrelevant: an explicit stack, larger half pushed, bounds the depth by log2(n)
 	int stack_l[32], stack_r[32];
 	int sp = 0;
-	int left = 0, right = n - 1;
 	for (;;) {
 		while (left < right) {
 			int i = left, j = right;
@@ -359,6 +454,116 @@ __device__ void bag_quicksort_desc(uint16_t *vs, uint32_t *order, int n)
 	}
 }
 
+// One partition step of that quicksort on [left, right], by the whole warp, with the permutation the serial loop produces.
+// The serial loop swaps the k-th position from the left whose value is <= pivot with the k-th position from the right whose
+// value is >= pivot, k = 0, 1, ... while the left one is not beyond the right one; both sequences can be read off the
+// UNCHANGED array (the scanning indices never re-enter swapped territory before they cross), the swapped positions are
+// pairwise distinct, and where the two indices end follows from the first unswapped stop on either side.
+__device__ void bag_partition_warp(uint16_t *vs, uint32_t *order, const int left, const int right, uint16_t *lpos, uint16_t *rpos,
+		const int lane, int &iout, int &jout)
+{
+	const unsigned lt = (1u << lane) - 1u;
+	const uint16_t pivot = vs[(left + right) / 2];
+	int nL = 0, nR = 0;
+	for (int b = left; b <= right; b += 32) {
+		const int p = b + lane;
+		const bool ok = p <= right && vs[p] <= pivot;
+		const unsigned m = __ballot_sync(kFull, ok);
+		if (ok)
+			lpos[nL + __popc(m & lt)] = (uint16_t)p;
+		nL += __popc(m);
+	}
+	for (int b = right; b >= left; b -= 32) {
+		const int p = b - lane;
+		const bool ok = p >= left && vs[p] >= pivot;
+		const unsigned m = __ballot_sync(kFull, ok);
+		if (ok)
+			rpos[nR + __popc(m & lt)] = (uint16_t)p;
+		nR += __popc(m);
+	}
+	__syncwarp();
+	const int nmin = min(nL, nR);
+	int K = 0;
+	for (int k = lane; k < nmin; k += 32)
+		K += lpos[k] <= rpos[k];
+#pragma unroll
+	for (int o = 16; o >= 1; o >>= 1)
+		K += __shfl_xor_sync(kFull, K, o);
+	// K >= 1: the pivot's own position is in both sequences
+	const int a_last = lpos[K - 1], b_last = rpos[K - 1];
+	int i = a_last + 1, j = b_last - 1;
+	if (i <= j) {
+		i = (K < nL && lpos[K] < b_last) ? lpos[K] : b_last;
+		j = (K < nR && rpos[K] > a_last) ? rpos[K] : a_last;
+	}
+	for (int k = lane; k < K; k += 32) {
+		const int pa = lpos[k], pb = rpos[k];
+		if (pa != pb) {
+			const uint16_t tv = vs[pa]; vs[pa] = vs[pb]; vs[pb] = tv;
+			const uint32_t to = order[pa]; order[pa] = order[pb]; order[pb] = to;
+		}
+	}
+	__syncwarp();
+	iout = i;
+	jout = j;
+}
+
+// QuickSortOrderDesc over vs/order[0..n): large ranges are partitioned by the warp, ranges below kBagSmall are collected and
+// then sorted serially, one lane per range (the ranges are disjoint).
+constexpr int kBagSmall = 96, kBagRanges = 512;
+__device__ void bag_sort_warp(uint16_t *vs, uint32_t *order, const int n, uint16_t *lpos, uint16_t *rpos, int *ranges, const int lane)
+{
+	// ranges[]: a stack of large ranges growing up from 0 (2 ints each), the list of small ranges growing down from the end
+	int nbig = 0, nsmall = 0;
+	int left = 0, right = n - 1;
+	bool have = n > 1;
+	while (have || nbig > 0) {
+		if (!have) {
+			--nbig;
+			left = ranges[2 * nbig];
+			right = ranges[2 * nbig + 1];
+		}
+		have = false;
+		if (right - left + 1 < kBagSmall || nsmall + nbig + 2 >= kBagRanges) {
+			if (nsmall + nbig + 1 < kBagRanges) {
+				if (lane == 0) {
+					ranges[2 * (kBagRanges - 1 - nsmall)] = left;
+					ranges[2 * (kBagRanges - 1 - nsmall) + 1] = right;
+				}
+				++nsmall;
+			} else {  // no room to remember it: sort it now
+				if (lane == 0)
+					bag_quicksort_desc(vs, order, left, right);
+				__syncwarp();
+			}
+			continue;
+		}
+		int i, j;
+		bag_partition_warp(vs, order, left, right, lpos, rpos, lane, i, j);
+		const bool hasL = left < j, hasR = i < right;
+		if (hasL && hasR) {
+			if (lane == 0) {
+				ranges[2 * nbig] = i;
+				ranges[2 * nbig + 1] = right;
+			}
+			++nbig;
+			right = j;
+			have = true;
+		} else if (hasL) {
+			right = j;
+			have = true;
+		} else if (hasR) {
+			left = i;
+			have = true;
+		}
+		__syncwarp();
+	}
+	__syncwarp();
+	for (int k = lane; k < nsmall; k += 32)
+		bag_quicksort_desc(vs, order, ranges[2 * (kBagRanges - 1 - k)], ranges[2 * (kBagRanges - 1 - k) + 1]);
+	__syncwarp();
+}
+
 __global__ void __launch_bounds__(32) pf_bag_kernel(const unsigned long long *__restrict__ val, const unsigned long long *__restrict__ seg_begin,
 		const unsigned long long *__restrict__ seg_end, uint32_t B, unsigned long long *out_key, uint32_t *out_n)
 {
@@ -368,6 +573,9 @@ __global__ void __launch_bounds__(32) pf_bag_kernel(const unsigned long long *__
 	uint32_t *t2 = order + 2 * B;               // [B]
 	uint16_t *s = (uint16_t *)(t2 + B);         // [2B] score of entry i
 	uint16_t *vs = s + 2 * B;                   // [2B] s[order[i]]
+	uint16_t *lpos = vs + 2 * B;                // [2B] scratch of the warp partition
+	uint16_t *rpos = lpos + 2 * B;              // [2B]
+	int *ranges = (int *)(((uintptr_t)(rpos + 2 * B) + 3) & ~(uintptr_t)3);  // [2 * kBagRanges]
 	const uint32_t q = blockIdx.x, lane = threadIdx.x;
 	unsigned long long pos = seg_begin[q];
 	const unsigned long long end = seg_end[q];
@@ -378,9 +586,7 @@ __global__ void __launch_bounds__(32) pf_bag_kernel(const unsigned long long *__
 			vs[k] = s[k];
 		}
 		__syncwarp();
-		if (lane == 0)
-			bag_quicksort_desc(vs, order, (int)n);
-		__syncwarp();
+		bag_sort_warp(vs, order, (int)n, lpos, rpos, ranges, (int)lane);
 		for (uint32_t k = lane; k < B; k += 32)
 			t2[k] = t[order[k]];
 		__syncwarp();
@@ -511,9 +717,9 @@ int pf_launch_neighborhood(const PfArgs &a, bool fill, cudaStream_t st)
 	if (a.nqk == 0)
 		return 0;
 	if (fill)
-		pf_neighborhood_kernel<true><<<(a.nqk + 3) / 4, 128, 0, st>>>(a);
+		pf_neighborhood_kernel<true><<<(a.nqk + kNbWarps - 1) / kNbWarps, kNbWarps * 32, 0, st>>>(a);
 	else
-		pf_neighborhood_kernel<false><<<(a.nqk + 3) / 4, 128, 0, st>>>(a);
+		pf_neighborhood_kernel<false><<<(a.nqk + kNbWarps - 1) / kNbWarps, kNbWarps * 32, 0, st>>>(a);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -555,7 +761,7 @@ int pf_launch_cands(const PfArgs &a, uint32_t ntl, bool write, cudaStream_t st)
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-size_t pf_bag_smem_bytes(uint32_t B) { return (size_t)B * (4 * 2 + 4 * 2 + 4 + 2 * 2 + 2 * 2) + 16; }
+size_t pf_bag_smem_bytes(uint32_t B) { return (size_t)B * (4 * 2 + 4 * 2 + 4 + 2 * 2 + 2 * 2 + 2 * 2 + 2 * 2) + 8 * kBagRanges + 32; }
 
 // stable sort of the triples by query (16 key bits), value = target<<16 | score
 int pf_sort_by_query(const uint32_t *qin, uint32_t *qout, const unsigned long long *vin, unsigned long long *vout, unsigned long long n,

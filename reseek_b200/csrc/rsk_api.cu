@@ -330,6 +330,9 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->pf_scratch = nullptr;
 	ctx->upload_stage.release();
 	ctx->sink.release(); ctx->h_sink[0].release(); ctx->h_sink[1].release();
+	ctx->h_up[0].release(); ctx->h_up[1].release();
+	for (auto &e : ctx->ev_up)
+		if (e) cudaEventDestroy(e);
 	ctx->dss_ss.release(); ctx->dss_conf.release(); ctx->dss_aa.release(); ctx->dss_dens.release(); ctx->dss_helix.release();
 	if (ctx->d_dss_tables) cudaFree(ctx->d_dss_tables);
 	ctx->ckpt.release(); ctx->tile.release(); ctx->best.release(); ctx->bnd.release(); ctx->stage.release(); ctx->rec.release(); ctx->pool.release();
@@ -453,7 +456,72 @@ extern "C" void rsk_chainset_free(rsk_chainset *cs)
 extern "C" uint32_t rsk_chainset_count(const rsk_chainset *cs) { return cs ? cs->d.n : 0; }
 extern "C" uint64_t rsk_chainset_residues(const rsk_chainset *cs) { return cs ? cs->d.total : 0; }
 
+// Host -> device copy of caller memory on the context stream.  Pinned (or registered) sources go straight to the copy engine.
+// Pageable sources are staged through the context's two pinned buffers in 32 MB chunks: worker threads fill buffer i+1 while
+// buffer i is on the bus, so a caller with ordinary malloc'ed arrays (the reference's vectors, a numpy array) gets the full
+// PCIe rate instead of the driver's single-threaded bounce path.  On return the caller's memory is no longer needed unless
+// *direct is set (the source was pinned and the DMA may still be reading it).
+int rsk_h2d(rsk_ctx *ctx, void *dst, const void *src, size_t bytes, bool *direct)
+{
+	if (bytes == 0)
+		return RSK_OK;
+	cudaStream_t st = ctx->stream;
+	cudaPointerAttributes at;
+	const bool known = cudaPointerGetAttributes(&at, src) == cudaSuccess;
+	cudaGetLastError();
+	const bool pinned = known && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+	if (pinned || bytes < ((size_t)1 << 20)) {
+		CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+		if (pinned && direct)
+			*direct = true;
+		return RSK_OK;
+	}
+	const size_t chunk = (size_t)32 << 20;
+	for (int k = 0; k < 2; ++k) {
+		if (ctx->h_up[k].ensure(std::min(bytes, chunk)))
+			return fail(RSK_ERR_NOMEM, "pinned upload staging");
+		if (!ctx->ev_up[k])
+			CK(cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming));
+	}
+	const size_t nchunks = (bytes + chunk - 1) / chunk;
+	for (size_t c = 0; c < nchunks; ++c) {
+		const size_t off = c * chunk, n = std::min(chunk, bytes - off);
+		const int buf = (int)(c & 1);
+		if (ctx->up_busy[buf])
+			CK(cudaEventSynchronize(ctx->ev_up[buf]));  // the DMA that last read this buffer
+		const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->host_threads, n >> 21));
+		if (T == 1) {
+			memcpy(ctx->h_up[buf].p, (const char *)src + off, n);
+		} else {
+			std::vector<std::thread> th;
+			for (int t = 0; t < T; ++t)
+				th.emplace_back([=]() {
+					const size_t b0 = n * (size_t)t / T, b1 = n * (size_t)(t + 1) / T;
+					memcpy(ctx->h_up[buf].p + b0, (const char *)src + off + b0, b1 - b0);
+				});
+			for (auto &t : th)
+				t.join();
+		}
+		CK(cudaMemcpyAsync((char *)dst + off, ctx->h_up[buf].p, n, cudaMemcpyHostToDevice, st));
+		CK(cudaEventRecord(ctx->ev_up[buf], st));
+		ctx->up_busy[buf] = true;
+	}
+	return RSK_OK;
+}
+
+static int chainset_upload_impl(rsk_ctx *ctx, const rsk_chains_host *h, rsk_chainset **out, bool async);
+
 extern "C" int rsk_chainset_upload(rsk_ctx *ctx, const rsk_chains_host *h, rsk_chainset **out)
+{
+	return chainset_upload_impl(ctx, h, out, false);
+}
+
+extern "C" int rsk_chainset_upload_async(rsk_ctx *ctx, const rsk_chains_host *h, rsk_chainset **out)
+{
+	return chainset_upload_impl(ctx, h, out, true);
+}
+
+static int chainset_upload_impl(rsk_ctx *ctx, const rsk_chains_host *h, rsk_chainset **out, bool async)
 {
 	if (!ctx || !h || !out)
 		return fail(RSK_ERR_ARG, "rsk_chainset_upload: null argument");
@@ -505,27 +573,37 @@ extern "C" int rsk_chainset_upload(rsk_ctx *ctx, const rsk_chains_host *h, rsk_c
 	if (h->selfrev)
 		sr.assign(h->selfrev, h->selfrev + d.n);
 	cudaError_t e = cudaSuccess;
+	bool direct = false;  // some caller buffer is pinned and read by the DMA itself
 	auto cp = [&](void *dst, const void *src, size_t bytes) {
-		if (e == cudaSuccess)
-			e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess && rsk_h2d(ctx, dst, src, bytes, &direct) != RSK_OK)
+			e = cudaErrorUnknown;
 	};
 	cp(d.len, h->len, sizeof(uint32_t) * d.n);
-	cp(d.off, cs->hoff.data(), sizeof(uint64_t) * d.n);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(d.off, cs->hoff.data(), sizeof(uint64_t) * d.n, cudaMemcpyHostToDevice, st);  // lives in the set
 	cp(d_planes, h->prof, (size_t)RSK_NFEAT * tot);
 	cp(d.x, h->xyz, sizeof(float) * tot);
 	cp(d.y, h->xyz + tot, sizeof(float) * tot);
 	cp(d.z, h->xyz + 2 * tot, sizeof(float) * tot);
-	cp(d.selfrev, sr.data(), sizeof(float) * d.n);
 	if (h->mu)
 		cp(d.mu, h->mu, tot);
+	if (e == cudaSuccess && h->selfrev)
+		cp(d.selfrev, h->selfrev, sizeof(float) * d.n);
+	else if (e == cudaSuccess) {
+		e = cudaMemcpyAsync(d.selfrev, sr.data(), sizeof(float) * d.n, cudaMemcpyHostToDevice, st);  // pageable: staged before it returns
+	}
 	int nl = 0;
 	if (e == cudaSuccess) {
 		nl = launch_pack_profiles(d_planes, tot, d.prof8, st);
 		if (nl < 0)
 			e = cudaErrorLaunchFailure;
 	}
-	if (e == cudaSuccess)
+	// Everything is queued on the context stream, in order before any later search call.  The synchronous entry waits (the
+	// caller may free or overwrite its arrays at once); the asynchronous one only promises that PAGEABLE sources have been
+	// read - pinned sources must stay untouched until rsk_ctx_sync() or the next call that returns results.
+	if (e == cudaSuccess && !async)
 		e = cudaStreamSynchronize(st);
+	(void)direct;
 	if (e != cudaSuccess) {
 		rsk_chainset_free(cs);
 		return fail(RSK_ERR_CUDA, "rsk_chainset_upload: %s", cudaGetErrorString(e));
@@ -701,8 +779,8 @@ int run_mkf(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b)
 		// x-drop grid: the lanes balance their load by pulling items from the work list, which needs several items per
 		// thread; too few threads on the other hand cannot hide the memory latency of the DP rows
 		static const int xgrid_env = getenv("RSK_XGRID") ? std::max(1, atoi(getenv("RSK_XGRID"))) : 0;  // blocks per SM (A/B switch)
-		int xblocks = xgrid_env ? ctx->num_sms * xgrid_env
-				: (int)std::min<uint64_t>((uint64_t)ctx->num_sms * 16, std::max<uint64_t>((uint64_t)ctx->num_sms * 2, (uint64_t)2 * m / (64 * 16)));
+		// the warp-per-item kernel (80 registers, 4 warps per CTA) fits 6 CTAs per SM; its warps pull items from the work list
+		int xblocks = ctx->num_sms * (xgrid_env ? xgrid_env : 6);
 		int nl = launch_mkf(ma, (uint32_t)hchain.size(), xblocks, st);
 		if (nl < 0)
 			return fail(RSK_ERR_CUDA, "long-chain kernels failed to launch: %s", cudaGetErrorString(cudaGetLastError()));
@@ -844,7 +922,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		}
 		if (b.cross) {
 			const uint32_t nrows = (uint32_t)rowlist.size();
-			task_cap = nrows * (ncols / kClassWarps[kSwClasses - 1] + 1);
+			task_cap = nrows * (ncols / (16 * kSwChain) + 2);  // a task holds W * kSwChain >= 16 * kSwChain column chains
 			if (ctx->c_blist.ensure(b.npairs) || ctx->c_bslot.ensure(b.npairs) || ctx->c_task_a.ensure((size_t)task_cap * kSwClasses) ||
 				ctx->c_task_begin.ensure((size_t)task_cap * kSwClasses) || ctx->c_task_cnt.ensure((size_t)task_cap * kSwClasses)) {
 				cudaGetLastError();
@@ -1118,7 +1196,7 @@ int upload_explicit_tasks(rsk_ctx *ctx, const SearchPlan &plan, Batch &b)
 	return RSK_OK;
 }
 
-struct SinkOpts { uint32_t a_base = 0, b_base = 0; };
+struct SinkOpts { uint32_t a_base = 0, b_base = 0; bool append = false; };  // append: keep what earlier calls put into the sink
 int run_to_sink(rsk_ctx *ctx, SearchPlan &plan, std::vector<Batch> &batches, const rsk_search_opts &opts, const SinkOpts &so);
 
 int search_impl(rsk_ctx *ctx, SearchPlan &plan, const rsk_search_opts *opts_in, rsk_results **out, bool device_only, const SinkOpts *sink = nullptr)
@@ -1605,10 +1683,12 @@ int run_to_sink(rsk_ctx *ctx, SearchPlan &plan, std::vector<Batch> &batches, con
 		CK(cudaMalloc((void **)&K.d_tot, 4 * sizeof(unsigned long long)));
 		CK(cudaHostAlloc((void **)&K.h_tot, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
 	}
-	CK(cudaMemsetAsync(K.d_tot, 0, 4 * sizeof(unsigned long long), st));
+	if (!so.append)
+		CK(cudaMemsetAsync(K.d_tot, 0, 4 * sizeof(unsigned long long), st));
 	const float ts_lo = sink_ts_threshold(ctx->params.max_evalue);
 	const uint32_t report_no_evalue = !((double)FLT_MAX > ctx->params.max_evalue) ? 1u : 0u;
-	unsigned long long conf_rec = 0, conf_pool = 0;
+	// exact totals so far (an appending call starts from what the previous call left; every call ends synchronised)
+	unsigned long long conf_rec = so.append ? K.h_tot[0] : 0, conf_pool = so.append ? K.h_tot[1] : 0;
 	size_t unconf_rec[2] = {0, 0}, unconf_pool[2] = {0, 0};
 	const size_t nb = batches.size();
 	int rc;
@@ -2199,6 +2279,74 @@ extern "C" int rsk_search_self(rsk_ctx *ctx, const rsk_chainset *Sx, const rsk_s
 	}
 	ctx->stats = acc;
 	*out = total ? total : new rsk_results();
+	return RSK_OK;
+}
+
+// RunSelf on several GPUs: every rank holds the whole set; rank r takes the rows i = r, r + N, r + 2N ... of the pair triangle
+// (row i has n - i pairs, so interleaved rows balance the ranks), hits are compacted on the device, gathered on the root and
+// put back into the order of the unsharded search (a, then b).
+extern "C" int rsk_search_self_sharded(rsk_ctx *ctx, rsk_comm *comm, const rsk_chainset *Sx, const rsk_search_opts *opts_in, int root,
+		rsk_results **out)
+{
+	if (!ctx || !Sx || !out)
+		return fail(RSK_ERR_ARG, "rsk_search_self_sharded: null argument");
+	*out = nullptr;
+	if (comm && comm_ctx(comm) != ctx)
+		return fail(RSK_ERR_ARG, "rsk_search_self_sharded: the communicator belongs to a different context");
+	const int N = comm_nranks(comm), me = comm_rank(comm);
+	if (root < 0 || root >= N)
+		return fail(RSK_ERR_ARG, "rsk_search_self_sharded: root %d of %d ranks", root, N);
+	rsk_search_opts opts;
+	memset(&opts, 0, sizeof(opts));
+	if (opts_in)
+		opts = *opts_in;
+	const uint64_t n = Sx->d.n;
+	uint64_t chunk_pairs = (uint64_t)1 << 26;
+	if (const char *e = getenv("RSK_SELF_CHUNK_PAIRS")) {
+		const long long v = atoll(e);
+		if (v > 0)
+			chunk_pairs = (uint64_t)v;
+	}
+	rsk_stats acc;
+	memset(&acc, 0, sizeof(acc));
+	int rc = sink_reset_empty(ctx);
+	if (rc)
+		return rc;
+	std::vector<uint32_t> ia, ib;
+	bool first = true;
+	for (uint64_t i0 = (uint64_t)me; i0 < n;) {
+		uint64_t i1 = i0, np = 0;
+		while (i1 < n && (i1 == i0 || np + (n - i1) <= chunk_pairs)) {
+			np += n - i1;
+			i1 += (uint64_t)N;
+		}
+		ia.resize(np);
+		ib.resize(np);
+		uint64_t k = 0;
+		for (uint64_t i = i0; i < i1; i += (uint64_t)N)
+			for (uint64_t j = i; j < n; ++j, ++k) {
+				ia[k] = (uint32_t)i;
+				ib[k] = (uint32_t)j;
+			}
+		SearchPlan plan;
+		rc = build_explicit_plan(plan, Sx, Sx, np, ia.data(), ib.data(), ctx->host_threads, ctx->params.mkfl);
+		if (rc)
+			return rc;
+		SinkOpts so;
+		so.append = !first;
+		if ((rc = search_impl(ctx, plan, &opts, nullptr, false, &so)))
+			return rc;
+		add_stats(acc, ctx->stats);
+		first = false;
+		i0 = i1;
+	}
+	ctx->stats = acc;
+	rc = sink_finish(ctx, comm, root, opts, out);
+	if (rc || !*out)
+		return rc;
+	// unsharded order: a ascending, b ascending (rows are interleaved over the ranks, and a rank schedules its pairs by length)
+	rsk_results *res = *out;
+	std::sort(res->hits, res->hits + res->nhits, [](const rsk_hit &x, const rsk_hit &y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
 	return RSK_OK;
 }
 

@@ -138,10 +138,10 @@ extern "C" int rsk_chainset_from_coords(rsk_ctx *ctx, const rsk_coords_host *h, 
 		return fail(RSK_ERR_NOMEM, "rsk_chainset_from_coords: device memory");
 	}
 	cudaStream_t st = ctx->stream;
-	cudaError_t e = cudaMemcpyAsync(cs->d.x, h->xyz, sizeof(float) * tot, cudaMemcpyHostToDevice, st);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(cs->d.y, h->xyz + tot, sizeof(float) * tot, cudaMemcpyHostToDevice, st);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(cs->d.z, h->xyz + 2 * tot, sizeof(float) * tot, cudaMemcpyHostToDevice, st);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dss_aa.p, h->aa, tot, cudaMemcpyHostToDevice, st);
+	cudaError_t e = cudaSuccess;
+	if (rsk_h2d(ctx, cs->d.x, h->xyz, sizeof(float) * tot, nullptr) || rsk_h2d(ctx, cs->d.y, h->xyz + tot, sizeof(float) * tot, nullptr) ||
+		rsk_h2d(ctx, cs->d.z, h->xyz + 2 * tot, sizeof(float) * tot, nullptr) || rsk_h2d(ctx, ctx->dss_aa.p, h->aa, tot, nullptr))
+		e = cudaErrorUnknown;
 	std::vector<float> sr(cs->d.n, FLT_MAX);  // "unset" (dssaligner.cpp:876-877) until rsk_chainset_selfrev fills them
 	if (e == cudaSuccess) e = cudaMemcpyAsync(cs->d.selfrev, sr.data(), sizeof(float) * cs->d.n, cudaMemcpyHostToDevice, st);
 	if (e != cudaSuccess) {

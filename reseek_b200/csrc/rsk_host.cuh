@@ -13,6 +13,8 @@
 #include "rsk_internal.cuh"
 
 int rsk_fail(int code, const char *fmt, ...);
+struct rsk_ctx;
+int rsk_h2d(rsk_ctx *ctx, void *dst, const void *src, size_t bytes, bool *direct);
 #define fail rsk_fail
 
 #define CK(call)                                                                                     \
@@ -148,7 +150,7 @@ struct rsk_ctx {
 	DevBuf<int2> mu_bnd;
 	DevBuf<uint32_t> c_blist, c_bslot, c_task_a, c_task_begin, c_task_cnt;  // compacted survivors
 	size_t filt_explicit_pairs = 0; uint64_t filt_explicit_cells = 0; uint32_t filt_explicit_tasks = 0; bool batch_cross = true;
-	struct Counters { uint32_t task_count[4]; uint32_t sw_task_counter[4]; uint32_t sat_count, mu_task_counter; unsigned long long pair_count, cell_count; };
+	struct Counters { uint32_t task_count[kSwClasses]; uint32_t sw_task_counter[kSwClasses]; uint32_t sat_count, mu_task_counter; unsigned long long pair_count, cell_count; };
 	DevBuf<uint32_t> rowlist, colsort;
 	// long-chain path (K4)
 	DevBuf<uint32_t> mk_a, mk_b, mk_slot, mk_hash, mk_hchain;
@@ -193,6 +195,9 @@ struct rsk_ctx {
 	DevBuf<uint8_t> dss_ss, dss_conf, dss_aa;
 	DevBuf<double> dss_dens;
 	DevBuf<uint32_t> dss_helix;
+	PinBuf<char> h_up[2];       // pinned staging of uploads from pageable caller memory (rsk_h2d)
+	cudaEvent_t ev_up[2] = {nullptr, nullptr};
+	bool up_busy[2] = {false, false};
 	HitSink sink;
 	PinBuf<SinkRec> h_sink[2];  // pinned staging of the sink read-out (chunked, double-buffered)
 	PinBuf<PairRec> h_rec[2];   // double-buffered: batch i is converted on the host while batch i+1 runs on the GPU

@@ -78,8 +78,10 @@ constexpr int kSwStripSteps = 16;            // wavefront steps between two chec
 #define RSK_SW_CHAIN 4
 #endif
 constexpr int kSwChain = RSK_SW_CHAIN;       // column chains a warp aligns back to back as one wavefront (one ramp per list)
-// SW kernel classes by rows per lane: R <= 5 | R == 6 | R = 7..8 | R = 9..12, with the warps per CTA (= pairs per task) of each
-constexpr int kSwClasses = 4;
+// SW kernel classes (one kernel each, so that every class gets its own register allocation and warps per CTA = pairs per task):
+//   half-warp chains (<= 192 residues): 0: R <= 5 | 1: R == 6 | 4: R = 7..8 | 5: R = 9..12
+//   full-warp chains:                   2: R = 7..8 | 3: R = 9..12   (a chain above 192 residues never has R < 7)
+constexpr int kSwClasses = 6;
 #ifndef RSK_CLASS_W0
 #define RSK_CLASS_W0 32
 #endif
@@ -92,14 +94,46 @@ constexpr int kSwClasses = 4;
 #ifndef RSK_CLASS_W3
 #define RSK_CLASS_W3 20
 #endif
-constexpr int kClassWarps[kSwClasses] = {RSK_CLASS_W0, RSK_CLASS_W1, RSK_CLASS_W2, RSK_CLASS_W3};
-constexpr int kSwMaxWarps = RSK_CLASS_W0 > 20 ? RSK_CLASS_W0 : 20;
-__host__ __device__ inline int sw_class_of_R(int R) { return R <= 5 ? 0 : R == 6 ? 1 : R <= 8 ? 2 : 3; }
-__host__ __device__ inline int sw_class_warps(int c) { return c == 0 ? RSK_CLASS_W0 : c == 1 ? RSK_CLASS_W1 : c == 2 ? RSK_CLASS_W2 : RSK_CLASS_W3; }
+#ifndef RSK_CLASS_W4
+#define RSK_CLASS_W4 16
+#endif
+#ifndef RSK_CLASS_W5
+#define RSK_CLASS_W5 20
+#endif
+constexpr int kClassWarps[kSwClasses] = {RSK_CLASS_W0, RSK_CLASS_W1, RSK_CLASS_W2, RSK_CLASS_W3, RSK_CLASS_W4, RSK_CLASS_W5};
+__host__ __device__ constexpr int sw_cmax(int a, int b) { return a > b ? a : b; }
+constexpr int kSwMaxWarps = sw_cmax(sw_cmax(sw_cmax(RSK_CLASS_W0, RSK_CLASS_W1), sw_cmax(RSK_CLASS_W2, RSK_CLASS_W3)), sw_cmax(RSK_CLASS_W4, RSK_CLASS_W5));
+__host__ __device__ inline int sw_class_of_R(int R, bool half)
+{
+	if (half)
+		return R <= 5 ? 0 : R == 6 ? 1 : R <= 8 ? 4 : 5;
+	return R <= 8 ? 2 : 3;
+}
+__host__ __device__ inline int sw_class_warps(int c)
+{
+	return c == 0 ? RSK_CLASS_W0 : c == 1 ? RSK_CLASS_W1 : c == 2 ? RSK_CLASS_W2 : c == 3 ? RSK_CLASS_W3 : c == 4 ? RSK_CLASS_W4 : RSK_CLASS_W5;
+}
 
-// How a chain of LA rows is cut into passes of 32*R rows (R rows per lane).
+// Row chains of at most 16*12 residues are swept by HALF warps: lanes 0-15 and lanes 16-31 run two independent wavefronts
+// (different column chains, same row chain), each lane owning twice as many rows.  The per-step overhead of the wavefront
+// (shuffles, column fetch, chain bookkeeping) is then shared by twice as many cells per lane - short chains were issue
+// bound at 47 instructions per cell (R = 5) against 29 at R = 10 - the ramp is 15 steps instead of 31, and 100 rows pad to
+// 112 instead of 128.
+#ifndef RSK_SW_HALF_MAX
+#define RSK_SW_HALF_MAX (16 * 12)
+#endif
+constexpr uint32_t kSwHalfMaxLen = RSK_SW_HALF_MAX;
+__host__ __device__ inline bool sw_half(uint32_t LA) { return LA <= kSwHalfMaxLen; }
+
+// How a chain of LA rows is cut into passes of 32*R rows (R rows per lane; 16*R rows in one pass for half-warp chains).
 __host__ __device__ inline void sw_geometry(uint32_t LA, int &npass, int &R)
 {
+	if (sw_half(LA)) {
+		npass = 1;
+		R = (int)((LA + 15u) / 16u);
+		if (R < 1) R = 1;
+		return;
+	}
 	npass = (int)((LA + kRowsPerPassMax - 1) / kRowsPerPassMax);
 	if (npass < 1) npass = 1;
 	R = (int)((LA + 32u * npass - 1) / (32u * npass));
@@ -109,7 +143,7 @@ __host__ __device__ inline int sw_class_of_len(uint32_t L)
 {
 	int npass, R;
 	sw_geometry(L, npass, R);
-	return sw_class_of_R(R);
+	return sw_class_of_R(R, sw_half(L));
 }
 
 // K1 arguments.  "row"/"col" are the kernel's view; tr says which reference slot supplies the rows.

@@ -420,7 +420,7 @@ int bag_device(rsk_ctx *ctx, uint32_t nQ, uint32_t B, const uint32_t *d_q, const
 	if (n == 0 || nQ == 0)
 		return RSK_OK;
 	if (pf_bag_smem_bytes(B) > 220 * 1024)
-		return fail(RSK_ERR_LIMIT, "rsk_prefilter: -rsb_size %u exceeds the bag kernel's shared memory (max ~8000)", B);
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter: -rsb_size %u exceeds the bag kernel's shared memory (max ~6000)", B);
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
 	PfScratch &S = pf_scratch(ctx);
@@ -557,6 +557,42 @@ extern "C" int rsk_prefilter_bag(uint32_t nq, uint64_t n, const uint32_t *t, con
 	res->raw = n;
 	finish_bags(bags, B, *res, nthreads);
 	*out = res;
+	return RSK_OK;
+}
+
+// The same bag on the device (pf_bag_kernel) over caller-supplied triples in stream order: what the sharded search runs on the
+// all-gathered stream, exposed for callers that collect the triples themselves and for the parity tests against the host form.
+extern "C" int rsk_prefilter_bag_device(rsk_ctx *ctx, uint32_t nq, uint64_t n, const uint32_t *t, const uint32_t *q, const uint16_t *s,
+		uint32_t rsb_size, rsk_prefilter_result **out)
+{
+	if (!ctx || !out || (n && (!t || !q || !s)))
+		return fail(RSK_ERR_ARG, "rsk_prefilter_bag_device: null argument");
+	*out = nullptr;
+	const uint32_t B = rsb_size ? rsb_size : 1500u;
+	if (nq >= (1u << 16))
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter_bag_device: at most 65535 queries (got %u)", nq);
+	std::vector<unsigned long long> v(n);
+	for (uint64_t k = 0; k < n; ++k) {
+		if (q[k] >= nq)
+			return fail(RSK_ERR_ARG, "rsk_prefilter_bag_device: triple %llu names query %u of %u", (unsigned long long)k, q[k], nq);
+		v[k] = ((unsigned long long)t[k] << 16) | s[k];
+	}
+	CK(cudaSetDevice(ctx->device));
+	PfScratch &S = pf_scratch(ctx);
+	NOMEM(S.raw_q.ensure(n + 1));
+	NOMEM(S.raw_v.ensure(n + 1));
+	if (n) {
+		CK(cudaMemcpyAsync(S.raw_q.p, q, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(S.raw_v.p, v.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	std::unique_ptr<rsk_prefilter_result> res(new rsk_prefilter_result());
+	uint64_t launches = 0;
+	int rc = bag_device(ctx, nq, B, S.raw_q.p, S.raw_v.p, n, *res, launches);
+	if (rc)
+		return rc;
+	ctx->stats.kernel_launches += launches;
+	*out = res.release();
 	return RSK_OK;
 }
 

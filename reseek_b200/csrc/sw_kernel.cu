@@ -46,7 +46,8 @@ constexpr size_t kSmemTab = 0;                          // float[2192] weighted 
 constexpr size_t kSmemP0 = 8768;                        // plane 0: float4[132][32], rows 0..3 of each lane
 constexpr size_t kPlaneBytes = (size_t)kNLet * 512;     // 67584
 constexpr int kPlaneFloats = kNLet * 128;
-__host__ __device__ constexpr int class_planes(int C) { return C >= 3 ? 3 : 2; }
+__host__ __device__ constexpr int class_planes(int C) { return (C == 3 || C == 5) ? 3 : 2; }  // R > 8 needs the third plane
+__host__ __device__ constexpr int planes_of_R(int R) { return R > 8 ? 3 : 2; }
 // after the planes: 16 bytes for the task broadcast, then the warps' column-chain lists (kSwMaxWarps x kSwChain x 24 B)
 __host__ __device__ constexpr size_t smem_bcast_off(int planes) { return kSmemP0 + (size_t)planes * kPlaneBytes; }
 __host__ __device__ constexpr size_t smem_chains_off(int planes) { return smem_bcast_off(planes) + 16; }
@@ -58,12 +59,14 @@ __host__ __device__ constexpr int plane_width(int n) { return n <= 0 ? 0 : n == 
 // table value of rows beyond the end of the chain: such cells are hugely negative and can never be a maximum
 constexpr float kPadScore = -1e30f;
 
-template <int R, int NTHREADS>
+// G = lanes per wavefront (32, or 16 for half-warp chains: lanes l and l + 16 then hold the same rows, each in its own bank
+// group, so that the two half-warps read without bank conflicts)
+template <int R, int NTHREADS, int G>
 __device__ __forceinline__ void build_rowtab(float *planes, const float *tab, const uint64_t *__restrict__ profA,
 		uint32_t LA, int pass)
 {
 	constexpr int W1 = plane_width(R - 4), W2 = plane_width(R - 8);
-	constexpr int ROWS = 32 * R;
+	constexpr int ROWS = G * R;
 	const uint32_t rowbase = (uint32_t)pass * ROWS;
 	for (int idx = threadIdx.x; idx < kNLet * ROWS; idx += NTHREADS) {
 		const int e = idx / ROWS;
@@ -79,12 +82,15 @@ __device__ __forceinline__ void build_rowtab(float *planes, const float *tab, co
 			const int a = (int)((pa >> (8 * f)) & 0xff) - feat_base(f);
 			v = tab[feat_table_off(f) + a * feat_alpha(f) + b];
 		}
-		if (r < 4)
-			planes[e * 128 + l * 4 + r] = v;
-		else if (r < 8)
-			planes[kPlaneFloats + e * 128 + l * W1 + (r - 4)] = v;
-		else
-			planes[2 * kPlaneFloats + e * 128 + l * W2 + (r - 8)] = v;
+#pragma unroll
+		for (int ll = l; ll < 32; ll += G) {
+			if (r < 4)
+				planes[e * 128 + ll * 4 + r] = v;
+			else if (r < 8)
+				planes[kPlaneFloats + e * 128 + ll * W1 + (r - 4)] = v;
+			else
+				planes[2 * kPlaneFloats + e * 128 + ll * W2 + (r - 8)] = v;
+		}
 	}
 }
 
@@ -145,7 +151,7 @@ struct ColChain {
 // One sweep over rows [pass*32R, (pass+1)*32R) of the row chain and the concatenated columns of the warp's chains.
 //   TRACE = false: the forward sweep.  Values only; saves a checkpoint every kStrip steps and tracks, per chain, the
 //                  lane's first maximum (kernel coordinates), parked in `best` when the lane moves on to the next chain.
-//   TRACE = true : re-run of strip `strip` (steps kStrip*strip .. s_last) from its checkpoint, writing one 64-bit
+//   TRACE = true : re-run of the first `s_last` steps of strip `strip` from its checkpoint, writing one 64-bit
 //                  trace word per lane and step (4 bits per row) into `tile[(step % kStrip)*32 + lane]`.
 // A lane that has consumed the last column of a chain re-initialises its row state and continues with column 0 of the
 // next chain at the very next step; its (M, D) hand-over registers keep serving the lane behind it, which is still one
@@ -155,13 +161,16 @@ struct ColChain {
 //             roles of the two gap states exchanged: the reference tests D (gap that consumes A) before I
 //             (sw.cpp:136-147), and its first-maximum rule prefers the smaller i, then the smaller j.
 // bnd_in / bnd_out: boundary row (indexed by concatenated column) written by the previous pass / by this one.
-template <int R, bool TR, bool TRACE>
+// G = 16: the two half-warps sweep their own chain lists (chs / nch / total are then per half); tmax / tmin = the larger /
+// smaller `total` of the warp's wavefronts (loop bound / range of the predicate-free steps).
+template <int R, bool TR, bool TRACE, int G>
 __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int lane, const bool first, const bool last,
-		const uint32_t row0, const uint32_t LA, const ColChain *chs, const int nch, const int total,
+		const uint32_t row0, const uint32_t LA, const ColChain *chs, const int nch, const int total, const int tmax, const int tmin,
 		const float2 *__restrict__ bnd_in, float2 *__restrict__ bnd_out, float4 *__restrict__ ck, const float open,
 		const float ext, float4 *__restrict__ best, const int strip, const int s_last,
 		unsigned long long *__restrict__ tile)
 {
+	const int sub = lane & (G - 1);
 	constexpr int W1 = plane_width(R - 4), W2 = plane_width(R - 8);
 	constexpr int NW4 = ckpt_words(R);
 	// Per-lane byte offsets into the planes.  They are made opaque to the optimiser so that "offset*16 + lane
@@ -182,13 +191,13 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 		Mrow[r] = kNegInf;  // M[i_r+1][0]
 		Irow[r] = kNegInf;  // I[i_r][0]
 	}
-	const bool lane0 = (lane == 0);
+	const bool lane0 = (sub == 0);
 	const bool use_bnd = lane0 && !first;
-	const bool put_bnd = (lane == 31) && !last;
+	const bool put_bnd = (sub == G - 1) && !last;
 	const float mdiag_init = (lane0 && first) ? 0.0f : kNegInf;  // M[i0][0]; M[0][0] = 0 (sw.cpp:116)
 	float mdiag_next = mdiag_init;
 	float outM = kNegInf, outD = kNegInf;
-	const int nsteps = total + 31;
+	const int nsteps = tmax + (G - 1);
 	const int ngroups = (nsteps + 3) >> 2;
 
 	auto save = [&](const int k) {
@@ -226,17 +235,18 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 	};
 
 	// position of this lane: concatenated column v, chain c, column j of that chain
-	int v = -lane;
+	int v = -sub;
 	int c = 0;
 	if (TRACE) {
 		load(strip);
-		v = kStrip * strip - lane;
+		v = kStrip * strip - sub;
 		while (c + 1 < nch && v >= chs[c + 1].base)
 			++c;
 	}
-	int LBc = chs[c].LB;
-	const uint64_t *colp = chs[c].col;
-	int j = v - chs[c].base;
+	// a half-warp without chains (tail of a task list) never enters a matrix
+	int LBc = nch > 0 ? chs[c].LB : -0x40000000;
+	const uint64_t *colp = nch > 0 ? chs[c].col : nullptr;
+	int j = nch > 0 ? v - chs[c].base : v;
 	uint64_t cv = 0;
 	if (j >= 0 && j < LBc)
 		cv = __ldg(colp + j);
@@ -427,16 +437,18 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 	};
 
 	if (TRACE) {
-		for (int s = kStrip * strip; s <= s_last; ++s) {
+		// s_last = number of steps to re-run from the start of the strip (warp-uniform; `strip` itself may differ between the
+		// two half-warps, each re-running the strip its own walk needs)
+		for (int n = 0; n < s_last; ++n) {
 			const unsigned long long tw = step(std::true_type{});
-			tile[(s & (kStrip - 1)) * 32 + lane] = tw;
+			tile[n * 32 + lane] = tw;
 		}
 	} else {
 		for (int g = 0; g < ngroups; ++g) {
 			const int s0 = 4 * g;
 			if ((g & (kStrip / 4 - 1)) == 0)
 				save(g / (kStrip / 4));
-			if (s0 >= 31 && s0 + 4 < total) {
+			if (s0 >= G - 1 && s0 + 4 < tmin) {
 				step(std::false_type{});
 				step(std::false_type{});
 				step(std::false_type{});
@@ -467,13 +479,16 @@ struct TileCache {
 
 // Walks while the path stays in pass `pass` (whose row table is the one in shared memory).  Returns true when the path is
 // complete, false when it continues in the pass above.
-template <int R, bool TR>
+// G / grp: lanes per wavefront and the half-warp (0 or 1) that swept the chain being walked; chs / nch / total are the
+// calling lane's own wavefront's (they feed the strip re-runs, which every lane of the warp takes part in).
+template <int R, bool TR, int G>
 __device__ __forceinline__ bool traceback_in_pass(const unsigned char *smem_p0, const int lane, const int pass, const int npass,
-		const uint32_t LA, const ColChain *chs, const int nch, const int total, const int cbase, float2 *__restrict__ bnd,
+		const uint32_t LA, const ColChain *chs, const int nch, const int total, const int tmax, const int tmin, const int grp,
+		const int cbase, float2 *__restrict__ bnd,
 		const uint32_t bnd_pass_stride, float4 *__restrict__ ck, const int nstrips, const float open, const float ext,
 		unsigned long long *__restrict__ tile, uint8_t *__restrict__ stage, TbState &t, TileCache &tc)
 {
-	constexpr int rows_per_pass = 32 * R;
+	constexpr int rows_per_pass = G * R;
 	for (;;) {
 		const int ci = (t.state == 2) ? t.i : t.i - 1;
 		const int cj = (t.state == 1) ? t.j : t.j - 1;
@@ -491,15 +506,15 @@ __device__ __forceinline__ bool traceback_in_pass(const unsigned char *smem_p0, 
 		const int k = s / kStrip;
 		if (p != tc.p || k != tc.k || s > tc.last) {
 			__syncwarp();
-			sw_pass<R, TR, true>(smem_p0, lane, p == 0, p == npass - 1, (uint32_t)p * rows_per_pass + (uint32_t)lane * R, LA, chs, nch,
-					total, bnd + (size_t)(p > 0 ? p - 1 : 0) * bnd_pass_stride, nullptr, ck + (size_t)p * nstrips * ckpt_words(R) * 32, open,
-					ext, nullptr, k, s, tile);
+			sw_pass<R, TR, true, G>(smem_p0, lane, p == 0, p == npass - 1, (uint32_t)p * rows_per_pass + (uint32_t)(lane & (G - 1)) * R, LA,
+					chs, nch, total, tmax, tmin, bnd + (size_t)(p > 0 ? p - 1 : 0) * bnd_pass_stride, nullptr,
+					ck + (size_t)p * nstrips * ckpt_words(R) * 32, open, ext, nullptr, k, s - kStrip * k + 1, tile);
 			__syncwarp();
 			tc.p = p;
 			tc.k = k;
 			tc.last = s;
 		}
-		const unsigned long long w = tile[(s & (kStrip - 1)) * 32 + srcl];
+		const unsigned long long w = tile[(s & (kStrip - 1)) * 32 + grp * G + srcl];
 		const uint32_t nib = (uint32_t)(w >> (4 * r)) & 15u;
 		if (t.state == 0) {
 			--t.i; --t.j;
@@ -514,6 +529,70 @@ __device__ __forceinline__ bool traceback_in_pass(const unsigned char *smem_p0, 
 			--t.j;
 			t.state = (nib & 8u) ? 0 : 2;
 		}
+	}
+}
+
+// Half-warp chains (always one pass): chain k of BOTH wavefronts is walked at the same time, each half-warp following its own
+// path.  When a walk needs trace words that its half of the tile does not hold, the warp re-runs strips once for both: each
+// half re-runs the strip ITS walk is in (a half that needs nothing repeats the strip it has), for as many steps as the longer
+// request - the per-pair strip re-run is the dominant cost of short chains, and pairing halves it.  `t`, `cbase`, `stage`
+// and `active` are per half-warp.
+template <int R, bool TR>
+__device__ __forceinline__ void traceback_halves(const unsigned char *smem_p0, const int lane, const uint32_t LA, const ColChain *chs,
+		const int nch, const int total, const int tmax, const int tmin, const int cbase, float2 *__restrict__ bnd,
+		float4 *__restrict__ ck, const float open, const float ext, unsigned long long *__restrict__ tile,
+		uint8_t *__restrict__ stage, TbState &t, const bool active)
+{
+	constexpr int G = 16;
+	const int sub = lane & (G - 1), grp = lane / G;
+	int tk = -1, tlast = -1;  // strip held by this half's part of the tile, last step of it that is valid
+	bool done = !active;
+	for (;;) {
+		int need_k = -1, need_s = 0;
+		while (!done) {
+			const int ci = (t.state == 2) ? t.i : t.i - 1;
+			const int cj = (t.state == 1) ? t.j : t.j - 1;
+			const int krow = TR ? cj : ci, kcol = TR ? ci : cj;
+			const int srcl = krow / R;
+			const int r = krow - srcl * R;
+			const int s = cbase + kcol + srcl;
+			const int k = s / kStrip;
+			if (k != tk || s > tlast) {
+				need_k = k;
+				need_s = s;
+				break;
+			}
+			if (sub == 0)
+				stage[t.n] = (uint8_t)(t.state == 0 ? 'M' : t.state == 1 ? 'D' : 'I');
+			++t.n;
+			const unsigned long long w = tile[(s & (kStrip - 1)) * 32 + grp * G + srcl];
+			const uint32_t nib = (uint32_t)(w >> (4 * r)) & 15u;
+			if (t.state == 0) {
+				--t.i; --t.j;
+				const uint32_t src = nib & 3u;
+				if (src == 3u)
+					done = true;
+				else
+					t.state = (int)src;  // 0 M, 1 D, 2 I
+			} else if (t.state == 1) {
+				--t.i;
+				t.state = (nib & 4u) ? 0 : 1;
+			} else {
+				--t.j;
+				t.state = (nib & 8u) ? 0 : 2;
+			}
+		}
+		if (!__ballot_sync(kFull, need_k >= 0))
+			break;
+		const int k = need_k >= 0 ? need_k : max(tk, 0);
+		int cnt = need_k >= 0 ? need_s - kStrip * need_k + 1 : 1;
+		cnt = max(cnt, __shfl_xor_sync(kFull, cnt, G));
+		__syncwarp();
+		sw_pass<R, TR, true, G>(smem_p0, lane, true, true, (uint32_t)sub * R, LA, chs, nch, total, tmax, tmin, bnd, nullptr, ck, open, ext,
+				nullptr, k, cnt, tile);
+		__syncwarp();
+		tlast = (k == tk) ? max(tlast, kStrip * k + cnt - 1) : kStrip * k + cnt - 1;
+		tk = k;
 	}
 }
 
@@ -538,27 +617,35 @@ __device__ __forceinline__ void emit_path(const SwArgs &a, const int lane, const
 	}
 }
 
-template <int R, bool TR, int W>
+template <int R, bool TR, int W, int G>
 __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *smem, const uint32_t rowchain,
 		const uint32_t begin, const uint32_t cnt)
 {
+	constexpr int NG = 32 / G;            // wavefronts per warp
+	constexpr int CG = kSwChain / NG;     // column chains per wavefront
+	static_assert(kSwChain % NG == 0, "chains per warp must split evenly over the half-warps");
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int grp = lane / G;
 	const float *tab = reinterpret_cast<const float *>(smem + kSmemTab);
 	float *planes = reinterpret_cast<float *>(smem + kSmemP0);
 	const unsigned char *smem_p0 = smem + kSmemP0;
-	ColChain *chs = reinterpret_cast<ColChain *>(smem + smem_chains_off(class_planes(sw_class_of_R(R)))) + warp * kSwChain;
+	ColChain *chs = reinterpret_cast<ColChain *>(smem + smem_chains_off(planes_of_R(R))) + warp * kSwChain;
 
 	const uint32_t LA = a.len_row[rowchain];  // kernel rows
 	const uint64_t *profA = a.prof_row + a.off_row[rowchain];
-	const int npass = (int)((LA + 32 * R - 1) / (32 * R));
+	const int npass = (int)((LA + G * R - 1) / (G * R));
 
 	// this warp's column chains: entries warp, warp + W, warp + 2W ... of the task's list (the list is sorted by length, so
-	// every warp gets a similar total)
-	int nch = 0, total = 0;
+	// every warp gets a similar total); entry kk goes to wavefront kk % NG as its chain kk / NG
+	int nchg[NG], totg[NG];
 #pragma unroll
-	for (int k = 0; k < kSwChain; ++k) {
-		const uint32_t e = (uint32_t)(k * W + warp);
+	for (int g = 0; g < NG; ++g)
+		nchg[g] = totg[g] = 0;
+#pragma unroll
+	for (int kk = 0; kk < kSwChain; ++kk) {
+		const uint32_t e = (uint32_t)(kk * W + warp);
 		if (e < cnt) {
+			const int g = kk % NG;
 			const uint32_t cidx = a.clist[begin + e];
 			const int LB = (int)a.len_col[cidx];
 			uint32_t slot;
@@ -569,18 +656,28 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 				slot = a.cslot[begin + e];
 			}
 			if (lane == 0) {
-				chs[nch].col = a.prof_col + a.off_col[cidx];
-				chs[nch].LB = LB;
-				chs[nch].base = total;
-				chs[nch].slot = slot;
+				ColChain &cc = chs[g * CG + nchg[g]];
+				cc.col = a.prof_col + a.off_col[cidx];
+				cc.LB = LB;
+				cc.base = totg[g];
+				cc.slot = slot;
 			}
-			total += LB;
-			++nch;
+			totg[g] += LB;
+			++nchg[g];
 		}
 	}
 	__syncwarp();
-	const bool have = nch > 0;
-	const int nstrips = (((total + 31 + 3) >> 2) + kStrip / 4 - 1) / (kStrip / 4);
+	int tmax = 0, tmin = 0x7fffffff, nall = 0;
+#pragma unroll
+	for (int g = 0; g < NG; ++g) {
+		tmax = max(tmax, totg[g]);
+		tmin = min(tmin, nchg[g] ? totg[g] : 0);
+		nall += nchg[g];
+	}
+	const bool have = nall > 0;
+	const ColChain *mychs = chs + grp * CG;
+	const int mynch = nchg[NG == 1 ? 0 : grp], mytot = totg[NG == 1 ? 0 : grp];
+	const int nstrips = (((tmax + (G - 1) + 3) >> 2) + kStrip / 4 - 1) / (kStrip / 4);
 	const size_t gw = (size_t)blockIdx.x * W + warp;
 	float4 *ck = a.ckpt + gw * a.ckpt_stride;
 	float2 *bnd = a.bnd + gw * a.bnd_stride;
@@ -590,77 +687,115 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 
 	for (int pass = 0; pass < npass; ++pass) {
 		__syncthreads();  // every warp is done with the previous row table
-		build_rowtab<R, W * 32>(planes, tab, profA, LA, pass);
+		build_rowtab<R, W * 32, G>(planes, tab, profA, LA, pass);
 		__syncthreads();
 		if (have)
-			sw_pass<R, TR, false>(smem_p0, lane, pass == 0, pass == npass - 1, (uint32_t)pass * 32 * R + (uint32_t)lane * R, LA, chs,
-					nch, total, bnd + (size_t)(pass > 0 ? pass - 1 : 0) * a.bnd_pass_stride, bnd + (size_t)pass * a.bnd_pass_stride,
-					ck + (size_t)pass * nstrips * ckpt_words(R) * 32, a.open, a.ext, best, 0, 0, nullptr);
+			sw_pass<R, TR, false, G>(smem_p0, lane, pass == 0, pass == npass - 1, (uint32_t)pass * G * R + (uint32_t)(lane & (G - 1)) * R, LA,
+					mychs, mynch, mytot, tmax, tmin, bnd + (size_t)(pass > 0 ? pass - 1 : 0) * a.bnd_pass_stride,
+					bnd + (size_t)pass * a.bnd_pass_stride, ck + (size_t)pass * nstrips * ckpt_words(R) * 32, a.open, a.ext, best, 0, 0, nullptr);
 	}
-	// per chain: first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j
+	// per chain: first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j.
+	// Chain k of every wavefront is reduced at once (inside its half-warp), then broadcast to the whole warp, which walks the
+	// paths one after the other.
 	float score[kSwChain];
 	TbState tb[kSwChain];
 	unsigned active = 0;
+	__syncwarp();
 #pragma unroll
-	for (int k = 0; k < kSwChain; ++k) {
-		score[k] = 0.0f;
-		tb[k].i = tb[k].j = 0; tb[k].state = 0; tb[k].n = 0;
-		if (k < nch) {
+	for (int k = 0; k < CG; ++k) {
+		float lbest = 0.0f;
+		int lbi = 0x7fffffff, lbj = 0x7fffffff;
+		if (k < mynch) {
 			const float4 b = best[k * 32 + lane];
-			float lbest = b.x;
-			int lbi = __float_as_int(b.y), lbj = __float_as_int(b.z);
+			lbest = b.x; lbi = __float_as_int(b.y); lbj = __float_as_int(b.z);
+		}
 #pragma unroll
-			for (int o = 16; o >= 1; o >>= 1) {
-				const float os = __shfl_xor_sync(kFull, lbest, o);
-				const int oi = __shfl_xor_sync(kFull, lbi, o);
-				const int oj = __shfl_xor_sync(kFull, lbj, o);
-				bool take;
-				if (!TR)  // i = row (unique per lane), j = column
-					take = os > lbest || (os == lbest && oi < lbi);
-				else      // i = column, j = row
-					take = os > lbest || (os == lbest && (oj < lbj || (oj == lbj && oi < lbi)));
-				if (take) {
-					lbest = os; lbi = oi; lbj = oj;
-				}
+		for (int o = G / 2; o >= 1; o >>= 1) {
+			const float os = __shfl_xor_sync(kFull, lbest, o);
+			const int oi = __shfl_xor_sync(kFull, lbi, o);
+			const int oj = __shfl_xor_sync(kFull, lbj, o);
+			bool take;
+			if (!TR)  // i = row (unique per lane), j = column
+				take = os > lbest || (os == lbest && oi < lbi);
+			else      // i = column, j = row
+				take = os > lbest || (os == lbest && (oj < lbj || (oj == lbj && oi < lbi)));
+			if (take) {
+				lbest = os; lbi = oi; lbj = oj;
 			}
-			PairRec *rec = a.rec + chs[k].slot;
-			if (lbest == 0.0f) {  // sw.cpp:200-201: no positive cell -> score 0, empty path
-				if (lane == 0) {
-					rec->score = 0.0f;
-					rec->lo_a = 0xffffffffu;
-					rec->lo_b = 0xffffffffu;
-					rec->path_len = 0;
-					rec->path_off = 0;
+		}
+#pragma unroll
+		for (int g = 0; g < NG; ++g) {
+			const int kk = g * CG + k;  // index of the chain in the warp's list in shared memory
+			score[kk] = 0.0f;
+			tb[kk].i = tb[kk].j = 0; tb[kk].state = 0; tb[kk].n = 0;
+			if (k < nchg[g]) {
+				const float gb = __shfl_sync(kFull, lbest, g * G);
+				const int gi = __shfl_sync(kFull, lbi, g * G), gj = __shfl_sync(kFull, lbj, g * G);
+				PairRec *rec = a.rec + chs[kk].slot;
+				if (gb == 0.0f) {  // sw.cpp:200-201: no positive cell -> score 0, empty path
+					if (lane == 0) {
+						rec->score = 0.0f;
+						rec->lo_a = 0xffffffffu;
+						rec->lo_b = 0xffffffffu;
+						rec->path_len = 0;
+						rec->path_off = 0;
+					}
+				} else {
+					active |= 1u << kk;
+					score[kk] = gb;
+					tb[kk].i = (TR ? gj : gi) + 1;
+					tb[kk].j = (TR ? gi : gj) + 1;
 				}
-			} else {
-				active |= 1u << k;
-				score[k] = lbest;
-				tb[k].i = (TR ? lbj : lbi) + 1;
-				tb[k].j = (TR ? lbi : lbj) + 1;
 			}
 		}
 	}
 	TileCache tc;
 	tc.p = -1; tc.k = -1; tc.last = -1;
 	__syncwarp();  // checkpoints and boundary rows written by other lanes of this warp are visible
+	if constexpr (G == 16) {
+		// one pass; the two wavefronts' chains are walked in pairs
+#pragma unroll
+		for (int k = 0; k < CG; ++k) {
+			if (!(active & ((1u << k) | (1u << (CG + k)))))
+				continue;
+			const int mykk = grp * CG + k;
+			TbState t = grp ? tb[(NG - 1) * CG + k] : tb[k];
+			traceback_halves<R, TR>(smem_p0, lane, LA, mychs, mynch, mytot, tmax, tmin, chs[mykk].base, bnd, ck, a.open, a.ext, tile,
+					stage + (size_t)mykk * a.stage_chain_stride, t, (active >> mykk) & 1u);
+#pragma unroll
+			for (int g = 0; g < NG; ++g) {
+				const int kk = g * CG + k;
+				if (active & (1u << kk)) {
+					TbState tg;
+					tg.i = __shfl_sync(kFull, t.i, g * G);
+					tg.j = __shfl_sync(kFull, t.j, g * G);
+					tg.n = __shfl_sync(kFull, t.n, g * G);
+					tg.state = 0;
+					__syncwarp();
+					emit_path(a, lane, stage + (size_t)kk * a.stage_chain_stride, score[kk], tg, a.rec + chs[kk].slot);
+				}
+			}
+		}
+	} else {
 	for (int p = npass - 1; p >= 0; --p) {
 		if (p != npass - 1) {
 			// the path of some warp continues above this pass: restage that pass's row table for the whole CTA
-			build_rowtab<R, W * 32>(planes, tab, profA, LA, p);
+			build_rowtab<R, W * 32, G>(planes, tab, profA, LA, p);
 			__syncthreads();
 		}
 #pragma unroll
-		for (int k = 0; k < kSwChain; ++k) {
-			if (active & (1u << k)) {
-				if (traceback_in_pass<R, TR>(smem_p0, lane, p, npass, LA, chs, nch, total, chs[k].base, bnd, a.bnd_pass_stride, ck, nstrips,
-							a.open, a.ext, tile, stage + (size_t)k * a.stage_chain_stride, tb[k], tc)) {
-					emit_path(a, lane, stage + (size_t)k * a.stage_chain_stride, score[k], tb[k], a.rec + chs[k].slot);
-					active &= ~(1u << k);
+		for (int kk = 0; kk < kSwChain; ++kk) {
+			if (active & (1u << kk)) {
+				if (traceback_in_pass<R, TR, G>(smem_p0, lane, p, npass, LA, mychs, mynch, mytot, tmax, tmin, kk / CG, chs[kk].base, bnd,
+							a.bnd_pass_stride, ck, nstrips, a.open, a.ext, tile, stage + (size_t)kk * a.stage_chain_stride, tb[kk], tc)) {
+					emit_path(a, lane, stage + (size_t)kk * a.stage_chain_stride, score[kk], tb[kk], a.rec + chs[kk].slot);
+					active &= ~(1u << kk);
 				}
 			}
 		}
 		if (p > 0 && !__syncthreads_or(active != 0 ? 1 : 0))
 			break;
+	}
 	}
 	__syncwarp();  // the chain list in shared memory is rewritten by the next task
 }
@@ -700,27 +835,30 @@ __global__ void __launch_bounds__(kClassWarps[C] * 32, 1) sw_affine_f32_tb_kerne
 		}
 		int npass, R;
 		sw_geometry(a.len_row[rowchain], npass, R);
+		// the class fixes the wavefront width: 0, 1, 4, 5 hold half-warp chains (<= 192 residues), 2 and 3 full-warp chains
 		if (C == 0) {
 			switch (R) {
-			case 1: process_task<1, TR, W>(a, smem, rowchain, begin, cnt); break;
-			case 2: process_task<2, TR, W>(a, smem, rowchain, begin, cnt); break;
-			case 3: process_task<3, TR, W>(a, smem, rowchain, begin, cnt); break;
-			case 4: process_task<4, TR, W>(a, smem, rowchain, begin, cnt); break;
-			default: process_task<5, TR, W>(a, smem, rowchain, begin, cnt); break;
+			case 1: process_task<1, TR, W, 16>(a, smem, rowchain, begin, cnt); break;
+			case 2: process_task<2, TR, W, 16>(a, smem, rowchain, begin, cnt); break;
+			case 3: process_task<3, TR, W, 16>(a, smem, rowchain, begin, cnt); break;
+			case 4: process_task<4, TR, W, 16>(a, smem, rowchain, begin, cnt); break;
+			default: process_task<5, TR, W, 16>(a, smem, rowchain, begin, cnt); break;
 			}
 		} else if (C == 1) {
-			process_task<6, TR, W>(a, smem, rowchain, begin, cnt);
-		} else if (C == 2) {
+			process_task<6, TR, W, 16>(a, smem, rowchain, begin, cnt);
+		} else if (C == 2 || C == 4) {
+			constexpr int G = C == 2 ? 32 : 16;
 			if (R == 7)
-				process_task<7, TR, W>(a, smem, rowchain, begin, cnt);
+				process_task<7, TR, W, G>(a, smem, rowchain, begin, cnt);
 			else
-				process_task<8, TR, W>(a, smem, rowchain, begin, cnt);
+				process_task<8, TR, W, G>(a, smem, rowchain, begin, cnt);
 		} else {
+			constexpr int G = C == 3 ? 32 : 16;
 			switch (R) {
-			case 9: process_task<9, TR, W>(a, smem, rowchain, begin, cnt); break;
-			case 10: process_task<10, TR, W>(a, smem, rowchain, begin, cnt); break;
-			case 11: process_task<11, TR, W>(a, smem, rowchain, begin, cnt); break;
-			default: process_task<12, TR, W>(a, smem, rowchain, begin, cnt); break;
+			case 9: process_task<9, TR, W, G>(a, smem, rowchain, begin, cnt); break;
+			case 10: process_task<10, TR, W, G>(a, smem, rowchain, begin, cnt); break;
+			case 11: process_task<11, TR, W, G>(a, smem, rowchain, begin, cnt); break;
+			default: process_task<12, TR, W, G>(a, smem, rowchain, begin, cnt); break;
 			}
 		}
 	}
@@ -746,7 +884,7 @@ __global__ void pack_profiles_kernel(const uint8_t *__restrict__ planes, uint64_
 
 }  // namespace
 
-size_t sw_smem_bytes() { return class_smem(kSwClasses - 1); }
+size_t sw_smem_bytes() { return class_smem(3); }
 
 // float4 units of checkpoints one warp needs for npass passes over `LB` concatenated columns (any R)
 uint64_t sw_ckpt_units(int npass, uint64_t LB)
@@ -771,7 +909,9 @@ int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream)
 	case 0: return tr ? launch_sw_ct<0, true>(args, grid, stream) : launch_sw_ct<0, false>(args, grid, stream);
 	case 1: return tr ? launch_sw_ct<1, true>(args, grid, stream) : launch_sw_ct<1, false>(args, grid, stream);
 	case 2: return tr ? launch_sw_ct<2, true>(args, grid, stream) : launch_sw_ct<2, false>(args, grid, stream);
-	default: return tr ? launch_sw_ct<3, true>(args, grid, stream) : launch_sw_ct<3, false>(args, grid, stream);
+	case 3: return tr ? launch_sw_ct<3, true>(args, grid, stream) : launch_sw_ct<3, false>(args, grid, stream);
+	case 4: return tr ? launch_sw_ct<4, true>(args, grid, stream) : launch_sw_ct<4, false>(args, grid, stream);
+	default: return tr ? launch_sw_ct<5, true>(args, grid, stream) : launch_sw_ct<5, false>(args, grid, stream);
 	}
 }
 

@@ -145,6 +145,8 @@ def load_library():
         fn.argtypes = [C.c_void_p]
         fn.restype = C.c_void_p
     L.rsk_prefilter_bag.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.rsk_prefilter_bag_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                           C.POINTER(C.c_void_p)]
     L.rsk_prefilter_select.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.rsk_prefilter_free.argtypes = [C.c_void_p]
     L.rsk_prefilter_free.restype = None
@@ -168,6 +170,7 @@ def load_library():
     L.rsk_partition_by_residues.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
     L.rsk_search_cross_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(SearchOpts),
                                            C.c_int, C.POINTER(C.c_void_p)]
+    L.rsk_search_self_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SearchOpts), C.c_int, C.POINTER(C.c_void_p)]
     L.rsk_search_fast_db_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(PrefilterOpts),
                                              C.POINTER(SearchOpts), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.rsk_results_digest.argtypes = [C.c_void_p]
@@ -623,6 +626,13 @@ class Context:
                                                         C.byref(o), int(root), C.byref(r)))
         return Results(r) if r else None
 
+    def search_self_sharded(self, comm, S, keep=KEEP_HITS, want_paths=True, root=0):
+        """DBSearcher::RunSelf with the rows of the pair triangle interleaved over the ranks (rsk_search_self_sharded)."""
+        o = self._opts(keep, want_paths, False)
+        r = C.c_void_p()
+        _check(load_library().rsk_search_self_sharded(self.handle, comm.handle if comm else None, S.handle, C.byref(o), int(root), C.byref(r)))
+        return Results(r) if r else None
+
     def search_fast_db_sharded(self, comm, Q, T_local, t_base, index_mode=0, rsb_size=0, kl_swap=True, keep=KEEP_HITS,
                                want_paths=True, root=0, want_cands=True):
         """`-search Q -db DB -fast` on this rank's block of the DB (rsk_search_fast_db_sharded).  Returns
@@ -635,6 +645,16 @@ class Context:
                                                           C.byref(po), C.byref(o), int(root), C.byref(r),
                                                           C.byref(c) if want_cands else None))
         return (Results(r) if r else None), (PrefilterResult(c) if c else None)
+
+    def prefilter_bag_device(self, nq, targets, queries, scores, rsb_size=0):
+        """RankedScoresBag on the device over (target, query, score) triples in stream order (rsk_prefilter_bag_device)."""
+        t = np.ascontiguousarray(targets, np.uint32)
+        q = np.ascontiguousarray(queries, np.uint32)
+        s = np.ascontiguousarray(scores, np.uint16)
+        assert len(t) == len(q) == len(s)
+        r = C.c_void_p()
+        _check(load_library().rsk_prefilter_bag_device(self.handle, int(nq), len(t), _ptr(t), _ptr(q), _ptr(s), int(rsb_size), C.byref(r)))
+        return PrefilterResult(r)
 
     def selfrev(self, S, Srev):
         """GetSelfRevScore for every chain of S (see rsk_chainset_selfrev); returns the float32 scores."""

@@ -121,3 +121,40 @@ def test_full_size_sensitive_is_a_filtered_subset(world):
     assert (hs["score"][~rej & ~both] < 7).all(), "CalcEvalue is skipped below MinFwdScore = 7 (dssaligner.cpp:861)"
     for f in ("hi_a", "hi_b", "ids", "gaps", "lddt", "ts", "evalue"):
         assert np.array_equal(hs[f][both], hv[f][both]), f
+
+
+@pytest.mark.parametrize("length,ndb", [(100, 100_000), (800, 12_500)])
+def test_full_size_other_lengths_sample_matches_oracle(built_lib, port, length, ndb):
+    """Config 5 at L = 100 (half-warp wavefronts, 1e7 pairs) and L = 800 (three passes of 32 x 9 rows per chain; the DB is cut to
+    12 500 chains = 8e11 cells to bound the test time - the kernels see the same shapes): random sample + best-scoring pairs against
+    the oracle, and the record invariants over the whole result."""
+    import reseek_b200 as rb
+    from reseek_b200 import synth
+    from tests.util import assert_hit_matches_oracle, to_oracle_chains
+    q = synth.make_chains(NQ, length, seed=20260122 + length)
+    db = synth.make_chains(ndb, length, seed=20260122 + 1000 + length)
+    synth.plant_homologs(db, q, 0.01, seed=20260122 + 7 + length)
+    ctx = rb.Context(0, rb.MODE_VERYSENSITIVE)
+    Q = ctx.upload(q.lens, q.prof, q.mu, q.xyz, q.selfrev)
+    D = ctx.upload(db.lens, db.prof, db.mu, db.xyz, db.selfrev)
+    res = ctx.search_cross(D, Q, keep=rb.KEEP_ALL, want_paths=True)
+    h = res.hits
+    assert len(h) == NQ * ndb
+    rng = np.random.default_rng(length)
+    ks = np.concatenate([rng.choice(len(h), 120 if length == 100 else 40, replace=False), np.argsort(h["score"])[-20:]])
+    oq = to_oracle_chains(q)
+    p = port(3)
+    for k in ks.tolist():
+        oa = to_oracle_chains(db.subset([int(h[k]["a"])]))[0]
+        r, rpath = p.align_pair(oa, oq[int(h[k]["b"])])
+        assert_hit_matches_oracle(h[k], res.path(k), r, rpath, ctx=f"L={length} pair {k}")
+    assert int(h["path_len"][ks[-1]]) > length // 3, "the best pair is a planted homolog with a long path"
+    has = h["path_len"] > 0
+    hh = h[has]
+    assert has.mean() > 0.99 and (hh["ids"] + hh["gaps"] == hh["path_len"]).all()
+    assert (hh["hi_a"] < length).all() and (hh["hi_b"] < length).all() and (hh["hi_a"] >= hh["lo_a"]).all()
+    # the device-compacted path returns the same records
+    r2 = ctx.search_cross_sharded(None, D, Q, 0, keep=rb.KEEP_HITS, want_paths=False)
+    rep = (h["flags"] & rb.HIT_REPORTED) != 0
+    assert len(r2.hits) == int(rep.sum()) and np.array_equal(r2.hits["score"].view(np.uint32), h["score"][rep].view(np.uint32))
+    ctx.close()

@@ -133,3 +133,31 @@ def test_prefilter_edge_cases(rb):
     with pytest.raises(rb.ReseekB200Error):
         ctx.prefilter(nomu, T)
     ctx.close()
+
+
+@pytest.mark.parametrize("B,span", [(3, 5), (50, 7), (100, 40), (1500, 12), (1500, 300), (400, 2)])
+def test_device_bag_equals_host_bag_on_tied_streams(built_lib, B, span):
+    """RankedScoresBag replayed on the device (warp-parallel exact Hoare partitions + per-lane small ranges) against the host
+    restatement (rsk_prefilter_bag, the reference's AddScore / TruncateVecs / QuickSortOrderDesc, rankedscoresbag.cpp:5-51,
+    sort.h:71-108): streams long enough for many truncations, scores drawn from `span` values so that the cut-off is always
+    inside a run of ties, plus rising and falling trends (the admission threshold then moves a lot / not at all)."""
+    import reseek_b200 as rb
+    rng = np.random.default_rng(1000 * B + span)
+    nq = 7
+    n = 60000
+    t = np.sort(rng.integers(0, 50000, size=n)).astype(np.uint32)
+    q = rng.integers(0, nq, size=n).astype(np.uint32)
+    s = rng.integers(1, 1 + span, size=n).astype(np.int64)
+    trend = np.linspace(0, 3 * span, n).astype(np.int64)
+    s = np.where(q % 3 == 0, s + trend, np.where(q % 3 == 1, s + trend[::-1], s)).astype(np.uint16)
+    # (target, query) pairs are unique in a real stream
+    key = t.astype(np.int64) * nq + q
+    _, first = np.unique(key, return_index=True)
+    first.sort()
+    t, q, s = t[first], q[first], s[first]
+    ctx = rb.Context(0, rb.MODE_FAST)
+    dev = ctx.prefilter_bag_device(nq, t, q, s, B)
+    host = rb.prefilter_bag(nq, t, q, s, B)
+    assert len(host.targets) > 0
+    assert np.array_equal(dev.targets, host.targets) and np.array_equal(dev.queries, host.queries) and np.array_equal(dev.scores, host.scores)
+    ctx.close()

@@ -126,6 +126,23 @@ def test_fast_db_sharded_one_rank_and_blocks(built_lib, rsb_size):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", ["sensitive", "fast"])
+def test_self_search_sink_one_rank(built_lib, mode, monkeypatch):
+    """RunSelf through the sharded entry with one rank (rows in several chunks, so the sink is appended to) equals rsk_search_self."""
+    import reseek_b200 as rb
+    monkeypatch.setenv("RSK_SELF_CHUNK_PAIRS", "500")
+    q, db = _sets(8, 70)
+    ctx = rb.Context(0, rb.MODE_SENSITIVE if mode == "sensitive" else rb.MODE_FAST)
+    S = _up(ctx, db)
+    ref = ctx.search_self(S, keep=rb.KEEP_HITS, want_paths=True)
+    res = ctx.search_self_sharded(None, S, keep=rb.KEEP_HITS, want_paths=True)
+    assert len(ref.hits) >= db.n
+    _assert_same_hits(res, ref, ordered=False)
+    h = res.hits
+    assert np.all((h["a"][1:] > h["a"][:-1]) | ((h["a"][1:] == h["a"][:-1]) & (h["b"][1:] > h["b"][:-1])))  # (a, b) ascending
+    ctx.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -210,6 +227,19 @@ def test_two_gpus_one_process_comm_init_all(built_lib):
     Q, T = _up(ctxs[0], q), _up(ctxs[0], db)
     ref = ctxs[0].search_cross(T, Q, keep=rb.KEEP_HITS, want_paths=True)
     _assert_same_hits(out[0], ref)
+    # RunSelf with the rows of the pair triangle interleaved over the two GPUs
+    sets = [_up(ctxs[r], db) for r in range(2)]
+
+    def work_self(r):
+        out[r] = ctxs[r].search_self_sharded(comms[r], sets[r], keep=rb.KEEP_HITS, want_paths=True)
+
+    th = [threading.Thread(target=work_self, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert out[1] is None
+    _assert_same_hits(out[0], ctxs[0].search_self(sets[0], keep=rb.KEEP_HITS, want_paths=True), ordered=False)
     for c in comms:
         c.close()
     for c in ctxs:

@@ -225,3 +225,43 @@ def test_alignpair_command_line_matches_reference_binary(built_lib, tmp_path):
         assert (tmp_path / "ap.aln").read_text() == (GOLDEN / name).read_text(), name
     r = _cli("-alignpair", q4)
     assert r.returncode == 1 and "Must specify -input2" in r.stderr
+
+
+@pytest.mark.gpu
+def test_history_dependent_pairs_of_the_reference(built_lib, tmp_path):
+    """A handful of the SCOP40 chain pairs on which the reference's all-vs-all output depends on what its aligner did before
+    (uncleared x-drop trace matrix, xdpmem.h:96-107; tools/check_history_pairs.py, profiles/r2_history_pairs.md): the lines the
+    reference prints for each pair ALONE (fixture) are the lines this engine prints."""
+    from reseek_b200 import chainio
+    g = np.load(GOLDEN / "history_pairs.npz", allow_pickle=True)
+    lens = g["lens"].astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    cols = str(g["columns"])
+    assert len(g["lines"]) >= 3
+    for k, members in enumerate(g["members"]):
+        ids = [int(m) for m in members if m >= 0]
+        chainio.write_bca(tmp_path / "pair.bca", [str(g["labels"][i]) for i in ids],
+                          [bytes(g["seq"][off[i]:off[i + 1]]) for i in ids], [g["xyz"][:, off[i]:off[i + 1]] for i in ids])
+        out = tmp_path / "pair.tsv"
+        r = _cli("-search", tmp_path / "pair.bca", "-fast", "-output", out, "-columns", cols)
+        assert r.returncode == 0, r.stderr
+        assert sorted(out.read_text().splitlines()) == sorted(str(g["lines"][k]).splitlines()), f"pair {k}"
+
+
+def test_bca_per_rank_ranges(built_lib, tmp_path):
+    """ChainReader2::OpenRange: every rank of a multi-process run reads its own contiguous, residue-balanced block of a shared
+    .bca straight from the file's length table (no GPU involved); the blocks tile the file and equal rsk_partition_by_residues."""
+    import reseek_b200 as rb
+    g6, g21 = golden_bca(tmp_path)
+    g = np.load(GOLDEN / "golden_chains.npz", allow_pickle=True)
+    lens = g["lens"]
+    for nranks in (1, 2, 5, 30):
+        want = rb.partition_by_residues(lens, nranks)
+        for r in range(nranks):
+            out = _run("bcarange", g21, r, nranks)
+            assert out.returncode == 0, out.stderr
+            lo, hi, first, last, res = out.stdout.split() if want[r][1] > want[r][0] else (out.stdout.split() + ["", ""])[:2] + ["", "", "0"]
+            assert (int(lo), int(hi)) == want[r]
+            if want[r][1] > want[r][0]:
+                assert first == str(g["labels"][want[r][0]]) and last == str(g["labels"][want[r][1] - 1])
+                assert int(res) == int(lens[want[r][0]:want[r][1]].sum())
