@@ -300,6 +300,20 @@ class Bench:
         self.ctx.set_params(self.rb.params_preset(m))
 
 
+def collective_block(B, comm, steps, step_ms):
+    """Per-step figures of the communicator's data-path collectives since reset_stats(): payload put on NVLink by all ranks, and
+    the device time of the gather rounds (CUDA events on the context stream).  A round cannot finish before the slowest rank
+    has arrived, so the time on a rank that arrived early is mostly waiting: `ms_per_step_min` (the rank that arrived last) is
+    the transfer itself, `ms_per_step_max` includes the load imbalance between the ranks."""
+    cs = comm.stats()
+    ms = cs["collective_ms"] / max(1, steps)
+    mx = B.reduce([ms])[0]
+    mn = -B.reduce([-ms])[0]
+    sent = B.reduce([float(cs["bytes_sent"]) / max(1, steps)], "sum")[0]
+    return {"ms_per_step_min": mn, "ms_per_step_max": mx, "nvlink_bytes_per_step": sent, "rounds_per_step": cs["collectives"] / max(1, steps),
+            "share_of_step": mn / step_ms if step_ms else None}
+
+
 def roofline_block(B, db_lens, q_lens, sw_ms_step, sw_launches_step, dev_ms_step, clocks, cells_rank):
     peak_src, peak = "fallback (B200_PROFILING.md)", 6650.0
     pk = ROOT / "MEASURED_PEAKS.json"
@@ -461,12 +475,11 @@ def leg_c4_strong(B, steps, warmup):
             out["digest"], out["hits"] = res.digest(), len(res.hits)
         del res
 
+    for _ in range(warmup):  # also establishes the NCCL point-to-point connections
+        dev_step()
     comm.reset_stats()
-    dev_ms, _ = B.timed(dev_step, steps, warmup)
-    cs = comm.stats()
-    ncalls = steps + warmup
-    coll_ms = B.reduce([cs["collective_ms"] / ncalls])[0]
-    sent = B.reduce([float(cs["bytes_sent"]) / ncalls], "sum")[0]
+    dev_ms, _ = B.timed(dev_step, steps, 0)
+    coll = collective_block(B, comm, steps, dev_ms)
     D.free()
     io = {"h2d": 0, "d2h": 0}
 
@@ -501,8 +514,7 @@ def leg_c4_strong(B, steps, warmup):
             "scaling": "strong", "metric": "chain_pairs_per_s", "value": pairs_all / (dev_ms * 1e-3), "unit": "pairs/s",
             "ms_per_step": dev_ms, "steps": steps, "pairs_per_step": pairs_all, "per_gpu_pairs": float(hi - lo) * q.n,
             "api": "rsk_search_cross_sharded (device hit sink + NCCL gather on rank 0), DB block resident",
-            "collective": {"what": "hit gather: 32-byte count all-gather + exact-size ncclSend/ncclRecv of records and path bytes to rank 0",
-                           "ms_per_step": coll_ms, "nvlink_bytes_per_step": sent, "share_of_step": coll_ms / dev_ms},
+            "collective": dict(coll, what="hit gather: 32-byte count all-gather + exact-size ncclSend/ncclRecv of records and path bytes to rank 0"),
             "e2e": {"value": pairs_all / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d / steps,
                     "d2h_bytes_per_step": d2h / steps, "steps": steps,
                     "api": "rsk_chainset_upload(block, pinned host) + rsk_search_cross_sharded incl. gather + read-out on rank 0"},
@@ -534,12 +546,11 @@ def leg_fastdb(B, q, blk, lo, steps, warmup):
             out["cands"] = len(cands)
         del res, cands
 
+    for _ in range(warmup):
+        step()
     comm.reset_stats()
-    dev_ms, wall_ms = B.timed(step, steps, warmup)
-    cs = comm.stats()
-    ncalls = steps + warmup
-    coll_ms = B.reduce([cs["collective_ms"] / ncalls])[0]
-    sent = B.reduce([float(cs["bytes_sent"]) / ncalls], "sum")[0]
+    dev_ms, wall_ms = B.timed(step, steps, 0)
+    coll = collective_block(B, comm, steps, dev_ms)
     check = None
     if B.rank == 0 and not args.no_digest_check:
         full = mine if B.world == 1 else c4_block(q, 0, ndb, seg=min(C4_SEG, args.c4_ndb))
@@ -560,8 +571,7 @@ def leg_fastdb(B, q, blk, lo, steps, warmup):
             "scaling": "strong", "metric": "chain_pairs_per_s", "value": pairs_all / (wall_ms * 1e-3), "unit": "pairs/s",
             "ms_per_step": wall_ms, "device_ms_per_step": dev_ms, "steps": steps, "candidates": out["cands"], "hits": out["hits"],
             "api": "rsk_search_fast_db_sharded (inputs resident; candidate list + hits read out on rank 0)",
-            "collective": {"what": "all-gather of (query, target<<16|score) triples in rank order + hit gather on rank 0",
-                           "ms_per_step": coll_ms, "nvlink_bytes_per_step": sent, "share_of_step": coll_ms / dev_ms},
+            "collective": dict(coll, what="all-gather of (query, target<<16|score) triples in rank order + hit gather on rank 0"),
             "digest_check": check}
 
 
@@ -589,12 +599,11 @@ def leg_c3(B, steps, warmup):
             info["digest"], info["hits"] = res.digest(), len(res.hits)
         del res
 
+    for _ in range(warmup):
+        step()
     comm.reset_stats()
-    dev_ms, wall_ms = B.timed(step, steps, warmup)
-    cs = comm.stats()
-    ncalls = steps + warmup
-    coll_ms = B.reduce([cs["collective_ms"] / ncalls])[0]
-    sent = B.reduce([float(cs["bytes_sent"]) / ncalls], "sum")[0]
+    dev_ms, wall_ms = B.timed(step, steps, 0)
+    coll = collective_block(B, comm, steps, dev_ms)
     tot = B.reduce([float(info.get("sw_pairs", 0)), float(info.get("sw_cells", 0)), float(info.get("mkf_pairs", 0))], "sum")
     kms = B.reduce([info.get("mu_ms", 0.0), info.get("sw_ms", 0.0), info.get("mkf_ms", 0.0)])
     check = None
@@ -614,7 +623,7 @@ def leg_c3(B, steps, warmup):
             "timing": "wall clock around rsk_search_self_sharded (plan + kernels + hit gather + read-out on rank 0), max over ranks",
             "sw_pairs": tot[0], "sw_cells": tot[1], "long_chain_pairs": tot[2], "hits": info["hits"],
             "kernel_ms_max_over_ranks": {"mu_filter": kms[0], "sw": kms[1], "long_chain": kms[2]},
-            "collective": {"what": "hit gather on rank 0", "ms_per_step": coll_ms, "nvlink_bytes_per_step": sent},
+            "collective": dict(coll, what="hit gather on rank 0"),
             "digest_check": check}
 
 
