@@ -70,29 +70,121 @@ __global__ void pf_query_kmers_kernel(const PfArgs a)
 }
 
 // ---- K6b/c: neighbourhoods.  One warp per query 5-mer X: every 5-mer Y with score(X, Y) >= 36. ----
-// Branch and bound over the letters of Y with the best achievable remainder as bound, breadth first and warp-wide: the lanes
-// scan the 36^3 prefixes (y0, y1, y2); survivors are compacted (ballot) into a shared-memory queue; a full queue is expanded
-// by y3 with ALL lanes working on flattened (entry, letter) pairs, its survivors are queued and expanded by y4 the same way.
-// (The depth-first form - each lane walking the subtree of its own prefixes - ran with 3 of 32 lanes active: subtree sizes
-// differ by orders of magnitude.)
-constexpr int kNbQ3 = 256, kNbQ4 = 1024, kNbWarps = 4;
+// Branch and bound over the letters of Y, breadth first and warp-wide, and work-efficient: per letter x the host supplies the 36
+// letters y sorted by S[x][y] descending, those scores, and ge[t] = #{y : S[x][y] >= t}.  A prefix of depth k with partial score p
+// has exactly ge_k[36 - p - (best achievable remainder)] children with a completion, and they are the first that many of the
+// sorted list - so a level is expanded by (1) one table look-up per parent, (2) a warp prefix sum, (3) rounds of 32 children,
+// each lane finding its parent by binary search over the 32 prefix sums.  No candidate is ever tested and rejected; the earlier
+// form scanned all 36^3 three-letter prefixes per k-mer and tested 36 letters per queued prefix (11 % of them hits).
+// Queues per level live in shared memory; a full queue is expanded (recursively, depth first) before its producer continues.
+// The order of the neighbours inside one k-mer's block is arbitrary: the index is sorted by neighbour code afterwards, and
+// within one block all codes are distinct (the k-mer's own second entry in query-neighbourhood mode carries the same value).
+constexpr int kNbWarps = 4, kNbCap = 256, kNbCap1 = 64;
+constexpr int kNbRow = 136;  // per letter: 36 sorted letters, 36 sorted scores (int8), 64 ge counts (threshold + 32)
+constexpr int kNbWarpWords = 32 + kNbCap1 + 3 * kNbCap + 5 * 64;  // Q0 | Q1 | Q2..Q4 | per level: 32 prefix sums + 32 parents
+
+struct NbState {
+	const uint8_t *tab[5];  // letter tables of x0..x4 (shared memory)
+	int rem[5];             // best achievable score of the letters after position k
+	uint32_t *Q[5];         // entries: prefix code << 8 | (partial score + 128)
+	uint32_t *scratch;
+	unsigned n[5];
+	unsigned acc;           // counting pass: this lane's share of the neighbourhood size
+	unsigned nout;          // fill pass: neighbours written so far
+	unsigned long long base;
+	uint32_t val;
+	uint32_t *ix_key, *ix_val;
+};
+
+template <int K, bool FILL>
+__device__ __forceinline__ void nb_expand(NbState &s, const unsigned lane)
+{
+	const uint8_t *tb = s.tab[K];
+	const uint32_t *Qk = s.Q[K];
+	const unsigned nk = s.n[K];
+	s.n[K] = 0;
+	const int need = kMinPair - s.rem[K] + 32;  // ge index of a parent with partial score p: need - p
+	if (K == 4 && !FILL) {
+		for (unsigned e = lane; e < nk; e += 32)
+			s.acc += tb[72 + min(max(need - ((int)(Qk[e] & 0xffu) - 128), 0), 63)];
+		__syncwarp();
+		return;
+	}
+	uint32_t *pre = s.scratch + 64 * K, *par = pre + 32;
+	unsigned e0 = 0, total = 0, o0 = 0;  // next chunk of parents, children of the current chunk, next child
+	for (;;) {
+		bool done = false;
+		while (o0 >= total) {
+			if (e0 >= nk) {
+				done = true;
+				break;
+			}
+			__syncwarp();  // the previous rounds are through with pre/par
+			const unsigned e = e0 + lane;
+			uint32_t q = 0;
+			unsigned cnt = 0;
+			if (e < nk) {
+				q = Qk[e];
+				cnt = tb[72 + min(max(need - ((int)(q & 0xffu) - 128), 0), 63)];
+			}
+			unsigned incl = cnt;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const unsigned t = __shfl_up_sync(kFull, incl, o);
+				if ((int)lane >= o)
+					incl += t;
+			}
+			pre[lane] = incl;
+			par[lane] = q;
+			__syncwarp();
+			total = __shfl_sync(kFull, incl, 31);
+			o0 = 0;
+			e0 += 32;
+		}
+		if (!done) {
+			const unsigned o = o0 + lane;
+			const unsigned nround = min(32u, total - o0);
+			if (lane < nround) {
+				unsigned j = 0;  // number of parents whose children all come before child o
+#pragma unroll
+				for (int step = 16; step >= 1; step >>= 1)
+					if (pre[j + step - 1] <= o)
+						j += step;
+				const unsigned rank = o - (j ? pre[j - 1] : 0u);
+				const uint32_t q = par[j];
+				const uint32_t code = (q >> 8) * 36u + tb[rank];
+				if (K == 4) {
+					s.ix_key[s.base + s.nout + lane] = code;
+					s.ix_val[s.base + s.nout + lane] = s.val;
+				} else {
+					s.Q[K < 4 ? K + 1 : 4][s.n[K < 4 ? K + 1 : 4] + lane] = (code << 8) | (uint32_t)((int)(q & 0xffu) + (int)(int8_t)tb[36 + rank]);
+				}
+			}
+			if (K == 4)
+				s.nout += nround;
+			else
+				s.n[K < 4 ? K + 1 : 4] += nround;
+			o0 += 32;
+		}
+		if constexpr (K < 4) {
+			if ((done && s.n[K + 1]) || s.n[K + 1] + 32 > (unsigned)(K + 1 == 1 ? kNbCap1 : kNbCap)) {
+				__syncwarp();
+				nb_expand<K + 1, FILL>(s, lane);
+			}
+		}
+		if (done)
+			break;
+	}
+	__syncwarp();
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(kNbWarps * 32) pf_neighborhood_kernel(const PfArgs a)
 {
-	__shared__ int S[36 * 36];
-	__shared__ int rowmax[36];
-	__shared__ uint32_t s_q3[kNbWarps][kNbQ3];  // prefix3 << 8 | (p3 + 128)
-	__shared__ uint32_t s_q4[kNbWarps][kNbQ4];  // prefix4 << 8 | (p4 + 128)
-	__shared__ uint8_t s_ge4[kNbWarps][256];
-	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
-		S[k] = a.kmer_mx[k];
-	__syncthreads();
-	if (threadIdx.x < 36) {
-		int m = -128;
-		for (int y = 0; y < 36; ++y)
-			m = max(m, S[36 * threadIdx.x + y]);
-		rowmax[threadIdx.x] = m;
-	}
+	__shared__ __align__(16) uint8_t s_tab[36 * kNbRow];
+	__shared__ uint32_t s_warp[kNbWarps][kNbWarpWords];
+	for (int k = threadIdx.x; k < 36 * kNbRow / 4; k += blockDim.x)
+		reinterpret_cast<uint32_t *>(s_tab)[k] = reinterpret_cast<const uint32_t *>(a.nb_tab)[k];
 	__syncthreads();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t i = blockIdx.x * kNbWarps + warp;
@@ -104,117 +196,45 @@ __global__ void __launch_bounds__(kNbWarps * 32) pf_neighborhood_kernel(const Pf
 			a.nb_count[i] = 0;
 		return;
 	}
-	int x[5];
+	NbState s;
 	{
 		uint32_t c = code;
+		int x[5];
 		for (int k = 4; k >= 0; --k) { x[k] = (int)(c % 36); c /= 36; }
-	}
-	const int *r0 = S + 36 * x[0], *r1 = S + 36 * x[1], *r2 = S + 36 * x[2], *r3 = S + 36 * x[3], *r4 = S + 36 * x[4];
-	const int m4 = rowmax[x[4]], m34 = rowmax[x[3]] + m4;
-	const uint32_t val = a.qk_val[i];
-	const unsigned long long base = FILL ? a.nb_off[i] : 0;
-	uint32_t *q3 = s_q3[warp], *q4 = s_q4[warp];
-	const unsigned lt = (1u << lane) - 1u;
-	unsigned n3 = 0, n4 = 0, nout = 0;
-
-	// counting pass: how many last letters reach the threshold is a function of the prefix score alone - one table look-up
-	// per queued prefix instead of 36 tests (s_ge4[k] = number of y4 with S[x4][y4] >= k - 128)
-	uint8_t *ge4 = s_ge4[warp];
-	if (!FILL) {
-		for (int k = lane; k < 256; k += 32) {
-			int c = 0;
-			for (int y = 0; y < 36; ++y)
-				c += r4[y] >= k - 128;
-			ge4[k] = (uint8_t)c;
-		}
-		__syncwarp();
-	}
-	unsigned acc = 0;  // counting pass: this lane's share of the neighbourhood size
-	auto drain4 = [&]() {  // expand the queued 4-letter prefixes by y4
-		const unsigned cnt4 = n4;
-		n4 = 0;
-		if (FILL) {
-			for (unsigned idx = lane; idx < ((cnt4 * 36 + 31) & ~31u); idx += 32) {
-				bool hit = false;
-				uint32_t y = 0;
-				if (idx < cnt4 * 36) {
-					const unsigned e = idx / 36, y4 = idx - e * 36;
-					const uint32_t q = q4[e];
-					hit = (int)(q & 0xffu) - 128 + r4[y4] >= kMinPair;
-					y = (q >> 8) * 36 + y4;
-				}
-				const unsigned m = __ballot_sync(kFull, hit);
-				if (hit) {
-					const unsigned slot = nout + __popc(m & lt);
-					a.ix_key[base + slot] = y;
-					a.ix_val[base + slot] = val;
-				}
-				nout += __popc(m);
-			}
-		} else {
-			for (unsigned e = lane; e < cnt4; e += 32)
-				acc += ge4[kMinPair + 256 - (int)(q4[e] & 0xffu)];
-		}
-		__syncwarp();
-	};
-	auto drain3 = [&]() {  // expand the queued 3-letter prefixes by y3
-		for (unsigned idx = lane; idx < ((n3 * 36 + 31) & ~31u); idx += 32) {
-			bool ok = false;
-			uint32_t q = 0;
-			if (idx < n3 * 36) {
-				const unsigned e = idx / 36, y3 = idx - e * 36;
-				const uint32_t q0 = q3[e];
-				const int p4 = (int)(q0 & 0xffu) - 128 + r3[y3];
-				ok = p4 + m4 >= kMinPair;
-				q = (((q0 >> 8) * 36 + y3) << 8) | (uint32_t)(p4 + 128);
-			}
-			const unsigned m = __ballot_sync(kFull, ok);
-			if (ok)
-				q4[n4 + __popc(m & lt)] = q;
-			n4 += __popc(m);
-			__syncwarp();
-			if (n4 > kNbQ4 - 32)
-				drain4();
-		}
-		n3 = 0;
-		__syncwarp();
-	};
-
-	int y0 = 0, y1 = 0, y2 = lane;  // lane < 36: prefix index = 32 * it + lane
-	for (int it = 0; it < (36 * 36 * 36 + 31) / 32; ++it) {
-		bool ok = false;
-		uint32_t q = 0;
-		if (y0 < 36) {
-			const int p3 = r0[y0] + r1[y1] + r2[y2];
-			ok = p3 + m34 >= kMinPair;
-			q = ((uint32_t)((y0 * 36 + y1) * 36 + y2) << 8) | (uint32_t)(p3 + 128);
-		}
-		const unsigned m = __ballot_sync(kFull, ok);
-		if (m) {
-			if (ok)
-				q3[n3 + __popc(m & lt)] = q;
-			n3 += __popc(m);
-			__syncwarp();
-			if (n3 > kNbQ3 - 32)
-				drain3();
-		}
-		y2 += 32;
-		if (y2 >= 36) {
-			y2 -= 36;
-			if (++y1 >= 36) {
-				y1 = 0;
-				++y0;
-			}
+		int rem = 0;
+		for (int k = 4; k >= 0; --k) {
+			s.tab[k] = s_tab + kNbRow * x[k];
+			s.rem[k] = rem;
+			rem += (int)(int8_t)s.tab[k][36];  // the best score of row x[k]
 		}
 	}
-	drain3();
-	drain4();
+	uint32_t *w = s_warp[warp];
+	s.Q[0] = w;
+	s.Q[1] = w + 32;
+	s.Q[2] = s.Q[1] + kNbCap1;
+	s.Q[3] = s.Q[2] + kNbCap;
+	s.Q[4] = s.Q[3] + kNbCap;
+	s.scratch = s.Q[4] + kNbCap;
+	for (int k = 0; k < 5; ++k)
+		s.n[k] = 0;
+	s.acc = 0;
+	s.nout = 0;
+	s.base = FILL ? a.nb_off[i] : 0;
+	s.val = a.qk_val[i];
+	s.ix_key = a.ix_key;
+	s.ix_val = a.ix_val;
+	if (lane == 0)
+		s.Q[0][0] = 128u;  // the empty prefix, score 0
+	s.n[0] = 1;
+	__syncwarp();
+	nb_expand<0, FILL>(s, lane);
 	if (FILL) {
 		if (a.exact_twice && lane == 0) {  // the k-mer itself is entered a second time (mudex.cpp:146-174)
-			a.ix_key[base + nout] = code;
-			a.ix_val[base + nout] = val;
+			a.ix_key[s.base + s.nout] = code;
+			a.ix_val[s.base + s.nout] = s.val;
 		}
 	} else {
+		unsigned acc = s.acc;
 #pragma unroll
 		for (int o = 16; o >= 1; o >>= 1)
 			acc += __shfl_xor_sync(kFull, acc, o);
@@ -224,19 +244,31 @@ __global__ void __launch_bounds__(kNbWarps * 32) pf_neighborhood_kernel(const Pf
 }
 
 // ---- K6d: dense row table over the dictionary from the sorted keys ----
-__global__ void pf_mark_rows_kernel(const uint32_t *__restrict__ key, unsigned long long n, uint32_t *row_start, uint32_t *row_end)
+__global__ void pf_mark_rows_kernel(const uint32_t *__restrict__ key, unsigned long long n, uint2 *row)
 {
 	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n)
 		return;
 	const uint32_t k = key[i];
 	if (i == 0 || key[i - 1] != k)
-		row_start[k] = (uint32_t)i;
+		row[k].x = (uint32_t)i;
 	if (i + 1 == n || key[i + 1] != k)
-		row_end[k] = (uint32_t)(i + 1);
+		row[k].y = (uint32_t)(i + 1);
 }
 
 // ---- K7: probe.  COUNT pass sizes each target's hit segment, FILL pass writes the (query, diagonal) keys. ----
+// One warp per target position: the lanes read the index row of its 5-mer side by side (coalesced 4-byte values); the row
+// bounds of the warp's NEXT position are fetched before the current row is walked, so the two dependent misses of a position
+// (row bounds, then row entries) overlap with the previous row.
+__device__ __forceinline__ uint2 probe_row(const PfArgs &a, const uint8_t *T, uint32_t LT, uint32_t tpos, const int *S)
+{
+	if (tpos + 7 > LT)
+		return make_uint2(0, 0);
+	bool masked;
+	const uint32_t y = kmer5(T + tpos, S, masked);
+	return masked ? make_uint2(0, 0) : __ldg(a.row + y);
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(128) pf_probe_kernel(const PfArgs a)
 {
@@ -251,28 +283,34 @@ __global__ void __launch_bounds__(128) pf_probe_kernel(const PfArgs a)
 	const uint32_t t = a.t_begin + tl;
 	const uint32_t LT = a.lenT[t];
 	const uint8_t *T = a.muT + a.offT[t];
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	unsigned long long cnt = 0;
 	const unsigned long long seg = FILL ? a.hit_off[tl] : 0;
+	if (FILL && a.hit_off[tl + 1] == seg)
+		return;  // no hits, or a target the fused kernel has taken
 	if (LT >= 7) {
-		for (uint32_t tpos = threadIdx.x; tpos + 7 <= LT; tpos += blockDim.x) {
-			bool masked;
-			const uint32_t y = kmer5(T + tpos, S, masked);
-			if (masked)
-				continue;
-			const uint32_t rs = a.row_start[y], re = a.row_end[y];
-			for (uint32_t e = rs; e < re; ++e) {
-				const uint32_t v = a.ix_val[e];
-				const uint32_t q = v >> 16, qpos = v & 0xffffu;
-				const uint32_t diag = a.lenQ[q] + tpos - qpos - 1;  // diag.h:22-25
-				if (diag > 0x3fffu)
-					continue;  // prefiltermu.cpp:254
-				if (FILL) {
-					const unsigned long long slot = atomicAdd(&s_cursor, 1ull);
-					a.hit_key[seg + slot] = (q << 14) | diag;
-				} else {
-					++cnt;
+		uint2 r = probe_row(a, T, LT, warp, S);
+		for (uint32_t tpos = warp; tpos + 7 <= LT; tpos += nwarps) {
+			const uint2 rn = probe_row(a, T, LT, tpos + nwarps, S);
+			if (!FILL && a.diag_safe) {
+				if (lane == 0)
+					cnt += r.y - r.x;  // no diagonal can exceed 16383: the row length is the count
+			} else {
+				for (uint32_t e = r.x + lane; e < r.y; e += 32) {
+					const uint32_t v = __ldg(a.ix_val + e);
+					const uint32_t q = v >> 16, qpos = v & 0xffffu;
+					const uint32_t diag = a.lenQ[q] + tpos - qpos - 1;  // diag.h:22-25
+					if (diag > 0x3fffu)
+						continue;  // prefiltermu.cpp:254
+					if (FILL) {
+						const unsigned long long slot = atomicAdd(&s_cursor, 1ull);
+						a.hit_key[seg + slot] = (q << 14) | diag;
+					} else {
+						++cnt;
+					}
 				}
 			}
+			r = rn;
 		}
 	}
 	if (!FILL) {
@@ -281,6 +319,129 @@ __global__ void __launch_bounds__(128) pf_probe_kernel(const PfArgs a)
 		const unsigned long long tot = BR(tmp).Sum(cnt);
 		if (threadIdx.x == 0)
 			a.hit_count[tl] = tot;
+	}
+}
+
+// FindHSP (prefiltermu.cpp:12-48) over the whole diagonal `d` of (query q, target T): Kadane scan in diagonal order, the best
+// score goes to best[tl][q].  Four positions per trip: the letters of both chains come as 32-bit words assembled from aligned
+// loads (one new word per chain and trip) - byte loads had the L1 data pipe 88 % busy.
+__device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int *S, const uint8_t *T, uint32_t LT, uint32_t tl, uint32_t k)
+{
+	const uint32_t q = k >> 14;
+	const int d = (int)(k & 0x3fffu);
+	const uint32_t LQ = a.lenQ[q];
+	const uint8_t *Q = a.muQ + a.offQ[q];
+	int qi = (int)LQ - d - 1, tj = 0;
+	if (qi < 0) { tj = -qi; qi = 0; }
+	int B = 0, F = 0;
+	int n = min((int)LQ - qi, (int)LT - tj);
+	const uint8_t *qp = Q + qi, *tp = T + tj;
+	if (n >= 8) {
+		const uint32_t *qw = reinterpret_cast<const uint32_t *>((uintptr_t)qp & ~(uintptr_t)3);
+		const uint32_t *tw = reinterpret_cast<const uint32_t *>((uintptr_t)tp & ~(uintptr_t)3);
+		const unsigned qs = ((uintptr_t)qp & 3u) * 8u, ts = ((uintptr_t)tp & 3u) * 8u;
+		uint32_t q0 = __ldg(qw), t0 = __ldg(tw);
+		const int groups = n >> 2;
+		for (int g = 0; g < groups; ++g) {
+			// the next aligned word holds at least one letter of this group whenever the chain's pointer is unaligned
+			uint32_t q1 = q0, t1 = t0;
+			if (qs || g + 1 < groups) q1 = __ldg(++qw);
+			if (ts || g + 1 < groups) t1 = __ldg(++tw);
+			const uint32_t qv = qs ? __funnelshift_r(q0, q1, qs) : q0;
+			const uint32_t tv = ts ? __funnelshift_r(t0, t1, ts) : t0;
+			q0 = q1; t0 = t1;
+#pragma unroll
+			for (int b = 0; b < 4; ++b) {
+				F += S[36 * ((qv >> (8 * b)) & 0xffu) + ((tv >> (8 * b)) & 0xffu)];
+				if (F > B) B = F;
+				else if (F < 0) F = 0;
+			}
+		}
+		qp += 4 * groups; tp += 4 * groups;
+		n -= 4 * groups;
+	}
+	for (int i = 0; i < n; ++i) {
+		F += S[36 * qp[i] + tp[i]];
+		if (F > B) B = F;
+		else if (F < 0) F = 0;
+	}
+	if (B > 0) {
+		if (B >= 65535) B = 65534;  // prefiltermu.cpp:294-295
+		atomicMax(&a.best[(size_t)tl * a.nQ + q], (unsigned)B);
+	}
+}
+
+// ---- K7+K8 fused, for targets with at most kFuseHits index hits (every target of a 100-query block against SCOP40-sized chains):
+// the hit keys never leave the SM.  A key is entered into a shared-memory hash set; the SECOND arrival of a key makes its
+// diagonal a two-hit diagonal (TwoHitDiag::SetDupes, twohitdiag.cpp:389) and queues it once; then the CTA walks the queued
+// diagonals.  Which thread sees the second arrival is timing dependent, the SET of queued diagonals is not, and best[] is a max.
+// This replaces, for those targets, the 4 B/hit key store, the segmented radix sort of the keys and the scan for runs.
+// Two sizes: 16384 slots (<= 8192 hits; two CTAs of 512 threads per SM) and 32768 slots (<= 16384 hits, one CTA of 1024).
+constexpr uint32_t kSlotEmpty = 0xffffffffu, kSlotDup = 0x80000000u, kSlotKey = 0x3fffffffu;  // keys are < 65535 << 14
+constexpr uint32_t kFuseSlotsS = 16384, kFuseSlotsL = 32768;
+constexpr size_t fuse_smem_bytes(uint32_t slots) { return sizeof(uint32_t) * (slots + slots / 4); }
+
+template <uint32_t SLOTS, int THREADS, uint32_t MINHITS>
+__global__ void __launch_bounds__(THREADS) pf_probe_extend_kernel(const PfArgs a)
+{
+	extern __shared__ __align__(16) uint32_t fuse_smem[];
+	uint32_t *tab = fuse_smem, *queue = fuse_smem + SLOTS;
+	__shared__ int S[36 * 36];
+	__shared__ unsigned s_n, s_next;
+	const uint32_t tl = blockIdx.x;
+	const uint32_t t = a.t_begin + tl;
+	const unsigned long long hits = a.hit_count[t];
+	if (hits <= MINHITS || hits > SLOTS / 2)
+		return;  // nothing to do / the other size / the global-memory path takes this target
+	// table size by the target's own hit count: at most half full
+	uint32_t slots = 256;
+	while (slots < 2 * (uint32_t)hits)
+		slots <<= 1;
+	const uint32_t mask = slots - 1;
+	const int shift = __clz(mask);  // 32 - log2(slots)
+	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
+		S[k] = a.kmer_mx[k];
+	for (uint32_t k = threadIdx.x; k < slots / 4; k += blockDim.x)
+		reinterpret_cast<uint4 *>(tab)[k] = make_uint4(kSlotEmpty, kSlotEmpty, kSlotEmpty, kSlotEmpty);
+	if (threadIdx.x == 0) { s_n = 0; s_next = 0; }
+	__syncthreads();
+	const uint32_t LT = a.lenT[t];
+	const uint8_t *T = a.muT + a.offT[t];
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	if (LT >= 7) {
+		uint2 r = probe_row(a, T, LT, warp, S);
+		for (uint32_t tpos = warp; tpos + 7 <= LT; tpos += nwarps) {
+			const uint2 rn = probe_row(a, T, LT, tpos + nwarps, S);
+			for (uint32_t e = r.x + lane; e < r.y; e += 32) {
+				const uint32_t v = __ldg(a.ix_val + e);
+				const uint32_t q = v >> 16, qpos = v & 0xffffu;
+				const uint32_t diag = a.lenQ[q] + tpos - qpos - 1;  // diag.h:22-25
+				if (diag > 0x3fffu)
+					continue;  // prefiltermu.cpp:254
+				const uint32_t key = (q << 14) | diag;
+				uint32_t h = (key * 2654435761u) >> shift;
+				for (;;) {
+					const uint32_t old = atomicCAS(&tab[h], kSlotEmpty, key);
+					if (old == kSlotEmpty)
+						break;  // first hit on this diagonal
+					if ((old & kSlotKey) == key) {
+						if (!(old & kSlotDup) && !(atomicOr(&tab[h], kSlotDup) & kSlotDup))
+							queue[atomicAdd(&s_n, 1u)] = key;  // second hit: a two-hit diagonal, queued once
+						break;
+					}
+					h = (h + 1) & mask;
+				}
+			}
+			r = rn;
+		}
+	}
+	__syncthreads();
+	const unsigned n = s_n;
+	for (;;) {
+		const unsigned w = atomicAdd(&s_next, 1u);
+		if (w >= n)
+			break;
+		walk_diagonal(a, S, T, LT, tl, queue[w]);
 	}
 }
 
@@ -319,51 +480,7 @@ __global__ void __launch_bounds__(128) pf_extend_kernel(const PfArgs a)
 			const unsigned w = atomicAdd(&s_next, 1u);
 			if (w >= n)
 				break;
-			const uint32_t k = s_queue[w];
-			const uint32_t q = k >> 14;
-			const int d = (int)(k & 0x3fffu);
-			const uint32_t LQ = a.lenQ[q];
-			const uint8_t *Q = a.muQ + a.offQ[q];
-			int qi = (int)LQ - d - 1, tj = 0;
-			if (qi < 0) { tj = -qi; qi = 0; }
-			int B = 0, F = 0;
-			// prefiltermu.cpp:27-46, four positions per trip: the letters of both chains come as 32-bit words assembled from
-			// aligned loads (one new word per chain and trip) - the kernel was bound by its byte loads (L1 data pipe 88 % busy)
-			int n = min((int)LQ - qi, (int)LT - tj);
-			const uint8_t *qp = Q + qi, *tp = T + tj;
-			if (n >= 8) {
-				const uint32_t *qw = reinterpret_cast<const uint32_t *>((uintptr_t)qp & ~(uintptr_t)3);
-				const uint32_t *tw = reinterpret_cast<const uint32_t *>((uintptr_t)tp & ~(uintptr_t)3);
-				const unsigned qs = ((uintptr_t)qp & 3u) * 8u, ts = ((uintptr_t)tp & 3u) * 8u;
-				uint32_t q0 = __ldg(qw), t0 = __ldg(tw);
-				const int groups = n >> 2;
-				for (int g = 0; g < groups; ++g) {
-					// the next aligned word holds at least one letter of this group whenever the chain's pointer is unaligned
-					uint32_t q1 = q0, t1 = t0;
-					if (qs || g + 1 < groups) q1 = __ldg(++qw);
-					if (ts || g + 1 < groups) t1 = __ldg(++tw);
-					const uint32_t qv = qs ? __funnelshift_r(q0, q1, qs) : q0;
-					const uint32_t tv = ts ? __funnelshift_r(t0, t1, ts) : t0;
-					q0 = q1; t0 = t1;
-#pragma unroll
-					for (int b = 0; b < 4; ++b) {
-						F += S[36 * ((qv >> (8 * b)) & 0xffu) + ((tv >> (8 * b)) & 0xffu)];
-						if (F > B) B = F;
-						else if (F < 0) F = 0;
-					}
-				}
-				qp += 4 * groups; tp += 4 * groups;
-				n -= 4 * groups;
-			}
-			for (int k = 0; k < n; ++k) {
-				F += S[36 * qp[k] + tp[k]];
-				if (F > B) B = F;
-				else if (F < 0) F = 0;
-			}
-			if (B > 0) {
-				if (B >= 65535) B = 65534;  // prefiltermu.cpp:294-295
-				atomicMax(&a.best[(size_t)tl * a.nQ + q], (unsigned)B);
-			}
+			walk_diagonal(a, S, T, LT, tl, s_queue[w]);
 		}
 		__syncthreads();
 		base = wend;
@@ -723,11 +840,11 @@ int pf_launch_neighborhood(const PfArgs &a, bool fill, cudaStream_t st)
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int pf_launch_mark_rows(const uint32_t *key, unsigned long long n, uint32_t *row_start, uint32_t *row_end, cudaStream_t st)
+int pf_launch_mark_rows(const uint32_t *key, unsigned long long n, uint2 *row, cudaStream_t st)
 {
 	if (n == 0)
 		return 0;
-	pf_mark_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, row_start, row_end);
+	pf_mark_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, row);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -741,6 +858,33 @@ int pf_launch_probe(const PfArgs &a, uint32_t ntl, bool fill, cudaStream_t st)
 		pf_probe_kernel<false><<<ntl, 128, 0, st>>>(a);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
+
+int pf_launch_probe_extend(const PfArgs &a, uint32_t ntl, int which, cudaStream_t st)
+{
+	if (ntl == 0)
+		return 0;
+	static bool configured = false;
+	if (!configured) {
+		if (cudaFuncSetAttribute(pf_probe_extend_kernel<kFuseSlotsS, 512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				(int)fuse_smem_bytes(kFuseSlotsS)) != cudaSuccess ||
+			cudaFuncSetAttribute(pf_probe_extend_kernel<kFuseSlotsL, 1024, kFuseSlotsS / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				(int)fuse_smem_bytes(kFuseSlotsL)) != cudaSuccess)
+			return -1;
+		configured = true;
+	}
+	int n = 0;
+	if (which & 1) {
+		pf_probe_extend_kernel<kFuseSlotsS, 512, 0><<<ntl, 512, fuse_smem_bytes(kFuseSlotsS), st>>>(a);
+		++n;
+	}
+	if (which & 2) {
+		pf_probe_extend_kernel<kFuseSlotsL, 1024, kFuseSlotsS / 2><<<ntl, 1024, fuse_smem_bytes(kFuseSlotsL), st>>>(a);
+		++n;
+	}
+	return cudaGetLastError() == cudaSuccess ? n : -1;
+}
+
+uint32_t pf_fuse_max_hits(int size) { return size == 0 ? kFuseSlotsS / 2 : kFuseSlotsL / 2; }
 
 int pf_launch_extend(const PfArgs &a, uint32_t ntl, cudaStream_t st)
 {

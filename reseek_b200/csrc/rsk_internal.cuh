@@ -299,6 +299,7 @@ int launch_global(const GlobalArgs &args, int blocks, cudaStream_t stream);
 // K6..K8: `-fast -db` 5-mer prefilter, see prefilter_kernel.cu
 struct PfArgs {
 	const int *kmer_mx;          // Mu_S_ij_i8 widened to int32 [36*36]
+	const uint8_t *nb_tab;       // [36][136] per letter: letters by descending score, those scores, ge counts (pf_neighborhood_kernel)
 	// query side (letters already K/L-swapped when the caller asks for it)
 	uint32_t nQ; uint32_t nqk;   // queries, total 5-mer slots (sum of max(L-6, 0))
 	const uint8_t *muQ; const uint64_t *offQ; const uint32_t *lenQ;
@@ -307,7 +308,8 @@ struct PfArgs {
 	uint32_t *nb_count; const unsigned long long *nb_off;  // [nqk] index entries contributed by each query 5-mer
 	uint32_t *ix_key, *ix_val;   // index entries (unsorted while filling; ix_val sorted by key when probing)
 	uint32_t exact_twice;        // query-neighbourhood mode: the k-mer itself is entered a second time
-	const uint32_t *row_start, *row_end;  // [36^5] dense row table over the sorted index
+	const uint2 *row;            // [36^5] dense row table over the sorted index: (first entry, one past the last)
+	uint32_t diag_safe;          // longest query + longest target <= 16384: no diagonal is dropped (prefiltermu.cpp:254)
 	// target side
 	uint32_t t_begin;            // first target of the batch
 	const uint8_t *muT; const uint64_t *offT; const uint32_t *lenT;
@@ -323,9 +325,12 @@ struct PfArgs {
 int pf_launch_swap_kl(const uint8_t *in, uint8_t *out, uint64_t n, cudaStream_t st);
 int pf_launch_query_kmers(const PfArgs &a, cudaStream_t st);
 int pf_launch_neighborhood(const PfArgs &a, bool fill, cudaStream_t st);
-int pf_launch_mark_rows(const uint32_t *key, unsigned long long n, uint32_t *row_start, uint32_t *row_end, cudaStream_t st);
+int pf_launch_mark_rows(const uint32_t *key, unsigned long long n, uint2 *row, cudaStream_t st);
 int pf_launch_probe(const PfArgs &a, uint32_t ntl, bool fill, cudaStream_t st);
 int pf_launch_extend(const PfArgs &a, uint32_t ntl, cudaStream_t st);
+// K7+K8 in shared memory: which & 1 = targets with <= pf_fuse_max_hits(0) hits, which & 2 = those up to pf_fuse_max_hits(1)
+int pf_launch_probe_extend(const PfArgs &a, uint32_t ntl, int which, cudaStream_t st);
+uint32_t pf_fuse_max_hits(int size);
 int pf_launch_cands(const PfArgs &a, uint32_t ntl, bool write, cudaStream_t st);
 size_t pf_bag_smem_bytes(uint32_t B);
 int pf_sort_by_query(const uint32_t *qin, uint32_t *qout, const unsigned long long *vin, unsigned long long *vout, unsigned long long n,

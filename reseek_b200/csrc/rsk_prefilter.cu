@@ -147,7 +147,8 @@ void finish_bags(std::vector<Bag> &bags, uint32_t B, rsk_prefilter_result &res, 
 
 struct PfScratch {
 	DevBuf<uint8_t> muq, tmp;
-	DevBuf<uint32_t> qk_off, qk_code, qk_val, nb_count, key_a, key_b, val_a, val_b, row_start, row_end;
+	DevBuf<uint32_t> qk_off, qk_code, qk_val, nb_count, key_a, key_b, val_a, val_b;
+	DevBuf<uint2> row;
 	DevBuf<unsigned long long> nb_off, hit_count, hit_off, cand_off;
 	DevBuf<uint32_t> hit_key, hit_sorted, cand_count, cand_t, cand_q;
 	DevBuf<unsigned> best;
@@ -155,16 +156,19 @@ struct PfScratch {
 	DevBuf<uint32_t> raw_q, srt_q, bag_n;
 	DevBuf<unsigned long long> raw_v, srt_v, seg_begin, seg_end, bag_key, bag_off, dense_a, dense_b;
 	int *kmer_mx = nullptr;
+	uint8_t *nb_tab = nullptr;
 	~PfScratch()
 	{
 		muq.release(); tmp.release(); qk_off.release(); qk_code.release(); qk_val.release(); nb_count.release();
-		key_a.release(); key_b.release(); val_a.release(); val_b.release(); row_start.release(); row_end.release();
+		key_a.release(); key_b.release(); val_a.release(); val_b.release(); row.release();
 		nb_off.release(); hit_count.release(); hit_off.release(); cand_off.release(); hit_key.release();
 		hit_sorted.release(); cand_count.release(); cand_t.release(); cand_q.release(); best.release(); cand_s.release();
 		raw_q.release(); srt_q.release(); bag_n.release(); raw_v.release(); srt_v.release(); seg_begin.release(); seg_end.release();
 		bag_key.release(); bag_off.release(); dense_a.release(); dense_b.release();
 		if (kmer_mx)
 			cudaFree(kmer_mx);
+		if (nb_tab)
+			cudaFree(nb_tab);
 	}
 };
 
@@ -262,11 +266,34 @@ int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset
 		const int8_t *m8 = rsk_mu_kmer_matrix_i8();
 		for (int k = 0; k < 36 * 36; ++k)
 			mx[k] = m8[k];
+		// per letter x: the 36 letters y by S[x][y] descending (ties by letter), those scores, ge[t] = #{y : S[x][y] >= t - 32}
+		std::vector<uint8_t> nb(36 * 136);
+		for (int x = 0; x < 36; ++x) {
+			int order[36];
+			for (int y = 0; y < 36; ++y)
+				order[y] = y;
+			std::stable_sort(order, order + 36, [&](int u, int v) { return m8[36 * x + u] > m8[36 * x + v]; });
+			for (int r = 0; r < 36; ++r) {
+				nb[136 * x + r] = (uint8_t)order[r];
+				nb[136 * x + 36 + r] = (uint8_t)m8[36 * x + order[r]];
+			}
+			for (int t = 0; t < 64; ++t) {
+				int c = 0;
+				for (int y = 0; y < 36; ++y)
+					c += m8[36 * x + y] >= t - 32;
+				nb[136 * x + 72 + t] = (uint8_t)c;
+			}
+			if (m8[36 * x + order[35]] < -32 || m8[36 * x + order[0]] > 30)
+				return fail(RSK_ERR_LIMIT, "rsk_prefilter: k-mer score outside the neighbourhood tables' range");
+		}
 		CK(cudaMalloc((void **)&S.kmer_mx, sizeof(int) * 36 * 36));
+		CK(cudaMalloc((void **)&S.nb_tab, nb.size()));
 		CK(cudaMemcpyAsync(S.kmer_mx, mx.data(), sizeof(int) * 36 * 36, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(S.nb_tab, nb.data(), nb.size(), cudaMemcpyHostToDevice, st));
 		CK(cudaStreamSynchronize(st));
 	}
 	a.kmer_mx = S.kmer_mx;
+	a.nb_tab = S.nb_tab;
 	a.nQ = nQ;
 	a.offQ = Q->d.off; a.lenQ = Q->d.len;
 	a.muT = T->d.mu; a.offT = T->d.off; a.lenT = T->d.len;
@@ -288,10 +315,8 @@ int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset
 	const uint32_t nqk = qk_off[nQ];
 	a.nqk = nqk;
 	unsigned long long nindex = 0;
-	NOMEM(S.row_start.ensure(kDict));
-	NOMEM(S.row_end.ensure(kDict));
-	CK(cudaMemsetAsync(S.row_start.p, 0, sizeof(uint32_t) * kDict, st));
-	CK(cudaMemsetAsync(S.row_end.p, 0, sizeof(uint32_t) * kDict, st));
+	NOMEM(S.row.ensure(kDict));
+	CK(cudaMemsetAsync(S.row.p, 0, sizeof(uint2) * kDict, st));
 	if (nqk) {
 		NOMEM(S.qk_off.ensure(nQ + 1));
 		NOMEM(S.qk_code.ensure(nqk));
@@ -327,11 +352,12 @@ int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset
 			if (pf_sort_pairs(S.key_a.p, S.key_b.p, S.val_a.p, S.val_b.p, nindex, S.tmp.p, tb, st))
 				return fail(RSK_ERR_CUDA, "rsk_prefilter: cub sort failed: %s", cudaGetErrorString(cudaGetLastError()));
 			launches += 4;
-			PFL(pf_launch_mark_rows(S.key_b.p, nindex, S.row_start.p, S.row_end.p, st));
+			PFL(pf_launch_mark_rows(S.key_b.p, nindex, S.row.p, st));
 			a.ix_key = S.key_b.p; a.ix_val = S.val_b.p;
 		}
 	}
-	a.row_start = S.row_start.p; a.row_end = S.row_end.p;
+	a.row = S.row.p;
+	a.diag_safe = (uint64_t)Q->maxlen + T->maxlen <= 0x4000u ? 1u : 0u;
 	tm.mark("K6 query index");
 	if (!nindex)
 		return RSK_OK;
@@ -361,30 +387,44 @@ int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset
 			t0 = t1;
 			continue;
 		}
+		// targets with few hits stay in shared memory (pf_probe_extend_kernel); the others go through global memory:
+		// keys written per target, segmented sort, scan for runs
+		const uint32_t fuse_small = pf_fuse_max_hits(0), fuse_max = pf_fuse_max_hits(1);
 		hoff.assign(ntl + 1, 0);
-		for (uint32_t k = 0; k < ntl; ++k)
-			hoff[k + 1] = hoff[k] + hcnt[t0 + k];
+		int which = 0;
+		for (uint32_t k = 0; k < ntl; ++k) {
+			const unsigned long long h = hcnt[t0 + k];
+			hoff[k + 1] = hoff[k] + (h > fuse_max ? h : 0);
+			which |= h == 0 ? 0 : h <= fuse_small ? 1 : h <= fuse_max ? 2 : 0;
+		}
+		const unsigned long long big = hoff[ntl];
 		NOMEM(S.hit_off.ensure(ntl + 1));
-		NOMEM(S.hit_key.ensure(tot));
-		NOMEM(S.hit_sorted.ensure(tot));
 		NOMEM(S.best.ensure((size_t)ntl * nQ));
 		NOMEM(S.cand_count.ensure(ntl));
 		NOMEM(S.cand_off.ensure(ntl + 1));
-		CK(cudaMemcpyAsync(S.hit_off.p, hoff.data(), sizeof(unsigned long long) * (ntl + 1), cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(S.best.p, 0, sizeof(unsigned) * (size_t)ntl * nQ, st));
 		a.t_begin = t0;
-		a.hit_off = S.hit_off.p; a.hit_key = S.hit_key.p; a.hit_sorted = S.hit_sorted.p; a.best = S.best.p;
+		a.best = S.best.p;
 		a.cand_count = S.cand_count.p; a.cand_off = S.cand_off.p;
-		PFL(pf_launch_probe(a, ntl, true, st));
-		size_t tb = 0;
-		if (pf_segmented_sort(S.hit_key.p, S.hit_sorted.p, tot, ntl, S.hit_off.p, nullptr, tb, st))
-			return fail(RSK_ERR_CUDA, "rsk_prefilter: cub segmented sort sizing failed");
-		NOMEM(S.tmp.ensure(tb));
-		if (pf_segmented_sort(S.hit_key.p, S.hit_sorted.p, tot, ntl, S.hit_off.p, S.tmp.p, tb, st))
-			return fail(RSK_ERR_CUDA, "rsk_prefilter: cub segmented sort failed: %s", cudaGetErrorString(cudaGetLastError()));
-		launches += 3;
-		tm.mark("K7 probe+sort");
-		PFL(pf_launch_extend(a, ntl, st));
+		if (which)
+			PFL(pf_launch_probe_extend(a, ntl, which, st));
+		tm.mark("K7+K8 in shared memory");
+		if (big) {
+			NOMEM(S.hit_key.ensure(big));
+			NOMEM(S.hit_sorted.ensure(big));
+			CK(cudaMemcpyAsync(S.hit_off.p, hoff.data(), sizeof(unsigned long long) * (ntl + 1), cudaMemcpyHostToDevice, st));
+			a.hit_off = S.hit_off.p; a.hit_key = S.hit_key.p; a.hit_sorted = S.hit_sorted.p;
+			PFL(pf_launch_probe(a, ntl, true, st));
+			size_t tb = 0;
+			if (pf_segmented_sort(S.hit_key.p, S.hit_sorted.p, big, ntl, S.hit_off.p, nullptr, tb, st))
+				return fail(RSK_ERR_CUDA, "rsk_prefilter: cub segmented sort sizing failed");
+			NOMEM(S.tmp.ensure(tb));
+			if (pf_segmented_sort(S.hit_key.p, S.hit_sorted.p, big, ntl, S.hit_off.p, S.tmp.p, tb, st))
+				return fail(RSK_ERR_CUDA, "rsk_prefilter: cub segmented sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+			launches += 3;
+			tm.mark("K7 probe+sort");
+			PFL(pf_launch_extend(a, ntl, st));
+		}
 		PFL(pf_launch_cands(a, ntl, false, st));
 		tm.mark("K8 extend+count");
 		ccnt.resize(ntl);
