@@ -371,72 +371,64 @@ __device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int *S, con
 	}
 }
 
-// ---- K7+K8 fused, for targets with at most kFuseHits index hits (every target of a 100-query block against SCOP40-sized chains):
-// the hit keys never leave the SM.  A key is entered into a shared-memory hash set; the SECOND arrival of a key makes its
-// diagonal a two-hit diagonal (TwoHitDiag::SetDupes, twohitdiag.cpp:389) and queues it once; then the CTA walks the queued
-// diagonals.  Which thread sees the second arrival is timing dependent, the SET of queued diagonals is not, and best[] is a max.
-// This replaces, for those targets, the 4 B/hit key store, the segmented radix sort of the keys and the scan for runs.
-// Two sizes: 16384 slots (<= 8192 hits; two CTAs of 512 threads per SM) and 32768 slots (<= 16384 hits, one CTA of 1024).
-constexpr uint32_t kSlotEmpty = 0xffffffffu, kSlotDup = 0x80000000u, kSlotKey = 0x3fffffffu;  // keys are < 65535 << 14
-constexpr uint32_t kFuseSlotsS = 16384, kFuseSlotsL = 32768;
-constexpr size_t fuse_smem_bytes(uint32_t slots) { return sizeof(uint32_t) * (slots + slots / 4); }
+// ---- K7+K8 fused: the hits of a target never leave the SM.  A target sees sum(LQ) + nQ * (LT - 1) distinct (query, diagonal)
+// pairs; with a block of 100 queries that is ~45 000 for a 300-residue target, so two BITMAPS over them fit in shared memory:
+// `seen` (a hit fell on the diagonal) and `twice` (a second one did - TwoHitDiag::SetDupes, twohitdiag.cpp:389).  The hit that
+// sets `twice` queues the diagonal, once; then the CTA walks the queued diagonals (a full queue makes the finder walk its
+// diagonal itself).  Which thread sees the second hit is timing dependent, the SET of walked diagonals is not, and best[] is a
+// max.  Against the global-memory path (4 B/hit key store, segmented radix sort, scan for runs) this is 8.4 -> ? ms per
+// 100 x 20 000 block.  Two size classes by bitmap size keep the short targets at high occupancy.
+constexpr uint32_t kBmSmallBits = 1u << 16, kBmLargeBits = 3u << 17;  // 2 x 8 KB and 2 x 48 KB of bitmaps
+constexpr size_t bm_smem_bytes(uint32_t bits, uint32_t queue) { return (size_t)bits / 8 * 2 + sizeof(uint32_t) * queue; }
 
-template <uint32_t SLOTS, int THREADS, uint32_t MINHITS>
+template <uint32_t MINBITS, uint32_t MAXBITS, uint32_t QUEUE, int THREADS>
 __global__ void __launch_bounds__(THREADS) pf_probe_extend_kernel(const PfArgs a)
 {
-	extern __shared__ __align__(16) uint32_t fuse_smem[];
-	uint32_t *tab = fuse_smem, *queue = fuse_smem + SLOTS;
+	extern __shared__ __align__(16) uint32_t bm_smem[];
 	__shared__ int S[36 * 36];
 	__shared__ unsigned s_n, s_next;
 	const uint32_t tl = blockIdx.x;
 	const uint32_t t = a.t_begin + tl;
-	const unsigned long long hits = a.hit_count[t];
-	if (hits <= MINHITS || hits > SLOTS / 2)
-		return;  // nothing to do / the other size / the global-memory path takes this target
-	// table size by the target's own hit count: at most half full
-	uint32_t slots = 256;
-	while (slots < 2 * (uint32_t)hits)
-		slots <<= 1;
-	const uint32_t mask = slots - 1;
-	const int shift = __clz(mask);  // 32 - log2(slots)
+	const uint32_t LT = a.lenT[t];
+	if (LT < 7)
+		return;
+	const unsigned long long nbits = (unsigned long long)a.sum_lenQ + (unsigned long long)a.nQ * (LT - 1);
+	if (nbits <= MINBITS || nbits > MAXBITS)
+		return;  // the other size class, or the global-memory path
+	const uint32_t words = ((uint32_t)nbits + 31) / 32;
+	uint32_t *seen = bm_smem, *twice = bm_smem + words, *queue = bm_smem + MAXBITS / 32 * 2;
 	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
 		S[k] = a.kmer_mx[k];
-	for (uint32_t k = threadIdx.x; k < slots / 4; k += blockDim.x)
-		reinterpret_cast<uint4 *>(tab)[k] = make_uint4(kSlotEmpty, kSlotEmpty, kSlotEmpty, kSlotEmpty);
+	for (uint32_t k = threadIdx.x; k < 2 * words; k += blockDim.x)
+		bm_smem[k] = 0;
 	if (threadIdx.x == 0) { s_n = 0; s_next = 0; }
 	__syncthreads();
-	const uint32_t LT = a.lenT[t];
 	const uint8_t *T = a.muT + a.offT[t];
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-	if (LT >= 7) {
-		uint2 r = probe_row(a, T, LT, warp, S);
-		for (uint32_t tpos = warp; tpos + 7 <= LT; tpos += nwarps) {
-			const uint2 rn = probe_row(a, T, LT, tpos + nwarps, S);
-			for (uint32_t e = r.x + lane; e < r.y; e += 32) {
-				const uint32_t v = __ldg(a.ix_val + e);
-				const uint32_t q = v >> 16, qpos = v & 0xffffu;
-				const uint32_t diag = a.lenQ[q] + tpos - qpos - 1;  // diag.h:22-25
-				if (diag > 0x3fffu)
-					continue;  // prefiltermu.cpp:254
-				const uint32_t key = (q << 14) | diag;
-				uint32_t h = (key * 2654435761u) >> shift;
-				for (;;) {
-					const uint32_t old = atomicCAS(&tab[h], kSlotEmpty, key);
-					if (old == kSlotEmpty)
-						break;  // first hit on this diagonal
-					if ((old & kSlotKey) == key) {
-						if (!(old & kSlotDup) && !(atomicOr(&tab[h], kSlotDup) & kSlotDup))
-							queue[atomicAdd(&s_n, 1u)] = key;  // second hit: a two-hit diagonal, queued once
-						break;
-					}
-					h = (h + 1) & mask;
-				}
+	uint2 r = probe_row(a, T, LT, warp, S);
+	for (uint32_t tpos = warp; tpos + 7 <= LT; tpos += nwarps) {
+		const uint2 rn = probe_row(a, T, LT, tpos + nwarps, S);
+		for (uint32_t e = r.x + lane; e < r.y; e += 32) {
+			const uint32_t v = __ldg(a.ix_val + e);
+			const uint32_t q = v >> 16, qpos = v & 0xffffu;
+			const uint2 qi = __ldg(a.qinfo + q);  // length, residues of the queries before q
+			const uint32_t diag = qi.x + tpos - qpos - 1;  // diag.h:22-25
+			if (diag > 0x3fffu)
+				continue;  // prefiltermu.cpp:254
+			const uint32_t idx = qi.y + q * (LT - 1) + diag;
+			const uint32_t w = idx >> 5, m = 1u << (idx & 31u);
+			if ((atomicOr(&seen[w], m) & m) && !(atomicOr(&twice[w], m) & m)) {
+				const unsigned slot = atomicAdd(&s_n, 1u);
+				if (slot < QUEUE)
+					queue[slot] = (q << 14) | diag;
+				else
+					walk_diagonal(a, S, T, LT, tl, (q << 14) | diag);
 			}
-			r = rn;
 		}
+		r = rn;
 	}
 	__syncthreads();
-	const unsigned n = s_n;
+	const unsigned n = min(s_n, QUEUE);
 	for (;;) {
 		const unsigned w = atomicAdd(&s_next, 1u);
 		if (w >= n)
@@ -863,28 +855,30 @@ int pf_launch_probe_extend(const PfArgs &a, uint32_t ntl, int which, cudaStream_
 {
 	if (ntl == 0)
 		return 0;
+	auto small = pf_probe_extend_kernel<0, kBmSmallBits, 2048, 256>;
+	auto large = pf_probe_extend_kernel<kBmSmallBits, kBmLargeBits, 4096, 512>;
+	const size_t smem_s = bm_smem_bytes(kBmSmallBits, 2048), smem_l = bm_smem_bytes(kBmLargeBits, 4096);
 	static bool configured = false;
 	if (!configured) {
-		if (cudaFuncSetAttribute(pf_probe_extend_kernel<kFuseSlotsS, 512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int)fuse_smem_bytes(kFuseSlotsS)) != cudaSuccess ||
-			cudaFuncSetAttribute(pf_probe_extend_kernel<kFuseSlotsL, 1024, kFuseSlotsS / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int)fuse_smem_bytes(kFuseSlotsL)) != cudaSuccess)
+		if (cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess ||
+			cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess)
 			return -1;
 		configured = true;
 	}
 	int n = 0;
 	if (which & 1) {
-		pf_probe_extend_kernel<kFuseSlotsS, 512, 0><<<ntl, 512, fuse_smem_bytes(kFuseSlotsS), st>>>(a);
+		small<<<ntl, 256, smem_s, st>>>(a);
 		++n;
 	}
 	if (which & 2) {
-		pf_probe_extend_kernel<kFuseSlotsL, 1024, kFuseSlotsS / 2><<<ntl, 1024, fuse_smem_bytes(kFuseSlotsL), st>>>(a);
+		large<<<ntl, 512, smem_l, st>>>(a);
 		++n;
 	}
 	return cudaGetLastError() == cudaSuccess ? n : -1;
 }
 
-uint32_t pf_fuse_max_hits(int size) { return size == 0 ? kFuseSlotsS / 2 : kFuseSlotsL / 2; }
+// (query, diagonal) pairs a target may have for the fused kernels: size class 0, size class 1
+unsigned long long pf_fuse_max_bits(int size) { return size == 0 ? kBmSmallBits : kBmLargeBits; }
 
 int pf_launch_extend(const PfArgs &a, uint32_t ntl, cudaStream_t st)
 {

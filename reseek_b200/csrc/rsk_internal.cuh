@@ -304,6 +304,7 @@ struct PfArgs {
 	uint32_t nQ; uint32_t nqk;   // queries, total 5-mer slots (sum of max(L-6, 0))
 	const uint8_t *muQ; const uint64_t *offQ; const uint32_t *lenQ;
 	const uint32_t *qk_off;      // [nQ+1] first 5-mer slot of each query
+	const uint2 *qinfo; uint32_t sum_lenQ;  // [nQ] (length, residues of the queries before it); total query residues
 	uint32_t *qk_code, *qk_val;  // [nqk] code (0xffffffff = masked), value = query<<16 | position
 	uint32_t *nb_count; const unsigned long long *nb_off;  // [nqk] index entries contributed by each query 5-mer
 	uint32_t *ix_key, *ix_val;   // index entries (unsorted while filling; ix_val sorted by key when probing)
@@ -328,9 +329,10 @@ int pf_launch_neighborhood(const PfArgs &a, bool fill, cudaStream_t st);
 int pf_launch_mark_rows(const uint32_t *key, unsigned long long n, uint2 *row, cudaStream_t st);
 int pf_launch_probe(const PfArgs &a, uint32_t ntl, bool fill, cudaStream_t st);
 int pf_launch_extend(const PfArgs &a, uint32_t ntl, cudaStream_t st);
-// K7+K8 in shared memory: which & 1 = targets with <= pf_fuse_max_hits(0) hits, which & 2 = those up to pf_fuse_max_hits(1)
+// K7+K8 in shared memory: which & 1 = targets with sum(LQ) + nQ * (LT - 1) <= pf_fuse_max_bits(0), which & 2 = those up to
+// pf_fuse_max_bits(1); the others are left to pf_launch_probe / pf_launch_extend
 int pf_launch_probe_extend(const PfArgs &a, uint32_t ntl, int which, cudaStream_t st);
-uint32_t pf_fuse_max_hits(int size);
+unsigned long long pf_fuse_max_bits(int size);
 int pf_launch_cands(const PfArgs &a, uint32_t ntl, bool write, cudaStream_t st);
 size_t pf_bag_smem_bytes(uint32_t B);
 int pf_sort_by_query(const uint32_t *qin, uint32_t *qout, const unsigned long long *vin, unsigned long long *vout, unsigned long long n,

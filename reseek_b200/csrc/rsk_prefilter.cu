@@ -148,7 +148,7 @@ void finish_bags(std::vector<Bag> &bags, uint32_t B, rsk_prefilter_result &res, 
 struct PfScratch {
 	DevBuf<uint8_t> muq, tmp;
 	DevBuf<uint32_t> qk_off, qk_code, qk_val, nb_count, key_a, key_b, val_a, val_b;
-	DevBuf<uint2> row;
+	DevBuf<uint2> row, qinfo;
 	DevBuf<unsigned long long> nb_off, hit_count, hit_off, cand_off;
 	DevBuf<uint32_t> hit_key, hit_sorted, cand_count, cand_t, cand_q;
 	DevBuf<unsigned> best;
@@ -160,7 +160,7 @@ struct PfScratch {
 	~PfScratch()
 	{
 		muq.release(); tmp.release(); qk_off.release(); qk_code.release(); qk_val.release(); nb_count.release();
-		key_a.release(); key_b.release(); val_a.release(); val_b.release(); row.release();
+		key_a.release(); key_b.release(); val_a.release(); val_b.release(); row.release(); qinfo.release();
 		nb_off.release(); hit_count.release(); hit_off.release(); cand_off.release(); hit_key.release();
 		hit_sorted.release(); cand_count.release(); cand_t.release(); cand_q.release(); best.release(); cand_s.release();
 		raw_q.release(); srt_q.release(); bag_n.release(); raw_v.release(); srt_v.release(); seg_begin.release(); seg_end.release();
@@ -362,42 +362,63 @@ int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset
 	if (!nindex)
 		return RSK_OK;
 
-	// ---- K7 count pass over all targets, then batches sized by hits ----
+	// ---- K7/K8: targets whose (query, diagonal) pairs fit two shared-memory bitmaps go through the fused kernel; the others
+	// (long targets against large query blocks) through global memory: count pass, keys per target, segmented sort, run scan ----
+	std::vector<uint2> qinfo(nQ);
+	uint64_t sumLQ = 0;
+	for (uint32_t q = 0; q < nQ; ++q) {
+		qinfo[q] = make_uint2(Q->hlen[q], (uint32_t)sumLQ);
+		sumLQ += Q->hlen[q];
+	}
+	if (sumLQ >= (1ull << 31))
+		return fail(RSK_ERR_LIMIT, "rsk_prefilter: more than 2^31 query residues; split the query set");
+	NOMEM(S.qinfo.ensure(nQ));
+	CK(cudaMemcpyAsync(S.qinfo.p, qinfo.data(), sizeof(uint2) * nQ, cudaMemcpyHostToDevice, st));
+	a.qinfo = S.qinfo.p;
+	a.sum_lenQ = (uint32_t)sumLQ;
+	// RSK_PF_NOFUSE=1 sends every target through global memory (the parity tests run both paths)
+	const bool nofuse = getenv("RSK_PF_NOFUSE") != nullptr;
+	const unsigned long long bits_small = nofuse ? 0 : pf_fuse_max_bits(0), bits_max = nofuse ? 0 : pf_fuse_max_bits(1);
+	auto fuse_bits = [&](uint32_t t) -> unsigned long long { return T->hlen[t] < 7 ? 0 : sumLQ + (unsigned long long)nQ * (T->hlen[t] - 1); };
+	bool any_global = false;
+	for (uint32_t t = 0; t < nT && !any_global; ++t)
+		any_global = fuse_bits(t) > bits_max;
 	std::vector<unsigned long long> hcnt(nT, 0);
-	NOMEM(S.hit_count.ensure(nT));
-	a.t_begin = 0;
-	a.hit_count = S.hit_count.p;
-	PFL(pf_launch_probe(a, nT, false, st));
-	CK(cudaMemcpyAsync(hcnt.data(), S.hit_count.p, sizeof(unsigned long long) * nT, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
-	tm.mark("K7 count pass");
+	if (any_global) {
+		NOMEM(S.hit_count.ensure(nT));
+		a.t_begin = 0;
+		a.hit_count = S.hit_count.p;
+		PFL(pf_launch_probe(a, nT, false, st));
+		CK(cudaMemcpyAsync(hcnt.data(), S.hit_count.p, sizeof(unsigned long long) * nT, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for (uint32_t t = 0; t < nT; ++t)
+			if (fuse_bits(t) <= bits_max)
+				hcnt[t] = 0;  // taken by the fused kernel
+		tm.mark("K7 count pass");
+	}
 	const unsigned long long kMaxHits = 1ull << 28;              // 1 GB of keys + 1 GB sorted per batch
 	const uint32_t kMaxT = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(1u << 16, ((uint64_t)1 << 26) / nQ));
 	std::vector<unsigned long long> hoff, coff;
 	std::vector<uint32_t> ccnt;
 	for (uint32_t t0 = 0; t0 < nT;) {
 		uint32_t t1 = t0;
-		unsigned long long tot = 0;
-		while (t1 < nT && t1 - t0 < kMaxT && (t1 == t0 || tot + hcnt[t1] <= kMaxHits))
-			tot += hcnt[t1++];
+		unsigned long long big = 0;
+		while (t1 < nT && t1 - t0 < kMaxT && (t1 == t0 || big + hcnt[t1] <= kMaxHits))
+			big += hcnt[t1++];
 		const uint32_t ntl = t1 - t0;
-		if (tot >= (1ull << 32))
-			return fail(RSK_ERR_LIMIT, "rsk_prefilter: target %u alone produces %llu index hits", t0, tot);
-		if (tot == 0) {  // nothing to extend in this batch
-			t0 = t1;
-			continue;
-		}
-		// targets with few hits stay in shared memory (pf_probe_extend_kernel); the others go through global memory:
-		// keys written per target, segmented sort, scan for runs
-		const uint32_t fuse_small = pf_fuse_max_hits(0), fuse_max = pf_fuse_max_hits(1);
+		if (big >= (1ull << 32))
+			return fail(RSK_ERR_LIMIT, "rsk_prefilter: target %u alone produces %llu index hits", t0, big);
 		hoff.assign(ntl + 1, 0);
 		int which = 0;
 		for (uint32_t k = 0; k < ntl; ++k) {
-			const unsigned long long h = hcnt[t0 + k];
-			hoff[k + 1] = hoff[k] + (h > fuse_max ? h : 0);
-			which |= h == 0 ? 0 : h <= fuse_small ? 1 : h <= fuse_max ? 2 : 0;
+			hoff[k + 1] = hoff[k] + hcnt[t0 + k];
+			const unsigned long long b = fuse_bits(t0 + k);
+			which |= b == 0 || nofuse ? 0 : b <= bits_small ? 1 : b <= bits_max ? 2 : 0;
 		}
-		const unsigned long long big = hoff[ntl];
+		if (!which && !big) {  // nothing to extend in this batch
+			t0 = t1;
+			continue;
+		}
 		NOMEM(S.hit_off.ensure(ntl + 1));
 		NOMEM(S.best.ensure((size_t)ntl * nQ));
 		NOMEM(S.cand_count.ensure(ntl));

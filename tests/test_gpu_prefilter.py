@@ -21,10 +21,14 @@ def _mu_only_set(ctx, mus):
     return ctx.upload(lens, np.zeros((8, tot), np.uint8), np.concatenate(mus).astype(np.uint8), np.zeros((3, tot), np.float32), None)
 
 
-@pytest.mark.parametrize("name,kw", [("idxq", {}), ("idxt", {"index_mode": 2}), ("rsb5", {"rsb_size": 5})])
-def test_prefilter_matches_reference_candidate_tsv(rb, name, kw):
-    """q10.bca vs q100.bca: the reference binary's candidate TSV at -threads 1 (-idxq default, -idxt, -rsb_size 5)."""
+@pytest.mark.parametrize("name,kw", [("idxq", {}), ("idxt", {"index_mode": 2}), ("rsb5", {"rsb_size": 5}), ("idxq", {"nofuse": 1})])
+def test_prefilter_matches_reference_candidate_tsv(rb, name, kw, monkeypatch):
+    """q10.bca vs q100.bca: the reference binary's candidate TSV at -threads 1 (-idxq default, -idxt, -rsb_size 5; the default
+    once more through the global-memory form of K7/K8)."""
     from tests.test_oracle_golden import _prefilter_fixture
+    kw = dict(kw)
+    if kw.pop("nofuse", 0):
+        monkeypatch.setenv("RSK_PF_NOFUSE", "1")
     g, mq, mt = _prefilter_fixture()
     ctx = rb.Context(0, rb.MODE_FAST)
     Q, T = _mu_only_set(ctx, mq), _mu_only_set(ctx, mt)
@@ -45,11 +49,15 @@ def test_prefilter_matches_reference_candidate_tsv(rb, name, kw):
     ctx.close()
 
 
+@pytest.mark.parametrize("path", ["fused", "global"])
 @pytest.mark.parametrize("nq,index_mode", [(7, 0), (7, 2), (120, 0)])
-def test_prefilter_scores_match_oracle_on_synthetic(rb, port, nq, index_mode):
+def test_prefilter_scores_match_oracle_on_synthetic(rb, port, nq, index_mode, path, monkeypatch):
     """Planted homologs + random chains, ragged lengths (incl. chains shorter than one 7-window): every (target, query)
-    two-hit diagonal score equals the oracle's brute-force restatement; > 100 queries switches the index side."""
+    two-hit diagonal score equals the oracle's brute-force restatement; > 100 queries switches the index side.  Both forms of
+    K7/K8: hits kept in shared-memory bitmaps (the default for these sizes) and the global-memory path (sorted keys per target)."""
     from reseek_b200 import synth
+    if path == "global":
+        monkeypatch.setenv("RSK_PF_NOFUSE", "1")
     q = synth.make_chains(nq, [5, 7, 60, 150, 300, 420, 33][:min(nq, 7)] + [90] * max(0, nq - 7), seed=501)
     t = synth.make_chains(60, 140, seed=502, length_jitter=0.7)
     synth.plant_homologs(t, q, 0.5, seed=503, sub=0.25, indel=0.03)
