@@ -30,7 +30,8 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMinPair = 36;      // MIN_KMER_PAIR_SCORE, also the self-score mask (prefiltermuparams.h)
 constexpr uint32_t kMasked = 0xffffffffu;
 
-__device__ __forceinline__ uint32_t kmer5(const uint8_t *w, const int *S, bool &masked)
+template <typename TS>
+__device__ __forceinline__ uint32_t kmer5(const uint8_t *w, const TS *S, bool &masked)
 {
 	// spaced pattern 1110011: offsets 0,1,2,5,6 (prefiltermuparams.h:7-10), base-36 big-endian (mudex.cpp:517-538)
 	const int o[5] = {0, 1, 2, 5, 6};
@@ -260,7 +261,8 @@ __global__ void pf_mark_rows_kernel(const uint32_t *__restrict__ key, unsigned l
 // One warp per target position: the lanes read the index row of its 5-mer side by side (coalesced 4-byte values); the row
 // bounds of the warp's NEXT position are fetched before the current row is walked, so the two dependent misses of a position
 // (row bounds, then row entries) overlap with the previous row.
-__device__ __forceinline__ uint2 probe_row(const PfArgs &a, const uint8_t *T, uint32_t LT, uint32_t tpos, const int *S)
+template <typename TS>
+__device__ __forceinline__ uint2 probe_row(const PfArgs &a, const uint8_t *T, uint32_t LT, uint32_t tpos, const TS *S)
 {
 	if (tpos + 7 > LT)
 		return make_uint2(0, 0);
@@ -323,9 +325,11 @@ __global__ void __launch_bounds__(128) pf_probe_kernel(const PfArgs a)
 }
 
 // FindHSP (prefiltermu.cpp:12-48) over the whole diagonal `d` of (query q, target T): Kadane scan in diagonal order, the best
-// score goes to best[tl][q].  Four positions per trip: the letters of both chains come as 32-bit words assembled from aligned
-// loads (one new word per chain and trip) - byte loads had the L1 data pipe 88 % busy.
-__device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int *S, const uint8_t *T, uint32_t LT, uint32_t tl, uint32_t k)
+// score goes to best[tl][q].  The reference's `F += s; if (F > B) B = F; else if (F < 0) F = 0` is F = max(F + s, 0),
+// B = max(B, F) - two DPX instructions (VIADDMNMX, VIMNMX).  Four positions per trip: the letters of both chains come as 32-bit
+// words assembled from aligned loads (one new word per chain and trip), the scores from an int8 table in shared memory:
+// per position two byte extracts, one IMAD, one LDS, two DPX (the first form - int table, compare-and-select - ran 16).
+__device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int8_t *S, const uint8_t *T, uint32_t LT, uint32_t tl, uint32_t k)
 {
 	const uint32_t q = k >> 14;
 	const int d = (int)(k & 0x3fffu);
@@ -347,23 +351,22 @@ __device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int *S, con
 			uint32_t q1 = q0, t1 = t0;
 			if (qs || g + 1 < groups) q1 = __ldg(++qw);
 			if (ts || g + 1 < groups) t1 = __ldg(++tw);
-			const uint32_t qv = qs ? __funnelshift_r(q0, q1, qs) : q0;
-			const uint32_t tv = ts ? __funnelshift_r(t0, t1, ts) : t0;
+			const uint32_t qv = __funnelshift_r(q0, q1, qs);
+			const uint32_t tv = __funnelshift_r(t0, t1, ts);
 			q0 = q1; t0 = t1;
 #pragma unroll
 			for (int b = 0; b < 4; ++b) {
-				F += S[36 * ((qv >> (8 * b)) & 0xffu) + ((tv >> (8 * b)) & 0xffu)];
-				if (F > B) B = F;
-				else if (F < 0) F = 0;
+				const int sc = S[36u * __byte_perm(qv, 0, 0x4440 + b) + __byte_perm(tv, 0, 0x4440 + b)];
+				F = __viaddmax_s32(F, sc, 0);
+				B = max(B, F);
 			}
 		}
 		qp += 4 * groups; tp += 4 * groups;
 		n -= 4 * groups;
 	}
 	for (int i = 0; i < n; ++i) {
-		F += S[36 * qp[i] + tp[i]];
-		if (F > B) B = F;
-		else if (F < 0) F = 0;
+		F = __viaddmax_s32(F, (int)S[36 * qp[i] + tp[i]], 0);
+		B = max(B, F);
 	}
 	if (B > 0) {
 		if (B >= 65535) B = 65534;  // prefiltermu.cpp:294-295
@@ -374,18 +377,20 @@ __device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int *S, con
 // ---- K7+K8 fused: the hits of a target never leave the SM.  A target sees sum(LQ) + nQ * (LT - 1) distinct (query, diagonal)
 // pairs; with a block of 100 queries that is ~45 000 for a 300-residue target, so two BITMAPS over them fit in shared memory:
 // `seen` (a hit fell on the diagonal) and `twice` (a second one did - TwoHitDiag::SetDupes, twohitdiag.cpp:389).  The hit that
-// sets `twice` queues the diagonal, once; then the CTA walks the queued diagonals (a full queue makes the finder walk its
-// diagonal itself).  Which thread sees the second hit is timing dependent, the SET of walked diagonals is not, and best[] is a
-// max.  Against the global-memory path (4 B/hit key store, segmented radix sort, scan for runs) this is 8.4 -> ? ms per
-// 100 x 20 000 block.  Two size classes by bitmap size keep the short targets at high occupancy.
+// sets `twice` queues the diagonal, once; then the CTA walks the queued diagonals, clearing their `twice` bits.  Diagonals that
+// found the queue full keep their bit and are collected from the bitmap afterwards, a queue-full at a time.  Which thread sees
+// the second hit is timing dependent, the SET of walked diagonals is not, and best[] is a max.  Against the global-memory path
+// (4 B/hit key store, segmented radix sort, scan for runs) this saves the sort and ~1.2 GB of traffic per 100 x 20 000 block.
+// Two size classes by bitmap size keep the short targets at high occupancy.
 constexpr uint32_t kBmSmallBits = 1u << 16, kBmLargeBits = 3u << 17;  // 2 x 8 KB and 2 x 48 KB of bitmaps
+constexpr uint32_t kBmSmallQueue = 4096, kBmLargeQueue = 8192;
 constexpr size_t bm_smem_bytes(uint32_t bits, uint32_t queue) { return (size_t)bits / 8 * 2 + sizeof(uint32_t) * queue; }
 
 template <uint32_t MINBITS, uint32_t MAXBITS, uint32_t QUEUE, int THREADS>
 __global__ void __launch_bounds__(THREADS) pf_probe_extend_kernel(const PfArgs a)
 {
 	extern __shared__ __align__(16) uint32_t bm_smem[];
-	__shared__ int S[36 * 36];
+	__shared__ int8_t S[36 * 36];
 	__shared__ unsigned s_n, s_next;
 	const uint32_t tl = blockIdx.x;
 	const uint32_t t = a.t_begin + tl;
@@ -396,9 +401,10 @@ __global__ void __launch_bounds__(THREADS) pf_probe_extend_kernel(const PfArgs a
 	if (nbits <= MINBITS || nbits > MAXBITS)
 		return;  // the other size class, or the global-memory path
 	const uint32_t words = ((uint32_t)nbits + 31) / 32;
+	const uint32_t qcap = a.queue_cap ? min(a.queue_cap, QUEUE) : QUEUE;  // (the tests shrink the queue to exercise the overflow)
 	uint32_t *seen = bm_smem, *twice = bm_smem + words, *queue = bm_smem + MAXBITS / 32 * 2;
 	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
-		S[k] = a.kmer_mx[k];
+		S[k] = (int8_t)a.kmer_mx[k];
 	for (uint32_t k = threadIdx.x; k < 2 * words; k += blockDim.x)
 		bm_smem[k] = 0;
 	if (threadIdx.x == 0) { s_n = 0; s_next = 0; }
@@ -419,21 +425,64 @@ __global__ void __launch_bounds__(THREADS) pf_probe_extend_kernel(const PfArgs a
 			const uint32_t w = idx >> 5, m = 1u << (idx & 31u);
 			if ((atomicOr(&seen[w], m) & m) && !(atomicOr(&twice[w], m) & m)) {
 				const unsigned slot = atomicAdd(&s_n, 1u);
-				if (slot < QUEUE)
+				if (slot < qcap)
 					queue[slot] = (q << 14) | diag;
-				else
-					walk_diagonal(a, S, T, LT, tl, (q << 14) | diag);
 			}
 		}
 		r = rn;
 	}
 	__syncthreads();
-	const unsigned n = min(s_n, QUEUE);
+	const unsigned found = s_n;
+	const unsigned n = min(found, qcap);
 	for (;;) {
 		const unsigned w = atomicAdd(&s_next, 1u);
 		if (w >= n)
 			break;
-		walk_diagonal(a, S, T, LT, tl, queue[w]);
+		const uint32_t k = queue[w];
+		if (found > qcap) {  // leave only the diagonals that missed the queue in `twice`
+			const uint32_t q = k >> 14;
+			const uint32_t idx = __ldg(a.qinfo + q).y + q * (LT - 1) + (k & 0x3fffu);
+			atomicAnd(&twice[idx >> 5], ~(1u << (idx & 31u)));
+		}
+		walk_diagonal(a, S, T, LT, tl, k);
+	}
+	if (found <= qcap)
+		return;
+	// the diagonals that found the queue full: collect them from the bitmap, at most a queue-full per round
+	const uint32_t wstep = max(qcap / 32u, 1u);
+	for (uint32_t w0 = 0; w0 < words; w0 += wstep) {
+		__syncthreads();
+		if (threadIdx.x == 0) { s_n = 0; s_next = 0; }
+		__syncthreads();
+		for (uint32_t w = w0 + threadIdx.x; w < min(words, w0 + wstep); w += blockDim.x) {
+			uint32_t bits = twice[w];
+			while (bits) {
+				const uint32_t idx = w * 32 + (__ffs(bits) - 1);
+				bits &= bits - 1;
+				// the query whose diagonals contain idx: the last q with qinfo[q].y + q * (LT - 1) <= idx
+				uint32_t lo = 0, hi = a.nQ - 1;
+				while (lo < hi) {
+					const uint32_t mid = (lo + hi + 1) >> 1;
+					if (__ldg(a.qinfo + mid).y + mid * (LT - 1) <= idx)
+						lo = mid;
+					else
+						hi = mid - 1;
+				}
+				const uint32_t diag = idx - (__ldg(a.qinfo + lo).y + lo * (LT - 1));
+				if (qcap >= 32)
+					queue[atomicAdd(&s_n, 1u)] = (lo << 14) | diag;
+				else
+					walk_diagonal(a, S, T, LT, tl, (lo << 14) | diag);
+			}
+		}
+		__syncthreads();
+		const unsigned n2 = s_n;
+		for (;;) {
+			const unsigned w = atomicAdd(&s_next, 1u);
+			if (w >= n2)
+				break;
+			walk_diagonal(a, S, T, LT, tl, queue[w]);
+		}
 	}
 }
 
@@ -444,11 +493,11 @@ __global__ void __launch_bounds__(THREADS) pf_probe_extend_kernel(const PfArgs a
 constexpr int kPfQueue = 2048;
 __global__ void __launch_bounds__(128) pf_extend_kernel(const PfArgs a)
 {
-	__shared__ int S[36 * 36];
+	__shared__ int8_t S[36 * 36];
 	__shared__ uint32_t s_queue[kPfQueue];
 	__shared__ unsigned s_n, s_next;
 	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
-		S[k] = a.kmer_mx[k];
+		S[k] = (int8_t)a.kmer_mx[k];
 	const uint32_t tl = blockIdx.x;
 	const uint32_t t = a.t_begin + tl;
 	const unsigned long long s0 = a.hit_off[tl], s1 = a.hit_off[tl + 1];
@@ -855,9 +904,9 @@ int pf_launch_probe_extend(const PfArgs &a, uint32_t ntl, int which, cudaStream_
 {
 	if (ntl == 0)
 		return 0;
-	auto small = pf_probe_extend_kernel<0, kBmSmallBits, 2048, 256>;
-	auto large = pf_probe_extend_kernel<kBmSmallBits, kBmLargeBits, 4096, 512>;
-	const size_t smem_s = bm_smem_bytes(kBmSmallBits, 2048), smem_l = bm_smem_bytes(kBmLargeBits, 4096);
+	auto small = pf_probe_extend_kernel<0, kBmSmallBits, kBmSmallQueue, 256>;
+	auto large = pf_probe_extend_kernel<kBmSmallBits, kBmLargeBits, kBmLargeQueue, 1024>;
+	const size_t smem_s = bm_smem_bytes(kBmSmallBits, kBmSmallQueue), smem_l = bm_smem_bytes(kBmLargeBits, kBmLargeQueue);
 	static bool configured = false;
 	if (!configured) {
 		if (cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess ||
@@ -871,7 +920,7 @@ int pf_launch_probe_extend(const PfArgs &a, uint32_t ntl, int which, cudaStream_
 		++n;
 	}
 	if (which & 2) {
-		large<<<ntl, 512, smem_l, st>>>(a);
+		large<<<ntl, 1024, smem_l, st>>>(a);
 		++n;
 	}
 	return cudaGetLastError() == cudaSuccess ? n : -1;

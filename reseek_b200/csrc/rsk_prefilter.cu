@@ -376,6 +376,8 @@ int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset
 	CK(cudaMemcpyAsync(S.qinfo.p, qinfo.data(), sizeof(uint2) * nQ, cudaMemcpyHostToDevice, st));
 	a.qinfo = S.qinfo.p;
 	a.sum_lenQ = (uint32_t)sumLQ;
+	if (const char *e = getenv("RSK_PF_QUEUE"))
+		a.queue_cap = (uint32_t)atoi(e);
 	// RSK_PF_NOFUSE=1 sends every target through global memory (the parity tests run both paths)
 	const bool nofuse = getenv("RSK_PF_NOFUSE") != nullptr;
 	const unsigned long long bits_small = nofuse ? 0 : pf_fuse_max_bits(0), bits_max = nofuse ? 0 : pf_fuse_max_bits(1);

@@ -49,15 +49,18 @@ def test_prefilter_matches_reference_candidate_tsv(rb, name, kw, monkeypatch):
     ctx.close()
 
 
-@pytest.mark.parametrize("path", ["fused", "global"])
+@pytest.mark.parametrize("path", ["fused", "fused_q16", "fused_q1", "global"])
 @pytest.mark.parametrize("nq,index_mode", [(7, 0), (7, 2), (120, 0)])
 def test_prefilter_scores_match_oracle_on_synthetic(rb, port, nq, index_mode, path, monkeypatch):
     """Planted homologs + random chains, ragged lengths (incl. chains shorter than one 7-window): every (target, query)
     two-hit diagonal score equals the oracle's brute-force restatement; > 100 queries switches the index side.  Both forms of
-    K7/K8: hits kept in shared-memory bitmaps (the default for these sizes) and the global-memory path (sorted keys per target)."""
+    K7/K8: hits kept in shared-memory bitmaps (the default for these sizes; also with a tiny two-hit queue, so that the overflow
+    rounds run) and the global-memory path (sorted keys per target)."""
     from reseek_b200 import synth
     if path == "global":
         monkeypatch.setenv("RSK_PF_NOFUSE", "1")
+    elif path.startswith("fused_q"):  # a two-hit queue of 16 / 1 entries: the overflow rounds over the bitmap do the work
+        monkeypatch.setenv("RSK_PF_QUEUE", path[7:])
     q = synth.make_chains(nq, [5, 7, 60, 150, 300, 420, 33][:min(nq, 7)] + [90] * max(0, nq - 7), seed=501)
     t = synth.make_chains(60, 140, seed=502, length_jitter=0.7)
     synth.plant_homologs(t, q, 0.5, seed=503, sub=0.25, indel=0.03)
