@@ -59,8 +59,18 @@ def search_fast_db_sharded(ctx, Q, T_local, t_lo, dist=None, index_mode=0, rsb_s
     post-filter of the candidates that fall into this rank's block, hit gather on rank `dst` (targets re-based to the
     unsharded DB).  Returns (merged candidate list, gathered hits or None, local Results)."""
     from . import lib
-    raw = ctx.prefilter(Q, T_local, index_mode=index_mode, rsb_size=rsb_size, kl_swap=kl_swap, raw_only=True)
+    empty = T_local is None or T_local.n == 0  # more ranks than chains, or one very long chain: this rank has no block
+    if empty:
+        # an empty block still takes part in every collective, with empty arrays (a rank that raised here would leave the
+        # others waiting in all_gather)
+        class _NoTriples:
+            targets = np.zeros(0, np.uint32); queries = np.zeros(0, np.uint32); scores = np.zeros(0, np.uint16)
+        raw = _NoTriples()
+    else:
+        raw = ctx.prefilter(Q, T_local, index_mode=index_mode, rsb_size=rsb_size, kl_swap=kl_swap, raw_only=True)
     merged = merge_prefilter_triples(Q.n, raw, t_lo, dist, rsb_size)
+    if empty:
+        return merged, gather_hits(np.zeros(0, lib.HIT_DTYPE), t_lo, dist, dst=dst, field="b"), None
     local = merged.select(t_lo, t_lo + T_local.n)
     res = ctx.postfilter(Q, T_local, local, keep=lib.KEEP_HITS, want_paths=want_paths)
     hits = gather_hits(res.hits, t_lo, dist, dst=dst, field="b")
@@ -71,7 +81,9 @@ def gather_hits(local_hits, offset, dist=None, dst=0, field="a"):
     """Gather the per-rank hit records (numpy structured arrays, HIT_DTYPE) on rank `dst`.
     `offset` is added to the local indices of the sharded side (`field`: "a" for RunQuery-style searches where the
     streamed -db side is A, "b" for the -fast -db post-filter) so that they refer to the unsharded DB.  Works with any
-    backend (gloo on CPU in the tests, NCCL on GPUs: the payload travels as a uint8 tensor)."""
+    backend (gloo on CPU in the tests, NCCL on GPUs: the payload travels as a uint8 tensor).  The gathered records carry NO
+    paths: `path_off` still points into the path pool of the rank that produced the record, so alignments have to be printed
+    from the local Results (or use Context.search_*_sharded, whose gather ships the path bytes and re-bases the offsets)."""
     import torch
     hits = np.array(local_hits, copy=True)
     if len(hits):
