@@ -51,7 +51,15 @@ __host__ __device__ constexpr int planes_of_R(int R) { return R > 8 ? 3 : 2; }
 // after the planes: 16 bytes for the task broadcast, then the warps' column-chain lists (kSwMaxWarps x kSwChain x 24 B)
 __host__ __device__ constexpr size_t smem_bcast_off(int planes) { return kSmemP0 + (size_t)planes * kPlaneBytes; }
 __host__ __device__ constexpr size_t smem_chains_off(int planes) { return smem_bcast_off(planes) + 16; }
-__host__ __device__ constexpr size_t class_smem(int C) { return smem_chains_off(class_planes(C)) + (size_t)kSwMaxWarps * kSwChain * 24; }
+__host__ __device__ constexpr size_t class_smem_base(int C) { return smem_chains_off(class_planes(C)) + (size_t)kSwMaxWarps * kSwChain * 24; }
+#ifdef RSK_SW_TMA_CKPT
+constexpr int kTmaStageBytes = 3072;  // per-warp staging of one checkpoint (ckpt_words <= 6 float4 per lane)
+// the two-plane classes with 16 warps have shared memory to spare for the staging
+__host__ __device__ constexpr bool tma_class(int planes, int warps) { return planes <= 2 && warps <= 16; }
+#define class_smem(C) (class_smem_base(C) + (tma_class(class_planes(C), kClassWarps[C]) ? (size_t)kClassWarps[C] * kTmaStageBytes : 0))
+#else
+#define class_smem(C) class_smem_base(C)
+#endif
 
 // floats per lane in plane 1 / 2 for n rows living there (rounded up to a vector width)
 __host__ __device__ constexpr int plane_width(int n) { return n <= 0 ? 0 : n == 1 ? 1 : n == 2 ? 2 : 4; }
@@ -168,7 +176,7 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 		const uint32_t row0, const uint32_t LA, const ColChain *chs, const int nch, const int total, const int tmax, const int tmin,
 		const float2 *__restrict__ bnd_in, float2 *__restrict__ bnd_out, float4 *__restrict__ ck, const float open,
 		const float ext, float4 *__restrict__ best, const int strip, const int s_last,
-		unsigned long long *__restrict__ tile)
+		unsigned long long *__restrict__ tile, float4 *stg = nullptr)
 {
 	const int sub = lane & (G - 1);
 	constexpr int W1 = plane_width(R - 4), W2 = plane_width(R - 8);
@@ -213,6 +221,28 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 #pragma unroll
 		for (int w = 2 * R + 3; w < NW4 * 4; ++w)
 			t[w] = 0.0f;
+#ifdef RSK_SW_TMA_CKPT
+		// Experiment (profiles/r2_tma_experiment.md): the checkpoint is staged in shared memory and leaves as ONE bulk copy
+		// (cp.async.bulk shared -> global, the TMA engine) instead of NW4 STG.128 per lane.
+		if (stg) {
+			if (lane == 0)
+				asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the engine has read the previous checkpoint
+			__syncwarp();
+#pragma unroll
+			for (int w = 0; w < NW4; ++w)
+				stg[w * 32 + lane] = make_float4(t[4 * w], t[4 * w + 1], t[4 * w + 2], t[4 * w + 3]);
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			__syncwarp();
+			if (lane == 0) {
+				const uint32_t src = (uint32_t)__cvta_generic_to_shared(stg);
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ck + (size_t)k * NW4 * 32), "r"(src),
+						"r"(NW4 * 512)
+						: "memory");
+				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			}
+			return;
+		}
+#endif
 #pragma unroll
 		for (int w = 0; w < NW4; ++w)
 			ck[((size_t)k * NW4 + w) * 32 + lane] = make_float4(t[4 * w], t[4 * w + 1], t[4 * w + 2], t[4 * w + 3]);
@@ -460,6 +490,14 @@ __device__ __forceinline__ void sw_pass(const unsigned char *smem_p0, const int 
 				step(std::true_type{});
 			}
 		}
+#ifdef RSK_SW_TMA_CKPT
+		if (stg) {  // the checkpoints are read back (generic proxy) by the traceback
+			if (lane == 0)
+				asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+			asm volatile("fence.proxy.async.global;" ::: "memory");
+			__syncwarp();
+		}
+#endif
 	}
 }
 
@@ -684,6 +722,11 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 	uint8_t *stage = a.stage + gw * a.stage_stride;
 	unsigned long long *tile = a.tile + gw * (kStrip * 32);
 	float4 *best = a.best + gw * (kSwChain * 32);
+	float4 *stg = nullptr;
+#ifdef RSK_SW_TMA_CKPT
+	if (tma_class(planes_of_R(R), W))
+		stg = reinterpret_cast<float4 *>(smem + smem_chains_off(planes_of_R(R)) + (size_t)kSwMaxWarps * kSwChain * 24) + (size_t)warp * (kTmaStageBytes / 16);
+#endif
 
 	for (int pass = 0; pass < npass; ++pass) {
 		__syncthreads();  // every warp is done with the previous row table
@@ -692,7 +735,8 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 		if (have)
 			sw_pass<R, TR, false, G>(smem_p0, lane, pass == 0, pass == npass - 1, (uint32_t)pass * G * R + (uint32_t)(lane & (G - 1)) * R, LA,
 					mychs, mynch, mytot, tmax, tmin, bnd + (size_t)(pass > 0 ? pass - 1 : 0) * a.bnd_pass_stride,
-					bnd + (size_t)pass * a.bnd_pass_stride, ck + (size_t)pass * nstrips * ckpt_words(R) * 32, a.open, a.ext, best, 0, 0, nullptr);
+					bnd + (size_t)pass * a.bnd_pass_stride, ck + (size_t)pass * nstrips * ckpt_words(R) * 32, a.open, a.ext, best, 0, 0, nullptr,
+					stg);
 	}
 	// per chain: first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j.
 	// Chain k of every wavefront is reduced at once (inside its half-warp), then broadcast to the whole warp, which walks the
