@@ -325,11 +325,16 @@ def roofline_block(B, db_lens, q_lens, sw_ms_step, sw_launches_step, dev_ms_step
     sw_ms_launch = sw_ms_step / sw_launches_step
     achieved = alg_bytes / (sw_ms_launch * 1e-3) / 1e9
     smem_peak = 148 * 128 * clocks["sm_mhz"] * 1e6 / 1e9 if clocks and clocks.get("sm_mhz") else None  # GB/s: 128 B/clk/SM
+    # measured DRAM bytes of the kernel (ncu dram__bytes_read + write, profiles/sw_kernel_traffic.json): per cell for the chain
+    # length that was captured, scaled to this leg's launch size; null for lengths without a capture
     traffic = None
     tf = ROOT / "profiles" / "sw_kernel_traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch_at_bench_shape")
+            per_cell = json.loads(tf.read_text()).get("dram_bytes_per_cell_by_chain_length", {})
+            key = str(int(round(float(np.mean(q_lens)))))
+            if key in per_cell:
+                traffic = float(per_cell[key]) * cells_rank / sw_launches_step
         except Exception:
             traffic = None
     smem_ach = 32.0 * cells_rank / (sw_ms_step * 1e-3) / 1e9
