@@ -647,7 +647,7 @@ def main():
     ap.add_argument("--nq", type=int, default=NQ)
     ap.add_argument("--ndb", type=int, default=NDB)
     ap.add_argument("--len", type=int, default=L, dest="length")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--legs", default="sensitive,c5_L100,c5_L800,c4_strong,fastdb_sharded,c3",
                     help="comma list of the extra legs to run ('' = headline only)")
