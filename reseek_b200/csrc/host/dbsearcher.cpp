@@ -279,8 +279,10 @@ void DBSearcher::RunSelf()
 		}
 	else
 		{
-		Check(rsk_search_self(C, m_DBSet, &O, &Res));
-		Phase("RunSelf: rsk_search_self", tp);
+		// one GPU: the sharded entry with no communicator - hits are compacted on the device and only they cross PCIe
+		// (rsk_search_self reads every pair record back: 4 GB for SCOP40's 6.3e7 pairs)
+		Check(rsk_search_self_sharded(C, 0, m_DBSet, &O, 0, &Res));
+		Phase("RunSelf: rsk_search_self_sharded (one rank)", tp);
 		AddStats();
 		}
 	const uint64_t N = rsk_results_count(Res);

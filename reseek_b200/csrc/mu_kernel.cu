@@ -532,6 +532,67 @@ __global__ void __launch_bounds__(256) compact_survivors_kernel(const CompactArg
 	}
 }
 
+// The same for explicit pair lists (PostMuFilter, RunSelf): one CTA per run of pairs with the same row chain (slots
+// [begin, begin + cnt) of the batch, column chains in a.clist, longest first); the survivors are compacted inside the run's own
+// slot range and cut into SW tasks of up to W pairs.  With this the host never reads the keep flags: the batch's kernels are
+// queued without a round trip (the host used to wait for the Mu filter, build the task lists and upload them).
+__global__ void __launch_bounds__(256) compact_explicit_kernel(const CompactArgs a)
+{
+	__shared__ uint32_t s_warp[8];
+	__shared__ uint32_t s_taskbase;
+	const uint32_t ridx = blockIdx.x;
+	const uint32_t rowchain = a.run_row[ridx], begin = a.run_begin[ridx], cnt = a.run_cnt[ridx];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	uint32_t running = 0;
+	unsigned long long lsum = 0;
+	for (uint32_t k0 = 0; k0 < cnt; k0 += 256) {
+		const uint32_t k = k0 + tid;
+		uint32_t c = 0, keep = 0;
+		if (k < cnt) {
+			c = a.clist[begin + k];
+			keep = a.keep[begin + k];
+			if (keep)
+				lsum += a.len_col[c];
+		}
+		const unsigned m = __ballot_sync(kFull, keep != 0);
+		if (lane == 0)
+			s_warp[warp] = __popc(m);
+		__syncthreads();
+		uint32_t before = 0, tot = 0;
+		for (int w = 0; w < 8; ++w) {
+			if (w < warp)
+				before += s_warp[w];
+			tot += s_warp[w];
+		}
+		if (keep) {
+			const uint32_t pos = begin + running + before + __popc(m & ((1u << lane) - 1u));
+			a.out_clist[pos] = c;
+			a.out_cslot[pos] = begin + k;
+		}
+		running += tot;
+		__syncthreads();
+	}
+	const int cls = sw_class_of_len(a.len_row[rowchain]);
+	const uint32_t W = (uint32_t)sw_class_warps(cls) * kSwChain;  // column chains per SW task
+	const uint32_t ntask = (running + W - 1) / W;
+#pragma unroll
+	for (int o = 16; o >= 1; o >>= 1)
+		lsum += __shfl_xor_sync(kFull, lsum, o);
+	if (lane == 0 && lsum)
+		atomicAdd(a.cell_count, lsum * (unsigned long long)a.len_row[rowchain]);
+	if (tid == 0) {
+		s_taskbase = ntask ? atomicAdd(a.task_count + cls, ntask) : 0;
+		atomicAdd(a.pair_count, (unsigned long long)running);
+	}
+	__syncthreads();
+	const size_t tb = (size_t)cls * a.task_cap + s_taskbase;
+	for (uint32_t t = tid; t < ntask; t += 256) {
+		a.task_row[tb + t] = rowchain;
+		a.task_begin[tb + t] = begin + t * W;
+		a.task_cnt[tb + t] = min(W, running - t * W);
+	}
+}
+
 }  // namespace
 
 size_t mu_smem_bytes() { return kMuSmemTotal; }
@@ -549,6 +610,14 @@ int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream)
 	if (cudaFuncSetAttribute(mu_sw_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMuSmemTotal) != cudaSuccess)
 		return -1;
 	mu_sw_filter_kernel<<<grid, kSwThreads, kMuSmemTotal, stream>>>(args);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_compact_explicit(const CompactArgs &args, uint32_t nruns, cudaStream_t stream)
+{
+	if (nruns == 0)
+		return 0;
+	compact_explicit_kernel<<<nruns, 256, 0, stream>>>(args);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -626,7 +626,7 @@ struct Batch {
 	// explicit mode: sorted pair range [k0,k1)
 	size_t k0 = 0, k1 = 0;
 	size_t npairs = 0;
-	uint32_t ntasks = 0;
+	uint32_t ntasks = 0, nruns = 0, sw_task_cap = 0;
 	uint32_t maxLA = 0, maxLB = 0;
 	uint64_t cells = 0;
 	uint64_t pool_bound = 0;
@@ -973,7 +973,31 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 	std::vector<uint32_t> e_row[kSwClasses], e_begin[kSwClasses], e_cnt[kSwClasses];
 	std::vector<uint32_t> e_clist, e_cslot;
 	uint32_t e_off[kSwClasses + 1] = {};
-	if (!b.cross) {
+	const bool dev_tasks = !b.cross && filter && !getenv("RSK_HOST_TASKS");  // SW tasks of explicit lists built on the device
+	if (dev_tasks) {
+		task_cap = b.sw_task_cap;
+		if (ctx->c_blist.ensure(b.npairs) || ctx->c_bslot.ensure(b.npairs) || ctx->c_task_a.ensure((size_t)task_cap * kSwClasses) ||
+			ctx->c_task_begin.ensure((size_t)task_cap * kSwClasses) || ctx->c_task_cnt.ensure((size_t)task_cap * kSwClasses)) {
+			cudaGetLastError();
+			return fail(RSK_ERR_NOMEM, "survivor task buffers for %zu pairs", b.npairs);
+		}
+		CompactArgs ca;
+		memset(&ca, 0, sizeof(ca));
+		ca.run_row = ctx->run_a.p; ca.run_begin = ctx->run_begin.p; ca.run_cnt = ctx->run_cnt.p;
+		ca.clist = ctx->blist.p; ca.keep = ctx->keep.p;
+		ca.len_row = Rw->d.len; ca.len_col = Cl->d.len;
+		ca.out_clist = ctx->c_blist.p; ca.out_cslot = ctx->c_bslot.p;
+		ca.task_row = ctx->c_task_a.p; ca.task_begin = ctx->c_task_begin.p; ca.task_cnt = ctx->c_task_cnt.p;
+		ca.task_cap = task_cap;
+		ca.task_count = ctx->d_counters->task_count;
+		ca.pair_count = &ctx->d_counters->pair_count;
+		ca.cell_count = &ctx->d_counters->cell_count;
+		const int nlc = launch_compact_explicit(ca, b.nruns, st);
+		if (nlc < 0)
+			return fail(RSK_ERR_CUDA, "compaction kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->stats.kernel_launches += nlc;
+	}
+	if (!b.cross && !dev_tasks) {
 		std::vector<uint8_t> keep;
 		const double tk0 = now_ms();
 		if (filter) {
@@ -1056,8 +1080,8 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 			sc.clist = tr ? ctx->colsort.p : ctx->blist.p;
 			sc.ntasks = nrows * sc.nseg;
 			g = (int)std::min<uint64_t>((uint64_t)grid, sc.ntasks);
-		} else if (b.cross) {
-			if (row_off[c + 1] == row_off[c])
+		} else if (b.cross || dev_tasks) {
+			if (b.cross && row_off[c + 1] == row_off[c])
 				continue;  // no row chain of this class: its task list stays empty
 			sc.cross = 0;
 			sc.task_row = ctx->c_task_a.p + (size_t)c * task_cap;
@@ -1120,7 +1144,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		ctx->stats.sw_cells += b.cells;
 	}
 	ctx->batch_filtered = filter;
-	ctx->batch_cross = b.cross;
+	ctx->batch_cross = b.cross || dev_tasks;  // SW pair/cell counts come from the device counters
 	return RSK_OK;
 }
 
@@ -1185,7 +1209,7 @@ int upload_explicit_tasks(rsk_ctx *ctx, const SearchPlan &plan, Batch &b)
 {
 	cudaStream_t st = ctx->stream;
 	rsk_stats &S = ctx->stats;
-	static thread_local std::vector<uint32_t> t_a, t_begin, t_cnt, slots;
+	static thread_local std::vector<uint32_t> t_a, t_begin, t_cnt, slots, r_a, r_begin, r_cnt;
 	// (cudaMemcpyAsync from pageable memory returns once the source has been staged, so the vectors can be reused per batch)
 	const size_t task_cols = (std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32")) ? (size_t)kMuTaskCols : (size_t)kSwWarps;
 	t_a.clear(); t_begin.clear(); t_cnt.clear();
@@ -1204,6 +1228,25 @@ int upload_explicit_tasks(rsk_ctx *ctx, const SearchPlan &plan, Batch &b)
 		k = e;
 	}
 	b.ntasks = (uint32_t)t_a.size();
+	// runs of the same row chain (the Mu tasks above are pieces of them): what compact_explicit_kernel cuts into SW tasks
+	r_a.clear(); r_begin.clear(); r_cnt.clear();
+	uint64_t sw_tasks_max = 0;
+	for (size_t t = 0; t < t_a.size();) {
+		size_t e = t;
+		uint32_t cnt = 0;
+		while (e < t_a.size() && t_a[e] == t_a[t] && t_begin[e] == t_begin[t] + cnt)
+			cnt += t_cnt[e++];
+		r_a.push_back(t_a[t]); r_begin.push_back(t_begin[t]); r_cnt.push_back(cnt);
+		sw_tasks_max += cnt / (16 * kSwChain) + 1;  // a task holds W * kSwChain >= 16 * kSwChain column chains
+		t = e;
+	}
+	b.nruns = (uint32_t)r_a.size();
+	b.sw_task_cap = (uint32_t)std::min<uint64_t>(sw_tasks_max, 0xffffffffull / kSwClasses);
+	if (ctx->run_a.ensure(b.nruns) || ctx->run_begin.ensure(b.nruns) || ctx->run_cnt.ensure(b.nruns))
+		return fail(RSK_ERR_NOMEM, "task buffers");
+	CK(cudaMemcpyAsync(ctx->run_a.p, r_a.data(), 4 * (size_t)b.nruns, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->run_begin.p, r_begin.data(), 4 * (size_t)b.nruns, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->run_cnt.p, r_cnt.data(), 4 * (size_t)b.nruns, cudaMemcpyHostToDevice, st));
 	if (ctx->blist.ensure(n) || ctx->bslot.ensure(n) || ctx->pair_a.ensure(n) || ctx->pair_b.ensure(n) ||
 		ctx->task_a.ensure(b.ntasks) || ctx->task_begin.ensure(b.ntasks) || ctx->task_cnt.ensure(b.ntasks)) {
 		return fail(RSK_ERR_NOMEM, "task buffers");
@@ -1215,7 +1258,7 @@ int upload_explicit_tasks(rsk_ctx *ctx, const SearchPlan &plan, Batch &b)
 	CK(cudaMemcpyAsync(ctx->task_a.p, t_a.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
 	CK(cudaMemcpyAsync(ctx->task_begin.p, t_begin.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
 	CK(cudaMemcpyAsync(ctx->task_cnt.p, t_cnt.data(), 4 * (size_t)b.ntasks, cudaMemcpyHostToDevice, st));
-	S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks;
+	S.h2d_bytes += 16 * n + 12 * (uint64_t)b.ntasks + 12 * (uint64_t)b.nruns;
 	return RSK_OK;
 }
 

@@ -143,6 +143,7 @@ struct rsk_ctx {
 	DevBuf<PairRec> rec;
 	DevBuf<uint8_t> pool;
 	DevBuf<uint32_t> blist, bslot, task_a, task_begin, task_cnt, pair_a, pair_b;
+	DevBuf<uint32_t> run_a, run_begin, run_cnt;  // explicit pair lists: runs of the same row chain
 	// Mu filter (K3) state
 	int *d_mu_mx = nullptr;                 // IntScoreMx_Mu widened to int32
 	float *d_mu_f32 = nullptr;              // ScoreMx_Mu

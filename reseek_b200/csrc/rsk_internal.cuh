@@ -216,6 +216,7 @@ struct MuArgs {
 struct CompactArgs {
 	uint32_t tr, a_begin, nB;
 	const uint32_t *rowlist; uint32_t ncols;
+	const uint32_t *run_row, *run_begin, *run_cnt;  // explicit pair lists: runs of pairs with the same row chain (compact_explicit_kernel)
 	const uint32_t *clist;
 	const uint8_t *keep;
 	const uint32_t *len_row; const uint32_t *len_col;
@@ -377,6 +378,7 @@ int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);
 int launch_mu_filter16(const MuArgs &args, int grid, cudaStream_t stream);
 size_t mu_smem_bytes();
 int launch_compact_survivors(const CompactArgs &args, uint32_t nrows, cudaStream_t stream);
+int launch_compact_explicit(const CompactArgs &args, uint32_t nruns, cudaStream_t stream);
 int launch_pack_profiles(const uint8_t *planes, uint64_t total, uint64_t *prof8, cudaStream_t stream);
 
 }  // namespace rsk
