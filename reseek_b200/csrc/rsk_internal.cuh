@@ -73,7 +73,10 @@ constexpr int kMuTaskCols = 2 * kSwWarps;     // column chains per task of the p
 constexpr uint32_t kMu16MaxLen = 8000;       // 4*L must stay below 2^15 for the 16-bit lanes
 constexpr int kMaxRowsPerLane = 12;          // R: DP rows owned by one lane within a pass
 constexpr int kRowsPerPassMax = 32 * kMaxRowsPerLane;
-constexpr int kSwStripSteps = 16;            // wavefront steps between two checkpoints of the forward sweep
+#ifndef RSK_SW_STRIP
+#define RSK_SW_STRIP 16
+#endif
+constexpr int kSwStripSteps = RSK_SW_STRIP;  // wavefront steps between two checkpoints of the forward sweep (multiple of 4; A/B: 8, 32)
 #ifndef RSK_SW_CHAIN
 #define RSK_SW_CHAIN 4
 #endif

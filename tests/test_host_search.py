@@ -124,6 +124,25 @@ def test_search_fast_db_matches_reference_binary(built_lib, tmp_path):
 
 
 @pytest.mark.gpu
+def test_reseek_command_lines_on_two_gpus_match_reference_binary(built_lib, tmp_path):
+    """`-gpus 2` (DBSearcher::m_GpuCount: rsk_comm_create_all, rows / DB blocks sharded, hits gathered over NCCL) through the
+    reference's own command lines: the sorted output equals the reference binary's, as on one GPU."""
+    import reseek_b200 as rb
+    if rb.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2); the one-GPU forms of the same commands run above")
+    g6, g21 = golden_bca(tmp_path)
+    out = tmp_path / "out.tsv"
+    for args, golden in (
+            (["-search", g21, "-fast"], "golden_search_self_fast.tsv"),
+            (["-search", g21, "-sensitive"], "golden_search_self_sensitive.tsv"),
+            (["-search", g6, "-db", g21, "-sensitive"], "golden_search_db_sensitive.tsv"),
+            (["-search", g6, "-db", g21, "-fast"], "golden_search_fastdb.tsv")):
+        r = _run(*args, "-gpus", 2, "-output", out, "-columns", SEARCH_COLUMNS)
+        assert r.returncode == 0, r.stderr
+        assert sorted(out.read_text().splitlines()) == _golden(golden), " ".join(map(str, args))
+
+
+@pytest.mark.gpu
 def test_selfsearch_aln_fasta2_and_row_columns_match_reference_binary(built_lib, tmp_path):
     """-aln, -fasta2 and the row columns (qrow, trow, qrowg, trowg, muscore, ...) of a whole `-search X -sensitive` run:
     identical to the reference binary's files (tools/make_golden_aln.py), hits in canonical order."""
