@@ -162,6 +162,107 @@ void DBSearcher::BaseOnAln(DSSAligner &DA, bool Up)
 	m_Lock.unlock();
 	}
 
+void DBSearcher::BaseOnAlnLine(DSSAligner &DA, bool Up, const char *Line, size_t n)
+	{
+	if (Reject(DA, Up))
+		return;
+	m_Lock.lock();
+	++m_HitCount;
+	DSSAligner::WriteTsvLine(m_fTsv, Line, n);
+	DA.m_RowLen = m_RowLen;
+	DA.ToAln(m_fAln, Up);
+	DA.ToFasta2(m_fFasta2, m_Unaligned, Up);
+	OnAln(DA, Up);
+	m_Lock.unlock();
+	}
+
+// The hits of one result block through BaseOnAln (dbsearcher.cpp:267-278), A = BlockA[hit.a] (the streamed block) or the DB chain
+// hit.a (RunSelf).  Formatting a TSV line (rsk_format_tsv: a dozen number conversions + the CIGAR) is the expensive part of
+// the replay - 1.3 s for the 1.85e6 lines of the SCOP40 all-vs-all - and independent per hit, so slices of the block are
+// formatted on host threads, each with its own DSSAligner view; the calling thread then walks the block in order.
+void DBSearcher::EmitHits(const rsk_hit *Hits, uint64_t N, const char *Pool, const vector<ChainData> *BlockA, bool BothDirections)
+	{
+	DSSAligner &DA = *m_DAs[0];
+	auto Load = [&](DSSAligner &D, const rsk_hit &H) -> bool
+		{
+		if (BothDirections && DSSAligner::m_NoSelf && H.a == H.b)
+			return false;   // runself.cpp:39-40
+		D.FromHit(H, Pool, BlockA ? (*BlockA)[H.a] : GetDBChainData(H.a), GetDBChainData(H.b));
+		return !D.m_Path.empty();
+		};
+	const uint64_t Slice = 1u << 16;
+	const uint T = (uint)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+	vector<string> Text(T);
+	vector<vector<uint32_t> > Len(T);
+	for (uint64_t k0 = 0; k0 < N; k0 += Slice)
+		{
+		const uint64_t k1 = std::min(N, k0 + Slice), n = k1 - k0;
+		const bool Pre = m_fTsv != 0 && n >= 1024;
+		if (Pre)
+			{
+			auto Work = [&](uint t)
+				{
+				DSSAligner W;
+				W.SetParams(*m_Params);
+				string &S = Text[t];
+				vector<uint32_t> &L = Len[t];
+				S.clear();
+				L.clear();
+				for (uint64_t k = k0 + n * t / T; k < k0 + n * (t + 1) / T; ++k)
+					{
+					uint32_t lu = 0, ld = 0;
+					if (Load(W, Hits[k]))
+						{
+						size_t b = S.size();
+						if (BothDirections && !Reject(W, true) && W.FormatTsvColumns(S, true, m_Columns))
+							lu = (uint32_t)(S.size() - b);
+						b = S.size();
+						if ((!BothDirections || Hits[k].a != Hits[k].b) && !Reject(W, false) && W.FormatTsvColumns(S, false, m_Columns))
+							ld = (uint32_t)(S.size() - b);
+						}
+					L.push_back(lu);
+					L.push_back(ld);
+					}
+				};
+			vector<std::thread> Th;
+			for (uint t = 1; t < T; ++t)
+				Th.emplace_back(Work, t);
+			Work(0);
+			for (std::thread &t : Th)
+				t.join();
+			}
+		for (uint t = 0; t < (Pre ? T : 1u); ++t)
+			{
+			const uint64_t a = Pre ? k0 + n * t / T : k0, b = Pre ? k0 + n * (t + 1) / T : k1;
+			const char *p = Pre ? Text[t].data() : 0;
+			for (uint64_t k = a; k < b; ++k)
+				{
+				const rsk_hit &H = Hits[k];
+				const uint32_t lu = Pre ? Len[t][2 * (k - a)] : 0, ld = Pre ? Len[t][2 * (k - a) + 1] : 0;
+				if (Load(DA, H))
+					{
+					if (Pre)
+						{
+						if (BothDirections)
+							BaseOnAlnLine(DA, true, p, lu);
+						if (!BothDirections || H.a != H.b)
+							BaseOnAlnLine(DA, false, p + lu, ld);
+						}
+					else
+						{
+						if (BothDirections)
+							BaseOnAln(DA, true);
+						if (!BothDirections || H.a != H.b)
+							BaseOnAln(DA, false);
+						}
+					}
+				if (Pre)
+					p += lu + ld;
+				}
+			}
+		}
+	}
+
 // runself.cpp:48-57 (-global): the same pairs through AlignQueryTarget_Global, emitted when the global path is not empty
 // (i.e. unless the Mu filter rejected the pair).  Rows of the pair triangle go to the GPU in chunks of about a million pairs.
 void DBSearcher::RunSelfGlobal()
@@ -288,18 +389,7 @@ void DBSearcher::RunSelf()
 	const uint64_t N = rsk_results_count(Res);
 	const rsk_hit *Hits = rsk_results_hits(Res);
 	const char *Pool = rsk_results_paths(Res);
-	for (uint64_t k = 0; k < N; ++k)
-		{
-		const rsk_hit &H = Hits[k];
-		if (DSSAligner::m_NoSelf && H.a == H.b)
-			continue;   // runself.cpp:39-40
-		DA.FromHit(H, Pool, GetDBChainData(H.a), GetDBChainData(H.b));
-		if (DA.m_Path.empty())
-			continue;
-		BaseOnAln(DA, true);
-		if (H.a != H.b)
-			BaseOnAln(DA, false);
-		}
+	EmitHits(Hits, N, Pool, 0, true);
 	Phase("RunSelf: BaseOnAln over the hits", tp);
 	rsk_results_free(Res);
 	m_ProcessedQueryCount = GetDBChainCount();
@@ -318,7 +408,6 @@ void DBSearcher::RunQueryBlock(const vector<ChainData> &Block)
 		RunQueryBlockSharded(Block);
 		return;
 		}
-	DSSAligner &DA = *m_DAs[0];
 	rsk_ctx *C = GetContext();
 	rsk_search_opts O;
 	memset(&O, 0, sizeof(O));
@@ -332,13 +421,7 @@ void DBSearcher::RunQueryBlock(const vector<ChainData> &Block)
 	const uint64_t N = rsk_results_count(Res);
 	const rsk_hit *Hits = rsk_results_hits(Res);
 	const char *Pool = rsk_results_paths(Res);
-	for (uint64_t k = 0; k < N; ++k)
-		{
-		const rsk_hit &H = Hits[k];
-		DA.FromHit(H, Pool, Block[H.a], GetDBChainData(H.b));
-		if (!DA.m_Path.empty())
-			BaseOnAln(DA, false);
-		}
+	EmitHits(Hits, N, Pool, &Block, false);
 	rsk_results_free(Res);
 	rsk_chainset_free(A);
 	m_ProcessedQueryCount += RSK_SIZE(Block);
@@ -453,17 +536,10 @@ void DBSearcher::RunQueryBlockSharded(const vector<ChainData> &Block)
 		m_ProcessedPairCount += (uint)S.pairs;
 		}
 	m_LastStats = Stats[0];
-	DSSAligner &DA = *m_DAs[0];
 	const uint64_t NH = rsk_results_count(Res);
 	const rsk_hit *Hits = rsk_results_hits(Res);
 	const char *Pool = rsk_results_paths(Res);
-	for (uint64_t k = 0; k < NH; ++k)
-		{
-		const rsk_hit &H = Hits[k];
-		DA.FromHit(H, Pool, Block[H.a], GetDBChainData(H.b));
-		if (!DA.m_Path.empty())
-			BaseOnAln(DA, false);
-		}
+	EmitHits(Hits, NH, Pool, &Block, false);
 	rsk_results_free(Res);
 	m_ProcessedQueryCount += NB;
 	}

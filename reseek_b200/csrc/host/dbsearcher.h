@@ -96,6 +96,11 @@ public:
 public:
 	virtual void OnSetup() {}
 	void BaseOnAln(DSSAligner &DA, bool Up);
+	// BaseOnAln with the TSV line already formatted (Line/n; n = 0: nothing to print).  EmitHits replays the hits of a result block
+	// through it: the lines of a block are formatted on the host threads first, then every hit goes through Reject / the
+	// writers / OnAln on the calling thread, in result order, with `DA` holding the hit as in BaseOnAln.
+	void BaseOnAlnLine(DSSAligner &DA, bool Up, const char *Line, size_t n);
+	void EmitHits(const rsk_hit *Hits, uint64_t N, const char *Pool, const vector<ChainData> *BlockA, bool BothDirections);
 	virtual void OnAln(DSSAligner &DA, bool Up) {}
 
 // shim plumbing

@@ -501,12 +501,10 @@ void DSSAligner::GetHitView(rsk_hit &H, rsk_hit_view &V) const
 	V.len_b = m_ChainB->GetSeqLength();
 	}
 
-void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
+bool DSSAligner::FormatTsvColumns(std::string &Out, bool Up, const char *Columns) const
 	{
-	if (f == 0)
-		return;
 	if (m_NoSelf && m_ChainA->m_Label == m_ChainB->m_Label)
-		return;
+		return false;
 	rsk_hit H;
 	rsk_hit_view V;
 	GetHitView(H, V);
@@ -516,10 +514,28 @@ void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
 	int n = rsk_format_tsv(&V, Up ? 1 : 0, Columns, Buf.data(), Buf.size());
 	if (n < 0)
 		Die("reseek_b200: %s", rsk_last_error());
+	Out.append(Buf.data(), (size_t)n);
+	Out.push_back('\n');
+	return true;
+	}
+
+void DSSAligner::WriteTsvLine(FILE *f, const char *Line, size_t n)
+	{
+	if (f == 0 || n == 0)
+		return;
 	m_OutputLock.lock();  // dssaligner.cpp:1022
-	fwrite(Buf.data(), 1, (size_t)n, f);
-	fputc('\n', f);
+	fwrite(Line, 1, n, f);
 	m_OutputLock.unlock();
+	}
+
+void DSSAligner::ToTsvColumns(FILE *f, bool Up, const char *Columns)
+	{
+	if (f == 0)
+		return;
+	static thread_local std::string Line;
+	Line.clear();
+	if (FormatTsvColumns(Line, Up, Columns))
+		WriteTsvLine(f, Line.data(), Line.size());
 	}
 
 // dssaligner.cpp:965-979 (PrettyAln) and :981-1014; the text itself comes from the C ABI

@@ -117,6 +117,9 @@ public:
 // Up is false if alignment is Query=B, Target=A
 	void ToTsv(FILE *f, bool Up);
 	void ToTsvColumns(FILE *f, bool Up, const char *Columns);  // -columns a+b+c (userfieldnames.h)
+	// the same line (with its newline) appended to Out instead of written; false if the reference would print nothing
+	bool FormatTsvColumns(std::string &Out, bool Up, const char *Columns) const;
+	static void WriteTsvLine(FILE *f, const char *Line, size_t n);  // under the output lock (dssaligner.cpp:1022)
 	void ToAln(FILE *f, bool Up) const;                         // -aln (dssaligner.cpp:965-979)
 	void ToFasta2(FILE *f, bool Global, bool Up) const;         // -fasta2 [-unaligned] (dssaligner.cpp:981-1014)
 	float GetMuScore() const { return m_MuFwdMinusRevScore; }

@@ -70,7 +70,8 @@ def test_runself_matches_cabi(built_lib, tmp_path, mode):
     got = (tmp_path / "self.tsv").read_text().splitlines()
     ctx = rb.Context(0, {"fast": 1, "sensitive": 2, "verysensitive": 3}[mode])
     S = ctx.upload(db.lens, db.prof, db.mu, db.xyz, db.selfrev)
-    res = ctx.search_self(S, keep=rb.KEEP_HITS, want_paths=True)
+    # DBSearcher::RunSelf goes through the sharded entry (hits compacted on the device, returned in (a, b) order), also on one GPU
+    res = ctx.search_self_sharded(None, S, keep=rb.KEEP_HITS, want_paths=True)
     seqs = _seqs(db, sd)
     want = []
     for k, h in enumerate(res.hits):
