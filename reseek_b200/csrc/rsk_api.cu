@@ -341,6 +341,9 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->h_rec[0].release(); ctx->h_rec[1].release(); ctx->h_pool[0].release(); ctx->h_pool[1].release();
 	ctx->keep.release(); ctx->mu_bnd.release(); ctx->c_blist.release(); ctx->c_bslot.release();
 	ctx->c_task_a.release(); ctx->c_task_begin.release(); ctx->c_task_cnt.release(); ctx->rowlist.release(); ctx->colsort.release();
+	ctx->run_a.release(); ctx->run_begin.release(); ctx->run_cnt.release();
+	ctx->gl_a.release(); ctx->gl_b.release(); ctx->gl_order.release(); ctx->gl_cnt.release(); ctx->gl_skip.release(); ctx->gl_tb.release();
+	ctx->gl_poff.release(); ctx->gl_pool.release(); ctx->gl_rec.release(); ctx->gl_bnd.release();
 	ctx->mk_a.release(); ctx->mk_b.release(); ctx->mk_slot.release(); ctx->mk_hash.release(); ctx->mk_hchain.release();
 	ctx->mk_off.release(); ctx->mk_work.release(); ctx->mk_cnt.release(); ctx->mk_ht.release(); ctx->mk_seed.release(); ctx->mk_x.release(); ctx->mk_scratch.release();
 	if (ctx->d_mu_mx) cudaFree(ctx->d_mu_mx);
@@ -2611,33 +2614,28 @@ extern "C" int rsk_align_global(rsk_ctx *ctx, const rsk_chainset *A, const rsk_c
 	const size_t tb_stride = (global_tb_bytes(maxLA, maxLB) + 15) & ~(size_t)15;
 	const uint32_t bnd_stride = (maxLB + 1 + 3) & ~3u;
 	const int wpb = global_warps_per_block();
-	size_t warps = std::min<size_t>((size_t)ctx->num_sms * 4 * wpb, (size_t)npairs);  // 62 registers: four 8-warp CTAs per SM
+	size_t warps = std::min<size_t>((size_t)ctx->num_sms * 2 * wpb, (size_t)npairs);  // 128 registers: two 8-warp CTAs per SM
 	warps = std::min<size_t>(warps, std::max<size_t>(1, ((size_t)8 << 30) / tb_stride));  // at most 8 GB of trace scratch
 	const int blocks = (int)((warps + wpb - 1) / wpb);
 	warps = (size_t)blocks * wpb;
-	uint32_t *d_a = nullptr, *d_b = nullptr, *d_order = nullptr;
-	uint8_t *d_skip = nullptr, *d_tb = nullptr;
-	unsigned long long *d_poff = nullptr;
-	char *d_pool = nullptr;
-	GlobalRec *d_rec = nullptr;
-	float *d_bnd = nullptr;
-	unsigned int *d_cnt = nullptr;
-	auto cleanup = [&]() {
-		cudaFree(d_a); cudaFree(d_b); cudaFree(d_order); cudaFree(d_skip); cudaFree(d_tb); cudaFree(d_poff);
-		cudaFree(d_pool); cudaFree(d_rec); cudaFree(d_bnd); cudaFree(d_cnt);
-	};
-	if (cudaMalloc((void **)&d_a, 4 * npairs) != cudaSuccess || cudaMalloc((void **)&d_b, 4 * npairs) != cudaSuccess ||
-		cudaMalloc((void **)&d_order, 4 * npairs) != cudaSuccess || cudaMalloc((void **)&d_skip, npairs) != cudaSuccess ||
-		cudaMalloc((void **)&d_poff, 8 * npairs) != cudaSuccess || cudaMalloc((void **)&d_pool, pool_bytes + 16) != cudaSuccess ||
-		cudaMalloc((void **)&d_rec, sizeof(GlobalRec) * npairs) != cudaSuccess ||
-		cudaMalloc((void **)&d_tb, tb_stride * warps) != cudaSuccess ||
-		cudaMalloc((void **)&d_bnd, sizeof(float) * 2 * bnd_stride * warps) != cudaSuccess ||
-		cudaMalloc((void **)&d_cnt, sizeof(unsigned int)) != cudaSuccess) {
+	// device buffers live in the context and are reused by the next call (the trace scratch alone is up to 8 GB: allocating and
+	// freeing it per call cost more than the kernel for batches of a few hundred thousand pairs)
+	if (ctx->gl_a.ensure(npairs) || ctx->gl_b.ensure(npairs) || ctx->gl_order.ensure(npairs) || ctx->gl_skip.ensure(npairs) ||
+		ctx->gl_poff.ensure(npairs) || ctx->gl_pool.ensure(pool_bytes + 16) || ctx->gl_rec.ensure(npairs) ||
+		ctx->gl_tb.ensure(tb_stride * warps) || ctx->gl_bnd.ensure((size_t)2 * bnd_stride * warps) || ctx->gl_cnt.ensure(1)) {
 		cudaGetLastError();
-		cleanup();
+		ctx->gl_tb.release();
 		delete res;
 		return fail(RSK_ERR_NOMEM, "rsk_align_global: device buffers (%zu warps x %zu trace bytes)", warps, tb_stride);
 	}
+	uint32_t *d_a = ctx->gl_a.p, *d_b = ctx->gl_b.p, *d_order = ctx->gl_order.p;
+	uint8_t *d_skip = ctx->gl_skip.p, *d_tb = ctx->gl_tb.p;
+	unsigned long long *d_poff = ctx->gl_poff.p;
+	char *d_pool = ctx->gl_pool.p;
+	GlobalRec *d_rec = ctx->gl_rec.p;
+	float *d_bnd = ctx->gl_bnd.p;
+	unsigned int *d_cnt = ctx->gl_cnt.p;
+	auto cleanup = [&]() {};
 	cudaMemcpyAsync(d_a, ia, 4 * npairs, cudaMemcpyHostToDevice, st);
 	cudaMemcpyAsync(d_b, ib, 4 * npairs, cudaMemcpyHostToDevice, st);
 	cudaMemcpyAsync(d_order, order.data(), 4 * npairs, cudaMemcpyHostToDevice, st);
@@ -2657,7 +2655,9 @@ extern "C" int rsk_align_global(rsk_ctx *ctx, const rsk_chainset *A, const rsk_c
 	ga.bnd = d_bnd; ga.bnd_stride = bnd_stride;
 	ga.counter = d_cnt;
 	ga.tables = ctx->d_tables;
+	cudaEventRecord(ctx->ev[0], st);
 	const int nl = launch_global(ga, blocks, st);
+	cudaEventRecord(ctx->ev[1], st);
 	std::vector<GlobalRec> recs(npairs);
 	size_t cap = 0;
 	res->paths = (char *)g_blocks.get(pool_bytes + 16, cap);
@@ -2702,6 +2702,11 @@ extern "C" int rsk_align_global(rsk_ctx *ctx, const rsk_chainset *A, const rsk_c
 	res->npath = pool_bytes;
 	ctx->stats.kernel_launches += nl;
 	ctx->stats.pairs = npairs;
+	{
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess)
+			ctx->stats.sw_kernel_ms = ms;  // the global kernel's device time
+	}
 	*out = res;
 	return RSK_OK;
 }

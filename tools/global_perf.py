@@ -23,7 +23,8 @@ for rep in range(3):
     t0 = time.time()
     res = ctx.align_global(A, A, ia, ib)
     dt = time.time() - t0
-    print(f"rep {rep}: {npairs} pairs, {cells:.3e} cells, wall {dt:.3f}s, {cells / dt:.3e} cells/s (end to end), hits {len(res.hits)}")
+    kms = ctx.stats()["sw_kernel_ms"]
+    print(f"rep {rep}: {npairs} pairs, {cells:.3e} cells, wall {dt:.3f}s, {cells / dt:.3e} cells/s (end to end), kernel {kms:.1f} ms = {cells / (kms * 1e-3):.3e} cells/s, hits {len(res.hits)}")
 
 # CPU side of the same thing: the oracle port (one thread) on a bounded sample of the same pairs
 from oracle.pyoracle import Port  # noqa: E402
