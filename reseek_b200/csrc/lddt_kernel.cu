@@ -19,13 +19,17 @@ namespace rsk {
 namespace {
 
 constexpr int kLddtThreads = 128;
+constexpr uint32_t kLddtScratchCtas = 296;  // CTAs of the global-scratch form (two per SM)
 constexpr unsigned kFull = 0xffffffffu;
 
 __global__ void __launch_bounds__(kLddtThreads) lddt_ts_kernel(const LddtArgs a)
 {
 	extern __shared__ __align__(16) float sm[];
 	const uint32_t mc = a.maxcols;
-	float *xa = sm, *ya = xa + mc, *za = ya + mc, *xb = za + mc, *yb = xb + mc, *zb = yb + mc;
+	// the aligned columns' coordinates and scores: shared memory, or - alignments of more than ~8 000 columns (titin-sized
+	// chains) - this CTA's slice of a global scratch buffer, which L1/L2 serve
+	float *base = a.scratch ? a.scratch + (size_t)blockIdx.x * 7 * mc : sm;
+	float *xa = base, *ya = xa + mc, *za = ya + mc, *xb = za + mc, *yb = xb + mc, *zb = yb + mc;
 	float *colscore = zb + mc;
 	__shared__ uint32_t s_counts[3];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -252,6 +256,10 @@ int launch_lddt(const LddtArgs &args, cudaStream_t stream)
 		lddt_ts_warp_kernel<<<wgrid, kLddtWarps * 32, wsmem, stream>>>(args);
 		return cudaGetLastError() == cudaSuccess ? 1 : -1;
 	}
+	if (args.scratch) {  // lddt_scratch_floats() said the columns do not fit shared memory
+		lddt_ts_kernel<<<std::min<uint32_t>(args.npairs, kLddtScratchCtas), kLddtThreads, 0, stream>>>(args);
+		return cudaGetLastError() == cudaSuccess ? 1 : -1;
+	}
 	const size_t smem = (size_t)args.maxcols * 7 * sizeof(float);
 	if (smem > 48 * 1024) {
 		if (cudaFuncSetAttribute(lddt_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -260,6 +268,12 @@ int launch_lddt(const LddtArgs &args, cudaStream_t stream)
 	const unsigned grid = args.npairs < (1u << 20) ? args.npairs : (1u << 20);
 	lddt_ts_kernel<<<grid, kLddtThreads, smem, stream>>>(args);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// floats of global scratch launch_lddt needs for alignments of up to maxcols columns (0: they fit shared memory)
+size_t lddt_scratch_floats(uint32_t maxcols)
+{
+	return (size_t)maxcols * 7 * sizeof(float) > 220 * 1024 ? (size_t)kLddtScratchCtas * 7 * maxcols : 0;
 }
 
 }  // namespace rsk

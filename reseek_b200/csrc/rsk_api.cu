@@ -341,7 +341,7 @@ extern "C" void rsk_ctx_destroy(rsk_ctx *ctx)
 	ctx->h_rec[0].release(); ctx->h_rec[1].release(); ctx->h_pool[0].release(); ctx->h_pool[1].release();
 	ctx->keep.release(); ctx->mu_bnd.release(); ctx->c_blist.release(); ctx->c_bslot.release();
 	ctx->c_task_a.release(); ctx->c_task_begin.release(); ctx->c_task_cnt.release(); ctx->rowlist.release(); ctx->colsort.release();
-	ctx->run_a.release(); ctx->run_begin.release(); ctx->run_cnt.release();
+	ctx->run_a.release(); ctx->run_begin.release(); ctx->run_cnt.release(); ctx->lddt_scratch.release();
 	ctx->gl_a.release(); ctx->gl_b.release(); ctx->gl_order.release(); ctx->gl_cnt.release(); ctx->gl_skip.release(); ctx->gl_tb.release();
 	ctx->gl_poff.release(); ctx->gl_pool.release(); ctx->gl_rec.release(); ctx->gl_bnd.release();
 	ctx->mk_a.release(); ctx->mk_b.release(); ctx->mk_slot.release(); ctx->mk_hash.release(); ctx->mk_hchain.release();
@@ -1134,8 +1134,11 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		la.pool = ctx->pool.p;
 		la.min_fwd_score = ctx->params.min_fwd_score;
 		la.maxcols = std::max(1u, std::min(b.maxLA, b.maxLB));
-		if ((size_t)la.maxcols * 7 * sizeof(float) > 220 * 1024)
-			return fail(RSK_ERR_LIMIT, "alignment of %u columns exceeds the LDDT kernel's shared-memory limit", la.maxcols);
+		if (const size_t nf = lddt_scratch_floats(la.maxcols)) {
+			if (ctx->lddt_scratch.ensure(nf))
+				return fail(RSK_ERR_NOMEM, "LDDT column buffers for alignments of %u columns", la.maxcols);
+			la.scratch = ctx->lddt_scratch.p;
+		}
 		int nl = launch_lddt(la, st);
 		if (nl < 0)
 			return fail(RSK_ERR_CUDA, "LDDT kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));

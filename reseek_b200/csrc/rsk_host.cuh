@@ -144,6 +144,7 @@ struct rsk_ctx {
 	DevBuf<uint8_t> pool;
 	DevBuf<uint32_t> blist, bslot, task_a, task_begin, task_cnt, pair_a, pair_b;
 	DevBuf<uint32_t> run_a, run_begin, run_cnt;  // explicit pair lists: runs of the same row chain
+	DevBuf<float> lddt_scratch;  // column buffers of the LDDT kernel for alignments that do not fit shared memory
 	// -global (K9): pair lists, records, path pool, per-warp trace matrices and boundary rows; kept between calls
 	DevBuf<uint32_t> gl_a, gl_b, gl_order, gl_cnt;
 	DevBuf<uint8_t> gl_skip, gl_tb;

@@ -191,6 +191,7 @@ struct LddtArgs {
 	const uint8_t *pool;
 	float min_fwd_score;
 	uint32_t maxcols;
+	float *scratch;  // null, or lddt_scratch_floats(maxcols) floats when the columns of an alignment do not fit shared memory
 };
 
 // K3: Mu int8 SW filter; same row/column task model as K1 (16 warps per CTA)
@@ -377,6 +378,7 @@ int launch_sw(const SwArgs &args, int cls, int grid, cudaStream_t stream);
 size_t sw_smem_bytes();
 uint64_t sw_ckpt_units(int npass, uint64_t LB);
 int launch_lddt(const LddtArgs &args, cudaStream_t stream);
+size_t lddt_scratch_floats(uint32_t maxcols);
 int launch_mu_filter(const MuArgs &args, int grid, cudaStream_t stream);
 int launch_mu_filter16(const MuArgs &args, int grid, cudaStream_t stream);
 size_t mu_smem_bytes();

@@ -105,6 +105,29 @@ def test_identical_and_very_long_chains(rb, port):
     ctx.close()
 
 
+def test_alignment_longer_than_the_lddt_shared_memory(rb, port):
+    """A 9 000-residue chain against itself and against a mutated copy: the alignment has more columns than the LDDT kernel's
+    shared-memory buffers hold (~8 000), so the kernel keeps them in global scratch - same records as the oracle (round 1
+    returned RSK_ERR_LIMIT for the whole call)."""
+    from reseek_b200 import synth
+    from tests.util import to_oracle_chains
+    s = synth.make_chains(1, [9000], seed=931)
+    t = synth.make_chains(1, [9000], seed=932)
+    synth.plant_homologs(t, s, 1.0, seed=933, sub=0.1, indel=0.002)
+    for mode in (rb.MODE_VERYSENSITIVE, rb.MODE_FAST):
+        ctx = rb.Context(0, mode)
+        S = ctx.upload(s.lens, s.prof, s.mu, s.xyz, s.selfrev)
+        T = ctx.upload(t.lens, t.prof, t.mu, t.xyz, t.selfrev)
+        z = np.zeros(1, np.uint32)
+        res = ctx.search_pairs(S, S, z, z, keep=rb.KEEP_ALL)
+        assert res.path(0) == "M" * 9000 and float(res.hits[0]["lddt"]) == 1.0
+        _check_all(port(mode), res, to_oracle_chains(s), to_oracle_chains(s))
+        res = ctx.search_pairs(S, T, z, z, keep=rb.KEEP_ALL)
+        assert int(res.hits[0]["ids"]) > 8100, "the alignment covers (nearly) the whole chain"
+        _check_all(port(mode), res, to_oracle_chains(s), to_oracle_chains(t))
+        ctx.close()
+
+
 def test_empty_requests_and_bad_arguments(rb):
     from reseek_b200 import synth
     s = synth.make_chains(4, 30, seed=931)
