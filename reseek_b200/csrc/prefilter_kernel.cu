@@ -329,12 +329,10 @@ __global__ void __launch_bounds__(128) pf_probe_kernel(const PfArgs a)
 // B = max(B, F) - two DPX instructions (VIADDMNMX, VIMNMX).  Four positions per trip: the letters of both chains come as 32-bit
 // words assembled from aligned loads (one new word per chain and trip), the scores from an int8 table in shared memory:
 // per position two byte extracts, one IMAD, one LDS, two DPX (the first form - int table, compare-and-select - ran 16).
-__device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int8_t *S, const uint8_t *T, uint32_t LT, uint32_t tl, uint32_t k)
+// SHARED: the letters of both chains were staged in shared memory (plain loads); otherwise they come from global memory.
+template <bool SHARED>
+__device__ __forceinline__ int walk_core(const int8_t *S, const uint8_t *Q, const uint32_t LQ, const uint8_t *T, const uint32_t LT, const int d)
 {
-	const uint32_t q = k >> 14;
-	const int d = (int)(k & 0x3fffu);
-	const uint32_t LQ = a.lenQ[q];
-	const uint8_t *Q = a.muQ + a.offQ[q];
 	int qi = (int)LQ - d - 1, tj = 0;
 	if (qi < 0) { tj = -qi; qi = 0; }
 	int B = 0, F = 0;
@@ -344,13 +342,13 @@ __device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int8_t *S, 
 		const uint32_t *qw = reinterpret_cast<const uint32_t *>((uintptr_t)qp & ~(uintptr_t)3);
 		const uint32_t *tw = reinterpret_cast<const uint32_t *>((uintptr_t)tp & ~(uintptr_t)3);
 		const unsigned qs = ((uintptr_t)qp & 3u) * 8u, ts = ((uintptr_t)tp & 3u) * 8u;
-		uint32_t q0 = __ldg(qw), t0 = __ldg(tw);
+		uint32_t q0 = SHARED ? *qw : __ldg(qw), t0 = SHARED ? *tw : __ldg(tw);
 		const int groups = n >> 2;
 		for (int g = 0; g < groups; ++g) {
 			// the next aligned word holds at least one letter of this group whenever the chain's pointer is unaligned
 			uint32_t q1 = q0, t1 = t0;
-			if (qs || g + 1 < groups) q1 = __ldg(++qw);
-			if (ts || g + 1 < groups) t1 = __ldg(++tw);
+			if (qs || g + 1 < groups) { ++qw; q1 = SHARED ? *qw : __ldg(qw); }
+			if (ts || g + 1 < groups) { ++tw; t1 = SHARED ? *tw : __ldg(tw); }
 			const uint32_t qv = __funnelshift_r(q0, q1, qs);
 			const uint32_t tv = __funnelshift_r(t0, t1, ts);
 			q0 = q1; t0 = t1;
@@ -368,6 +366,13 @@ __device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int8_t *S, 
 		F = __viaddmax_s32(F, (int)S[36 * qp[i] + tp[i]], 0);
 		B = max(B, F);
 	}
+	return B;
+}
+
+__device__ __forceinline__ void walk_diagonal(const PfArgs &a, const int8_t *S, const uint8_t *T, uint32_t LT, uint32_t tl, uint32_t k)
+{
+	const uint32_t q = k >> 14;
+	int B = walk_core<false>(S, a.muQ + a.offQ[q], a.lenQ[q], T, LT, (int)(k & 0x3fffu));
 	if (B > 0) {
 		if (B >= 65535) B = 65534;  // prefiltermu.cpp:294-295
 		atomicMax(&a.best[(size_t)tl * a.nQ + q], (unsigned)B);
@@ -482,6 +487,153 @@ __global__ void __launch_bounds__(THREADS) pf_probe_extend_kernel(const PfArgs a
 			if (w >= n2)
 				break;
 			walk_diagonal(a, S, T, LT, tl, queue[w]);
+		}
+	}
+}
+
+// The same with the letters in shared memory, for query blocks small enough to stage (<= kStageQBytes residues, <= kStageQMax
+// queries): persistent CTAs pull targets from a counter, the query letters and the per-query (length, offset) pairs are staged
+// once per CTA, the target's letters once per target.  The diagonal walks then read both chains from shared memory - in the
+// unstaged form each lane's letter words were separate uncoalesced L1 requests and kept the L1 data pipe 92 % busy.
+constexpr uint32_t kStageQBytes = 40960, kStageQMax = 1024, kStageTBytes = 4096;
+__host__ __device__ constexpr size_t bm_stage_bytes(uint32_t nq, uint32_t sumq) { return (size_t)nq * 8 + ((sumq + 3) & ~3u) + 8 + kStageTBytes + 8; }
+
+template <uint32_t MAXBITS, uint32_t QUEUE, int THREADS>
+__global__ void __launch_bounds__(THREADS) pf_probe_extend_staged_kernel(const PfArgs a, const uint32_t ntl)
+{
+	extern __shared__ __align__(16) uint32_t bm_smem[];
+	__shared__ int8_t S[36 * 36];
+	__shared__ unsigned s_n, s_next, s_target;
+	uint32_t *queue = bm_smem + MAXBITS / 32 * 2;
+	uint2 *s_qinfo = reinterpret_cast<uint2 *>(queue + QUEUE);
+	uint8_t *sQraw = reinterpret_cast<uint8_t *>(s_qinfo + a.nQ);
+	uint8_t *sT = sQraw + ((a.sum_lenQ + 3) & ~3u) + 8;
+	const unsigned qsh = (unsigned)((uintptr_t)a.muQ & 3u);  // the block's letters are copied from the aligned word at or below them
+	const uint8_t *sQ = sQraw + qsh;
+	for (int k = threadIdx.x; k < 36 * 36; k += blockDim.x)
+		S[k] = (int8_t)a.kmer_mx[k];
+	for (uint32_t k = threadIdx.x; k < a.nQ; k += blockDim.x)
+		s_qinfo[k] = a.qinfo[k];
+	{
+		// chain sets are packed (offsets = prefix sums of the lengths), so the block's letters are one contiguous range
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(a.muQ - qsh);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(sQraw);
+		for (uint32_t k = threadIdx.x; k < (a.sum_lenQ + qsh + 3) / 4; k += blockDim.x)
+			dst[k] = __ldg(src + k);
+	}
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const uint32_t qcap = a.queue_cap ? min(a.queue_cap, QUEUE) : QUEUE;
+	for (;;) {
+		__syncthreads();  // the previous target is done with the bitmaps, the queue and sT
+		if (threadIdx.x == 0)
+			s_target = atomicAdd(a.fuse_counter, 1u);
+		__syncthreads();
+		const uint32_t tl = s_target;
+		if (tl >= ntl)
+			break;
+		const uint32_t t = a.t_begin + tl;
+		const uint32_t LT = a.lenT[t];
+		if (LT < 7)
+			continue;
+		const unsigned long long nbits = (unsigned long long)a.sum_lenQ + (unsigned long long)a.nQ * (LT - 1);
+		if (nbits > MAXBITS || LT > kStageTBytes)
+			continue;  // the other size class, or the global-memory path
+		const uint32_t words = ((uint32_t)nbits + 31) / 32;
+		uint32_t *seen = bm_smem, *twice = bm_smem + words;
+		for (uint32_t k = threadIdx.x; k < 2 * words; k += blockDim.x)
+			bm_smem[k] = 0;
+		{
+			// the target's letters, from the aligned word at or below its first byte
+			const uint8_t *Tg = a.muT + a.offT[t];
+			const unsigned sh = (unsigned)((uintptr_t)Tg & 3u);
+			const uint32_t *src = reinterpret_cast<const uint32_t *>(Tg - sh);
+			uint32_t *dst = reinterpret_cast<uint32_t *>(sT);
+			for (uint32_t k = threadIdx.x; k < (LT + sh + 3) / 4; k += blockDim.x)
+				dst[k] = __ldg(src + k);
+			if (threadIdx.x == 0) { s_n = 0; s_next = 0; }
+			__syncthreads();
+			const uint8_t *T = sT + sh;
+			uint2 r = probe_row(a, T, LT, warp, S);
+			for (uint32_t tpos = warp; tpos + 7 <= LT; tpos += nwarps) {
+				const uint2 rn = probe_row(a, T, LT, tpos + nwarps, S);
+				for (uint32_t e = r.x + lane; e < r.y; e += 32) {
+					const uint32_t v = __ldg(a.ix_val + e);
+					const uint32_t q = v >> 16, qpos = v & 0xffffu;
+					const uint2 qi = s_qinfo[q];  // length, residues of the queries before q
+					const uint32_t diag = qi.x + tpos - qpos - 1;  // diag.h:22-25
+					if (diag > 0x3fffu)
+						continue;  // prefiltermu.cpp:254
+					const uint32_t idx = qi.y + q * (LT - 1) + diag;
+					const uint32_t w = idx >> 5, m = 1u << (idx & 31u);
+					if ((atomicOr(&seen[w], m) & m) && !(atomicOr(&twice[w], m) & m)) {
+						const unsigned slot = atomicAdd(&s_n, 1u);
+						if (slot < qcap)
+							queue[slot] = (q << 14) | diag;
+					}
+				}
+				r = rn;
+			}
+			__syncthreads();
+			auto walk = [&](const uint32_t k) {
+				const uint32_t q = k >> 14;
+				const uint2 qi = s_qinfo[q];
+				int B = walk_core<true>(S, sQ + qi.y, qi.x, T, LT, (int)(k & 0x3fffu));
+				if (B > 0) {
+					if (B >= 65535) B = 65534;  // prefiltermu.cpp:294-295
+					atomicMax(&a.best[(size_t)tl * a.nQ + q], (unsigned)B);
+				}
+			};
+			const unsigned found = s_n;
+			const unsigned n = min(found, qcap);
+			for (;;) {
+				const unsigned w = atomicAdd(&s_next, 1u);
+				if (w >= n)
+					break;
+				const uint32_t k = queue[w];
+				if (found > qcap) {  // leave only the diagonals that missed the queue in `twice`
+					const uint32_t q = k >> 14;
+					const uint32_t idx = s_qinfo[q].y + q * (LT - 1) + (k & 0x3fffu);
+					atomicAnd(&twice[idx >> 5], ~(1u << (idx & 31u)));
+				}
+				walk(k);
+			}
+			if (found <= qcap)
+				continue;
+			// the diagonals that found the queue full: collect them from the bitmap, at most a queue-full per round
+			const uint32_t wstep = max(qcap / 32u, 1u);
+			for (uint32_t w0 = 0; w0 < words; w0 += wstep) {
+				__syncthreads();
+				if (threadIdx.x == 0) { s_n = 0; s_next = 0; }
+				__syncthreads();
+				for (uint32_t w = w0 + threadIdx.x; w < min(words, w0 + wstep); w += blockDim.x) {
+					uint32_t bits = twice[w];
+					while (bits) {
+						const uint32_t idx = w * 32 + (__ffs(bits) - 1);
+						bits &= bits - 1;
+						uint32_t lo = 0, hi = a.nQ - 1;  // the last q with s_qinfo[q].y + q * (LT - 1) <= idx
+						while (lo < hi) {
+							const uint32_t mid = (lo + hi + 1) >> 1;
+							if (s_qinfo[mid].y + mid * (LT - 1) <= idx)
+								lo = mid;
+							else
+								hi = mid - 1;
+						}
+						const uint32_t diag = idx - (s_qinfo[lo].y + lo * (LT - 1));
+						if (qcap >= 32)
+							queue[atomicAdd(&s_n, 1u)] = (lo << 14) | diag;
+						else
+							walk((lo << 14) | diag);
+					}
+				}
+				__syncthreads();
+				const unsigned n2 = s_n;
+				for (;;) {
+					const unsigned w = atomicAdd(&s_next, 1u);
+					if (w >= n2)
+						break;
+					walk(queue[w]);
+				}
+			}
 		}
 	}
 }
@@ -906,17 +1058,33 @@ int pf_launch_probe_extend(const PfArgs &a, uint32_t ntl, int which, cudaStream_
 		return 0;
 	auto small = pf_probe_extend_kernel<0, kBmSmallBits, kBmSmallQueue, 256>;
 	auto large = pf_probe_extend_kernel<kBmSmallBits, kBmLargeBits, kBmLargeQueue, 1024>;
+	auto staged = pf_probe_extend_staged_kernel<kBmSmallBits, kBmSmallQueue, 256>;
 	const size_t smem_s = bm_smem_bytes(kBmSmallBits, kBmSmallQueue), smem_l = bm_smem_bytes(kBmLargeBits, kBmLargeQueue);
+	const size_t smem_st = smem_s + bm_stage_bytes(a.nQ, a.sum_lenQ);
 	static bool configured = false;
 	if (!configured) {
 		if (cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess ||
-			cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess)
+			cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess ||
+			cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				(int)(smem_s + bm_stage_bytes(kStageQMax, kStageQBytes))) != cudaSuccess)
 			return -1;
 		configured = true;
 	}
 	int n = 0;
 	if (which & 1) {
-		small<<<ntl, 256, smem_s, st>>>(a);
+		// small class: letters staged in shared memory when the query block allows it (and the caller gave a target counter);
+		// at least 17 queries bound a small-class target to kStageTBytes residues
+		const bool stage = a.fuse_counter && a.nQ >= 17 && a.nQ <= kStageQMax && a.sum_lenQ <= kStageQBytes && !a.no_stage;
+		if (stage) {
+			int dev = 0, sms = 148;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (size_t)220 * 1024 / (smem_st + 2048)));
+			const unsigned grid = (unsigned)std::min<uint64_t>(ntl, (uint64_t)sms * per_sm);
+			staged<<<grid, 256, smem_st, st>>>(a, ntl);
+		} else {
+			small<<<ntl, 256, smem_s, st>>>(a);
+		}
 		++n;
 	}
 	if (which & 2) {

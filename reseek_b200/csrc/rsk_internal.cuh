@@ -316,6 +316,8 @@ struct PfArgs {
 	uint32_t exact_twice;        // query-neighbourhood mode: the k-mer itself is entered a second time
 	const uint2 *row;            // [36^5] dense row table over the sorted index: (first entry, one past the last)
 	uint32_t queue_cap;          // 0, or a smaller two-hit queue for the fused kernel (tests: RSK_PF_QUEUE)
+	uint32_t *fuse_counter;      // zeroed target counter of the staged fused kernel (persistent CTAs), or null
+	uint32_t no_stage;           // tests: RSK_PF_NOSTAGE keeps the letters in global memory
 	uint32_t diag_safe;          // longest query + longest target <= 16384: no diagonal is dropped (prefiltermu.cpp:254)
 	// target side
 	uint32_t t_begin;            // first target of the batch

@@ -149,6 +149,7 @@ struct PfScratch {
 	DevBuf<uint8_t> muq, tmp;
 	DevBuf<uint32_t> qk_off, qk_code, qk_val, nb_count, key_a, key_b, val_a, val_b;
 	DevBuf<uint2> row, qinfo;
+	DevBuf<uint32_t> fuse_counter;
 	DevBuf<unsigned long long> nb_off, hit_count, hit_off, cand_off;
 	DevBuf<uint32_t> hit_key, hit_sorted, cand_count, cand_t, cand_q;
 	DevBuf<unsigned> best;
@@ -160,7 +161,7 @@ struct PfScratch {
 	~PfScratch()
 	{
 		muq.release(); tmp.release(); qk_off.release(); qk_code.release(); qk_val.release(); nb_count.release();
-		key_a.release(); key_b.release(); val_a.release(); val_b.release(); row.release(); qinfo.release();
+		key_a.release(); key_b.release(); val_a.release(); val_b.release(); row.release(); qinfo.release(); fuse_counter.release();
 		nb_off.release(); hit_count.release(); hit_off.release(); cand_off.release(); hit_key.release();
 		hit_sorted.release(); cand_count.release(); cand_t.release(); cand_q.release(); best.release(); cand_s.release();
 		raw_q.release(); srt_q.release(); bag_n.release(); raw_v.release(); srt_v.release(); seg_begin.release(); seg_end.release();
@@ -378,6 +379,9 @@ int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset
 	a.sum_lenQ = (uint32_t)sumLQ;
 	if (const char *e = getenv("RSK_PF_QUEUE"))
 		a.queue_cap = (uint32_t)atoi(e);
+	a.no_stage = getenv("RSK_PF_NOSTAGE") ? 1u : 0u;
+	NOMEM(S.fuse_counter.ensure(1));
+	a.fuse_counter = S.fuse_counter.p;
 	// RSK_PF_NOFUSE=1 sends every target through global memory (the parity tests run both paths)
 	const bool nofuse = getenv("RSK_PF_NOFUSE") != nullptr;
 	const unsigned long long bits_small = nofuse ? 0 : pf_fuse_max_bits(0), bits_max = nofuse ? 0 : pf_fuse_max_bits(1);
@@ -429,8 +433,10 @@ int prefilter_raw_device(rsk_ctx *ctx, const rsk_chainset *Q, const rsk_chainset
 		a.t_begin = t0;
 		a.best = S.best.p;
 		a.cand_count = S.cand_count.p; a.cand_off = S.cand_off.p;
-		if (which)
+		if (which) {
+			CK(cudaMemsetAsync(S.fuse_counter.p, 0, sizeof(uint32_t), st));
 			PFL(pf_launch_probe_extend(a, ntl, which, st));
+		}
 		tm.mark("K7+K8 in shared memory");
 		if (big) {
 			NOMEM(S.hit_key.ensure(big));

@@ -49,7 +49,7 @@ def test_prefilter_matches_reference_candidate_tsv(rb, name, kw, monkeypatch):
     ctx.close()
 
 
-@pytest.mark.parametrize("path", ["fused", "fused_q16", "fused_q1", "global"])
+@pytest.mark.parametrize("path", ["fused", "fused_q16", "fused_q1", "fused_nostage", "fused_nostage_q16", "global"])
 @pytest.mark.parametrize("nq,index_mode", [(7, 0), (7, 2), (120, 0)])
 def test_prefilter_scores_match_oracle_on_synthetic(rb, port, nq, index_mode, path, monkeypatch):
     """Planted homologs + random chains, ragged lengths (incl. chains shorter than one 7-window): every (target, query)
@@ -61,6 +61,10 @@ def test_prefilter_scores_match_oracle_on_synthetic(rb, port, nq, index_mode, pa
         monkeypatch.setenv("RSK_PF_NOFUSE", "1")
     elif path.startswith("fused_q"):  # a two-hit queue of 16 / 1 entries: the overflow rounds over the bitmap do the work
         monkeypatch.setenv("RSK_PF_QUEUE", path[7:])
+    elif path.startswith("fused_nostage"):  # letters read from global memory (the form for query blocks too large to stage)
+        monkeypatch.setenv("RSK_PF_NOSTAGE", "1")
+        if path.endswith("q16"):
+            monkeypatch.setenv("RSK_PF_QUEUE", "16")
     q = synth.make_chains(nq, [5, 7, 60, 150, 300, 420, 33][:min(nq, 7)] + [90] * max(0, nq - 7), seed=501)
     t = synth.make_chains(60, 140, seed=502, length_jitter=0.7)
     synth.plant_homologs(t, q, 0.5, seed=503, sub=0.25, indel=0.03)
