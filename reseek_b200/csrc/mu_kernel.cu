@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(256) compact_survivors_kernel(const CompactArg
 		__syncthreads();
 	}
 	const int cls = sw_class_of_len(a.len_row[rowchain]);
-	const uint32_t W = (uint32_t)sw_class_warps(cls) * kSwChain;  // column chains per SW task
+	const uint32_t W = (uint32_t)sw_class_warps(cls) * sw_class_chains(cls);  // column chains per SW task
 	const uint32_t ntask = (running + W - 1) / W;
 #pragma unroll
 	for (int o = 16; o >= 1; o >>= 1)
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(256) compact_explicit_kernel(const CompactArgs
 		__syncthreads();
 	}
 	const int cls = sw_class_of_len(a.len_row[rowchain]);
-	const uint32_t W = (uint32_t)sw_class_warps(cls) * kSwChain;  // column chains per SW task
+	const uint32_t W = (uint32_t)sw_class_warps(cls) * sw_class_chains(cls);  // column chains per SW task
 	const uint32_t ntask = (running + W - 1) / W;
 #pragma unroll
 	for (int o = 16; o >= 1; o >>= 1)

@@ -669,20 +669,20 @@ int ensure_scratch(rsk_ctx *ctx, uint32_t maxRow, uint32_t maxCol, int &grid, ui
 	sw_geometry(maxRow, npass, R);
 	// every pair of the batch has npass(rows) <= npass(maxRow) and columns <= maxCol; a warp sweeps up to kSwChain column
 	// chains as one concatenated wavefront
-	const uint64_t cols = (uint64_t)maxCol * kSwChain;
+	const uint64_t cols = (uint64_t)maxCol * kSwChainMax;
 	ckpt_stride = sw_ckpt_units(npass, cols);  // float4 units
 	bnd_pass_stride = (uint32_t)(((cols + 3) & ~(uint64_t)3) + 4);
 	bnd_stride = (uint64_t)bnd_pass_stride * (uint64_t)npass;
 	stage_chain_stride = ((maxRow + maxCol + 16) + 15) & ~15u;
-	stage_stride = stage_chain_stride * kSwChain;
-	const uint64_t per_cta = (ckpt_stride * 16 + bnd_stride * 8 + stage_stride + kSwStripSteps * 32 * 8 + kSwChain * 32 * 16) * kSwMaxWarps;
+	stage_stride = stage_chain_stride * kSwChainMax;
+	const uint64_t per_cta = (ckpt_stride * 16 + bnd_stride * 8 + stage_stride + kSwStripSteps * 32 * 8 + kSwChainMax * 32 * 16) * kSwMaxWarps;
 	grid = ctx->num_sms;
 	if (per_cta * (uint64_t)grid > ctx->scratch_budget)
 		grid = (int)std::max<uint64_t>(1, ctx->scratch_budget / per_cta);
 	const size_t warps = (size_t)grid * kSwMaxWarps;
 	if (ctx->ckpt.ensure(ckpt_stride * warps) || ctx->bnd.ensure((size_t)bnd_stride * warps) ||
 		ctx->tile.ensure((size_t)kSwStripSteps * 32 * warps) || ctx->stage.ensure((size_t)stage_stride * warps) ||
-		ctx->best.ensure((size_t)kSwChain * 32 * warps)) {
+		ctx->best.ensure((size_t)kSwChainMax * 32 * warps)) {
 		cudaGetLastError();
 		return fail(RSK_ERR_NOMEM, "SW scratch allocation failed (rows=%u cols=%u)", maxRow, maxCol);
 	}
@@ -1016,7 +1016,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		while (k < b.npairs) {
 			const uint32_t a0 = plan.sa[b.k0 + k];
 			const int cls = sw_class_of_len(A->hlen[a0]);
-			const uint32_t W = (uint32_t)kClassWarps[cls] * kSwChain;  // column chains per SW task
+			const uint32_t W = (uint32_t)kClassWarps[cls] * sw_class_chains(cls);  // column chains per SW task
 			const uint32_t begin = (uint32_t)e_clist.size();
 			uint32_t cnt = 0;
 			while (k < b.npairs && plan.sa[b.k0 + k] == a0 && cnt < W) {
@@ -1079,7 +1079,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 			sc.cross = 1;
 			sc.rowlist = ctx->rowlist.p + row_off[c];
 			sc.ncols = ncols;
-			sc.nseg = (ncols + kClassWarps[c] * kSwChain - 1) / (kClassWarps[c] * kSwChain);
+			sc.nseg = (ncols + kClassWarps[c] * sw_class_chains(c) - 1) / (kClassWarps[c] * sw_class_chains(c));
 			sc.clist = tr ? ctx->colsort.p : ctx->blist.p;
 			sc.ntasks = nrows * sc.nseg;
 			g = (int)std::min<uint64_t>((uint64_t)grid, sc.ntasks);

@@ -81,6 +81,15 @@ constexpr int kSwStripSteps = RSK_SW_STRIP;  // wavefront steps between two chec
 #define RSK_SW_CHAIN 4
 #endif
 constexpr int kSwChain = RSK_SW_CHAIN;       // column chains a warp aligns back to back as one wavefront (one ramp per list)
+// The half-warp classes (chains <= 192 residues) split a warp's list over two wavefronts, and their sweeps are short, so the ramp
+// weighs more: eight chains per warp = four per wavefront (A/B profiles/r2_chain_ab.log: L = 100 +5.5 %; L = 300, a full-warp
+// class, loses 1 % with eight and keeps four)
+#ifndef RSK_SW_CHAIN_HALF
+#define RSK_SW_CHAIN_HALF 8
+#endif
+constexpr int kSwChainHalf = RSK_SW_CHAIN_HALF;
+constexpr int kSwChainMax = kSwChain > kSwChainHalf ? kSwChain : kSwChainHalf;
+__host__ __device__ constexpr int sw_class_chains(int cls) { return (cls == 2 || cls == 3) ? kSwChain : kSwChainHalf; }
 // SW kernel classes (one kernel each, so that every class gets its own register allocation and warps per CTA = pairs per task):
 //   half-warp chains (<= 192 residues): 0: R <= 5 | 1: R == 6 | 4: R = 7..8 | 5: R = 9..12
 //   full-warp chains:                   2: R = 7..8 | 3: R = 9..12   (a chain above 192 residues never has R < 7)
@@ -172,7 +181,7 @@ struct SwArgs {
 	uint32_t bnd_pass_stride;
 	uint8_t *stage; uint32_t stage_stride; // reversed path staging: per warp, one region of stage_chain_stride per chain
 	uint32_t stage_chain_stride;
-	float4 *best;                          // per warp kSwChain*32 parked (score, row, column) maxima
+	float4 *best;                          // per warp kSwChainMax*32 parked (score, row, column) maxima
 	// outputs
 	PairRec *rec;
 	uint8_t *pool; unsigned long long *pool_cursor;

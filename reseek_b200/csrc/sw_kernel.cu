@@ -48,10 +48,10 @@ constexpr size_t kPlaneBytes = (size_t)kNLet * 512;     // 67584
 constexpr int kPlaneFloats = kNLet * 128;
 __host__ __device__ constexpr int class_planes(int C) { return (C == 3 || C == 5) ? 3 : 2; }  // R > 8 needs the third plane
 __host__ __device__ constexpr int planes_of_R(int R) { return R > 8 ? 3 : 2; }
-// after the planes: 16 bytes for the task broadcast, then the warps' column-chain lists (kSwMaxWarps x kSwChain x 24 B)
+// after the planes: 16 bytes for the task broadcast, then the warps' column-chain lists (kSwMaxWarps x kSwChainMax x 24 B)
 __host__ __device__ constexpr size_t smem_bcast_off(int planes) { return kSmemP0 + (size_t)planes * kPlaneBytes; }
 __host__ __device__ constexpr size_t smem_chains_off(int planes) { return smem_bcast_off(planes) + 16; }
-__host__ __device__ constexpr size_t class_smem_base(int C) { return smem_chains_off(class_planes(C)) + (size_t)kSwMaxWarps * kSwChain * 24; }
+__host__ __device__ constexpr size_t class_smem_base(int C) { return smem_chains_off(class_planes(C)) + (size_t)kSwMaxWarps * kSwChainMax * 24; }
 #ifdef RSK_SW_TMA_CKPT
 constexpr int kTmaStageBytes = 3072;  // per-warp staging of one checkpoint (ckpt_words <= 6 float4 per lane)
 // the two-plane classes with 16 warps have shared memory to spare for the staging
@@ -660,14 +660,15 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 		const uint32_t begin, const uint32_t cnt)
 {
 	constexpr int NG = 32 / G;            // wavefronts per warp
-	constexpr int CG = kSwChain / NG;     // column chains per wavefront
-	static_assert(kSwChain % NG == 0, "chains per warp must split evenly over the half-warps");
+	constexpr int CH = G == 16 ? kSwChainHalf : kSwChain;  // column chains per warp (= sw_class_chains of the task's class)
+	constexpr int CG = CH / NG;           // column chains per wavefront
+	static_assert(CH % NG == 0, "chains per warp must split evenly over the half-warps");
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int grp = lane / G;
 	const float *tab = reinterpret_cast<const float *>(smem + kSmemTab);
 	float *planes = reinterpret_cast<float *>(smem + kSmemP0);
 	const unsigned char *smem_p0 = smem + kSmemP0;
-	ColChain *chs = reinterpret_cast<ColChain *>(smem + smem_chains_off(planes_of_R(R))) + warp * kSwChain;
+	ColChain *chs = reinterpret_cast<ColChain *>(smem + smem_chains_off(planes_of_R(R))) + warp * kSwChainMax;
 
 	const uint32_t LA = a.len_row[rowchain];  // kernel rows
 	const uint64_t *profA = a.prof_row + a.off_row[rowchain];
@@ -680,7 +681,7 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 	for (int g = 0; g < NG; ++g)
 		nchg[g] = totg[g] = 0;
 #pragma unroll
-	for (int kk = 0; kk < kSwChain; ++kk) {
+	for (int kk = 0; kk < CH; ++kk) {
 		const uint32_t e = (uint32_t)(kk * W + warp);
 		if (e < cnt) {
 			const int g = kk % NG;
@@ -721,11 +722,11 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 	float2 *bnd = a.bnd + gw * a.bnd_stride;
 	uint8_t *stage = a.stage + gw * a.stage_stride;
 	unsigned long long *tile = a.tile + gw * (kStrip * 32);
-	float4 *best = a.best + gw * (kSwChain * 32);
+	float4 *best = a.best + gw * (kSwChainMax * 32);
 	float4 *stg = nullptr;
 #ifdef RSK_SW_TMA_CKPT
 	if (tma_class(planes_of_R(R), W))
-		stg = reinterpret_cast<float4 *>(smem + smem_chains_off(planes_of_R(R)) + (size_t)kSwMaxWarps * kSwChain * 24) + (size_t)warp * (kTmaStageBytes / 16);
+		stg = reinterpret_cast<float4 *>(smem + smem_chains_off(planes_of_R(R)) + (size_t)kSwMaxWarps * kSwChainMax * 24) + (size_t)warp * (kTmaStageBytes / 16);
 #endif
 
 	for (int pass = 0; pass < npass; ++pass) {
@@ -741,8 +742,8 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 	// per chain: first maximum in the reference's row-major (i, j) order: max score, then smallest i, then smallest j.
 	// Chain k of every wavefront is reduced at once (inside its half-warp), then broadcast to the whole warp, which walks the
 	// paths one after the other.
-	float score[kSwChain];
-	TbState tb[kSwChain];
+	float score[CH];
+	TbState tb[CH];
 	unsigned active = 0;
 	__syncwarp();
 #pragma unroll
@@ -828,7 +829,7 @@ __device__ __forceinline__ void process_task(const SwArgs &a, unsigned char *sme
 			__syncthreads();
 		}
 #pragma unroll
-		for (int kk = 0; kk < kSwChain; ++kk) {
+		for (int kk = 0; kk < CH; ++kk) {
 			if (active & (1u << kk)) {
 				if (traceback_in_pass<R, TR, G>(smem_p0, lane, p, npass, LA, mychs, mynch, mytot, tmax, tmin, kk / CG, chs[kk].base, bnd,
 							a.bnd_pass_stride, ck, nstrips, a.open, a.ext, tile, stage + (size_t)kk * a.stage_chain_stride, tb[kk], tc)) {
@@ -870,8 +871,8 @@ __global__ void __launch_bounds__(kClassWarps[C] * 32, 1) sw_affine_f32_tb_kerne
 			const uint32_t ridx = task / a.nseg;
 			const uint32_t seg = task - ridx * a.nseg;
 			rowchain = a.rowlist[ridx];
-			begin = seg * (W * kSwChain);
-			cnt = min((uint32_t)(W * kSwChain), a.ncols - begin);
+			begin = seg * (W * sw_class_chains(C));
+			cnt = min((uint32_t)(W * sw_class_chains(C)), a.ncols - begin);
 		} else {
 			rowchain = a.task_row[task];
 			begin = a.task_begin[task];
