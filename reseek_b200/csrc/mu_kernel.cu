@@ -229,11 +229,16 @@ constexpr size_t kMu16SmemT = 36 * 36 * 4;
 constexpr size_t kMu16SmemBcast = kMu16SmemT + (size_t)kMu16Letters * 2 * 32 * 16;
 constexpr size_t kMu16SmemTotal = kMu16SmemBcast + 16;
 
-template <int R>
+// G = 32: the warp is one wavefront over rows [pass*32R, (pass+1)*32R).  G = 16 (row chains of <= 192 residues, one pass):
+// the two half-warps are independent 16-lane wavefronts over the same rows, each with its own packed pair of column chains
+// (colB0/colB1/LB0/LB1 are then per half, LBm the warp-wide loop bound) - the ramp is 15 steps instead of 31 and no lane idles
+// on rows beyond the chain: a 174-residue chain fills 91 % of the lane-steps instead of 77 %.
+template <int R, int G>
 __device__ __forceinline__ unsigned mu16_pass(const uint4 *__restrict__ T, const int lane, const bool first, const bool last,
-		const uint8_t *__restrict__ colB0, const int LB0, const uint8_t *__restrict__ colB1, const int LB1,
+		const uint8_t *__restrict__ colB0, const int LB0, const uint8_t *__restrict__ colB1, const int LB1, const int LBmax,
 		uint2 *__restrict__ bnd, const unsigned nopen, const unsigned next)
 {
+	const int sub = lane & (G - 1);
 	unsigned H[R], E[R];  // H[i][j-1] (previous column), E[i][j]; pair 0 in the low half, pair 1 in the high half
 #pragma unroll
 	for (int r = 0; r < R; ++r) {
@@ -241,26 +246,26 @@ __device__ __forceinline__ unsigned mu16_pass(const uint4 *__restrict__ T, const
 		E[r] = 0;
 	}
 	unsigned best = 0, hdiag_next = 0, outH = 0, outF = 0;
-	const int LBm = max(LB0, LB1);
-	const int nsteps = LBm + 31;
-	int j = -lane;
+	const int LBm = max(LB0, LB1);     // this wavefront's columns
+	const int nsteps = (G == 32 ? LBm : LBmax) + G - 1;  // warp-uniform (G = 16: the longer of the two half-warps' columns)
+	int j = -sub;
 	int cb0 = (j >= 0 && j < LB0) ? (int)colB0[j] : 36;
 	int cb1 = (j >= 0 && j < LB1) ? (int)colB1[j] : 36;
 	uint2 bn = make_uint2(0, 0);
-	if (lane == 0 && !first)
+	if (G == 32 && lane == 0 && !first)
 		bn = bnd[0];
 	for (int s = 0; s < nsteps; ++s, ++j) {
-		const unsigned inH = __shfl_up_sync(kFull, outH, 1);
-		const unsigned inF = __shfl_up_sync(kFull, outF, 1);
+		const unsigned inH = __shfl_up_sync(kFull, outH, 1, G);
+		const unsigned inF = __shfl_up_sync(kFull, outF, 1, G);
 		const int jn = j + 1;
 		const int cb0n = (jn >= 0 && jn < LB0) ? (int)colB0[jn] : 36;
 		const int cb1n = (jn >= 0 && jn < LB1) ? (int)colB1[jn] : 36;
 		uint2 bn_next = bn;
-		if (lane == 0 && !first && jn < LBm)
+		if (G == 32 && lane == 0 && !first && jn < LBm)
 			bn_next = bnd[jn];
 		if (j >= 0 && j < LBm) {
 			unsigned f, hd = hdiag_next;
-			if (lane == 0) {
+			if (sub == 0) {
 				f = first ? 0u : bn.y;           // F entering row i0 at column j
 				hdiag_next = first ? 0u : bn.x;  // H[i0-1][j]
 			} else {
@@ -296,7 +301,7 @@ __device__ __forceinline__ unsigned mu16_pass(const uint4 *__restrict__ T, const
 			}
 			outH = H[R - 1];
 			outF = f;
-			if (lane == 31 && !last)
+			if (G == 32 && lane == 31 && !last)
 				bnd[j] = make_uint2(outH, outF);
 		}
 		cb0 = cb0n;
@@ -307,14 +312,15 @@ __device__ __forceinline__ unsigned mu16_pass(const uint4 *__restrict__ T, const
 }
 
 __device__ __forceinline__ void build_mu16_table(short *T16, const int *mx, const uint8_t *__restrict__ muA, const int LA,
-		const int pass, const int R, const bool reversed, const bool tr)
+		const int pass, const int R, const bool reversed, const bool tr, const bool half)
 {
-	// T[b][plane][lane][q]: row rr = lane*R + plane*8 + q of this pass, q < 8; unused slots are never read
+	// T[b][plane][lane][q]: row rr = lane*R + plane*8 + q of this pass, q < 8; unused slots are never read.  Half-warp mode:
+	// lane l holds the rows of sub-lane l & 15 (both half-warps read the same rows, each lane its own 16 bytes).
 	const int rows = 32 * R;
 	for (int idx = threadIdx.x; idx < kMu16Letters * rows; idx += kSwThreads) {
 		const int b = idx / rows;
 		const int rr = idx - b * rows;
-		const int row = pass * rows + rr;
+		const int row = half ? ((rr / R) & 15) * R + rr % R : pass * rows + rr;
 		int v = -1000;  // rows beyond the chain and the padding letter: never contribute (every value is floored at 0)
 		if (row < LA && b < kMuLetters) {
 			const int a = muA[reversed ? (LA - 1 - row) : row];
@@ -325,51 +331,61 @@ __device__ __forceinline__ void build_mu16_table(short *T16, const int *mx, cons
 	}
 }
 
-template <int R>
-__device__ __forceinline__ unsigned mu16_dir(const MuArgs &a, short *T16, const int *mx, const uint8_t *muA, const int LA,
-		const int npass, const bool reversed, const bool run, const int lane, const uint8_t *colB0, const int LB0,
-		const uint8_t *colB1, const int LB1, uint2 *bnd)
-{
-	const uint4 *T = reinterpret_cast<const uint4 *>(T16);
-	const unsigned no = (unsigned)(unsigned short)(short)(-a.open), ne = (unsigned)(unsigned short)(short)(-a.ext);
-	const unsigned nopen = no | (no << 16), next = ne | (ne << 16);
-	unsigned best = 0;
-	for (int pass = 0; pass < npass; ++pass) {
-		__syncthreads();
-		build_mu16_table(T16, mx, muA, LA, pass, R, reversed, a.tr != 0);
-		__syncthreads();
-		if (run)
-			best = __vmaxs2(best, mu16_pass<R>(T, lane, pass == 0, pass == npass - 1, colB0, LB0, colB1, LB1, bnd, nopen, next));
-	}
-#pragma unroll
-	for (int o = 16; o >= 1; o >>= 1)
-		best = __vmaxs2(best, __shfl_xor_sync(kFull, best, o));
-	return best;
-}
-
 // rows per lane and passes for a row chain of LA residues (R even, <= 12: 24 state registers + 12 scores fit the
-// 64-register budget of two 16-warp CTAs per SM)
-__host__ __device__ inline void mu16_geometry(int LA, int &npass, int &R)
+// 64-register budget of two 16-warp CTAs per SM); chains of <= 192 residues run as two 16-lane wavefronts per warp
+__host__ __device__ inline void mu16_geometry(int LA, int &npass, int &R, bool &half)
 {
-	npass = (LA + 383) / 384;
+	half = LA <= 16 * 12;
+	const int lanes = half ? 16 : 32;
+	npass = half ? 1 : (LA + 383) / 384;
 	if (npass < 1) npass = 1;
-	R = (LA + 32 * npass - 1) / (32 * npass);
+	R = (LA + lanes * npass - 1) / (lanes * npass);
 	R = (R + 1) & ~1;
 	if (R < 2) R = 2;
 }
 
+template <int R, int G>
+__device__ __forceinline__ unsigned mu16_run(const uint4 *T, const int lane, const bool first, const bool last, const uint8_t *c0,
+		const int L0, const uint8_t *c1, const int L1, const int LBmax, uint2 *bnd, const unsigned nopen, const unsigned next)
+{
+	return mu16_pass<R, G>(T, lane, first, last, c0, L0, c1, L1, LBmax, bnd, nopen, next);
+}
+
+// one pass of one round: dispatch on the rows per lane
+template <int G>
+__device__ __forceinline__ unsigned mu16_pass_R(const int R, const uint4 *T, const int lane, const bool first, const bool last,
+		const uint8_t *c0, const int L0, const uint8_t *c1, const int L1, const int LBmax, uint2 *bnd, const unsigned nopen,
+		const unsigned next)
+{
+	switch (R) {
+	case 2: return mu16_run<2, G>(T, lane, first, last, c0, L0, c1, L1, LBmax, bnd, nopen, next);
+	case 4: return mu16_run<4, G>(T, lane, first, last, c0, L0, c1, L1, LBmax, bnd, nopen, next);
+	case 6: return mu16_run<6, G>(T, lane, first, last, c0, L0, c1, L1, LBmax, bnd, nopen, next);
+	case 8: return mu16_run<8, G>(T, lane, first, last, c0, L0, c1, L1, LBmax, bnd, nopen, next);
+	case 10: return mu16_run<10, G>(T, lane, first, last, c0, L0, c1, L1, LBmax, bnd, nopen, next);
+	default: return mu16_run<12, G>(T, lane, first, last, c0, L0, c1, L1, LBmax, bnd, nopen, next);
+	}
+}
+
+// A task = one row chain x a segment of the column list.  Row chains of <= 192 residues: 64 column chains per task, warp w
+// takes columns 4w .. 4w+3 as two packed pairs that run side by side on its two half-warps.  Longer row chains: 32 column
+// chains per task, warp w takes columns 2w, 2w+1 as one packed pair on the whole warp.  (Cross mode numbers its segments in
+// units of 32 columns; a short row chain uses the even ones, each covering two units.)
 __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter16_kernel(const MuArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	int *mx = reinterpret_cast<int *>(smem + kMuSmemMx);
 	short *T16 = reinterpret_cast<short *>(smem + kMu16SmemT);
+	const uint4 *T = reinterpret_cast<const uint4 *>(T16);
 	volatile int *bcast = reinterpret_cast<volatile int *>(smem + kMu16SmemBcast);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (int k = threadIdx.x; k < 36 * 36; k += kSwThreads)
 		mx[k] = a.mu_mx[k];
 	__syncthreads();
 	const size_t gw = (size_t)blockIdx.x * kSwWarps + warp;
-	uint2 *bnd = reinterpret_cast<uint2 *>(a.bnd + gw * a.bnd_stride);
+	uint2 *bnd0 = reinterpret_cast<uint2 *>(a.bnd + gw * (size_t)a.bnd_stride);
+	const unsigned no = (unsigned)(unsigned short)(short)(-a.open), ne = (unsigned)(unsigned short)(short)(-a.ext);
+	const unsigned nopen = no | (no << 16), next = ne | (ne << 16);
 	for (;;) {
 		if (threadIdx.x == 0)
 			bcast[0] = (int)atomicAdd(a.task_counter, 1u);
@@ -383,8 +399,8 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter16_kernel(const MuA
 			const uint32_t ridx = task / a.nseg;
 			const uint32_t seg = task - ridx * a.nseg;
 			rowchain = a.rowlist[ridx];
-			begin = seg * kMuTaskCols;
-			cnt = min((uint32_t)kMuTaskCols, a.ncols - begin);
+			begin = seg * (kMuTaskCols / 2);
+			cnt = a.ncols - begin;
 		} else {
 			rowchain = a.task_row[task];
 			begin = a.task_begin[task];
@@ -393,18 +409,25 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter16_kernel(const MuA
 		const int LA = (int)a.len_row[rowchain];
 		const uint8_t *muA = a.mu_row + a.off_row[rowchain];
 		int npass, R;
-		mu16_geometry(LA, npass, R);
-		// this warp's two column chains
-		bool have[2], runp[2], mkf[2];
-		uint32_t cidx[2] = {0, 0};
-		int LB[2] = {0, 0};
-		const uint8_t *colB[2] = {muA, muA};  // never dereferenced when LB = 0
+		bool half;
+		mu16_geometry(LA, npass, R, half);
+		if (a.cross) {
+			if (half && (task - (task / a.nseg) * a.nseg) % 2 != 0)
+				continue;  // covered by the even segment before it
+			cnt = min(cnt, (uint32_t)(half ? kMuTaskCols : kMuTaskCols / 2));
+		}
+		const int per = half ? 4 : 2;  // column chains per warp
+		// this warp's column chains: pairs (0, 1) and - half-warp mode - (2, 3)
+		bool have[4], runp[4], mkf[4];
+		uint32_t cidx[4] = {0, 0, 0, 0};
+		int LB[4] = {0, 0, 0, 0};
+		const uint8_t *colB[4] = {muA, muA, muA, muA};  // never dereferenced when LB = 0
 #pragma unroll
-		for (int p = 0; p < 2; ++p) {
-			have[p] = (uint32_t)(2 * warp + p) < cnt;
+		for (int p = 0; p < 4; ++p) {
+			have[p] = p < per && (uint32_t)(per * warp + p) < cnt;
 			mkf[p] = false;
 			if (have[p]) {
-				cidx[p] = a.clist[begin + 2 * warp + p];
+				cidx[p] = a.clist[begin + per * warp + p];
 				LB[p] = (int)a.len_col[cidx[p]];
 				colB[p] = a.mu_col + a.off_col[cidx[p]];
 				// DoMKF() pairs are not the filter's business (dssaligner.cpp:811-815 returns before the filter)
@@ -412,46 +435,71 @@ __global__ void __launch_bounds__(kSwThreads, 2) mu_sw_filter16_kernel(const MuA
 			}
 			runp[p] = have[p] && !mkf[p];
 		}
-		const int LBr[2] = {runp[0] ? LB[0] : 0, runp[1] ? LB[1] : 0};
-		int fwd[2] = {0, 0}, rev[2] = {0, 0};
-		bool need_rev[2] = {false, false};
+		int fwd[4] = {0, 0, 0, 0}, rev[4] = {0, 0, 0, 0};
+		bool need_rev[4] = {false, false, false, false};
 		for (int dir = 0; dir < 2; ++dir) {
-			bool run = runp[0] || runp[1];
-			if (dir == 1) {
-				// reversed pass only when some warp of the CTA still needs it
-				need_rev[0] = runp[0] && !((float)fwd[0] < a.omega_fwd);
-				need_rev[1] = runp[1] && !((float)fwd[1] < a.omega_fwd);
-				run = need_rev[0] || need_rev[1];
-				if (!__syncthreads_or(run ? 1 : 0))
-					break;
+			int Ld[4];  // columns of each chain in this direction (0 = not run)
+			bool any = false;
+#pragma unroll
+			for (int p = 0; p < 4; ++p) {
+				if (dir == 1)
+					need_rev[p] = runp[p] && !((float)fwd[p] < a.omega_fwd);
+				Ld[p] = (dir == 0 ? runp[p] : need_rev[p]) ? LB[p] : 0;
+				any = any || Ld[p] > 0;
 			}
-			const int L0 = (dir == 0 || need_rev[0]) ? LBr[0] : 0, L1 = (dir == 0 || need_rev[1]) ? LBr[1] : 0;
-			unsigned best;
-			switch (R) {
-			case 2: best = mu16_dir<2>(a, T16, mx, muA, LA, npass, dir == 1, run, lane, colB[0], L0, colB[1], L1, bnd); break;
-			case 4: best = mu16_dir<4>(a, T16, mx, muA, LA, npass, dir == 1, run, lane, colB[0], L0, colB[1], L1, bnd); break;
-			case 6: best = mu16_dir<6>(a, T16, mx, muA, LA, npass, dir == 1, run, lane, colB[0], L0, colB[1], L1, bnd); break;
-			case 8: best = mu16_dir<8>(a, T16, mx, muA, LA, npass, dir == 1, run, lane, colB[0], L0, colB[1], L1, bnd); break;
-			case 10: best = mu16_dir<10>(a, T16, mx, muA, LA, npass, dir == 1, run, lane, colB[0], L0, colB[1], L1, bnd); break;
-			default: best = mu16_dir<12>(a, T16, mx, muA, LA, npass, dir == 1, run, lane, colB[0], L0, colB[1], L1, bnd); break;
+			// reversed pass only when some warp of the CTA still needs it
+			if (dir == 1 && !__syncthreads_or(any ? 1 : 0))
+				break;
+			unsigned best[1] = {0};
+			const int LBw = max(max(Ld[0], Ld[1]), max(Ld[2], Ld[3]));
+			for (int pass = 0; pass < npass; ++pass) {
+				__syncthreads();
+				build_mu16_table(T16, mx, muA, LA, pass, R, dir == 1, a.tr != 0, half);
+				__syncthreads();
+				if (!any)
+					continue;
+				if (half) {
+					const bool h = lane >= 16;  // explicit selects: a runtime index would put the arrays into local memory
+					best[0] = mu16_pass_R<16>(R, T, lane, true, true, h ? colB[2] : colB[0], h ? Ld[2] : Ld[0], h ? colB[3] : colB[1],
+							h ? Ld[3] : Ld[1], LBw, nullptr, nopen, next);
+				} else {
+					best[0] = __vmaxs2(best[0], mu16_pass_R<32>(R, T, lane, pass == 0, pass == npass - 1, colB[0], Ld[0], colB[1], Ld[1], LBw,
+							bnd0, nopen, next));
+				}
 			}
-			const int b0 = (int)(short)(best & 0xffffu), b1 = (int)(short)(best >> 16);
-			if (dir == 0) {
-				fwd[0] = b0 > 250 ? 777 : b0;  // parasail_mu.cpp:133-137
-				fwd[1] = b1 > 250 ? 777 : b1;
+			// packed maxima of the two pairs: full mode = reduced over the warp per round, half mode = over each half-warp
+			unsigned b01, b23;
+			if (half) {
+				unsigned b = best[0];
+#pragma unroll
+				for (int o = 8; o >= 1; o >>= 1)
+					b = __vmaxs2(b, __shfl_xor_sync(kFull, b, o));
+				b01 = __shfl_sync(kFull, b, 0);
+				b23 = __shfl_sync(kFull, b, 16);
 			} else {
-				rev[0] = b0 > 250 ? 255 : b0;  // value read before the 777 assignment (:149-155)
-				rev[1] = b1 > 250 ? 255 : b1;
+				b01 = best[0];
+				b23 = 0;
+#pragma unroll
+				for (int o = 16; o >= 1; o >>= 1)
+					b01 = __vmaxs2(b01, __shfl_xor_sync(kFull, b01, o));
+			}
+			const int bv[4] = {(int)(short)(b01 & 0xffffu), (int)(short)(b01 >> 16), (int)(short)(b23 & 0xffffu), (int)(short)(b23 >> 16)};
+#pragma unroll
+			for (int p = 0; p < 4; ++p) {
+				if (dir == 0)
+					fwd[p] = bv[p] > 250 ? 777 : bv[p];  // parasail_mu.cpp:133-137
+				else
+					rev[p] = bv[p] > 250 ? 255 : bv[p];  // value read before the 777 assignment (:149-155)
 			}
 		}
-		if (lane < 2 && have[lane]) {
+		if (lane < 4 && have[lane]) {
 			const int p = lane;
 			uint32_t slot;
 			if (a.cross) {
 				const uint32_t ra = a.tr ? cidx[p] : rowchain, rb = a.tr ? rowchain : cidx[p];
 				slot = (ra - a.a_begin) * a.nB + rb;
 			} else {
-				slot = a.cslot[begin + 2 * warp + p];
+				slot = a.cslot[begin + per * warp + p];
 			}
 			PairRec *rec = a.rec + slot;
 			float score = 0.0f;

@@ -891,7 +891,8 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		ma.a_begin = b.a0; ma.nB = B->d.n;
 		// packed 16-bit lanes (two column chains per warp) unless a pair could exceed their range
 		const bool mu16 = std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32");
-		const uint32_t task_cols = mu16 ? (uint32_t)kMuTaskCols : (uint32_t)kSwWarps;
+		// cross mode numbers the packed kernel's segments in units of kMuTaskCols / 2 columns (a short row chain takes two at a time)
+		const uint32_t task_cols = mu16 ? (uint32_t)kMuTaskCols / 2 : (uint32_t)kSwWarps;
 		if (b.cross) {
 			ma.nseg = (ncols + task_cols - 1) / task_cols;
 			ma.ncols = ncols;
@@ -1217,7 +1218,11 @@ int upload_explicit_tasks(rsk_ctx *ctx, const SearchPlan &plan, Batch &b)
 	rsk_stats &S = ctx->stats;
 	static thread_local std::vector<uint32_t> t_a, t_begin, t_cnt, slots, r_a, r_begin, r_cnt;
 	// (cudaMemcpyAsync from pageable memory returns once the source has been staged, so the vectors can be reused per batch)
-	const size_t task_cols = (std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32")) ? (size_t)kMuTaskCols : (size_t)kSwWarps;
+	const bool mu16 = std::min(b.maxLA, b.maxLB) <= kMu16MaxLen && !getenv("RSK_MU32");
+	// column chains per Mu task: the packed kernel takes 64 for row chains of <= 192 residues (half-warp wavefronts), 32 otherwise
+	auto task_cols_of = [&](uint32_t a) -> size_t {
+		return !mu16 ? (size_t)kSwWarps : plan.A->hlen[a] <= 192 ? (size_t)kMuTaskCols : (size_t)kMuTaskCols / 2;
+	};
 	t_a.clear(); t_begin.clear(); t_cnt.clear();
 	const size_t n = b.k1 - b.k0;
 	slots.resize(n);
@@ -1226,6 +1231,7 @@ int upload_explicit_tasks(rsk_ctx *ctx, const SearchPlan &plan, Batch &b)
 	size_t k = 0;
 	while (k < n) {
 		size_t e = k + 1;
+		const size_t task_cols = task_cols_of(plan.sa[b.k0 + k]);
 		while (e < n && e - k < task_cols && plan.sa[b.k0 + e] == plan.sa[b.k0 + k])
 			++e;
 		t_a.push_back(plan.sa[b.k0 + k]);

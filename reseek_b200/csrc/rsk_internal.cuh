@@ -69,7 +69,7 @@ int launch_sink_append(const SinkArgs &a, void *tmp, size_t tmp_bytes, cudaStrea
 // ---- SW kernel geometry ----
 constexpr int kSwWarps = 16;                 // warps per CTA of the Mu filter kernel
 constexpr int kSwThreads = kSwWarps * 32;
-constexpr int kMuTaskCols = 2 * kSwWarps;     // column chains per task of the packed 16-bit Mu filter (two per warp)
+constexpr int kMuTaskCols = 4 * kSwWarps;     // column chains per task of the packed 16-bit Mu filter (two packed pairs per warp)
 constexpr uint32_t kMu16MaxLen = 8000;       // 4*L must stay below 2^15 for the 16-bit lanes
 constexpr int kMaxRowsPerLane = 12;          // R: DP rows owned by one lane within a pass
 constexpr int kRowsPerPassMax = 32 * kMaxRowsPerLane;
