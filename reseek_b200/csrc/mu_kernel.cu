@@ -560,7 +560,10 @@ __global__ void __launch_bounds__(256) compact_survivors_kernel(const CompactArg
 		__syncthreads();
 	}
 	const int cls = sw_class_of_len(a.len_row[rowchain]);
-	const uint32_t W = (uint32_t)sw_class_warps(cls) * sw_class_chains(cls);  // column chains per SW task
+	// column chains per SW task: every warp of the CTA gets one chain before any warp gets a second one, and a row chain with few
+	// survivors is cut into more, smaller tasks (one CTA each) - in an all-vs-all most row chains keep a few dozen partners and a
+	// launch of a few large tasks leaves most SMs idle; rows with thousands of survivors get full lists (one ramp per list)
+	const uint32_t W = (uint32_t)sw_class_warps(cls) * sw_task_chains(running, sw_class_warps(cls), sw_class_chains(cls));
 	const uint32_t ntask = (running + W - 1) / W;
 #pragma unroll
 	for (int o = 16; o >= 1; o >>= 1)
@@ -621,7 +624,10 @@ __global__ void __launch_bounds__(256) compact_explicit_kernel(const CompactArgs
 		__syncthreads();
 	}
 	const int cls = sw_class_of_len(a.len_row[rowchain]);
-	const uint32_t W = (uint32_t)sw_class_warps(cls) * sw_class_chains(cls);  // column chains per SW task
+	// column chains per SW task: every warp of the CTA gets one chain before any warp gets a second one, and a row chain with few
+	// survivors is cut into more, smaller tasks (one CTA each) - in an all-vs-all most row chains keep a few dozen partners and a
+	// launch of a few large tasks leaves most SMs idle; rows with thousands of survivors get full lists (one ramp per list)
+	const uint32_t W = (uint32_t)sw_class_warps(cls) * sw_task_chains(running, sw_class_warps(cls), sw_class_chains(cls));
 	const uint32_t ntask = (running + W - 1) / W;
 #pragma unroll
 	for (int o = 16; o >= 1; o >>= 1)

@@ -949,7 +949,7 @@ int run_batch(rsk_ctx *ctx, const SearchPlan &plan, const Batch &b, const rsk_se
 		}
 		if (b.cross) {
 			const uint32_t nrows = (uint32_t)rowlist.size();
-			task_cap = nrows * (ncols / (16 * kSwChain) + 2);  // a task holds W * kSwChain >= 16 * kSwChain column chains
+			task_cap = nrows * (ncols / (16 * kSwChain) + 10);  // sw_task_chains: at most 9 small tasks per row chain, or full lists of >= 16 * kSwChain
 			if (ctx->c_blist.ensure(b.npairs) || ctx->c_bslot.ensure(b.npairs) || ctx->c_task_a.ensure((size_t)task_cap * kSwClasses) ||
 				ctx->c_task_begin.ensure((size_t)task_cap * kSwClasses) || ctx->c_task_cnt.ensure((size_t)task_cap * kSwClasses)) {
 				cudaGetLastError();
@@ -1249,7 +1249,7 @@ int upload_explicit_tasks(rsk_ctx *ctx, const SearchPlan &plan, Batch &b)
 		while (e < t_a.size() && t_a[e] == t_a[t] && t_begin[e] == t_begin[t] + cnt)
 			cnt += t_cnt[e++];
 		r_a.push_back(t_a[t]); r_begin.push_back(t_begin[t]); r_cnt.push_back(cnt);
-		sw_tasks_max += cnt / (16 * kSwChain) + 1;  // a task holds W * kSwChain >= 16 * kSwChain column chains
+		sw_tasks_max += cnt / (16 * kSwChain) + 10;  // sw_task_chains: at most 9 small tasks per row chain, or full lists of >= 16 * kSwChain
 		t = e;
 	}
 	b.nruns = (uint32_t)r_a.size();

@@ -90,6 +90,12 @@ constexpr int kSwChain = RSK_SW_CHAIN;       // column chains a warp aligns back
 constexpr int kSwChainHalf = RSK_SW_CHAIN_HALF;
 constexpr int kSwChainMax = kSwChain > kSwChainHalf ? kSwChain : kSwChainHalf;
 __host__ __device__ constexpr int sw_class_chains(int cls) { return (cls == 2 || cls == 3) ? kSwChain : kSwChainHalf; }
+// chains per warp for the SW tasks of a row chain with `n` surviving partners: aim at eight tasks per row chain before lists grow
+__host__ __device__ inline uint32_t sw_task_chains(uint32_t n, int warps, int max_chains)
+{
+	const uint32_t c = (n + (uint32_t)warps * 8 - 1) / ((uint32_t)warps * 8);
+	return c < 1 ? 1u : c > (uint32_t)max_chains ? (uint32_t)max_chains : c;
+}
 // SW kernel classes (one kernel each, so that every class gets its own register allocation and warps per CTA = pairs per task):
 //   half-warp chains (<= 192 residues): 0: R <= 5 | 1: R == 6 | 4: R = 7..8 | 5: R = 9..12
 //   full-warp chains:                   2: R = 7..8 | 3: R = 9..12   (a chain above 192 residues never has R < 7)
