@@ -314,20 +314,38 @@ __device__ __forceinline__ unsigned mu16_pass(const uint4 *__restrict__ T, const
 __device__ __forceinline__ void build_mu16_table(short *T16, const int *mx, const uint8_t *__restrict__ muA, const int LA,
 		const int pass, const int R, const bool reversed, const bool tr, const bool half)
 {
-	// T[b][plane][lane][q]: row rr = lane*R + plane*8 + q of this pass, q < 8; unused slots are never read.  Half-warp mode:
+	// T[b][plane][lane][q]: row lane*R + plane*8 + q of this pass, q < 8; unused slots are never read.  Half-warp mode:
 	// lane l holds the rows of sub-lane l & 15 (both half-warps read the same rows, each lane its own 16 bytes).
-	const int rows = 32 * R;
-	for (int idx = threadIdx.x; idx < kMu16Letters * rows; idx += kSwThreads) {
-		const int b = idx / rows;
-		const int rr = idx - b * rows;
-		const int row = half ? ((rr / R) & 15) * R + rr % R : pass * rows + rr;
-		int v = -1000;  // rows beyond the chain and the padding letter: never contribute (every value is floored at 0)
-		if (row < LA && b < kMuLetters) {
-			const int a = muA[reversed ? (LA - 1 - row) : row];
-			v = tr ? mx[b * kMuLetters + a] : mx[a * kMuLetters + b];  // matrix[reference A letter][reference B letter]
+	// Division-free: thread (l, g) of the CTA owns lane slot l and the letters b = g, g + 16, g + 32; it reads the letters of the
+	// slot's R rows once and writes whole 16-byte slots.  (The first form mapped a flat index to (b, lane, row) with two runtime
+	// divisions per 2-byte element - ~7 % of a task's time for 300-residue chains.)
+	constexpr int kGroups = kSwThreads / 32;
+	const int l = threadIdx.x & 31, g = threadIdx.x >> 5;
+	const int row0 = half ? (l & 15) * R : (pass * 32 + l) * R;
+	int arow[12];
+#pragma unroll
+	for (int r = 0; r < 12; ++r) {
+		const int row = row0 + r;
+		arow[r] = (r < R && row < LA) ? (int)muA[reversed ? (LA - 1 - row) : row] : -1;
+	}
+	uint4 *T4 = reinterpret_cast<uint4 *>(T16);
+	for (int b = g; b < kMu16Letters; b += kGroups) {
+		unsigned w[8];
+#pragma unroll
+		for (int k = 0; k < 6; ++k) {
+			int v[2];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const int a = arow[2 * k + h];
+				// rows beyond the chain and the padding letter never contribute (every value is floored at 0)
+				v[h] = (a >= 0 && b < kMuLetters) ? (tr ? mx[b * kMuLetters + a] : mx[a * kMuLetters + b]) : -1000;  // matrix[ref A letter][ref B letter]
+			}
+			w[k] = ((unsigned)v[0] & 0xffffu) | ((unsigned)v[1] << 16);
 		}
-		const int l = rr / R, r = rr - l * R;
-		T16[(((b * 2 + (r >> 3)) * 32 + l) << 3) + (r & 7)] = (short)v;
+		w[6] = w[7] = 0xfc18fc18u;  // -1000, -1000
+		T4[(b * 2 + 0) * 32 + l] = make_uint4(w[0], w[1], w[2], w[3]);
+		if (R > 8)
+			T4[(b * 2 + 1) * 32 + l] = make_uint4(w[4], w[5], w[6], w[7]);
 	}
 }
 
