@@ -143,27 +143,45 @@ __global__ void __launch_bounds__(kSeedWarps * 32) mkf_seed_kernel(const MkfArgs
 			}
 		}
 		__syncwarp();
-		if (lane == 0) {
-			for (int c = 0; c < 32 * kHashW; ++c) {
-				const Hsp h = cand[c];
-				if (h.score < 0 || h.score < a.min_hsp_score)
-					continue;
-				found = true;
+		// The gate is order dependent (PosT ascending, slot ascending = candidate index ascending), but candidates that reach
+		// MinHSPScore are rare: every lane flags its own qualifying slots, and the warp walks only the flagged ones, in order,
+		// with nh / best / found kept uniform.  (One lane scanning all 32 x 4 slots of every chunk was 90 % of this kernel's
+		// issued instructions: 3.4 of 32 lanes active.)
+		unsigned my = 0;
+#pragma unroll
+		for (int w = 0; w < kHashW; ++w) {
+			const int sc = cand[lane * kHashW + w].score;
+			if (sc >= 0 && sc >= a.min_hsp_score)
+				my |= 1u << w;
+		}
+		unsigned lanes = __ballot_sync(kFull, my != 0);
+		if (lanes)
+			found = true;
+		while (lanes) {
+			const int src = __ffs(lanes) - 1;
+			lanes &= lanes - 1;
+			unsigned m = __shfl_sync(kFull, my, src);
+			while (m) {
+				const int w = __ffs(m) - 1;
+				m &= m - 1;
+				const Hsp h = cand[src * kHashW + w];
 				if (h.score > best) {
 					best = h.score;
 					bool old = false;
-					for (int i = 0; i < nh; ++i)
-						if (hsp[i].loi == h.loi) { old = true; break; }
-					if (!old && nh < kMaxHsp)
-						hsp[nh++] = h;
+					for (int i = lane; i < nh; i += 32)
+						old = old || hsp[i].loi == h.loi;
+					old = __any_sync(kFull, old);
+					if (!old && nh < kMaxHsp) {
+						if (lane == 0)
+							hsp[nh] = h;
+						++nh;
+						__syncwarp();
+					}
 				}
 			}
 		}
 		__syncwarp();
 	}
-	nh = __shfl_sync(kFull, nh, 0);
-	best = __shfl_sync(kFull, best, 0);
-	found = __shfl_sync(kFull, (int)found, 0) != 0;
 	out.best_hsp = best;
 
 	// ---- chaining on the query axis (chainer.cpp:31-194); lane 0, N is tiny ----
