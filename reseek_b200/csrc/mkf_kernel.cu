@@ -28,6 +28,7 @@ constexpr int kDict = 36 * 36 * 36;       // 3-mer dictionary (pattern "111", ds
 constexpr int kHashW = 4;                 // first 4 positions of every 3-mer (mukmerfilter.h:7)
 constexpr int kMaxHsp = 80;               // kept HSPs per pair (each must beat the previous best score: never many)
 constexpr int kSeedWarps = 4;
+constexpr int kCandCap = 256;             // listed hash hits per flush of the seed kernel (a chunk of 32 positions adds at most 128)
 
 // ---- query hash tables: uint16 ht[kDict][4], 0xffff = empty ----
 __global__ void __launch_bounds__(256) mkf_hash_kernel(const MkfArgs a)
@@ -96,7 +97,9 @@ __global__ void __launch_bounds__(kSeedWarps * 32) mkf_seed_kernel(const MkfArgs
 {
 	__shared__ int s_mx[36 * 36];
 	__shared__ float s_tab[RSK_TABLE_FLOATS];
-	__shared__ Hsp s_cand[kSeedWarps][32 * kHashW];
+	__shared__ Hsp s_cand[kSeedWarps][kCandCap];       // extension results of the listed hits; later the chainer's breakpoints
+	__shared__ uint32_t s_cpt[kSeedWarps][kCandCap];   // listed hits: target position ...
+	__shared__ uint16_t s_cpq[kSeedWarps][kCandCap];   // ... and query position
 	__shared__ Hsp s_hsp[kSeedWarps][kMaxHsp];
 	__shared__ int s_chain[kSeedWarps][kMaxHsp];
 	__shared__ float s_mega[kSeedWarps][kMaxHsp];
@@ -121,55 +124,40 @@ __global__ void __launch_bounds__(kSeedWarps * 32) mkf_seed_kernel(const MkfArgs
 	out.valid = 0; out.lo_a = 0; out.lo_b = 0; out.best_hsp = 0; out.best_chain = 0;
 
 	// ---- seeds + gating (mukmerfilter.cpp:316-389): the order is PosT ascending, slot ascending ----
+	// The hash hits of a target are sparse (about one per 32 positions), and an ungapped x-drop extension is a loop of its own
+	// length: extending each position's hits where they are found kept 1-2 lanes of the warp busy.  So the hits are first
+	// collected, in order, into a list (position, query position); a full list is flushed: every lane extends one hit at a time
+	// (all lanes busy), then the gate - which is order dependent, but only for the rare extensions that reach MinHSPScore -
+	// walks the flagged results in list order with nh / best / found uniform over the warp.
 	int nh = 0, best = 0;
 	bool found = false;
 	const int nkT = LT - 2;
-	for (int base = 0; base < nkT; base += 32) {
-		const int pt = base + lane;
-#pragma unroll
-		for (int w = 0; w < kHashW; ++w)
-			cand[lane * kHashW + w].score = -1;
-		if (pt < nkT) {
-			const int k = (T[pt] * 36 + T[pt + 1]) * 36 + T[pt + 2];
-			const ushort4 slots = *reinterpret_cast<const ushort4 *>(ht + kHashW * k);
-			const uint16_t pq[4] = {slots.x, slots.y, slots.z, slots.w};
-#pragma unroll
-			for (int w = 0; w < kHashW; ++w) {
-				if (pq[w] != 0xffff) {
-					Hsp h;
-					h.score = mu_xdrop(s_mx, Q, LQ, T, LT, (int)pq[w], pt, a.x1, h.loi, h.loj, h.len);
-					cand[lane * kHashW + w] = h;
-				}
-			}
+	uint32_t *cpt = s_cpt[warp];
+	uint16_t *cpq = s_cpq[warp];
+	int ncand = 0;
+	auto flush = [&]() {
+		__syncwarp();
+		for (int i = lane; i < ncand; i += 32) {
+			Hsp h;
+			h.score = mu_xdrop(s_mx, Q, LQ, T, LT, (int)cpq[i], (int)cpt[i], a.x1, h.loi, h.loj, h.len);
+			cand[i] = h;
 		}
 		__syncwarp();
-		// The gate is order dependent (PosT ascending, slot ascending = candidate index ascending), but candidates that reach
-		// MinHSPScore are rare: every lane flags its own qualifying slots, and the warp walks only the flagged ones, in order,
-		// with nh / best / found kept uniform.  (One lane scanning all 32 x 4 slots of every chunk was 90 % of this kernel's
-		// issued instructions: 3.4 of 32 lanes active.)
-		unsigned my = 0;
-#pragma unroll
-		for (int w = 0; w < kHashW; ++w) {
-			const int sc = cand[lane * kHashW + w].score;
-			if (sc >= 0 && sc >= a.min_hsp_score)
-				my |= 1u << w;
-		}
-		unsigned lanes = __ballot_sync(kFull, my != 0);
-		if (lanes)
-			found = true;
-		while (lanes) {
-			const int src = __ffs(lanes) - 1;
-			lanes &= lanes - 1;
-			unsigned m = __shfl_sync(kFull, my, src);
+		for (int c0 = 0; c0 < ncand; c0 += 32) {
+			const int i = c0 + lane;
+			const int sc = i < ncand ? cand[i].score : -1;
+			unsigned m = __ballot_sync(kFull, sc >= 0 && sc >= a.min_hsp_score);
+			if (m)
+				found = true;
 			while (m) {
-				const int w = __ffs(m) - 1;
+				const int src = __ffs(m) - 1;
 				m &= m - 1;
-				const Hsp h = cand[src * kHashW + w];
+				const Hsp h = cand[c0 + src];
 				if (h.score > best) {
 					best = h.score;
 					bool old = false;
-					for (int i = lane; i < nh; i += 32)
-						old = old || hsp[i].loi == h.loi;
+					for (int k = lane; k < nh; k += 32)
+						old = old || hsp[k].loi == h.loi;
 					old = __any_sync(kFull, old);
 					if (!old && nh < kMaxHsp) {
 						if (lane == 0)
@@ -181,7 +169,46 @@ __global__ void __launch_bounds__(kSeedWarps * 32) mkf_seed_kernel(const MkfArgs
 			}
 		}
 		__syncwarp();
+		ncand = 0;
+	};
+	for (int base = 0; base < nkT; base += 32) {
+		const int pt = base + lane;
+		uint16_t pq[kHashW];
+		unsigned cnt = 0;
+#pragma unroll
+		for (int w = 0; w < kHashW; ++w)
+			pq[w] = 0xffff;
+		if (pt < nkT) {
+			const int k = (T[pt] * 36 + T[pt + 1]) * 36 + T[pt + 2];
+			const ushort4 slots = *reinterpret_cast<const ushort4 *>(ht + kHashW * k);
+			pq[0] = slots.x; pq[1] = slots.y; pq[2] = slots.z; pq[3] = slots.w;
+#pragma unroll
+			for (int w = 0; w < kHashW; ++w)
+				cnt += pq[w] != 0xffff;
+		}
+		unsigned incl = cnt;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned t = __shfl_up_sync(kFull, incl, o);
+			if (lane >= o)
+				incl += t;
+		}
+		const int total = (int)__shfl_sync(kFull, incl, 31);
+		if (total == 0)
+			continue;
+		if (ncand + total > kCandCap)
+			flush();
+		int pos = ncand + (int)(incl - cnt);
+#pragma unroll
+		for (int w = 0; w < kHashW; ++w)
+			if (pq[w] != 0xffff) {
+				cpt[pos] = (uint32_t)pt;
+				cpq[pos] = pq[w];
+				++pos;
+			}
+		ncand += total;
 	}
+	flush();
 	out.best_hsp = best;
 
 	// ---- chaining on the query axis (chainer.cpp:31-194); lane 0, N is tiny ----
