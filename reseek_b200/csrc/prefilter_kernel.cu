@@ -3,18 +3,19 @@
 // Replaces MuPreFilter (muprefilter.cpp:64-133): MuDex::FromSeqDB incl. the k-mer neighbourhoods
 // (mudex.cpp:386-442, :130-180; MerMx::GetHighScoring5mers mermx.cpp:484-584), PrefilterMu::Search
 // (prefiltermu.cpp:382-393) = Search_TargetKmer (:213-261) + TwoHitDiag::Add/SetDupes (twohitdiag.cpp:47/389)
-// + FindHSP (:12-48) + AddTwoHitDiag (:288-313).  The per-query top-B bag (RankedScoresBag) is order dependent and
-// tiny, so it runs on the host (rsk_api.cu) over the (target, query, score) triples this file produces.
+// + FindHSP (:12-48) + AddTwoHitDiag (:288-313), and RankedScoresBag (rankedscoresbag.cpp:5-51, 185-232) - the per-query top-B
+// bag, order dependent down to the swap sequence of the reference's unstable quicksort - as pf_bag_kernel.
 //
 //   K6  query index: every unmasked query 5-mer X and all 5-mers Y with pair score >= 36 (its neighbourhood, which
 //       contains X itself; in query-neighbourhood mode X is entered a second time, exactly like the reference's
 //       Put + neighbourhood loop) -> (key = Y, value = query<<16 | position) pairs, radix-sorted by key, with a
-//       dense row table over the 36^5 dictionary.
-//   K7  probe: one CTA per target; every unmasked target 5-mer reads its index row (coalesced 4-byte values) and
-//       emits key = query<<14 | diagonal for every hit (diagonals > 16383 dropped, prefiltermu.cpp:254).
-//       The keys of a target are sorted (CUB segmented radix sort); a key that occurs twice is a two-hit diagonal.
-//   K8  extend: one thread per two-hit diagonal runs the reference's Kadane scan over the whole diagonal
-//       (int adds in diagonal order) and atomicMax-es the per-(target, query) best score.
+//       dense row table over the 36^5 dictionary.  The neighbourhood is enumerated work-efficiently (sorted letter lists +
+//       count tables: no candidate is tested and rejected).
+//   K7+K8 fused (pf_probe_extend*_kernel): one CTA per target; every unmasked target 5-mer reads its index row; a hit sets a bit
+//       per (query, diagonal) in shared-memory bitmaps (diagonals > 16383 dropped, prefiltermu.cpp:254), the second hit on a
+//       diagonal queues it, and the CTA walks the queued diagonals with the reference's Kadane scan (int adds in diagonal
+//       order), atomicMax-ing the per-(target, query) best score.  Targets whose bitmaps do not fit shared memory take the
+//       global-memory form: K7 probe -> key = query<<14 | diagonal per hit, CUB segmented sort, K8 extend from the runs.
 //
 // Bound: HBM/L2 latency of the index probe (random 8-byte row lookups + short coalesced rows); algorithmic bytes per
 // target k-mer: 8 (row start/end) + 4*rowsize, per hit 4 B written + sorted, per diagonal 2*len letter bytes.
