@@ -1062,15 +1062,13 @@ int pf_launch_probe_extend(const PfArgs &a, uint32_t ntl, int which, cudaStream_
 	auto staged = pf_probe_extend_staged_kernel<kBmSmallBits, kBmSmallQueue, 256>;
 	const size_t smem_s = bm_smem_bytes(kBmSmallBits, kBmSmallQueue), smem_l = bm_smem_bytes(kBmLargeBits, kBmLargeQueue);
 	const size_t smem_st = smem_s + bm_stage_bytes(a.nQ, a.sum_lenQ);
-	static bool configured = false;
-	if (!configured) {
-		if (cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess ||
-			cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess ||
-			cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int)(smem_s + bm_stage_bytes(kStageQMax, kStageQBytes))) != cudaSuccess)
-			return -1;
-		configured = true;
-	}
+	// per launch, not once per process: the attribute belongs to the current device, and `-gpus N` drives several devices from
+	// the threads of one process
+	if (cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess ||
+		cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess ||
+		cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			(int)(smem_s + bm_stage_bytes(kStageQMax, kStageQBytes))) != cudaSuccess)
+		return -1;
 	int n = 0;
 	if (which & 1) {
 		// small class: letters staged in shared memory when the query block allows it (and the caller gave a target counter);
@@ -1145,12 +1143,10 @@ int pf_launch_bag(const unsigned long long *val, const unsigned long long *seg_b
 	if (nQ == 0)
 		return 0;
 	const size_t smem = pf_bag_smem_bytes(B);
-	static size_t configured = 0;
-	if (smem > 48 * 1024 && smem > configured) {
-		if (cudaFuncSetAttribute(pf_bag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-			return -1;
-		configured = smem;
-	}
+	// per launch: the attribute belongs to the current device (several devices per process under `-gpus N`)
+	if (smem > 48 * 1024 &&
+		cudaFuncSetAttribute(pf_bag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+		return -1;
 	pf_bag_kernel<<<nQ, 32, smem, st>>>(val, seg_begin, seg_end, B, out_key, out_n);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
