@@ -23,6 +23,20 @@ def test_partition_balances_residues():
     assert partition_by_residues([5, 5], 4)[-1][1] == 2  # more ranks than chains: empty shards are allowed
 
 
+def test_cabi_partition_equals_python_helper(built_lib):
+    """rsk_partition_by_residues (what DBSearcher -gpus N and bench.py cut the DB with; exact 128-bit compare) gives the blocks of
+    shard.partition_by_residues, including more ranks than chains, a dominating chain, and residue totals beyond 2^32."""
+    from reseek_b200 import lib
+    rng = np.random.default_rng(3)
+    cases = [rng.integers(30, 1400, size=5000), np.array([5, 5]), np.array([7]), np.array([100000, 1, 1, 1, 1]),
+             np.full(9000, 600000, np.int64)]  # 5.4e9 residues
+    for lens in cases:
+        for world in (1, 2, 3, 8):
+            want = partition_by_residues(lens, world)
+            got = lib.partition_by_residues(lens, world)
+            assert got == want, (len(lens), world)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
