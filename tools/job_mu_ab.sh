@@ -1,3 +1,6 @@
+#!/bin/bash
+# A/B of the Mu filter (K3) between two builds: the tree's library and build/libreseek_b200_head.so, which has to be built
+# first from the commit to compare against (git archive <commit> reseek_b200/csrc include | tar -x -C /tmp/x; make OBJDIR=... OUT=...).
 for L in 150 300; do
   for v in head new head new; do
     lib=$PWD/reseek_b200/libreseek_b200.so; [ $v = head ] && lib=$PWD/build/libreseek_b200_head.so
